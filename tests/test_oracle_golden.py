@@ -1,0 +1,138 @@
+"""The numpy oracle against the reference's own outputs (tests/golden, made by
+oracle/make_golden.py from the live reference).  CPU only."""
+import numpy as np
+import pytest
+
+import flow_oracle as orc
+from conftest import golden_flow_names, load_golden, oracle_params_from_golden
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_forward_inverse_match_reference(name):
+    g = load_golden('flow_' + name)
+    p = oracle_params_from_golden(g, np.float64)
+    zs, ld = orc.flow_forward(p, g['x'].astype(np.float64))
+    # fp64 oracle vs fp32 reference: reference's own fp32 noise floor is 2e-7..3e-6
+    for l in range(int(g['L'])):
+        assert rel(zs[l], g['zs'][l]) < 5e-6
+    assert np.max(np.abs(ld - g['logdet'])) < 5e-6 * max(1.0, np.max(np.abs(g['logdet'])))
+    assert rel(zs[-1], g['z64']) < 1e-12
+    assert np.max(np.abs(ld - g['logdet64'])) < 1e-12 * max(1.0, np.max(np.abs(g['logdet64'])))
+    xs, ldi = orc.flow_inverse(p, g['zs'][-1].astype(np.float64))
+    for l in range(int(g['L'])):
+        assert rel(xs[l], g['xs'][l]) < 2e-5
+    assert np.max(np.abs(ldi - g['logdet_inv'])) < 5e-6 * max(1.0, np.max(np.abs(g['logdet_inv'])))
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_fp32_oracle_matches_reference_fp32(name):
+    g = load_golden('flow_' + name)
+    p = oracle_params_from_golden(g, np.float32)
+    zs, ld = orc.flow_forward(p, g['x'])
+    assert zs[-1].dtype == np.float32
+    assert rel(zs[-1], g['zs'][-1]) < 5e-6
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+@pytest.mark.parametrize('tag,eps,gamma', [('cal', 1e-7, 1.0), ('script', 0.0, 1.0), ('script_nodet', 0.0, 0.0)])
+def test_analytic_gradients_match_reference_autograd(name, tag, eps, gamma):
+    g = load_golden('flow_' + name)
+    p = oracle_params_from_golden(g, np.float64)
+    loss, ce, ldm, grads, gx = orc.train_step_grads(p, g['x'].astype(np.float64), g['y'], eps, gamma)
+    assert abs(loss - g['loss_' + tag]) < 2e-6 * max(1.0, abs(g['loss_' + tag]))
+    flat_g = orc.flatten(grads)
+    ref = g['grad_' + tag]
+    assert flat_g.shape == ref.shape
+    assert rel(flat_g, ref) < 2e-4
+    assert rel(gx, g['gx_' + tag]) < 2e-4
+    # dead first-layer columns / last-layer rows get exactly zero
+    assert np.all(flat_g[ref == 0] == 0) or np.max(np.abs(flat_g[ref == 0])) < 1e-12
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_adam_and_sgd_trajectories(name):
+    g = load_golden('flow_' + name)
+    like = oracle_params_from_golden(g, np.float64)
+    x, y = g['x'].astype(np.float64), g['y']
+    flat = g['flat'].astype(np.float64)
+    m = np.zeros_like(flat)
+    v = np.zeros_like(flat)
+    losses = []
+    for t in range(1, 4):
+        p = orc.unflatten(flat, like)
+        loss, _, _, grads, _ = orc.train_step_grads(p, x, y)
+        losses.append(loss)
+        flat, m, v = orc.adam_step(flat, orc.flatten(grads), m, v, t)
+    assert np.allclose(losses, g['adam3_losses'], rtol=1e-4, atol=1e-5)
+    # after 3 Adam steps every live weight moved by ~3e-3; compare the displacement
+    disp_ref = g['adam3_flat'] - g['flat']
+    disp = flat - g['flat']
+    assert np.max(np.abs(disp - disp_ref)) < 0.05 * np.max(np.abs(disp_ref))
+    dead = g['grad_cal'] == 0
+    assert np.all(disp[dead] == 0)
+
+    flat = g['flat'].astype(np.float64)
+    for _ in range(2):
+        p = orc.unflatten(flat, like)
+        _, _, _, grads, _ = orc.train_step_grads(p, x, y, eps=0.0, gamma=1.0)
+        flat = orc.sgd_step(flat, orc.flatten(grads), lr=1e-2, wd=1e-2)
+    assert rel(flat - g['flat'], g['sgd2_flat'] - g['flat']) < 1e-3
+
+
+def test_metrics_match_reference():
+    g = load_golden('metrics')
+    names = sorted(k[:-len('_probs')] for k in g if k.endswith('_probs'))
+    assert names
+    for n in names:
+        p, y = g[n + '_probs'], g[n + '_y']
+        assert abs(orc.expected_calibration_error(p, y, 15) - g[n + '_ece15']) < 1e-6
+        assert abs(orc.expected_calibration_error(p, y, 10) - g[n + '_ece10']) < 1e-6
+        oh = np.zeros(p.shape, dtype=np.int32)
+        oh[np.arange(len(y)), y] = 1
+        assert abs(orc.neg_log_likelihood(p, oh) - g[n + '_nll']) < 1e-6 * max(1, abs(g[n + '_nll']))
+        assert orc.accuracy(p, oh) == g[n + '_acc']
+
+
+@pytest.mark.parametrize('name', ['cal_nice_k3', 'cal_nvp_k10'])
+def test_calibrator_history_and_predict(name):
+    g = load_golden('calibrator_' + name)
+    K = int(g['K'])
+    x = orc.center(g['x'])
+    y = g['y']
+    like = orc.init_params(K, int(g['layers']), [int(h) for h in g['hidden']], bool(g['scale']), True)
+    flat = g['flat0'].astype(np.float64)
+    m = np.zeros_like(flat)
+    v = np.zeros_like(flat)
+    x32 = x.astype(np.float32).astype(np.float64)     # calibrators.py:248 casts to float
+    hist = []
+    for t in range(1, int(g['epochs']) + 1):
+        p = orc.unflatten(flat, like)
+        _, _, _, grads, _ = orc.train_step_grads(p, x32, y)
+        flat, m, v = orc.adam_step(flat, orc.flatten(grads), m, v, t)
+        p = orc.unflatten(flat, like)
+        zs, ld = orc.flow_forward(p, x32)
+        loss, ce, ldm, _, _ = orc.nll_head(zs[-1], ld, y)
+        hist.append((loss, ce, ldm))
+    hist = np.array(hist)
+    assert np.allclose(hist[:, 0], g['hist_loss'], rtol=2e-4, atol=1e-5)
+    assert np.allclose(hist[:, 1], g['hist_ce'], rtol=2e-4, atol=1e-5)
+    assert np.allclose(hist[:, 2], g['hist_log_det'], rtol=2e-3, atol=1e-5)
+    lp = orc.log_priors(orc.onehot_encode(y))
+    assert np.allclose(lp, g['log_priors'])
+    p_end = orc.unflatten(g['flat_end'].astype(np.float64), like)
+    xt = orc.center(g['x_test']).astype(np.float32).astype(np.float64)
+    zs, _ = orc.flow_forward(p_end, xt)
+    assert rel(zs[-1], g['pred_logits']) < 5e-6
+    pred = orc.calibrated_probs(zs[-1].astype(np.float32), lp)
+    assert np.max(np.abs(pred - g['pred'])) < 1e-5
+
+
+def test_pi_maps_even_odd():
+    pi = orc.pi_maps(5, 3)
+    assert list(pi[0]) == [0, 1, 2, 3, 4]
+    assert list(pi[1]) == [4, 3, 2, 1, 0]
+    assert list(pi[2]) == [0, 1, 2, 3, 4]
