@@ -1,0 +1,237 @@
+"""Host-side engine: owns the device buffers of one fused coupling stack and drives
+libcnf_b200 through the C ABI.  torch is used for device memory, streams and autograd
+plumbing only; every arithmetic step is a kernel from the library.
+
+Buffers (all on the flow's CUDA device):
+  flat        float32 [n_flat]     canonical parameter vector; the nn.Parameters of the stack
+                                   are views into it, so load_state_dict / .to() / optimisers
+                                   keep working (reference state_dict keys are unchanged)
+  gather      int32   [n_packed]   packed <- flat index map (host-planned, csrc/cnf_plan.cpp)
+  tables      int32   [n_tables]   physical-slot index tables (flips / permutations folded)
+  packed      float32 [n_packed]   kernel-side weights, refreshed by cnf_pack_weights
+  packed_tc   bf16 blob            tensor-core kernel weights (only when supported)
+  partials    float32 [rows, n_packed]  per-CTA gradient partials (allocated on first use)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, what='input'):
+    if not t.is_cuda:
+        raise RuntimeError('cnf_b200: %s must be a CUDA tensor (got %s). The flow kernels are '
+                           'sm_100a CUDA only; there is no CPU fallback.' % (what, t.device))
+
+
+class StackEngine:
+    """One homogeneous stack of coupling layers (same K, hidden sizes, scale/shift flags)."""
+
+    def __init__(self, K, hidden, scale, shift, perms, param_lists):
+        """param_lists: per layer, the list of nn.Parameters in canonical order
+        (s-net then t-net; per Linear weight then bias)."""
+        self.K, self.hidden, self.scale, self.shift = int(K), [int(h) for h in hidden], bool(scale), bool(shift)
+        self.L = len(param_lists)
+        self.perms = perms
+        self.params = [p for lay in param_lists for p in lay]
+        self.desc, self._keep = _lib.make_desc(self.K, self.L, self.hidden, scale, shift, _lib.PREC_FP32, perms)
+        self.desc_tc, self._keep_tc = _lib.make_desc(self.K, self.L, self.hidden, scale, shift, _lib.PREC_BF16_TC, perms)
+        info = _lib.PlanInfo()
+        _lib.call('cnf_plan_info_get', ctypes.byref(self.desc), ctypes.byref(info))
+        self.info = info
+        self.n_flat, self.n_packed = int(info.n_flat), int(info.n_packed)
+        self.n_rows = int(info.n_grad_rows)
+        self.tc_bytes = int(info.tc_bytes)
+        assert self.n_flat == sum(p.numel() for p in self.params), 'parameter list does not match the plan'
+        gather = np.empty(self.n_packed, dtype=np.int32)
+        tables = np.empty(int(info.n_tables), dtype=np.int32)
+        _lib.call('cnf_plan_build', ctypes.byref(self.desc), gather.ctypes.data_as(ctypes.c_void_p),
+                  tables.ctypes.data_as(ctypes.c_void_p))
+        self._gather_host, self._tables_host = gather, tables
+        self._gather_tc_host = None
+        if self.tc_bytes > 0:
+            g = np.empty(self.tc_bytes // 2, dtype=np.int32)
+            _lib.call('cnf_plan_build_tc', ctypes.byref(self.desc_tc), g.ctypes.data_as(ctypes.c_void_p))
+            self._gather_tc_host = g
+        self.device = None
+        self.flat = None
+        self.partials = None
+        self.flat_grad = None
+        self.adam_m = self.adam_v = None
+        self.adam_t = 0
+
+    # ------------------------------------------------------------------ buffers
+    def _bind(self, device):
+        """(Re)create device buffers on `device` and alias the parameters into `flat`."""
+        with torch.no_grad():
+            vals = [p.detach().to(device=device, dtype=torch.float32).reshape(-1) for p in self.params]
+            self.flat = torch.cat(vals) if vals else torch.zeros(0, device=device)
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.data = self.flat[off:off + n].view(p.shape)
+                off += n
+        self.device = device
+        self.gather = torch.from_numpy(self._gather_host).to(device)
+        self.tables = torch.from_numpy(self._tables_host).to(device)
+        self.packed = torch.empty(self.n_packed, dtype=torch.float32, device=device)
+        self.packed_tc = None
+        if self._gather_tc_host is not None:
+            self.gather_tc = torch.from_numpy(self._gather_tc_host).to(device)
+            self.packed_tc = torch.empty(self.tc_bytes // 2, dtype=torch.bfloat16, device=device)
+        self.partials = None
+        self.flat_grad = None
+        # optimiser state follows the parameters (the reference keeps it in self.optimizer)
+        if self.adam_m is not None:
+            self.adam_m = self.adam_m.to(device)
+            self.adam_v = self.adam_v.to(device)
+
+    def ensure(self, device):
+        """Make sure the parameters still alias `flat` on `device` (module.to(), a replaced
+        nn.Parameter or load_state_dict(assign=True) break the aliasing)."""
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('cnf_b200: the flow must live on a CUDA device (got %s); no CPU fallback' % device)
+        ok = self.flat is not None and self.device == device
+        if ok:
+            base, off = self.flat.data_ptr(), 0
+            for p in self.params:
+                if p.data_ptr() != base + 4 * off or p.device != device:
+                    ok = False
+                    break
+                off += p.numel()
+        if not ok:
+            self._bind(device)
+
+    def pack(self, tc=False):
+        st = _stream(self.device)
+        _lib.call('cnf_pack_weights', ctypes.byref(self.desc), _ptr(self.flat), _ptr(self.gather), _ptr(self.packed), st)
+        if tc and self.packed_tc is not None:
+            _lib.call('cnf_pack_weights_tc', ctypes.byref(self.desc_tc), _ptr(self.flat), _ptr(self.gather_tc),
+                      _ptr(self.packed_tc), st)
+
+    def _want_partials(self):
+        if self.partials is None:
+            self.partials = torch.empty(self.n_rows * self.n_packed, dtype=torch.float32, device=self.device)
+            self.flat_grad = torch.zeros(self.n_flat, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ kernels
+    def apply(self, x, inverse=False, want_all=False, precision='fp32', repack=True):
+        """Returns (out [N,K], logdet [N], all_or_None [L,N,K])."""
+        require_cuda(x)
+        x = x.detach().to(torch.float32).contiguous()
+        self.ensure(x.device)
+        N = x.shape[0]
+        use_tc = precision == 'bf16'
+        if use_tc and self.packed_tc is None:
+            raise NotImplementedError('cnf_b200: the bf16 tensor-core path does not cover this flow shape '
+                                      '(K=%d, hidden=%s); use precision="fp32"' % (self.K, self.hidden))
+        if repack:
+            self.pack(tc=use_tc)
+        out = torch.empty_like(x)
+        ld = torch.empty(N, dtype=torch.float32, device=x.device)
+        allz = torch.empty((self.L, N, self.K), dtype=torch.float32, device=x.device) if want_all else None
+        fn = 'cnf_flow_inverse' if inverse else 'cnf_flow_forward'
+        desc = self.desc_tc if use_tc else self.desc
+        packed = self.packed_tc if use_tc else self.packed
+        _lib.call(fn, ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x), _ptr(out), _ptr(ld),
+                  _ptr(allz), ctypes.c_int64(N), _stream(x.device))
+        return out, ld, allz
+
+    def backward(self, x, g_z, g_ld, need_gx=True):
+        """Generic autograd backward: returns (g_x or None, flat_grad)."""
+        self.ensure(x.device)
+        self._want_partials()
+        N = x.shape[0]
+        g_z = g_z.to(torch.float32).contiguous()
+        g_ld = g_ld.to(torch.float32).contiguous()
+        gx = torch.empty_like(x) if need_gx else None
+        st = _stream(x.device)
+        _lib.call('cnf_flow_backward', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
+                  _ptr(g_z), _ptr(g_ld), _ptr(gx), _ptr(self.partials), ctypes.c_int64(N), st)
+        flat_grad = torch.empty(self.n_flat, dtype=torch.float32, device=x.device)
+        _lib.call('cnf_grad_reduce', ctypes.byref(self.desc), _ptr(self.partials), _ptr(self.gather),
+                  _ptr(flat_grad), st)
+        return gx, flat_grad
+
+    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True):
+        """One fused forward+loss(+backward) pass over the local samples.  Accumulates the
+        loss sums into loss_acc (float64 [4], device) and, with_grad, leaves
+        d(sum loss)/n_total in self.flat_grad."""
+        N = x.shape[0]
+        n_total = N if n_total is None else n_total
+        st = _stream(x.device)
+        if with_grad:
+            self._want_partials()
+        _lib.call('cnf_nll_train_step', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
+                  _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
+                  ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials) if with_grad else None,
+                  _ptr(loss_acc), st)
+        if with_grad:
+            _lib.call('cnf_grad_reduce', ctypes.byref(self.desc), _ptr(self.partials), _ptr(self.gather),
+                      _ptr(self.flat_grad), st)
+
+    def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+            self.adam_t = 0
+        self.adam_t += 1
+        _lib.call('cnf_adam_step', _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                  ctypes.c_int64(self.n_flat), ctypes.c_int64(self.adam_t), ctypes.c_float(lr),
+                  ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
+                  ctypes.c_float(weight_decay), _stream(self.device))
+
+    def sgd(self, lr, weight_decay=0.0):
+        _lib.call('cnf_sgd_step', _ptr(self.flat), _ptr(self.flat_grad), ctypes.c_int64(self.n_flat),
+                  ctypes.c_float(lr), ctypes.c_float(weight_decay), _stream(self.device))
+
+
+class _StackFunction(torch.autograd.Function):
+    """Autograd node for one fused stack: saves only x; the backward kernel recomputes."""
+
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        out, ld, _ = engine.apply(x)
+        ctx.engine = engine
+        ctx.save_for_backward(x.detach().to(torch.float32).contiguous())
+        ctx.x_needs_grad = x.requires_grad
+        return out, ld
+
+    @staticmethod
+    def backward(ctx, g_z, g_ld):
+        engine = ctx.engine
+        (x,) = ctx.saved_tensors
+        if g_z is None:
+            g_z = torch.zeros_like(x)
+        if g_ld is None:
+            g_ld = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
+        engine.ensure(x.device)
+        engine.pack()
+        gx, flat_grad = engine.backward(x, g_z, g_ld, need_gx=ctx.x_needs_grad)
+        grads, off = [], 0
+        for p in engine.params:
+            n = p.numel()
+            grads.append(flat_grad[off:off + n].view(p.shape))
+            off += n
+        return (None, gx) + tuple(grads)
+
+
+def stack_forward(engine, x):
+    """Differentiable fused forward of one stack."""
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in engine.params))
+    if need_grad:
+        engine.ensure(x.device)
+        return _StackFunction.apply(engine, x, *engine.params)
+    out, ld, _ = engine.apply(x)
+    return out, ld

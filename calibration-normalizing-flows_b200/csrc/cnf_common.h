@@ -1,0 +1,43 @@
+// Shared host/device definitions for libcnf_b200 (not part of the public ABI).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cnf.h"
+
+#define CNF_CH 16          // hidden-unit chunk held in registers by the fp32 kernels
+#define CNF_GRAD_ROWS 296  // 2 x 148 SMs: rows of the gradient partial buffer
+#define CNF_GRAD_BUDGET_FLOATS (64ll << 20)
+
+// Everything the kernels need to know about the model, derived from cnf_flow_desc.
+// Passed by value as a kernel parameter.
+struct CnfDims {
+  int K, L, m, d0, d1, d0p;
+  int nets;     // bit0: s-net, bit1: t-net
+  int n_nets;   // popcount(nets)
+  int H[CNF_MAX_HIDDEN];   // true hidden widths
+  int Hp[CNF_MAX_HIDDEN];  // padded to CNF_CH
+  int Hmax;                // max padded width (0 if m == 0)
+  int w_off[CNF_MAX_HIDDEN + 1];  // float offsets inside one net block
+  int b_off[CNF_MAX_HIDDEN + 1];
+  int net_stride, layer_stride, n_packed;
+  int tab_pi, tab_cond, tab_trans, n_tables;  // offsets inside the int32 tables
+  int n_flat;
+  int grad_rows;
+};
+
+void cnf_set_error(const char* fmt, ...);
+int cnf_make_dims(const cnf_flow_desc* desc, CnfDims* out);
+long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d);
+
+static inline int cnf_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+#define CNF_CHECK_CUDA(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      cnf_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CNF_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)

@@ -1,0 +1,725 @@
+// fp32 CUDA-core kernels of the coupling-flow stack (sm_100a): the 1e-5 parity path for
+// every shape, and the only path for shapes the tensor-core kernel does not cover.
+//
+// One fused kernel per flow stack.  A CTA owns a tile of TS = NT*SPT samples; one thread
+// owns SPT samples for the whole stack (all L coupling layers), so there is no barrier
+// between layers.  The tile lives in shared memory feature-major, act[slot][sample]
+// (row stride TSP = TS+4: conflict-free for per-sample scalar access and for the 128-bit
+// row reads of the weight-gradient pass).  Packed weights of all layers are staged once
+// per CTA in shared memory when they fit (read with broadcast LDS.128), otherwise read
+// through L1 with __ldg.  Flips/permutations are index maps (tables), data never moves.
+//
+// Reference arithmetic restated here:
+//   coupling forward  z = x_b + (1-m)(x*exp(s)+t), ld = sum (1-m)s     flows/flows.py:101-112
+//   coupling inverse  x = x_b + (1-m)(z-t)*exp(-s), ld = -sum (1-m)s   flows/flows.py:114-126
+//   conditioner MLP   Linear-ReLU-...-Linear                            flows/utils.py:26-31
+//   NLL head          -mean(log(softmax(z)[y]+eps) + gamma*ld)          calibrators.py:288-291
+//                     (eps=0: CrossEntropyLoss)                         run_experiment3D.py:107
+#include <cuda_runtime.h>
+
+#include "cnf_common.h"
+
+namespace {
+
+constexpr int CH = CNF_CH;
+
+template <bool WS>
+__device__ __forceinline__ float4 ldw4(const float* p) {
+  if (WS) return *reinterpret_cast<const float4*>(p);
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <bool WS>
+__device__ __forceinline__ float ldw1(const float* p) {
+  if (WS) return *p;
+  return __ldg(p);
+}
+
+// Per-CTA shared-memory carve-up (in floats from the dynamic smem base).
+struct Smem {
+  int w;       // packed weights (WS only)
+  int tab;     // int tables
+  int act;     // [K][TSP]
+  int outs;    // [2][d0][TSP]   s and t outputs
+  int hid;     // [hid_rows][TSP]
+  // backward only
+  int gact;    // [K][TSP]
+  int tape;    // [L][d0][TSP]
+  int gout;    // [2][d0][TSP]
+  int gbuf;    // [2][Hmax][TSP] (m >= 2)
+  int total;   // floats
+};
+
+__host__ __device__ inline int hid_rows(const CnfDims& d, bool store_last) {
+  int r = 0;
+  for (int j = 0; j < d.m; ++j)
+    if (j < d.m - 1 || store_last) r += d.Hp[j];
+  return r;
+}
+
+__host__ __device__ inline Smem make_smem(const CnfDims& d, int TSP, bool ws, bool backward) {
+  Smem s;
+  int off = 0;
+  s.w = off; off += ws ? d.n_packed : 0;
+  s.tab = off; off += (d.n_tables + 3) / 4 * 4;
+  s.act = off; off += d.K * TSP;
+  s.outs = off; off += 2 * d.d0 * TSP;
+  s.hid = off; off += hid_rows(d, backward) * TSP;
+  s.gact = off; off += backward ? d.K * TSP : 0;
+  s.tape = off; off += backward ? d.L * d.d0 * TSP : 0;
+  s.gout = off; off += backward ? 2 * d.d0 * TSP : 0;
+  s.gbuf = off; off += (backward && d.m >= 2) ? 2 * d.Hmax * TSP : 0;
+  s.total = off;
+  return s;
+}
+
+// h[k][r] = b[r0+r] + sum_i W[i*ldw + r0 + r] * src[row(i)][sample k]
+template <int SPT, bool WS>
+__device__ __forceinline__ void chunk_from_inputs(float (&h)[SPT][CH], const float* W, int ldw, const float* b,
+                                                  int r0, int n_in, const float* src, const int* idx, int TSP,
+                                                  int tid, int NT) {
+  if (b != nullptr) {
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      float4 bv = ldw4<WS>(b + r0 + 4 * r4);
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        h[k][4 * r4 + 0] = bv.x; h[k][4 * r4 + 1] = bv.y; h[k][4 * r4 + 2] = bv.z; h[k][4 * r4 + 3] = bv.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int r = 0; r < CH; ++r) h[k][r] = 0.f;
+  }
+  for (int i = 0; i < n_in; ++i) {
+    const int row = idx ? idx[i] : i;
+    float xin[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) xin[k] = src[row * TSP + tid + k * NT];
+    const float* wrow = W + (size_t)i * ldw + r0;
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      float4 wv = ldw4<WS>(wrow + 4 * r4);
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        h[k][4 * r4 + 0] = fmaf(wv.x, xin[k], h[k][4 * r4 + 0]);
+        h[k][4 * r4 + 1] = fmaf(wv.y, xin[k], h[k][4 * r4 + 1]);
+        h[k][4 * r4 + 2] = fmaf(wv.z, xin[k], h[k][4 * r4 + 2]);
+        h[k][4 * r4 + 3] = fmaf(wv.w, xin[k], h[k][4 * r4 + 3]);
+      }
+    }
+  }
+}
+
+// for each of n_out rows o: acc = sum_r W[o*ldw + r0 + r] * h[k][r];
+//   dst[row(o)][sample k] = (init ? (b ? b[o] : 0) : dst) + acc
+template <int SPT, bool WS>
+__device__ __forceinline__ void chunk_to_outputs(const float (&h)[SPT][CH], const float* W, int ldw, const float* b,
+                                                 int r0, int n_out, float* dst, const int* idx, bool init,
+                                                 bool accumulate_always, int TSP, int tid, int NT) {
+  for (int o = 0; o < n_out; ++o) {
+    const float* wrow = W + (size_t)o * ldw + r0;
+    float acc[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      float4 wv = ldw4<WS>(wrow + 4 * r4);
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        acc[k] = fmaf(wv.x, h[k][4 * r4 + 0], acc[k]);
+        acc[k] = fmaf(wv.y, h[k][4 * r4 + 1], acc[k]);
+        acc[k] = fmaf(wv.z, h[k][4 * r4 + 2], acc[k]);
+        acc[k] = fmaf(wv.w, h[k][4 * r4 + 3], acc[k]);
+      }
+    }
+    const int row = idx ? idx[o] : o;
+    float base0 = 0.f;
+    if (init && !accumulate_always && b != nullptr) base0 = ldw1<WS>(b + o);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      float* p = dst + row * TSP + tid + k * NT;
+      float base = (init && !accumulate_always) ? base0 : *p;
+      *p = base + acc[k];
+    }
+  }
+}
+
+// Conditioner MLP for this thread's SPT samples.  Inputs: act rows cond[0..d1).
+// Outputs (if want_out): out[q][sample], q < d0.  Hidden post-ReLU activations of layers
+// 0..m-2 (and m-1 when store_last) are written to hid (layer j at row offset sum Hp[<j]).
+template <int SPT, bool WS>
+__device__ __forceinline__ void net_forward(const CnfDims& d, const float* Wn, const float* act, const int* cond,
+                                            float* out, float* hid, bool store_last, bool want_out, int TSP,
+                                            int tid, int NT) {
+  float h[SPT][CH];
+  if (d.m == 0) {
+    if (!want_out) return;
+    for (int r0 = 0; r0 < d.d0p; r0 += CH) {
+      chunk_from_inputs<SPT, WS>(h, Wn + d.w_off[0], d.d0p, Wn + d.b_off[0], r0, d.d1, act, cond, TSP, tid, NT);
+#pragma unroll
+      for (int r = 0; r < CH; ++r)
+        if (r0 + r < d.d0) {
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) out[(r0 + r) * TSP + tid + k * NT] = h[k][r];
+        }
+    }
+    return;
+  }
+  int hoff = 0, hoff_prev = 0;
+  for (int j = 0; j < d.m; ++j) {
+    const bool last = (j == d.m - 1);
+    const int n_in = (j == 0) ? d.d1 : d.Hp[j - 1];
+    const float* src = (j == 0) ? act : hid + hoff_prev * TSP;
+    const int* idx = (j == 0) ? cond : nullptr;
+    for (int r0 = 0; r0 < d.Hp[j]; r0 += CH) {
+      chunk_from_inputs<SPT, WS>(h, Wn + d.w_off[j], d.Hp[j], Wn + d.b_off[j], r0, n_in, src, idx, TSP, tid, NT);
+#pragma unroll
+      for (int k = 0; k < SPT; ++k)
+#pragma unroll
+        for (int r = 0; r < CH; ++r) h[k][r] = fmaxf(h[k][r], 0.f);
+      if (!last || store_last) {
+#pragma unroll
+        for (int r = 0; r < CH; ++r)
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) hid[(hoff + r0 + r) * TSP + tid + k * NT] = h[k][r];
+      }
+      if (last && want_out)
+        chunk_to_outputs<SPT, WS>(h, Wn + d.w_off[d.m], d.Hp[j], Wn + d.b_off[d.m], r0, d.d0, out, nullptr,
+                                  r0 == 0, false, TSP, tid, NT);
+    }
+    hoff_prev = hoff;
+    hoff += d.Hp[j];
+  }
+}
+
+// cooperative: copy n floats global -> shared
+__device__ __forceinline__ void coop_copy(float* dst, const float* src, int n, int tid, int NT) {
+  const int n4 = n / 4;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = tid; i < n4; i += NT) d4[i] = __ldg(s4 + i);
+  for (int i = n4 * 4 + tid; i < n; i += NT) dst[i] = __ldg(src + i);
+}
+
+// cooperative tile load: global [TS][K] (row-major) -> act[slot(f)][sample]
+__device__ __forceinline__ void load_tile(float* act, const float* g, int64_t base, int64_t N, int K, int TS,
+                                          int TSP, const int* slot_of, int tid, int NT) {
+  const int total = TS * K;
+  const float* gp = g + base * K;
+  const int64_t avail = (N - base) * (int64_t)K;
+  for (int e = tid; e < total; e += NT) {
+    const int s = e / K, f = e - s * K;
+    const float v = (e < avail) ? __ldg(gp + e) : 0.f;
+    act[(slot_of ? slot_of[f] : f) * TSP + s] = v;
+  }
+}
+__device__ __forceinline__ void store_tile(const float* act, float* g, int64_t base, int64_t N, int K, int TS,
+                                           int TSP, const int* slot_of, int tid, int NT) {
+  const int total = TS * K;
+  float* gp = g + base * K;
+  const int64_t avail = (N - base) * (int64_t)K;
+  for (int e = tid; e < total; e += NT) {
+    const int s = e / K, f = e - s * K;
+    if (e < avail) gp[e] = act[(slot_of ? slot_of[f] : f) * TSP + s];
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// forward / inverse
+// --------------------------------------------------------------------------------------
+template <int SPT, bool WS>
+__global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                                  const float* __restrict__ xin, float* __restrict__ zout,
+                                  float* __restrict__ logdet, float* __restrict__ zs, int64_t N, int inverse) {
+  extern __shared__ __align__(16) float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TS = NT * SPT, TSP = TS + 4;
+  const Smem sm = make_smem(d, TSP, WS, false);
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* outs_s = smem + sm.outs;
+  float* outs_t = outs_s + d.d0 * TSP;
+  float* hid = smem + sm.hid;
+  const float* W = WS ? smem + sm.w : packed;
+  if (WS) coop_copy(smem + sm.w, packed, d.n_packed, tid, NT);
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  __syncthreads();
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    load_tile(act, xin, base, N, d.K, TS, TSP, inverse ? pi_last : nullptr, tid, NT);
+    __syncthreads();
+    float ld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) ld[k] = 0.f;
+    for (int li = 0; li < d.L; ++li) {
+      const int l = inverse ? d.L - 1 - li : li;
+      const int* cond = tab + d.tab_cond + l * d.d1;
+      const int* trans = tab + d.tab_trans + l * d.d0;
+      const float* Wl = W + (size_t)l * d.layer_stride;
+      int slot = 0;
+      if (d.nets & 1) { net_forward<SPT, WS>(d, Wl, act, cond, outs_s, hid, false, true, TSP, tid, NT); ++slot; }
+      if (d.nets & 2)
+        net_forward<SPT, WS>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, hid, false, true, TSP, tid, NT);
+      for (int q = 0; q < d.d0; ++q) {
+        const int p = trans[q];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const float xv = act[p * TSP + s];
+          const float sv = (d.nets & 1) ? outs_s[q * TSP + s] : 0.f;
+          const float tv = (d.nets & 2) ? outs_t[q * TSP + s] : 0.f;
+          float yv;
+          if (!inverse) { yv = xv * expf(sv) + tv; ld[k] += sv; }
+          else          { yv = (xv - tv) * expf(-sv); ld[k] -= sv; }
+          act[p * TSP + s] = yv;
+        }
+      }
+      if (zs != nullptr) {
+        // forward: zs[l] is the output of layer l in its logical order pi_{l+1};
+        // inverse: xs[li] is the input of layer l in logical order pi_l.
+        const int* pi = tab + d.tab_pi + (inverse ? l : l + 1) * d.K;
+        float* dst = zs + (size_t)li * N * d.K;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const int64_t n = base + s;
+          if (n < N)
+            for (int j = 0; j < d.K; ++j) dst[n * d.K + j] = act[pi[j] * TSP + s];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int64_t n = base + tid + k * NT;
+      if (n < N) logdet[n] = ld[k];
+    }
+    __syncthreads();
+    store_tile(act, zout, base, N, d.K, TS, TSP, inverse ? nullptr : pi_last, tid, NT);
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// training: forward + loss head + backward, one pass
+// --------------------------------------------------------------------------------------
+// G[a*ldg + b] += sum_s A[rowA(a)][s] * B[b][s]   (a < na, b < nb), atomics on global.
+__device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, const int* idxA, int na,
+                                            const float* B, int nb, float* Gbias_b, int TS, int TSP, int tid,
+                                            int NT) {
+  constexpr int AB = 8;
+  const int nablk = (na + AB - 1) / AB;
+  const int items = nb * nablk;
+  for (int it = tid; it < items; it += NT) {
+    const int b = it % nb, ablk = it / nb;
+    const int a0 = ablk * AB;
+    const int an = min(AB, na - a0);
+    float acc[AB];
+#pragma unroll
+    for (int a = 0; a < AB; ++a) acc[a] = 0.f;
+    float bsum = 0.f;
+    int rowA[AB];
+#pragma unroll
+    for (int a = 0; a < AB; ++a) {
+      const int aa = a0 + min(a, an - 1);
+      rowA[a] = (idxA ? idxA[aa] : aa) * TSP;
+    }
+    const float* Brow = B + b * TSP;
+    for (int s = 0; s < TS; s += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(Brow + s);
+      bsum += (bv.x + bv.y) + (bv.z + bv.w);
+#pragma unroll
+      for (int a = 0; a < AB; ++a) {
+        const float4 av = *reinterpret_cast<const float4*>(A + rowA[a] + s);
+        acc[a] = fmaf(av.x, bv.x, acc[a]);
+        acc[a] = fmaf(av.y, bv.y, acc[a]);
+        acc[a] = fmaf(av.z, bv.z, acc[a]);
+        acc[a] = fmaf(av.w, bv.w, acc[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < AB; ++a)
+      if (a < an) atomicAdd(G + (size_t)(a0 + a) * ldg + b, acc[a]);
+    if (Gbias_b != nullptr && ablk == 0) atomicAdd(Gbias_b + b, bsum);
+  }
+}
+
+// Gb[a] += sum_s A[a][s]
+__device__ __forceinline__ void wgrad_rowsum(float* Gb, const float* A, int na, int TS, int TSP, int tid, int NT) {
+  for (int a = tid; a < na; a += NT) {
+    float acc = 0.f;
+    const float* row = A + a * TSP;
+    for (int s = 0; s < TS; s += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + s);
+      acc += (v.x + v.y) + (v.z + v.w);
+    }
+    atomicAdd(Gb + a, acc);
+  }
+}
+
+// Backward of one conditioner net for the tile.  On entry: hid holds every hidden layer's
+// post-ReLU activations (from net_forward with store_last), gout[q][s] the gradient wrt the
+// net's d0 outputs.  Adds input gradients to gact rows cond[], weight gradients to Gn
+// (global, this net's block of the CTA's partial row).  Contains __syncthreads().
+template <int SPT, bool WS>
+__device__ __forceinline__ void net_backward(const CnfDims& d, const float* Wn, float* Gn, const float* act,
+                                             const int* cond, const float* gout, float* hid, float* gbuf,
+                                             float* gact, int TS, int TSP, int tid, int NT) {
+  float g[SPT][CH];
+  if (d.m == 0) {
+    // thread: gact[cond[c]] += sum_q W[c][q] gout[q]
+    for (int r0 = 0; r0 < d.d0p; r0 += CH) {
+#pragma unroll
+      for (int r = 0; r < CH; ++r)
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+          g[k][r] = (r0 + r < d.d0) ? gout[(r0 + r) * TSP + tid + k * NT] : 0.f;
+      chunk_to_outputs<SPT, WS>(g, Wn + d.w_off[0], d.d0p, nullptr, r0, d.d1, gact, cond, false, true, TSP, tid, NT);
+    }
+    __syncthreads();
+    wgrad_outer(Gn + d.w_off[0], d.d0p, act, cond, d.d1, gout, d.d0, Gn + d.b_off[0], TS, TSP, tid, NT);
+    __syncthreads();
+    return;
+  }
+  int hoff[CNF_MAX_HIDDEN];
+  {
+    int o = 0;
+    for (int j = 0; j < d.m; ++j) { hoff[j] = o; o += d.Hp[j]; }
+  }
+  // last linear: dW[q][r] = sum_s gout[q][s] hid_{m-1}[r][s]; db[q] = sum_s gout[q][s]
+  __syncthreads();
+  wgrad_outer(Gn + d.w_off[d.m], d.Hp[d.m - 1], gout, nullptr, d.d0, hid + hoff[d.m - 1] * TSP, d.Hp[d.m - 1],
+              nullptr, TS, TSP, tid, NT);
+  wgrad_rowsum(Gn + d.b_off[d.m], gout, d.d0, TS, TSP, tid, NT);
+  __syncthreads();
+  for (int j = d.m - 1; j >= 0; --j) {
+    float* hj = hid + hoff[j] * TSP;
+    float* gin_cur = gbuf + ((j & 1) ? d.Hmax * TSP : 0);         // gradient wrt hid_j (pre-mask), j < m-1
+    float* gin_prev = gbuf + (((j - 1) & 1) ? d.Hmax * TSP : 0);  // accumulates gradient wrt hid_{j-1}
+    for (int r0 = 0; r0 < d.Hp[j]; r0 += CH) {
+      if (j == d.m - 1) {
+        chunk_from_inputs<SPT, WS>(g, Wn + d.w_off[d.m], d.Hp[j], nullptr, r0, d.d0, gout, nullptr, TSP, tid, NT);
+      } else {
+#pragma unroll
+        for (int r = 0; r < CH; ++r)
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) g[k][r] = gin_cur[(r0 + r) * TSP + tid + k * NT];
+      }
+      // ReLU mask, then overwrite the activation in place with the pre-activation gradient
+#pragma unroll
+      for (int r = 0; r < CH; ++r)
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          float* hp = hj + (r0 + r) * TSP + tid + k * NT;
+          g[k][r] = (*hp > 0.f) ? g[k][r] : 0.f;
+          *hp = g[k][r];
+        }
+      if (j == 0)
+        chunk_to_outputs<SPT, WS>(g, Wn + d.w_off[0], d.Hp[0], nullptr, r0, d.d1, gact, cond, false, true, TSP, tid, NT);
+      else
+        chunk_to_outputs<SPT, WS>(g, Wn + d.w_off[j], d.Hp[j], nullptr, r0, d.Hp[j - 1], gin_prev, nullptr, r0 == 0,
+                                  false, TSP, tid, NT);
+    }
+    __syncthreads();
+    // dW_j[in][out] = sum_s in_j[in][s] gpre_j[out][s]; db_j[out] = sum_s gpre_j[out][s]
+    if (j == 0)
+      wgrad_outer(Gn + d.w_off[0], d.Hp[0], act, cond, d.d1, hj, d.Hp[0], Gn + d.b_off[0], TS, TSP, tid, NT);
+    else
+      wgrad_outer(Gn + d.w_off[j], d.Hp[j], hid + hoff[j - 1] * TSP, nullptr, d.Hp[j - 1], hj, d.Hp[j],
+                  Gn + d.b_off[j], TS, TSP, tid, NT);
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int NT) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (tid == 0)
+    for (int w = 0; w < (NT + 31) / 32; ++w) t += red[w];
+  return t;
+}
+
+template <int SPT, bool WS>
+__global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                                  const float* __restrict__ xin, const int64_t* __restrict__ labels,
+                                  const float* __restrict__ gz_ext, const float* __restrict__ gld_ext,
+                                  float* __restrict__ gx_out, float* __restrict__ partials,
+                                  double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n,
+                                  int head) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[32];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TS = NT * SPT, TSP = TS + 4;
+  const bool do_bwd = (partials != nullptr);
+  const Smem sm = make_smem(d, TSP, WS, true);
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* outs_s = smem + sm.outs;
+  float* outs_t = outs_s + d.d0 * TSP;
+  float* hid = smem + sm.hid;
+  float* gact = smem + sm.gact;
+  float* tape = smem + sm.tape;
+  float* gout_s = smem + sm.gout;
+  float* gout_t = gout_s + d.d0 * TSP;
+  float* gbuf = smem + sm.gbuf;
+  const float* W = WS ? smem + sm.w : packed;
+  float* Grow = do_bwd ? partials + (size_t)(blockIdx.x % d.grad_rows) * d.n_packed : nullptr;
+  if (WS) coop_copy(smem + sm.w, packed, d.n_packed, tid, NT);
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  __syncthreads();
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    load_tile(act, xin, base, N, d.K, TS, TSP, nullptr, tid, NT);
+    if (head == CNF_HEAD_EXTERNAL) load_tile(gact, gz_ext, base, N, d.K, TS, TSP, pi_last, tid, NT);
+    __syncthreads();
+    float ld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) ld[k] = 0.f;
+    // ---- forward, recording the pre-layer value of every transformed slot -----------
+    for (int l = 0; l < d.L; ++l) {
+      const int* cond = tab + d.tab_cond + l * d.d1;
+      const int* trans = tab + d.tab_trans + l * d.d0;
+      const float* Wl = W + (size_t)l * d.layer_stride;
+      int slot = 0;
+      if (d.nets & 1) { net_forward<SPT, WS>(d, Wl, act, cond, outs_s, hid, false, true, TSP, tid, NT); ++slot; }
+      if (d.nets & 2)
+        net_forward<SPT, WS>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, hid, false, true, TSP, tid, NT);
+      for (int q = 0; q < d.d0; ++q) {
+        const int p = trans[q];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const float xv = act[p * TSP + s];
+          const float sv = (d.nets & 1) ? outs_s[q * TSP + s] : 0.f;
+          const float tv = (d.nets & 2) ? outs_t[q * TSP + s] : 0.f;
+          tape[(l * d.d0 + q) * TSP + s] = xv;
+          act[p * TSP + s] = xv * expf(sv) + tv;
+          ld[k] += sv;
+        }
+      }
+    }
+    // ---- loss head ------------------------------------------------------------------
+    float gld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int s = tid + k * NT;
+      const int64_t n = base + s;
+      const bool valid = n < N;
+      gld[k] = 0.f;
+      if (head == CNF_HEAD_NLL) {
+        float mx = -INFINITY;
+        for (int j = 0; j < d.K; ++j) mx = fmaxf(mx, act[pi_last[j] * TSP + s]);
+        float se = 0.f;
+        for (int j = 0; j < d.K; ++j) se += expf(act[pi_last[j] * TSP + s] - mx);
+        int yy = valid ? (int)labels[n] : 0;
+        yy = min(max(yy, 0), d.K - 1);  // out-of-range labels are clamped, never read out of bounds
+        const float zy = act[pi_last[yy] * TSP + s];
+        const float inv_se = 1.f / se;
+        const float py = expf(zy - mx) * inv_se;
+        float ce, coef;
+        if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+        else            { ce = logf(py + eps); coef = py / (py + eps); }
+        if (valid) {
+          const float tot = ce + gamma * ld[k];
+          a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld[k];
+          if (!isfinite(tot)) a_bad += 1.0;
+        }
+        if (do_bwd) {
+          const float sc = valid ? -inv_n * coef : 0.f;
+          for (int j = 0; j < d.K; ++j) {
+            const int p = pi_last[j];
+            const float pj = expf(act[p * TSP + s] - mx) * inv_se;
+            gact[p * TSP + s] = sc * ((j == yy ? 1.f : 0.f) - pj);
+          }
+          gld[k] = valid ? -gamma * inv_n : 0.f;
+        }
+      } else {
+        gld[k] = valid ? gld_ext[n] : 0.f;
+      }
+    }
+    // ---- backward -------------------------------------------------------------------
+    if (do_bwd) {
+      for (int l = d.L - 1; l >= 0; --l) {
+        const int* cond = tab + d.tab_cond + l * d.d1;
+        const int* trans = tab + d.tab_trans + l * d.d0;
+        const float* Wl = W + (size_t)l * d.layer_stride;
+        float* Gl = Grow + (size_t)l * d.layer_stride;
+        int slot = 0;
+        if (d.nets & 1) {
+          net_forward<SPT, WS>(d, Wl, act, cond, outs_s, hid, true, true, TSP, tid, NT);
+          for (int q = 0; q < d.d0; ++q) {
+            const int p = trans[q];
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) {
+              const int s = tid + k * NT;
+              const float gy = gact[p * TSP + s];
+              const float es = expf(outs_s[q * TSP + s]);
+              const float xv = tape[(l * d.d0 + q) * TSP + s];
+              gout_s[q * TSP + s] = gy * xv * es + gld[k];
+              gout_t[q * TSP + s] = gy;
+              gact[p * TSP + s] = gy * es;
+            }
+          }
+          net_backward<SPT, WS>(d, Wl, Gl, act, cond, gout_s, hid, gbuf, gact, TS, TSP, tid, NT);
+          ++slot;
+        } else if (d.nets & 2) {
+          for (int q = 0; q < d.d0; ++q) {
+            const int p = trans[q];
+#pragma unroll
+            for (int k = 0; k < SPT; ++k) gout_t[q * TSP + tid + k * NT] = gact[p * TSP + tid + k * NT];
+          }
+        }
+        if (d.nets & 2) {
+          net_forward<SPT, WS>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, hid, true, false, TSP, tid, NT);
+          net_backward<SPT, WS>(d, Wl + (size_t)slot * d.net_stride, Gl + (size_t)slot * d.net_stride, act, cond,
+                                gout_t, hid, gbuf, gact, TS, TSP, tid, NT);
+        }
+        // step the tile state back to the input of layer l
+        for (int q = 0; q < d.d0; ++q) {
+          const int p = trans[q];
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) act[p * TSP + tid + k * NT] = tape[(l * d.d0 + q) * TSP + tid + k * NT];
+        }
+      }
+      if (gx_out != nullptr) {
+        __syncthreads();
+        store_tile(gact, gx_out, base, N, d.K, TS, TSP, nullptr, tid, NT);
+      }
+    }
+    __syncthreads();
+  }
+  if (loss_acc != nullptr && head == CNF_HEAD_NLL) {
+    double t0 = block_sum(a_loss, red, tid, NT);
+    double t1 = block_sum(a_ce, red, tid, NT);
+    double t2 = block_sum(a_ld, red, tid, NT);
+    double t3 = block_sum(a_bad, red, tid, NT);
+    if (tid == 0) {
+      atomicAdd(loss_acc + 0, t0);
+      atomicAdd(loss_acc + 1, t1);
+      atomicAdd(loss_acc + 2, t2);
+      atomicAdd(loss_acc + 3, t3);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// launch plumbing
+// --------------------------------------------------------------------------------------
+struct LaunchCfg { int spt, nt; bool ws; size_t smem; };
+
+int g_max_smem = -1, g_num_sms = -1;
+
+int device_limits() {
+  if (g_max_smem >= 0) return CNF_OK;
+  int dev = 0;
+  CNF_CHECK_CUDA(cudaGetDevice(&dev));
+  int v = 0, s = 0;
+  CNF_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
+  g_max_smem = v; g_num_sms = s;
+  return CNF_OK;
+}
+
+// Pick the widest tile whose shared-memory plan fits, preferring weights in shared memory.
+int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out) {
+  const int budget = g_max_smem - (backward ? 1024 : 256);
+  const int spts[2] = {2, 1};
+  for (int ws = 1; ws >= 0; --ws)
+    for (int nt = 128; nt >= 32; nt >>= 1)
+      for (int si = 0; si < 2; ++si) {
+        const int spt = spts[si];
+        if (nt < 128 && spt > 1) continue;
+        const int TSP = nt * spt + 4;
+        const Smem sm = make_smem(d, TSP, ws != 0, backward);
+        const size_t bytes = (size_t)sm.total * 4;
+        if ((long long)bytes <= budget) {
+          out->spt = spt; out->nt = nt; out->ws = ws != 0; out->smem = bytes;
+          return CNF_OK;
+        }
+      }
+  cnf_set_error("model does not fit shared memory (K=%d, Hmax=%d, L=%d)", d.K, d.Hmax, d.L);
+  return CNF_E_SMEM;
+}
+
+template <typename Kern>
+int set_smem(Kern k, size_t bytes) {
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CNF_OK;
+}
+
+}  // namespace
+
+int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
+                   float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (N == 0) return CNF_OK;
+  if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  if ((rc = device_limits())) return rc;
+  LaunchCfg c;
+  if ((rc = choose_cfg(d, false, &c))) return rc;
+  const int64_t ntiles = (N + c.nt * c.spt - 1) / (c.nt * c.spt);
+  int ctas_per_sm = (int)(g_max_smem / (c.smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  const int grid = (int)(ntiles < (int64_t)g_num_sms * ctas_per_sm ? ntiles : (int64_t)g_num_sms * ctas_per_sm);
+#define LAUNCH_APPLY(SPT, WS)                                                                         \
+  do {                                                                                                \
+    if ((rc = set_smem(flow_apply_kernel<SPT, WS>, c.smem))) return rc;                               \
+    flow_apply_kernel<SPT, WS><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, z, logdet, zs, N, inverse); \
+  } while (0)
+  if (c.spt == 2 && c.ws) LAUNCH_APPLY(2, true);
+  else if (c.spt == 2) LAUNCH_APPLY(2, false);
+  else if (c.ws) LAUNCH_APPLY(1, true);
+  else LAUNCH_APPLY(1, false);
+#undef LAUNCH_APPLY
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x,
+                   const int64_t* y, const float* gz, const float* gld, float* gx, float* partials, double* loss_acc,
+                   int64_t N, float eps, float gamma, float inv_n, int head, cudaStream_t st) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!packed || !tables || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  if (head == CNF_HEAD_NLL && (!y || !loss_acc)) { cnf_set_error("NLL head needs labels and loss_acc"); return CNF_E_ARG; }
+  if (head == CNF_HEAD_EXTERNAL && (!gz || !gld || !partials)) { cnf_set_error("external head needs g_z, g_logdet, partials"); return CNF_E_ARG; }
+  if ((rc = device_limits())) return rc;
+  if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)d.grad_rows * d.n_packed * sizeof(float), st));
+  if (N == 0) return CNF_OK;
+  if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
+  LaunchCfg c;
+  if ((rc = choose_cfg(d, true, &c))) return rc;
+  const int64_t ntiles = (N + c.nt * c.spt - 1) / (c.nt * c.spt);
+  int ctas_per_sm = (int)(g_max_smem / (c.smem + 2048));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  const int64_t cap = (int64_t)g_num_sms * ctas_per_sm;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+#define LAUNCH_TRAIN(SPT, WS)                                                                          \
+  do {                                                                                                 \
+    if ((rc = set_smem(flow_train_kernel<SPT, WS>, c.smem))) return rc;                                \
+    flow_train_kernel<SPT, WS><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, \
+                                                           loss_acc, N, eps, gamma, inv_n, head);      \
+  } while (0)
+  if (c.spt == 2 && c.ws) LAUNCH_TRAIN(2, true);
+  else if (c.spt == 2) LAUNCH_TRAIN(2, false);
+  else if (c.ws) LAUNCH_TRAIN(1, true);
+  else LAUNCH_TRAIN(1, false);
+#undef LAUNCH_TRAIN
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}

@@ -1,0 +1,135 @@
+// Parameter plumbing around the flow kernels (sm_100a): flat <-> packed gather/scatter,
+// gradient-partial reduction, and the optimiser updates.  All O(P) with P <= a few MB;
+// one launch each so a whole training step can be captured in a CUDA graph.
+//
+// Reference arithmetic restated here (third-party torch semantics the reference calls):
+//   torch.optim.Adam.step    calibrators.py:259,295; run_experiment3D.py:55-57,135
+//   torch.optim.SGD.step     run_experiment3D.py:59-61,135
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "cnf_common.h"
+
+namespace {
+
+__global__ void gather_kernel(const float* __restrict__ flat, const int* __restrict__ gather, float* __restrict__ packed,
+                              int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int g = gather[i];
+    packed[i] = g >= 0 ? flat[g] : 0.f;
+  }
+}
+
+__global__ void gather_bf16_kernel(const float* __restrict__ flat, const int* __restrict__ gather,
+                                   __nv_bfloat16* __restrict__ packed, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int g = gather[i];
+    float v = 0.f;
+    if (g >= 0) v = flat[g];
+    else if (g == -2) v = 1.f;       // constant-one entries (bias folding)
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// flat_grad[gather[i]] = sum_rows partials[row][i]; rows summed in fixed order (deterministic
+// given the partials).  flat_grad must be zeroed first (dead entries keep exactly 0).
+__global__ void grad_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ gather,
+                                   float* __restrict__ flat_grad, int n_packed, int rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_packed) return;
+  const int g = gather[i];
+  if (g < 0) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4) {
+    a0 += partials[(size_t)(r + 0) * n_packed + i];
+    a1 += partials[(size_t)(r + 1) * n_packed + i];
+    a2 += partials[(size_t)(r + 2) * n_packed + i];
+    a3 += partials[(size_t)(r + 3) * n_packed + i];
+  }
+  for (; r < rows; ++r) a0 += partials[(size_t)r * n_packed + i];
+  flat_grad[g] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2,
+                            float eps, float wd) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  const float pi = p[i];
+  if (wd != 0.f) gi = fmaf(wd, pi, gi);
+  // torch: exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] = pi - lr_over_bc1 * (mi / denom);
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  if (wd != 0.f) gi = fmaf(wd, p[i], gi);
+  p[i] = p[i] - lr * gi;
+}
+
+}  // namespace
+
+extern "C" int cnf_pack_weights(const cnf_flow_desc* desc, const float* flat, const int32_t* gather, float* packed,
+                                void* stream) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!flat || !gather || !packed) { cnf_set_error("cnf_pack_weights: null pointer"); return CNF_E_ARG; }
+  gather_kernel<<<(d.n_packed + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat, gather, packed, d.n_packed);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st) {
+  gather_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(flat, gather, (__nv_bfloat16*)packed, n);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_partials, const int32_t* gather,
+                               float* flat_grad, void* stream) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!grad_partials || !gather || !flat_grad) { cnf_set_error("cnf_grad_reduce: null pointer"); return CNF_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
+  grad_reduce_kernel<<<(d.n_packed + 127) / 128, 128, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, d.grad_rows);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             void* stream) {
+  if (!params || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) { cnf_set_error("cnf_adam_step: bad argument"); return CNF_E_ARG; }
+  if (n == 0) return CNF_OK;
+  // bias corrections in double on the host, as torch does for python-float steps
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float lr_over_bc1 = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n,
+                                                                             lr_over_bc1, inv_sqrt_bc2, beta1, beta2,
+                                                                             eps, weight_decay);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_sgd_step(float* params, const float* grad, int64_t n, float lr, float weight_decay, void* stream) {
+  if (!params || !grad || n < 0) { cnf_set_error("cnf_sgd_step: bad argument"); return CNF_E_ARG; }
+  if (n == 0) return CNF_OK;
+  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, n, lr, weight_decay);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}

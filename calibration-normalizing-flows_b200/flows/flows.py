@@ -1,0 +1,267 @@
+"""Drop-in for the reference's ``flows/flows.py``: ``Flow`` (:8-37) and ``NvpCouplingLayer``
+(:68-126) with the same constructor arguments, attributes and ``state_dict`` keys.
+
+The modules hold parameters; the arithmetic is one fused CUDA kernel per run of consecutive
+coupling layers (``_engine.StackEngine`` -> libcnf_b200).  Quirks of the reference that are
+preserved on purpose:
+  * fixed half-split mask ``mask[:, dim//2:] = 1`` and a data flip after every layer, so for odd
+    K the middle logit is never transformed and for odd L the class order comes out reversed
+    (flows/flows.py:81-86, 112);
+  * ``Flow.forward`` returns ``(zs, cum_log_det)`` with ``zs`` a list of the L intermediate
+    outputs (flows/flows.py:17-25) -- here a lazy sequence: ``zs[-1]`` is the fused result,
+    other entries are materialised by a second launch only when indexed;
+  * ``log_det`` is squeezed, i.e. 0-d when N == 1 (flows/flows.py:109, 125);
+  * ``Flow.backward`` raises ``ValueError('Flow inverse not tractable!')`` when a layer is not
+    invertible (flows/flows.py:28-29).
+Difference: ``random_flip=True`` also works on CUDA (the reference calls ``.numpy()`` on the
+permutation and is CPU-only there).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .utils import MLP
+from .._engine import StackEngine, stack_forward, require_cuda
+
+
+def _zero_net(x):
+    return x.new_zeros(x.size())
+
+
+class NvpCouplingLayer(nn.Module):
+    def __init__(self, dim, hidden_size=[5, 5], scale=True, shift=True, random_flip=False):
+        super().__init__()
+        self.dim = int(dim)
+        self.hidden_size = list(hidden_size)
+        # Plain callables returning zeros stand in for an absent net, as in the reference.
+        self.s = MLP(dim, self.hidden_size, wscale=0.001) if scale else _zero_net
+        self.t = MLP(dim, self.hidden_size, wscale=0.001) if shift else _zero_net
+        mask = torch.zeros(1, dim)
+        mask[:, dim // 2:] = 1
+        self.mask = nn.Parameter(mask, requires_grad=False)
+        self.invertible = True
+        self.random_flip = random_flip
+        if random_flip:
+            perm = np.random.permutation(dim)
+            rev = np.empty(dim, dtype=np.int64)
+            rev[perm] = np.arange(dim)
+            self.perm = nn.Parameter(torch.as_tensor(perm, dtype=torch.long).view(1, -1), requires_grad=False)
+            self.rev_perm = nn.Parameter(torch.as_tensor(rev, dtype=torch.long).view(1, -1), requires_grad=False)
+        self._engine = None
+        self._perm_cache = None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_engine'] = None          # device handles are rebuilt lazily, never pickled
+        return state
+
+    # -- structure helpers ---------------------------------------------------------------
+    @property
+    def has_scale(self):
+        return isinstance(self.s, nn.Module)
+
+    @property
+    def has_shift(self):
+        return isinstance(self.t, nn.Module)
+
+    @property
+    def coupling_func(self):
+        """NICE-style accessor the reference's notebooks used on additive layers."""
+        return self.t
+
+    def shape_signature(self):
+        return (self.dim, tuple(self.hidden_size), self.has_scale, self.has_shift)
+
+    def signature(self):
+        return self.shape_signature() + (tuple(self.perm_list()) if self.random_flip else None,)
+
+    def canonical_parameters(self):
+        out = []
+        if self.has_scale:
+            out += self.s.canonical_parameters()
+        if self.has_shift:
+            out += self.t.canonical_parameters()
+        return out
+
+    def perm_list(self):
+        if not self.random_flip:
+            return list(range(self.dim))
+        if self._perm_cache is None:      # one host read; refreshed after load_state_dict
+            self._perm_cache = [int(v) for v in self.perm.detach().view(-1).tolist()]
+        return self._perm_cache
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._perm_cache = None
+        self._engine = None
+
+    # -- reference API -------------------------------------------------------------------
+    def _own_engine(self):
+        if self._engine is None:
+            self._engine = build_engine([self])
+        return self._engine
+
+    def forward(self, x):
+        z, ld = stack_forward(self._own_engine(), x)
+        return z, ld.squeeze()
+
+    def backward(self, z):
+        x, ld, _ = self._own_engine().apply(z, inverse=True)
+        return x, ld.squeeze()
+
+
+def build_engine(layers):
+    first = layers[0]
+    perms = [lay.perm_list() for lay in layers] if any(lay.random_flip for lay in layers) else None
+    return StackEngine(first.dim, first.hidden_size, first.has_scale, first.has_shift, perms,
+                       [lay.canonical_parameters() for lay in layers])
+
+
+class _LazyOutputs:
+    """List-like view of the per-layer outputs of a Flow pass.  ``[-1]`` is available at once;
+    any other index triggers (once per fused segment) a launch that writes all intermediates."""
+
+    def __init__(self, flow, segments, seg_inputs, seg_outputs, inverse):
+        self._flow, self._segments = flow, segments
+        self._inputs, self._outputs = seg_inputs, seg_outputs
+        self._inverse = inverse
+        self._cache = {}
+        self._n = sum(seg[2] - seg[1] for seg in segments)
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError('list index out of range')
+        pos = 0
+        for si, (kind, a, b, eng) in enumerate(self._segments):
+            n = b - a
+            if i < pos + n:
+                if i == pos + n - 1:
+                    return self._outputs[si]
+                if si not in self._cache:
+                    with torch.no_grad():
+                        _, _, allz = eng.apply(self._inputs[si], inverse=self._inverse, want_all=True)
+                    self._cache[si] = allz
+                return self._cache[si][i - pos]
+            pos += n
+        raise IndexError(i)
+
+
+class Flow(nn.Module):
+    def __init__(self, layers, **kwargs):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.invertible = all([layer.invertible for layer in self.layers])
+        self.precision = kwargs.get('precision', 'fp32')
+        self._plan = None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_plan'] = None
+        return state
+
+    # Consecutive coupling layers with the same shape fuse into one kernel launch; any other
+    # module that follows the (z, log_det) layer protocol is called as is.
+    def _segments(self):
+        key = tuple((id(l), l.signature() if isinstance(l, NvpCouplingLayer) else None) for l in self.layers)
+        if self._plan is not None and self._plan[0] == key:
+            return self._plan[1]
+        segs, i, layers = [], 0, list(self.layers)
+        while i < len(layers):
+            lay = layers[i]
+            if isinstance(lay, NvpCouplingLayer):
+                j = i + 1
+                while (j < len(layers) and isinstance(layers[j], NvpCouplingLayer)
+                       and layers[j].shape_signature() == lay.shape_signature()
+                       and len({id(l) for l in layers[i:j + 1]}) == j + 1 - i):
+                    j += 1
+                segs.append(('stack', i, j, build_engine(layers[i:j])))
+                i = j
+            else:
+                segs.append(('module', i, i + 1, lay))
+                i += 1
+        self._plan = (key, segs)
+        return segs
+
+    def engine(self):
+        """The single fused engine when the whole flow is one homogeneous coupling stack."""
+        segs = self._segments()
+        if len(segs) == 1 and segs[0][0] == 'stack':
+            return segs[0][3]
+        return None
+
+    def forward(self, x):
+        require_cuda(x)
+        segs = self._segments()
+        cum, ins, outs = 0.0, [], []
+        for kind, a, b, obj in segs:
+            ins.append(x)
+            if kind == 'stack':
+                if self.precision == 'bf16' and not torch.is_grad_enabled():
+                    x, ld, _ = obj.apply(x, precision='bf16')
+                else:
+                    x, ld = stack_forward(obj, x)
+                ld = ld.squeeze()
+            else:
+                x, ld = obj(x)
+            outs.append(x)
+            cum = cum + ld
+        return _LazyOutputs(self, segs, ins, outs, False), cum
+
+    def backward(self, z):
+        if not self.invertible:
+            raise ValueError('Flow inverse not tractable!')
+        require_cuda(z)
+        segs = self._segments()[::-1]
+        cum, ins, outs = 0.0, [], []
+        for kind, a, b, obj in segs:
+            ins.append(z)
+            if kind == 'stack':
+                z, ld, _ = obj.apply(z, inverse=True, precision=self.precision)
+                ld = ld.squeeze()
+            else:
+                z, ld = obj.backward(z)
+            outs.append(z)
+            cum = cum + ld
+        return _LazyOutputs(self, segs, ins, outs, True), cum
+
+
+class CouplingStack(nn.Module):
+    """Factory-style flow with the contract ``TorchFlowCalibrator`` expects from the class it is
+    given (calibrators.py:251, 287, 304, 339): ``Flow(dim, **kwargs)`` must swallow the
+    calibrator's own kwargs (dev, epochs, batch_size), ``flow(x)`` returns ``(z, log_det)`` and
+    ``.layers`` iterates the coupling layers.  Defaults follow the Keras predecessors
+    (code-old/nice.py:104-113, code-old/realNVP.py:47-52): 4 layers, hidden ``[dim]``."""
+
+    def __init__(self, dim, layers=4, hidden_size=None, scale=True, shift=True, random_flip=False,
+                 precision='fp32', **ignored):
+        super().__init__()
+        hidden_size = [dim] if hidden_size is None else list(hidden_size)
+        self.flow = Flow([NvpCouplingLayer(dim, hidden_size=hidden_size, scale=scale, shift=shift,
+                                           random_flip=random_flip) for _ in range(layers)],
+                         precision=precision)
+        self.invertible = True
+
+    @property
+    def layers(self):
+        return self.flow.layers
+
+    def engine(self):
+        return self.flow.engine()
+
+    def forward(self, x):
+        zs, ld = self.flow(x)
+        return zs[-1], ld
+
+    def backward(self, z):
+        xs, ld = self.flow.backward(z)
+        return xs[-1], ld

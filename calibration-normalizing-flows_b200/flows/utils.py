@@ -1,0 +1,44 @@
+"""Conditioner network container -- drop-in for the reference's ``flows/utils.py:6-31``.
+
+``MLP`` only *holds* the parameters (same attribute names, shapes, init and state_dict keys
+as the reference: ``layers.{j}.weight`` [out, in], ``layers.{j}.bias``).  Inside a coupling
+layer the network is never evaluated module by module: the fused CUDA kernel reads the
+packed weights.  ``forward`` exists for standalone use of the container (reference
+``run_experiment3D.py:40`` builds a bare MLP as its "dnn" baseline, out of this path's scope).
+"""
+import math
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+class MLP(nn.Module):
+    def __init__(self, dim, hidden_size=[], activation=F.relu, wscale=1.):
+        super().__init__()
+        self.activation = activation
+        widths = [dim, *hidden_size, dim]
+        self.layers = nn.ModuleList()
+        for fan_in, fan_out in zip(widths, widths[1:]):
+            lin = nn.Linear(fan_in, fan_out)
+            # nn.Linear default init, then weight AND bias scaled (reference flows/utils.py:19-21)
+            with torch.no_grad():
+                lin.weight.mul_(wscale)
+                lin.bias.mul_(wscale)
+            self.layers.append(lin)
+
+    @property
+    def hidden_size(self):
+        return [lin.out_features for lin in list(self.layers)[:-1]]
+
+    def canonical_parameters(self):
+        out = []
+        for lin in self.layers:
+            out += [lin.weight, lin.bias]
+        return out
+
+    def forward(self, x):
+        *hidden, last = list(self.layers)
+        for lin in hidden:
+            x = self.activation(lin(x))
+        return last(x)

@@ -1,0 +1,153 @@
+/*
+ * cnf.h -- C ABI of the B200-native coupling-flow calibration hot path.
+ *
+ * One shared library (libcnf_b200.so, sm_100a) replaces the arithmetic of the
+ * reference's PyTorch modules on this path.  Every entry point is extern "C",
+ * takes plain pointers and sizes, returns 0 on success or a negative CNF_E_*
+ * code (message via cnf_last_error(), thread-local), never throws, never
+ * allocates or frees caller-visible memory, and launches asynchronously on the
+ * caller's cudaStream_t (passed as void*).  There is no CPU fallback: a call
+ * without a usable CUDA device returns CNF_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   cnf_flow_forward     Flow.forward            flows/flows.py:17-25
+ *                        NvpCouplingLayer.forward flows/flows.py:101-112
+ *                        MLP.forward              flows/utils.py:26-31
+ *   cnf_flow_inverse     Flow.backward            flows/flows.py:27-37
+ *                        NvpCouplingLayer.backward flows/flows.py:114-126
+ *   cnf_nll_train_step   loss + loss.backward()   calibrators.py:287-293,
+ *                                                 run_experiment3D.py:102-107,133-134
+ *   cnf_flow_backward    autograd of Flow.forward (torch, third party)
+ *   cnf_adam_step        torch.optim.Adam.step    calibrators.py:259,295
+ *   cnf_sgd_step         torch.optim.SGD.step     run_experiment3D.py:59-61,135
+ *   cnf_metrics          expected_calibration_error / neg_log_likelihood / accuracy
+ *                                                 utils/metrics.py:35-73, 6-15, 76-80
+ *                        (+ Calibrator.predict tail calibrators.py:40-44, 350-353)
+ *
+ * Data conventions: logits x, z are float32 [N, K] row-major contiguous; labels
+ * are int64 [N]; log-det is float32 [N].  "flat" is the trainable parameter
+ * vector in canonical order (per coupling layer: s-net then t-net; per Linear:
+ * weight [out,in] row-major then bias), i.e. the reference state_dict tensors
+ * laid end to end.  "packed" is the kernel-side copy with the half-split mask,
+ * flips and permutations folded in (dead rows/columns dropped).
+ */
+#ifndef CNF_B200_H
+#define CNF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNF_VERSION 100
+#define CNF_MAX_HIDDEN 4
+
+enum {
+  CNF_OK = 0,
+  CNF_E_ARG = -1,      /* bad descriptor / null pointer / unsupported shape */
+  CNF_E_CUDA = -2,     /* CUDA runtime error (no device, launch failure, ...) */
+  CNF_E_SMEM = -3,     /* model does not fit the kernel's shared-memory plan */
+  CNF_E_UNSUPPORTED = -4
+};
+
+enum { CNF_PREC_FP32 = 0, CNF_PREC_BF16_TC = 1 };
+
+/* Loss-head selector for cnf_nll_train_step / cnf_flow_backward */
+enum { CNF_HEAD_NLL = 0, CNF_HEAD_EXTERNAL = 1 };
+
+/* cnf_metrics input modes */
+enum {
+  CNF_METRICS_PROBS = 0,       /* input rows are probabilities                       */
+  CNF_METRICS_LOGITS = 1,      /* softmax(z) first (predict_post, calibrators.py:352) */
+  CNF_METRICS_CALIBRATED = 2   /* softmax(log(softmax(z)+1e-7) - log_priors), :44     */
+};
+
+typedef struct cnf_flow_desc {
+  int32_t K;                       /* classes = flow dimension                      */
+  int32_t L;                       /* coupling layers                               */
+  int32_t n_hidden;                /* hidden layers of each conditioner MLP (0..4)  */
+  int32_t hidden[CNF_MAX_HIDDEN];  /* their widths                                  */
+  int32_t scale;                   /* 1: s-net present (RealNVP), 0: NICE additive  */
+  int32_t shift;                   /* 1: t-net present                              */
+  int32_t precision;               /* CNF_PREC_*                                    */
+  const int32_t* perm;             /* HOST [L*K] random_flip permutations or NULL   */
+} cnf_flow_desc;
+
+typedef struct cnf_plan_info {
+  int64_t n_flat;          /* floats in the canonical flat parameter vector         */
+  int64_t n_packed;        /* floats in the fp32 packed blob                        */
+  int64_t n_tables;        /* int32 entries of the index tables                     */
+  int64_t n_grad_rows;     /* rows of the per-CTA gradient partial buffer           */
+  int64_t tc_bytes;        /* bytes of the bf16 tensor-core blob, 0 if shape not    */
+                           /* supported by the tensor-core path                     */
+  int32_t d0, d1;          /* transformed / conditioning dims per layer             */
+  int32_t hidden_padded[CNF_MAX_HIDDEN];
+} cnf_plan_info;
+
+const char* cnf_last_error(void);
+int cnf_version(void);
+
+/* ---- host-side planning (pure index logic, no device needed) ---------------- */
+int cnf_plan_info_get(const cnf_flow_desc* desc, cnf_plan_info* out);
+/* gather[i] = index into flat for packed float i, or -1 for structural zero.
+ * tables = [pi (L+1)*K | cond L*d1 | trans L*d0] physical-slot index maps.     */
+int cnf_plan_build(const cnf_flow_desc* desc, int32_t* gather_host, int32_t* tables_host);
+/* Same gather for the tensor-core blob: entry i addresses bf16 element i.       */
+int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* gather_tc_host);
+
+/* ---- device: parameter packing ----------------------------------------------- */
+int cnf_pack_weights(const cnf_flow_desc* desc, const float* flat, const int32_t* gather,
+                     float* packed, void* stream);
+int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat, const int32_t* gather_tc,
+                        void* packed_tc, void* stream);
+
+/* ---- device: the flow --------------------------------------------------------- */
+/* zs (optional, may be NULL): float32 [L, N, K], every intermediate output.     */
+int cnf_flow_forward(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                     const float* x, float* z, float* logdet, float* zs, int64_t N, void* stream);
+/* xs (optional): float32 [L, N, K]; xs[L-1] == x.                                */
+int cnf_flow_inverse(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                     const float* z, float* x, float* logdet, float* xs, int64_t N, void* stream);
+
+/* ---- device: training --------------------------------------------------------- */
+/* One fused pass over N local samples: forward, loss head, backward.
+ *   loss_i = -( log(softmax(z_i)[y_i] + eps) + gamma * logdet_i );  eps==0 -> log-softmax.
+ * grad_partials: float32 [n_grad_rows, n_packed], overwritten; sum of rows is
+ *   d(sum_i loss_i * inv_n_total)/d(packed).  NULL = evaluation only.
+ * loss_acc: float64 [4] ACCUMULATED (zero it first): sum(ce_i + gamma*ld_i),
+ *   sum(ce_i), sum(ld_i), count of non-finite samples; ce_i = log(p_y+eps).      */
+int cnf_nll_train_step(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                       const float* x, const int64_t* y, int64_t N, float eps, float gamma,
+                       float inv_n_total, float* grad_partials, double* loss_acc, void* stream);
+/* Backward for arbitrary upstream gradients (autograd of Flow.forward):
+ * g_z [N,K], g_logdet [N] -> g_x [N,K] (may be NULL) and grad_partials.          */
+int cnf_flow_backward(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                      const float* x, const float* g_z, const float* g_logdet, float* g_x,
+                      float* grad_partials, int64_t N, void* stream);
+/* flat_grad[gather[i]] = sum over rows of grad_partials[:, i]; dead entries = 0. */
+int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_partials, const int32_t* gather,
+                    float* flat_grad, void* stream);
+/* torch.optim.Adam (L2 weight decay, bias correction as torch); step is 1-based. */
+int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  void* stream);
+int cnf_sgd_step(float* params, const float* grad, int64_t n, float lr, float weight_decay,
+                 void* stream);
+
+/* ---- device: metrics ----------------------------------------------------------- */
+/* in: [N,K] float32 (is_f64 == 0) or float64 (is_f64 == 1); labels int64 [N].
+ * edges: DEVICE float64 [bins+1], edge i = i*(1/bins) as the reference forms it.
+ * acc: DEVICE float64 [3*bins+3], ACCUMULATED: per bin count, sum conf, sum acc;
+ *      then sum -log(p_y+1e-7), number correct, N.                               */
+int cnf_metrics(const void* in, int32_t is_f64, const int64_t* y, int64_t N, int32_t K,
+                int32_t bins, int32_t mode, const double* log_priors, const double* edges,
+                double* acc, void* stream);
+/* Full Calibrator.predict tail on device: probs_out float64 [N,K].              */
+int cnf_calibrated_probs(const float* z, int64_t N, int32_t K, const double* log_priors,
+                         double* probs_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNF_B200_H */

@@ -1,0 +1,117 @@
+"""Shared test helpers: build drop-in flows from golden fixtures, emulate the packed layout."""
+import ctypes
+
+import numpy as np
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def build_flow_from_golden(g, device=None, precision='fp32'):
+    """cnf_b200.Flow with the golden weights loaded (canonical flat order)."""
+    import torch
+    import cnf_b200
+    K, L = int(g['K']), int(g['L'])
+    hidden = [int(h) for h in g['hidden']]
+    rf = bool(int(g['random_flip']))
+    layers = [cnf_b200.NvpCouplingLayer(K, hidden_size=hidden, scale=bool(g['scale']), shift=bool(g['shift']),
+                                        random_flip=rf) for _ in range(L)]
+    flat = torch.from_numpy(g['flat'].astype(np.float32))
+    off = 0
+    with torch.no_grad():
+        for l, lay in enumerate(layers):
+            for p in lay.canonical_parameters():
+                n = p.numel()
+                p.copy_(flat[off:off + n].view(p.shape))
+                off += n
+            if rf:
+                perm = torch.from_numpy(g['perms'][l].astype(np.int64)).view(1, -1)
+                rev = torch.empty_like(perm)
+                rev[0, perm[0]] = torch.arange(K)
+                lay.perm.copy_(perm)
+                lay.rev_perm.copy_(rev)
+                lay._perm_cache = None
+    assert off == flat.numel()
+    flow = cnf_b200.Flow(layers, precision=precision)
+    if device is not None:
+        flow.to(device)
+    return flow
+
+
+def plan_host(K, L, hidden, scale, shift, perms=None):
+    """(info, gather, tables) from the C planner via ctypes -- no GPU needed."""
+    import cnf_b200  # noqa: F401  (loads the library)
+    from cnf_b200 import _lib
+    desc, keep = _lib.make_desc(K, L, hidden, scale, shift, _lib.PREC_FP32, perms)
+    info = _lib.PlanInfo()
+    _lib.call('cnf_plan_info_get', ctypes.byref(desc), ctypes.byref(info))
+    gather = np.empty(int(info.n_packed), dtype=np.int32)
+    tables = np.empty(int(info.n_tables), dtype=np.int32)
+    _lib.call('cnf_plan_build', ctypes.byref(desc), gather.ctypes.data_as(ctypes.c_void_p),
+              tables.ctypes.data_as(ctypes.c_void_p))
+    return info, gather, tables
+
+
+def emulate_packed_forward(K, L, hidden, scale, shift, info, gather, tables, flat, x):
+    """numpy emulation of what the fp32 kernel computes from (packed, tables): validates the
+    planner's gather map and index tables on the CPU."""
+    CH = 16
+    d0, d1 = K // 2, K - K // 2
+    m = len(hidden)
+    Hp = [(h + CH - 1) // CH * CH for h in hidden]
+    d0p = (d0 + CH - 1) // CH * CH
+    packed = np.where(gather >= 0, flat[np.maximum(gather, 0)], 0.0)
+    # net block offsets, mirroring cnf_make_dims
+    w_off, b_off, off = [], [], 0
+    if m == 0:
+        w_off.append(off); off += d1 * d0p
+        b_off.append(off); off += d0p
+    else:
+        w_off.append(off); off += d1 * Hp[0]
+        b_off.append(off); off += Hp[0]
+        for j in range(1, m):
+            w_off.append(off); off += Hp[j - 1] * Hp[j]
+            b_off.append(off); off += Hp[j]
+        w_off.append(off); off += d0 * Hp[m - 1]
+        b_off.append(off); off += (d0 + 3) // 4 * 4
+    net_stride = off
+    n_nets = int(scale) + int(shift)
+    layer_stride = net_stride * n_nets
+    assert layer_stride * L == packed.size
+    tab_cond = (L + 1) * K
+    tab_trans = tab_cond + L * d1
+    a = x.astype(np.float64).copy()
+    ld = np.zeros(x.shape[0])
+
+    def net(Wn, u):
+        if m == 0:
+            W = Wn[w_off[0]:w_off[0] + d1 * d0p].reshape(d1, d0p)
+            return (u @ W + Wn[b_off[0]:b_off[0] + d0p])[:, :d0]
+        h = u
+        n_in = d1
+        for j in range(m):
+            W = Wn[w_off[j]:w_off[j] + n_in * Hp[j]].reshape(n_in, Hp[j])
+            h = np.maximum(h @ W + Wn[b_off[j]:b_off[j] + Hp[j]], 0)
+            n_in = Hp[j]
+        W = Wn[w_off[m]:w_off[m] + d0 * Hp[m - 1]].reshape(d0, Hp[m - 1])
+        return h @ W.T + Wn[b_off[m]:b_off[m] + d0]
+
+    for l in range(L):
+        cond = tables[tab_cond + l * d1: tab_cond + (l + 1) * d1]
+        trans = tables[tab_trans + l * d0: tab_trans + (l + 1) * d0]
+        Wl = packed[l * layer_stride:(l + 1) * layer_stride]
+        u = a[:, cond]
+        slot = 0
+        s = np.zeros((x.shape[0], d0))
+        t = np.zeros((x.shape[0], d0))
+        if scale:
+            s = net(Wl[slot * net_stride:(slot + 1) * net_stride], u); slot += 1
+        if shift:
+            t = net(Wl[slot * net_stride:(slot + 1) * net_stride], u)
+        a[:, trans] = a[:, trans] * np.exp(s) + t
+        ld += s.sum(axis=1)
+    pi_last = tables[L * K:(L + 1) * K]
+    return a[:, pi_last], ld

