@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the coupling-flow hot path (see BASELINE.json, DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Own arm.  Workload at every N: BASELINE config C2 -- RealNVP affine flow, K=10 classes, 6 coupling
+layers, hidden 128, fused forward + log-det over a batch of 1,000,000 synthetic logits per GPU per
+step (weak scaling: samples shard with no collective).  `value` = samples/s with inputs resident in
+HBM; `e2e` = the same pass through the public host-buffer API (pinned host logits -> H2D -> kernel ->
+D2H of z and log-det inside the timed region).  Extra keys: `roofline` (dominant kernel, CUDA
+events), `cpu_baseline` (the reference's arithmetic on the box's host cores), `train_step`
+(config C3 shape: fused NLL forward+backward+Adam, NCCL all-reduce of the flat gradient at N>1).
+
+Reference arm (--impl reference): the reference's own CPU implementation of the same pass
+(oracle/ref_port_torch.py: the reference's torch op sequence; /root/reference does not exist on
+the GPU box) on all host threads, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'calibrated samples/sec (flow fwd+logdet)'
+UNIT = 'samples/s'
+K, L, HIDDEN = 10, 6, [128]
+N_STEP = 1_000_000
+N_ROT = 8                       # rotating input batches: 8 x 84 MB in+out > 126 MB L2
+BYTES_PER_SAMPLE = 8 * K + 4    # read x, write z, write log-det
+FLOPS_PER_SAMPLE = L * 2 * 2 * (5 * 128 + 128 * 5)   # minimal, mask-exploiting
+WORKLOAD = 'C2: RealNVP K=10 L=6 hidden=[128], fused fwd+logdet, N=1,000,000 synthetic logits per GPU per step'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p['hbm_gbs'], p['bf16_tflops'], 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_weights(seed=1):
+    """Reference init (nn.Linear default x 0.001, flows/flows.py:76-79) x 300 = 'trained-like' scale."""
+    import torch
+    import cnf_b200
+    torch.manual_seed(seed)
+    model = cnf_b200.RealNvpFlow(K, layers=L, hidden_size=HIDDEN)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(300.0)
+    return model
+
+
+def synth(n, seed, device=None):
+    """Over-confident 80%-accurate synthetic classifier logits, row-centred."""
+    import torch
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    y = torch.randint(0, K, (n,), generator=g)
+    x = 1.5 * torch.randn((n, K), generator=g)
+    hit = (torch.rand(n, generator=g) < 0.8).float()
+    x[torch.arange(n), y] += 3.0 * hit
+    x -= x.mean(dim=1, keepdim=True)
+    if device is not None:
+        return x.to(device), y.to(device)
+    return x, y
+
+
+def cpu_reference_pass(flat, x, reps, warm=1):
+    """Seconds per forward+log-det pass of the reference's torch-CPU arithmetic on x."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_port_torch as rp
+    layers = rp.unflatten(flat, K, L, HIDDEN)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            zs, ld = rp.forward(layers, x)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    times.sort()
+    return times[len(times) // 2], times
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = make_weights()
+    flat = torch.cat([p.detach().reshape(-1) for lay in model.layers for p in lay.canonical_parameters()])
+    # size the per-step sample so the whole run stays within ~2 minutes
+    probe, _ = synth(100_000, 7)
+    t_probe, _ = cpu_reference_pass(flat, probe, reps=1, warm=1)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = int(min(N_STEP, max(50_000, 100_000 * budget / max(t_probe, 1e-6))))
+    x, _ = synth(n, 11)
+    med, times = cpu_reference_pass(flat, x, reps=args.steps, warm=args.warmup)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample_per_step': n, 'device': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': '%d samples per step, %d steps, torch CPU ops restating flows/flows.py:101-112 '
+                                   '(oracle/ref_port_torch.py)' % (n, len(times))},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cnf_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model = make_weights().to(dev)
+    eng = model.engine()
+    precision = args.precision
+    if precision == 'auto':
+        precision = 'bf16' if eng.tc_bytes > 0 else 'fp32'
+    eng.ensure(dev)
+    eng.pack(tc=(precision == 'bf16'))
+
+    # ---- kernel-resident measurement: inputs already in HBM ---------------------------------
+    xs = [synth(N_STEP, 100 + rank * N_ROT + i, dev)[0] for i in range(N_ROT)]
+    import ctypes
+    from cnf_b200 import _lib
+    from cnf_b200._engine import _ptr, _stream
+    z = torch.empty_like(xs[0])
+    ld = torch.empty(N_STEP, dtype=torch.float32, device=dev)
+    desc = eng.desc_tc if precision == 'bf16' else eng.desc
+    packed = eng.packed_tc if precision == 'bf16' else eng.packed
+
+    def step(i):
+        _lib.call('cnf_flow_forward', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
+                  _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * N_STEP * args.steps / (ms * 1e-3)
+    kern_ms = e0.elapsed_time(e1) / args.steps        # one kernel per step on this stream
+    launches = args.steps
+
+    # ---- end to end through the public host-buffer API ---------------------------------------
+    xh = torch.empty((N_STEP, K), dtype=torch.float32, pin_memory=True)
+    xh.copy_(synth(N_STEP, 999 + rank)[0])
+    zh = torch.empty((N_STEP, K), dtype=torch.float32, pin_memory=True)
+    lh = torch.empty(N_STEP, dtype=torch.float32, pin_memory=True)
+    model.flow.precision = precision
+    for _ in range(max(3, args.warmup)):
+        model.transform_host(xh, zh, lh, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.transform_host(xh, zh, lh, device=dev)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {'value': world * N_STEP * args.steps / e2e_s, 'unit': UNIT,
+           'h2d_bytes_per_step': xh.numel() * 4, 'd2h_bytes_per_step': zh.numel() * 4 + lh.numel() * 4,
+           'api': 'RealNvpFlow.transform_host (pinned host logits in, host z + log-det out)'}
+
+    # ---- training step, config C3 shape (fp32 path) ------------------------------------------
+    train = None
+    if not args.no_train:
+        n_loc = args.train_n
+        xt, yt = synth(n_loc, 5000 + rank, dev)
+        tmodel = make_weights(seed=2)
+        with torch.no_grad():
+            for p in tmodel.parameters():
+                if p.requires_grad:
+                    p.mul_(1.0 / 300.0)          # reference init for training
+        tmodel.to(dev)
+        tr = cnf_b200.FusedNLLTrainer(tmodel.engine(), xt, yt, n_total=n_loc * world)
+        for _ in range(3):
+            tr.step()
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        tsteps = max(3, min(args.steps, 5))
+        for _ in range(tsteps):
+            tr.step()
+        t1e.record()
+        barrier()
+        tms = max_over_ranks(t0e.elapsed_time(t1e))
+        train = {'value': world * n_loc * tsteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / tsteps,
+                 'samples_per_gpu': n_loc, 'steps': tsteps, 'dtype': 'f32',
+                 'what': 'fused NLL fwd+bwd kernel + grad reduce' + (' + NCCL all-reduce' if world > 1 else '') +
+                         ' + Adam + repack per step', 'loss': -float(tr.loss_acc[0]) / (n_loc * world)}
+        del xt, yt
+
+    hbm, tf, src = peaks()
+    ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
+    roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+            'kernel': 'flow_tc_kernel' if precision == 'bf16' else 'flow_apply_kernel', 'peak_source': src,
+            'note': 'algorithmic bytes 84 B/sample x 1e6 samples per launch'}
+    ach_tf = FLOPS_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e12
+    roof_tensor = {'bound': 'tensor', 'achieved': ach_tf, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach_tf / tf,
+                   'note': 'minimal (mask-exploiting) 30720 flop/sample; peak = measured bf16 burst'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        flat = eng.flat.detach().cpu()
+        xc, _ = synth(N_STEP, 11)
+        med, times = cpu_reference_pass(flat, xc, reps=3, warm=1)
+        cpu = {'value': N_STEP / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '1,000,000 samples x 3 passes (median), torch CPU ops restating flows/flows.py:101-112'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'l2': 'inputs larger than L2: %d rotating batches' % N_ROT,
+                           'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1'},
+                'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
+                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='auto', choices=['auto', 'fp32', 'bf16'])
+    ap.add_argument('--train-n', type=int, default=8 * (1 << 20))
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', '29511', os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

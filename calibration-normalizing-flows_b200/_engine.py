@@ -148,6 +148,54 @@ class StackEngine:
                   _ptr(allz), ctypes.c_int64(N), _stream(x.device))
         return out, ld, allz
 
+    def apply_host(self, x_host, out_host=None, ld_host=None, inverse=False, precision='fp32',
+                   chunk=1 << 18, slots=3, repack=True, device=None):
+        """Host buffers in, host buffers out: the samples stream through the GPU in chunks on
+        `slots` CUDA streams so that the H2D copy, the flow kernel and the D2H copy of
+        neighbouring chunks overlap.  x_host: CPU float32 [N,K] (pinned memory gives full PCIe
+        speed).  Returns (out_host, ld_host) as CPU tensors (pinned when allocated here)."""
+        device = torch.device(device) if device is not None else (self.device or torch.device('cuda', torch.cuda.current_device()))
+        x_host = torch.as_tensor(x_host, dtype=torch.float32)
+        if x_host.is_cuda:
+            raise RuntimeError('apply_host expects host memory')
+        x_host = x_host.contiguous()
+        N, K = x_host.shape
+        if out_host is None:
+            out_host = torch.empty((N, K), dtype=torch.float32, pin_memory=True)
+        if ld_host is None:
+            ld_host = torch.empty(N, dtype=torch.float32, pin_memory=True)
+        self.ensure(device)
+        use_tc = precision == 'bf16'
+        if use_tc and self.packed_tc is None:
+            raise NotImplementedError('cnf_b200: bf16 tensor-core path not available for this flow shape')
+        if repack:
+            self.pack(tc=use_tc)
+        st = getattr(self, '_host_slots', None)
+        if st is None or st[0] != (device, chunk, slots):
+            bufs = [(torch.cuda.Stream(device), torch.empty((chunk, K), dtype=torch.float32, device=device),
+                     torch.empty((chunk, K), dtype=torch.float32, device=device),
+                     torch.empty(chunk, dtype=torch.float32, device=device)) for _ in range(slots)]
+            st = self._host_slots = ((device, chunk, slots), bufs)
+        main = torch.cuda.current_stream(device)
+        fn = 'cnf_flow_inverse' if inverse else 'cnf_flow_forward'
+        desc = self.desc_tc if use_tc else self.desc
+        packed = self.packed_tc if use_tc else self.packed
+        for i, lo in enumerate(range(0, N, chunk)):
+            hi = min(N, lo + chunk)
+            n = hi - lo
+            stream, xin, zout, ldout = st[1][i % slots]
+            if i < slots:
+                stream.wait_stream(main)        # weights were packed on the caller's stream
+            with torch.cuda.stream(stream):
+                xin[:n].copy_(x_host[lo:hi], non_blocking=True)
+                _lib.call(fn, ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(xin), _ptr(zout),
+                          _ptr(ldout), None, ctypes.c_int64(n), ctypes.c_void_p(stream.cuda_stream))
+                out_host[lo:hi].copy_(zout[:n], non_blocking=True)
+                ld_host[lo:hi].copy_(ldout[:n], non_blocking=True)
+        for stream, *_ in st[1]:
+            main.wait_stream(stream)
+        return out_host, ld_host
+
     def backward(self, x, g_z, g_ld, need_gx=True):
         """Generic autograd backward: returns (g_x or None, flat_grad)."""
         self.ensure(x.device)

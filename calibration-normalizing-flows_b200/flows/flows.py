@@ -262,6 +262,18 @@ class CouplingStack(nn.Module):
         zs, ld = self.flow(x)
         return zs[-1], ld
 
+    def transform_host(self, x_host, out_host=None, ld_host=None, device=None, **kw):
+        """numpy / CPU tensor in, CPU tensors out: (z, log_det), streamed through the GPU in
+        overlapping chunks (see StackEngine.apply_host).  Synchronises before returning."""
+        eng = self.engine()
+        if eng is None:
+            raise NotImplementedError('transform_host needs a homogeneous coupling stack')
+        dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.to(dev)
+        z, ld = eng.apply_host(x_host, out_host, ld_host, precision=self.flow.precision, device=dev, **kw)
+        torch.cuda.current_stream(dev).synchronize()
+        return z, ld
+
     def backward(self, z):
         xs, ld = self.flow.backward(z)
         return xs[-1], ld
