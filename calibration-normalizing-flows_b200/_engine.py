@@ -60,7 +60,9 @@ class StackEngine:
         self._gather_host, self._tables_host = gather, tables
         self._gather_tc_host = None
         if self.tc_bytes > 0:
-            g = np.empty(self.tc_bytes // 2, dtype=np.int32)
+            n_g = ctypes.c_int64(0)
+            _lib.call('cnf_tc_gather_len', ctypes.byref(self.desc_tc), ctypes.byref(n_g))
+            g = np.empty(int(n_g.value), dtype=np.int32)
             _lib.call('cnf_plan_build_tc', ctypes.byref(self.desc_tc), g.ctypes.data_as(ctypes.c_void_p))
             self._gather_tc_host = g
         self.device = None
@@ -88,7 +90,7 @@ class StackEngine:
         self.packed_tc = None
         if self._gather_tc_host is not None:
             self.gather_tc = torch.from_numpy(self._gather_tc_host).to(device)
-            self.packed_tc = torch.empty(self.tc_bytes // 2, dtype=torch.bfloat16, device=device)
+            self.packed_tc = torch.empty(self.tc_bytes, dtype=torch.uint8, device=device)
         self.partials = None
         self.flat_grad = None
         # optimiser state follows the parameters (the reference keeps it in self.optimizer)

@@ -41,6 +41,7 @@ _I64, _I32, _F32 = ctypes.c_int64, ctypes.c_int32, ctypes.c_float
 SIGNATURES = {
     'cnf_plan_info_get': [_DESC, ctypes.POINTER(PlanInfo)],
     'cnf_plan_build': [_DESC, _P, _P],
+    'cnf_tc_gather_len': [_DESC, ctypes.POINTER(ctypes.c_int64)],
     'cnf_plan_build_tc': [_DESC, _P],
     'cnf_pack_weights': [_DESC, _P, _P, _P, _P],
     'cnf_pack_weights_tc': [_DESC, _P, _P, _P, _P],

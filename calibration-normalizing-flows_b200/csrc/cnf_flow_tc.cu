@@ -1,20 +1,522 @@
-// bf16 tcgen05 tensor-core kernel of the coupling-flow stack (placeholder until the kernel lands).
+// bf16 tensor-core kernel of the coupling-flow stack for sm_100a: tcgen05.mma with TMEM
+// accumulators, one persistent CTA per SM, forward and inverse, fp32 coupling arithmetic.
+//
+// Shape coverage (cnf_tc_supported): one hidden layer per conditioner, K <= 16 classes
+// (d1+1 <= 16, d0 <= 8), N1 = n_nets*pad16(H) <= 256.  Everything else runs on the fp32 kernel.
+//
+// Per coupling layer and per tile of 128 samples (TMEM lane = sample row):
+//   GEMM1  D1[128 x N1] = A1[128 x 16] . B1^T          tcgen05.mma SS, bf16 in, fp32 out (TMEM)
+//          A1 row = (u_0..u_{d1-1}, 1, 0..): the conditioning logits plus a constant-one column
+//          that folds the first-layer bias; B1 = first Linear of the s-net and of the t-net side
+//          by side (flows/utils.py:26-31, flows/flows.py:105).
+//   EPI1   h = relu(D1) -> bf16, written back to TMEM in place (A2 aliases the low half of D1).
+//   GEMM2  D2[128 x 16] = A2[128 x N1] . B2^T            tcgen05.mma TS (A from TMEM), N1/16 k-steps
+//          B2 = block-diagonal last Linears: columns 0..7 <- first present net, 8..15 <- second.
+//   EPI2   s,t = D2 + b2 (fp32); y = x*exp(s)+t, ld += sum s   (flows/flows.py:107-109); inverse
+//          x = (y-t)*exp(-s), ld -= sum s (flows/flows.py:121-125).
+// A CTA keeps two tiles in flight (two 256-column TMEM slots, one epilogue warpgroup each) so the
+// tensor pipe works on one tile while CUDA cores run the other tile's epilogue.  Warp 0 lane 0
+// issues every MMA and polls the slots' mbarriers; all packed weights of all layers stay
+// resident in shared memory in the canonical no-swizzle K-major UMMA layout.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "cnf_common.h"
 
-long long cnf_tc_blob_bytes(const cnf_flow_desc*, const CnfDims&) { return 0; }
+int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
 
-extern "C" int cnf_plan_build_tc(const cnf_flow_desc*, int32_t*) {
-  cnf_set_error("tensor-core path not available for this shape");
-  return CNF_E_UNSUPPORTED;
+namespace {
+
+constexpr int TC_THREADS = 384;
+constexpr int TILE_M = 128;
+constexpr int A1_BYTES = TILE_M * 32;   // 128 rows x 16 bf16
+constexpr int LBO1 = 128, SBO1 = 256;   // A1 / B1: k-halves adjacent, 8-row groups 256 B apart
+constexpr int LBO2 = 256, SBO2 = 128;   // B2 per k-step: two 8-row groups adjacent, k-halves 256 B apart
+
+struct TcDims {
+  int K, L, d0, d1, Hp, nets, n_nets, N1;
+  int b_layer_bytes;                 // bytes of one layer's B1 (== B2): N1*16*2
+  int b1_off, b2_off, bias_off;      // byte offsets inside the blob
+  int n_bf16, n_f32, blob_bytes;
+  int tab_pi, tab_cond, tab_trans, n_tables;
+  // shared-memory carve-up (bytes)
+  int sm_tab, sm_slot, sm_slot_stride, sm_bar, sm_total;
+};
+
+bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
+  if (d.m != 1 || d.n_nets < 1) return false;
+  if (d.d1 + 1 > 16 || d.d0 > 8) return false;
+  const int N1 = d.n_nets * d.Hp[0];
+  if (N1 < 16 || N1 > 256) return false;
+  t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->Hp = d.Hp[0]; t->nets = d.nets; t->n_nets = d.n_nets;
+  t->N1 = N1;
+  t->b_layer_bytes = N1 * 16 * 2;
+  t->b1_off = 0;
+  t->b2_off = d.L * t->b_layer_bytes;
+  t->bias_off = 2 * d.L * t->b_layer_bytes;
+  t->n_bf16 = t->bias_off / 2;
+  t->n_f32 = d.L * 16;
+  t->blob_bytes = t->bias_off + t->n_f32 * 4;
+  t->tab_pi = d.tab_pi; t->tab_cond = d.tab_cond; t->tab_trans = d.tab_trans; t->n_tables = d.n_tables;
+  int off = (t->blob_bytes + 127) / 128 * 128;
+  t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
+  t->sm_slot = off;
+  t->sm_slot_stride = A1_BYTES + (d.K * TILE_M * 4 + 127) / 128 * 128;
+  off += 2 * t->sm_slot_stride;
+  t->sm_bar = off; off += 128;
+  t->sm_total = off;
+  (void)desc;
+  return t->sm_total <= 227 * 1024;
 }
-extern "C" int cnf_pack_weights_tc(const cnf_flow_desc*, const float*, const int32_t*, void*, void*) {
-  cnf_set_error("tensor-core path not available for this shape");
-  return CNF_E_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-int cnf_tc_apply(const cnf_flow_desc*, const void*, const int32_t*, const float*, float*, float*, int64_t, int,
-                 cudaStream_t) {
-  cnf_set_error("tensor-core path not available for this shape");
-  return CNF_E_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
+__host__ __device__ inline uint32_t make_idesc(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The loaded registers are named as in/out operands so that no use of them can be scheduled
+// above the wait (tcgen05.ld completes asynchronously).
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// {hi, lo} -> bf16x2 with ReLU: low 16 bits = lo (element 2i), high 16 bits = hi (element 2i+1)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void wg_sync(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
+               const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
+               int inverse, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
+  uint64_t* a1_ready = bars + 0;   // [2] epilogue -> MMA: A1 in smem (128 arrivals)
+  uint64_t* a2_ready = bars + 2;   // [2] epilogue -> MMA: A2 in TMEM (128 arrivals)
+  uint64_t* d1_ready = bars + 4;   // [2] MMA -> epilogue: D1 complete (tcgen05.commit)
+  uint64_t* d2_ready = bars + 6;   // [2] MMA -> epilogue: D2 complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < p.blob_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < p.n_tables; i += TC_THREADS) tab[i] = tables[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a1_ready + s, 128); mbar_init(a2_ready + s, 128);
+      mbar_init(d1_ready + s, 1);   mbar_init(d2_ready + s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();          // the weight image was written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
+  const int G = gridDim.x;
+  const int N1 = p.N1;
+  const int d2_col = N1 / 2;          // D2 lives just above the (in-place) bf16 copy of the hidden units
+
+  if (warp == 0) {
+    // ================================ MMA issuer ==============================================
+    if (lane == 0) {
+      int64_t total[2];
+      for (int s = 0; s < 2; ++s) {
+        const int64_t first = blockIdx.x + (int64_t)s * G;
+        total[s] = first < ntiles ? ((ntiles - first + 2 * G - 1) / (2 * G)) * p.L : 0;
+      }
+      int64_t it[2] = {0, 0};
+      int ph[2] = {0, 0};
+      const uint32_t idesc1 = make_idesc(N1), idesc2 = make_idesc(16);
+      const uint32_t lbo1 = (variant & 1) ? SBO1 : LBO1, sbo1 = (variant & 1) ? LBO1 : SBO1;
+      const uint32_t lbo2 = (variant & 1) ? SBO2 : LBO2, sbo2 = (variant & 1) ? LBO2 : SBO2;
+      const uint32_t smem_base = smem_u32(smem);
+      while (it[0] < total[0] || it[1] < total[1]) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (it[s] >= total[s]) continue;
+          const int li = (int)(it[s] % p.L);
+          const int l = inverse ? p.L - 1 - li : li;
+          const uint32_t par = (uint32_t)(it[s] & 1);
+          const uint32_t tm = tmem_base + s * 256;
+          if (ph[s] == 0) {
+            if (mbar_test(a1_ready + s, par)) {
+              tc_fence_after();
+              const uint64_t ad = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, lbo1, sbo1);
+              const uint64_t bd = make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, lbo1, sbo1);
+              mma_ss(tm, ad, bd, idesc1, 0u);
+              tc_commit(d1_ready + s);
+              ph[s] = 1;
+              progressed = true;
+            }
+          } else {
+            if (mbar_test(a2_ready + s, par)) {
+              tc_fence_after();
+              const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
+              for (int j = 0; j < N1 / 16; ++j)
+                mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + j * 512, lbo2, sbo2), idesc2, j > 0 ? 1u : 0u);
+              tc_commit(d2_ready + s);
+              ph[s] = 0;
+              ++it[s];
+              progressed = true;
+            }
+          }
+        }
+        if (!progressed) __nanosleep(20);   // do not starve the epilogue warps on this SMSP
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue warpgroups =====================================
+    const int slot = (warp - 4) >> 2;
+    const int t = tid - 128 * (1 + slot);             // sample row inside the tile == TMEM lane
+    uint8_t* a1 = smem + p.sm_slot + slot * p.sm_slot_stride;
+    float* act = reinterpret_cast<float*>(a1 + A1_BYTES);
+    const float* bias = reinterpret_cast<const float*>(smem + p.bias_off);
+    const uint32_t tm = tmem_base + slot * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    const int* pi_last = tab + p.tab_pi + p.L * p.K;
+    uint32_t it = 0;
+    const int a1_row = (t >> 3) * SBO1 + (t & 7) * 16;
+    const int col_s = 0, col_t = (p.nets & 1) ? 8 : 0;
+    for (int64_t tile = blockIdx.x + (int64_t)slot * G; tile < ntiles; tile += 2 * G) {
+      const int64_t base = tile * TILE_M;
+      // ---- tile load (coalesced) -> act[slot][sample] ---------------------------------------
+      {
+        const float* gp = xin + base * p.K;
+        const int64_t avail = (N - base) * (int64_t)p.K;
+        for (int e = t; e < TILE_M * p.K; e += 128) {
+          const int s = e / p.K, f = e - s * p.K;
+          const float v = (e < avail) ? __ldg(gp + e) : 0.f;
+          act[(inverse ? pi_last[f] : f) * TILE_M + s] = v;
+        }
+      }
+      wg_sync(slot);
+      float ld = 0.f;
+      for (int li = 0; li < p.L; ++li, ++it) {
+        const int l = inverse ? p.L - 1 - li : li;
+        const int* cond = tab + p.tab_cond + l * p.d1;
+        const int* trans = tab + p.tab_trans + l * p.d0;
+        // ---- A1 row: (u, 1, 0...) as 16 bf16 ------------------------------------------------
+        {
+          float u[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : (k == p.d1 ? 1.f : 0.f);
+          uint4 lo, hi;
+          lo.x = pack_bf16(u[0], u[1]);   lo.y = pack_bf16(u[2], u[3]);   lo.z = pack_bf16(u[4], u[5]);
+          lo.w = pack_bf16(u[6], u[7]);   hi.x = pack_bf16(u[8], u[9]);   hi.y = pack_bf16(u[10], u[11]);
+          hi.z = pack_bf16(u[12], u[13]); hi.w = pack_bf16(u[14], u[15]);
+          *reinterpret_cast<uint4*>(a1 + a1_row) = lo;
+          *reinterpret_cast<uint4*>(a1 + a1_row + LBO1) = hi;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(a1_ready + slot);
+        // ---- EPI1: relu + bf16, in place ----------------------------------------------------
+        mbar_wait(d1_ready + slot, it & 1);
+        tc_fence_after();
+        {
+          uint32_t ra[32], rb[32], pk[16];
+          tmem_ld32(tm, ra);
+          for (int c = 0; c < N1; c += 64) {
+            tmem_wait_ld32(ra);
+            if (c + 32 < N1) tmem_ld32(tm + c + 32, rb);
+            if (variant & 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(ra[2 * i + 1]), __uint_as_float(ra[2 * i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+            }
+            tmem_st16(tm + c / 2, pk);
+            if (c + 32 < N1) {
+              tmem_wait_ld32(rb);
+              if (c + 64 < N1) tmem_ld32(tm + c + 64, ra);
+              if (variant & 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rb[2 * i + 1]), __uint_as_float(rb[2 * i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+              }
+              tmem_st16(tm + c / 2 + 16, pk);
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a2_ready + slot);
+        // ---- EPI2: coupling update in fp32 --------------------------------------------------
+        mbar_wait(d2_ready + slot, it & 1);
+        tc_fence_after();
+        {
+          uint32_t r[16];
+          tmem_ld16(tm + d2_col, r);
+          tmem_wait_ld16(r);
+          const float* bl = bias + l * 16;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q < p.d0) {
+              const int ps = trans[q];
+              const float sv = (p.nets & 1) ? __uint_as_float(r[col_s + q]) + bl[col_s + q] : 0.f;
+              const float tv = (p.nets & 2) ? __uint_as_float(r[col_t + q]) + bl[col_t + q] : 0.f;
+              const float xv = act[ps * TILE_M + t];
+              float yv;
+              if (!inverse) { yv = xv * expf(sv) + tv; ld += sv; }
+              else          { yv = (xv - tv) * expf(-sv); ld -= sv; }
+              act[ps * TILE_M + t] = yv;
+            }
+          }
+        }
+      }
+      if (base + t < N) logdet[base + t] = ld;
+      wg_sync(slot);
+      {
+        float* gp = zout + base * p.K;
+        const int64_t avail = (N - base) * (int64_t)p.K;
+        for (int e = t; e < TILE_M * p.K; e += 128) {
+          const int s = e / p.K, f = e - s * p.K;
+          if (e < avail) gp[e] = act[(inverse ? f : pi_last[f]) * TILE_M + s];
+        }
+      }
+      wg_sync(slot);
+    }
+  }
+  // ---- teardown -----------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int g_tc_sms = -1;
+
+}  // namespace
+
+long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d) {
+  TcDims t;
+  return tc_dims(desc, d, &t) ? (long long)t.blob_bytes : 0;
+}
+
+// gather_tc: entry i < n_bf16 addresses bf16 element i of the B1/B2 image; the remaining n_f32
+// entries address the fp32 last-layer biases.  -1 = zero.  Length = cnf_tc_gather_len().
+extern "C" int cnf_tc_gather_len(const cnf_flow_desc* desc, int64_t* n) {
+  CnfDims d; TcDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!n) { cnf_set_error("null out"); return CNF_E_ARG; }
+  *n = tc_dims(desc, d, &t) ? (int64_t)t.n_bf16 + t.n_f32 : 0;
+  return CNF_OK;
+}
+
+extern "C" int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* g) {
+  CnfDims d; TcDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
+  if (!g) { cnf_set_error("null output"); return CNF_E_ARG; }
+  const int K = d.K, half = K / 2, H = d.H[0], Hp = d.Hp[0];
+  for (int i = 0; i < t.n_bf16 + t.n_f32; ++i) g[i] = -1;
+  // canonical flat offsets of one net: W0 [H,K], b0 [H], W1 [K,H], b1 [K]
+  const long long net_sz = (long long)H * K + H + (long long)K * H + K;
+  for (int l = 0; l < d.L; ++l) {
+    int slot = 0;
+    for (int net = 0; net < 2; ++net) {
+      if (!(d.nets & (1 << net))) continue;
+      const long long base = ((long long)l * d.n_nets + slot) * net_sz;
+      const long long w0 = base, b0 = base + (long long)H * K, w1 = b0 + H, b1 = w1 + (long long)K * H;
+      // B1 image: element (n, k), n = slot*Hp + h
+      int32_t* B1 = g + (t.b1_off + l * t.b_layer_bytes) / 2;
+      for (int h = 0; h < H; ++h) {
+        const int n = slot * Hp + h;
+        for (int k = 0; k <= d.d1; ++k) {
+          const int byte = (n / 8) * SBO1 + (k / 8) * LBO1 + (n % 8) * 16 + (k % 8) * 2;
+          B1[byte / 2] = (int32_t)(k < d.d1 ? w0 + (long long)h * K + half + k : b0 + h);
+        }
+      }
+      // B2 image: element (n2, kk), n2 = slot*8 + q, kk = slot*Hp + h
+      int32_t* B2 = g + (t.b2_off + l * t.b_layer_bytes) / 2;
+      for (int q = 0; q < d.d0; ++q) {
+        const int n2 = slot * 8 + q;
+        for (int h = 0; h < H; ++h) {
+          const int kk = slot * Hp + h;
+          const int byte = (kk / 16) * 512 + ((kk % 16) / 8) * LBO2 + (n2 / 8) * SBO2 + (n2 % 8) * 16 + (kk % 8) * 2;
+          B2[byte / 2] = (int32_t)(w1 + (long long)q * H + h);
+        }
+        g[t.n_bf16 + l * 16 + n2] = (int32_t)(b1 + q);
+      }
+      ++slot;
+    }
+  }
+  return CNF_OK;
+}
+
+namespace {
+__global__ void gather_f32_kernel(const float* __restrict__ flat, const int* __restrict__ gather, float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int gi = gather[i]; out[i] = gi >= 0 ? flat[gi] : 0.f; }
+}
+}  // namespace
+
+extern "C" int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat, const int32_t* gather_tc,
+                                   void* packed_tc, void* stream) {
+  CnfDims d; TcDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
+  if (!flat || !gather_tc || !packed_tc) { cnf_set_error("cnf_pack_weights_tc: null pointer"); return CNF_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = cnf_pack_bf16(flat, gather_tc, packed_tc, t.n_bf16, st))) return rc;
+  gather_f32_kernel<<<(t.n_f32 + 127) / 128, 128, 0, st>>>(flat, gather_tc + t.n_bf16,
+                                                           reinterpret_cast<float*>((uint8_t*)packed_tc + t.bias_off), t.n_f32);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                 float* logdet, int64_t N, int inverse, cudaStream_t st) {
+  CnfDims d; TcDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
+  if (N == 0) return CNF_OK;
+  if (!packed_tc || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  if (g_tc_sms < 0) {
+    int dev = 0, s = 0;
+    CNF_CHECK_CUDA(cudaGetDevice(&dev));
+    CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
+    g_tc_sms = s;
+  }
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+  const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
+  const int grid = (int)(ntiles < g_tc_sms ? ntiles : g_tc_sms);
+  int variant = 0;
+  if (const char* v = getenv("CNF_TC_VARIANT")) variant = atoi(v);
+  flow_tc_kernel<<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse,
+                                                       variant);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
 }
