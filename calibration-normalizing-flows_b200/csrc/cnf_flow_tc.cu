@@ -40,7 +40,7 @@ struct TcDims {
   int n_bf16, n_f32, blob_bytes;
   int tab_pi, tab_cond, tab_trans, n_tables;
   // shared-memory carve-up (bytes)
-  int sm_tab, sm_slot, sm_slot_stride, sm_bar, sm_total;
+  int sm_tab, sm_slot, sm_slot_stride, sm_act, sm_raw_in, sm_raw_out, sm_bar, sm_total;
 };
 
 bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
@@ -61,7 +61,13 @@ bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
   int off = (t->blob_bytes + 127) / 128 * 128;
   t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
   t->sm_slot = off;
-  t->sm_slot_stride = A1_BYTES + (d.K * TILE_M * 4 + 127) / 128 * 128;
+  {
+    const int tile_bytes = (d.K * TILE_M * 4 + 127) / 128 * 128;
+    t->sm_act = A1_BYTES;                       // offsets inside one slot
+    t->sm_raw_in = t->sm_act + tile_bytes;      // cp.async landing zone of the NEXT tile (row-major)
+    t->sm_raw_out = t->sm_raw_in + tile_bytes;  // row-major staging of the finished tile
+    t->sm_slot_stride = t->sm_raw_out + tile_bytes;
+  }
   off += 2 * t->sm_slot_stride;
   t->sm_bar = off; off += 128;
   t->sm_total = off;
@@ -195,19 +201,43 @@ __device__ __forceinline__ void wg_sync(int slot) { asm volatile("bar.sync %0, 1
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+// EPI selects how EPI1 turns fp32 hidden units into the bf16 A operand of GEMM2:
+//   0: cvt.rn.relu.bf16x2.f32 (round to nearest; F2FP runs on the quarter-rate XU pipe)
+//   1: byte-permute truncation + packed bf16 max(.,0); the mean shrink of truncation
+//      (E[ulp loss] ~ 0.72 * 2^-9 relative) is compensated on the fp32 GEMM2 output.
+template <int EPI>
+__device__ __forceinline__ uint32_t pack_hidden(uint32_t lo, uint32_t hi) {
+  if (EPI == 0) return pack_relu_bf16(__uint_as_float(lo), __uint_as_float(hi));
+  const uint32_t pk = __byte_perm(lo, hi, 0x7632);
+  __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&pk);
+  const uint32_t zero = 0u;
+  v = __hmax2(v, *reinterpret_cast<const __nv_bfloat162*>(&zero));
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
-               int inverse, int variant) {
+               int inverse, int io16) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
-  uint64_t* a1_ready = bars + 0;   // [2] epilogue -> MMA: A1 in smem (128 arrivals)
-  uint64_t* a2_ready = bars + 2;   // [2] epilogue -> MMA: A2 in TMEM (128 arrivals)
-  uint64_t* d1_ready = bars + 4;   // [2] MMA -> epilogue: D1 complete (tcgen05.commit)
-  uint64_t* d2_ready = bars + 6;   // [2] MMA -> epilogue: D2 complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* a1_ready = bars + 0;   // [2] epilogue -> MMA: A1 in smem (128 arrivals, once per layer)
+  uint64_t* d1_ready = bars + 2;   // [2] MMA -> epilogue: D1 complete (tcgen05.commit)
+  uint64_t* d2_ready = bars + 4;   // [2] MMA -> epilogue: D2 complete
+  // [2][4] epilogue -> MMA: group g (64 hidden columns) is in TMEM.  One barrier per group, each
+  // completing once per layer: a waiter may be at most one phase behind an mbarrier, and the
+  // epilogue can run several groups ahead of the issuing thread.
+  uint64_t* a2_ready = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   // ---- one-time setup ---------------------------------------------------------------------
   {
@@ -215,15 +245,21 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < p.blob_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     for (int i = tid; i < p.n_tables; i += TC_THREADS) tab[i] = tables[i];
+    // A1 tiles start as zeros; the constant-one (bias) column is written once below.
+    for (int s = 0; s < 2; ++s) {
+      uint4* a1z = reinterpret_cast<uint4*>(smem + p.sm_slot + s * p.sm_slot_stride);
+      for (int i = tid; i < A1_BYTES / 16; i += TC_THREADS) a1z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a1_ready + s, 128); mbar_init(a2_ready + s, 128);
+      mbar_init(a1_ready + s, 128);
       mbar_init(d1_ready + s, 1);   mbar_init(d2_ready + s, 1);
+      for (int g = 0; g < 4; ++g) mbar_init(a2_ready + 4 * s + g, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -237,55 +273,42 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int G = gridDim.x;
   const int N1 = p.N1;
-  const int d2_col = N1 / 2;          // D2 lives just above the (in-place) bf16 copy of the hidden units
+  const int n_grp = (N1 + 63) / 64;   // EPI1 hands the hidden units to GEMM2 in groups of 64 columns
+  // D2 (16 columns) goes above D1 when the 256-column slot has room; otherwise it reuses D1
+  // columns [N1/2, N1/2+16) and GEMM2 may only start once EPI1 has consumed them (group g_first).
+  const bool d2_above = (N1 + 16 <= 256);
+  const int d2_col = d2_above ? N1 : N1 / 2;
+  const int g_first = d2_above ? 0 : (N1 / 2 + 15) / 64;
 
-  if (warp == 0) {
-    // ================================ MMA issuer ==============================================
+  if (warp < 2) {
+    // ================================ MMA issuers: warp s drives slot s ========================
     if (lane == 0) {
-      int64_t total[2];
-      for (int s = 0; s < 2; ++s) {
-        const int64_t first = blockIdx.x + (int64_t)s * G;
-        total[s] = first < ntiles ? ((ntiles - first + 2 * G - 1) / (2 * G)) * p.L : 0;
-      }
-      int64_t it[2] = {0, 0};
-      int ph[2] = {0, 0};
+      const int s = warp;
+      const int64_t first = blockIdx.x + (int64_t)s * G;
+      const int64_t total = first < ntiles ? ((ntiles - first + 2 * G - 1) / (2 * G)) * p.L : 0;
       const uint32_t idesc1 = make_idesc(N1), idesc2 = make_idesc(16);
-      const uint32_t lbo1 = (variant & 1) ? SBO1 : LBO1, sbo1 = (variant & 1) ? LBO1 : SBO1;
-      const uint32_t lbo2 = (variant & 1) ? SBO2 : LBO2, sbo2 = (variant & 1) ? LBO2 : SBO2;
       const uint32_t smem_base = smem_u32(smem);
-      while (it[0] < total[0] || it[1] < total[1]) {
-        bool progressed = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (it[s] >= total[s]) continue;
-          const int li = (int)(it[s] % p.L);
-          const int l = inverse ? p.L - 1 - li : li;
-          const uint32_t par = (uint32_t)(it[s] & 1);
-          const uint32_t tm = tmem_base + s * 256;
-          if (ph[s] == 0) {
-            if (mbar_test(a1_ready + s, par)) {
-              tc_fence_after();
-              const uint64_t ad = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, lbo1, sbo1);
-              const uint64_t bd = make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, lbo1, sbo1);
-              mma_ss(tm, ad, bd, idesc1, 0u);
-              tc_commit(d1_ready + s);
-              ph[s] = 1;
-              progressed = true;
-            }
-          } else {
-            if (mbar_test(a2_ready + s, par)) {
-              tc_fence_after();
-              const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
-              for (int j = 0; j < N1 / 16; ++j)
-                mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + j * 512, lbo2, sbo2), idesc2, j > 0 ? 1u : 0u);
-              tc_commit(d2_ready + s);
-              ph[s] = 0;
-              ++it[s];
-              progressed = true;
-            }
-          }
+      const uint32_t tm = tmem_base + s * 256;
+      const uint64_t ad = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, LBO1, SBO1);
+      int li = 0;
+      for (int64_t it = 0; it < total; ++it) {
+        const int l = inverse ? p.L - 1 - li : li;
+        mbar_wait(a1_ready + s, (uint32_t)(it & 1));
+        tc_fence_after();
+        mma_ss(tm, ad, make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, LBO1, SBO1), idesc1, 0u);
+        tc_commit(d1_ready + s);
+        const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
+        int j = 0;
+        for (int g = 0; g < n_grp; ++g) {
+          mbar_wait(a2_ready + 4 * s + g, (uint32_t)(it & 1));
+          if (g < g_first) continue;
+          tc_fence_after();
+          const int j1 = min(4 * g + 4, N1 / 16);
+          for (; j < j1; ++j)
+            mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + j * 512, LBO2, SBO2), idesc2, j > 0 ? 1u : 0u);
         }
-        if (!progressed) __nanosleep(20);   // do not starve the epilogue warps on this SMSP
+        tc_commit(d2_ready + s);
+        if (++li == p.L) li = 0;
       }
     }
     __syncwarp();
@@ -294,47 +317,92 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
     const int slot = (warp - 4) >> 2;
     const int t = tid - 128 * (1 + slot);             // sample row inside the tile == TMEM lane
     uint8_t* a1 = smem + p.sm_slot + slot * p.sm_slot_stride;
-    float* act = reinterpret_cast<float*>(a1 + A1_BYTES);
+    float* act = reinterpret_cast<float*>(a1 + p.sm_act);
+    float* raw_in = reinterpret_cast<float*>(a1 + p.sm_raw_in);
+    float* raw_out = reinterpret_cast<float*>(a1 + p.sm_raw_out);
     const float* bias = reinterpret_cast<const float*>(smem + p.bias_off);
     const uint32_t tm = tmem_base + slot * 256 + ((uint32_t)((warp & 3) * 32) << 16);
     const int* pi_last = tab + p.tab_pi + p.L * p.K;
     uint32_t it = 0;
-    const int a1_row = (t >> 3) * SBO1 + (t & 7) * 16;
-    const int col_s = 0, col_t = (p.nets & 1) ? 8 : 0;
-    for (int64_t tile = blockIdx.x + (int64_t)slot * G; tile < ntiles; tile += 2 * G) {
+    uint8_t* a1_row = a1 + (t >> 3) * SBO1 + (t & 7) * 16;
+    const bool both = (p.nets == 3);
+    const int K = p.K, tile_elems = TILE_M * p.K;
+    // truncation shrinks every hidden unit by ~0.72*2^-9 on average; undo it on the fp32 output
+    const float comp = (EPI == 1) ? 1.0f + 0.72f / 512.0f : 1.0f;
+    const uint32_t one_bits = 0x3f80u;   // bf16 1.0
+    // (s, f) walk of e = t + 128*i without integer division
+    const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
+    auto prefetch = [&](int64_t tile) {   // row-major copy of a FULL tile, 16 B per cp.async
+      const float* gp = xin + tile * TILE_M * (int64_t)K;
+      for (int c = t; c < tile_elems / 4; c += 128) cp_async16(raw_in + 4 * c, gp + 4 * c);
+      cp_async_commit();
+    };
+    const int64_t tile0 = blockIdx.x + (int64_t)slot * G;
+    bool prefetched = false;
+    if (io16 && tile0 < ntiles && (tile0 + 1) * TILE_M <= N) { prefetch(tile0); prefetched = true; }
+    for (int64_t tile = tile0; tile < ntiles; tile += 2 * G) {
       const int64_t base = tile * TILE_M;
-      // ---- tile load (coalesced) -> act[slot][sample] ---------------------------------------
-      {
-        const float* gp = xin + base * p.K;
-        const int64_t avail = (N - base) * (int64_t)p.K;
-        for (int e = t; e < TILE_M * p.K; e += 128) {
-          const int s = e / p.K, f = e - s * p.K;
+      // ---- tile -> act[slot][sample] (transposing) --------------------------------------------
+      if (prefetched) {
+        cp_async_wait_all();
+        wg_sync(slot);
+        int s = s0, f = f0;
+        for (int e = t; e < tile_elems; e += 128) {
+          act[(inverse ? pi_last[f] : f) * TILE_M + s] = raw_in[e];
+          s += ds; f += df;
+          if (f >= K) { f -= K; ++s; }
+        }
+      } else {
+        const float* gp = xin + base * K;
+        const int64_t avail = (N - base) * (int64_t)K;
+        int s = s0, f = f0;
+        for (int e = t; e < tile_elems; e += 128) {
           const float v = (e < avail) ? __ldg(gp + e) : 0.f;
           act[(inverse ? pi_last[f] : f) * TILE_M + s] = v;
+          s += ds; f += df;
+          if (f >= K) { f -= K; ++s; }
         }
       }
       wg_sync(slot);
+      {
+        const int64_t nxt = tile + 2 * G;
+        prefetched = false;
+        if (io16 && nxt < ntiles && (nxt + 1) * TILE_M <= N) { prefetch(nxt); prefetched = true; }
+      }
       float ld = 0.f;
       for (int li = 0; li < p.L; ++li, ++it) {
         const int l = inverse ? p.L - 1 - li : li;
         const int* cond = tab + p.tab_cond + l * p.d1;
         const int* trans = tab + p.tab_trans + l * p.d0;
-        // ---- A1 row: (u, 1, 0...) as 16 bf16 ------------------------------------------------
+        // ---- A1 row: conditioning logits as bf16 + the constant one (independent loads) -------
         {
-          float u[16];
+          float u[8];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : (k == p.d1 ? 1.f : 0.f);
-          uint4 lo, hi;
-          lo.x = pack_bf16(u[0], u[1]);   lo.y = pack_bf16(u[2], u[3]);   lo.z = pack_bf16(u[4], u[5]);
-          lo.w = pack_bf16(u[6], u[7]);   hi.x = pack_bf16(u[8], u[9]);   hi.y = pack_bf16(u[10], u[11]);
-          hi.z = pack_bf16(u[12], u[13]); hi.w = pack_bf16(u[14], u[15]);
-          *reinterpret_cast<uint4*>(a1 + a1_row) = lo;
-          *reinterpret_cast<uint4*>(a1 + a1_row + LBO1) = hi;
+          for (int k = 0; k < 8; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : 0.f;
+          uint4 lo;
+          lo.x = pack_bf16(u[0], u[1]); lo.y = pack_bf16(u[2], u[3]);
+          lo.z = pack_bf16(u[4], u[5]); lo.w = pack_bf16(u[6], u[7]);
+          if (p.d1 < 8) {
+            const uint32_t ob = one_bits << ((p.d1 & 1) * 16);
+            const int wi = p.d1 >> 1;
+            lo.x |= (wi == 0) ? ob : 0u; lo.y |= (wi == 1) ? ob : 0u;
+            lo.z |= (wi == 2) ? ob : 0u; lo.w |= (wi == 3) ? ob : 0u;
+          }
+          *reinterpret_cast<uint4*>(a1_row) = lo;
+          if (p.d1 >= 8) {      // K >= 15: second k-half carries u_8.. and the one
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (k + 8 < p.d1) ? act[cond[k + 8] * TILE_M + t] : (k + 8 == p.d1 ? 1.f : 0.f);
+            uint4 hi;
+            hi.x = pack_bf16(v[0], v[1]); hi.y = pack_bf16(v[2], v[3]);
+            hi.z = pack_bf16(v[4], v[5]); hi.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a1_row + LBO1) = hi;
+          }
         }
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(a1_ready + slot);
-        // ---- EPI1: relu + bf16, in place ----------------------------------------------------
+        // ---- EPI1: relu + bf16, in place, handed to GEMM2 64 columns at a time ------------------
         mbar_wait(d1_ready + slot, it & 1);
         tc_fence_after();
         {
@@ -343,71 +411,85 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
           for (int c = 0; c < N1; c += 64) {
             tmem_wait_ld32(ra);
             if (c + 32 < N1) tmem_ld32(tm + c + 32, rb);
-            if (variant & 2) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(ra[2 * i + 1]), __uint_as_float(ra[2 * i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
-            }
+            for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(ra[2 * i], ra[2 * i + 1]);
             tmem_st16(tm + c / 2, pk);
             if (c + 32 < N1) {
               tmem_wait_ld32(rb);
               if (c + 64 < N1) tmem_ld32(tm + c + 64, ra);
-              if (variant & 2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rb[2 * i + 1]), __uint_as_float(rb[2 * i]));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
-              }
+              for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(rb[2 * i], rb[2 * i + 1]);
               tmem_st16(tm + c / 2 + 16, pk);
             }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(a2_ready + 4 * slot + (c >> 6));
           }
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(a2_ready + slot);
         // ---- EPI2: coupling update in fp32 --------------------------------------------------
+        float xv[8];
+        int ps[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          ps[q] = (q < p.d0) ? trans[q] * TILE_M + t : t;
+          xv[q] = act[ps[q]];
+        }
+        const float* bl = bias + l * 16;
         mbar_wait(d2_ready + slot, it & 1);
         tc_fence_after();
         {
           uint32_t r[16];
           tmem_ld16(tm + d2_col, r);
           tmem_wait_ld16(r);
-          const float* bl = bias + l * 16;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (q < p.d0) {
-              const int ps = trans[q];
-              const float sv = (p.nets & 1) ? __uint_as_float(r[col_s + q]) + bl[col_s + q] : 0.f;
-              const float tv = (p.nets & 2) ? __uint_as_float(r[col_t + q]) + bl[col_t + q] : 0.f;
-              const float xv = act[ps * TILE_M + t];
+              // columns 0..7 belong to the first present net, 8..15 to the second
+              const float first = fmaf(__uint_as_float(r[q]), comp, bl[q]);
+              const float second = fmaf(__uint_as_float(r[8 + q]), comp, bl[8 + q]);
+              const float sv = (p.nets & 1) ? first : 0.f;
+              const float tv = both ? second : ((p.nets & 2) ? first : 0.f);
               float yv;
-              if (!inverse) { yv = xv * expf(sv) + tv; ld += sv; }
-              else          { yv = (xv - tv) * expf(-sv); ld -= sv; }
-              act[ps * TILE_M + t] = yv;
+              if (!inverse) { yv = xv[q] * expf(sv) + tv; ld += sv; }
+              else          { yv = (xv[q] - tv) * expf(-sv); ld -= sv; }
+              act[ps[q]] = yv;
             }
           }
         }
       }
       if (base + t < N) logdet[base + t] = ld;
-      wg_sync(slot);
+      // ---- act -> row-major staging -> coalesced global store ---------------------------------
       {
-        float* gp = zout + base * p.K;
-        const int64_t avail = (N - base) * (int64_t)p.K;
-        for (int e = t; e < TILE_M * p.K; e += 128) {
-          const int s = e / p.K, f = e - s * p.K;
-          if (e < avail) gp[e] = act[(inverse ? f : pi_last[f]) * TILE_M + s];
+        int s = s0, f = f0;
+        const bool full = io16 && (base + TILE_M <= N);
+        float* gp = zout + base * K;
+        const int64_t avail = (N - base) * (int64_t)K;
+        if (full) {
+          wg_sync(slot);                       // every row of act is final
+          for (int e = t; e < tile_elems; e += 128) {
+            raw_out[e] = act[(inverse ? f : pi_last[f]) * TILE_M + s];
+            s += ds; f += df;
+            if (f >= K) { f -= K; ++s; }
+          }
+          wg_sync(slot);
+          for (int c = t; c < tile_elems / 4; c += 128)
+            *reinterpret_cast<float4*>(gp + 4 * c) = *reinterpret_cast<const float4*>(raw_out + 4 * c);
+        } else {
+          wg_sync(slot);
+          for (int e = t; e < tile_elems; e += 128) {
+            if (e < avail) gp[e] = act[(inverse ? f : pi_last[f]) * TILE_M + s];
+            s += ds; f += df;
+            if (f >= K) { f -= K; ++s; }
+          }
+          wg_sync(slot);
         }
       }
-      wg_sync(slot);
     }
   }
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
@@ -510,13 +592,19 @@ int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t
     CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
     g_tc_sms = s;
   }
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int grid = (int)(ntiles < g_tc_sms ? ntiles : g_tc_sms);
-  int variant = 0;
-  if (const char* v = getenv("CNF_TC_VARIANT")) variant = atoi(v);
-  flow_tc_kernel<<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse,
-                                                       variant);
+  // 16-byte tile I/O needs 16 B-aligned pointers and whole tiles that are a multiple of 16 B
+  const int io16 = (((uintptr_t)x | (uintptr_t)z) % 16 == 0 && (TILE_M * d.K) % 4 == 0) ? 1 : 0;
+  int epi = 0;
+  if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
+  if (epi == 0) {
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    flow_tc_kernel<0><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16);
+  } else {
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    flow_tc_kernel<1><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16);
+  }
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
