@@ -136,3 +136,64 @@ def test_pi_maps_even_odd():
     assert list(pi[0]) == [0, 1, 2, 3, 4]
     assert list(pi[1]) == [4, 3, 2, 1, 0]
     assert list(pi[2]) == [0, 1, 2, 3, 4]
+
+
+def _c_oracle():
+    import ctypes
+    import os
+    import subprocess
+    from conftest import ROOT
+    so = os.path.join(ROOT, 'oracle', '_ref', 'libcnf_oracle.so')
+    if not os.path.exists(so):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize('name', golden_flow_names())
+def test_c_oracle_matches_reference(name):
+    """The plain-C restatement (oracle/cnf_oracle.c) against the reference's float64 outputs."""
+    import ctypes
+    lib = _c_oracle()
+    g = load_golden('flow_' + name)
+    K, L, N = int(g['K']), int(g['L']), g['x'].shape[0]
+    H = np.ascontiguousarray(g['hidden'], dtype=np.int32)
+    perm = np.ascontiguousarray(g['perms'], dtype=np.int32) if int(g['random_flip']) else None
+    flat = np.ascontiguousarray(g['flat'], dtype=np.float64)
+    x = np.ascontiguousarray(g['x'], dtype=np.float64)
+    z, ld, zs = np.empty((N, K)), np.empty(N), np.empty((L, N, K))
+    vp = ctypes.c_void_p
+
+    def ptr(a):
+        return a.ctypes.data_as(vp) if a is not None else None
+
+    rc = lib.cnf_oracle_forward(K, L, len(H), ptr(H), int(g['scale']), int(g['shift']), ptr(perm), ptr(flat), ptr(x),
+                                ptr(z), ptr(ld), ptr(zs), ctypes.c_long(N))
+    assert rc == 0
+    assert rel(z, g['z64']) < 1e-12
+    assert np.max(np.abs(ld - g['logdet64'])) < 1e-12 * max(1.0, np.max(np.abs(g['logdet64'])))
+    for l in range(L):
+        assert rel(zs[l], g['zs'][l]) < 5e-6
+    xr, ldi, xs = np.empty((N, K)), np.empty(N), np.empty((L, N, K))
+    zin = np.ascontiguousarray(g['zs'][-1], dtype=np.float64)
+    rc = lib.cnf_oracle_inverse(K, L, len(H), ptr(H), int(g['scale']), int(g['shift']), ptr(perm), ptr(flat),
+                                ptr(zin), ptr(xr), ptr(ldi), ptr(xs), ctypes.c_long(N))
+    assert rc == 0
+    for l in range(L):
+        assert rel(xs[l], g['xs'][l]) < 2e-5
+    assert np.max(np.abs(ldi - g['logdet_inv'])) < 5e-6 * max(1.0, np.max(np.abs(g['logdet_inv'])))
+
+
+def test_c_oracle_metrics_match_reference():
+    import ctypes
+    lib = _c_oracle()
+    g = load_golden('metrics')
+    for n in ('f64_k10', 'f64_k3', 'edges_f64'):
+        p = np.ascontiguousarray(g[n + '_probs'], dtype=np.float64)
+        y = np.ascontiguousarray(g[n + '_y'], dtype=np.int64)
+        st = np.empty(48)
+        lib.cnf_oracle_metrics(p.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p),
+                               ctypes.c_long(p.shape[0]), p.shape[1], 15, st.ctypes.data_as(ctypes.c_void_p))
+        ece = sum(abs(st[30 + i] / st[i] - st[15 + i] / st[i]) * st[i] for i in range(15) if st[i] > 0) / st[47]
+        assert abs(ece - g[n + '_ece15']) < 1e-6   # reference averages float32 hit flags
+        assert abs(st[45] / st[47] - g[n + '_nll']) < 1e-9
+        assert st[46] / st[47] == g[n + '_acc']
