@@ -45,23 +45,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms; falls back
+    to polling nvidia-smi when pynvml is unavailable)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(',') if v.strip() != '']
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def _run(self):
+        n = self.nvml
         while not self.stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(',')])
+                if n is not None:
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                        n, 'nvmlDeviceGetCurrentClocksEventReasons') else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.rows.append((mhz, self.max_mhz, r))
+                    self.stop.wait(0.005)
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index),
+                                          '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active',
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                         timeout=5).stdout.strip().split(',')
+                    self.rows.append((float(out[0]), float(out[1]), int(out[2].strip(), 16)))
+                    self.stop.wait(0.05)
             except Exception:
-                pass
-            self.stop.wait(0.1)
+                self.stop.wait(0.05)
 
     def __enter__(self):
         self.t.start()
@@ -72,19 +97,13 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+        # NVML clocks-event-reason bits
+        bits = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20,
+                'hw_thermal_slowdown': 0x40, 'hw_power_brake_slowdown': 0x80}
+        sm = sorted(r[0] for r in self.rows)
+        mx = max((r[1] for r in self.rows), default=None)
+        reasons = sorted({name for r in self.rows for name, b in bits.items() if r[2] & b})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons,
                 'samples': len(sm)}
 
 
@@ -277,8 +296,13 @@ def run_ours(args):
 
     hbm, tf, src = peaks()
     ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
-    roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
-            'kernel': 'flow_tc_kernel' if precision == 'bf16' else 'flow_apply_kernel', 'peak_source': src,
+    kname = 'flow_tc_kernel' if precision == 'bf16' else 'flow_apply_kernel'
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from ncu --set full
+        traffic = json.load(open(tpath)).get(kname)
+    roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': traffic,
+            'kernel': kname, 'peak_source': src,
             'note': 'algorithmic bytes 84 B/sample x 1e6 samples per launch'}
     ach_tf = FLOPS_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e12
     roof_tensor = {'bound': 'tensor', 'achieved': ach_tf, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach_tf / tf,
@@ -309,7 +333,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='auto', choices=['auto', 'fp32', 'bf16'])

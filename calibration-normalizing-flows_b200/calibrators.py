@@ -61,6 +61,11 @@ def _dist():
     return None
 
 
+def shard_bounds(n, rank, world):
+    """Contiguous row block [lo, hi) of rank `rank` when n samples are split over `world` ranks."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
 class FusedNLLTrainer:
     """The calibrator's optimisation loop on device buffers.  Data-parallel when
     torch.distributed is initialised: every rank holds a contiguous shard of the samples, the
@@ -155,7 +160,7 @@ class TorchFlowCalibrator(Calibrator):
         if dist is not None:
             # contiguous row blocks per rank; every rank was given the full arrays
             rank, world = dist.get_rank(), dist.get_world_size()
-            lo, hi = (n_all * rank) // world, (n_all * (rank + 1)) // world
+            lo, hi = shard_bounds(n_all, rank, world)
             logits, target = logits[lo:hi], target[lo:hi]
         x = logits.to(self.dev).contiguous()
         y = target.to(self.dev).contiguous()

@@ -1,0 +1,78 @@
+"""Multi-GPU data-parallel training on real devices (skipped with fewer than 2 GPUs): the NCCL
+all-reduced gradient and the resulting parameters equal the single-GPU full-batch run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import flow_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, 'oracle'), os.path.join(root, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    from cnf_b200.calibrators import FusedNLLTrainer, shard_bounds
+    from conftest import load_golden
+    from helpers import build_flow_from_golden
+    g = load_golden('flow_c2_nvp_k10_init')
+    N = 200_003
+    x, y = orc.synth_logits(N, 10, seed=21)
+    lo, hi = shard_bounds(N, rank, world)
+    flow = build_flow_from_golden(g, dev)
+    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev))
+    assert tr.n_total == N
+    losses = []
+    for _ in range(4):
+        tr.step()
+        losses.append(-float(tr.loss_acc[0]) / N)
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flat=flow.engine().flat.cpu().numpy(),
+             losses=np.array(losses), grad=flow.engine().flat_grad.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_two_gpu_dp_matches_single_gpu(tmp_path, cuda_device):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from cnf_b200.calibrators import FusedNLLTrainer
+    from conftest import load_golden
+    from helpers import build_flow_from_golden, rel_err
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [dict(np.load(os.path.join(str(tmp_path), 'rank%d.npz' % i))) for i in range(world)]
+    assert np.array_equal(r[0]['flat'], r[1]['flat'])           # identical update on every rank
+    g = load_golden('flow_c2_nvp_k10_init')
+    N = 200_003
+    x, y = orc.synth_logits(N, 10, seed=21)
+    flow = build_flow_from_golden(g, cuda_device)
+    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device))
+    losses = []
+    for _ in range(4):
+        tr.step()
+        losses.append(-float(tr.loss_acc[0]) / N)
+    assert np.allclose(losses, r[0]['losses'], rtol=1e-6, atol=1e-7)
+    assert rel_err(r[0]['grad'], flow.engine().flat_grad.cpu().numpy()) < 1e-4
+    disp = flow.engine().flat.cpu().numpy() - g['flat']
+    assert rel_err(r[0]['flat'] - g['flat'], disp) < 2e-2      # Adam normalises tiny gradients: compare displacements
