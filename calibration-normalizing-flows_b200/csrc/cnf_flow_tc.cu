@@ -27,7 +27,9 @@ int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n,
 
 namespace {
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_SLOTS = 3;                       // tiles in flight per CTA
+constexpr int TC_THREADS = 128 + 128 * TC_SLOTS;  // warps 0..2 MMA issuers, warp 3 TMEM allocator, then one epilogue warpgroup per slot
+constexpr int SLOT_COLS = 160;                    // TMEM columns per slot: D1 (<=128) + D2 (16), padded
 constexpr int TILE_M = 128;
 constexpr int A1_BYTES = TILE_M * 32;   // 128 rows x 16 bf16
 constexpr int LBO1 = 128, SBO1 = 256;   // A1 / B1: k-halves adjacent, 8-row groups 256 B apart
@@ -47,7 +49,7 @@ bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
   if (d.m != 1 || d.n_nets < 1) return false;
   if (d.d1 + 1 > 16 || d.d0 > 8) return false;
   const int N1 = d.n_nets * d.Hp[0];
-  if (N1 < 16 || N1 > 256) return false;
+  if (d.Hp[0] < 16 || d.Hp[0] > 128) return false;   // one net's hidden units fill at most 128 TMEM columns
   t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->Hp = d.Hp[0]; t->nets = d.nets; t->n_nets = d.n_nets;
   t->N1 = N1;
   t->b_layer_bytes = N1 * 16 * 2;
@@ -68,7 +70,7 @@ bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
     t->sm_raw_out = t->sm_raw_in + tile_bytes;  // row-major staging of the finished tile
     t->sm_slot_stride = t->sm_raw_out + tile_bytes;
   }
-  off += 2 * t->sm_slot_stride;
+  off += TC_SLOTS * t->sm_slot_stride;
   t->sm_bar = off; off += 128;
   t->sm_total = off;
   (void)desc;
@@ -230,14 +232,16 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
-  uint64_t* a1_ready = bars + 0;   // [2] epilogue -> MMA: A1 in smem (128 arrivals, once per layer)
-  uint64_t* d1_ready = bars + 2;   // [2] MMA -> epilogue: D1 complete (tcgen05.commit)
-  uint64_t* d2_ready = bars + 4;   // [2] MMA -> epilogue: D2 complete
-  // [2][4] epilogue -> MMA: group g (64 hidden columns) is in TMEM.  One barrier per group, each
-  // completing once per layer: a waiter may be at most one phase behind an mbarrier, and the
-  // epilogue can run several groups ahead of the issuing thread.
-  uint64_t* a2_ready = bars + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  // per slot s: a1_ready[s] (128 arrivals, once per layer)      epilogue -> MMA: A1 row block in smem
+  //             d1_ready[s] (commit, once per net phase)        MMA -> epilogue: this net's D1 is complete
+  //             a2_ready[2s+g] (128 arrivals, once per phase)   epilogue -> MMA: 64 more hidden columns in TMEM
+  //             d2_ready[s] (commit, once per layer)            MMA -> epilogue: D2 complete
+  // A waiter is never more than one phase behind any of them (see the hand-off order below).
+  uint64_t* a1_ready = bars;
+  uint64_t* d1_ready = bars + TC_SLOTS;
+  uint64_t* d2_ready = bars + 2 * TC_SLOTS;
+  uint64_t* a2_ready = bars + 3 * TC_SLOTS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 * TC_SLOTS);
 
   // ---- one-time setup ---------------------------------------------------------------------
   {
@@ -245,21 +249,18 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < p.blob_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     for (int i = tid; i < p.n_tables; i += TC_THREADS) tab[i] = tables[i];
-    // A1 tiles start as zeros; the constant-one (bias) column is written once below.
-    for (int s = 0; s < 2; ++s) {
-      uint4* a1z = reinterpret_cast<uint4*>(smem + p.sm_slot + s * p.sm_slot_stride);
-      for (int i = tid; i < A1_BYTES / 16; i += TC_THREADS) a1z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TC_SLOTS; ++s) {
       mbar_init(a1_ready + s, 128);
-      mbar_init(d1_ready + s, 1);   mbar_init(d2_ready + s, 1);
-      for (int g = 0; g < 4; ++g) mbar_init(a2_ready + 4 * s + g, 128);
+      mbar_init(d1_ready + s, 1);
+      mbar_init(d2_ready + s, 1);
+      mbar_init(a2_ready + 2 * s, 128);
+      mbar_init(a2_ready + 2 * s + 1, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -272,40 +273,42 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
 
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int G = gridDim.x;
-  const int N1 = p.N1;
-  const int n_grp = (N1 + 63) / 64;   // EPI1 hands the hidden units to GEMM2 in groups of 64 columns
-  // D2 (16 columns) goes above D1 when the 256-column slot has room; otherwise it reuses D1
-  // columns [N1/2, N1/2+16) and GEMM2 may only start once EPI1 has consumed them (group g_first).
-  const bool d2_above = (N1 + 16 <= 256);
-  const int d2_col = d2_above ? N1 : N1 / 2;
-  const int g_first = d2_above ? 0 : (N1 / 2 + 15) / 64;
+  const int Hp = p.Hp;                 // hidden units (TMEM columns of D1) per net phase
+  const int n_ph = p.n_nets;           // net phases per layer: s then t (or the single present net)
+  const int n_grp = (Hp + 63) / 64;    // EPI1 releases the hidden units to GEMM2 in groups of 64 columns
+  const int d2_col = 128;              // D2 sits above D1 inside the slot
 
-  if (warp < 2) {
+  if (warp < TC_SLOTS) {
     // ================================ MMA issuers: warp s drives slot s ========================
     if (lane == 0) {
       const int s = warp;
       const int64_t first = blockIdx.x + (int64_t)s * G;
-      const int64_t total = first < ntiles ? ((ntiles - first + 2 * G - 1) / (2 * G)) * p.L : 0;
-      const uint32_t idesc1 = make_idesc(N1), idesc2 = make_idesc(16);
+      const int64_t total = first < ntiles ? ((ntiles - first + TC_SLOTS * (int64_t)G - 1) / (TC_SLOTS * (int64_t)G)) * p.L : 0;
+      const uint32_t idesc1 = make_idesc(Hp), idesc2 = make_idesc(16);
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t tm = tmem_base + s * 256;
+      const uint32_t tm = tmem_base + s * SLOT_COLS;
       const uint64_t ad = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, LBO1, SBO1);
       int li = 0;
+      uint32_t cnt = 0;                // net phases issued so far on this slot
       for (int64_t it = 0; it < total; ++it) {
         const int l = inverse ? p.L - 1 - li : li;
+        const uint32_t b1 = smem_base + p.b1_off + l * p.b_layer_bytes;
+        const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
         mbar_wait(a1_ready + s, (uint32_t)(it & 1));
         tc_fence_after();
-        mma_ss(tm, ad, make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, LBO1, SBO1), idesc1, 0u);
-        tc_commit(d1_ready + s);
-        const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
-        int j = 0;
-        for (int g = 0; g < n_grp; ++g) {
-          mbar_wait(a2_ready + 4 * s + g, (uint32_t)(it & 1));
-          if (g < g_first) continue;
-          tc_fence_after();
-          const int j1 = min(4 * g + 4, N1 / 16);
-          for (; j < j1; ++j)
-            mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + j * 512, LBO2, SBO2), idesc2, j > 0 ? 1u : 0u);
+        for (int ph = 0; ph < n_ph; ++ph, ++cnt) {
+          // GEMM1 of this net: D1[128 x Hp] = A1 . B1[ph]^T   (rows ph*Hp.. of the B1 image)
+          mma_ss(tm, ad, make_desc(b1 + ph * (Hp / 8) * SBO1, LBO1, SBO1), idesc1, 0u);
+          tc_commit(d1_ready + s);
+          int j = 0;
+          for (int g = 0; g < n_grp; ++g) {
+            mbar_wait(a2_ready + 2 * s + g, cnt & 1);
+            tc_fence_after();
+            const int j1 = min(4 * g + 4, Hp / 16);
+            for (; j < j1; ++j)     // GEMM2 k-steps of this net accumulate into the shared 16-column D2
+              mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + (ph * (Hp / 16) + j) * 512, LBO2, SBO2), idesc2,
+                     (ph > 0 || j > 0) ? 1u : 0u);
+          }
         }
         tc_commit(d2_ready + s);
         if (++li == p.L) li = 0;
@@ -321,9 +324,9 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
     float* raw_in = reinterpret_cast<float*>(a1 + p.sm_raw_in);
     float* raw_out = reinterpret_cast<float*>(a1 + p.sm_raw_out);
     const float* bias = reinterpret_cast<const float*>(smem + p.bias_off);
-    const uint32_t tm = tmem_base + slot * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tm = tmem_base + slot * SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const int* pi_last = tab + p.tab_pi + p.L * p.K;
-    uint32_t it = 0;
+    uint32_t it = 0, cnt = 0;
     uint8_t* a1_row = a1 + (t >> 3) * SBO1 + (t & 7) * 16;
     const bool both = (p.nets == 3);
     const int K = p.K, tile_elems = TILE_M * p.K;
@@ -337,10 +340,13 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
       for (int c = t; c < tile_elems / 4; c += 128) cp_async16(raw_in + 4 * c, gp + 4 * c);
       cp_async_commit();
     };
+    // second k-half of the A1 row is constant unless d1 >= 8: zero it once
+    *reinterpret_cast<uint4*>(a1_row + LBO1) = make_uint4(0u, 0u, 0u, 0u);
     const int64_t tile0 = blockIdx.x + (int64_t)slot * G;
+    const int64_t tstep = (int64_t)TC_SLOTS * G;
     bool prefetched = false;
     if (io16 && tile0 < ntiles && (tile0 + 1) * TILE_M <= N) { prefetch(tile0); prefetched = true; }
-    for (int64_t tile = tile0; tile < ntiles; tile += 2 * G) {
+    for (int64_t tile = tile0; tile < ntiles; tile += tstep) {
       const int64_t base = tile * TILE_M;
       // ---- tile -> act[slot][sample] (transposing) --------------------------------------------
       if (prefetched) {
@@ -365,7 +371,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
       }
       wg_sync(slot);
       {
-        const int64_t nxt = tile + 2 * G;
+        const int64_t nxt = tile + tstep;
         prefetched = false;
         if (io16 && nxt < ntiles && (nxt + 1) * TILE_M <= N) { prefetch(nxt); prefetched = true; }
       }
@@ -402,31 +408,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(a1_ready + slot);
-        // ---- EPI1: relu + bf16, in place, handed to GEMM2 64 columns at a time ------------------
-        mbar_wait(d1_ready + slot, it & 1);
-        tc_fence_after();
-        {
-          uint32_t ra[32], rb[32], pk[16];
-          tmem_ld32(tm, ra);
-          for (int c = 0; c < N1; c += 64) {
-            tmem_wait_ld32(ra);
-            if (c + 32 < N1) tmem_ld32(tm + c + 32, rb);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(ra[2 * i], ra[2 * i + 1]);
-            tmem_st16(tm + c / 2, pk);
-            if (c + 32 < N1) {
-              tmem_wait_ld32(rb);
-              if (c + 64 < N1) tmem_ld32(tm + c + 64, ra);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(rb[2 * i], rb[2 * i + 1]);
-              tmem_st16(tm + c / 2 + 16, pk);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(a2_ready + 4 * slot + (c >> 6));
-          }
-        }
-        // ---- EPI2: coupling update in fp32 --------------------------------------------------
+        // pre-load what EPI2 needs while the tensor pipe works
         float xv[8];
         int ps[8];
 #pragma unroll
@@ -435,6 +417,31 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
           xv[q] = act[ps[q]];
         }
         const float* bl = bias + l * 16;
+        // ---- EPI1 per net phase: relu + bf16 in place, released 64 columns at a time -----------
+        for (int ph = 0; ph < n_ph; ++ph, ++cnt) {
+          mbar_wait(d1_ready + slot, cnt & 1);
+          tc_fence_after();
+          uint32_t ra[32], rb[32], pk[16];
+          tmem_ld32(tm, ra);
+          for (int c = 0; c < Hp; c += 64) {
+            tmem_wait_ld32(ra);
+            if (c + 32 < Hp) tmem_ld32(tm + c + 32, rb);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(ra[2 * i], ra[2 * i + 1]);
+            tmem_st16(tm + c / 2, pk);
+            if (c + 32 < Hp) {
+              tmem_wait_ld32(rb);
+              if (c + 64 < Hp) tmem_ld32(tm + c + 64, ra);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_hidden<EPI>(rb[2 * i], rb[2 * i + 1]);
+              tmem_st16(tm + c / 2 + 16, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(a2_ready + 2 * slot + (c >> 6));
+          }
+        }
+        // ---- EPI2: coupling update in fp32 --------------------------------------------------
         mbar_wait(d2_ready + slot, it & 1);
         tc_fence_after();
         {
@@ -489,7 +496,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
