@@ -92,6 +92,7 @@ __device__ __forceinline__ void chunk_from_inputs(float (&h)[SPT][CH], const flo
 #pragma unroll
       for (int r = 0; r < CH; ++r) h[k][r] = 0.f;
   }
+#pragma unroll 4
   for (int i = 0; i < n_in; ++i) {
     const int row = idx ? idx[i] : i;
     float xin[SPT];
@@ -118,6 +119,7 @@ template <int SPT, bool WS>
 __device__ __forceinline__ void chunk_to_outputs(const float (&h)[SPT][CH], const float* W, int ldw, const float* b,
                                                  int r0, int n_out, float* dst, const int* idx, bool init,
                                                  bool accumulate_always, int TSP, int tid, int NT) {
+#pragma unroll 2
   for (int o = 0; o < n_out; ++o) {
     const float* wrow = W + (size_t)o * ldw + r0;
     float acc[SPT];

@@ -27,141 +27,146 @@ struct BinCache {
   int bin; unsigned cnt, correct; double sconf;
 };
 
+// Confidence sums are kept in shared memory as 2^-40 fixed point in 64-bit integers: integer
+// atomics are native (a double atomicAdd on shared memory is a CAS loop that spins under the
+// contention of a popular bin) and make the per-CTA sum order-independent.  A CTA sums < 2^24.
+#define CNF_FX_SCALE 1099511627776.0 /* 2^40 */
 __device__ __forceinline__ void flush(BinCache& c, unsigned* s_cnt, unsigned* s_cor, double* s_conf) {
   if (c.bin >= 0 && c.cnt) {
     atomicAdd(s_cnt + c.bin, c.cnt);
     atomicAdd(s_cor + c.bin, c.correct);
-    atomicAdd(s_conf + c.bin, c.sconf);
+    atomicAdd(reinterpret_cast<unsigned long long*>(s_conf) + c.bin,
+              (unsigned long long)__double2ll_rn(c.sconf * CNF_FX_SCALE));
   }
   c.cnt = 0; c.correct = 0; c.sconf = 0.0;
 }
 
-// T = element type of the input rows; mode as CNF_METRICS_*.
-template <typename T, bool STAGED>
-__global__ void metrics_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, int64_t N, int K, int bins,
-                               int mode, const double* __restrict__ log_priors, const double* __restrict__ edges,
-                               double* __restrict__ acc, double* __restrict__ probs_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NT = blockDim.x, tid = threadIdx.x;
-  // layout: [edges T (bins+1)] [s_conf double bins] [s_cnt u32 bins] [s_cor u32 bins] [lp double K] [tile]
-  double* s_conf = reinterpret_cast<double*>(smem_raw);
-  double* s_lp = s_conf + bins;
-  T* s_edges = reinterpret_cast<T*>(s_lp + K);
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_edges + (bins + 2));
-  unsigned* s_cor = s_cnt + bins;
-  size_t off = reinterpret_cast<unsigned char*>(s_cor + bins) - smem_raw;
-  off = (off + 15) / 16 * 16;
-  T* tile = reinterpret_cast<T*>(smem_raw + off);
-  __shared__ double red[32];
-
-  for (int i = tid; i < bins; i += NT) { s_conf[i] = 0.0; s_cnt[i] = 0u; s_cor[i] = 0u; }
-  if (edges != nullptr)
-    for (int i = tid; i <= bins; i += NT) s_edges[i] = (T)edges[i];
-  if (log_priors != nullptr)
-    for (int i = tid; i < K; i += NT) s_lp[i] = log_priors[i];
-  __syncthreads();
-
-  BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
-  double a_nll = 0.0, a_correct = 0.0, a_n = 0.0;
-  const int64_t ntiles = (N + NT - 1) / NT;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * NT;
-    if (STAGED) {
-      const int64_t avail = (N - base) * (int64_t)K;
-      const int total = (int)(avail < (int64_t)NT * K ? avail : (int64_t)NT * K);
-      const T* gp = in + base * K;
-      __syncthreads();
-      for (int e = tid; e < total; e += NT) tile[skew(e)] = gp[e];
-      __syncthreads();
-    }
-    const int64_t n = base + tid;
-    if (n < N) {
-      const T* grow = in + n * K;
-      auto get = [&](int j) -> T { return STAGED ? tile[skew(tid * K + j)] : grow[j]; };
-      int yy = (y != nullptr) ? (int)y[n] : -1;
-      T conf, py;
-      int pred = 0;
-      if (mode == CNF_METRICS_PROBS) {
-        conf = get(0);
-        for (int j = 1; j < K; ++j) { T v = get(j); if (v > conf) { conf = v; pred = j; } }
-        py = (yy >= 0 && yy < K) ? get(yy) : (T)0;
-        a_nll -= (double)t_log<T>(py + (T)1e-7);
-      } else {
-        // float32 softmax of the logits (scipy.special.softmax on float32)
-        float mx = (float)get(0);
-        for (int j = 1; j < K; ++j) { float v = (float)get(j); if (v > mx) { mx = v; pred = j; } }
-        float se = 0.f;
-        for (int j = 0; j < K; ++j) se += expf((float)get(j) - mx);
-        if (mode == CNF_METRICS_LOGITS) {
-          // arg-max over the float32 probabilities: ties resolve to the first index
-          float best = -1.f; pred = 0;
-          for (int j = 0; j < K; ++j) { float p = expf((float)get(j) - mx) / se; if (p > best) { best = p; pred = j; } }
-          conf = (T)best;
-          float pyf = (yy >= 0 && yy < K) ? expf((float)get(yy) - mx) / se : 0.f;
-          py = (T)pyf;
-          a_nll -= (double)logf(pyf + 1e-7f);
-        } else {
-          // u_j = (double)log(p_j + 1e-7f) - log_prior_j ; float64 softmax of u
-          double umax = -INFINITY;
-          for (int j = 0; j < K; ++j) {
-            float p = expf((float)get(j) - mx) / se;
-            double u = (double)logf(p + 1e-7f) - s_lp[j];
-            if (u > umax) umax = u;
-          }
-          double sd = 0.0;
-          for (int j = 0; j < K; ++j) {
-            float p = expf((float)get(j) - mx) / se;
-            double u = (double)logf(p + 1e-7f) - s_lp[j];
-            sd += exp(u - umax);
-          }
-          double best = -1.0, pyd = 0.0; pred = 0;
-          for (int j = 0; j < K; ++j) {
-            float p = expf((float)get(j) - mx) / se;
-            double u = (double)logf(p + 1e-7f) - s_lp[j];
-            double q = exp(u - umax) / sd;
-            if (probs_out != nullptr) probs_out[n * K + j] = q;
-            if (q > best) { best = q; pred = j; }
-            if (j == yy) pyd = q;
-          }
-          conf = (T)best; py = (T)pyd;
-          // calibrated probabilities are float64 in the reference: bin and score in double
-          a_nll -= log(pyd + 1e-7);
-          if (edges != nullptr) {
-            // binning below is done in T; for float inputs re-do it in double here
-            double c = best;
-            int j = (int)ceil(c * bins) - 1;
-            j = j < 0 ? 0 : (j > bins - 1 ? bins - 1 : j);
-            while (j > 0 && !(edges[j] < c)) --j;
-            while (j < bins - 1 && !(c <= edges[j + 1])) ++j;
-            const bool inbin = (edges[j] < c) && (c <= edges[j + 1]);
-            const unsigned ok = (pred == yy) ? 1u : 0u;
-            if (inbin) {
-              if (j != cache.bin) { flush(cache, s_cnt, s_cor, s_conf); cache.bin = j; }
-              cache.cnt += 1; cache.correct += ok; cache.sconf += c;
-            }
-            a_correct += ok; a_n += 1.0;
-            continue;
-          }
-        }
+// Statistics of one row.  get(jj) returns the element stored at position jj of the row and
+// col(jj) its class index (identity unless the row is read in a lane-rotated order to dodge
+// shared-memory bank conflicts); ties resolve to the smallest class index, as np.argmax does.
+template <typename T, int mode, bool ROT, typename Get, typename Col>
+__device__ __forceinline__ void row_stats(Get get, Col col, int yy, int64_t n, int K, int bins,
+                                          const double* s_lp, const T* s_edges, const double* __restrict__ edges,
+                                          double* __restrict__ probs_out, int& out_bin, unsigned& out_ok,
+                                          double& out_conf, double& a_nll, double& a_correct, double& a_n) {
+  out_bin = -1;
+  T conf, py = (T)0;
+  int pred = 0;
+  if (mode == CNF_METRICS_PROBS) {
+    conf = get(0); pred = col(0);
+    if (ROT) {
+      if (pred == yy) py = conf;
+      for (int jj = 1; jj < K; ++jj) {
+        const T v = get(jj);
+        const int c = col(jj);
+        if (v > conf || (v == conf && c < pred)) { conf = v; pred = c; }
+        if (c == yy) py = v;
       }
+    } else {   // elements arrive in class order: strict '>' keeps the first maximum, as np.argmax
+      for (int jj = 1; jj < K; ++jj) {
+        const T v = get(jj);
+        if (v > conf) { conf = v; pred = jj; }
+      }
+      py = (yy >= 0 && yy < K) ? get(yy) : (T)0;
+    }
+    a_nll -= (double)t_log<T>(py + (T)1e-7);
+  } else {
+    // float32 softmax of the logits (scipy.special.softmax on float32)
+    float mx = (float)get(0);
+    for (int jj = 1; jj < K; ++jj) mx = fmaxf(mx, (float)get(jj));
+    float se = 0.f;
+    for (int jj = 0; jj < K; ++jj) se += expf((float)get(jj) - mx);
+    if (mode == CNF_METRICS_LOGITS) {
+      float best = -1.f, pyf = 0.f;
+      for (int jj = 0; jj < K; ++jj) {
+        const float pj = expf((float)get(jj) - mx) / se;
+        const int c = col(jj);
+        if (pj > best || (pj == best && c < pred)) { best = pj; pred = c; }
+        if (c == yy) pyf = pj;
+      }
+      conf = (T)best; py = (T)pyf;
+      a_nll -= (double)logf(pyf + 1e-7f);
+    } else {
+      // u_j = (double)log(p_j + 1e-7f) - log_prior_j ; float64 softmax of u
+      double umax = -INFINITY;
+      for (int jj = 0; jj < K; ++jj) {
+        const float pj = expf((float)get(jj) - mx) / se;
+        const double u = (double)logf(pj + 1e-7f) - s_lp[col(jj)];
+        if (u > umax) umax = u;
+      }
+      double sd = 0.0;
+      for (int jj = 0; jj < K; ++jj) {
+        const float pj = expf((float)get(jj) - mx) / se;
+        sd += exp((double)logf(pj + 1e-7f) - s_lp[col(jj)] - umax);
+      }
+      double best = -1.0, pyd = 0.0;
+      for (int jj = 0; jj < K; ++jj) {
+        const float pj = expf((float)get(jj) - mx) / se;
+        const int c = col(jj);
+        const double q = exp((double)logf(pj + 1e-7f) - s_lp[c] - umax) / sd;
+        if (probs_out != nullptr) probs_out[n * K + c] = q;
+        if (q > best || (q == best && c < pred)) { best = q; pred = c; }
+        if (c == yy) pyd = q;
+      }
+      a_nll -= log(pyd + 1e-7);
       const unsigned ok = (pred == yy) ? 1u : 0u;
       a_correct += ok; a_n += 1.0;
-      if (edges != nullptr) {
-        const T c = conf;
-        int j = (int)ceil((double)c * bins) - 1;
+      if (edges != nullptr) {   // calibrated probabilities are float64 in the reference: bin in double
+        const double c = best;
+        int j = (int)ceil(c * bins) - 1;
         j = j < 0 ? 0 : (j > bins - 1 ? bins - 1 : j);
-        while (j > 0 && !(s_edges[j] < c)) --j;
-        while (j < bins - 1 && !(c <= s_edges[j + 1])) ++j;
-        const bool inbin = (s_edges[j] < c) && (c <= s_edges[j + 1]);
-        if (inbin) {
-          if (j != cache.bin) { flush(cache, s_cnt, s_cor, s_conf); cache.bin = j; }
-          cache.cnt += 1; cache.correct += ok; cache.sconf += (double)c;
-        }
+        while (j > 0 && !(edges[j] < c)) --j;
+        while (j < bins - 1 && !(c <= edges[j + 1])) ++j;
+        if ((edges[j] < c) && (c <= edges[j + 1])) { out_bin = j; out_ok = ok; out_conf = c; }
       }
+      return;
     }
   }
-  flush(cache, s_cnt, s_cor, s_conf);
-  // block reduction of the three scalars
+  const unsigned ok = (pred == yy) ? 1u : 0u;
+  a_correct += ok; a_n += 1.0;
+  if (edges != nullptr) {
+    const T c = conf;
+    int j = __float2int_ru((float)c * (float)bins) - 1;
+    j = j < 0 ? 0 : (j > bins - 1 ? bins - 1 : j);
+    while (j > 0 && !(s_edges[j] < c)) --j;
+    while (j < bins - 1 && !(c <= s_edges[j + 1])) ++j;
+    if ((s_edges[j] < c) && (c <= s_edges[j + 1])) { out_bin = j; out_ok = ok; out_conf = (double)c; }
+  }
+}
+
+// Every lane keeps a run cache (bin, count, correct, sum conf) and touches the shared histogram
+// only when its bin changes; with a confident classifier most consecutive samples share a bin.
+// (A warp-aggregated variant -- ballot/popc/shuffle per distinct bin -- measured 2x slower.)
+__device__ __forceinline__ void warp_accumulate(int bin, unsigned ok, double conf, int bins, BinCache& cache,
+                                                unsigned* s_cnt, unsigned* s_cor, double* s_conf, int lane) {
+  (void)bins; (void)lane;
+  if (bin >= 0) {
+    if (bin != cache.bin) { flush(cache, s_cnt, s_cor, s_conf); cache.bin = bin; }
+    cache.cnt += 1; cache.correct += ok; cache.sconf += conf;
+  }
+}
+
+struct MetricsSmem {
+  double* s_conf; double* s_lp; unsigned* s_cnt; unsigned* s_cor; unsigned char* ring;
+};
+
+template <typename T>
+__device__ __forceinline__ T* carve(unsigned char* smem_raw, int bins, int K, MetricsSmem& m) {
+  m.s_conf = reinterpret_cast<double*>(smem_raw);
+  m.s_lp = m.s_conf + bins;
+  T* s_edges = reinterpret_cast<T*>(m.s_lp + K);
+  m.s_cnt = reinterpret_cast<unsigned*>(s_edges + (bins + 2));
+  m.s_cor = m.s_cnt + bins;
+  size_t off = reinterpret_cast<unsigned char*>(m.s_cor + bins) - smem_raw;
+  off = (off + 15) / 16 * 16;
+  m.ring = smem_raw + off;
+  return s_edges;
+}
+
+__device__ __forceinline__ void finish_block(double a_nll, double a_correct, double a_n, BinCache& cache,
+                                             const MetricsSmem& m, int bins, double* __restrict__ acc, double* red,
+                                             int tid, int NT) {
+  flush(cache, m.s_cnt, m.s_cor, m.s_conf);
   double v3[3] = {a_nll, a_correct, a_n};
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -180,40 +185,187 @@ __global__ void metrics_kernel(const T* __restrict__ in, const int64_t* __restri
   __syncthreads();
   if (acc != nullptr)
     for (int i = tid; i < bins; i += NT) {
-      if (s_cnt[i]) {
-        atomicAdd(acc + i, (double)s_cnt[i]);
-        atomicAdd(acc + bins + i, s_conf[i]);
-        atomicAdd(acc + 2 * bins + i, (double)s_cor[i]);
+      if (m.s_cnt[i]) {
+        atomicAdd(acc + i, (double)m.s_cnt[i]);
+        atomicAdd(acc + bins + i, (double)reinterpret_cast<const unsigned long long*>(m.s_conf)[i] * (1.0 / CNF_FX_SCALE));
+        atomicAdd(acc + 2 * bins + i, (double)m.s_cor[i]);
       }
     }
+}
+
+// Streaming kernel: every warp owns a ring of `stages` shared-memory tiles of 32 rows, filled with
+// 16-byte cp.async copies (fully coalesced, no block-level barrier); lane i then reads row i.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256, (MODE == CNF_METRICS_CALIBRATED || sizeof(T) == 8) ? 2 : 4)
+metrics_stream_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, int64_t N, int K,
+                                      int bins, const double* __restrict__ log_priors,
+                                      const double* __restrict__ edges, double* __restrict__ acc,
+                                      double* __restrict__ probs_out, int stages, int rot) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
+  MetricsSmem m;
+  T* s_edges = carve<T>(smem_raw, bins, K, m);
+  for (int i = tid; i < bins; i += NT) { m.s_conf[i] = 0.0; m.s_cnt[i] = 0u; m.s_cor[i] = 0u; }   // 0.0 == 0ull
+  if (edges != nullptr)
+    for (int i = tid; i <= bins; i += NT) s_edges[i] = (T)edges[i];
+  if (log_priors != nullptr)
+    for (int i = tid; i < K; i += NT) m.s_lp[i] = log_priors[i];
+  __syncthreads();
+
+  const int tile_elems = 32 * K;
+  const int tile_chunks = tile_elems * (int)sizeof(T) / 16;
+  T* ring = reinterpret_cast<T*>(m.ring) + (size_t)warp * stages * tile_elems;
+  const int64_t ntiles = (N + 31) / 32;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
+  auto issue = [&](int64_t tile, int stage) {
+    if (tile < ntiles && (tile + 1) * 32 <= N) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(in + tile * tile_elems);
+      unsigned char* dst = reinterpret_cast<unsigned char*>(ring + (size_t)stage * tile_elems);
+      for (int c = lane; c < tile_chunks; c += 32) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 16 * c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int s = 0; s < stages - 1; ++s) issue(gw + (int64_t)s * GW, s);
+
+  BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
+  double a_nll = 0.0, a_correct = 0.0, a_n = 0.0;
+  int stage = 0;
+  for (int64_t tile = gw, i = 0; tile < ntiles; tile += GW, ++i) {
+    int pre = stage + stages - 1;
+    if (pre >= stages) pre -= stages;
+    issue(tile + (int64_t)(stages - 1) * GW, pre);
+    const int64_t n = tile * 32 + lane;
+    const int yy = (y != nullptr && n < N) ? (int)y[n] : -1;
+    // all but the newest (stages-1) groups have landed -> this tile's copy is complete
+    if (stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+    __syncwarp();
+    int r_bin = -1;
+    unsigned r_ok = 0u;
+    double r_conf = 0.0;
+    if (n < N) {
+      const bool full = (tile + 1) * 32 <= N;
+      const T* srow = ring + (size_t)stage * tile_elems + lane * K;
+      const T* grow = in + n * K;
+      if (full) {
+        if (rot) {
+          auto col = [&](int jj) -> int { int c = jj + lane; return c >= K ? c - K * (c / K) : c; };
+          auto get = [&](int jj) -> T { return srow[col(jj)]; };
+          row_stats<T, MODE, true>(get, col, yy, n, K, bins, m.s_lp, s_edges, edges, probs_out, r_bin, r_ok, r_conf, a_nll,
+                       a_correct, a_n);
+        } else {
+          auto col = [&](int jj) -> int { return jj; };
+          auto get = [&](int jj) -> T { return srow[jj]; };
+          row_stats<T, MODE, false>(get, col, yy, n, K, bins, m.s_lp, s_edges, edges, probs_out, r_bin, r_ok, r_conf, a_nll,
+                       a_correct, a_n);
+        }
+      } else {
+        auto col = [&](int jj) -> int { return jj; };
+        auto get = [&](int jj) -> T { return grow[jj]; };
+        row_stats<T, MODE, false>(get, col, yy, n, K, bins, m.s_lp, s_edges, edges, probs_out, r_bin, r_ok, r_conf, a_nll,
+                     a_correct, a_n);
+      }
+    }
+    warp_accumulate(r_bin, r_ok, r_conf, bins, cache, m.s_cnt, m.s_cor, m.s_conf, lane);
+    __syncwarp();
+    if (++stage == stages) stage = 0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  finish_block(a_nll, a_correct, a_n, cache, m, bins, acc, red, tid, NT);
+}
+
+// Fallback for rows too wide to stage: one thread per row straight from global memory.
+template <typename T, int MODE>
+__global__ void metrics_direct_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, int64_t N, int K,
+                                      int bins, const double* __restrict__ log_priors,
+                                      const double* __restrict__ edges, double* __restrict__ acc,
+                                      double* __restrict__ probs_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  MetricsSmem m;
+  T* s_edges = carve<T>(smem_raw, bins, K, m);
+  for (int i = tid; i < bins; i += NT) { m.s_conf[i] = 0.0; m.s_cnt[i] = 0u; m.s_cor[i] = 0u; }   // 0.0 == 0ull
+  if (edges != nullptr)
+    for (int i = tid; i <= bins; i += NT) s_edges[i] = (T)edges[i];
+  if (log_priors != nullptr)
+    for (int i = tid; i < K; i += NT) m.s_lp[i] = log_priors[i];
+  __syncthreads();
+  BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
+  double a_nll = 0.0, a_correct = 0.0, a_n = 0.0;
+  for (int64_t n0 = (int64_t)blockIdx.x * NT; n0 < N; n0 += (int64_t)gridDim.x * NT) {
+    const int64_t n = n0 + tid;
+    int r_bin = -1;
+    unsigned r_ok = 0u;
+    double r_conf = 0.0;
+    if (n < N) {
+      const T* grow = in + n * K;
+      const int yy = (y != nullptr) ? (int)y[n] : -1;
+      auto col = [&](int jj) -> int { return jj; };
+      auto get = [&](int jj) -> T { return grow[jj]; };
+      row_stats<T, MODE, false>(get, col, yy, n, K, bins, m.s_lp, s_edges, edges, probs_out, r_bin, r_ok, r_conf, a_nll,
+                   a_correct, a_n);
+    }
+    warp_accumulate(r_bin, r_ok, r_conf, bins, cache, m.s_cnt, m.s_cor, m.s_conf, tid & 31);
+  }
+  finish_block(a_nll, a_correct, a_n, cache, m, bins, acc, red, tid, NT);
 }
 
 template <typename T>
 int launch_metrics(const T* in, const int64_t* y, int64_t N, int K, int bins, int mode, const double* lp,
                    const double* edges, double* acc, double* probs_out, cudaStream_t st) {
-  int dev = 0, max_smem = 0, sms = 0;
+  int dev = 0, sms = 0;
   CNF_CHECK_CUDA(cudaGetDevice(&dev));
-  CNF_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   CNF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t fixed = (size_t)bins * 8 + (size_t)K * 8 + (size_t)(bins + 2) * sizeof(T) + (size_t)bins * 8 + 32;
-  int nt = 256;
-  bool staged = false;
-  for (; nt >= 64; nt >>= 1) {
-    const size_t tile = ((size_t)nt * K + (size_t)nt * K / 32 + 8) * sizeof(T);
-    if (fixed + tile <= 100 * 1024) { staged = true; break; }   // keep >= 2 CTAs per SM
-  }
-  if (!staged) nt = 128;
-  const size_t tile = staged ? ((size_t)nt * K + (size_t)nt * K / 32 + 8) * sizeof(T) : 0;
-  const size_t smem = fixed + tile;
-  const int64_t ntiles = (N + nt - 1) / nt;
-  const int64_t cap = (int64_t)sms * 4;
-  const int grid = (int)(ntiles < cap ? ntiles : cap);
-  if (staged) {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    metrics_kernel<T, true><<<grid, nt, smem, st>>>(in, y, N, K, bins, mode, lp, edges, acc, probs_out);
+  const size_t tile = (size_t)32 * K * sizeof(T);
+  // widest ring that keeps the CTA under ~56 KB (4 CTAs per SM); needs 16 B-aligned rows of tiles
+  int nwarps = 0, stages = 0;
+  const bool aligned = ((uintptr_t)in % 16 == 0);
+  const int wopts[3] = {8, 4, 2}, sopts[3] = {4, 3, 2};
+  for (int wi = 0; wi < 3 && !nwarps && aligned; ++wi)
+    for (int si = 0; si < 3; ++si)
+      if (fixed + tile * wopts[wi] * sopts[si] <= 56 * 1024) { nwarps = wopts[wi]; stages = sopts[si]; break; }
+  if (nwarps) {
+    const size_t smem = fixed + tile * nwarps * stages;
+    const int64_t nt = (N + 31) / 32;
+    const int per_sm = (int)(200 * 1024 / (smem + 1024)) > 8 ? 8 : (int)(200 * 1024 / (smem + 1024));
+    int64_t grid = (nt + nwarps - 1) / nwarps;
+    const int64_t cap = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > cap) grid = cap;
+    const int words = K * (int)sizeof(T) / 4;
+    const int rot = (words % 8 == 0) ? 1 : 0;     // row stride would hit >= 8-way bank conflicts
+#define LAUNCH_STREAM(M)                                                                                     \
+  do {                                                                                                       \
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_stream_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                         \
+    metrics_stream_kernel<T, M><<<(int)grid, nwarps * 32, smem, st>>>(in, y, N, K, bins, lp, edges, acc, probs_out, \
+                                                                        stages, rot);                        \
+  } while (0)
+    if (mode == CNF_METRICS_PROBS) LAUNCH_STREAM(CNF_METRICS_PROBS);
+    else if (mode == CNF_METRICS_LOGITS) LAUNCH_STREAM(CNF_METRICS_LOGITS);
+    else LAUNCH_STREAM(CNF_METRICS_CALIBRATED);
+#undef LAUNCH_STREAM
   } else {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    metrics_kernel<T, false><<<grid, nt, smem, st>>>(in, y, N, K, bins, mode, lp, edges, acc, probs_out);
+    const int nt = 128;
+    const int64_t cap = (int64_t)sms * 8;
+    const int64_t want = (N + nt - 1) / nt;
+    const int grid = (int)(want < cap ? want : cap);
+#define LAUNCH_DIRECT(M)                                                                                     \
+  do {                                                                                                       \
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_direct_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)fixed));                                                        \
+    metrics_direct_kernel<T, M><<<grid, nt, fixed, st>>>(in, y, N, K, bins, lp, edges, acc, probs_out);        \
+  } while (0)
+    if (mode == CNF_METRICS_PROBS) LAUNCH_DIRECT(CNF_METRICS_PROBS);
+    else if (mode == CNF_METRICS_LOGITS) LAUNCH_DIRECT(CNF_METRICS_LOGITS);
+    else LAUNCH_DIRECT(CNF_METRICS_CALIBRATED);
+#undef LAUNCH_DIRECT
   }
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
