@@ -27,16 +27,22 @@ struct BinCache {
   int bin; unsigned cnt, correct; double sconf;
 };
 
-// Confidence sums are kept in shared memory as 2^-40 fixed point in 64-bit integers: integer
-// atomics are native (a double atomicAdd on shared memory is a CAS loop that spins under the
-// contention of a popular bin) and make the per-CTA sum order-independent.  A CTA sums < 2^24.
+// Confidence sums are kept in shared memory as 2^-40 fixed point, 64 bits split into two 32-bit
+// words: only 32-bit integer atomics are native on shared memory (double and 64-bit atomicAdd
+// compile to CAS loops that spin under the contention of a popular bin).  The low-word add returns
+// the old value, so each add knows whether it wrapped and carries into the high word itself; the
+// pair therefore always sums to the exact 64-bit total.  Order-independent; a CTA sums < 2^24.
 #define CNF_FX_SCALE 1099511627776.0 /* 2^40 */
 __device__ __forceinline__ void flush(BinCache& c, unsigned* s_cnt, unsigned* s_cor, double* s_conf) {
   if (c.bin >= 0 && c.cnt) {
     atomicAdd(s_cnt + c.bin, c.cnt);
     atomicAdd(s_cor + c.bin, c.correct);
-    atomicAdd(reinterpret_cast<unsigned long long*>(s_conf) + c.bin,
-              (unsigned long long)__double2ll_rn(c.sconf * CNF_FX_SCALE));
+    const unsigned long long fx = (unsigned long long)__double2ll_rn(c.sconf * CNF_FX_SCALE);
+    unsigned* w = reinterpret_cast<unsigned*>(s_conf) + 2 * c.bin;
+    const unsigned lo = (unsigned)fx, hi = (unsigned)(fx >> 32);
+    const unsigned old = atomicAdd(w, lo);
+    const unsigned carry = (old + lo < old) ? 1u : 0u;
+    if (hi + carry) atomicAdd(w + 1, hi + carry);
   }
   c.cnt = 0; c.correct = 0; c.sconf = 0.0;
 }
