@@ -268,7 +268,7 @@ def run_ours(args):
     # ---- training step, config C3 shape (fp32 path) ------------------------------------------
     train = None
     if not args.no_train:
-        n_loc = args.train_n
+        n_loc = args.train_n or (64 * (1 << 20)) // world
         xt, yt = synth(n_loc, 5000 + rank, dev)
         tmodel = make_weights(seed=2)
         with torch.no_grad():
@@ -289,10 +289,55 @@ def run_ours(args):
         barrier()
         tms = max_over_ranks(t0e.elapsed_time(t1e))
         train = {'value': world * n_loc * tsteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / tsteps,
-                 'samples_per_gpu': n_loc, 'steps': tsteps, 'dtype': 'f32',
+                 'samples_per_gpu': n_loc, 'samples_total': n_loc * world, 'scaling': 'strong (C3: 64 Mi samples over all GPUs)' if not args.train_n else 'weak', 'steps': tsteps, 'dtype': 'f32',
                  'what': 'fused NLL fwd+bwd kernel + grad reduce' + (' + NCCL all-reduce' if world > 1 else '') +
                          ' + Adam + repack per step', 'loss': -float(tr.loss_acc[0]) / (n_loc * world)}
         del xt, yt
+
+    # ---- config C5 pieces: inverse pass and the metrics kernel (HBM-bound) -------------------
+    extra = None
+    if not args.no_extra:
+        from cnf_b200.utils import metrics as M
+        for i in range(3):
+            _lib.call('cnf_flow_inverse', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
+                      _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for i in range(20):
+            _lib.call('cnf_flow_inverse', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
+                      _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
+        i1.record()
+        barrier()
+        inv_ms = max_over_ranks(i0.elapsed_time(i1)) / 20
+        n_m = 12_500_000                      # 10^8 samples over 8 GPUs (config C5)
+        pm = torch.softmax(synth(n_m, 31 + rank, dev)[0], dim=1).contiguous()
+        ym = synth(n_m, 31 + rank)[1].to(dev)
+        edges = torch.from_numpy(M.bin_edges(15)).to(dev)
+        macc = torch.zeros(48, dtype=torch.float64, device=dev)
+
+        def mstep():
+            _lib.call('cnf_metrics', _ptr(pm), ctypes.c_int32(0), _ptr(ym), ctypes.c_int64(n_m), ctypes.c_int32(K),
+                      ctypes.c_int32(15), ctypes.c_int32(0), None, _ptr(edges), _ptr(macc), _stream(dev))
+        for _ in range(3):
+            mstep()
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(20):
+            mstep()
+        m1.record()
+        barrier()
+        met_ms = max_over_ranks(m0.elapsed_time(m1)) / 20
+        hbm_peak = peaks()[0]
+        mb = (4 * K + 8) * n_m / (met_ms * 1e-3) / 1e9
+        extra = {'inverse': {'value': world * N_STEP / (inv_ms * 1e-3), 'unit': UNIT, 'ms_per_step': inv_ms,
+                             'what': 'Flow.backward (inverse + log-det) on 1,000,000 samples per GPU, same path as value'},
+                 'metrics': {'value': world * n_m / (met_ms * 1e-3), 'unit': UNIT, 'ms_per_step': met_ms,
+                             'samples_per_gpu': n_m, 'what': 'ECE(15 bins)+NLL+accuracy in one pass over fp32 probabilities',
+                             'roofline': {'bound': 'hbm', 'achieved': mb, 'peak': hbm_peak, 'unit': 'GB/s',
+                                          'frac': mb / hbm_peak, 'note': 'algorithmic bytes 4K+8 = 48 B/sample'}}}
+        del pm, ym
 
     hbm, tf, src = peaks()
     ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
@@ -324,7 +369,7 @@ def run_ours(args):
                 'config': {'workload': WORKLOAD, 'l2': 'inputs larger than L2: %d rotating batches' % N_ROT,
                            'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1'},
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
-                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train}
+                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'c5': extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -337,9 +382,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='auto', choices=['auto', 'fp32', 'bf16'])
-    ap.add_argument('--train-n', type=int, default=8 * (1 << 20))
+    ap.add_argument('--train-n', type=int, default=0, help='training samples per GPU (default: 64 Mi / n_gpus, config C3)')
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
