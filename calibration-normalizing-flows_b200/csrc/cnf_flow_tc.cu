@@ -22,15 +22,24 @@
 #include <cuda_runtime.h>
 
 #include "cnf_common.h"
+#include "cnf_tc_ptx.cuh"
 
 int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
+// wide variant (cnf_flow_tcw.cu): used when the resident-weight kernel does not cover the shape
+bool cnf_tcw_supported(const CnfDims& d);
+long long cnf_tcw_blob_bytes(const CnfDims& d);
+long long cnf_tcw_gather_len(const CnfDims& d);
+int cnf_tcw_plan_build(const CnfDims& d, int32_t* g);
+int cnf_tcw_pack(const CnfDims& d, const float* flat, const int32_t* gather_tc, void* packed_tc, cudaStream_t st);
+int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                  float* logdet, int64_t N, int inverse, cudaStream_t st);
 
 namespace {
 
 constexpr int TC_SLOTS = 3;                       // tiles in flight per CTA
 constexpr int TC_THREADS = 128 + 128 * TC_SLOTS;  // warps 0..2 MMA issuers, warp 3 TMEM allocator, then one epilogue warpgroup per slot
 constexpr int SLOT_COLS = 160;                    // TMEM columns per slot: D1 (<=128) + D2 (16), padded
-constexpr int TILE_M = 128;
+
 constexpr int A1_BYTES = TILE_M * 32;   // 128 rows x 16 bf16
 constexpr int LBO1 = 128, SBO1 = 256;   // A1 / B1: k-halves adjacent, 8-row groups 256 B apart
 constexpr int LBO2 = 256, SBO2 = 128;   // B2 per k-step: two 8-row groups adjacent, k-halves 256 B apart
@@ -78,129 +87,6 @@ bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
 }
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) {}
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] . B[smem desc]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-
-// no-swizzle K-major shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
-  return d;
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
-__host__ __device__ inline uint32_t make_idesc(int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// The loaded registers are named as in/out operands so that no use of them can be scheduled
-// above the wait (tcgen05.ld completes asynchronously).
-__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :: "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :: "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// {hi, lo} -> bf16x2 with ReLU: low 16 bits = lo (element 2i), high 16 bits = hi (element 2i+1)
-__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ void wg_sync(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
-
-// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 // EPI selects how EPI1 turns fp32 hidden units into the bf16 A operand of GEMM2:
@@ -216,12 +102,6 @@ __device__ __forceinline__ uint32_t pack_hidden(uint32_t lo, uint32_t hi) {
   v = __hmax2(v, *reinterpret_cast<const __nv_bfloat162*>(&zero));
   return *reinterpret_cast<const uint32_t*>(&v);
 }
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -507,7 +387,8 @@ int g_tc_sms = -1;
 
 long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d) {
   TcDims t;
-  return tc_dims(desc, d, &t) ? (long long)t.blob_bytes : 0;
+  if (tc_dims(desc, d, &t)) return (long long)t.blob_bytes;
+  return cnf_tcw_blob_bytes(d);
 }
 
 // gather_tc: entry i < n_bf16 addresses bf16 element i of the B1/B2 image; the remaining n_f32
@@ -517,7 +398,7 @@ extern "C" int cnf_tc_gather_len(const cnf_flow_desc* desc, int64_t* n) {
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!n) { cnf_set_error("null out"); return CNF_E_ARG; }
-  *n = tc_dims(desc, d, &t) ? (int64_t)t.n_bf16 + t.n_f32 : 0;
+  *n = tc_dims(desc, d, &t) ? (int64_t)t.n_bf16 + t.n_f32 : (int64_t)cnf_tcw_gather_len(d);
   return CNF_OK;
 }
 
@@ -525,8 +406,8 @@ extern "C" int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* g) {
   CnfDims d; TcDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
-  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   if (!g) { cnf_set_error("null output"); return CNF_E_ARG; }
+  if (!tc_dims(desc, d, &t)) return cnf_tcw_plan_build(d, g);
   const int K = d.K, half = K / 2, H = d.H[0], Hp = d.Hp[0];
   for (int i = 0; i < t.n_bf16 + t.n_f32; ++i) g[i] = -1;
   // canonical flat offsets of one net: W0 [H,K], b0 [H], W1 [K,H], b1 [K]
@@ -575,9 +456,9 @@ extern "C" int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat,
   CnfDims d; TcDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
-  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   if (!flat || !gather_tc || !packed_tc) { cnf_set_error("cnf_pack_weights_tc: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (!tc_dims(desc, d, &t)) return cnf_tcw_pack(d, flat, gather_tc, packed_tc, st);
   if ((rc = cnf_pack_bf16(flat, gather_tc, packed_tc, t.n_bf16, st))) return rc;
   gather_f32_kernel<<<(t.n_f32 + 127) / 128, 128, 0, st>>>(flat, gather_tc + t.n_bf16,
                                                            reinterpret_cast<float*>((uint8_t*)packed_tc + t.bias_off), t.n_f32);
@@ -590,9 +471,9 @@ int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t
   CnfDims d; TcDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
-  if (!tc_dims(desc, d, &t)) { cnf_set_error("tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   if (N == 0) return CNF_OK;
   if (!packed_tc || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  if (!tc_dims(desc, d, &t)) return cnf_tcw_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
   if (g_tc_sms < 0) {
     int dev = 0, s = 0;
     CNF_CHECK_CUDA(cudaGetDevice(&dev));

@@ -75,3 +75,35 @@ def test_tc_matches_fp32_path_statistically_at_c2_size(cuda_device):
     assert abs(M.ece_from_statistics(s32, 15) - M.ece_from_statistics(sbf, 15)) < 1e-3
     assert abs(s32[45] / s32[47] - sbf[45] / sbf[47]) < 1e-3          # NLL
     assert abs(s32[46] - sbf[46]) / s32[47] < 1e-3                    # accuracy
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift,wmul', [(100, 8, [512], True, True, 60.0), (33, 3, [200], False, True, 100.0),
+                                                         (40, 2, [24], True, True, 200.0), (126, 2, [130], True, True, 60.0),
+                                                         (20, 4, [300], True, False, 100.0)])
+def test_tc_wide_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda_device):
+    """Shapes beyond the resident-weight kernel run on the streamed-weight kernel (cnf_flow_tcw.cu)."""
+    import torch
+    import cnf_b200
+    torch.manual_seed(K + L)
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)],
+                         precision='bf16')
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(wmul)
+    like = orc.init_params(K, L, hidden, scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    flow.to(cuda_device)
+    assert flow.engine().tc_bytes > 0
+    for N in (1, 300, 128 * 148 * 2 + 77):
+        x, _ = orc.synth_logits(N, K, seed=3 + N)
+        with torch.no_grad():
+            zs, ld = flow(torch.from_numpy(x).to(cuda_device))
+            xr, ldr = flow.backward(zs[-1])
+        zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+        zz = zs[-1].cpu().numpy()
+        assert np.isfinite(zz).all()
+        assert rel_err(zz, zo[-1]) < RTOL
+        assert np.max(np.abs(ld.cpu().numpy().reshape(-1) - ldo)) < RTOL * max(1.0, np.max(np.abs(ldo)))
+        assert rel_err(xr[-1].cpu().numpy(), x) < RTOL
