@@ -338,6 +338,44 @@ def run_ours(args):
                              'roofline': {'bound': 'hbm', 'achieved': mb, 'peak': hbm_peak, 'unit': 'GB/s',
                                           'frac': mb / hbm_peak, 'note': 'algorithmic bytes 4K+8 = 48 B/sample'}}}
         del pm, ym
+        # config C4: K=100, 8 couplings, hidden 512 on the streamed-weight tensor-core kernel
+        torch.manual_seed(4)
+        c4 = cnf_b200.RealNvpFlow(100, layers=8, hidden_size=[512])
+        with torch.no_grad():
+            for prm in c4.parameters():
+                if prm.requires_grad:
+                    prm.mul_(60.0)
+        c4.to(dev)
+        e4 = c4.engine()
+        e4.ensure(dev)
+        e4.pack(tc=True)
+        n4 = 1_000_000
+        g4 = torch.Generator(device=dev).manual_seed(40 + rank)
+        x4 = 1.5 * torch.randn((n4, 100), generator=g4, device=dev)
+        x4 -= x4.mean(dim=1, keepdim=True)
+        z4 = torch.empty_like(x4)
+        l4 = torch.empty(n4, dtype=torch.float32, device=dev)
+
+        def c4step():
+            _lib.call('cnf_flow_forward', ctypes.byref(e4.desc_tc), _ptr(e4.packed_tc), _ptr(e4.tables), _ptr(x4),
+                      _ptr(z4), _ptr(l4), None, ctypes.c_int64(n4), _stream(dev))
+        for _ in range(2):
+            c4step()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            c4step()
+        c1.record()
+        barrier()
+        c4_ms = max_over_ranks(c0.elapsed_time(c1)) / 5
+        c4_flops = 8 * 2 * 2 * (50 * 512 + 512 * 50)
+        extra['c4_forward'] = {'value': world * n4 / (c4_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4_ms, 'dtype': 'bf16',
+                               'what': 'C4: RealNVP K=100 L=8 hidden=[512] fwd+logdet, 1,000,000 samples per GPU, '
+                                       'streamed-weight tcgen05 kernel',
+                               'tensor_tflops_minimal': c4_flops * n4 / (c4_ms * 1e-3) / 1e12,
+                               'frac_of_bf16_peak': c4_flops * n4 / (c4_ms * 1e-3) / 1e12 / peaks()[1]}
+        del x4, z4, l4
 
     hbm, tf, src = peaks()
     ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9

@@ -1,0 +1,70 @@
+"""Property tests on random shapes (hypothesis): fp32 path vs the float64 oracle to 1e-5, tensor-core
+path (when the shape is covered) to the stated bf16 tolerance, inverse round trip, ragged N."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+import flow_oracle as orc
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@st.composite
+def shapes(draw):
+    K = draw(st.integers(2, 40))
+    L = draw(st.integers(1, 7))
+    m = draw(st.integers(0, 3))
+    hidden = [draw(st.integers(1, 70)) for _ in range(m)]
+    scale = draw(st.booleans())
+    shift = draw(st.booleans()) or not scale
+    rf = draw(st.booleans())
+    N = draw(st.sampled_from([1, 2, 31, 128, 129, 500, 1025]))
+    return K, L, hidden, scale, shift, rf, N
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(cfg=shapes(), seed=st.integers(0, 10_000))
+def test_random_shapes_match_oracle(cfg, seed, cuda_device):
+    import torch
+    import cnf_b200
+    K, L, hidden, scale, shift, rf, N = cfg
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    layers = [cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift, random_flip=rf) for _ in range(L)]
+    flow = cnf_b200.Flow(layers)
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(150.0)
+    like = orc.init_params(K, L, hidden, scale, shift)
+    for l, lay in enumerate(like):
+        lay['perm'] = np.array(layers[l].perm_list()) if rf else None
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    x, y = orc.synth_logits(N, K, seed=seed)
+    zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+    scale_ld = max(1.0, float(np.max(np.abs(ldo))))
+    flow.to(cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device)
+    eng = flow.engine()
+    z, ld, allz = eng.apply(xt, want_all=True)
+    assert rel_err(z.cpu().numpy(), zo[-1]) < 1e-5
+    assert np.max(np.abs(ld.cpu().numpy() - ldo)) < 1e-5 * scale_ld
+    for l in range(L):
+        assert rel_err(allz[l].cpu().numpy(), zo[l]) < 1e-5
+    xr, ldr, _ = eng.apply(z, inverse=True)
+    assert rel_err(xr.cpu().numpy(), x) < 1e-4
+    # gradients of the fused train step vs the oracle's analytic backward
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.pack()
+    eng.nll_step(xt, torch.from_numpy(y).to(cuda_device), acc)
+    loss, _, _, grads, _ = orc.train_step_grads(params, x.astype(np.float64), y)
+    go = orc.flatten(grads)
+    assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+    if np.max(np.abs(go)) > 0:
+        assert rel_err(eng.flat_grad.cpu().numpy(), go) < 5e-4
+    if eng.tc_bytes > 0:
+        zb, lb, _ = eng.apply(xt, precision='bf16')
+        assert rel_err(zb.cpu().numpy(), zo[-1]) < 1e-2
+        assert np.max(np.abs(lb.cpu().numpy() - ldo)) < 1e-2 * scale_ld
