@@ -198,14 +198,24 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
       const int64_t tile = blockIdx.x + (2 * r + slot) * (int64_t)G;
       const int64_t base = tile * TILE_M;
       {
+        // coalesced loads, 10 in flight per thread, then the transposing stores
         const float* gp = xin + base * K;
         const int64_t avail = (N - base) * (int64_t)K;
         int s = s0, f = f0;
-        for (int e = t; e < tile_elems; e += 128) {
-          const float v = (e < avail) ? __ldg(gp + e) : 0.f;
-          act[(inverse ? pi_last[f] : f) * TILE_M + s] = v;
-          s += ds; f += df;
-          while (f >= K) { f -= K; ++s; }
+        constexpr int U = 10;
+        for (int e0 = t; e0 < tile_elems; e0 += 128 * U) {
+          float v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + 128 * u;
+            v[u] = (e < tile_elems && e < avail) ? __ldg(gp + e) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (e0 + 128 * u < tile_elems) act[(inverse ? pi_last[f] : f) * TILE_M + s] = v[u];
+            s += ds; f += df;
+            while (f >= K) { f -= K; ++s; }
+          }
         }
       }
       wg_sync(slot);
