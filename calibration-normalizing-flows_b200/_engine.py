@@ -151,7 +151,7 @@ class StackEngine:
         return out, ld, allz
 
     def apply_host(self, x_host, out_host=None, ld_host=None, inverse=False, precision='fp32',
-                   chunk=1 << 18, slots=3, repack=True, device=None):
+                   chunk=1 << 17, slots=4, repack=True, device=None):
         """Host buffers in, host buffers out: the samples stream through the GPU in chunks on
         `slots` CUDA streams so that the H2D copy, the flow kernel and the D2H copy of
         neighbouring chunks overlap.  x_host: CPU float32 [N,K] (pinned memory gives full PCIe
@@ -172,30 +172,15 @@ class StackEngine:
             raise NotImplementedError('cnf_b200: bf16 tensor-core path not available for this flow shape')
         if repack:
             self.pack(tc=use_tc)
-        st = getattr(self, '_host_slots', None)
-        if st is None or st[0] != (device, chunk, slots):
-            bufs = [(torch.cuda.Stream(device), torch.empty((chunk, K), dtype=torch.float32, device=device),
-                     torch.empty((chunk, K), dtype=torch.float32, device=device),
-                     torch.empty(chunk, dtype=torch.float32, device=device)) for _ in range(slots)]
-            st = self._host_slots = ((device, chunk, slots), bufs)
-        main = torch.cuda.current_stream(device)
-        fn = 'cnf_flow_inverse' if inverse else 'cnf_flow_forward'
+        ws = getattr(self, '_host_ws', None)
+        need = slots * chunk * (2 * K + 1) * 4
+        if ws is None or ws.device != device or ws.numel() < need:
+            ws = self._host_ws = torch.empty(need, dtype=torch.uint8, device=device)
         desc = self.desc_tc if use_tc else self.desc
         packed = self.packed_tc if use_tc else self.packed
-        for i, lo in enumerate(range(0, N, chunk)):
-            hi = min(N, lo + chunk)
-            n = hi - lo
-            stream, xin, zout, ldout = st[1][i % slots]
-            if i < slots:
-                stream.wait_stream(main)        # weights were packed on the caller's stream
-            with torch.cuda.stream(stream):
-                xin[:n].copy_(x_host[lo:hi], non_blocking=True)
-                _lib.call(fn, ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(xin), _ptr(zout),
-                          _ptr(ldout), None, ctypes.c_int64(n), ctypes.c_void_p(stream.cuda_stream))
-                out_host[lo:hi].copy_(zout[:n], non_blocking=True)
-                ld_host[lo:hi].copy_(ldout[:n], non_blocking=True)
-        for stream, *_ in st[1]:
-            main.wait_stream(stream)
+        _lib.call('cnf_flow_apply_host', ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x_host),
+                  _ptr(out_host), _ptr(ld_host), ctypes.c_int64(N), ctypes.c_int32(1 if inverse else 0), _ptr(ws),
+                  ctypes.c_int64(need), ctypes.c_int64(chunk), _stream(device))
         return out_host, ld_host
 
     def backward(self, x, g_z, g_ld, need_gx=True):

@@ -47,6 +47,7 @@ SIGNATURES = {
     'cnf_pack_weights_tc': [_DESC, _P, _P, _P, _P],
     'cnf_flow_forward': [_DESC, _P, _P, _P, _P, _P, _P, _I64, _P],
     'cnf_flow_inverse': [_DESC, _P, _P, _P, _P, _P, _P, _I64, _P],
+    'cnf_flow_apply_host': [_DESC, _P, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I64, _P],
     'cnf_nll_train_step': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P],
     'cnf_flow_backward': [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
     'cnf_grad_reduce': [_DESC, _P, _P, _P, _P],

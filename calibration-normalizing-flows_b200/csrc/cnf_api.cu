@@ -2,6 +2,8 @@
 // kernels (cnf_flow_fp32.cu) and the bf16 tcgen05 kernel (cnf_flow_tc.cu).  See include/cnf.h.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cnf_common.h"
 
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
@@ -61,4 +63,93 @@ extern "C" int cnf_flow_backward(const cnf_flow_desc* desc, const void* packed, 
   if (desc->precision != CNF_PREC_FP32) { cnf_set_error("backward runs on the fp32 path"); return CNF_E_UNSUPPORTED; }
   return cnf_fp32_train(desc, (const float*)packed, tables, x, nullptr, g_z, g_logdet, g_x, grad_partials, nullptr, N,
                         0.f, 0.f, 0.f, CNF_HEAD_EXTERNAL, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer entry point: the whole N-sample pass with the H2D copy of x and the D2H copies of
+// z / log-det inside, chunked over a small pool of internal streams so that the copy-in, the
+// flow kernel and the copy-out of neighbouring chunks overlap (PCIe is full duplex).  The chunk
+// loop runs here, not in Python: at ~250k samples per chunk the per-chunk host cost must stay
+// in the microseconds.  Asynchronous like every other call: completion is ordered on `stream`.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int kHostSlots = 4;
+struct HostPool {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t s[kHostSlots];
+  cudaEvent_t done[kHostSlots];
+  cudaEvent_t start;
+};
+HostPool g_pool;   // one-time, per process (single device per process in this framework)
+
+int pool_init() {
+  int dev = 0;
+  CNF_CHECK_CUDA(cudaGetDevice(&dev));
+  if (g_pool.ready && g_pool.device == dev) return CNF_OK;
+  for (int i = 0; i < kHostSlots; ++i) {
+    CNF_CHECK_CUDA(cudaStreamCreateWithFlags(&g_pool.s[i], cudaStreamNonBlocking));
+    CNF_CHECK_CUDA(cudaEventCreateWithFlags(&g_pool.done[i], cudaEventDisableTiming));
+  }
+  CNF_CHECK_CUDA(cudaEventCreateWithFlags(&g_pool.start, cudaEventDisableTiming));
+  g_pool.ready = true;
+  g_pool.device = dev;
+  return CNF_OK;
+}
+}  // namespace
+
+extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                                   const float* x_host, float* z_host, float* logdet_host, int64_t N, int32_t inverse,
+                                   void* workspace, int64_t workspace_bytes, int64_t chunk, void* stream) {
+  int rc = check_prec(desc);
+  if (rc) return rc;
+  if (N == 0) return CNF_OK;
+  if (!packed || !tables || !x_host || !z_host || !logdet_host || !workspace || N < 0 || chunk < 1) {
+    cnf_set_error("cnf_flow_apply_host: bad argument");
+    return CNF_E_ARG;
+  }
+  const int K = desc->K;
+  const int64_t per_slot = chunk * (2 * (int64_t)K + 1) * (int64_t)sizeof(float);
+  int slots = (int)(workspace_bytes / per_slot);
+  if (slots > kHostSlots) slots = kHostSlots;
+  if (slots < 1) { cnf_set_error("cnf_flow_apply_host: workspace smaller than one chunk (%lld bytes needed)", (long long)per_slot); return CNF_E_ARG; }
+  cudaStream_t user = (cudaStream_t)stream;
+  // Zero-copy fast path: when all three host buffers are pinned (device-addressable under UVA) and
+  // the tensor-core kernel runs, launch it ONCE on the host pointers.  Its tile prefetch
+  // (cp.async, one tile ahead per slot, ~2 MB in flight) hides the PCIe latency and both
+  // directions stream concurrently, without per-chunk DMA set-up costs: 1.18 ms vs 1.58 ms per
+  // 10^6 K=10 samples on B200 (46 GB/s per direction when both are busy).
+  if (desc->precision == CNF_PREC_BF16_TC && !getenv("CNF_NO_ZEROCOPY")) {
+    cudaPointerAttributes ax, az, al;
+    const bool ok = cudaPointerGetAttributes(&ax, x_host) == cudaSuccess && ax.type == cudaMemoryTypeHost &&
+                    cudaPointerGetAttributes(&az, z_host) == cudaSuccess && az.type == cudaMemoryTypeHost &&
+                    cudaPointerGetAttributes(&al, logdet_host) == cudaSuccess && al.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers
+    if (ok)
+      return cnf_tc_apply(desc, packed, tables, (const float*)ax.devicePointer, (float*)az.devicePointer,
+                          (float*)al.devicePointer, N, inverse, user);
+  }
+  if ((rc = pool_init())) return rc;
+  CNF_CHECK_CUDA(cudaEventRecord(g_pool.start, user));          // weights were packed on the caller's stream
+  for (int i = 0; i < slots; ++i) CNF_CHECK_CUDA(cudaStreamWaitEvent(g_pool.s[i], g_pool.start, 0));
+  int64_t lo = 0;
+  for (int64_t c = 0; lo < N; ++c, lo += chunk) {
+    const int64_t n = (N - lo < chunk) ? N - lo : chunk;
+    const int i = (int)(c % slots);
+    cudaStream_t st = g_pool.s[i];
+    float* xin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + (size_t)i * per_slot);
+    float* zout = xin + chunk * K;
+    float* ld = zout + chunk * K;
+    CNF_CHECK_CUDA(cudaMemcpyAsync(xin, x_host + lo * K, (size_t)n * K * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (desc->precision == CNF_PREC_BF16_TC) rc = cnf_tc_apply(desc, packed, tables, xin, zout, ld, n, inverse, st);
+    else rc = cnf_fp32_apply(desc, (const float*)packed, tables, xin, zout, ld, nullptr, n, inverse, st);
+    if (rc) return rc;
+    CNF_CHECK_CUDA(cudaMemcpyAsync(z_host + lo * K, zout, (size_t)n * K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CNF_CHECK_CUDA(cudaMemcpyAsync(logdet_host + lo, ld, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < slots; ++i) {
+    CNF_CHECK_CUDA(cudaEventRecord(g_pool.done[i], g_pool.s[i]));
+    CNF_CHECK_CUDA(cudaStreamWaitEvent(user, g_pool.done[i], 0));
+  }
+  return CNF_OK;
 }

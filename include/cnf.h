@@ -112,6 +112,17 @@ int cnf_flow_forward(const cnf_flow_desc* desc, const void* packed, const int32_
 int cnf_flow_inverse(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
                      const float* z, float* x, float* logdet, float* xs, int64_t N, void* stream);
 
+/* Host-buffer variant of the two calls above: x_host / z_host / logdet_host are HOST pointers
+ * (pinned memory gives full PCIe speed).  The samples stream through the GPU in chunks of `chunk`
+ * rows on internal streams so H2D, kernel and D2H of neighbouring chunks overlap; `workspace` is a
+ * DEVICE buffer of at least chunk*(2K+1)*4 bytes (up to 4 such slots are used).  Asynchronous:
+ * completion is ordered on `stream`.  This is what predict_logits (calibrators.py:330-348) does
+ * with tensor.to(dev) / .cpu().                                                              */
+int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                        const float* x_host, float* z_host, float* logdet_host, int64_t N,
+                        int32_t inverse, void* workspace, int64_t workspace_bytes, int64_t chunk,
+                        void* stream);
+
 /* ---- device: training --------------------------------------------------------- */
 /* One fused pass over N local samples: forward, loss head, backward.
  *   loss_i = -( log(softmax(z_i)[y_i] + eps) + gamma * logdet_i );  eps==0 -> log-softmax.

@@ -296,3 +296,28 @@ def test_full_size_properties_c2(cuda_device):
     zo, ldo = orc.flow_forward(p, x[idx].astype(np.float64))
     assert rel_err(zs[-1][tidx].cpu().numpy(), zo[-1]) < TOL
     assert ld_err(ld[tidx].cpu().numpy(), ldo) < TOL
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_host_buffer_api_matches_device_api(precision, cuda_device):
+    """cnf_flow_apply_host (chunked H2D -> kernel -> D2H on internal streams) == device-resident call."""
+    import torch
+    import cnf_b200
+    torch.manual_seed(0)
+    model = cnf_b200.RealNvpFlow(10, layers=6, hidden_size=[128], precision=precision)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(300.0)
+    model.to(cuda_device)
+    N = 300_007                                      # ragged: not a multiple of the chunk or the tile
+    x, _ = orc.synth_logits(N, 10, seed=8)
+    xh = torch.from_numpy(x).pin_memory()
+    zh, lh = model.transform_host(xh, device=cuda_device, chunk=65536)
+    with torch.no_grad():
+        z, ld = model(torch.from_numpy(x).to(cuda_device))
+    assert torch.equal(zh, z.cpu()) and torch.equal(lh, ld.cpu())
+    # pageable numpy input and inverse direction
+    zi, li = model.engine().apply_host(zh.numpy(), inverse=True, precision=precision, device=cuda_device)
+    torch.cuda.synchronize()
+    assert rel_err(zi.numpy(), x) < (1e-2 if precision == 'bf16' else 5e-5)
