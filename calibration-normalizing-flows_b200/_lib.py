@@ -55,6 +55,8 @@ SIGNATURES = {
     'cnf_sgd_step': [_P, _P, _I64, _F32, _F32, _P],
     'cnf_metrics': [_P, _I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
     'cnf_calibrated_probs': [_P, _I64, _I32, _P, _P, _P],
+    'cnf_affine_const': [_P, _P, _P, _P, _I64, _I32, _I32, _P],
+    'cnf_affine_const_backward': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
 }
 
 _lib = None

@@ -21,11 +21,84 @@ import torch
 from torch import nn
 
 from .utils import MLP
-from .._engine import StackEngine, stack_forward, require_cuda
+import ctypes
+
+from .. import _lib
+from .._engine import StackEngine, stack_forward, require_cuda, _ptr, _stream
 
 
 def _zero_net(x):
     return x.new_zeros(x.size())
+
+
+class _AffineConstFn(torch.autograd.Function):
+    """z = x*exp(s)+t per dimension through cnf_affine_const; s/t are [K] tensors or None."""
+
+    @staticmethod
+    def forward(ctx, x, s, t):
+        x = x.to(torch.float32).contiguous()
+        N, K = x.shape
+        z = torch.empty_like(x)
+        sv = None if s is None else s.detach().to(torch.float32).contiguous()
+        tv = None if t is None else t.detach().to(torch.float32).contiguous()
+        _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(N), ctypes.c_int32(K),
+                  ctypes.c_int32(0), _stream(x.device))
+        ctx.save_for_backward(x, sv)
+        ctx.has = (s is not None, t is not None)
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        x, sv = ctx.saved_tensors
+        N, K = x.shape
+        g_z = g_z.to(torch.float32).contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gs = torch.empty(K, dtype=torch.float32, device=x.device) if ctx.has[0] else None
+        gt = torch.empty(K, dtype=torch.float32, device=x.device) if ctx.has[1] else None
+        _lib.call('cnf_affine_const_backward', _ptr(x), _ptr(g_z), _ptr(sv), _ptr(gx), _ptr(gs), _ptr(gt),
+                  ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        return gx, gs, gt
+
+
+def affine_const_apply(x, s=None, t=None, inverse=False):
+    """Non-differentiable helper: forward or inverse of the per-dimension affine map."""
+    require_cuda(x)
+    x = x.detach().to(torch.float32).contiguous()
+    z = torch.empty_like(x)
+    sv = None if s is None else s.detach().to(torch.float32).contiguous().view(-1)
+    tv = None if t is None else t.detach().to(torch.float32).contiguous().view(-1)
+    _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(x.shape[0]),
+              ctypes.c_int32(x.shape[1]), ctypes.c_int32(1 if inverse else 0), _stream(x.device))
+    return z
+
+
+class AffineConstantLayer(nn.Module):
+    """Drop-in for reference ``flows/flows.py:40-65``: learned per-dimension scale and shift.
+    As in the reference, ``log_det`` has shape [1] when ``scale`` (it is ``sum(s, dim=1)`` of a
+    [1, dim] parameter) and [N] zeros otherwise."""
+
+    def __init__(self, dim, scale=True, shift=True):
+        super().__init__()
+        self.s = nn.Parameter(torch.zeros(1, dim)) if scale else None
+        self.t = nn.Parameter(torch.zeros(1, dim)) if shift else None
+        self.invertible = True
+
+    def forward(self, x):
+        require_cuda(x)
+        s = None if self.s is None else self.s.view(-1)
+        t = None if self.t is None else self.t.view(-1)
+        if torch.is_grad_enabled() and (x.requires_grad or s is not None or t is not None):
+            z = _AffineConstFn.apply(x, s, t)
+        else:
+            z = affine_const_apply(x, s, t)
+        log_det = torch.sum(self.s, dim=1) if self.s is not None else x.new_zeros(x.shape[0])
+        return z, log_det
+
+    def backward(self, z):
+        require_cuda(z)
+        x = affine_const_apply(z, None if self.s is None else self.s, None if self.t is None else self.t, inverse=True)
+        log_det = torch.sum(-self.s, dim=1).detach() if self.s is not None else z.new_zeros(z.shape[0])
+        return x, log_det
 
 
 class NvpCouplingLayer(nn.Module):

@@ -42,3 +42,25 @@ class MLP(nn.Module):
         for lin in hidden:
             x = self.activation(lin(x))
         return last(x)
+
+
+class TempScaler(nn.Module):
+    """Drop-in for reference ``flows/utils.py:34-48``: ``z = x / |T|`` (and its inverse), through the
+    per-dimension affine kernel with ``s_k = -log|T|``.  Returns the tensor only, as the reference."""
+
+    def __init__(self):
+        super().__init__()
+        self.T = nn.Parameter(torch.ones(1))
+
+    def _s(self, x):
+        return (-torch.log(torch.abs(self.T))).expand(x.shape[1])
+
+    def forward(self, x):
+        from .flows import _AffineConstFn, affine_const_apply
+        if torch.is_grad_enabled():
+            return _AffineConstFn.apply(x, self._s(x), None)
+        return affine_const_apply(x, self._s(x), None)
+
+    def backward(self, z):
+        from .flows import affine_const_apply
+        return affine_const_apply(z, self._s(z), None, inverse=True)

@@ -160,6 +160,17 @@ int cnf_metrics(const void* in, int32_t is_f64, const int64_t* y, int64_t N, int
 int cnf_calibrated_probs(const float* z, int64_t N, int32_t K, const double* log_priors,
                          double* probs_out, void* stream);
 
+/* ---- device: per-dimension constant affine layer (next-row 8f/2) ---------------------------------
+ * AffineConstantLayer.forward / .backward (flows/flows.py:53-65): z = x*exp(s)+t, or with
+ * inverse != 0 x = (z-t)*exp(-s).  s / t are DEVICE float32 [K] or NULL (= zeros).  TempScaler
+ * (flows/utils.py:40-48) is s_k = -log|T|, t = NULL.                                              */
+int cnf_affine_const(const float* x, const float* s, const float* t, float* z, int64_t N, int32_t K,
+                     int32_t inverse, void* stream);
+/* Gradients of the forward direction: g_x = g_z*exp(s) (may be NULL), g_s[k] = sum_n g_z*x*exp(s),
+ * g_t[k] = sum_n g_z (either may be NULL; both are overwritten).                                    */
+int cnf_affine_const_backward(const float* x, const float* g_z, const float* s, float* g_x, float* g_s,
+                              float* g_t, int64_t N, int32_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,9 +245,51 @@ def gen_metrics_cases():
     print('metrics cases', {k: float(v) for k, v in out.items() if k.endswith('ece15')})
 
 
+def gen_affine_case():
+    """AffineConstantLayer / TempScaler (flows/flows.py:40-65, flows/utils.py:34-48) inside a Flow with
+    coupling layers on both sides, as notebooks/train-flows-det.ipynb cell 11 stacks them."""
+    from flows.flows import AffineConstantLayer
+    from flows.utils import TempScaler
+    torch.manual_seed(31)
+    K, N = 6, 50
+    aff = AffineConstantLayer(K)
+    with torch.no_grad():
+        aff.s.copy_(0.3 * torch.randn(1, K))
+        aff.t.copy_(torch.randn(1, K))
+    c0 = NvpCouplingLayer(K, hidden_size=[8])
+    c1 = NvpCouplingLayer(K, hidden_size=[8])
+    with torch.no_grad():
+        for lay in (c0, c1):
+            for p in lay.parameters():
+                if p.requires_grad:
+                    p.mul_(300.0)
+    flow = Flow([c0, aff, c1])
+    x, y = orc.synth_logits(N, K, seed=9)
+    xt = torch.as_tensor(x).requires_grad_(True)
+    zs, ld = flow(xt)
+    loss = torch.nn.CrossEntropyLoss()(zs[-1], torch.as_tensor(y)) - torch.mean(ld)
+    loss.backward()
+    with torch.no_grad():
+        xs, ldi = flow.backward(zs[-1])
+    ts = TempScaler()
+    with torch.no_grad():
+        ts.T.fill_(-1.7)
+    zt = ts(torch.as_tensor(x).requires_grad_(True))
+    lt = (zt ** 2).sum()
+    lt.backward()
+    sd = {k: v.detach().numpy() for k, v in flow.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, 'affine.npz'), K=K, x=x, y=y, z=zs[-1].detach().numpy(), z_mid=zs[1].detach().numpy(),
+                        logdet=ld.detach().numpy(), loss=float(loss.detach()), gx=xt.grad.numpy(),
+                        g_s=aff.s.grad.numpy(), g_t=aff.t.grad.numpy(), g_w=c0.s.layers[0].weight.grad.numpy(),
+                        x_rec=xs[-1].numpy(), logdet_inv=ldi.numpy(), temp_z=zt.detach().numpy(),
+                        temp_gT=ts.T.grad.numpy(), **{'sd_' + k: v for k, v in sd.items()})
+    print('affine case loss', float(loss.detach()))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # bit-stable reductions
     gen_flow_cases()
     gen_calibrator_case()
     gen_metrics_cases()
+    gen_affine_case()

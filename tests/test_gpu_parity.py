@@ -321,3 +321,46 @@ def test_host_buffer_api_matches_device_api(precision, cuda_device):
     zi, li = model.engine().apply_host(zh.numpy(), inverse=True, precision=precision, device=cuda_device)
     torch.cuda.synchronize()
     assert rel_err(zi.numpy(), x) < (1e-2 if precision == 'bf16' else 5e-5)
+
+
+def test_affine_constant_layer_and_tempscaler_vs_reference(cuda_device):
+    """AffineConstantLayer between coupling layers (loaded through the reference's
+    own state_dict keys), forward / inverse / autograd; TempScaler forward and dT."""
+    import torch
+    import cnf_b200
+    g = load_golden('affine')
+    K = int(g['K'])
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, [8]), cnf_b200.AffineConstantLayer(K),
+                          cnf_b200.NvpCouplingLayer(K, [8])])
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd_')}
+    assert set(sd) == set(flow.state_dict().keys())
+    flow.load_state_dict(sd)
+    flow.to(cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device).requires_grad_(True)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    zs, ld = flow(x)
+    assert rel_err(zs[-1].detach().cpu().numpy(), g['z']) < 1e-5
+    assert rel_err(zs[1].detach().cpu().numpy(), g['z_mid']) < 1e-5
+    assert np.max(np.abs(ld.detach().cpu().numpy() - g['logdet'])) < 1e-5 * max(1.0, np.max(np.abs(g['logdet'])))
+    loss = torch.nn.CrossEntropyLoss()(zs[-1], y) - torch.mean(ld)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g['loss'])) < 1e-5
+    assert rel_err(x.grad.cpu().numpy(), g['gx']) < 2e-4
+    aff = flow.layers[1]
+    assert rel_err(aff.s.grad.cpu().numpy(), g['g_s']) < 2e-4
+    assert rel_err(aff.t.grad.cpu().numpy(), g['g_t']) < 2e-4
+    assert rel_err(flow.layers[0].s.layers[0].weight.grad.cpu().numpy(), g['g_w']) < 2e-4
+    with torch.no_grad():
+        xs, ldi = flow.backward(zs[-1].detach())
+    assert rel_err(xs[-1].cpu().numpy(), g['x_rec']) < 5e-5
+    assert np.max(np.abs(ldi.cpu().numpy() - g['logdet_inv'])) < 1e-5 * max(1.0, np.max(np.abs(g['logdet_inv'])))
+    ts = cnf_b200.TempScaler().to(cuda_device)
+    with torch.no_grad():
+        ts.T.fill_(-1.7)
+    xt = torch.from_numpy(g['x']).to(cuda_device)
+    zt = ts(xt)
+    assert rel_err(zt.detach().cpu().numpy(), g['temp_z']) < 1e-6
+    (zt ** 2).sum().backward()
+    assert rel_err(ts.T.grad.cpu().numpy(), g['temp_gT']) < 1e-4
+    with torch.no_grad():
+        assert rel_err(ts.backward(zt.detach()).cpu().numpy(), g['x']) < 1e-6
