@@ -125,3 +125,29 @@ def test_onehot_matches_oracle():
     y = np.array([0, 3, 1, 3, 2])
     assert np.array_equal(cnf_b200.onehot_encode(y), orc.onehot_encode(y))
     assert cnf_b200.onehot_encode(y).dtype == np.int32
+
+
+def test_on_disk_logit_formats_round_trip(tmp_path):
+    """the reference's file layouts (utils/data.py:170-210, scripts/compute_logits.py:70-74)."""
+    import pickle
+    import torch
+    from cnf_b200.utils import data as D
+    rng = np.random.default_rng(0)
+    lg, tg = rng.standard_normal((20, 3)), rng.integers(0, 3, 20)
+    np.save(tmp_path / 'bayes_separable_logits.npy', lg)
+    np.save(tmp_path / 'bayes_separable_target.npy', tg)
+    a, b = D.load_toy_dataset(str(tmp_path), 'bayes')
+    assert np.array_equal(a, lg) and np.array_equal(b, tg)
+    folder = tmp_path / 'resnet_cifar10'
+    folder.mkdir()
+    for split, n in (('train', 11), ('valid', 5), ('test', 7)):
+        np.save(folder / ('cifar10_resnet_logit_prediction_%s.npy' % split), rng.standard_normal((n, 10)))
+        np.save(folder / ('cifar10_resnet_true_%s.npy' % split), rng.integers(0, 10, n).astype(np.int32))
+    train, val, test = D.load_logits('cifar10', 'resnet', data_path=str(tmp_path), pin=False)
+    assert train[0].shape == (11, 10) and train[0].dtype == torch.float32 and train[1].dtype == torch.int64
+    assert val[0].shape == (5, 10) and test[1].shape == (7,)
+    for name, n in (('train_logits.pkl', 9), ('test_logits.pkl', 4)):
+        with open(tmp_path / name, 'wb') as f:
+            pickle.dump(rng.standard_normal((n, 10)).astype(np.float32), f)
+    tr, te = D.load_pickled_logits(str(tmp_path), pin=False)
+    assert tr.shape == (9, 10) and te.shape == (4, 10) and tr.dtype == torch.float32
