@@ -265,33 +265,46 @@ def run_ours(args):
            'h2d_bytes_per_step': xh.numel() * 4, 'd2h_bytes_per_step': zh.numel() * 4 + lh.numel() * 4,
            'api': 'RealNvpFlow.transform_host (pinned host logits in, host z + log-det out)'}
 
-    # ---- training step, config C3 shape (fp32 path) ------------------------------------------
-    train = None
+    # ---- training step, config C3 shape: tensor-core path (headline) and fp32 path -------------
+    train = train_fp32 = None
     if not args.no_train:
         n_loc = args.train_n or (64 * (1 << 20)) // world
         xt, yt = synth(n_loc, 5000 + rank, dev)
-        tmodel = make_weights(seed=2)
-        with torch.no_grad():
-            for p in tmodel.parameters():
-                if p.requires_grad:
-                    p.mul_(1.0 / 300.0)          # reference init for training
-        tmodel.to(dev)
-        tr = cnf_b200.FusedNLLTrainer(tmodel.engine(), xt, yt, n_total=n_loc * world)
-        for _ in range(3):
-            tr.step()
-        barrier()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        tsteps = max(3, min(args.steps, 5))
-        for _ in range(tsteps):
-            tr.step()
-        t1e.record()
-        barrier()
-        tms = max_over_ranks(t0e.elapsed_time(t1e))
-        train = {'value': world * n_loc * tsteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / tsteps,
-                 'samples_per_gpu': n_loc, 'samples_total': n_loc * world, 'scaling': 'strong (C3: 64 Mi samples over all GPUs)' if not args.train_n else 'weak', 'steps': tsteps, 'dtype': 'f32',
-                 'what': 'fused NLL fwd+bwd kernel + grad reduce' + (' + NCCL all-reduce' if world > 1 else '') +
-                         ' + Adam + repack per step', 'loss': -float(tr.loss_acc[0]) / (n_loc * world)}
+
+        def time_training(prec):
+            tmodel = make_weights(seed=2)
+            with torch.no_grad():
+                for p in tmodel.parameters():
+                    if p.requires_grad:
+                        p.mul_(1.0 / 300.0)          # reference init for training
+            tmodel.to(dev)
+            tr = cnf_b200.FusedNLLTrainer(tmodel.engine(), xt, yt, n_total=n_loc * world, precision=prec)
+            for _ in range(3):
+                tr.step()
+            barrier()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            tsteps = max(3, min(args.steps, 5))
+            for _ in range(tsteps):
+                tr.step()
+            t1e.record()
+            barrier()
+            tms = max_over_ranks(t0e.elapsed_time(t1e))
+            kern = ('tcgen05 forward (+tape) and backward kernels per 2^20-sample chunk' if prec == 'bf16'
+                    else 'fused NLL fwd+bwd kernel')
+            return {'value': world * n_loc * tsteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / tsteps,
+                    'samples_per_gpu': n_loc, 'samples_total': n_loc * world,
+                    'scaling': 'strong (C3: 64 Mi samples over all GPUs)' if not args.train_n else 'weak',
+                    'steps': tsteps, 'dtype': 'bf16' if prec == 'bf16' else 'f32',
+                    'what': kern + ' + grad reduce' + (' + NCCL all-reduce' if world > 1 else '') +
+                            ' + Adam + repack per step', 'loss': -float(tr.loss_acc[0]) / (n_loc * world)}
+
+        if precision == 'bf16':
+            train = time_training('bf16')
+            train['tensor_tflops_minimal'] = train['value'] * 4 * FLOPS_PER_SAMPLE / 1e12   # fwd + recompute + dgrad + wgrad
+        train_fp32 = time_training('fp32')
+        if train is None:
+            train = train_fp32
         del xt, yt
 
     # ---- config C5 pieces: inverse pass and the metrics kernel (HBM-bound) -------------------
@@ -407,7 +420,7 @@ def run_ours(args):
                 'config': {'workload': WORKLOAD, 'l2': 'inputs larger than L2: %d rotating batches' % N_ROT,
                            'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1'},
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
-                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'c5': extra}
+                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'train_step_fp32': train_fp32, 'c5': extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -65,6 +65,16 @@ class StackEngine:
             g = np.empty(int(n_g.value), dtype=np.int32)
             _lib.call('cnf_plan_build_tc', ctypes.byref(self.desc_tc), g.ctypes.data_as(ctypes.c_void_p))
             self._gather_tc_host = g
+        # tensor-core training (cnf_flow_tcb.cu): partial-row length, row count, workspace per sample
+        self.tc_train = None
+        if self.tc_bytes > 0:
+            ng, rows, wsb = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            _lib.call('cnf_tc_train_info', ctypes.byref(self.desc_tc), ctypes.byref(ng), ctypes.byref(rows),
+                      ctypes.byref(wsb))
+            if ng.value > 0:
+                g = np.empty(int(ng.value), dtype=np.int32)
+                _lib.call('cnf_plan_build_tcgrad', ctypes.byref(self.desc_tc), g.ctypes.data_as(ctypes.c_void_p))
+                self.tc_train = (int(ng.value), int(rows.value), int(wsb.value), g)
         self.device = None
         self.flat = None
         self.partials = None
@@ -93,6 +103,7 @@ class StackEngine:
             self.packed_tc = torch.empty(self.tc_bytes, dtype=torch.uint8, device=device)
         self.partials = None
         self.flat_grad = None
+        self.partials_tc = self.gather_tcgrad = self._train_ws = None
         # optimiser state follows the parameters (the reference keeps it in self.optimizer)
         if self.adam_m is not None:
             self.adam_m = self.adam_m.to(device)
@@ -199,12 +210,41 @@ class StackEngine:
                   _ptr(flat_grad), st)
         return gx, flat_grad
 
-    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True):
+    TRAIN_CHUNK = 1 << 20   # samples per forward/backward kernel pair on the tensor-core training path
+
+    def _nll_step_tc(self, x, y, loss_acc, eps, gamma, n_total, with_grad):
+        if self.tc_train is None:
+            raise NotImplementedError('cnf_b200: the bf16 tensor-core training path does not cover this flow shape '
+                                      '(K=%d, hidden=%s, L=%d); use precision="fp32"' % (self.K, self.hidden, self.L))
+        n_grad, rows, wsb, g_host = self.tc_train
+        N = x.shape[0]
+        st = _stream(x.device)
+        if self.flat_grad is None:
+            self.flat_grad = torch.zeros(self.n_flat, dtype=torch.float32, device=self.device)
+        if with_grad and self.partials_tc is None:
+            self.partials_tc = torch.empty(rows * n_grad, dtype=torch.float32, device=self.device)
+            self.gather_tcgrad = torch.from_numpy(g_host).to(self.device)
+        chunk = max(1024, min(self.TRAIN_CHUNK, (N + 1023) // 1024 * 1024))
+        need = chunk * wsb
+        if self._train_ws is None or self._train_ws.numel() < need:
+            self._train_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.call('cnf_nll_train_step_tc', ctypes.byref(self.desc_tc), _ptr(self.packed_tc), _ptr(self.tables),
+                  _ptr(x), _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
+                  ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials_tc) if with_grad else None,
+                  _ptr(loss_acc), _ptr(self._train_ws), ctypes.c_int64(need), st)
+        if with_grad:
+            _lib.call('cnf_grad_reduce_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc),
+                      _ptr(self.gather_tcgrad), _ptr(self.flat_grad), st)
+
+    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision='fp32'):
         """One fused forward+loss(+backward) pass over the local samples.  Accumulates the
         loss sums into loss_acc (float64 [4], device) and, with_grad, leaves
-        d(sum loss)/n_total in self.flat_grad."""
+        d(sum loss)/n_total in self.flat_grad.  precision='bf16' runs the tcgen05 forward and
+        backward kernels (weights must have been packed with pack(tc=True))."""
         N = x.shape[0]
         n_total = N if n_total is None else n_total
+        if precision == 'bf16':
+            return self._nll_step_tc(x, y, loss_acc, eps, gamma, n_total, with_grad)
         st = _stream(x.device)
         if with_grad:
             self._want_partials()

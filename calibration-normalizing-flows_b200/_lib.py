@@ -51,6 +51,11 @@ SIGNATURES = {
     'cnf_nll_train_step': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P],
     'cnf_flow_backward': [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
     'cnf_grad_reduce': [_DESC, _P, _P, _P, _P],
+    'cnf_tc_train_info': [_DESC, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                          ctypes.POINTER(ctypes.c_int64)],
+    'cnf_plan_build_tcgrad': [_DESC, _P],
+    'cnf_nll_train_step_tc': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P, _I64, _P],
+    'cnf_grad_reduce_tc': [_DESC, _P, _P, _P, _P],
     'cnf_adam_step': [_P, _P, _P, _P, _I64, _I64, _F32, _F32, _F32, _F32, _F32, _P],
     'cnf_sgd_step': [_P, _P, _I64, _F32, _F32, _P],
     'cnf_metrics': [_P, _I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],

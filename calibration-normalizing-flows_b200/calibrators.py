@@ -73,8 +73,9 @@ class FusedNLLTrainer:
     same optimiser update, so parameters stay bit-identical across ranks without a broadcast."""
 
     def __init__(self, engine, x, y, n_total=None, eps=1e-7, gamma=1.0, lr=1e-3, betas=(0.9, 0.999),
-                 adam_eps=1e-8, weight_decay=0.0, optim='adam'):
+                 adam_eps=1e-8, weight_decay=0.0, optim='adam', precision='fp32'):
         self.engine, self.x, self.y = engine, x, y
+        self.precision = precision
         self.n_local = x.shape[0]
         self.dist = _dist()
         if n_total is None:
@@ -87,7 +88,7 @@ class FusedNLLTrainer:
         self.eps, self.gamma = eps, gamma
         self.lr, self.betas, self.adam_eps, self.wd, self.optim = lr, betas, adam_eps, weight_decay, optim
         engine.ensure(x.device)
-        engine.pack()
+        engine.pack(tc=(precision == 'bf16'))
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=x.device)
 
     def step(self, xb=None, yb=None, n_batch_total=None):
@@ -98,7 +99,7 @@ class FusedNLLTrainer:
         yb = self.y if yb is None else yb
         n_tot = self.n_total if n_batch_total is None else n_batch_total
         self.loss_acc.zero_()
-        e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True)
+        e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision)
         if self.dist is not None:
             self.dist.all_reduce(e.flat_grad)
             self.dist.all_reduce(self.loss_acc)
@@ -106,7 +107,7 @@ class FusedNLLTrainer:
             e.adam(self.lr, self.betas, self.adam_eps, self.wd)
         else:
             e.sgd(self.lr, self.wd)
-        e.pack()
+        e.pack(tc=(self.precision == 'bf16'))
 
     def evaluate(self, xb=None, yb=None, out=None):
         """Loss statistics (sum(ce+gamma*ld), sum ce, sum ld, #non-finite) of a batch, summed
@@ -115,7 +116,7 @@ class FusedNLLTrainer:
         xb = self.x if xb is None else xb
         yb = self.y if yb is None else yb
         acc = torch.zeros(4, dtype=torch.float64, device=xb.device) if out is None else out.zero_()
-        e.nll_step(xb, yb, acc, self.eps, self.gamma, self.n_total, with_grad=False)
+        e.nll_step(xb, yb, acc, self.eps, self.gamma, self.n_total, with_grad=False, precision=self.precision)
         if self.dist is not None:
             self.dist.all_reduce(acc)
         return acc
@@ -139,6 +140,8 @@ class TorchFlowCalibrator(Calibrator):
         if self.dev.index is None:
             self.dev = torch.device('cuda', torch.cuda.current_device())
 
+        # extension: precision='bf16' trains on the tcgen05 kernels (stated bf16 tolerance); default fp32
+        self.precision = kwargs.get('precision', 'fp32')
         self.CE = torch.nn.CrossEntropyLoss()
         self.optimizer = torch.optim.Adam(self.flow.parameters())
         self.history = self.fit(self.logits, self.target,
@@ -168,7 +171,8 @@ class TorchFlowCalibrator(Calibrator):
         eng = self._engine()
         group = self.optimizer.param_groups[0]
         trainer = FusedNLLTrainer(eng, x, y, n_total=n_all, eps=1e-7, gamma=1.0, lr=group['lr'],
-                                  betas=group['betas'], adam_eps=group['eps'], weight_decay=group['weight_decay'])
+                                  betas=group['betas'], adam_eps=group['eps'], weight_decay=group['weight_decay'],
+                                  precision=getattr(self, 'precision', 'fp32'))
         self.trainer = trainer
         n_local = x.shape[0]
         world = dist.get_world_size() if dist is not None else 1

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "cnf_common.h"
+#include "cnf_tc_dims.h"
 #include "cnf_tc_ptx.cuh"
 
 int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
@@ -44,17 +45,10 @@ constexpr int A1_BYTES = TILE_M * 32;   // 128 rows x 16 bf16
 constexpr int LBO1 = 128, SBO1 = 256;   // A1 / B1: k-halves adjacent, 8-row groups 256 B apart
 constexpr int LBO2 = 256, SBO2 = 128;   // B2 per k-step: two 8-row groups adjacent, k-halves 256 B apart
 
-struct TcDims {
-  int K, L, d0, d1, Hp, nets, n_nets, N1;
-  int b_layer_bytes;                 // bytes of one layer's B1 (== B2): N1*16*2
-  int b1_off, b2_off, bias_off;      // byte offsets inside the blob
-  int n_bf16, n_f32, blob_bytes;
-  int tab_pi, tab_cond, tab_trans, n_tables;
-  // shared-memory carve-up (bytes)
-  int sm_tab, sm_slot, sm_slot_stride, sm_act, sm_raw_in, sm_raw_out, sm_bar, sm_total;
-};
 
-bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
+}  // namespace
+
+bool cnf_tc_dims(const CnfDims& d, TcDims* t) {
   if (d.m != 1 || d.n_nets < 1) return false;
   if (d.d1 + 1 > 16 || d.d0 > 8) return false;
   const int N1 = d.n_nets * d.Hp[0];
@@ -82,9 +76,10 @@ bool tc_dims(const cnf_flow_desc* desc, const CnfDims& d, TcDims* t) {
   off += TC_SLOTS * t->sm_slot_stride;
   t->sm_bar = off; off += 128;
   t->sm_total = off;
-  (void)desc;
   return t->sm_total <= 227 * 1024;
 }
+
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // kernel
@@ -107,7 +102,7 @@ template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
-               int inverse, int io16) {
+               int inverse, int io16, float* __restrict__ tape) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
@@ -326,6 +321,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         tc_fence_after();
         {
           uint32_t r[16];
+          float svs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           tmem_ld16(tm + d2_col, r);
           tmem_wait_ld16(r);
 #pragma unroll
@@ -340,7 +336,15 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
               if (!inverse) { yv = xv[q] * expf(sv) + tv; ld += sv; }
               else          { yv = (xv[q] - tv) * expf(-sv); ld -= sv; }
               act[ps[q]] = yv;
+              svs[q] = sv;
             }
+          }
+          if (tape != nullptr && base + t < N) {   // training: what autograd would save for this layer
+            float4* tp = reinterpret_cast<float4*>(tape + ((size_t)l * N + (base + t)) * 16);
+            tp[0] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            tp[1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
+            tp[2] = make_float4(svs[0], svs[1], svs[2], svs[3]);
+            tp[3] = make_float4(svs[4], svs[5], svs[6], svs[7]);
           }
         }
       }
@@ -387,7 +391,7 @@ int g_tc_sms = -1;
 
 long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d) {
   TcDims t;
-  if (tc_dims(desc, d, &t)) return (long long)t.blob_bytes;
+  if (cnf_tc_dims(d, &t)) return (long long)t.blob_bytes;
   return cnf_tcw_blob_bytes(d);
 }
 
@@ -398,7 +402,7 @@ extern "C" int cnf_tc_gather_len(const cnf_flow_desc* desc, int64_t* n) {
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!n) { cnf_set_error("null out"); return CNF_E_ARG; }
-  *n = tc_dims(desc, d, &t) ? (int64_t)t.n_bf16 + t.n_f32 : (int64_t)cnf_tcw_gather_len(d);
+  *n = cnf_tc_dims(d, &t) ? (int64_t)t.n_bf16 + t.n_f32 : (int64_t)cnf_tcw_gather_len(d);
   return CNF_OK;
 }
 
@@ -407,7 +411,7 @@ extern "C" int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* g) {
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!g) { cnf_set_error("null output"); return CNF_E_ARG; }
-  if (!tc_dims(desc, d, &t)) return cnf_tcw_plan_build(d, g);
+  if (!cnf_tc_dims(d, &t)) return cnf_tcw_plan_build(d, g);
   const int K = d.K, half = K / 2, H = d.H[0], Hp = d.Hp[0];
   for (int i = 0; i < t.n_bf16 + t.n_f32; ++i) g[i] = -1;
   // canonical flat offsets of one net: W0 [H,K], b0 [H], W1 [K,H], b1 [K]
@@ -458,7 +462,7 @@ extern "C" int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat,
   if (rc) return rc;
   if (!flat || !gather_tc || !packed_tc) { cnf_set_error("cnf_pack_weights_tc: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (!tc_dims(desc, d, &t)) return cnf_tcw_pack(d, flat, gather_tc, packed_tc, st);
+  if (!cnf_tc_dims(d, &t)) return cnf_tcw_pack(d, flat, gather_tc, packed_tc, st);
   if ((rc = cnf_pack_bf16(flat, gather_tc, packed_tc, t.n_bf16, st))) return rc;
   gather_f32_kernel<<<(t.n_f32 + 127) / 128, 128, 0, st>>>(flat, gather_tc + t.n_bf16,
                                                            reinterpret_cast<float*>((uint8_t*)packed_tc + t.bias_off), t.n_f32);
@@ -466,14 +470,27 @@ extern "C" int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat,
   return CNF_OK;
 }
 
+int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                      float* logdet, float* tape, int64_t N, int inverse, cudaStream_t st);
+
 int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                  float* logdet, int64_t N, int inverse, cudaStream_t st) {
+  return cnf_tc_apply_tape(desc, packed_tc, tables, x, z, logdet, nullptr, N, inverse, st);
+}
+
+// tape (optional, resident-weight kernel only): float32 [L, N, 16]; per layer and sample the pre-layer
+// values of the transformed slots (0..7) and the scale-net outputs s (8..15).
+int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                      float* logdet, float* tape, int64_t N, int inverse, cudaStream_t st) {
   CnfDims d; TcDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (N == 0) return CNF_OK;
   if (!packed_tc || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
-  if (!tc_dims(desc, d, &t)) return cnf_tcw_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
+  if (!cnf_tc_dims(d, &t)) {
+    if (tape) { cnf_set_error("the training tape is only produced by the resident-weight tensor-core kernel"); return CNF_E_UNSUPPORTED; }
+    return cnf_tcw_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
+  }
   if (g_tc_sms < 0) {
     int dev = 0, s = 0;
     CNF_CHECK_CUDA(cudaGetDevice(&dev));
@@ -488,10 +505,10 @@ int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t
   if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
   if (epi == 0) {
     CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
-    flow_tc_kernel<0><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16);
+    flow_tc_kernel<0><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16, tape);
   } else {
     CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
-    flow_tc_kernel<1><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16);
+    flow_tc_kernel<1><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16, tape);
   }
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;

@@ -1,0 +1,558 @@
+// bf16 tensor-core TRAINING backward of the coupling-flow stack for sm_100a (tcgen05 + TMEM).
+//
+// Replaces, for the shapes the resident-weight forward kernel covers (one hidden layer, K <= 14,
+// pad16(H) <= 128, L*nets <= 15), the autograd backward that the reference gets from torch
+// (loss.backward() at calibrators.py:293-294 / run_experiment3D.py:133-134) for the calibrator's
+// loss  -mean(log(softmax(z)[y]+eps) + gamma*log_det)  (calibrators.py:288-291).
+//
+// Inputs: the forward kernel's outputs for the same samples -- z, log-det and the per-layer tape
+// (pre-layer values of the transformed slots and the scale-net outputs s: exactly what autograd would
+// have saved) -- plus the labels.  Per tile of 128 samples and per coupling layer l = L-1 .. 0
+// (u = conditioning logits, x_t = transformed logits, g_y = upstream gradient on the transformed slots):
+//
+//   E0    g_s = g_y * x_t * e^s + g_ld ; g_t = g_y ; g_xt = g_y * e^s          (fp32, one thread per sample)
+//         shared-memory record per 8 samples: [G2s | G2t | 0 | A1 | 0] (bf16, 8x8 core matrices)
+//   per conditioner net p (s, then t):
+//   T1    D1 [128 smp x Hp] = A1 . B1p^T         (recompute of the hidden pre-activations, bias folded)
+//         GH [128 smp x Hp] = G2 . W2p           (B operand: the forward's B2 image read MN-major)
+//   E1    ghm = GH * [D1 > 0]  -> bf16, in place in TMEM
+//   T2    GU [128 smp x 16] += ghm . W1p         (A from TMEM; B: the forward's B1 image read MN-major)
+//   T3    D1T [128 hid x 128 smp] = B1p . A1^T,  GHT = W2p^T . G2^T   (same operands, roles swapped)
+//   E3    hT = relu(D1T), ghmT = GHT * [D1T > 0] -> bf16, in place (one thread per hidden unit)
+//   T4    ACC[l][p] [128 hid x 16] += hT . [G2p | 0] + ghmT . [0 | A1]   (contraction over the samples)
+//         columns 0..7: d/dW2p (last Linear), 8..15: d/dW1p and, through A1's constant-one column, d/db1p
+//   E5    g_u += GU                                                         (fp32)
+// The weight-gradient accumulators ACC stay in TMEM for the whole launch (fp32, 16 columns per layer
+// and net) and are added to the CTA's own row of the partial buffer at the end; last-layer bias
+// gradients are warp-reduced in fp32.  One persistent CTA per SM, 4 epilogue warps + 1 MMA warp.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "cnf_common.h"
+#include "cnf_tc_dims.h"
+#include "cnf_tc_ptx.cuh"
+
+namespace {
+
+constexpr int TB_THREADS = 160;        // warps 0..3: epilogue (TMEM lane quarter == warp), warp 4: MMA issuer + allocator
+constexpr int COL_D1 = 0, COL_GH = 128, COL_GU = 256, COL_ACC = 272;
+constexpr int LBO1 = 128, SBO1 = 256;  // the forward kernel's B1 image (K-major)
+constexpr int REC = 640;               // bytes of one 8-sample record of the A1/G2 image
+constexpr int OFF_G2 = 0, OFF_Z = 256, OFF_A1 = 384;
+
+struct TbDims {
+  int K, L, d0, d1, Hp, nets, n_nets;
+  int b_layer_bytes, b1_off, b2_off, blob_bytes;
+  int tab_pi, tab_cond, tab_trans, n_tables;
+  int n_grad;                                    // floats per partial row
+  int sm_tab, sm_ag, sm_act, sm_gact, sm_gb2, sm_red, sm_bar, sm_total;
+};
+
+bool tb_dims(const CnfDims& d, TbDims* t) {
+  TcDims f;
+  if (!cnf_tc_dims(d, &f)) return false;
+  if (d.d1 + 1 > 8) return false;                          // A1 must fit one 8-column block (shared accumulator)
+  if (COL_ACC + d.L * d.n_nets * 16 > 512) return false;    // weight-gradient accumulators live in TMEM
+  t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->Hp = f.Hp; t->nets = d.nets; t->n_nets = d.n_nets;
+  t->b_layer_bytes = f.b_layer_bytes; t->b1_off = f.b1_off; t->b2_off = f.b2_off;
+  t->blob_bytes = f.bias_off;                               // the fp32 biases are already folded into the tape
+  t->tab_pi = d.tab_pi; t->tab_cond = d.tab_cond; t->tab_trans = d.tab_trans; t->n_tables = d.n_tables;
+  t->n_grad = d.L * d.n_nets * 128 * 16 + d.L * 16;
+  int off = (t->blob_bytes + 127) / 128 * 128;
+  t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
+  t->sm_ag = off; off += 16 * REC;
+  t->sm_act = off; off += d.K * TILE_M * 4;
+  t->sm_gact = off; off += d.K * TILE_M * 4;
+  t->sm_gb2 = off; off += 4 * d.L * 16 * 4;
+  t->sm_red = off; off += 4 * 4 * 8;
+  t->sm_bar = off; off += 128;
+  t->sm_total = off;
+  return t->sm_total <= 227 * 1024;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
+                const float* __restrict__ zin, const float* __restrict__ logdet, const float* __restrict__ tape,
+                const int64_t* __restrict__ labels, float* __restrict__ partials, double* __restrict__ loss_acc,
+                int64_t N, float eps, float gamma, float inv_n, int do_bwd) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
+  uint8_t* ag = smem + p.sm_ag;
+  float* act = reinterpret_cast<float*>(smem + p.sm_act);
+  float* gact = reinterpret_cast<float*>(smem + p.sm_gact);
+  float* gb2 = reinterpret_cast<float*>(smem + p.sm_gb2);     // [warp][L][16]
+  double* red = reinterpret_cast<double*>(smem + p.sm_red);   // [4 sums][4 warps]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
+  uint64_t* ag_ready = bars + 0;    // 128 arrivals, once per layer:  A1/G2 records written
+  uint64_t* t1_done = bars + 1;     // commit, once per net phase:    D1, GH complete
+  uint64_t* ghm_ready = bars + 2;   // 128 arrivals, per phase:       ghm (bf16) in TMEM
+  uint64_t* t3_done = bars + 3;     // commit, per phase:             GU update issued before it, D1T, GHT complete
+  uint64_t* ht_ready = bars + 4;    // 128 arrivals, per phase:       hT, ghmT (bf16) in TMEM
+  uint64_t* t4_done = bars + 5;     // commit, per phase:             weight-gradient MMAs complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    if (do_bwd)
+      for (int i = tid; i < p.blob_bytes / 16; i += TB_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < p.n_tables; i += TB_THREADS) tab[i] = tables[i];
+    uint4* z4 = reinterpret_cast<uint4*>(ag);
+    for (int i = tid; i < 16 * REC / 16; i += TB_THREADS) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 4 * p.L * 16; i += TB_THREADS) gb2[i] = 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(ag_ready, 128);
+    mbar_init(t1_done, 1);
+    mbar_init(ghm_ready, 128);
+    mbar_init(t3_done, 1);
+    mbar_init(ht_ready, 128);
+    mbar_init(t4_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
+  const int G = gridDim.x;
+  const int Hp = p.Hp, n_ph = p.n_nets;
+
+  if (warp == 4) {
+    // ================================ MMA issuer ==============================================
+    if (lane == 0 && do_bwd) {
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t rec = smem_base + p.sm_ag;
+      const uint32_t tm = tmem_base;
+      const uint64_t a1_k = make_desc(rec + OFF_A1, 128, REC);     // [128 smp x 16] K-major (second k-block = zeros)
+      const uint64_t g2_k = make_desc(rec + OFF_G2, 128, REC);     // [128 smp x 16] K-major: g_s | g_t
+      const uint32_t id_t1a = make_idesc_ex(Hp, 0, 0), id_t1b = make_idesc_ex(Hp, 0, 1);
+      const uint32_t id_t2 = make_idesc_ex(16, 0, 1);
+      const uint32_t id_t3a = make_idesc_ex(128, 0, 0), id_t3b = make_idesc_ex(128, 1, 0);
+      const uint32_t id_t4 = make_idesc_ex(16, 0, 1);
+      uint32_t lc = 0, pc = 0;
+      bool first_tile = true;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
+        for (int li = 0; li < p.L; ++li, ++lc) {
+          const int l = p.L - 1 - li;
+          const uint32_t b1 = smem_base + p.b1_off + l * p.b_layer_bytes;
+          const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
+          mbar_wait(ag_ready, lc & 1);
+          tc_fence_after();
+          for (int ph = 0; ph < n_ph; ++ph, ++pc) {
+            const uint32_t b1p = b1 + ph * (Hp / 8) * SBO1;      // rows ph*Hp.. of the B1 image
+            const uint32_t b2p = b2 + ph * (Hp / 16) * 512;      // k-steps of net ph in the B2 image
+            // B2 image, element (n2, hid): (hid/8)*256 + (n2/8)*128 + (n2%8)*16 + (hid%8)*2
+            //   -> MN-major with the hidden unit as the MN index: S_mn = 256, S_k = 128
+            const uint64_t w2_mn = make_desc(b2p, 128, 256);
+            // ---- T1
+            mma_ss(tm + COL_D1, a1_k, make_desc(b1p, LBO1, SBO1), id_t1a, 0u);
+            mma_ss(tm + COL_GH, g2_k, w2_mn, id_t1b, 0u);
+            tc_commit(t1_done);
+            // ---- T2: GU += ghm . W1p ; B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
+            mbar_wait(ghm_ready, pc & 1);
+            tc_fence_after();
+            for (int j = 0; j < Hp / 16; ++j)
+              mma_ts(tm + COL_GU, tm + COL_GH + j * 8, make_desc(b1p + j * 512, 256, 128), id_t2,
+                     (ph > 0 || j > 0) ? 1u : 0u);
+            // ---- T3: the transposed pair
+            mma_ss(tm + COL_D1, make_desc(b1p, LBO1, SBO1), a1_k, id_t3a, 0u);
+            mma_ss(tm + COL_GH, w2_mn, g2_k, id_t3b, 0u);
+            tc_commit(t3_done);
+            // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16)
+            mbar_wait(ht_ready, pc & 1);
+            tc_fence_after();
+            const uint32_t acc = tm + COL_ACC + (l * n_ph + ph) * 16;
+            const uint32_t sbo_g = (ph == 0) ? 256u : 128u;      // [G2p | 0]: the zero block sits at OFF_Z
+            for (int j = 0; j < 8; ++j)
+              mma_ts(acc, tm + COL_D1 + j * 8, make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4,
+                     (!first_tile || j > 0) ? 1u : 0u);
+            for (int j = 0; j < 8; ++j)     // [0 | A1]
+              mma_ts(acc, tm + COL_GH + j * 8, make_desc(rec + OFF_Z + j * 2 * REC, REC, 128), id_t4, 1u);
+            tc_commit(t4_done);
+          }
+        }
+        first_tile = false;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue warps ==========================================
+    const int t = tid;                                   // sample row (E0/E1/E5) or hidden unit (E3) == TMEM lane
+    const uint32_t tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* rec_row = ag + (t >> 3) * REC + (t & 7) * 16;
+    const int* pi_last = tab + p.tab_pi + p.L * p.K;
+    const int K = p.K, tile_elems = TILE_M * p.K;
+    const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
+    const bool has_s = (p.nets & 1) != 0, has_t = (p.nets & 2) != 0;
+    const uint32_t one_bits = 0x3f80u;
+    double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+    uint32_t pc = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
+      const int64_t base = tile * TILE_M;
+      const int64_t n = base + t;
+      const bool valid = n < N;
+      // ---- z tile -> act[physical slot][sample] ------------------------------------------------
+      {
+        const float* gp = zin + base * K;
+        const int64_t avail = (N - base) * (int64_t)K;
+        int s = s0, f = f0;
+        for (int e = t; e < tile_elems; e += 128) {
+          act[pi_last[f] * TILE_M + s] = (e < avail) ? __ldg(gp + e) : 0.f;
+          s += ds; f += df;
+          if (f >= K) { f -= K; ++s; }
+        }
+      }
+      wg_sync(0);
+      // ---- loss head (calibrators.py:288-291), one thread per sample ----------------------------
+      float gld = 0.f;
+      {
+        const float ldv = valid ? __ldg(logdet + n) : 0.f;
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, act[j * TILE_M + t]);
+        float se = 0.f;
+        for (int j = 0; j < K; ++j) se += expf(act[j * TILE_M + t] - mx);
+        int yy = valid ? (int)labels[n] : 0;
+        yy = min(max(yy, 0), K - 1);
+        const int py_slot = pi_last[yy];
+        const float zy = act[py_slot * TILE_M + t];
+        const float inv_se = 1.f / se;
+        const float py = expf(zy - mx) * inv_se;
+        float ce, coef;
+        if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+        else            { ce = logf(py + eps); coef = py / (py + eps); }
+        if (valid) {
+          const float tot = ce + gamma * ldv;
+          a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ldv;
+          if (!isfinite(tot)) a_bad += 1.0;
+        }
+        if (do_bwd) {
+          const float sc = valid ? -inv_n * coef : 0.f;
+          for (int j = 0; j < K; ++j) {     // j walks physical slots here
+            const float pj = expf(act[j * TILE_M + t] - mx) * inv_se;
+            gact[j * TILE_M + t] = sc * ((j == py_slot ? 1.f : 0.f) - pj);
+          }
+          gld = valid ? -gamma * inv_n : 0.f;
+        }
+      }
+      if (do_bwd) {
+        for (int li = 0; li < p.L; ++li) {
+          const int l = p.L - 1 - li;
+          const int* cond = tab + p.tab_cond + l * p.d1;
+          const int* trans = tab + p.tab_trans + l * p.d0;
+          // ---- E0 -------------------------------------------------------------------------------
+          {
+            float xt[8], sv[8];
+            if (valid) {
+              const float4* tp = reinterpret_cast<const float4*>(tape + ((size_t)l * N + n) * 16);
+              const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+              xt[0] = a.x; xt[1] = a.y; xt[2] = a.z; xt[3] = a.w; xt[4] = b.x; xt[5] = b.y; xt[6] = b.z; xt[7] = b.w;
+              sv[0] = c.x; sv[1] = c.y; sv[2] = c.z; sv[3] = c.w; sv[4] = d.x; sv[5] = d.y; sv[6] = d.z; sv[7] = d.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { xt[q] = 0.f; sv[q] = 0.f; }
+            }
+            float g_first[8], g_second[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              g_first[q] = 0.f; g_second[q] = 0.f;
+              if (q < p.d0) {
+                const int ps = trans[q] * TILE_M + t;
+                const float gy = gact[ps];
+                const float es = has_s ? expf(sv[q]) : 1.f;
+                const float gs = gy * xt[q] * es + gld;
+                act[ps] = xt[q];               // step the tile state back to the input of layer l
+                gact[ps] = gy * es;
+                if (has_s) { g_first[q] = gs; g_second[q] = has_t ? gy : 0.f; }
+                else       { g_first[q] = gy; }
+              }
+            }
+            // last-layer bias gradients: per-warp fp32 sums, no atomics
+            float* gw = gb2 + (warp * p.L + l) * 16;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q < p.d0) {
+                const float a = warp_sum(g_first[q]);
+                const float b = warp_sum(g_second[q]);
+                if (lane == 0) { gw[q] += a; gw[8 + q] += b; }
+              }
+            }
+            uint4 v;
+            v.x = pack_bf16(g_first[0], g_first[1]); v.y = pack_bf16(g_first[2], g_first[3]);
+            v.z = pack_bf16(g_first[4], g_first[5]); v.w = pack_bf16(g_first[6], g_first[7]);
+            *reinterpret_cast<uint4*>(rec_row + OFF_G2) = v;
+            v.x = pack_bf16(g_second[0], g_second[1]); v.y = pack_bf16(g_second[2], g_second[3]);
+            v.z = pack_bf16(g_second[4], g_second[5]); v.w = pack_bf16(g_second[6], g_second[7]);
+            *reinterpret_cast<uint4*>(rec_row + OFF_G2 + 128) = v;
+            float u[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : 0.f;
+            v.x = pack_bf16(u[0], u[1]); v.y = pack_bf16(u[2], u[3]);
+            v.z = pack_bf16(u[4], u[5]); v.w = pack_bf16(u[6], u[7]);
+            {
+              const uint32_t ob = one_bits << ((p.d1 & 1) * 16);
+              const int wi = p.d1 >> 1;
+              v.x |= (wi == 0) ? ob : 0u; v.y |= (wi == 1) ? ob : 0u;
+              v.z |= (wi == 2) ? ob : 0u; v.w |= (wi == 3) ? ob : 0u;
+            }
+            *reinterpret_cast<uint4*>(rec_row + OFF_A1) = v;
+          }
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(ag_ready);
+          for (int ph = 0; ph < n_ph; ++ph, ++pc) {
+            // ---- E1: ghm = GH * [D1 > 0] -> bf16 over the low half of GH -------------------------
+            mbar_wait(t1_done, pc & 1);
+            tc_fence_after();
+            for (int c = 0; c < Hp; c += 32) {
+              uint32_t rd[32], rg[32], pk[16];
+              tmem_ld32(tm + COL_D1 + c, rd);
+              tmem_ld32(tm + COL_GH + c, rg);
+              tmem_wait_ld32(rd);
+              tmem_wait_ld32(rg);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float lo = __uint_as_float(rd[2 * i]) > 0.f ? __uint_as_float(rg[2 * i]) : 0.f;
+                const float hi = __uint_as_float(rd[2 * i + 1]) > 0.f ? __uint_as_float(rg[2 * i + 1]) : 0.f;
+                pk[i] = pack_bf16(lo, hi);
+              }
+              tmem_st16(tm + COL_GH + c / 2, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(ghm_ready);
+            // ---- E3: hidden-major; lane = hidden unit, columns = samples ----------------------------
+            mbar_wait(t3_done, pc & 1);
+            tc_fence_after();
+            for (int c = 0; c < TILE_M; c += 32) {
+              uint32_t rd[32], rg[32], pk[16];
+              tmem_ld32(tm + COL_D1 + c, rd);
+              tmem_ld32(tm + COL_GH + c, rg);
+              tmem_wait_ld32(rd);
+              tmem_wait_ld32(rg);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float lo = __uint_as_float(rd[2 * i]) > 0.f ? __uint_as_float(rg[2 * i]) : 0.f;
+                const float hi = __uint_as_float(rd[2 * i + 1]) > 0.f ? __uint_as_float(rg[2 * i + 1]) : 0.f;
+                pk[i] = pack_bf16(lo, hi);
+              }
+              tmem_st16(tm + COL_GH + c / 2, pk);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
+              tmem_st16(tm + COL_D1 + c / 2, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(ht_ready);
+          }
+          // ---- E5: gradient on the conditioning logits ---------------------------------------------
+          mbar_wait(t4_done, (pc - 1) & 1);
+          tc_fence_after();
+          {
+            uint32_t r[16];
+            tmem_ld16(tm + COL_GU, r);
+            tmem_wait_ld16(r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < p.d1) gact[cond[k] * TILE_M + t] += __uint_as_float(r[k]);
+          }
+          tc_fence_before();
+        }
+      }
+      wg_sync(0);   // every thread is done with act / gact before the next tile overwrites them
+    }
+    // ---- loss sums -------------------------------------------------------------------------------
+    if (loss_acc != nullptr) {
+      const double v0 = warp_sum_d(a_loss), v1 = warp_sum_d(a_ce), v2 = warp_sum_d(a_ld), v3 = warp_sum_d(a_bad);
+      if (lane == 0) { red[0 * 4 + warp] = v0; red[1 * 4 + warp] = v1; red[2 * 4 + warp] = v2; red[3 * 4 + warp] = v3; }
+      wg_sync(0);
+      if (t < 4) atomicAdd(loss_acc + t, (red[t * 4 + 0] + red[t * 4 + 1]) + (red[t * 4 + 2] + red[t * 4 + 3]));
+    }
+    // ---- weight-gradient accumulators -> this CTA's row of the partial buffer ---------------------
+    if (do_bwd) {
+      float* row = partials + (size_t)blockIdx.x * p.n_grad;
+      tc_fence_after();
+      for (int a = 0; a < p.L * n_ph; ++a) {
+        uint32_t r[16];
+        tmem_ld16(tm + COL_ACC + a * 16, r);
+        tmem_wait_ld16(r);
+        float4* dst = reinterpret_cast<float4*>(row + ((size_t)a * 128 + t) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 o = dst[i];
+          o.x += __uint_as_float(r[4 * i]); o.y += __uint_as_float(r[4 * i + 1]);
+          o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
+          dst[i] = o;
+        }
+      }
+      wg_sync(0);   // gb2 rows of all four warps are final
+      float* rb = row + (size_t)p.L * n_ph * 128 * 16;
+      for (int i = t; i < p.L * 16; i += 128)
+        rb[i] += (gb2[(0 * p.L) * 16 + i] + gb2[(1 * p.L) * 16 + i]) + (gb2[(2 * p.L) * 16 + i] + gb2[(3 * p.L) * 16 + i]);
+    }
+  }
+  // ---- teardown -----------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+__global__ void tcb_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ gather,
+                                  float* __restrict__ flat_grad, int n_grad, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_grad) return;
+  const int g = gather[i];
+  if (g < 0) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4) {
+    a0 += partials[(size_t)(r + 0) * n_grad + i];
+    a1 += partials[(size_t)(r + 1) * n_grad + i];
+    a2 += partials[(size_t)(r + 2) * n_grad + i];
+    a3 += partials[(size_t)(r + 3) * n_grad + i];
+  }
+  for (; r < rows; ++r) a0 += partials[(size_t)r * n_grad + i];
+  flat_grad[g] = (a0 + a1) + (a2 + a3);
+}
+
+int g_tb_sms = -1;
+
+int tb_sms() {
+  if (g_tb_sms < 0) {
+    int dev = 0, s = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    g_tb_sms = s;
+  }
+  return g_tb_sms;
+}
+
+}  // namespace
+
+int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                      float* logdet, float* tape, int64_t N, int inverse, cudaStream_t st);
+
+// Rows of the partial buffer: one per CTA of the persistent grid (fixed upper bound, so that the
+// host can size it without a device query).
+#define CNF_TCB_ROWS 160
+
+extern "C" int cnf_tc_train_info(const cnf_flow_desc* desc, int64_t* n_grad, int64_t* rows, int64_t* ws_bytes_per_sample) {
+  CnfDims d; TbDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!n_grad || !rows || !ws_bytes_per_sample) { cnf_set_error("cnf_tc_train_info: null out"); return CNF_E_ARG; }
+  if (!tb_dims(d, &t)) { *n_grad = 0; *rows = 0; *ws_bytes_per_sample = 0; return CNF_OK; }
+  *n_grad = t.n_grad;
+  *rows = CNF_TCB_ROWS;
+  *ws_bytes_per_sample = (int64_t)(d.K + 1 + 16 * d.L) * 4;      // z, log-det, tape
+  return CNF_OK;
+}
+
+// gather[i] = index into flat of partial-row entry i, or -1
+extern "C" int cnf_plan_build_tcgrad(const cnf_flow_desc* desc, int32_t* g) {
+  CnfDims d; TbDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!g) { cnf_set_error("null output"); return CNF_E_ARG; }
+  if (!tb_dims(d, &t)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
+  const int K = d.K, half = K / 2, H = d.H[0];
+  for (int i = 0; i < t.n_grad; ++i) g[i] = -1;
+  const long long net_sz = (long long)H * K + H + (long long)K * H + K;
+  int32_t* gb = g + (size_t)d.L * d.n_nets * 128 * 16;
+  for (int l = 0; l < d.L; ++l) {
+    int slot = 0;
+    for (int net = 0; net < 2; ++net) {
+      if (!(d.nets & (1 << net))) continue;
+      const long long base = ((long long)l * d.n_nets + slot) * net_sz;
+      const long long w0 = base, b0 = base + (long long)H * K, w1 = b0 + H, b1 = w1 + (long long)K * H;
+      int32_t* ga = g + ((size_t)(l * d.n_nets + slot) * 128) * 16;
+      for (int h = 0; h < H; ++h) {
+        for (int q = 0; q < d.d0; ++q) ga[h * 16 + q] = (int32_t)(w1 + (long long)q * H + h);
+        for (int k = 0; k < d.d1; ++k) ga[h * 16 + 8 + k] = (int32_t)(w0 + (long long)h * K + half + k);
+        ga[h * 16 + 8 + d.d1] = (int32_t)(b0 + h);
+      }
+      for (int q = 0; q < d.d0; ++q) gb[l * 16 + slot * 8 + q] = (int32_t)(b1 + q);
+      ++slot;
+    }
+  }
+  return CNF_OK;
+}
+
+// One training pass on the tensor-core path: per chunk of samples the forward kernel (with tape) and
+// the backward kernel above.  workspace: DEVICE, >= chunk * ws_bytes_per_sample; chunk is derived from
+// workspace_bytes.  grad_partials_tc: float32 [rows, n_grad], overwritten (NULL = evaluation only).
+extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables,
+                                     const float* x, const int64_t* y, int64_t N, float eps, float gamma,
+                                     float inv_n_total, float* grad_partials_tc, double* loss_acc, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  CnfDims d; TbDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (desc->precision != CNF_PREC_BF16_TC) { cnf_set_error("cnf_nll_train_step_tc needs a CNF_PREC_BF16_TC descriptor"); return CNF_E_ARG; }
+  if (!tb_dims(d, &t)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
+  if (!packed_tc || !tables || !y || !loss_acc || !workspace || N < 0) { cnf_set_error("cnf_nll_train_step_tc: null pointer / negative N"); return CNF_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = tb_sms();
+  if (sms <= 0) { cnf_set_error("no CUDA device"); return CNF_E_CUDA; }
+  if (sms > CNF_TCB_ROWS) { cnf_set_error("device has more SMs than partial rows"); return CNF_E_UNSUPPORTED; }
+  if (grad_partials_tc) CNF_CHECK_CUDA(cudaMemsetAsync(grad_partials_tc, 0, (size_t)CNF_TCB_ROWS * t.n_grad * sizeof(float), st));
+  if (N == 0) return CNF_OK;
+  if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
+  const int64_t per_sample = (int64_t)(d.K + 1 + 16 * d.L) * 4;
+  int64_t chunk = workspace_bytes / per_sample;
+  chunk = chunk / 1024 * 1024;                    // keeps every sub-buffer 16-byte aligned
+  if (chunk < 1024) { cnf_set_error("cnf_nll_train_step_tc: workspace smaller than 1024 samples (%lld bytes each)", (long long)per_sample); return CNF_E_ARG; }
+  if (chunk > N) chunk = (N + 1023) / 1024 * 1024;
+  float* zbuf = reinterpret_cast<float*>(workspace);
+  float* ldbuf = zbuf + chunk * d.K;
+  float* tapebuf = ldbuf + chunk;
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+  for (int64_t lo = 0; lo < N; lo += chunk) {
+    const int64_t n = (N - lo < chunk) ? N - lo : chunk;
+    rc = cnf_tc_apply_tape(desc, packed_tc, tables, x + lo * d.K, zbuf, ldbuf, grad_partials_tc ? tapebuf : nullptr, n, 0, st);
+    if (rc) return rc;
+    const int64_t ntiles = (n + TILE_M - 1) / TILE_M;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    flow_tcb_kernel<<<grid, TB_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, zbuf, ldbuf, tapebuf,
+                                                         y + lo, grad_partials_tc, loss_acc, n, eps, gamma, inv_n_total,
+                                                         grad_partials_tc ? 1 : 0);
+    CNF_CHECK_CUDA(cudaGetLastError());
+  }
+  return CNF_OK;
+}
+
+extern "C" int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, const int32_t* gather_tcgrad,
+                                  float* flat_grad, void* stream) {
+  CnfDims d; TbDims t;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!tb_dims(d, &t)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
+  if (!grad_partials_tc || !gather_tcgrad || !flat_grad) { cnf_set_error("cnf_grad_reduce_tc: null pointer"); return CNF_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
+  tcb_reduce_kernel<<<(t.n_grad + 127) / 128, 128, 0, st>>>(grad_partials_tc, gather_tcgrad, flat_grad, t.n_grad, CNF_TCB_ROWS);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}

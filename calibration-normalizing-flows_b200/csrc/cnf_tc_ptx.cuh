@@ -72,6 +72,21 @@ __host__ __device__ inline uint32_t make_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// general form: MN-major operands (transposed views of the same shared-memory images)
+__host__ __device__ inline uint32_t make_idesc_ex(int N, int a_mn_major, int b_mn_major) {
+  return make_idesc(N) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

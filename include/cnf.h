@@ -148,6 +148,25 @@ int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_a
 int cnf_sgd_step(float* params, const float* grad, int64_t n, float lr, float weight_decay,
                  void* stream);
 
+/* ---- device: training on the bf16 tensor-core path ------------------------------------------------
+ * Same loss and gradient as cnf_nll_train_step, computed by the tcgen05 forward kernel (which also
+ * writes a per-layer tape) and a tcgen05 backward kernel.  Shapes: one hidden layer, K <= 14,
+ * pad16(H) <= 128, L*nets <= 15; cnf_tc_train_info reports n_grad == 0 otherwise (use the fp32 path).
+ *   n_grad:  floats per row of the partial buffer; rows: its row count;
+ *   ws_bytes_per_sample: bytes of DEVICE workspace per sample of a chunk (z, log-det, tape).      */
+int cnf_tc_train_info(const cnf_flow_desc* desc, int64_t* n_grad, int64_t* rows, int64_t* ws_bytes_per_sample);
+/* gather_tcgrad[i] = index into flat of partial-row entry i, or -1; length n_grad (host).         */
+int cnf_plan_build_tcgrad(const cnf_flow_desc* desc, int32_t* gather_tcgrad_host);
+/* packed_tc: blob of cnf_pack_weights_tc.  The samples are processed in chunks of
+ * workspace_bytes / ws_bytes_per_sample (rounded down to 1024) samples.  grad_partials_tc:
+ * float32 [rows, n_grad], overwritten; NULL = evaluation only.  loss_acc as cnf_nll_train_step.  */
+int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables,
+                          const float* x, const int64_t* y, int64_t N, float eps, float gamma,
+                          float inv_n_total, float* grad_partials_tc, double* loss_acc,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc,
+                       const int32_t* gather_tcgrad, float* flat_grad, void* stream);
+
 /* ---- device: metrics ----------------------------------------------------------- */
 /* in: [N,K] float32 (is_f64 == 0) or float64 (is_f64 == 1); labels int64 [N].
  * edges: DEVICE float64 [bins+1], edge i = i*(1/bins) as the reference forms it.
