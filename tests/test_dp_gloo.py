@@ -32,7 +32,7 @@ class OracleEngine:
     def pack(self, tc=False):
         pass
 
-    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True):
+    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision="fp32"):
         p = orc.unflatten(self.flat.numpy(), self.like)
         xn, yn = x.numpy().astype(np.float64), y.numpy()
         zs, ld = orc.flow_forward(p, xn)
