@@ -1,7 +1,7 @@
 """Per-tensor error of the tensor-core training gradient (bf16) against the float64 oracle.
 Run on the GPU box: python profiles/microbench/diag_tcgrad.py [N]"""
 import sys, numpy as np, torch
-sys.path.insert(0, 'tests'); sys.path.insert(0, 'oracle')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); sys.path.insert(0, 'oracle')
 import flow_oracle as orc
 from conftest import load_golden, oracle_params_from_golden
 from helpers import build_flow_from_golden

@@ -182,8 +182,10 @@ def test_tc_train_step_ragged_and_chunked_vs_oracle(N, cuda_device):
 
 
 def test_tc_training_follows_the_fp32_loss_trajectory(cuda_device):
-    """40 full-batch Adam steps from the reference initialisation: the bf16 trainer's loss curve
-    stays within 2e-3 (absolute, nats) of the fp32 trainer's and ends lower than it started."""
+    """25 full-batch Adam steps from the reference initialisation: the bf16 trainer's loss curve
+    stays within 2e-3 (absolute, nats) of the fp32 trainer's and ends lower than it started.
+    (The reference objective -mean(log p_y + log_det) is unbounded below; with lr 1e-3 both paths
+    -- and the reference -- reach non-finite values around step 30, hence 25.)"""
     import torch
     import cnf_b200
     from cnf_b200.calibrators import FusedNLLTrainer
@@ -196,7 +198,7 @@ def test_tc_training_follows_the_fp32_loss_trajectory(cuda_device):
         flow = cnf_b200.RealNvpFlow(K, layers=6, hidden_size=[128]).to(cuda_device)
         tr = FusedNLLTrainer(flow.engine(), xt, yt, lr=1e-3, precision=prec)
         losses = []
-        for _ in range(40):
+        for _ in range(25):
             tr.step()
             losses.append(-float(tr.loss_acc[0]) / N)
         curves[prec] = np.array(losses)
