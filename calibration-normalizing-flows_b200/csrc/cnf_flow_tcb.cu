@@ -15,16 +15,20 @@
 //   per conditioner net p (s, then t):
 //   T1    D1 [128 smp x Hp] = A1 . B1p^T         (recompute of the hidden pre-activations, bias folded)
 //         GH [128 smp x Hp] = G2 . W2p           (B operand: the forward's B2 image read MN-major)
-//   E1    ghm = GH * [D1 > 0]  -> bf16, in place in TMEM
-//   T2    GU [128 smp x 16] += ghm . W1p         (A from TMEM; B: the forward's B1 image read MN-major)
-//   T3    D1T [128 hid x 128 smp] = B1p . A1^T,  GHT = W2p^T . G2^T   (same operands, roles swapped)
-//   E3    hT = relu(D1T), ghmT = GHT * [D1T > 0] -> bf16, in place (one thread per hidden unit)
-//   T4    ACC[l][p] [128 hid x 16] += hT . [G2p | 0] + ghmT . [0 | A1]   (contraction over the samples)
+//   E1    h = relu(D1), ghm = GH * [D1 > 0]  -> bf16 shared-memory images [128 smp x Hp] whose 8x8 core
+//         matrices serve both as a K-major operand (contraction over the hidden units) and as an
+//         MN-major operand (contraction over the samples)
+//   T2    GU [128 smp x 16] += ghm . W1p         (B: the forward's B1 image read MN-major)
+//   T4    ACC[l][p] [128 hid x 16] += h^T . [G2p | 0] + ghm^T . [0 | A1]   (contraction over the samples)
 //         columns 0..7: d/dW2p (last Linear), 8..15: d/dW1p and, through A1's constant-one column, d/db1p
 //   E5    g_u += GU                                                         (fp32)
 // The weight-gradient accumulators ACC stay in TMEM for the whole launch (fp32, 16 columns per layer
 // and net) and are added to the CTA's own row of the partial buffer at the end; last-layer bias
 // gradients are warp-reduced in fp32.  One persistent CTA per SM, 4 epilogue warps + 1 MMA warp.
+// Measured on B200 (profiles/microbench/tmem_bw.cu): tcgen05.ld moves 128 B/clk per SM whatever the
+// number of warps, so the [128 x Hp] fp32 reads of D1 and GH (1024 clk per net at Hp = 128) are the
+// epilogue's floor; an earlier version that formed h^T / ghm^T by a second, transposed recompute in
+// TMEM doubled those reads and ran at half the speed.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -45,7 +49,7 @@ struct TbDims {
   int b_layer_bytes, b1_off, b2_off, blob_bytes;
   int tab_pi, tab_cond, tab_trans, n_tables;
   int n_grad;                                    // floats per partial row
-  int sm_tab, sm_ag, sm_act, sm_gact, sm_gb2, sm_red, sm_bar, sm_total;
+  int sm_tab, sm_ag, sm_h, sm_ghm, sm_act, sm_gact, sm_gb2, sm_red, sm_bar, sm_total;
 };
 
 bool tb_dims(const CnfDims& d, TbDims* t) {
@@ -61,6 +65,9 @@ bool tb_dims(const CnfDims& d, TbDims* t) {
   int off = (t->blob_bytes + 127) / 128 * 128;
   t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
   t->sm_ag = off; off += 16 * REC;
+  off = (off + 1023) / 1024 * 1024;
+  t->sm_h = off; off += TILE_M * f.Hp * 2;
+  t->sm_ghm = off; off += TILE_M * f.Hp * 2;
   t->sm_act = off; off += d.K * TILE_M * 4;
   t->sm_gact = off; off += d.K * TILE_M * 4;
   t->sm_gb2 = off; off += 4 * d.L * 16 * 4;
@@ -97,10 +104,8 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
   uint64_t* ag_ready = bars + 0;    // 128 arrivals, once per layer:  A1/G2 records written
   uint64_t* t1_done = bars + 1;     // commit, once per net phase:    D1, GH complete
-  uint64_t* ghm_ready = bars + 2;   // 128 arrivals, per phase:       ghm (bf16) in TMEM
-  uint64_t* t3_done = bars + 3;     // commit, per phase:             GU update issued before it, D1T, GHT complete
-  uint64_t* ht_ready = bars + 4;    // 128 arrivals, per phase:       hT, ghmT (bf16) in TMEM
-  uint64_t* t4_done = bars + 5;     // commit, per phase:             weight-gradient MMAs complete
+  uint64_t* hg_ready = bars + 2;    // 128 arrivals, per phase:       h, ghm (bf16) images in shared memory
+  uint64_t* t4_done = bars + 3;     // commit, per phase:             GU update and weight-gradient MMAs complete
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   // ---- one-time setup ---------------------------------------------------------------------
@@ -117,9 +122,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   if (tid == 0) {
     mbar_init(ag_ready, 128);
     mbar_init(t1_done, 1);
-    mbar_init(ghm_ready, 128);
-    mbar_init(t3_done, 1);
-    mbar_init(ht_ready, 128);
+    mbar_init(hg_ready, 128);
     mbar_init(t4_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -148,8 +151,9 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       const uint64_t g2_k = make_desc(rec + OFF_G2, 128, REC);     // [128 smp x 16] K-major: g_s | g_t
       const uint32_t id_t1a = make_idesc_ex(Hp, 0, 0), id_t1b = make_idesc_ex(Hp, 0, 1);
       const uint32_t id_t2 = make_idesc_ex(16, 0, 1);
-      const uint32_t id_t3a = make_idesc_ex(128, 0, 0), id_t3b = make_idesc_ex(128, 1, 0);
-      const uint32_t id_t4 = make_idesc_ex(16, 0, 1);
+      const uint32_t id_t4 = make_idesc_ex(16, 1, 1);
+      const uint32_t h_img = smem_base + p.sm_h, ghm_img = smem_base + p.sm_ghm;
+      const uint32_t img_sr = (uint32_t)(Hp / 8) * 128;       // bytes between 8-sample row groups of the images
       uint32_t lc = 0, pc = 0;
       bool first_tile = true;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
@@ -169,26 +173,23 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             mma_ss(tm + COL_D1, a1_k, make_desc(b1p, LBO1, SBO1), id_t1a, 0u);
             mma_ss(tm + COL_GH, g2_k, w2_mn, id_t1b, 0u);
             tc_commit(t1_done);
-            // ---- T2: GU += ghm . W1p ; B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
-            mbar_wait(ghm_ready, pc & 1);
+            // ---- T2: GU += ghm . W1p ; A: the ghm image K-major (k-step = 16 hidden = 2 core matrices);
+            //      B: B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
+            mbar_wait(hg_ready, pc & 1);
             tc_fence_after();
             for (int j = 0; j < Hp / 16; ++j)
-              mma_ts(tm + COL_GU, tm + COL_GH + j * 8, make_desc(b1p + j * 512, 256, 128), id_t2,
+              mma_ss(tm + COL_GU, make_desc(ghm_img + j * 256, 128, img_sr), make_desc(b1p + j * 512, 256, 128), id_t2,
                      (ph > 0 || j > 0) ? 1u : 0u);
-            // ---- T3: the transposed pair
-            mma_ss(tm + COL_D1, make_desc(b1p, LBO1, SBO1), a1_k, id_t3a, 0u);
-            mma_ss(tm + COL_GH, w2_mn, g2_k, id_t3b, 0u);
-            tc_commit(t3_done);
-            // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16)
-            mbar_wait(ht_ready, pc & 1);
-            tc_fence_after();
+            // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16);
+            //      A: the h / ghm images read MN-major (M = hidden unit): S_mn = 128, S_k = img_sr
             const uint32_t acc = tm + COL_ACC + (l * n_ph + ph) * 16;
             const uint32_t sbo_g = (ph == 0) ? 256u : 128u;      // [G2p | 0]: the zero block sits at OFF_Z
             for (int j = 0; j < 8; ++j)
-              mma_ts(acc, tm + COL_D1 + j * 8, make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4,
-                     (!first_tile || j > 0) ? 1u : 0u);
+              mma_ss(acc, make_desc(h_img + j * 2 * img_sr, img_sr, 128),
+                     make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4, (!first_tile || j > 0) ? 1u : 0u);
             for (int j = 0; j < 8; ++j)     // [0 | A1]
-              mma_ts(acc, tm + COL_GH + j * 8, make_desc(rec + OFF_Z + j * 2 * REC, REC, 128), id_t4, 1u);
+              mma_ss(acc, make_desc(ghm_img + j * 2 * img_sr, img_sr, 128), make_desc(rec + OFF_Z + j * 2 * REC, REC, 128),
+                     id_t4, 1u);
             tc_commit(t4_done);
           }
         }
@@ -198,42 +199,74 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
     __syncwarp();
   } else {
     // ================================ epilogue warps ==========================================
-    const int t = tid;                                   // sample row (E0/E1/E5) or hidden unit (E3) == TMEM lane
+    const int t = tid;                                   // sample row of the tile == TMEM lane
     const uint32_t tm = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* rec_row = ag + (t >> 3) * REC + (t & 7) * 16;
+    const uint32_t img_row = (uint32_t)((t >> 3) * (Hp / 8) * 128 + (t & 7) * 16);   // 16-byte slot in core matrix 0
+    const uint32_t h_row = smem_u32(smem + p.sm_h) + img_row, ghm_row = smem_u32(smem + p.sm_ghm) + img_row;
     const int* pi_last = tab + p.tab_pi + p.L * p.K;
-    const int K = p.K, tile_elems = TILE_M * p.K;
+    const int K = p.K;
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
     const bool has_s = (p.nets & 1) != 0, has_t = (p.nets & 2) != 0;
     const uint32_t one_bits = 0x3f80u;
     double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
     uint32_t pc = 0;
+    // register prefetch of the next tile's inputs (element e = t + 128*i of the row-major z tile)
+    constexpr int KMAX = 14;
+    float zr[KMAX], ld_r = 0.f;
+    int y_r = 0;
+    auto fetch_tile = [&](int64_t tile) {
+      const int64_t base = tile * TILE_M;
+      const float* gp = zin + base * K;
+      const int64_t avail = (N - base) * (int64_t)K;
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {
+        const int e = t + 128 * i;
+        zr[i] = (i < K && e < avail) ? __ldg(gp + e) : 0.f;
+      }
+      const bool v = base + t < N;
+      ld_r = v ? __ldg(logdet + base + t) : 0.f;
+      y_r = v ? (int)labels[base + t] : 0;
+    };
+    float4 tq[4];                                        // tape record of the next layer to process
+    auto fetch_tape = [&](int l, int64_t n) {
+      if (n < N) {
+        const float4* tp = reinterpret_cast<const float4*>(tape + ((size_t)l * N + n) * 16);
+        tq[0] = __ldg(tp); tq[1] = __ldg(tp + 1); tq[2] = __ldg(tp + 2); tq[3] = __ldg(tp + 3);
+      } else {
+        tq[0] = tq[1] = tq[2] = tq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
       const int64_t base = tile * TILE_M;
       const int64_t n = base + t;
       const bool valid = n < N;
+      if (do_bwd) fetch_tape(p.L - 1, n);
       // ---- z tile -> act[physical slot][sample] ------------------------------------------------
       {
-        const float* gp = zin + base * K;
-        const int64_t avail = (N - base) * (int64_t)K;
         int s = s0, f = f0;
-        for (int e = t; e < tile_elems; e += 128) {
-          act[pi_last[f] * TILE_M + s] = (e < avail) ? __ldg(gp + e) : 0.f;
-          s += ds; f += df;
-          if (f >= K) { f -= K; ++s; }
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          if (i < K) {
+            act[pi_last[f] * TILE_M + s] = zr[i];
+            s += ds; f += df;
+            if (f >= K) { f -= K; ++s; }
+          }
         }
       }
+      const float ldv = ld_r;
+      const int ylab = y_r;
       wg_sync(0);
+      if (tile + G < ntiles) fetch_tile(tile + G);
       // ---- loss head (calibrators.py:288-291), one thread per sample ----------------------------
       float gld = 0.f;
       {
-        const float ldv = valid ? __ldg(logdet + n) : 0.f;
         float mx = -INFINITY;
         for (int j = 0; j < K; ++j) mx = fmaxf(mx, act[j * TILE_M + t]);
         float se = 0.f;
         for (int j = 0; j < K; ++j) se += expf(act[j * TILE_M + t] - mx);
-        int yy = valid ? (int)labels[n] : 0;
-        yy = min(max(yy, 0), K - 1);
+        const int yy = min(max(ylab, 0), K - 1);
         const int py_slot = pi_last[yy];
         const float zy = act[py_slot * TILE_M + t];
         const float inv_se = 1.f / se;
@@ -262,20 +295,12 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           const int* trans = tab + p.tab_trans + l * p.d0;
           // ---- E0 -------------------------------------------------------------------------------
           {
-            float xt[8], sv[8];
-            if (valid) {
-              const float4* tp = reinterpret_cast<const float4*>(tape + ((size_t)l * N + n) * 16);
-              const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
-              xt[0] = a.x; xt[1] = a.y; xt[2] = a.z; xt[3] = a.w; xt[4] = b.x; xt[5] = b.y; xt[6] = b.z; xt[7] = b.w;
-              sv[0] = c.x; sv[1] = c.y; sv[2] = c.z; sv[3] = c.w; sv[4] = d.x; sv[5] = d.y; sv[6] = d.z; sv[7] = d.w;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) { xt[q] = 0.f; sv[q] = 0.f; }
-            }
-            float g_first[8], g_second[8];
+            const float xt[8] = {tq[0].x, tq[0].y, tq[0].z, tq[0].w, tq[1].x, tq[1].y, tq[1].z, tq[1].w};
+            const float sv[8] = {tq[2].x, tq[2].y, tq[2].z, tq[2].w, tq[3].x, tq[3].y, tq[3].z, tq[3].w};
+            float gv[16];                      // 0..7: gradient on the first present net's outputs, 8..15: second
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              g_first[q] = 0.f; g_second[q] = 0.f;
+              gv[q] = 0.f; gv[8 + q] = 0.f;
               if (q < p.d0) {
                 const int ps = trans[q] * TILE_M + t;
                 const float gy = gact[ps];
@@ -283,26 +308,17 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
                 const float gs = gy * xt[q] * es + gld;
                 act[ps] = xt[q];               // step the tile state back to the input of layer l
                 gact[ps] = gy * es;
-                if (has_s) { g_first[q] = gs; g_second[q] = has_t ? gy : 0.f; }
-                else       { g_first[q] = gy; }
+                if (has_s) { gv[q] = gs; gv[8 + q] = has_t ? gy : 0.f; }
+                else       { gv[q] = gy; }
               }
             }
-            // last-layer bias gradients: per-warp fp32 sums, no atomics
-            float* gw = gb2 + (warp * p.L + l) * 16;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q < p.d0) {
-                const float a = warp_sum(g_first[q]);
-                const float b = warp_sum(g_second[q]);
-                if (lane == 0) { gw[q] += a; gw[8 + q] += b; }
-              }
-            }
+            if (l > 0) fetch_tape(l - 1, n);   // in flight while this layer's MMAs and epilogues run
             uint4 v;
-            v.x = pack_bf16(g_first[0], g_first[1]); v.y = pack_bf16(g_first[2], g_first[3]);
-            v.z = pack_bf16(g_first[4], g_first[5]); v.w = pack_bf16(g_first[6], g_first[7]);
+            v.x = pack_bf16(gv[0], gv[1]); v.y = pack_bf16(gv[2], gv[3]);
+            v.z = pack_bf16(gv[4], gv[5]); v.w = pack_bf16(gv[6], gv[7]);
             *reinterpret_cast<uint4*>(rec_row + OFF_G2) = v;
-            v.x = pack_bf16(g_second[0], g_second[1]); v.y = pack_bf16(g_second[2], g_second[3]);
-            v.z = pack_bf16(g_second[4], g_second[5]); v.w = pack_bf16(g_second[6], g_second[7]);
+            v.x = pack_bf16(gv[8], gv[9]); v.y = pack_bf16(gv[10], gv[11]);
+            v.z = pack_bf16(gv[12], gv[13]); v.w = pack_bf16(gv[14], gv[15]);
             *reinterpret_cast<uint4*>(rec_row + OFF_G2 + 128) = v;
             float u[8];
 #pragma unroll
@@ -316,54 +332,89 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
               v.z |= (wi == 2) ? ob : 0u; v.w |= (wi == 3) ? ob : 0u;
             }
             *reinterpret_cast<uint4*>(rec_row + OFF_A1) = v;
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(ag_ready);
+            // last-layer bias gradients: the warp's 16 column sums by a halving butterfly (15 shuffles);
+            // lane L ends up with column ((L>>1) & 15) bit-reversed as below, fp32, no atomics
+            float w8[8], w4[4], w2[2], w1;
+            {
+              const bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = hi ? gv[i] : gv[8 + i], keep = hi ? gv[8 + i] : gv[i];
+                w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+            }
+            {
+              const bool hi = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = hi ? w8[i] : w8[4 + i], keep = hi ? w8[4 + i] : w8[i];
+                w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+            }
+            {
+              const bool hi = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = hi ? w4[i] : w4[2 + i], keep = hi ? w4[2 + i] : w4[i];
+                w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+            }
+            {
+              const bool hi = (lane & 2) != 0;
+              const float send = hi ? w2[0] : w2[1], keep = hi ? w2[1] : w2[0];
+              w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+            if ((lane & 1) == 0) {
+              const int col = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+              gb2[(warp * p.L + l) * 16 + col] += w1;
+            }
           }
-          fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(ag_ready);
           for (int ph = 0; ph < n_ph; ++ph, ++pc) {
-            // ---- E1: ghm = GH * [D1 > 0] -> bf16 over the low half of GH -------------------------
+            // ---- E1: h = relu(D1), ghm = GH * [D1 > 0] -> bf16 shared-memory images ------------------
+            // t1_done of this phase also says that the previous phase's MMAs no longer read the images.
+            // TMEM loads of the next 32 columns are in flight while the current 32 are converted.
             mbar_wait(t1_done, pc & 1);
             tc_fence_after();
-            for (int c = 0; c < Hp; c += 32) {
-              uint32_t rd[32], rg[32], pk[16];
-              tmem_ld32(tm + COL_D1 + c, rd);
-              tmem_ld32(tm + COL_GH + c, rg);
-              tmem_wait_ld32(rd);
-              tmem_wait_ld32(rg);
+            uint32_t rd0[32], rg0[32], rd1[32], rg1[32];
+            auto convert = [&](const uint32_t (&rd)[32], const uint32_t (&rg)[32], int c) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float lo = __uint_as_float(rd[2 * i]) > 0.f ? __uint_as_float(rg[2 * i]) : 0.f;
-                const float hi = __uint_as_float(rd[2 * i + 1]) > 0.f ? __uint_as_float(rg[2 * i + 1]) : 0.f;
-                pk[i] = pack_bf16(lo, hi);
+              for (int b8 = 0; b8 < 4; ++b8) {
+                uint32_t vh[4], vg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float d0v = __uint_as_float(rd[8 * b8 + 2 * i]), d1v = __uint_as_float(rd[8 * b8 + 2 * i + 1]);
+                  vh[i] = pack_relu_bf16(d0v, d1v);
+                  vg[i] = pack_bf16(d0v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i]) : 0.f,
+                                    d1v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i + 1]) : 0.f);
+                }
+                if (c + 8 * b8 < Hp) {               // Hp is a multiple of 16, not of 32
+                  const uint32_t off = (uint32_t)(c / 8 + b8) * 128;
+                  sts128(h_row + off, vh[0], vh[1], vh[2], vh[3]);
+                  sts128(ghm_row + off, vg[0], vg[1], vg[2], vg[3]);
+                }
               }
-              tmem_st16(tm + COL_GH + c / 2, pk);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(ghm_ready);
-            // ---- E3: hidden-major; lane = hidden unit, columns = samples ----------------------------
-            mbar_wait(t3_done, pc & 1);
-            tc_fence_after();
-            for (int c = 0; c < TILE_M; c += 32) {
-              uint32_t rd[32], rg[32], pk[16];
-              tmem_ld32(tm + COL_D1 + c, rd);
-              tmem_ld32(tm + COL_GH + c, rg);
-              tmem_wait_ld32(rd);
-              tmem_wait_ld32(rg);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float lo = __uint_as_float(rd[2 * i]) > 0.f ? __uint_as_float(rg[2 * i]) : 0.f;
-                const float hi = __uint_as_float(rd[2 * i + 1]) > 0.f ? __uint_as_float(rg[2 * i + 1]) : 0.f;
-                pk[i] = pack_bf16(lo, hi);
+            };
+            tmem_ld32(tm + COL_D1, rd0);
+            tmem_ld32(tm + COL_GH, rg0);
+            for (int c = 0; c < Hp; c += 64) {
+              tmem_wait_ld32(rd0);
+              tmem_wait_ld32(rg0);
+              if (c + 32 < Hp) { tmem_ld32(tm + COL_D1 + c + 32, rd1); tmem_ld32(tm + COL_GH + c + 32, rg1); }
+              convert(rd0, rg0, c);
+              if (c + 32 < Hp) {
+                tmem_wait_ld32(rd1);
+                tmem_wait_ld32(rg1);
+                if (c + 64 < Hp) { tmem_ld32(tm + COL_D1 + c + 64, rd0); tmem_ld32(tm + COL_GH + c + 64, rg0); }
+                convert(rd1, rg1, c + 32);
               }
-              tmem_st16(tm + COL_GH + c / 2, pk);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
-              tmem_st16(tm + COL_D1 + c / 2, pk);
             }
-            tmem_wait_st();
+            fence_async_smem();
             tc_fence_before();
-            mbar_arrive(ht_ready);
+            mbar_arrive(hg_ready);
           }
           // ---- E5: gradient on the conditioning logits ---------------------------------------------
           mbar_wait(t4_done, (pc - 1) & 1);
