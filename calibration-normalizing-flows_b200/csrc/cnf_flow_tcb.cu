@@ -12,23 +12,31 @@
 //
 //   E0    g_s = g_y * x_t * e^s + g_ld ; g_t = g_y ; g_xt = g_y * e^s          (fp32, one thread per sample)
 //         shared-memory record per 8 samples: [G2s | G2t | 0 | A1 | 0] (bf16, 8x8 core matrices)
-//   per conditioner net p (s, then t):
-//   T1    D1 [128 smp x Hp] = A1 . B1p^T         (recompute of the hidden pre-activations, bias folded)
-//         GH [128 smp x Hp] = G2 . W2p           (B operand: the forward's B2 image read MN-major)
+//   per conditioner net p (s, then t), in halves of 64 hidden units:
+//   T1    D1 [128 smp x 64] = A1 . B1p^T         (recompute of the hidden pre-activations, bias folded)
+//         GH [128 smp x 64] = G2 . W2p           (B operand: the forward's B2 image read MN-major)
 //   E1    h = relu(D1), ghm = GH * [D1 > 0]  -> bf16 shared-memory images [128 smp x Hp] whose 8x8 core
 //         matrices serve both as a K-major operand (contraction over the hidden units) and as an
 //         MN-major operand (contraction over the samples)
 //   T2    GU [128 smp x 16] += ghm . W1p         (B: the forward's B1 image read MN-major)
+//   then, per net:
 //   T4    ACC[l][p] [128 hid x 16] += h^T . [G2p | 0] + ghm^T . [0 | A1]   (contraction over the samples)
 //         columns 0..7: d/dW2p (last Linear), 8..15: d/dW1p and, through A1's constant-one column, d/db1p
 //   E5    g_u += GU                                                         (fp32)
 // The weight-gradient accumulators ACC stay in TMEM for the whole launch (fp32, 16 columns per layer
-// and net) and are added to the CTA's own row of the partial buffer at the end; last-layer bias
-// gradients are warp-reduced in fp32.  One persistent CTA per SM, 4 epilogue warps + 1 MMA warp.
+// and net, zeroed at the start) and are added to the CTA's own row of the partial buffer at the end;
+// last-layer bias gradients are warp-reduced in fp32.
+//
+// One persistent CTA per SM, 352 threads.  TWO tiles are in flight (slots): each has its own epilogue
+// warpgroup, MMA-issuer warp, TMEM working set (144 columns) and shared-memory records / images, so one
+// tile's epilogue runs under the other tile's MMAs; both accumulate into the same ACC columns.  A
+// producer warp streams each layer's B1 / B2 images (the forward kernel's blob) through a 3-stage
+// shared-memory ring with TMA bulk copies (full / empty mbarriers, one empty arrival per slot).
+//
 // Measured on B200 (profiles/microbench/tmem_bw.cu): tcgen05.ld moves 128 B/clk per SM whatever the
-// number of warps, so the [128 x Hp] fp32 reads of D1 and GH (1024 clk per net at Hp = 128) are the
-// epilogue's floor; an earlier version that formed h^T / ghm^T by a second, transposed recompute in
-// TMEM doubled those reads and ran at half the speed.
+// number of warps (stores ride along for free), so the fp32 reads of D1 and GH (2 x 512 clk per net at
+// Hp = 128) are a floor of the epilogue; a first version that formed h^T / ghm^T by a second,
+// transposed recompute in TMEM doubled those reads and ran at 0.6x the speed of this one.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -38,18 +46,23 @@
 
 namespace {
 
-constexpr int TB_THREADS = 160;        // warps 0..3: epilogue (TMEM lane quarter == warp), warp 4: MMA issuer + allocator
-constexpr int COL_D1 = 0, COL_GH = 128, COL_GU = 256, COL_ACC = 272;
-constexpr int LBO1 = 128, SBO1 = 256;  // the forward kernel's B1 image (K-major)
-constexpr int REC = 640;               // bytes of one 8-sample record of the A1/G2 image
+constexpr int TB_SLOTS = 2;                       // tiles in flight per CTA, one epilogue warpgroup each
+constexpr int TB_THREADS = 128 * TB_SLOTS + 96;   // + one MMA-issuer warp per slot + the weight-producer / allocator warp
+constexpr int SLOT_COLS = 144;                    // TMEM columns per slot: D1 half (64) + GH half (64) + GU (16)
+constexpr int COL_D1 = 0, COL_GH = 64, COL_GU = 128, COL_ACC = TB_SLOTS * SLOT_COLS;
+constexpr int LBO1 = 128, SBO1 = 256;             // the forward kernel's B1 image (K-major)
+constexpr int REC = 640;                          // bytes of one 8-sample record of the A1/G2 image
 constexpr int OFF_G2 = 0, OFF_Z = 256, OFF_A1 = 384;
+constexpr int MAX_STAGES = 3;
 
 struct TbDims {
   int K, L, d0, d1, Hp, nets, n_nets;
-  int b_layer_bytes, b1_off, b2_off, blob_bytes;
+  int b_layer_bytes, b1_off, b2_off;
   int tab_pi, tab_cond, tab_trans, n_tables;
   int n_grad;                                    // floats per partial row
-  int sm_tab, sm_ag, sm_h, sm_ghm, sm_act, sm_gact, sm_gb2, sm_red, sm_bar, sm_total;
+  int n_stages;                                  // weight ring depth (one stage = one layer's B1 and B2 images)
+  // shared memory (bytes): ring | tables | per slot {records, h image, ghm image, act, gact} | gb2 | red | barriers
+  int sm_tab, sm_slot, sm_slot_stride, sm_h, sm_ghm, sm_act, sm_gact, sm_gb2, sm_red, sm_bar, sm_total;
 };
 
 bool tb_dims(const CnfDims& d, TbDims* t) {
@@ -59,22 +72,32 @@ bool tb_dims(const CnfDims& d, TbDims* t) {
   if (COL_ACC + d.L * d.n_nets * 16 > 512) return false;    // weight-gradient accumulators live in TMEM
   t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->Hp = f.Hp; t->nets = d.nets; t->n_nets = d.n_nets;
   t->b_layer_bytes = f.b_layer_bytes; t->b1_off = f.b1_off; t->b2_off = f.b2_off;
-  t->blob_bytes = f.bias_off;                               // the fp32 biases are already folded into the tape
   t->tab_pi = d.tab_pi; t->tab_cond = d.tab_cond; t->tab_trans = d.tab_trans; t->n_tables = d.n_tables;
   t->n_grad = d.L * d.n_nets * 128 * 16 + d.L * 16;
-  int off = (t->blob_bytes + 127) / 128 * 128;
-  t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
-  t->sm_ag = off; off += 16 * REC;
-  off = (off + 1023) / 1024 * 1024;
-  t->sm_h = off; off += TILE_M * f.Hp * 2;
-  t->sm_ghm = off; off += TILE_M * f.Hp * 2;
-  t->sm_act = off; off += d.K * TILE_M * 4;
-  t->sm_gact = off; off += d.K * TILE_M * 4;
-  t->sm_gb2 = off; off += 4 * d.L * 16 * 4;
-  t->sm_red = off; off += 4 * 4 * 8;
-  t->sm_bar = off; off += 128;
-  t->sm_total = off;
-  return t->sm_total <= 227 * 1024;
+  for (int ns = MAX_STAGES; ns >= 2; --ns) {
+    t->n_stages = ns;
+    int off = ns * 2 * f.b_layer_bytes;
+    off = (off + 127) / 128 * 128;
+    t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
+    off = (off + 1023) / 1024 * 1024;
+    t->sm_slot = off;
+    {
+      int o = 16 * REC;                         // records first
+      o = (o + 1023) / 1024 * 1024;
+      t->sm_h = o; o += TILE_M * f.Hp * 2;
+      t->sm_ghm = o; o += TILE_M * f.Hp * 2;
+      t->sm_act = o; o += d.K * TILE_M * 4;
+      t->sm_gact = o; o += d.K * TILE_M * 4;
+      t->sm_slot_stride = (o + 1023) / 1024 * 1024;
+    }
+    off += TB_SLOTS * t->sm_slot_stride;
+    t->sm_gb2 = off; off += 4 * TB_SLOTS * d.L * 16 * 4;
+    t->sm_red = off; off += 4 * 4 * TB_SLOTS * 8;
+    t->sm_bar = off; off += 256;
+    t->sm_total = off;
+    if (t->sm_total <= 227 * 1024) return true;
+  }
+  return false;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -87,6 +110,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ void epi_sync_all() { asm volatile("bar.sync 3, %0;" ::"n"(128 * TB_SLOTS) : "memory"); }
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
 flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
@@ -96,37 +120,41 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
-  uint8_t* ag = smem + p.sm_ag;
-  float* act = reinterpret_cast<float*>(smem + p.sm_act);
-  float* gact = reinterpret_cast<float*>(smem + p.sm_gact);
-  float* gb2 = reinterpret_cast<float*>(smem + p.sm_gb2);     // [warp][L][16]
-  double* red = reinterpret_cast<double*>(smem + p.sm_red);   // [4 sums][4 warps]
+  float* gb2 = reinterpret_cast<float*>(smem + p.sm_gb2);     // [epilogue warp][L][16]
+  double* red = reinterpret_cast<double*>(smem + p.sm_red);   // [4 sums][epilogue warps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
-  uint64_t* ag_ready = bars + 0;    // 128 arrivals, once per layer:  A1/G2 records written
-  uint64_t* t1_done = bars + 1;     // commit, once per net phase:    D1, GH complete
-  uint64_t* hg_ready = bars + 2;    // 128 arrivals, per phase:       h, ghm (bf16) images in shared memory
-  uint64_t* t4_done = bars + 3;     // commit, per phase:             GU update and weight-gradient MMAs complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  // per slot s:  ag_ready (128 arrivals, once per layer)   epilogue -> MMA: A1/G2 records written
+  //              t1_done  (commit, once per half phase)    MMA -> epilogue: D1 / GH halves complete
+  //              hg_ready (128 arrivals, per half phase)   epilogue -> MMA: 64 more columns of the h / ghm images
+  //              t4_done  (commit, once per net phase)     MMA -> epilogue: GU update and weight-gradient MMAs done
+  // weight ring: full[st] (expect_tx, producer -> MMA), empty[st] (one commit per slot, MMA -> producer)
+  uint64_t* ag_ready = bars;
+  uint64_t* t1_done = bars + TB_SLOTS;
+  uint64_t* hg_ready = bars + 2 * TB_SLOTS;
+  uint64_t* t4_done = bars + 3 * TB_SLOTS;
+  uint64_t* w_full = bars + 4 * TB_SLOTS;
+  uint64_t* w_empty = w_full + MAX_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + MAX_STAGES);
+  constexpr int MMA_WARP0 = 4 * TB_SLOTS, PROD_WARP = 4 * TB_SLOTS + TB_SLOTS;
 
   // ---- one-time setup ---------------------------------------------------------------------
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(blob);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    if (do_bwd)
-      for (int i = tid; i < p.blob_bytes / 16; i += TB_THREADS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < p.n_tables; i += TB_THREADS) tab[i] = tables[i];
-    uint4* z4 = reinterpret_cast<uint4*>(ag);
+  for (int i = tid; i < p.n_tables; i += TB_THREADS) tab[i] = tables[i];
+  for (int sl = 0; sl < TB_SLOTS; ++sl) {       // zero blocks of the records stay zero for the whole launch
+    uint4* z4 = reinterpret_cast<uint4*>(smem + p.sm_slot + sl * p.sm_slot_stride);
     for (int i = tid; i < 16 * REC / 16; i += TB_THREADS) z4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 4 * p.L * 16; i += TB_THREADS) gb2[i] = 0.f;
   }
+  for (int i = tid; i < 4 * TB_SLOTS * p.L * 16; i += TB_THREADS) gb2[i] = 0.f;
   if (tid == 0) {
-    mbar_init(ag_ready, 128);
-    mbar_init(t1_done, 1);
-    mbar_init(hg_ready, 128);
-    mbar_init(t4_done, 1);
+    for (int sl = 0; sl < TB_SLOTS; ++sl) {
+      mbar_init(ag_ready + sl, 128);
+      mbar_init(t1_done + sl, 1);
+      mbar_init(hg_ready + sl, 128);
+      mbar_init(t4_done + sl, 1);
+    }
+    for (int st = 0; st < MAX_STAGES; ++st) { mbar_init(w_full + st, 1); mbar_init(w_empty + st, TB_SLOTS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == PROD_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -136,81 +164,123 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int Hp = p.Hp, n_ph = p.n_nets;
+  if (warp < 4 && do_bwd) {                      // the weight-gradient accumulators start at zero
+    uint32_t zero[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zero[i] = 0u;
+    for (int a = 0; a < p.L * n_ph; ++a) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + COL_ACC + a * 16, zero);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int G = gridDim.x;
-  const int Hp = p.Hp, n_ph = p.n_nets;
+  const int64_t my_tiles = (ntiles - blockIdx.x + G - 1) / G;          // tiles blockIdx.x, +G, +2G, ...
+  const int64_t npairs = (my_tiles + TB_SLOTS - 1) / TB_SLOTS;         // slot s takes tile index TB_SLOTS*i + s
+  const int n_half = (Hp + 63) / 64;
+  const uint32_t img_sr = (uint32_t)(Hp / 8) * 128;                    // bytes between 8-sample row groups of the images
+  const int stage_bytes = 2 * p.b_layer_bytes;
 
-  if (warp == 4) {
-    // ================================ MMA issuer ==============================================
+  if (warp == PROD_WARP) {
+    // ================================ weight producer ==========================================
     if (lane == 0 && do_bwd) {
+      const int64_t n_items = npairs * p.L;
+      for (int64_t it = 0; it < n_items; ++it) {
+        const int st = (int)(it % p.n_stages);
+        const uint32_t round = (uint32_t)(it / p.n_stages);
+        if (round > 0) mbar_wait_backoff(w_empty + st, (round - 1) & 1);
+        const int l = p.L - 1 - (int)(it % p.L);
+        uint8_t* dst = smem + st * stage_bytes;
+        mbar_expect_tx(w_full + st, (uint32_t)stage_bytes);
+        bulk_copy_g2s(dst, blob + p.b1_off + (size_t)l * p.b_layer_bytes, (uint32_t)p.b_layer_bytes, w_full + st);
+        bulk_copy_g2s(dst + p.b_layer_bytes, blob + p.b2_off + (size_t)l * p.b_layer_bytes, (uint32_t)p.b_layer_bytes, w_full + st);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= MMA_WARP0) {
+    // ================================ MMA issuers: one per slot ================================
+    if (lane == 0 && do_bwd) {
+      const int sl = warp - MMA_WARP0;
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t rec = smem_base + p.sm_ag;
-      const uint32_t tm = tmem_base;
+      const uint32_t slot_base = smem_base + p.sm_slot + sl * p.sm_slot_stride;
+      const uint32_t rec = slot_base;
+      const uint32_t h_img = slot_base + p.sm_h, ghm_img = slot_base + p.sm_ghm;
+      const uint32_t tm = tmem_base + sl * SLOT_COLS;
       const uint64_t a1_k = make_desc(rec + OFF_A1, 128, REC);     // [128 smp x 16] K-major (second k-block = zeros)
       const uint64_t g2_k = make_desc(rec + OFF_G2, 128, REC);     // [128 smp x 16] K-major: g_s | g_t
-      const uint32_t id_t1a = make_idesc_ex(Hp, 0, 0), id_t1b = make_idesc_ex(Hp, 0, 1);
       const uint32_t id_t2 = make_idesc_ex(16, 0, 1);
       const uint32_t id_t4 = make_idesc_ex(16, 1, 1);
-      const uint32_t h_img = smem_base + p.sm_h, ghm_img = smem_base + p.sm_ghm;
-      const uint32_t img_sr = (uint32_t)(Hp / 8) * 128;       // bytes between 8-sample row groups of the images
-      uint32_t lc = 0, pc = 0;
-      bool first_tile = true;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
-        for (int li = 0; li < p.L; ++li, ++lc) {
+      uint32_t lc = 0, hc = 0;
+      for (int64_t i = 0; i < npairs; ++i) {
+        const bool has_tile = TB_SLOTS * i + sl < my_tiles;
+        for (int li = 0; li < p.L; ++li) {
+          const int64_t it = i * p.L + li;
+          const int st = (int)(it % p.n_stages);
+          mbar_wait_backoff(w_full + st, (uint32_t)(it / p.n_stages) & 1);
+          if (!has_tile) { mbar_arrive(w_empty + st); continue; }     // keep the ring's arrival count
           const int l = p.L - 1 - li;
-          const uint32_t b1 = smem_base + p.b1_off + l * p.b_layer_bytes;
-          const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
-          mbar_wait(ag_ready, lc & 1);
+          const uint32_t b1 = smem_base + st * stage_bytes;
+          const uint32_t b2 = b1 + p.b_layer_bytes;
+          mbar_wait_backoff(ag_ready + sl, lc & 1);
+          ++lc;
           tc_fence_after();
-          for (int ph = 0; ph < n_ph; ++ph, ++pc) {
+          for (int ph = 0; ph < n_ph; ++ph) {
             const uint32_t b1p = b1 + ph * (Hp / 8) * SBO1;      // rows ph*Hp.. of the B1 image
             const uint32_t b2p = b2 + ph * (Hp / 16) * 512;      // k-steps of net ph in the B2 image
-            // B2 image, element (n2, hid): (hid/8)*256 + (n2/8)*128 + (n2%8)*16 + (hid%8)*2
-            //   -> MN-major with the hidden unit as the MN index: S_mn = 256, S_k = 128
-            const uint64_t w2_mn = make_desc(b2p, 128, 256);
-            // ---- T1
-            mma_ss(tm + COL_D1, a1_k, make_desc(b1p, LBO1, SBO1), id_t1a, 0u);
-            mma_ss(tm + COL_GH, g2_k, w2_mn, id_t1b, 0u);
-            tc_commit(t1_done);
-            // ---- T2: GU += ghm . W1p ; A: the ghm image K-major (k-step = 16 hidden = 2 core matrices);
-            //      B: B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
-            mbar_wait(hg_ready, pc & 1);
-            tc_fence_after();
-            for (int j = 0; j < Hp / 16; ++j)
-              mma_ss(tm + COL_GU, make_desc(ghm_img + j * 256, 128, img_sr), make_desc(b1p + j * 512, 256, 128), id_t2,
-                     (ph > 0 || j > 0) ? 1u : 0u);
+            for (int hf = 0; hf < n_half; ++hf, ++hc) {
+              const int h0 = 64 * hf, w = min(64, Hp - h0);
+              // ---- T1 (half): D1 = A1 . B1p[h0..]^T ; GH = G2 . W2p[.., h0..]
+              // B2 image, element (n2, hid): (hid/8)*256 + (n2/8)*128 + (n2%8)*16 + (hid%8)*2
+              //   -> MN-major with the hidden unit as the MN index: S_mn = 256, S_k = 128
+              mma_ss(tm + COL_D1, a1_k, make_desc(b1p + (h0 / 8) * SBO1, LBO1, SBO1), make_idesc_ex(w, 0, 0), 0u);
+              mma_ss(tm + COL_GH, g2_k, make_desc(b2p + (h0 / 16) * 512, 128, 256), make_idesc_ex(w, 0, 1), 0u);
+              tc_commit(t1_done + sl);
+              // ---- T2 (half): GU += ghm . W1p ; A: the ghm image K-major (k-step = 16 hidden = 2 core
+              //      matrices); B: B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
+              mbar_wait_backoff(hg_ready + sl, hc & 1);
+              tc_fence_after();
+              for (int j = h0 / 16; j < (h0 + w) / 16; ++j)
+                mma_ss(tm + COL_GU, make_desc(ghm_img + j * 256, 128, img_sr), make_desc(b1p + j * 512, 256, 128), id_t2,
+                       (ph > 0 || j > 0) ? 1u : 0u);
+            }
             // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16);
             //      A: the h / ghm images read MN-major (M = hidden unit): S_mn = 128, S_k = img_sr
-            const uint32_t acc = tm + COL_ACC + (l * n_ph + ph) * 16;
+            const uint32_t acc = tmem_base + COL_ACC + (l * n_ph + ph) * 16;
             const uint32_t sbo_g = (ph == 0) ? 256u : 128u;      // [G2p | 0]: the zero block sits at OFF_Z
             for (int j = 0; j < 8; ++j)
               mma_ss(acc, make_desc(h_img + j * 2 * img_sr, img_sr, 128),
-                     make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4, (!first_tile || j > 0) ? 1u : 0u);
+                     make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4, 1u);
             for (int j = 0; j < 8; ++j)     // [0 | A1]
               mma_ss(acc, make_desc(ghm_img + j * 2 * img_sr, img_sr, 128), make_desc(rec + OFF_Z + j * 2 * REC, REC, 128),
                      id_t4, 1u);
-            tc_commit(t4_done);
+            tc_commit(t4_done + sl);
           }
+          tc_commit(w_empty + st);           // this slot no longer reads the stage once everything above completed
         }
-        first_tile = false;
       }
     }
     __syncwarp();
   } else {
-    // ================================ epilogue warps ==========================================
-    const int t = tid;                                   // sample row of the tile == TMEM lane
-    const uint32_t tm = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint8_t* rec_row = ag + (t >> 3) * REC + (t & 7) * 16;
-    const uint32_t img_row = (uint32_t)((t >> 3) * (Hp / 8) * 128 + (t & 7) * 16);   // 16-byte slot in core matrix 0
-    const uint32_t h_row = smem_u32(smem + p.sm_h) + img_row, ghm_row = smem_u32(smem + p.sm_ghm) + img_row;
+    // ================================ epilogue warpgroups =====================================
+    const int sl = warp >> 2;
+    const int t = tid & 127;                              // sample row of the tile == TMEM lane
+    const uint32_t tm = tmem_base + sl * SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* slot_base = smem + p.sm_slot + sl * p.sm_slot_stride;
+    uint8_t* rec_row = slot_base + (t >> 3) * REC + (t & 7) * 16;
+    float* act = reinterpret_cast<float*>(slot_base + p.sm_act);
+    float* gact = reinterpret_cast<float*>(slot_base + p.sm_gact);
+    const uint32_t img_row = (uint32_t)(t >> 3) * img_sr + (t & 7) * 16;   // 16-byte slot in core matrix 0
+    const uint32_t h_row = smem_u32(slot_base + p.sm_h) + img_row, ghm_row = smem_u32(slot_base + p.sm_ghm) + img_row;
     const int* pi_last = tab + p.tab_pi + p.L * p.K;
     const int K = p.K;
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
     const bool has_s = (p.nets & 1) != 0, has_t = (p.nets & 2) != 0;
     const uint32_t one_bits = 0x3f80u;
     double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
-    uint32_t pc = 0;
+    uint32_t hc = 0, pc = 0;
     // register prefetch of the next tile's inputs (element e = t + 128*i of the row-major z tile)
     constexpr int KMAX = 14;
     float zr[KMAX], ld_r = 0.f;
@@ -237,8 +307,9 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
         tq[0] = tq[1] = tq[2] = tq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if ((int64_t)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
+    const int64_t tile0 = blockIdx.x + (int64_t)sl * G, tstep = (int64_t)TB_SLOTS * G;
+    if (tile0 < ntiles) fetch_tile(tile0);
+    for (int64_t tile = tile0; tile < ntiles; tile += tstep) {
       const int64_t base = tile * TILE_M;
       const int64_t n = base + t;
       const bool valid = n < N;
@@ -257,8 +328,8 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       }
       const float ldv = ld_r;
       const int ylab = y_r;
-      wg_sync(0);
-      if (tile + G < ntiles) fetch_tile(tile + G);
+      wg_sync(sl);
+      if (tile + tstep < ntiles) fetch_tile(tile + tstep);
       // ---- loss head (calibrators.py:288-291), one thread per sample ----------------------------
       float gld = 0.f;
       {
@@ -334,9 +405,9 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             *reinterpret_cast<uint4*>(rec_row + OFF_A1) = v;
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(ag_ready);
-            // last-layer bias gradients: the warp's 16 column sums by a halving butterfly (15 shuffles);
-            // lane L ends up with column ((L>>1) & 15) bit-reversed as below, fp32, no atomics
+            mbar_arrive(ag_ready + sl);
+            // last-layer bias gradients: the warp's 16 column sums by a halving butterfly (15 shuffles),
+            // fp32, no atomics; lane L (even) ends up with the column whose bits are L's bits 4..1
             float w8[8], w4[4], w2[2], w1;
             {
               const bool hi = (lane & 16) != 0;
@@ -374,50 +445,51 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             }
           }
           for (int ph = 0; ph < n_ph; ++ph, ++pc) {
-            // ---- E1: h = relu(D1), ghm = GH * [D1 > 0] -> bf16 shared-memory images ------------------
-            // t1_done of this phase also says that the previous phase's MMAs no longer read the images.
-            // TMEM loads of the next 32 columns are in flight while the current 32 are converted.
-            mbar_wait(t1_done, pc & 1);
-            tc_fence_after();
-            uint32_t rd0[32], rg0[32], rd1[32], rg1[32];
-            auto convert = [&](const uint32_t (&rd)[32], const uint32_t (&rg)[32], int c) {
+            for (int hf = 0; hf < n_half; ++hf, ++hc) {
+              // ---- E1 (half): h = relu(D1), ghm = GH * [D1 > 0] -> bf16 shared-memory images -----------
+              // The first t1_done of a net phase also says that the previous phase's MMAs no longer read
+              // the images.  TMEM loads of the next 16 columns fly while the current 16 are converted.
+              const int h0 = 64 * hf, w = min(64, Hp - h0);
+              mbar_wait(t1_done + sl, hc & 1);
+              tc_fence_after();
+              uint32_t rdA[16], rgA[16], rdB[16], rgB[16];
+              auto convert = [&](const uint32_t (&rd)[16], const uint32_t (&rg)[16], int c) {
 #pragma unroll
-              for (int b8 = 0; b8 < 4; ++b8) {
-                uint32_t vh[4], vg[4];
+                for (int b8 = 0; b8 < 2; ++b8) {
+                  uint32_t vh[4], vg[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float d0v = __uint_as_float(rd[8 * b8 + 2 * i]), d1v = __uint_as_float(rd[8 * b8 + 2 * i + 1]);
-                  vh[i] = pack_relu_bf16(d0v, d1v);
-                  vg[i] = pack_bf16(d0v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i]) : 0.f,
-                                    d1v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i + 1]) : 0.f);
-                }
-                if (c + 8 * b8 < Hp) {               // Hp is a multiple of 16, not of 32
-                  const uint32_t off = (uint32_t)(c / 8 + b8) * 128;
+                  for (int i = 0; i < 4; ++i) {
+                    const float d0v = __uint_as_float(rd[8 * b8 + 2 * i]), d1v = __uint_as_float(rd[8 * b8 + 2 * i + 1]);
+                    vh[i] = pack_relu_bf16(d0v, d1v);
+                    vg[i] = pack_bf16(d0v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i]) : 0.f,
+                                      d1v > 0.f ? __uint_as_float(rg[8 * b8 + 2 * i + 1]) : 0.f);
+                  }
+                  const uint32_t off = (uint32_t)((h0 + c) / 8 + b8) * 128;
                   sts128(h_row + off, vh[0], vh[1], vh[2], vh[3]);
                   sts128(ghm_row + off, vg[0], vg[1], vg[2], vg[3]);
                 }
+              };
+              tmem_ld16(tm + COL_D1, rdA);
+              tmem_ld16(tm + COL_GH, rgA);
+              for (int c = 0; c < w; c += 32) {
+                tmem_wait_ld16(rdA);
+                tmem_wait_ld16(rgA);
+                if (c + 16 < w) { tmem_ld16(tm + COL_D1 + c + 16, rdB); tmem_ld16(tm + COL_GH + c + 16, rgB); }
+                convert(rdA, rgA, c);
+                if (c + 16 < w) {
+                  tmem_wait_ld16(rdB);
+                  tmem_wait_ld16(rgB);
+                  if (c + 32 < w) { tmem_ld16(tm + COL_D1 + c + 32, rdA); tmem_ld16(tm + COL_GH + c + 32, rgA); }
+                  convert(rdB, rgB, c + 16);
+                }
               }
-            };
-            tmem_ld32(tm + COL_D1, rd0);
-            tmem_ld32(tm + COL_GH, rg0);
-            for (int c = 0; c < Hp; c += 64) {
-              tmem_wait_ld32(rd0);
-              tmem_wait_ld32(rg0);
-              if (c + 32 < Hp) { tmem_ld32(tm + COL_D1 + c + 32, rd1); tmem_ld32(tm + COL_GH + c + 32, rg1); }
-              convert(rd0, rg0, c);
-              if (c + 32 < Hp) {
-                tmem_wait_ld32(rd1);
-                tmem_wait_ld32(rg1);
-                if (c + 64 < Hp) { tmem_ld32(tm + COL_D1 + c + 64, rd0); tmem_ld32(tm + COL_GH + c + 64, rg0); }
-                convert(rd1, rg1, c + 32);
-              }
+              fence_async_smem();
+              tc_fence_before();
+              mbar_arrive(hg_ready + sl);
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(hg_ready);
           }
           // ---- E5: gradient on the conditioning logits ---------------------------------------------
-          mbar_wait(t4_done, (pc - 1) & 1);
+          mbar_wait(t4_done + sl, (pc - 1) & 1);
           tc_fence_after();
           {
             uint32_t r[16];
@@ -430,22 +502,29 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           tc_fence_before();
         }
       }
-      wg_sync(0);   // every thread is done with act / gact before the next tile overwrites them
+      wg_sync(sl);   // every thread is done with act / gact before the next tile overwrites them
     }
     // ---- loss sums -------------------------------------------------------------------------------
+    constexpr int EW = 4 * TB_SLOTS;
     if (loss_acc != nullptr) {
       const double v0 = warp_sum_d(a_loss), v1 = warp_sum_d(a_ce), v2 = warp_sum_d(a_ld), v3 = warp_sum_d(a_bad);
-      if (lane == 0) { red[0 * 4 + warp] = v0; red[1 * 4 + warp] = v1; red[2 * 4 + warp] = v2; red[3 * 4 + warp] = v3; }
-      wg_sync(0);
-      if (t < 4) atomicAdd(loss_acc + t, (red[t * 4 + 0] + red[t * 4 + 1]) + (red[t * 4 + 2] + red[t * 4 + 3]));
+      if (lane == 0) { red[0 * EW + warp] = v0; red[1 * EW + warp] = v1; red[2 * EW + warp] = v2; red[3 * EW + warp] = v3; }
+    }
+    tc_fence_before();
+    epi_sync_all();      // both slots are done: every MMA has completed, gb2 and red are final
+    tc_fence_after();
+    if (loss_acc != nullptr && tid < 4) {
+      double a = 0.0;
+      for (int wv = 0; wv < EW; ++wv) a += red[tid * EW + wv];
+      atomicAdd(loss_acc + tid, a);
     }
     // ---- weight-gradient accumulators -> this CTA's row of the partial buffer ---------------------
-    if (do_bwd) {
+    if (do_bwd && sl == 0) {
       float* row = partials + (size_t)blockIdx.x * p.n_grad;
-      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + COL_ACC;
       for (int a = 0; a < p.L * n_ph; ++a) {
         uint32_t r[16];
-        tmem_ld16(tm + COL_ACC + a * 16, r);
+        tmem_ld16(tacc + a * 16, r);
         tmem_wait_ld16(r);
         float4* dst = reinterpret_cast<float4*>(row + ((size_t)a * 128 + t) * 16);
 #pragma unroll
@@ -456,16 +535,18 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           dst[i] = o;
         }
       }
-      wg_sync(0);   // gb2 rows of all four warps are final
       float* rb = row + (size_t)p.L * n_ph * 128 * 16;
-      for (int i = t; i < p.L * 16; i += 128)
-        rb[i] += (gb2[(0 * p.L) * 16 + i] + gb2[(1 * p.L) * 16 + i]) + (gb2[(2 * p.L) * 16 + i] + gb2[(3 * p.L) * 16 + i]);
+      for (int i = t; i < p.L * 16; i += 128) {
+        float a = 0.f;
+        for (int wv = 0; wv < EW; ++wv) a += gb2[(wv * p.L) * 16 + i];
+        rb[i] += a;
+      }
     }
   }
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == PROD_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }

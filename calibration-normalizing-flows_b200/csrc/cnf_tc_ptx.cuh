@@ -35,6 +35,11 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) { 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try(bar, parity)) {}
 }
+// for single-thread issuer / producer warps: back off between polls so the spinning warp does not
+// take issue slots from the epilogue warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) __nanosleep(20);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
