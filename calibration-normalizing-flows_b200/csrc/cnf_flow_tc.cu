@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t pack_hidden(uint32_t lo, uint32_t hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int EPI>
+template <int EPI, bool TAPE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
@@ -336,10 +336,10 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
               if (!inverse) { yv = xv[q] * expf(sv) + tv; ld += sv; }
               else          { yv = (xv[q] - tv) * expf(-sv); ld -= sv; }
               act[ps[q]] = yv;
-              svs[q] = sv;
+              if (TAPE) svs[q] = sv;
             }
           }
-          if (tape != nullptr && base + t < N) {   // training: what autograd would save for this layer
+          if (TAPE && base + t < N) {   // training: what autograd would save for this layer
             float4* tp = reinterpret_cast<float4*>(tape + ((size_t)l * N + (base + t)) * 16);
             tp[0] = make_float4(xv[0], xv[1], xv[2], xv[3]);
             tp[1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
@@ -503,13 +503,15 @@ int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const in
   const int io16 = (((uintptr_t)x | (uintptr_t)z) % 16 == 0 && (TILE_M * d.K) % 4 == 0) ? 1 : 0;
   int epi = 0;
   if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
-  if (epi == 0) {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
-    flow_tc_kernel<0><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16, tape);
-  } else {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
-    flow_tc_kernel<1><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse, io16, tape);
-  }
+#define LAUNCH_TC(E, T)                                                                                         \
+  do {                                                                                                          \
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
+    flow_tc_kernel<E, T><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N,   \
+                                                               inverse, io16, tape);                            \
+  } while (0)
+  if (tape) { if (epi == 0) LAUNCH_TC(0, true); else LAUNCH_TC(1, true); }
+  else      { if (epi == 0) LAUNCH_TC(0, false); else LAUNCH_TC(1, false); }
+#undef LAUNCH_TC
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
