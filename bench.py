@@ -180,7 +180,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -421,12 +421,27 @@ def run_ours(args):
                            'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1'},
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
                 'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'train_step_fp32': train_fp32, 'c5': extra}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that libraries
+    write to fd 1 (NCCL prints its version banner there) is redirected to stderr in main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
@@ -444,7 +459,7 @@ def main():
     if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', '29511', os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_JSON_OUT.fileno()))
     run_ours(args)
 
 
