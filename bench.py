@@ -412,6 +412,46 @@ def run_ours(args):
         med, times = cpu_reference_pass(flat, xc, reps=3, warm=1)
         cpu = {'value': N_STEP / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': '1,000,000 samples x 3 passes (median), torch CPU ops restating flows/flows.py:101-112'}
+        # the other legs of SURVEY.md 8(d) on the same host cores, bounded samples
+        import ref_port_torch as rp
+        import flow_oracle as orc
+        cores = torch.get_num_threads()
+        if train is not None:
+            n_t = 200_000
+            xt_c, yt_c = synth(n_t, 13)
+            st = rp.TrainState(flat / 300.0, K, L, HIDDEN)
+            st.step(xt_c, yt_c)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                st.step(xt_c, yt_c)
+            dt = (time.perf_counter() - t0) / 2
+            cb = {'value': n_t / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                  'sample': '200,000 samples x 2 full-batch steps: torch autograd + torch.optim.Adam on the '
+                            'reference op sequence (calibrators.py:287-295)'}
+            train['cpu_baseline'] = cb
+            if train_fp32 is not None:
+                train_fp32['cpu_baseline'] = cb
+        if extra is not None:
+            layers = rp.unflatten(flat, K, L, HIDDEN)
+            with torch.no_grad():
+                rp.inverse(layers, xc[:200_000])
+                t0 = time.perf_counter()
+                rp.inverse(layers, xc)
+                dt = time.perf_counter() - t0
+            extra['inverse']['cpu_baseline'] = {'value': N_STEP / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                                'sample': '1,000,000 samples, one pass, flows/flows.py:114-126 in torch CPU ops'}
+            n_mc = 2_000_000
+            xm, ym_c = synth(n_mc, 17)
+            pm_c = torch.softmax(xm, dim=1).numpy()
+            ym_n = ym_c.numpy()
+            t0 = time.perf_counter()
+            orc.expected_calibration_error(pm_c, ym_n, 15)
+            orc.neg_log_likelihood(pm_c, ym_n)
+            orc.accuracy(pm_c, ym_n)
+            dt = time.perf_counter() - t0
+            extra['metrics']['cpu_baseline'] = {'value': n_mc / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                                                'sample': '2,000,000 samples: numpy restatement of utils/metrics.py:35-73, 6-15, 76-80 '
+                                                          '(15 masked passes + one-hot NLL + argmax accuracy)'}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,

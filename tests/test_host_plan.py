@@ -151,3 +151,39 @@ def test_on_disk_logit_formats_round_trip(tmp_path):
             pickle.dump(rng.standard_normal((n, 10)).astype(np.float32), f)
     tr, te = D.load_pickled_logits(str(tmp_path), pin=False)
     assert tr.shape == (9, 10) and te.shape == (4, 10) and tr.dtype == torch.float32
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(10, 6, [128], True, True), (3, 4, [32], False, True),
+                                                    (7, 5, [16], True, True), (2, 4, [7], True, True),
+                                                    (14, 7, [100], True, True)])
+def test_tc_training_gradient_map_covers_exactly_the_live_parameters(K, L, hidden, scale, shift):
+    """cnf_plan_build_tcgrad (partial-row entry -> flat index) is a bijection onto the flat entries the
+    fp32 planner's gather map references, i.e. onto the parameters with a non-zero gradient."""
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    info, gather, _ = plan_host(K, L, hidden, scale, shift)
+    desc, _keep = _lib.make_desc(K, L, hidden, scale, shift, _lib.PREC_BF16_TC)
+    ng, rows, wsb = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.call('cnf_tc_train_info', ctypes.byref(desc), ctypes.byref(ng), ctypes.byref(rows), ctypes.byref(wsb))
+    n_nets = int(scale) + int(shift)
+    assert ng.value == L * n_nets * 128 * 16 + L * 16 and rows.value >= 148
+    assert wsb.value == (K + 1 + 16 * L) * 4
+    g = np.empty(ng.value, dtype=np.int32)
+    _lib.call('cnf_plan_build_tcgrad', ctypes.byref(desc), g.ctypes.data_as(ctypes.c_void_p))
+    used = g[g >= 0]
+    assert used.size == np.unique(used).size
+    assert set(used.tolist()) == set(gather[gather >= 0].tolist())
+    assert used.max() < info.n_flat
+
+
+def test_tc_training_shapes_outside_coverage_report_zero():
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    for K, L, hidden in ((16, 4, [64]), (10, 8, [128]), (10, 2, [64, 64]), (10, 2, [256])):
+        desc, _keep = _lib.make_desc(K, L, hidden, True, True, _lib.PREC_BF16_TC)
+        ng, rows, wsb = ctypes.c_int64(-1), ctypes.c_int64(-1), ctypes.c_int64(-1)
+        _lib.call('cnf_tc_train_info', ctypes.byref(desc), ctypes.byref(ng), ctypes.byref(rows), ctypes.byref(wsb))
+        assert ng.value == 0
+        g = np.empty(16, dtype=np.int32)
+        rc = _lib.load().cnf_plan_build_tcgrad(ctypes.byref(desc), g.ctypes.data_as(ctypes.c_void_p))
+        assert rc == -4
