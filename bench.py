@@ -342,9 +342,36 @@ def run_ours(args):
         m1.record()
         barrier()
         met_ms = max_over_ranks(m0.elapsed_time(m1)) / 20
+        # AffineConstantLayer / TempScaler streaming kernel: pure 8K B/sample
+        n_a = 10_000_000
+        xa = synth(n_a, 41 + rank, dev)[0]
+        za = torch.empty_like(xa)
+        sa = torch.full((K,), 0.1, device=dev)
+        ta = torch.full((K,), -0.2, device=dev)
+
+        def astep():
+            _lib.call('cnf_affine_const', _ptr(xa), _ptr(sa), _ptr(ta), _ptr(za), ctypes.c_int64(n_a), ctypes.c_int32(K),
+                      ctypes.c_int32(0), _stream(dev))
+        for _ in range(3):
+            astep()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            astep()
+        a1.record()
+        barrier()
+        aff_ms = max_over_ranks(a0.elapsed_time(a1)) / 20
+        del xa, za
         hbm_peak = peaks()[0]
+        ab = 8 * K * n_a / (aff_ms * 1e-3) / 1e9
         mb = (4 * K + 8) * n_m / (met_ms * 1e-3) / 1e9
-        extra = {'inverse': {'value': world * N_STEP / (inv_ms * 1e-3), 'unit': UNIT, 'ms_per_step': inv_ms,
+        extra = {'affine_const': {'value': world * n_a / (aff_ms * 1e-3), 'unit': UNIT, 'ms_per_step': aff_ms,
+                                  'samples_per_gpu': n_a,
+                                  'what': 'AffineConstantLayer.forward z = x*exp(s)+t (flows/flows.py:53-58), fp32',
+                                  'roofline': {'bound': 'hbm', 'achieved': ab, 'peak': hbm_peak, 'unit': 'GB/s',
+                                               'frac': ab / hbm_peak, 'note': 'algorithmic bytes 8K = 80 B/sample'}},
+                 'inverse': {'value': world * N_STEP / (inv_ms * 1e-3), 'unit': UNIT, 'ms_per_step': inv_ms,
                              'what': 'Flow.backward (inverse + log-det) on 1,000,000 samples per GPU, same path as value'},
                  'metrics': {'value': world * n_m / (met_ms * 1e-3), 'unit': UNIT, 'ms_per_step': met_ms,
                              'samples_per_gpu': n_m, 'what': 'ECE(15 bins)+NLL+accuracy in one pass over fp32 probabilities',
