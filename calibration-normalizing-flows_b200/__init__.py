@@ -8,7 +8,8 @@ from . import _lib
 
 _lib.load()
 
-from .flows.flows import Flow, NvpCouplingLayer, CouplingStack, AffineConstantLayer  # noqa: E402
+from .flows.flows import (Flow, NvpCouplingLayer, CouplingStack, AffineConstantLayer, PlanarLayer,  # noqa: E402
+                          RadialLayer)
 from .flows.utils import MLP, TempScaler  # noqa: E402
 from .flows.nice_torch import NiceFlow  # noqa: E402
 from .flows.realNVP_torch import RealNvpFlow  # noqa: E402
@@ -16,6 +17,6 @@ from .calibrators import Calibrator, TorchFlowCalibrator, FusedNLLTrainer  # noq
 from .utils.metrics import expected_calibration_error, neg_log_likelihood, accuracy  # noqa: E402
 from .utils.ops import onehot_encode  # noqa: E402
 
-__all__ = ['Flow', 'NvpCouplingLayer', 'CouplingStack', 'AffineConstantLayer', 'TempScaler', 'MLP', 'NiceFlow', 'RealNvpFlow', 'Calibrator',
+__all__ = ['Flow', 'NvpCouplingLayer', 'CouplingStack', 'AffineConstantLayer', 'PlanarLayer', 'RadialLayer', 'TempScaler', 'MLP', 'NiceFlow', 'RealNvpFlow', 'Calibrator',
            'TorchFlowCalibrator', 'FusedNLLTrainer', 'expected_calibration_error', 'neg_log_likelihood',
            'accuracy', 'onehot_encode']

@@ -62,6 +62,10 @@ SIGNATURES = {
     'cnf_calibrated_probs': [_P, _I64, _I32, _P, _P, _P],
     'cnf_affine_const': [_P, _P, _P, _P, _I64, _I32, _I32, _P],
     'cnf_affine_const_backward': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'cnf_planar_forward': [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'cnf_planar_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    'cnf_radial_forward': [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    'cnf_radial_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
 }
 
 _lib = None

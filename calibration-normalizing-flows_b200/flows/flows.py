@@ -101,6 +101,116 @@ class AffineConstantLayer(nn.Module):
         return x, log_det
 
 
+class _PlanarFn(torch.autograd.Function):
+    """(x, w, u_hat, b) -> (z, log_det) through cnf_planar_forward / cnf_planar_backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, u_hat, b):
+        x = x.to(torch.float32).contiguous()
+        N, K = x.shape
+        wv, uv, bv = (t.detach().to(torch.float32).contiguous().view(-1) for t in (w, u_hat, b))
+        z = torch.empty_like(x)
+        ld = torch.empty(N, dtype=torch.float32, device=x.device)
+        _lib.call('cnf_planar_forward', _ptr(x), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(z), _ptr(ld), ctypes.c_int64(N),
+                  ctypes.c_int32(K), _stream(x.device))
+        ctx.save_for_backward(x, wv, uv, bv)
+        ctx.shapes = (w.shape, u_hat.shape, b.shape)
+        return z, ld
+
+    @staticmethod
+    def backward(ctx, g_z, g_ld):
+        x, wv, uv, bv = ctx.saved_tensors
+        N, K = x.shape
+        g_z = torch.zeros_like(x) if g_z is None else g_z.to(torch.float32).contiguous()
+        g_ld = None if g_ld is None else g_ld.to(torch.float32).contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty(K, dtype=torch.float32, device=x.device)
+        gu = torch.empty(K, dtype=torch.float32, device=x.device)
+        gb = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.call('cnf_planar_backward', _ptr(x), _ptr(g_z), _ptr(g_ld), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(gx),
+                  _ptr(gw), _ptr(gu), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        ws, us, bs = ctx.shapes
+        return gx, gw.view(ws), gu.view(us), gb.view(bs)
+
+
+class PlanarLayer(nn.Module):
+    """Drop-in for reference ``flows/flows.py:129-164`` (forward direction only; ``invertible`` is
+    False, so a ``Flow`` containing it raises on ``backward`` exactly as the reference does).  The
+    K-vector re-parametrisation of ``u`` (:150-153) stays in torch ops; the per-sample work is one
+    streaming kernel, differentiable through ``cnf_planar_backward``."""
+
+    def __init__(self, dim=0, params=None):
+        super().__init__()
+        if params is not None:
+            self.w = params['w'].squeeze()
+            self.u = params['u'].squeeze()
+            self.b = params['b'].squeeze()
+        else:
+            if dim < 1:
+                raise ValueError('Either dim of params must be provided!')
+            self.w = nn.Parameter(torch.rand(dim))
+            self.u = nn.Parameter(torch.rand(dim))
+            self.b = nn.Parameter(torch.rand(1))
+        self.invertible = False
+
+    def forward(self, x):
+        require_cuda(x)
+        wtu = torch.dot(self.w, self.u)
+        m = -1 + torch.log1p(torch.exp(wtu))
+        u_hat = self.u + (m - wtu) * self.w / torch.norm(self.w)
+        z, log_det = _PlanarFn.apply(x, self.w, u_hat, self.b.reshape(1))
+        return z, log_det.squeeze()
+
+
+class _RadialFn(torch.autograd.Function):
+    """(x, z0, a, b_hat) -> z through cnf_radial_forward / cnf_radial_backward."""
+
+    @staticmethod
+    def forward(ctx, x, z0, a, b_hat):
+        x = x.to(torch.float32).contiguous()
+        N, K = x.shape
+        zv, av, bv = (t.detach().to(torch.float32).contiguous().view(-1) for t in (z0, a, b_hat))
+        z = torch.empty_like(x)
+        _lib.call('cnf_radial_forward', _ptr(x), _ptr(zv), _ptr(av), _ptr(bv), _ptr(z), ctypes.c_int64(N),
+                  ctypes.c_int32(K), _stream(x.device))
+        ctx.save_for_backward(x, zv, av, bv)
+        ctx.shapes = (z0.shape, a.shape, b_hat.shape)
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        x, zv, av, bv = ctx.saved_tensors
+        N, K = x.shape
+        g_z = g_z.to(torch.float32).contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gz0 = torch.empty(K, dtype=torch.float32, device=x.device)
+        ga = torch.empty(1, dtype=torch.float32, device=x.device)
+        gb = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.call('cnf_radial_backward', _ptr(x), _ptr(g_z), _ptr(zv), _ptr(av), _ptr(bv), _ptr(gx), _ptr(gz0),
+                  _ptr(ga), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        zs, as_, bs = ctx.shapes
+        return gx, gz0.view(zs), ga.view(as_), gb.view(bs)
+
+
+class RadialLayer(nn.Module):
+    """Drop-in for reference ``flows/flows.py:167-193``.  As in the reference the returned log-det
+    is the constant ``log(tensor(1.0))`` (a 0-d CPU tensor there; :188-190), not the true one."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.z0 = nn.Parameter(torch.rand(dim))
+        self.a = nn.Parameter(torch.rand(1))
+        self.b = nn.Parameter(torch.rand(1))
+        self.invertible = False
+
+    def forward(self, x):
+        require_cuda(x)
+        b_hat = -self.a + torch.log1p(torch.exp(self.b))
+        z = _RadialFn.apply(x, self.z0, self.a, b_hat)
+        log_det = torch.log(torch.tensor(1.0))
+        return z, log_det
+
+
 class NvpCouplingLayer(nn.Module):
     def __init__(self, dim, hidden_size=[5, 5], scale=True, shift=True, random_flip=False):
         super().__init__()

@@ -190,6 +190,26 @@ int cnf_affine_const(const float* x, const float* s, const float* t, float* z, i
 int cnf_affine_const_backward(const float* x, const float* g_z, const float* s, float* g_x, float* g_s,
                               float* g_t, int64_t N, int32_t K, void* stream);
 
+/* ---- device: PlanarLayer / RadialLayer (next-row 8f/4 tail) ----------------------------------------
+ * PlanarLayer.forward (flows/flows.py:148-164): h = tanh(x.w + b), z = x + h*u_hat,
+ * logdet = log|1 + (1-h^2)(w.u_hat)|.  w, u_hat DEVICE float32 [K], b DEVICE float32 [1]; u_hat (the
+ * invertibility-constrained u, :150-153) is formed by the caller.  K <= 512 and 32 rows x 4 warps must
+ * fit shared memory (CNF_E_SMEM otherwise).                                                          */
+int cnf_planar_forward(const float* x, const float* w, const float* u_hat, const float* b, float* z,
+                       float* logdet, int64_t N, int32_t K, void* stream);
+/* Gradients for upstream g_z [N,K], g_logdet [N] (may be NULL = zeros): g_x [N,K] (may be NULL),
+ * g_w [K], g_uhat [K], g_b [1] (overwritten).                                                       */
+int cnf_planar_backward(const float* x, const float* g_z, const float* g_logdet, const float* w,
+                        const float* u_hat, const float* b, float* g_x, float* g_w, float* g_uhat,
+                        float* g_b, int64_t N, int32_t K, void* stream);
+/* RadialLayer.forward (flows/flows.py:180-193): z = x + b_hat*(x-z0)/(a + |x-z0|); its log-det is the
+ * constant log(1.0) in the reference and is produced by the caller.  z0 [K], a [1], b_hat [1] DEVICE. */
+int cnf_radial_forward(const float* x, const float* z0, const float* a, const float* b_hat, float* z,
+                       int64_t N, int32_t K, void* stream);
+int cnf_radial_backward(const float* x, const float* g_z, const float* z0, const float* a,
+                        const float* b_hat, float* g_x, float* g_z0, float* g_a, float* g_bhat,
+                        int64_t N, int32_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

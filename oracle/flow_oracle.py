@@ -368,6 +368,47 @@ def expected_calibration_error(probs, target, bins=15):
 
 
 # --------------------------------------------------------------------------- #
+# PlanarLayer / RadialLayer (flows/flows.py:129-193), forward direction
+# --------------------------------------------------------------------------- #
+def planar_forward(w, u, b, x):
+    """flows/flows.py:148-164.  Returns (z, log_det, u_hat)."""
+    w, u, x = np.asarray(w), np.asarray(u), np.asarray(x)
+    b = np.asarray(b).reshape(-1)[0]
+    wtu = w @ u
+    m = -1 + np.log1p(np.exp(wtu))
+    u_hat = u + (m - wtu) * w / np.linalg.norm(w)
+    h = np.tanh(x @ w + b)
+    z = x + h[:, None] * u_hat[None, :]
+    hp = 1 - h ** 2
+    log_det = np.log(np.abs(1 + hp * (w @ u_hat)))
+    return z, log_det, u_hat
+
+
+def planar_backward(w, u_hat, b, x, g_z, g_ld):
+    """Gradients w.r.t. (x, w, u_hat, b) treating u_hat as an input (the caller chains u_hat -> (w, u))."""
+    w, u_hat, x, g_z, g_ld = (np.asarray(v, dtype=np.float64) for v in (w, u_hat, x, g_z, g_ld))
+    b = float(np.asarray(b).reshape(-1)[0])
+    h = np.tanh(x @ w + b)
+    hp = 1 - h ** 2
+    wu = w @ u_hat
+    D = 1 + hp * wu
+    g_a = (g_z @ u_hat) * hp - 2 * h * hp * (g_ld * wu / D)
+    c = (g_ld * hp / D).sum()
+    return g_z + g_a[:, None] * w[None, :], x.T @ g_a + c * u_hat, g_z.T @ h + c * w, g_a.sum()
+
+
+def radial_forward(z0, a, b, x):
+    """flows/flows.py:180-193.  Returns (z, log_det) with the reference's constant log_det = log(1.0)."""
+    z0, x = np.asarray(z0), np.asarray(x)
+    a = np.asarray(a).reshape(-1)[0]
+    b = np.asarray(b).reshape(-1)[0]
+    b_hat = -a + np.log1p(np.exp(b))
+    d = x - z0
+    h = 1.0 / (a + np.linalg.norm(d, axis=1, keepdims=True))
+    return x + b_hat * h * d, np.log(1.0)
+
+
+# --------------------------------------------------------------------------- #
 # index-map restatement (SURVEY.md Appendix A "folding flips/perms"); used to
 # check the C++ planner in csrc/cnf_plan.cpp
 # --------------------------------------------------------------------------- #

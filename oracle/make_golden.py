@@ -286,10 +286,58 @@ def gen_affine_case():
     print('affine case loss', float(loss.detach()))
 
 
+def gen_planar_radial_case():
+    """PlanarLayer / RadialLayer (flows/flows.py:129-193): forward outputs and autograd gradients of a
+    seeded linear functional of (z, log_det), and both inside a Flow with a coupling layer."""
+    from flows.flows import PlanarLayer, RadialLayer
+    out = {}
+    for K in (3, 10, 40):
+        torch.manual_seed(100 + K)
+        N = 77
+        x, _ = orc.synth_logits(N, K, seed=20 + K)
+        cz = torch.randn(N, K)
+        cl = torch.randn(N)
+        pl = PlanarLayer(K)
+        xt = torch.as_tensor(x).requires_grad_(True)
+        z, ld = pl(xt)
+        ((z * cz).sum() + (ld * cl).sum()).backward()
+        tag = 'planar_k%d_' % K
+        out.update({tag + 'x': x, tag + 'cz': cz.numpy(), tag + 'cl': cl.numpy(), tag + 'w': pl.w.detach().numpy(),
+                    tag + 'u': pl.u.detach().numpy(), tag + 'b': pl.b.detach().numpy(), tag + 'z': z.detach().numpy(),
+                    tag + 'ld': ld.detach().numpy(), tag + 'gx': xt.grad.numpy(), tag + 'gw': pl.w.grad.numpy(),
+                    tag + 'gu': pl.u.grad.numpy(), tag + 'gb': pl.b.grad.numpy()})
+        rl = RadialLayer(K)
+        xt = torch.as_tensor(x).requires_grad_(True)
+        z, ld = rl(xt)
+        (z * cz).sum().backward()
+        tag = 'radial_k%d_' % K
+        out.update({tag + 'x': x, tag + 'cz': cz.numpy(), tag + 'z0': rl.z0.detach().numpy(),
+                    tag + 'a': rl.a.detach().numpy(), tag + 'b': rl.b.detach().numpy(), tag + 'z': z.detach().numpy(),
+                    tag + 'ld': ld.detach().numpy(), tag + 'gx': xt.grad.numpy(), tag + 'gz0': rl.z0.grad.numpy(),
+                    tag + 'ga': rl.a.grad.numpy(), tag + 'gb': rl.b.grad.numpy()})
+    # both inside a Flow, as the notebooks stack arbitrary layers
+    torch.manual_seed(7)
+    K, N = 6, 33
+    pl, rl, cp = PlanarLayer(K), RadialLayer(K), NvpCouplingLayer(K, hidden_size=[8])
+    with torch.no_grad():
+        for p in cp.parameters():
+            if p.requires_grad:
+                p.mul_(300.0)
+    flow = Flow([pl, cp, rl])
+    x, _ = orc.synth_logits(N, K, seed=3)
+    with torch.no_grad():
+        zs, ld = flow(torch.as_tensor(x))
+    sd = {k: v.detach().numpy() for k, v in flow.state_dict().items()}
+    out.update({'flow_x': x, 'flow_z': zs[-1].numpy(), 'flow_ld': ld.numpy(), 'flow_K': K})
+    out.update({'flow_sd_' + k: v for k, v in sd.items()})
+    np.savez_compressed(os.path.join(OUT, 'planar_radial.npz'), **out)
+    print('planar/radial cases written')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # bit-stable reductions
-    gen_flow_cases()
-    gen_calibrator_case()
-    gen_metrics_cases()
-    gen_affine_case()
+    cases = {'flow': gen_flow_cases, 'calibrator': gen_calibrator_case, 'metrics': gen_metrics_cases,
+             'affine': gen_affine_case, 'planar_radial': gen_planar_radial_case}
+    for name in (sys.argv[1:] or list(cases)):
+        cases[name]()

@@ -364,3 +364,76 @@ def test_affine_constant_layer_and_tempscaler_vs_reference(cuda_device):
     assert rel_err(ts.T.grad.cpu().numpy(), g['temp_gT']) < 1e-4
     with torch.no_grad():
         assert rel_err(ts.backward(zt.detach()).cpu().numpy(), g['x']) < 1e-6
+
+
+@pytest.mark.parametrize('K', [3, 10, 40])
+def test_planar_and_radial_layers_vs_reference(K, cuda_device):
+    """PlanarLayer / RadialLayer drop-ins (flows/flows.py:129-193): outputs and autograd gradients against
+    the reference's own run (tests/golden/planar_radial.npz); fp32 tolerance 1e-5 / 2e-4 on gradients."""
+    import torch
+    import cnf_b200
+    g = load_golden('planar_radial')
+    t = 'planar_k%d_' % K
+    lay = cnf_b200.PlanarLayer(K).to(cuda_device)
+    with torch.no_grad():
+        lay.w.copy_(torch.from_numpy(g[t + 'w'])); lay.u.copy_(torch.from_numpy(g[t + 'u'])); lay.b.copy_(torch.from_numpy(g[t + 'b']))
+    x = torch.from_numpy(g[t + 'x']).to(cuda_device).requires_grad_(True)
+    z, ld = lay(x)
+    assert lay.invertible is False and ld.shape == (x.shape[0],)
+    ((z * torch.from_numpy(g[t + 'cz']).to(cuda_device)).sum() + (ld * torch.from_numpy(g[t + 'cl']).to(cuda_device)).sum()).backward()
+    assert rel_err(z.detach().cpu().numpy(), g[t + 'z']) < TOL
+    assert np.max(np.abs(ld.detach().cpu().numpy() - g[t + 'ld'])) < TOL * max(1.0, np.max(np.abs(g[t + 'ld'])))
+    assert rel_err(x.grad.cpu().numpy(), g[t + 'gx']) < 2e-4
+    assert rel_err(lay.w.grad.cpu().numpy(), g[t + 'gw']) < 2e-4
+    assert rel_err(lay.u.grad.cpu().numpy(), g[t + 'gu']) < 2e-4
+    assert rel_err(lay.b.grad.cpu().numpy(), g[t + 'gb']) < 2e-4
+    t = 'radial_k%d_' % K
+    lay = cnf_b200.RadialLayer(K).to(cuda_device)
+    with torch.no_grad():
+        lay.z0.copy_(torch.from_numpy(g[t + 'z0'])); lay.a.copy_(torch.from_numpy(g[t + 'a'])); lay.b.copy_(torch.from_numpy(g[t + 'b']))
+    x = torch.from_numpy(g[t + 'x']).to(cuda_device).requires_grad_(True)
+    z, ld = lay(x)
+    assert ld.dim() == 0 and float(ld) == 0.0                # the reference's constant log(1.0)
+    (z * torch.from_numpy(g[t + 'cz']).to(cuda_device)).sum().backward()
+    assert rel_err(z.detach().cpu().numpy(), g[t + 'z']) < TOL
+    assert rel_err(x.grad.cpu().numpy(), g[t + 'gx']) < 2e-4
+    assert rel_err(lay.z0.grad.cpu().numpy(), g[t + 'gz0']) < 2e-4
+    assert rel_err(lay.a.grad.cpu().numpy(), g[t + 'ga']) < 2e-4
+    assert rel_err(lay.b.grad.cpu().numpy(), g[t + 'gb']) < 2e-4
+
+
+def test_planar_radial_inside_a_flow_and_ragged_sizes(cuda_device):
+    """Planar -> coupling -> radial in one Flow (state_dict keys as the reference's), Flow.backward raises,
+    and the streaming kernels agree with the oracle on ragged / multi-tile batch sizes."""
+    import torch
+    import cnf_b200
+    g = load_golden('planar_radial')
+    K = int(g['flow_K'])
+    flow = cnf_b200.Flow([cnf_b200.PlanarLayer(K), cnf_b200.NvpCouplingLayer(K, hidden_size=[8]), cnf_b200.RadialLayer(K)])
+    sd = {k[len('flow_sd_'):]: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith('flow_sd_')}
+    assert set(flow.state_dict().keys()) == set(sd.keys())
+    flow.load_state_dict(sd)
+    flow.to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(torch.from_numpy(g['flow_x']).to(cuda_device))
+    assert rel_err(zs[-1].cpu().numpy(), g['flow_z']) < TOL
+    assert np.max(np.abs(ld.cpu().numpy() - g['flow_ld'])) < TOL * max(1.0, np.max(np.abs(g['flow_ld'])))
+    with pytest.raises(ValueError, match='not tractable'):
+        flow.backward(zs[-1])
+    rng = np.random.default_rng(5)
+    for N, K in ((1, 5), (31, 10), (33, 10), (4097, 100), (100003, 10)):
+        x, _ = orc.synth_logits(N, K, seed=N)
+        w, u, b = rng.random(K).astype(np.float32), rng.random(K).astype(np.float32), rng.random(1).astype(np.float32)
+        pl = cnf_b200.PlanarLayer(K).to(cuda_device)
+        with torch.no_grad():
+            pl.w.copy_(torch.from_numpy(w)); pl.u.copy_(torch.from_numpy(u)); pl.b.copy_(torch.from_numpy(b))
+            z, l2 = pl(torch.from_numpy(x).to(cuda_device))
+        zo, lo, _ = orc.planar_forward(w.astype(np.float64), u.astype(np.float64), b, x.astype(np.float64))
+        assert rel_err(z.cpu().numpy(), zo) < TOL
+        assert np.max(np.abs(l2.cpu().numpy().reshape(-1) - lo)) < TOL * max(1.0, np.max(np.abs(lo)))
+        rl = cnf_b200.RadialLayer(K).to(cuda_device)
+        with torch.no_grad():
+            z, _ = rl(torch.from_numpy(x).to(cuda_device))
+        zo, _ = orc.radial_forward(rl.z0.detach().cpu().numpy().astype(np.float64), rl.a.detach().cpu().numpy(),
+                                   rl.b.detach().cpu().numpy(), x.astype(np.float64))
+        assert rel_err(z.cpu().numpy(), zo) < TOL

@@ -205,3 +205,36 @@ def test_tc_training_follows_the_fp32_loss_trajectory(cuda_device):
     assert np.isfinite(curves['bf16']).all()
     assert curves['bf16'][-1] < curves['bf16'][0] - 0.05
     assert np.max(np.abs(curves['bf16'] - curves['fp32'])) < 2e-3
+
+
+@pytest.mark.parametrize('name', ['cal_nice_k3', 'cal_nvp_k10'])
+def test_calibrator_fit_on_the_tensor_core_path_vs_reference(name, cuda_device):
+    """TorchFlowCalibrator(..., precision='bf16'): fit (tcgen05 forward+backward, fused Adam) then predict,
+    against the reference's own fit on the same data and initial weights (stated bf16 tolerance)."""
+    import torch
+    import cnf_b200
+    g = load_golden('calibrator_' + name)
+    hidden = [int(h) for h in g['hidden']]
+
+    class Factory(cnf_b200.CouplingStack):
+        def __init__(self, dim, **kw):
+            super().__init__(dim, layers=int(g['layers']), hidden_size=hidden, scale=bool(g['scale']),
+                             precision='bf16', **{k: v for k, v in kw.items()
+                                                  if k not in ('layers', 'hidden_size', 'scale', 'precision')})
+            flat = torch.from_numpy(g['flat0'].astype(np.float32))
+            off = 0
+            with torch.no_grad():
+                for lay in self.layers:
+                    for p in lay.canonical_parameters():
+                        p.copy_(flat[off:off + p.numel()].view(p.shape))
+                        off += p.numel()
+
+    cal = cnf_b200.TorchFlowCalibrator(Factory, g['x'], g['y'], epochs=int(g['epochs']), dev=cuda_device,
+                                       precision='bf16')
+    assert cal.trainer.precision == 'bf16'
+    hist = {k: np.array([float(v) for v in cal.history[k]]) for k in ('loss', 'ce', 'log_det')}
+    assert np.isfinite(hist['loss']).all()
+    assert np.allclose(hist['loss'], g['hist_loss'], rtol=1e-2, atol=1e-2)
+    assert np.allclose(hist['log_det'], g['hist_log_det'], rtol=1e-2, atol=1e-2)
+    pred = cal.predict(g['x_test'])
+    assert np.max(np.abs(pred - g['pred'])) < ATOL_P

@@ -5,6 +5,7 @@ import pytest
 
 import flow_oracle as orc
 from conftest import golden_flow_names, load_golden, oracle_params_from_golden
+from helpers import rel_err
 
 
 def rel(a, b):
@@ -197,3 +198,22 @@ def test_c_oracle_metrics_match_reference():
         assert abs(ece - g[n + '_ece15']) < 1e-6   # reference averages float32 hit flags
         assert abs(st[45] / st[47] - g[n + '_nll']) < 1e-9
         assert st[46] / st[47] == g[n + '_acc']
+
+
+def test_planar_and_radial_oracle_vs_reference_golden():
+    """oracle planar_forward / planar_backward / radial_forward against the reference's PlanarLayer /
+    RadialLayer outputs and autograd gradients (tests/golden/planar_radial.npz)."""
+    g = load_golden('planar_radial')
+    for K in (3, 10, 40):
+        t = 'planar_k%d_' % K
+        x = g[t + 'x'].astype(np.float64)
+        z, ld, u_hat = orc.planar_forward(g[t + 'w'].astype(np.float64), g[t + 'u'].astype(np.float64), g[t + 'b'], x)
+        assert rel_err(z, g[t + 'z']) < 1e-5
+        assert np.max(np.abs(ld - g[t + 'ld'])) < 1e-5 * max(1.0, np.max(np.abs(g[t + 'ld'])))
+        gx, gw_direct, gu_hat, gb = orc.planar_backward(g[t + 'w'], u_hat, g[t + 'b'], x, g[t + 'cz'], g[t + 'cl'])
+        assert rel_err(gx, g[t + 'gx']) < 1e-4
+        assert abs(gb - float(g[t + 'gb'][0])) < 1e-4 * max(1.0, abs(float(g[t + 'gb'][0])))
+        t = 'radial_k%d_' % K
+        z, ld = orc.radial_forward(g[t + 'z0'].astype(np.float64), g[t + 'a'], g[t + 'b'], g[t + 'x'].astype(np.float64))
+        assert rel_err(z, g[t + 'z']) < 1e-5
+        assert ld == 0.0 and float(g[t + 'ld']) == 0.0
