@@ -98,7 +98,10 @@ __device__ __forceinline__ uint32_t pack_hidden(uint32_t lo, uint32_t hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int EPI, bool TAPE>
+// SH: 1 = the shape constants of BASELINE configs C2/C3/C5 (K = 10: d0 = d1 = 5, 128 hidden units, both nets)
+// are compile-time, which removes the guards and index arithmetic of the generic loops (about a quarter
+// of the epilogue's instructions); 0 = every shape the kernel covers, read from TcDims.
+template <int EPI, bool TAPE, int SH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
@@ -148,8 +151,9 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
 
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int G = gridDim.x;
-  const int Hp = p.Hp;                 // hidden units (TMEM columns of D1) per net phase
-  const int n_ph = p.n_nets;           // net phases per layer: s then t (or the single present net)
+  const int Hp = SH ? 128 : p.Hp;      // hidden units (TMEM columns of D1) per net phase
+  const int D0 = SH ? 5 : p.d0, D1 = SH ? 5 : p.d1, KK = SH ? 10 : p.K;
+  const int n_ph = SH ? 2 : p.n_nets;           // net phases per layer: s then t (or the single present net)
   const int n_grp = (Hp + 63) / 64;    // EPI1 releases the hidden units to GEMM2 in groups of 64 columns
   const int d2_col = 128;              // D2 sits above D1 inside the slot
 
@@ -203,8 +207,8 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
     const int* pi_last = tab + p.tab_pi + p.L * p.K;
     uint32_t it = 0, cnt = 0;
     uint8_t* a1_row = a1 + (t >> 3) * SBO1 + (t & 7) * 16;
-    const bool both = (p.nets == 3);
-    const int K = p.K, tile_elems = TILE_M * p.K;
+    const bool both = SH ? true : (p.nets == 3);
+    const int K = KK, tile_elems = TILE_M * KK;
     // truncation shrinks every hidden unit by ~0.72*2^-9 on average; undo it on the fp32 output
     const float comp = (EPI == 1) ? 1.0f + 0.72f / 512.0f : 1.0f;
     const uint32_t one_bits = 0x3f80u;   // bf16 1.0
@@ -253,27 +257,27 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
       float ld = 0.f;
       for (int li = 0; li < p.L; ++li, ++it) {
         const int l = inverse ? p.L - 1 - li : li;
-        const int* cond = tab + p.tab_cond + l * p.d1;
-        const int* trans = tab + p.tab_trans + l * p.d0;
+        const int* cond = tab + p.tab_cond + l * D1;
+        const int* trans = tab + p.tab_trans + l * D0;
         // ---- A1 row: conditioning logits as bf16 + the constant one (independent loads) -------
         {
           float u[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : 0.f;
+          for (int k = 0; k < 8; ++k) u[k] = (k < D1) ? act[cond[k] * TILE_M + t] : 0.f;
           uint4 lo;
           lo.x = pack_bf16(u[0], u[1]); lo.y = pack_bf16(u[2], u[3]);
           lo.z = pack_bf16(u[4], u[5]); lo.w = pack_bf16(u[6], u[7]);
-          if (p.d1 < 8) {
-            const uint32_t ob = one_bits << ((p.d1 & 1) * 16);
-            const int wi = p.d1 >> 1;
+          if (D1 < 8) {
+            const uint32_t ob = one_bits << ((D1 & 1) * 16);
+            const int wi = D1 >> 1;
             lo.x |= (wi == 0) ? ob : 0u; lo.y |= (wi == 1) ? ob : 0u;
             lo.z |= (wi == 2) ? ob : 0u; lo.w |= (wi == 3) ? ob : 0u;
           }
           *reinterpret_cast<uint4*>(a1_row) = lo;
-          if (p.d1 >= 8) {      // K >= 15: second k-half carries u_8.. and the one
+          if (D1 >= 8) {      // K >= 15: second k-half carries u_8.. and the one
             float v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = (k + 8 < p.d1) ? act[cond[k + 8] * TILE_M + t] : (k + 8 == p.d1 ? 1.f : 0.f);
+            for (int k = 0; k < 8; ++k) v[k] = (k + 8 < D1) ? act[cond[k + 8] * TILE_M + t] : (k + 8 == D1 ? 1.f : 0.f);
             uint4 hi;
             hi.x = pack_bf16(v[0], v[1]); hi.y = pack_bf16(v[2], v[3]);
             hi.z = pack_bf16(v[4], v[5]); hi.w = pack_bf16(v[6], v[7]);
@@ -288,7 +292,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         int ps[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          ps[q] = (q < p.d0) ? trans[q] * TILE_M + t : t;
+          ps[q] = (q < D0) ? trans[q] * TILE_M + t : t;
           xv[q] = act[ps[q]];
         }
         const float* bl = bias + l * 16;
@@ -326,11 +330,11 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
           tmem_wait_ld16(r);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            if (q < p.d0) {
+            if (q < D0) {
               // columns 0..7 belong to the first present net, 8..15 to the second
               const float first = fmaf(__uint_as_float(r[q]), comp, bl[q]);
               const float second = fmaf(__uint_as_float(r[8 + q]), comp, bl[8 + q]);
-              const float sv = (p.nets & 1) ? first : 0.f;
+              const float sv = (SH || (p.nets & 1)) ? first : 0.f;
               const float tv = both ? second : ((p.nets & 2) ? first : 0.f);
               float yv;
               if (!inverse) { yv = xv[q] * expf(sv) + tv; ld += sv; }
@@ -503,14 +507,20 @@ int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const in
   const int io16 = (((uintptr_t)x | (uintptr_t)z) % 16 == 0 && (TILE_M * d.K) % 4 == 0) ? 1 : 0;
   int epi = 0;
   if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
+  const int sh = (d.K == 10 && t.Hp == 128 && d.nets == 3 && !getenv("CNF_TC_GENERIC")) ? 1 : 0;
+#define LAUNCH_TC_S(E, T, S)                                                                                    \
+  do {                                                                                                          \
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
+    flow_tc_kernel<E, T, S><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, \
+                                                                  inverse, io16, tape);                         \
+  } while (0)
 #define LAUNCH_TC(E, T)                                                                                         \
   do {                                                                                                          \
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
-    flow_tc_kernel<E, T><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N,   \
-                                                               inverse, io16, tape);                            \
+    if (sh) LAUNCH_TC_S(E, T, 1); else LAUNCH_TC_S(E, T, 0);                                                    \
   } while (0)
   if (tape) { if (epi == 0) LAUNCH_TC(0, true); else LAUNCH_TC(1, true); }
   else      { if (epi == 0) LAUNCH_TC(0, false); else LAUNCH_TC(1, false); }
+#undef LAUNCH_TC_S
 #undef LAUNCH_TC
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
