@@ -171,23 +171,32 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
       uint32_t cnt = 0;                // net phases issued so far on this slot
       for (int64_t it = 0; it < total; ++it) {
         const int l = inverse ? p.L - 1 - li : li;
-        const uint32_t b1 = smem_base + p.b1_off + l * p.b_layer_bytes;
-        const uint32_t b2 = smem_base + p.b2_off + l * p.b_layer_bytes;
+        // descriptors of this layer's B1 / B2 images; the start-address field (16-byte units) is the only
+        // part that changes between nets and k-steps, so they are advanced by plain adds
+        const uint64_t db1 = make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, LBO1, SBO1);
+        const uint64_t db2 = make_desc(smem_base + p.b2_off + l * p.b_layer_bytes, LBO2, SBO2);
         mbar_wait(a1_ready + s, (uint32_t)(it & 1));
         tc_fence_after();
-        for (int ph = 0; ph < n_ph; ++ph, ++cnt) {
+#pragma unroll
+        for (int ph = 0; ph < (SH ? 2 : 2); ++ph) {
+          if (ph >= n_ph) break;
           // GEMM1 of this net: D1[128 x Hp] = A1 . B1[ph]^T   (rows ph*Hp.. of the B1 image)
-          mma_ss(tm, ad, make_desc(b1 + ph * (Hp / 8) * SBO1, LBO1, SBO1), idesc1, 0u);
+          mma_ss(tm, ad, db1 + (uint64_t)(ph * (Hp / 8) * (SBO1 / 16)), idesc1, 0u);
           tc_commit(d1_ready + s);
-          int j = 0;
-          for (int g = 0; g < n_grp; ++g) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g >= n_grp) break;
             mbar_wait(a2_ready + 2 * s + g, cnt & 1);
             tc_fence_after();
-            const int j1 = min(4 * g + 4, Hp / 16);
-            for (; j < j1; ++j)     // GEMM2 k-steps of this net accumulate into the shared 16-column D2
-              mma_ts(tm + d2_col, tm + j * 8, make_desc(b2 + (ph * (Hp / 16) + j) * 512, LBO2, SBO2), idesc2,
-                     (ph > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {     // GEMM2 k-steps of this net accumulate into the shared 16-column D2
+              const int j = 4 * g + jj;
+              if (j < Hp / 16)
+                mma_ts(tm + d2_col, tm + j * 8, db2 + (uint64_t)((ph * (Hp / 16) + j) * 32), idesc2,
+                       (ph > 0 || j > 0) ? 1u : 0u);
+            }
           }
+          ++cnt;
         }
         tc_commit(d2_ready + s);
         if (++li == p.L) li = 0;

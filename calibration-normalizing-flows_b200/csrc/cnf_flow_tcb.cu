@@ -40,6 +40,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cnf_common.h"
 #include "cnf_tc_dims.h"
 #include "cnf_tc_ptx.cuh"
@@ -112,6 +114,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 __device__ __forceinline__ void epi_sync_all() { asm volatile("bar.sync 3, %0;" ::"n"(128 * TB_SLOTS) : "memory"); }
 
+// SH = 1: compile-time shape of BASELINE configs C2/C3/C5 (K = 10, d0 = d1 = 5, 128 hidden units, both
+// nets); SH = 0: every covered shape, read from TbDims.
+template <int SH>
 __global__ void __launch_bounds__(TB_THREADS, 1)
 flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                 const float* __restrict__ zin, const float* __restrict__ logdet, const float* __restrict__ tape,
@@ -164,7 +169,8 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int Hp = p.Hp, n_ph = p.n_nets;
+  const int Hp = SH ? 128 : p.Hp, n_ph = SH ? 2 : p.n_nets;
+  const int D0 = SH ? 5 : p.d0, D1 = SH ? 5 : p.d1;
   if (warp < 4 && do_bwd) {                      // the weight-gradient accumulators start at zero
     uint32_t zero[16];
 #pragma unroll
@@ -274,10 +280,10 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
     float* gact = reinterpret_cast<float*>(slot_base + p.sm_gact);
     const uint32_t img_row = (uint32_t)(t >> 3) * img_sr + (t & 7) * 16;   // 16-byte slot in core matrix 0
     const uint32_t h_row = smem_u32(slot_base + p.sm_h) + img_row, ghm_row = smem_u32(slot_base + p.sm_ghm) + img_row;
-    const int* pi_last = tab + p.tab_pi + p.L * p.K;
-    const int K = p.K;
+    const int* pi_last = tab + p.tab_pi + p.L * (SH ? 10 : p.K);
+    const int K = SH ? 10 : p.K;
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
-    const bool has_s = (p.nets & 1) != 0, has_t = (p.nets & 2) != 0;
+    const bool has_s = SH ? true : (p.nets & 1) != 0, has_t = SH ? true : (p.nets & 2) != 0;
     const uint32_t one_bits = 0x3f80u;
     double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
     uint32_t hc = 0, pc = 0;
@@ -362,8 +368,8 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       if (do_bwd) {
         for (int li = 0; li < p.L; ++li) {
           const int l = p.L - 1 - li;
-          const int* cond = tab + p.tab_cond + l * p.d1;
-          const int* trans = tab + p.tab_trans + l * p.d0;
+          const int* cond = tab + p.tab_cond + l * D1;
+          const int* trans = tab + p.tab_trans + l * D0;
           // ---- E0 -------------------------------------------------------------------------------
           {
             const float xt[8] = {tq[0].x, tq[0].y, tq[0].z, tq[0].w, tq[1].x, tq[1].y, tq[1].z, tq[1].w};
@@ -372,7 +378,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               gv[q] = 0.f; gv[8 + q] = 0.f;
-              if (q < p.d0) {
+              if (q < D0) {
                 const int ps = trans[q] * TILE_M + t;
                 const float gy = gact[ps];
                 const float es = has_s ? expf(sv[q]) : 1.f;
@@ -393,12 +399,12 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             *reinterpret_cast<uint4*>(rec_row + OFF_G2 + 128) = v;
             float u[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) u[k] = (k < p.d1) ? act[cond[k] * TILE_M + t] : 0.f;
+            for (int k = 0; k < 8; ++k) u[k] = (k < D1) ? act[cond[k] * TILE_M + t] : 0.f;
             v.x = pack_bf16(u[0], u[1]); v.y = pack_bf16(u[2], u[3]);
             v.z = pack_bf16(u[4], u[5]); v.w = pack_bf16(u[6], u[7]);
             {
-              const uint32_t ob = one_bits << ((p.d1 & 1) * 16);
-              const int wi = p.d1 >> 1;
+              const uint32_t ob = one_bits << ((D1 & 1) * 16);
+              const int wi = D1 >> 1;
               v.x |= (wi == 0) ? ob : 0u; v.y |= (wi == 1) ? ob : 0u;
               v.z |= (wi == 2) ? ob : 0u; v.w |= (wi == 3) ? ob : 0u;
             }
@@ -497,7 +503,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             tmem_wait_ld16(r);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (k < p.d1) gact[cond[k] * TILE_M + t] += __uint_as_float(r[k]);
+              if (k < D1) gact[cond[k] * TILE_M + t] += __uint_as_float(r[k]);
           }
           tc_fence_before();
         }
@@ -660,16 +666,23 @@ extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* pack
   float* zbuf = reinterpret_cast<float*>(workspace);
   float* ldbuf = zbuf + chunk * d.K;
   float* tapebuf = ldbuf + chunk;
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+  const bool sh = d.K == 10 && t.Hp == 128 && d.nets == 3 && !getenv("CNF_TC_GENERIC");
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
   for (int64_t lo = 0; lo < N; lo += chunk) {
     const int64_t n = (N - lo < chunk) ? N - lo : chunk;
     rc = cnf_tc_apply_tape(desc, packed_tc, tables, x + lo * d.K, zbuf, ldbuf, grad_partials_tc ? tapebuf : nullptr, n, 0, st);
     if (rc) return rc;
     const int64_t ntiles = (n + TILE_M - 1) / TILE_M;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    flow_tcb_kernel<<<grid, TB_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, zbuf, ldbuf, tapebuf,
-                                                         y + lo, grad_partials_tc, loss_acc, n, eps, gamma, inv_n_total,
-                                                         grad_partials_tc ? 1 : 0);
+    if (sh)
+      flow_tcb_kernel<1><<<grid, TB_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, zbuf, ldbuf, tapebuf,
+                                                              y + lo, grad_partials_tc, loss_acc, n, eps, gamma,
+                                                              inv_n_total, grad_partials_tc ? 1 : 0);
+    else
+      flow_tcb_kernel<0><<<grid, TB_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, zbuf, ldbuf, tapebuf,
+                                                              y + lo, grad_partials_tc, loss_acc, n, eps, gamma,
+                                                              inv_n_total, grad_partials_tc ? 1 : 0);
     CNF_CHECK_CUDA(cudaGetLastError());
   }
   return CNF_OK;
