@@ -175,7 +175,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         // part that changes between nets and k-steps, so they are advanced by plain adds
         const uint64_t db1 = make_desc(smem_base + p.b1_off + l * p.b_layer_bytes, LBO1, SBO1);
         const uint64_t db2 = make_desc(smem_base + p.b2_off + l * p.b_layer_bytes, LBO2, SBO2);
-        mbar_wait(a1_ready + s, (uint32_t)(it & 1));
+        mbar_wait_backoff(a1_ready + s, (uint32_t)(it & 1));
         tc_fence_after();
 #pragma unroll
         for (int ph = 0; ph < (SH ? 2 : 2); ++ph) {
@@ -186,7 +186,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (g >= n_grp) break;
-            mbar_wait(a2_ready + 2 * s + g, cnt & 1);
+            mbar_wait_backoff(a2_ready + 2 * s + g, cnt & 1);
             tc_fence_after();
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {     // GEMM2 k-steps of this net accumulate into the shared 16-column D2
