@@ -17,6 +17,8 @@
 //                     (eps=0: CrossEntropyLoss)                         run_experiment3D.py:107
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cnf_common.h"
 
 namespace {
@@ -636,8 +638,12 @@ int device_limits() {
 int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out) {
   const int budget = g_max_smem - (backward ? 1024 : 256);
   const int spts[2] = {2, 1};
+  // 256-thread CTAs share one staged copy of the weights between twice as many warps: 16 instead of 8
+  // resident warps per SM at the C2 shape, 1.83 -> 1.34 ms per 2^20 samples on B200
+  int nt_max = 256;
+  if (const char* v = getenv("CNF_FP32_NT")) { const int n = atoi(v); if (n == 256 || n == 128) nt_max = n; }
   for (int ws = 1; ws >= 0; --ws)
-    for (int nt = 128; nt >= 32; nt >>= 1)
+    for (int nt = nt_max; nt >= 32; nt >>= 1)
       for (int si = 0; si < 2; ++si) {
         const int spt = spts[si];
         if (nt < 128 && spt > 1) continue;
