@@ -23,8 +23,9 @@ int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n,
 
 namespace {
 
-constexpr int W_THREADS = 384;   // warp 0 MMA issuer, 1 weight producer, 2 TMEM allocator, 4-7 / 8-11 epilogue
+constexpr int W_THREADS = 384;   // warps 0 / 3 MMA issuers (slot 0 / 1), 1 weight producer, 2 TMEM allocator, 4-7 / 8-11 epilogue
 constexpr int HB = 128;          // hidden units per phase
+constexpr int ACT_LD = TILE_M + 1;   // act[slot][sample] row stride: odd, so the transposing tile load / store is bank-conflict free
 constexpr int W_LBO1 = 2048, W_SBO1 = 128;   // A1 / B1 block: [k-block][row-block] 128-byte core matrices
 constexpr int W_SBO2 = 128;                  // B2 block per k-step: [k-half][row-block]
 
@@ -59,7 +60,7 @@ bool tcw_dims(const CnfDims& d, TcwDims* t) {
   t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
   t->sm_slot = off;
   t->sm_act = HB * t->K1 * 2;                       // A1 tile first, then the fp32 tile
-  t->sm_slot_stride = t->sm_act + (d.K * TILE_M * 4 + 127) / 128 * 128;
+  t->sm_slot_stride = t->sm_act + (d.K * ACT_LD * 4 + 127) / 128 * 128;
   off += 2 * t->sm_slot_stride;
   t->sm_bar = off; off += 128;
   t->sm_total = off;
@@ -76,7 +77,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
   float* bias = reinterpret_cast<float*>(smem + p.sm_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
   uint64_t* w_full = bars;          // [2] producer (TMA complete_tx) -> MMA: weight stage landed
-  uint64_t* w_empty = bars + 2;     // [2] MMA (commit) -> producer: stage consumed by both tiles
+  uint64_t* w_empty = bars + 2;     // [2] MMA (one commit per slot) -> producer: stage consumed by both tiles
   uint64_t* a1_ready = bars + 4;    // [2] epilogue -> MMA, once per layer
   uint64_t* d1_ready = bars + 6;    // [2] MMA -> epilogue, once per phase
   uint64_t* d2_ready = bars + 8;    // [2] MMA -> epilogue, once per layer
@@ -90,7 +91,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
   }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1);
+      mbar_init(w_full + s, 1); mbar_init(w_empty + s, 2);
       mbar_init(a1_ready + s, 128); mbar_init(d1_ready + s, 1); mbar_init(d2_ready + s, 1);
       mbar_init(a2_ready + 2 * s, 128); mbar_init(a2_ready + 2 * s + 1, 128);
     }
@@ -133,52 +134,67 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         }
     }
     __syncwarp();
-  } else if (warp == 0) {
-    // ================================ MMA issuer (both slots, lockstep) =========================
+  } else if (warp == 0 || warp == 3) {
+    // ================================ MMA issuers: warp 0 -> slot 0, warp 3 -> slot 1 ===============
+    // One thread per slot: a single thread issuing both slots' 24 MMAs per phase (descriptor arithmetic
+    // included) was the kernel's critical path.  Both walk the same sequence of weight stages; a stage is
+    // released when both have committed (or, for a slot without a tile in the last round, arrived).
     if (lane == 0) {
+      const int s = warp == 0 ? 0 : 1;
       const uint32_t idesc1 = make_idesc(HB), idesc2 = make_idesc(p.N2);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t lbo2 = (uint32_t)p.N2 * 16;
-      uint32_t g = 0, lay_cnt[2] = {0, 0}, ph_cnt[2] = {0, 0};
-      for (int64_t r = 0; r < rounds; ++r)
+      const uint32_t tm = tmem_base + s * 256;
+      const uint64_t a1d = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, W_LBO1, W_SBO1);
+      const uint64_t kstep1 = (uint64_t)(2 * W_LBO1 / 16);          // descriptor start-address units per GEMM1 k-step
+      const uint64_t kstep2 = (uint64_t)(p.N2 * 32 / 16);
+      uint32_t g = 0, lay_cnt = 0, ph_cnt = 0;
+      auto gemm1 = [&](uint32_t gg) {
+        const uint64_t b1d = make_desc(smem_base + p.sm_ring + (gg & 1) * p.phase_bytes, W_LBO1, W_SBO1);
+        for (int j = 0; j < k1_steps; ++j) mma_ss(tm, a1d + j * kstep1, b1d + j * kstep1, idesc1, j > 0 ? 1u : 0u);
+        tc_commit(d1_ready + s);
+      };
+      for (int64_t r = 0; r < rounds; ++r) {
+        const bool has_tile = r < nt[s];
         for (int li = 0; li < p.L; ++li) {
-          for (int s = 0; s < 2; ++s)
-            if (r < nt[s]) mbar_wait(a1_ready + s, lay_cnt[s] & 1);
+          if (!has_tile) {           // keep the ring's arrival count
+            for (int ph = 0; ph < n_ph; ++ph, ++g) {
+              mbar_wait_backoff(w_full + (g & 1), (g >> 1) & 1);
+              mbar_arrive(w_empty + (g & 1));
+            }
+            continue;
+          }
+          mbar_wait_backoff(a1_ready + s, lay_cnt & 1);
+          ++lay_cnt;
+          mbar_wait_backoff(w_full + (g & 1), (g >> 1) & 1);
           tc_fence_after();
+          gemm1(g);
           for (int ph = 0; ph < n_ph; ++ph, ++g) {
             const int st = g & 1;
             const int net = ph / n_blk, blk = ph - net * n_blk;
-            mbar_wait(w_full + st, (g >> 1) & 1);
-            tc_fence_after();
-            const uint32_t b1 = smem_base + p.sm_ring + st * p.phase_bytes;
-            const uint32_t b2 = b1 + p.b1_bytes;
-            for (int s = 0; s < 2; ++s) {
-              if (r >= nt[s]) continue;
-              const uint32_t tm = tmem_base + s * 256;
-              const uint32_t a1 = smem_base + p.sm_slot + s * p.sm_slot_stride;
-              for (int j = 0; j < k1_steps; ++j)
-                mma_ss(tm, make_desc(a1 + j * 2 * W_LBO1, W_LBO1, W_SBO1), make_desc(b1 + j * 2 * W_LBO1, W_LBO1, W_SBO1),
-                       idesc1, j > 0 ? 1u : 0u);
-              tc_commit(d1_ready + s);
+            const uint64_t b2d = make_desc(smem_base + p.sm_ring + st * p.phase_bytes + p.b1_bytes, lbo2, W_SBO2);
+            const uint32_t d2 = tm + d2_col0 + net * p.N2;
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+              mbar_wait_backoff(a2_ready + 2 * s + grp, ph_cnt & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int j = 4 * grp; j < 4 * grp + 4; ++j)
+                mma_ts(d2, tm + j * 8, b2d + j * kstep2, idesc2, (blk > 0 || j > 0) ? 1u : 0u);
             }
-            for (int s = 0; s < 2; ++s) {
-              if (r >= nt[s]) continue;
-              const uint32_t tm = tmem_base + s * 256;
-              const uint32_t d2 = tm + d2_col0 + net * p.N2;
-              for (int grp = 0; grp < 2; ++grp) {
-                mbar_wait(a2_ready + 2 * s + grp, ph_cnt[s] & 1);
-                tc_fence_after();
-                for (int j = 4 * grp; j < 4 * grp + 4; ++j)
-                  mma_ts(d2, tm + j * 8, make_desc(b2 + j * (p.N2 * 32), lbo2, W_SBO2), idesc2,
-                         (blk > 0 || j > 0) ? 1u : 0u);
-              }
-              ++ph_cnt[s];
+            ++ph_cnt;
+            // this slot's GEMM1 of the next phase goes in right behind its GEMM2 (D1 is free once the GEMM2
+            // ahead of it in the pipe has read it): the next EPI1 overlaps the other slot's tensor work
+            if (ph + 1 < n_ph) {
+              mbar_wait_backoff(w_full + ((g + 1) & 1), ((g + 1) >> 1) & 1);
+              tc_fence_after();
+              gemm1(g + 1);
             }
             tc_commit(w_empty + st);
           }
-          for (int s = 0; s < 2; ++s)
-            if (r < nt[s]) { tc_commit(d2_ready + s); ++lay_cnt[s]; }
+          tc_commit(d2_ready + s);
         }
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -212,7 +228,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            if (e0 + 128 * u < tile_elems) act[(inverse ? pi_last[f] : f) * TILE_M + s] = v[u];
+            if (e0 + 128 * u < tile_elems) act[(inverse ? pi_last[f] : f) * ACT_LD + s] = v[u];
             s += ds; f += df;
             while (f >= K) { f -= K; ++s; }
           }
@@ -230,7 +246,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int k = kb * 8 + i;
-            u[i] = (k < p.d1) ? act[cond[k] * TILE_M + t] : (k == p.d1 ? 1.f : 0.f);
+            u[i] = (k < p.d1) ? act[cond[k] * ACT_LD + t] : (k == p.d1 ? 1.f : 0.f);
           }
           uint4 v;
           v.x = pack_bf16(u[0], u[1]); v.y = pack_bf16(u[2], u[3]);
@@ -281,7 +297,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
               const float second = both ? __uint_as_float(r2[i]) + bl[p.N2 + q] : 0.f;
               const float sv = (p.nets & 1) ? first : 0.f;
               const float tv = both ? second : ((p.nets & 2) ? first : 0.f);
-              const int ps = trans[q] * TILE_M + t;
+              const int ps = trans[q] * ACT_LD + t;
               const float xv = act[ps];
               float yv;
               if (!inverse) { yv = xv * expf(sv) + tv; ld += sv; }
@@ -298,7 +314,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         const int64_t avail = (N - base) * (int64_t)K;
         int s = s0, f = f0;
         for (int e = t; e < tile_elems; e += 128) {
-          if (e < avail) gp[e] = act[(inverse ? f : pi_last[f]) * TILE_M + s];
+          if (e < avail) gp[e] = act[(inverse ? f : pi_last[f]) * ACT_LD + s];
           s += ds; f += df;
           while (f >= K) { f -= K; ++s; }
         }
