@@ -16,6 +16,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cnf_common.h"
 #include "cnf_tc_ptx.cuh"
 
@@ -67,6 +69,9 @@ bool tcw_dims(const CnfDims& d, TcwDims* t) {
   return t->sm_total <= 227 * 1024;
 }
 
+// SH = 1: compile-time shape of BASELINE config C4 (K = 100: d0 = d1 = 50, K1 = N2 = 64; 512 hidden
+// units = 4 blocks; both nets = 8 phases); SH = 0: every covered shape, read from TcwDims.
+template <int SH>
 __global__ void __launch_bounds__(W_THREADS, 1)
 flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                 const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
@@ -113,8 +118,10 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
   const int64_t mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + G - 1) / G : 0;
   const int64_t nt[2] = {(mine + 1) / 2, mine / 2};
   const int64_t rounds = nt[0];
-  const int n_ph = p.n_ph, n_blk = p.n_blk;
-  const int k1_steps = p.K1 / 16;
+  const int n_ph = SH ? 8 : p.n_ph, n_blk = SH ? 4 : p.n_blk;
+  const int K1 = SH ? 64 : p.K1, N2 = SH ? 64 : p.N2, D0 = SH ? 50 : p.d0, D1 = SH ? 50 : p.d1, KK = SH ? 100 : p.K;
+  const int NETS = SH ? 3 : p.nets;
+  const int k1_steps = K1 / 16;
   const int d2_col0 = 128;
 
   if (warp == 1) {
@@ -141,13 +148,13 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
     // released when both have committed (or, for a slot without a tile in the last round, arrived).
     if (lane == 0) {
       const int s = warp == 0 ? 0 : 1;
-      const uint32_t idesc1 = make_idesc(HB), idesc2 = make_idesc(p.N2);
+      const uint32_t idesc1 = make_idesc(HB), idesc2 = make_idesc(N2);
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t lbo2 = (uint32_t)p.N2 * 16;
+      const uint32_t lbo2 = (uint32_t)N2 * 16;
       const uint32_t tm = tmem_base + s * 256;
       const uint64_t a1d = make_desc(smem_base + p.sm_slot + s * p.sm_slot_stride, W_LBO1, W_SBO1);
       const uint64_t kstep1 = (uint64_t)(2 * W_LBO1 / 16);          // descriptor start-address units per GEMM1 k-step
-      const uint64_t kstep2 = (uint64_t)(p.N2 * 32 / 16);
+      const uint64_t kstep2 = (uint64_t)(N2 * 32 / 16);
       uint32_t g = 0, lay_cnt = 0, ph_cnt = 0;
       auto gemm1 = [&](uint32_t gg) {
         const uint64_t b1d = make_desc(smem_base + p.sm_ring + (gg & 1) * p.phase_bytes, W_LBO1, W_SBO1);
@@ -173,7 +180,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
             const int st = g & 1;
             const int net = ph / n_blk, blk = ph - net * n_blk;
             const uint64_t b2d = make_desc(smem_base + p.sm_ring + st * p.phase_bytes + p.b1_bytes, lbo2, W_SBO2);
-            const uint32_t d2 = tm + d2_col0 + net * p.N2;
+            const uint32_t d2 = tm + d2_col0 + net * N2;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
               mbar_wait_backoff(a2_ready + 2 * s + grp, ph_cnt & 1);
@@ -204,11 +211,11 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
     uint8_t* a1 = smem + p.sm_slot + slot * p.sm_slot_stride;
     float* act = reinterpret_cast<float*>(a1 + p.sm_act);
     const uint32_t tm = tmem_base + slot * 256 + ((uint32_t)((warp & 3) * 32) << 16);
-    const int* pi_last = tab + p.tab_pi + p.L * p.K;
+    const int* pi_last = tab + p.tab_pi + p.L * KK;
     uint8_t* a1_row = a1 + (t >> 3) * W_SBO1 + (t & 7) * 16;
-    const int K = p.K, tile_elems = TILE_M * p.K;
+    const int K = KK, tile_elems = TILE_M * KK;
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
-    const bool both = (p.nets == 3);
+    const bool both = (NETS == 3);
     uint32_t lay_cnt = 0, ph_cnt = 0;
     for (int64_t r = 0; r < nt[slot]; ++r) {
       const int64_t tile = blockIdx.x + (2 * r + slot) * (int64_t)G;
@@ -238,15 +245,15 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
       float ld = 0.f;
       for (int li = 0; li < p.L; ++li, ++lay_cnt) {
         const int l = inverse ? p.L - 1 - li : li;
-        const int* cond = tab + p.tab_cond + l * p.d1;
-        const int* trans = tab + p.tab_trans + l * p.d0;
+        const int* cond = tab + p.tab_cond + l * D1;
+        const int* trans = tab + p.tab_trans + l * D0;
         // ---- A1 row: K1 bf16 = conditioning logits, the constant one, zero padding ------------
-        for (int kb = 0; kb < p.K1 / 8; ++kb) {
+        for (int kb = 0; kb < K1 / 8; ++kb) {
           float u[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int k = kb * 8 + i;
-            u[i] = (k < p.d1) ? act[cond[k] * ACT_LD + t] : (k == p.d1 ? 1.f : 0.f);
+            u[i] = (k < D1) ? act[cond[k] * ACT_LD + t] : (k == D1 ? 1.f : 0.f);
           }
           uint4 v;
           v.x = pack_bf16(u[0], u[1]); v.y = pack_bf16(u[2], u[3]);
@@ -282,21 +289,21 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         // ---- EPI2: coupling update in fp32, 16 outputs at a time --------------------------------
         mbar_wait(d2_ready + slot, lay_cnt & 1);
         tc_fence_after();
-        const float* bl = bias + l * 2 * p.N2;
-        for (int qc = 0; qc < p.N2; qc += 16) {
+        const float* bl = bias + l * 2 * N2;
+        for (int qc = 0; qc < N2; qc += 16) {
           uint32_t r1[16], r2[16];
           tmem_ld16(tm + d2_col0 + qc, r1);
-          if (both) tmem_ld16(tm + d2_col0 + p.N2 + qc, r2);
+          if (both) tmem_ld16(tm + d2_col0 + N2 + qc, r2);
           tmem_wait_ld16(r1);
           if (both) tmem_wait_ld16(r2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int q = qc + i;
-            if (q < p.d0) {
+            if (q < D0) {
               const float first = __uint_as_float(r1[i]) + bl[q];
-              const float second = both ? __uint_as_float(r2[i]) + bl[p.N2 + q] : 0.f;
-              const float sv = (p.nets & 1) ? first : 0.f;
-              const float tv = both ? second : ((p.nets & 2) ? first : 0.f);
+              const float second = both ? __uint_as_float(r2[i]) + bl[N2 + q] : 0.f;
+              const float sv = (NETS & 1) ? first : 0.f;
+              const float tv = both ? second : ((NETS & 2) ? first : 0.f);
               const int ps = trans[q] * ACT_LD + t;
               const float xv = act[ps];
               float yv;
@@ -407,10 +414,16 @@ int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables
     g_tcw_sms = s;
   }
   if ((uintptr_t)packed_tc % 16 != 0) { cnf_set_error("packed_tc must be 16-byte aligned"); return CNF_E_ARG; }
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int grid = (int)(ntiles < g_tcw_sms ? ntiles : g_tcw_sms);
-  flow_tcw_kernel<<<grid, W_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse);
+  const bool sh = d.K == 100 && d.H[0] == 512 && d.nets == 3 && !getenv("CNF_TC_GENERIC");
+  if (sh) {
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    flow_tcw_kernel<1><<<grid, W_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse);
+  } else {
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    flow_tcw_kernel<0><<<grid, W_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse);
+  }
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
