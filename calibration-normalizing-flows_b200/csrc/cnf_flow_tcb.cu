@@ -215,8 +215,16 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       const uint32_t rec = slot_base;
       const uint32_t h_img = slot_base + p.sm_h, ghm_img = slot_base + p.sm_ghm;
       const uint32_t tm = tmem_base + sl * SLOT_COLS;
+      // Descriptors are formed once; inside the loops only their start-address field (16-byte units) moves,
+      // by plain 64-bit adds: the issuing thread's instruction stream is on the kernel's critical path.
       const uint64_t a1_k = make_desc(rec + OFF_A1, 128, REC);     // [128 smp x 16] K-major (second k-block = zeros)
       const uint64_t g2_k = make_desc(rec + OFF_G2, 128, REC);     // [128 smp x 16] K-major: g_s | g_t
+      const uint64_t ghm_k = make_desc(ghm_img, 128, img_sr);      // ghm image K-major: k-step = 2 core matrices = 256 B
+      const uint64_t h_mn = make_desc(h_img, img_sr, 128);         // h / ghm images MN-major (M = hidden unit):
+      const uint64_t ghm_mn = make_desc(ghm_img, img_sr, 128);     //   S_mn = 128, S_k = img_sr; k-step = 2*img_sr
+      const uint64_t g2p_mn[2] = {make_desc(rec + OFF_G2, REC, 256), make_desc(rec + OFF_G2 + 128, REC, 128)};  // [G2p | 0]
+      const uint64_t a1_mn = make_desc(rec + OFF_Z, REC, 128);     // [0 | A1]
+      const uint64_t img_kstep = (uint64_t)(2 * img_sr / 16), rec_kstep = (uint64_t)(2 * REC / 16);
       const uint32_t id_t2 = make_idesc_ex(16, 0, 1);
       const uint32_t id_t4 = make_idesc_ex(16, 1, 1);
       uint32_t lc = 0, hc = 0;
@@ -233,35 +241,42 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           mbar_wait_backoff(ag_ready + sl, lc & 1);
           ++lc;
           tc_fence_after();
-          for (int ph = 0; ph < n_ph; ++ph) {
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            if (ph >= n_ph) break;
             const uint32_t b1p = b1 + ph * (Hp / 8) * SBO1;      // rows ph*Hp.. of the B1 image
             const uint32_t b2p = b2 + ph * (Hp / 16) * 512;      // k-steps of net ph in the B2 image
-            for (int hf = 0; hf < n_half; ++hf, ++hc) {
+            const uint64_t b1_k = make_desc(b1p, LBO1, SBO1);    // B1p K-major: 8 hidden rows = SBO1 bytes
+            // B2 image, element (n2, hid): (hid/8)*256 + (n2/8)*128 + (n2%8)*16 + (hid%8)*2
+            //   -> MN-major with the hidden unit as the MN index: S_mn = 256, S_k = 128; 16 hidden = 512 B
+            const uint64_t w2_mn = make_desc(b2p, 128, 256);
+            // B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256; k-step (16 hidden) = 512 B
+            const uint64_t w1_mn = make_desc(b1p, 256, 128);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (hf >= n_half) break;
               const int h0 = 64 * hf, w = min(64, Hp - h0);
               // ---- T1 (half): D1 = A1 . B1p[h0..]^T ; GH = G2 . W2p[.., h0..]
-              // B2 image, element (n2, hid): (hid/8)*256 + (n2/8)*128 + (n2%8)*16 + (hid%8)*2
-              //   -> MN-major with the hidden unit as the MN index: S_mn = 256, S_k = 128
-              mma_ss(tm + COL_D1, a1_k, make_desc(b1p + (h0 / 8) * SBO1, LBO1, SBO1), make_idesc_ex(w, 0, 0), 0u);
-              mma_ss(tm + COL_GH, g2_k, make_desc(b2p + (h0 / 16) * 512, 128, 256), make_idesc_ex(w, 0, 1), 0u);
+              mma_ss(tm + COL_D1, a1_k, b1_k + (uint64_t)((h0 / 8) * (SBO1 / 16)), make_idesc_ex(w, 0, 0), 0u);
+              mma_ss(tm + COL_GH, g2_k, w2_mn + (uint64_t)((h0 / 16) * 32), make_idesc_ex(w, 0, 1), 0u);
               tc_commit(t1_done + sl);
-              // ---- T2 (half): GU += ghm . W1p ; A: the ghm image K-major (k-step = 16 hidden = 2 core
-              //      matrices); B: B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256
-              mbar_wait_backoff(hg_ready + sl, hc & 1);
+              ++hc;
+              // ---- T2 (half): GU += ghm . W1p
+              mbar_wait_backoff(hg_ready + sl, (hc - 1) & 1);
               tc_fence_after();
-              for (int j = h0 / 16; j < (h0 + w) / 16; ++j)
-                mma_ss(tm + COL_GU, make_desc(ghm_img + j * 256, 128, img_sr), make_desc(b1p + j * 512, 256, 128), id_t2,
-                       (ph > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = h0 / 16 + jj;
+                if (j < (h0 + w) / 16)
+                  mma_ss(tm + COL_GU, ghm_k + (uint64_t)(j * 16), w1_mn + (uint64_t)(j * 32), id_t2, (ph > 0 || j > 0) ? 1u : 0u);
+              }
             }
-            // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16);
-            //      A: the h / ghm images read MN-major (M = hidden unit): S_mn = 128, S_k = img_sr
+            // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16)
             const uint32_t acc = tmem_base + COL_ACC + (l * n_ph + ph) * 16;
-            const uint32_t sbo_g = (ph == 0) ? 256u : 128u;      // [G2p | 0]: the zero block sits at OFF_Z
-            for (int j = 0; j < 8; ++j)
-              mma_ss(acc, make_desc(h_img + j * 2 * img_sr, img_sr, 128),
-                     make_desc(rec + OFF_G2 + ph * 128 + j * 2 * REC, REC, sbo_g), id_t4, 1u);
-            for (int j = 0; j < 8; ++j)     // [0 | A1]
-              mma_ss(acc, make_desc(ghm_img + j * 2 * img_sr, img_sr, 128), make_desc(rec + OFF_Z + j * 2 * REC, REC, 128),
-                     id_t4, 1u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_ss(acc, h_mn + j * img_kstep, g2p_mn[ph] + j * rec_kstep, id_t4, 1u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_ss(acc, ghm_mn + j * img_kstep, a1_mn + j * rec_kstep, id_t4, 1u);
             tc_commit(t4_done + sl);
           }
           tc_commit(w_empty + st);           // this slot no longer reads the stage once everything above completed
