@@ -183,6 +183,26 @@ def run_reference(args):
     emit(line)
 
 
+def bind_to_gpu_cpus(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so the pinned host buffers of the
+    end-to-end leg are first-touched on the GPU's own NUMA node.  (On this pool's single-NUMA-node VMs it
+    changes nothing: 1.20 vs 1.21 G samples/s end to end on 2 GPUs.)  Returns the number of CPUs, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -195,6 +215,7 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_cpus(local) if world > 1 and not os.environ.get('CNF_NO_AFFINITY') else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -485,7 +506,8 @@ def run_ours(args):
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD, 'l2': 'inputs larger than L2: %d rotating batches' % N_ROT,
-                           'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1'},
+                           'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1',
+                           'cpu_affinity': ('%d GPU-local CPUs per rank' % numa) if numa else 'default'},
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
                 'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'train_step_fp32': train_fp32, 'c5': extra}
         emit(line)
