@@ -187,3 +187,31 @@ def test_tc_training_shapes_outside_coverage_report_zero():
         g = np.empty(16, dtype=np.int32)
         rc = _lib.load().cnf_plan_build_tcgrad(ctypes.byref(desc), g.ctypes.data_as(ctypes.c_void_p))
         assert rc == -4
+
+
+def test_new_entry_points_validate_arguments_without_a_device():
+    """Bad arguments are rejected before any CUDA call (so this runs on the CPU-only box): planar / radial
+    layers, the affine layer and the tensor-core training step."""
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)          # never dereferenced: validation fails first
+    assert lib.cnf_planar_forward(n, one, one, one, one, one, 4, 3, None) == -1
+    assert lib.cnf_planar_forward(one, one, one, one, one, one, 4, 0, None) == -1
+    assert lib.cnf_planar_forward(one, one, one, one, one, one, 4, 513, None) == -1
+    assert b'K <= 512' in lib.cnf_last_error()
+    assert lib.cnf_planar_backward(one, one, None, one, one, one, None, n, one, one, 4, 3, None) == -1
+    assert lib.cnf_radial_forward(one, n, one, one, one, 4, 3, None) == -1
+    assert lib.cnf_radial_backward(one, one, one, one, one, None, one, one, n, 4, 3, None) == -1
+    assert lib.cnf_affine_const(n, None, None, one, 4, 3, 0, None) == -1
+    # N == 0 is a no-op that needs no device
+    assert lib.cnf_planar_forward(one, one, one, one, one, one, 0, 3, None) == 0
+    assert lib.cnf_radial_forward(one, one, one, one, one, 0, 3, None) == 0
+    desc, _keep = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_FP32)
+    acc = ctypes.c_void_p(16)
+    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None)
+    assert rc == -1 and b'BF16_TC' in lib.cnf_last_error()
+    desc, _keep = _lib.make_desc(16, 6, [128], True, True, _lib.PREC_BF16_TC)
+    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None)
+    assert rc == -4
