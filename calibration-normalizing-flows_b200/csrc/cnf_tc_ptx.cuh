@@ -18,11 +18,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef CNF_MBAR_HINT_NS
+#define CNF_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if CNF_MBAR_HINT_NS > 0
+  // suspend-time hint: the hardware may park the thread up to this long before the try returns false
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)CNF_MBAR_HINT_NS) : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
   return ok;
 }
 __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
