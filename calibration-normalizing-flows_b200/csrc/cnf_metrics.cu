@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "cnf_common.h"
+#include "cnf_tc_ptx.cuh"   // mbarrier + cp.async.bulk wrappers
 
 namespace {
 
@@ -56,7 +57,7 @@ template <typename T, int mode, bool ROT, int KT, typename Get, typename Col>
 __device__ __forceinline__ void row_stats(Get get, Col col, int yy, int64_t n, int Krt, int bins,
                                           const double* s_lp, const T* s_edges, const double* __restrict__ edges,
                                           double* __restrict__ probs_out, int& out_bin, unsigned& out_ok,
-                                          double& out_conf, double& a_nll, double& a_correct, double& a_n) {
+                                          double& out_conf, double& a_nll, unsigned& a_correct, unsigned& a_n) {
   const int K = KT > 0 ? KT : Krt;      // compile-time row width for the specialised instantiations
   out_bin = -1;
   T conf, py = (T)0;
@@ -127,7 +128,7 @@ __device__ __forceinline__ void row_stats(Get get, Col col, int yy, int64_t n, i
       }
       a_nll -= log(pyd + 1e-7);
       const unsigned ok = (pred == yy) ? 1u : 0u;
-      a_correct += ok; a_n += 1.0;
+      a_correct += ok; a_n += 1u;
       if (edges != nullptr) {   // calibrated probabilities are float64 in the reference: bin in double
         const double c = best;
         int j = (int)ceil(c * bins) - 1;
@@ -140,14 +141,18 @@ __device__ __forceinline__ void row_stats(Get get, Col col, int yy, int64_t n, i
     }
   }
   const unsigned ok = (pred == yy) ? 1u : 0u;
-  a_correct += ok; a_n += 1.0;
+  a_correct += ok; a_n += 1u;
   if (edges != nullptr) {
     const T c = conf;
     int j = __float2int_ru((float)c * (float)bins) - 1;
     j = j < 0 ? 0 : (j > bins - 1 ? bins - 1 : j);
-    while (j > 0 && !(s_edges[j] < c)) --j;
-    while (j < bins - 1 && !(c <= s_edges[j + 1])) ++j;
-    if ((s_edges[j] < c) && (c <= s_edges[j + 1])) { out_bin = j; out_ok = ok; out_conf = (double)c; }
+    T e_lo = s_edges[j], e_hi = s_edges[j + 1];
+    if (!((e_lo < c) && (c <= e_hi))) {          // rare: the product rounded across an edge
+      while (j > 0 && !(s_edges[j] < c)) --j;
+      while (j < bins - 1 && !(c <= s_edges[j + 1])) ++j;
+      e_lo = s_edges[j]; e_hi = s_edges[j + 1];
+    }
+    if ((e_lo < c) && (c <= e_hi)) { out_bin = j; out_ok = ok; out_conf = (double)c; }
   }
 }
 
@@ -180,11 +185,12 @@ __device__ __forceinline__ T* carve(unsigned char* smem_raw, int bins, int K, Me
   return s_edges;
 }
 
-__device__ __forceinline__ void finish_block(double a_nll, double a_correct, double a_n, BinCache& cache,
+__device__ __forceinline__ void finish_block(double a_nll, unsigned a_correct_u, unsigned a_n_u, BinCache& cache,
                                              const MetricsSmem& m, int bins, double* __restrict__ acc, double* red,
                                              int tid, int NT) {
   flush(cache, m.s_cnt, m.s_cor, m.s_conf);
-  double v3[3] = {a_nll, a_correct, a_n};
+  // per-thread row counts stay below 2^32 (a thread sees at most N / grid-threads rows); exact in double
+  double v3[3] = {a_nll, (double)a_correct_u, (double)a_n_u};
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double v = v3[q];
@@ -256,21 +262,26 @@ metrics_stream_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, i
   unsigned n_rows = 0u, n_ok = 0u;
   const int64_t ntiles = (N + 31) / 32;
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, GW = (int64_t)gridDim.x * nwarps;
+  // One TMA bulk copy per tile (lane 0: expect_tx + cp.async.bulk, completion on the stage's mbarrier)
+  // instead of 16-byte cp.async copies issued by every lane: ~15 fewer instructions per 32 rows.
+  __shared__ uint64_t tile_bar[8][4];
+  if (lane == 0)
+    for (int s = 0; s < stages; ++s) mbar_init(&tile_bar[warp][s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(T));
   auto issue = [&](int64_t tile, int stage) {
-    if (tile < ntiles && (tile + 1) * 32 <= N) {
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(in + tile * tile_elems);
-      unsigned char* dst = reinterpret_cast<unsigned char*>(ring + (size_t)stage * tile_elems);
-      for (int c = lane; c < tile_chunks; c += 32) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 16 * c) : "memory");
-      }
+    if (lane == 0 && tile < ntiles && (tile + 1) * 32 <= N) {
+      mbar_expect_tx(&tile_bar[warp][stage], tile_bytes);
+      bulk_copy_g2s(ring + (size_t)stage * tile_elems, in + tile * tile_elems, tile_bytes, &tile_bar[warp][stage]);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   for (int s = 0; s < stages - 1; ++s) issue(gw + (int64_t)s * GW, s);
+  unsigned phase_bits = 0u;      // bit s: parity of the next completion of stage s
 
   BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
-  double a_nll = 0.0, a_correct = 0.0, a_n = 0.0;
+  double a_nll = 0.0;
+  unsigned a_correct = 0u, a_n = 0u;
   int stage = 0;
   for (int64_t tile = gw, i = 0; tile < ntiles; tile += GW, ++i) {
     int pre = stage + stages - 1;
@@ -278,11 +289,10 @@ metrics_stream_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, i
     issue(tile + (int64_t)(stages - 1) * GW, pre);
     const int64_t n = tile * 32 + lane;
     const int yy = (y != nullptr && n < N) ? (int)y[n] : -1;
-    // all but the newest (stages-1) groups have landed -> this tile's copy is complete
-    if (stages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else if (stages == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else asm volatile("cp.async.wait_group 3;" ::: "memory");
-    __syncwarp();
+    if ((tile + 1) * 32 <= N) {           // a full tile was copied into this stage: wait for its bytes
+      mbar_wait(&tile_bar[warp][stage], (phase_bits >> stage) & 1u);
+      phase_bits ^= 1u << stage;
+    }
     int r_bin = -1;
     unsigned r_ok = 0u;
     double r_conf = 0.0;
@@ -320,7 +330,6 @@ metrics_stream_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, i
     __syncwarp();
     if (++stage == stages) stage = 0;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   (void)n_rows; (void)n_ok;
   finish_block(a_nll, a_correct, a_n, cache, m, bins, acc, red, tid, NT);
   if (PRIV && acc != nullptr) {
@@ -368,7 +377,8 @@ __global__ void metrics_direct_kernel(const T* __restrict__ in, const int64_t* _
     for (int i = tid; i < K; i += NT) m.s_lp[i] = log_priors[i];
   __syncthreads();
   BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
-  double a_nll = 0.0, a_correct = 0.0, a_n = 0.0;
+  double a_nll = 0.0;
+  unsigned a_correct = 0u, a_n = 0u;
   for (int64_t n0 = (int64_t)blockIdx.x * NT; n0 < N; n0 += (int64_t)gridDim.x * NT) {
     const int64_t n = n0 + tid;
     int r_bin = -1;
