@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "cnf_common.h"
+#include "cnf_tc_ptx.cuh"   // mbarrier + cp.async.bulk wrappers
 
 namespace {
 
@@ -32,38 +33,81 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
   for (int e = lane; e < nel; e += 32) __stcs(dst + e, src[e]);
 }
 
+// Full tiles of the forward kernels move by TMA bulk copies (global -> shared on an mbarrier, shared ->
+// global as a bulk group): no per-element copy loop, which was half of the instructions of these kernels.
+// bulk != 0 requires 16-byte aligned x / z (a full tile is 128*K bytes).
+__device__ __forceinline__ void bulk_store_s2g(void* dst_global, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Common tile pipeline of the two forward kernels: row_fn(row_ptr, n) transforms one row in place.
+template <typename RowFn>
+__device__ __forceinline__ void forward_tiles(const float* __restrict__ x, float* __restrict__ z, int64_t N, int K,
+                                              float* tile, uint64_t* bar, int bulk, RowFn row_fn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ntiles = (N + 31) / 32;
+  const uint32_t tile_bytes = (uint32_t)(32 * K * sizeof(float));
+  uint32_t parity = 0;
+  for (int64_t t = (int64_t)blockIdx.x * PR_WARPS + warp; t < ntiles; t += (int64_t)gridDim.x * PR_WARPS) {
+    const int64_t n0 = t * 32;
+    const int rows = (int)((N - n0) < 32 ? (N - n0) : 32);
+    const bool full = bulk && rows == 32;
+    if (full) {
+      if (lane == 0) {
+        bulk_store_wait_read();                       // the previous tile's store has finished reading the buffer
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_copy_g2s(tile, x + n0 * K, tile_bytes, bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    } else {
+      if (lane == 0) bulk_store_wait_read();
+      __syncwarp();
+      tile_load(tile, x + n0 * K, rows * K, lane);
+      __syncwarp();
+    }
+    if (lane < rows) row_fn(tile + lane * K, n0 + lane);
+    if (full) {
+      fence_async_smem();                             // generic-proxy writes -> visible to the bulk store
+      __syncwarp();
+      if (lane == 0) bulk_store_s2g(z + n0 * K, tile, tile_bytes);
+    } else {
+      __syncwarp();
+      tile_store(z + n0 * K, tile, rows * K, lane);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_store_wait_read();
+}
+
 __global__ void __launch_bounds__(PR_WARPS * 32)
 planar_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ uhat,
-                  const float* __restrict__ b, float* __restrict__ z, float* __restrict__ logdet, int64_t N, int K) {
-  extern __shared__ float sm[];
-  float* sw = sm;
-  float* su = sm + K;
-  float* tile = sm + 2 * K + (size_t)(threadIdx.x >> 5) * 32 * K;
+                  const float* __restrict__ b, float* __restrict__ z, float* __restrict__ logdet, int64_t N, int K,
+                  int bulk) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bars[PR_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = sm + (size_t)warp * 32 * K;                 // tiles first: 128*K bytes each, 16-byte aligned
+  float* sw = sm + (size_t)PR_WARPS * 32 * K;
+  float* su = sw + K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) { sw[k] = w[k]; su[k] = uhat[k]; }
+  if (lane == 0) mbar_init(&bars[warp], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   float wu = 0.f;
   for (int k = lane; k < K; k += 32) wu = fmaf(sw[k], su[k], wu);
   wu = wsum(wu);
   const float bias = b[0];
-  const int64_t ntiles = (N + 31) / 32;
-  for (int64_t t = (int64_t)blockIdx.x * PR_WARPS + warp; t < ntiles; t += (int64_t)gridDim.x * PR_WARPS) {
-    const int64_t n0 = t * 32;
-    const int rows = (int)((N - n0) < 32 ? (N - n0) : 32);
-    tile_load(tile, x + n0 * K, rows * K, lane);
-    __syncwarp();
-    if (lane < rows) {
-      float* row = tile + lane * K;
-      float a = bias;
-      for (int k = 0; k < K; ++k) a = fmaf(row[k], sw[k], a);
-      const float h = tanhf(a);
-      for (int k = 0; k < K; ++k) row[k] = fmaf(h, su[k], row[k]);
-      logdet[n0 + lane] = logf(fabsf(1.f + (1.f - h * h) * wu));
-    }
-    __syncwarp();
-    tile_store(z + n0 * K, tile, rows * K, lane);
-    __syncwarp();
-  }
+  forward_tiles(x, z, N, K, tile, &bars[warp], bulk, [&](float* row, int64_t n) {
+    float a = bias;
+    for (int k = 0; k < K; ++k) a = fmaf(row[k], sw[k], a);
+    const float h = tanhf(a);
+    for (int k = 0; k < K; ++k) row[k] = fmaf(h, su[k], row[k]);
+    logdet[n] = logf(fabsf(1.f + (1.f - h * h) * wu));
+  });
 }
 
 // g_x = g_z + g_a*w ; g_w = sum_n g_a x_n + (sum_n c_n) u_hat ; g_uhat = sum_n h_n g_z_n + (sum_n c_n) w ;
@@ -150,31 +194,23 @@ planar_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gz, con
 
 __global__ void __launch_bounds__(PR_WARPS * 32)
 radial_fwd_kernel(const float* __restrict__ x, const float* __restrict__ z0, const float* __restrict__ a_p,
-                  const float* __restrict__ bhat_p, float* __restrict__ z, int64_t N, int K) {
-  extern __shared__ float sm[];
-  float* s0 = sm;
-  float* tile = sm + K + (size_t)(threadIdx.x >> 5) * 32 * K;
+                  const float* __restrict__ bhat_p, float* __restrict__ z, int64_t N, int K, int bulk) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bars[PR_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = sm + (size_t)warp * 32 * K;
+  float* s0 = sm + (size_t)PR_WARPS * 32 * K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) s0[k] = z0[k];
+  if (lane == 0) mbar_init(&bars[warp], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   const float a = a_p[0], bhat = bhat_p[0];
-  const int64_t ntiles = (N + 31) / 32;
-  for (int64_t t = (int64_t)blockIdx.x * PR_WARPS + warp; t < ntiles; t += (int64_t)gridDim.x * PR_WARPS) {
-    const int64_t n0 = t * 32;
-    const int rows = (int)((N - n0) < 32 ? (N - n0) : 32);
-    tile_load(tile, x + n0 * K, rows * K, lane);
-    __syncwarp();
-    if (lane < rows) {
-      float* row = tile + lane * K;
-      float r2 = 0.f;
-      for (int k = 0; k < K; ++k) { const float d = row[k] - s0[k]; r2 = fmaf(d, d, r2); }
-      const float c = bhat / (a + sqrtf(r2));
-      for (int k = 0; k < K; ++k) row[k] = fmaf(c, row[k] - s0[k], row[k]);
-    }
-    __syncwarp();
-    tile_store(z + n0 * K, tile, rows * K, lane);
-    __syncwarp();
-  }
+  forward_tiles(x, z, N, K, tile, &bars[warp], bulk, [&](float* row, int64_t) {
+    float r2 = 0.f;
+    for (int k = 0; k < K; ++k) { const float d = row[k] - s0[k]; r2 = fmaf(d, d, r2); }
+    const float c = bhat / (a + sqrtf(r2));
+    for (int k = 0; k < K; ++k) row[k] = fmaf(c, row[k] - s0[k], row[k]);
+  });
 }
 
 // d = x - z0, r = |d|, h = 1/(a+r), s = g_z.d :
@@ -279,7 +315,8 @@ extern "C" int cnf_planar_forward(const float* x, const float* w, const float* u
   int grid = 1, rc;
   if ((rc = launch_cfg(N, K, smem, &grid))) return rc;
   if ((rc = set_smem(planar_fwd_kernel, smem))) return rc;
-  planar_fwd_kernel<<<grid, PR_WARPS * 32, smem, (cudaStream_t)stream>>>(x, w, u_hat, b, z, logdet, N, K);
+  planar_fwd_kernel<<<grid, PR_WARPS * 32, smem, (cudaStream_t)stream>>>(x, w, u_hat, b, z, logdet, N, K,
+                                                                         (((uintptr_t)x | (uintptr_t)z) % 16 == 0) ? 1 : 0);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -312,7 +349,8 @@ extern "C" int cnf_radial_forward(const float* x, const float* z0, const float* 
   int grid = 1, rc;
   if ((rc = launch_cfg(N, K, smem, &grid))) return rc;
   if ((rc = set_smem(radial_fwd_kernel, smem))) return rc;
-  radial_fwd_kernel<<<grid, PR_WARPS * 32, smem, (cudaStream_t)stream>>>(x, z0, a, b_hat, z, N, K);
+  radial_fwd_kernel<<<grid, PR_WARPS * 32, smem, (cudaStream_t)stream>>>(x, z0, a, b_hat, z, N, K,
+                                                                         (((uintptr_t)x | (uintptr_t)z) % 16 == 0) ? 1 : 0);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -32,3 +32,21 @@ for K in (10, 100, 3):
     gb = n * K * 8 / 1e6
     print('K=%3d N=%9d  copy %.3f ms (%.0f GB/s) | affine fwd %.3f ms (%.0f GB/s) inv %.3f ms (%.0f GB/s) | backward %.3f ms (%.0f GB/s of 12K B/sample)'
           % (K, n, ms_copy, gb / ms_copy, ms_f, gb / ms_f, ms_i, gb / ms_i, ms_b, n * K * 12 / 1e6 / ms_b))
+
+# PlanarLayer / RadialLayer streaming kernels (8K+4 / 8K bytes per sample forward)
+import cnf_b200
+for K in (10, 100):
+    n = 100_000_000 // K
+    x = torch.randn(n, K, device=dev)
+    pl = cnf_b200.PlanarLayer(K).to(dev)
+    rl = cnf_b200.RadialLayer(K).to(dev)
+    with torch.no_grad():
+        ms_p = timeit(lambda: pl(x))
+        ms_r = timeit(lambda: rl(x))
+    xg = x.clone().requires_grad_(True)
+    def fb(layer):
+        z, ld = layer(xg)
+        (z.sum() + ld.sum()).backward()
+    ms_pb = timeit(lambda: fb(pl), reps=5)
+    print('K=%3d planar fwd %.3f ms (%.0f GB/s)  radial fwd %.3f ms (%.0f GB/s)  planar fwd+bwd via autograd %.3f ms'
+          % (K, ms_p, n * (8 * K + 4) / 1e6 / ms_p, ms_r, n * 8 * K / 1e6 / ms_r, ms_pb))
