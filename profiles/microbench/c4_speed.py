@@ -3,7 +3,6 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np, torch, cnf_b200
-import flow_oracle as orc
 dev = torch.device('cuda:0')
 K, L, H = 100, 8, [512]
 torch.manual_seed(4)
@@ -14,7 +13,10 @@ with torch.no_grad():
 m.to(dev)
 eng = m.engine()
 n = 200_000
-x = torch.from_numpy(orc.synth_logits(n, K, seed=1)[0]).to(dev)
+g = torch.Generator().manual_seed(1)
+x = (1.5 * torch.randn(n, K, generator=g))
+x[torch.arange(n), torch.randint(0, K, (n,), generator=g)] += 3.0
+x = (x - x.mean(dim=1, keepdim=True)).to(dev)
 eng.ensure(dev); eng.pack(tc=True)
 def timeit(f, reps=5):
     for _ in range(2): f()

@@ -1,5 +1,6 @@
 """Per-tensor error of the tensor-core training gradient (bf16) against the float64 oracle.
-Run on the GPU box: python profiles/microbench/diag_tcgrad.py [N]"""
+Diagnostic (test infrastructure, uses the oracle as the checker).  Run on the GPU box from the repo root:
+    python tests/diag_tcgrad.py [N]"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); sys.path.insert(0, 'oracle')
 import flow_oracle as orc

@@ -113,7 +113,7 @@ def test_tc_wide_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda
 # tensor-core TRAINING path (cnf_flow_tcb.cu): stated bf16 tolerance on the gradient:
 #   max|g - g_ref| <= 2e-2 * max|g_ref| over the whole flat gradient for batches of >= 4096 samples,
 #   1e-1 on the 48-sample golden batches, loss within 1e-2 relative.
-# Where the error comes from (profiles/microbench/diag_tcgrad.py): the bf16 rounding of the conditioning
+# Where the error comes from (tests/diag_tcgrad.py): the bf16 rounding of the conditioning
 # logits moves ~0.3 % of the hidden pre-activations across zero, which flips their ReLU mask; each flip
 # adds or removes one whole (sample, unit) term of the first-Linear gradients.  On 48 samples that is a
 # visible fraction of those (small) tensors; the last-Linear gradients stay within 0.6 % even there.
