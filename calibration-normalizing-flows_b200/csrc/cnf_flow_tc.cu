@@ -4,20 +4,25 @@
 // Shape coverage (cnf_tc_supported): one hidden layer per conditioner, K <= 16 classes
 // (d1+1 <= 16, d0 <= 8), N1 = n_nets*pad16(H) <= 256.  Everything else runs on the fp32 kernel.
 //
-// Per coupling layer and per tile of 128 samples (TMEM lane = sample row):
-//   GEMM1  D1[128 x N1] = A1[128 x 16] . B1^T          tcgen05.mma SS, bf16 in, fp32 out (TMEM)
+// Per coupling layer and per tile of 128 samples (TMEM lane = sample row), per conditioner net (s, then t):
+//   GEMM1  D1[128 x Hp] = A1[128 x 16] . B1[net]^T     tcgen05.mma SS, bf16 in, fp32 out (TMEM)
 //          A1 row = (u_0..u_{d1-1}, 1, 0..): the conditioning logits plus a constant-one column
-//          that folds the first-layer bias; B1 = first Linear of the s-net and of the t-net side
-//          by side (flows/utils.py:26-31, flows/flows.py:105).
-//   EPI1   h = relu(D1) -> bf16, written back to TMEM in place (A2 aliases the low half of D1).
-//   GEMM2  D2[128 x 16] = A2[128 x N1] . B2^T            tcgen05.mma TS (A from TMEM), N1/16 k-steps
-//          B2 = block-diagonal last Linears: columns 0..7 <- first present net, 8..15 <- second.
+//          that folds the first-layer bias; B1 = first Linear of the s-net and of the t-net one
+//          after the other (flows/utils.py:26-31, flows/flows.py:105).
+//   EPI1   h = relu(D1) -> bf16, written back to TMEM in place (A2 aliases the low half of D1),
+//          released to the issuer 64 hidden units at a time.
+//   GEMM2  D2[128 x 16] += A2[128 x Hp] . B2[net]^T     tcgen05.mma TS (A from TMEM), Hp/16 k-steps
+//          B2 = block-diagonal last Linears: columns 0..7 <- first present net, 8..15 <- second;
+//          the other net's GEMM1 is issued right behind (the in-order tensor pipe resolves the WAR on D1).
+// then
 //   EPI2   s,t = D2 + b2 (fp32); y = x*exp(s)+t, ld += sum s   (flows/flows.py:107-109); inverse
 //          x = (y-t)*exp(-s), ld -= sum s (flows/flows.py:121-125).
-// A CTA keeps two tiles in flight (two 256-column TMEM slots, one epilogue warpgroup each) so the
-// tensor pipe works on one tile while CUDA cores run the other tile's epilogue.  Warp 0 lane 0
-// issues every MMA and polls the slots' mbarriers; all packed weights of all layers stay
-// resident in shared memory in the canonical no-swizzle K-major UMMA layout.
+// A CTA keeps THREE tiles in flight (TMEM slots of 160 columns: D1 128 + D2 16; one epilogue warpgroup and
+// one MMA-issuer warp each) so the tensor pipe works on one tile while CUDA cores run the other tiles'
+// epilogues; all packed weights of all layers stay resident in shared memory in the canonical
+// no-swizzle K-major UMMA layout.  TAPE (training): the epilogue also writes, per layer, the pre-layer
+// values of the transformed logits and the scale-net outputs for cnf_flow_tcb.cu.  SH: compile-time
+// shape of BASELINE configs C2/C3/C5 (see the kernel).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
