@@ -437,6 +437,31 @@ def run_ours(args):
                                'tensor_tflops_minimal': c4_flops * n4 / (c4_ms * 1e-3) / 1e12,
                                'frac_of_bf16_peak': c4_flops * n4 / (c4_ms * 1e-3) / 1e12 / peaks()[1]}
         del x4, z4, l4
+        # config C1 through the calibrator API (rank 0, N=1 only): NICE, K=3, N=10,000, 4 additive couplings,
+        # hidden 32, fit (50 full-batch epochs) + predict, host numpy in and out (calibrators.py:241-353)
+        if rank == 0 and world == 1:
+            import numpy as np
+            rs = np.random.RandomState(3)
+            y1 = rs.randint(0, 3, size=10_000)
+            x1 = (1.5 * rs.randn(10_000, 3)).astype(np.float32)
+            x1[np.arange(10_000), y1] += 3.0 * (rs.rand(10_000) < 0.8)
+            t1 = np.eye(3, dtype=np.float32)[y1]
+
+            def c1_run():
+                cal = cnf_b200.TorchFlowCalibrator(cnf_b200.NiceFlow, x1, t1, layers=4, hidden_size=[32], epochs=50,
+                                                   dev=dev)
+                return cal.predict(x1)
+            c1_run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p1 = c1_run()
+            torch.cuda.synchronize()
+            c1_s = time.perf_counter() - t0
+            extra['c1_calibrator'] = {'value': 10_000 * 50 / c1_s, 'unit': UNIT, 'wall_s': c1_s, 'dtype': 'f32',
+                                      'what': 'C1: TorchFlowCalibrator(NiceFlow, K=3, N=10,000, 4 couplings, hidden 32): '
+                                              'fit 50 full-batch epochs + predict, host numpy in/out; value = '
+                                              'training samples per second of wall time',
+                                      'finite': bool(np.isfinite(p1).all())}
 
     hbm, tf, src = peaks()
     ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
@@ -488,6 +513,22 @@ def run_ours(args):
                 dt = time.perf_counter() - t0
             extra['inverse']['cpu_baseline'] = {'value': N_STEP / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                                 'sample': '1,000,000 samples, one pass, flows/flows.py:114-126 in torch CPU ops'}
+            if 'c1_calibrator' in extra:
+                g1 = torch.Generator().manual_seed(5)
+                xs1 = 1.5 * torch.randn(10_000, 3, generator=g1)
+                ys1 = torch.randint(0, 3, (10_000,), generator=g1)
+                n1 = 4 * (32 * 3 + 32 + 3 * 32 + 3)
+                st1 = rp.TrainState(0.001 * torch.randn(n1, generator=g1), 3, 4, [32], scale=False, shift=True)
+                st1.step(xs1, ys1)
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    st1.step(xs1, ys1)
+                dt1 = time.perf_counter() - t0
+                extra['c1_calibrator']['cpu_baseline'] = {
+                    'value': 10_000 * 50 / dt1, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'sample': '50 full-batch steps on 10,000 samples: torch autograd + Adam on the reference op '
+                              'sequence WITHOUT its DataLoader (calibrators.py:268-283 collates per sample, which '
+                              'dominates the reference at this size, SURVEY.md 6)'}
             n_mc = 2_000_000
             xm, ym_c = synth(n_mc, 17)
             pm_c = torch.softmax(xm, dim=1).numpy()
