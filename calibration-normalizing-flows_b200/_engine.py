@@ -257,6 +257,8 @@ class StackEngine:
                       _ptr(self.flat_grad), st)
 
     def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if getattr(self, 'adam_step_dev', None) is not None:      # steps were taken on the device-counted path
+            return self.adam_dev(lr, betas, eps, weight_decay)
         if self.adam_m is None:
             self.adam_m = torch.zeros_like(self.flat)
             self.adam_v = torch.zeros_like(self.flat)
@@ -264,6 +266,21 @@ class StackEngine:
         self.adam_t += 1
         _lib.call('cnf_adam_step', _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
                   ctypes.c_int64(self.n_flat), ctypes.c_int64(self.adam_t), ctypes.c_float(lr),
+                  ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
+                  ctypes.c_float(weight_decay), _stream(self.device))
+
+    def adam_dev(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """Adam with the step count kept on the device (cnf_adam_step_dev): no host state, so the call can
+        sit inside a captured CUDA graph.  Continues from the host-counted steps taken so far."""
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+            self.adam_t = 0
+        if getattr(self, 'adam_step_dev', None) is None or self.adam_step_dev.device != self.flat.device:
+            self.adam_step_dev = torch.full((1,), int(self.adam_t), dtype=torch.int64, device=self.flat.device)
+            self.adam_coef = torch.zeros(2, dtype=torch.float32, device=self.flat.device)
+        _lib.call('cnf_adam_step_dev', _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                  ctypes.c_int64(self.n_flat), _ptr(self.adam_step_dev), _ptr(self.adam_coef), ctypes.c_float(lr),
                   ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
                   ctypes.c_float(weight_decay), _stream(self.device))
 

@@ -69,6 +69,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi - lr_over_bc1 * (mi / denom);
 }
 
+// CUDA-graph friendly Adam: the step count lives in device memory, so a captured training step can be
+// replayed (a host-computed bias correction would be baked into the graph at capture time).
+__global__ void adam_prep_kernel(long long* __restrict__ step, float* __restrict__ coef, float lr, float b1, float b2) {
+  const long long t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  coef[0] = (float)((double)lr / bc1);
+  coef[1] = (float)(1.0 / sqrt(bc2));
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ coef, float b1, float b2,
+                                float eps, float wd) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_over_bc1 = coef[0], inv_sqrt_bc2 = coef[1];
+  float gi = g[i];
+  const float pi = p[i];
+  if (wd != 0.f) gi = fmaf(wd, pi, gi);
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] = pi - lr_over_bc1 * (mi / denom);
+}
+
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -122,6 +149,19 @@ extern "C" int cnf_adam_step(float* params, const float* grad, float* exp_avg, f
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n,
                                                                              lr_over_bc1, inv_sqrt_bc2, beta1, beta2,
                                                                              eps, weight_decay);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_adam_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 int64_t* step_dev, float* coef_dev, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, void* stream) {
+  if (!params || !grad || !exp_avg || !exp_avg_sq || !step_dev || !coef_dev || n < 0) { cnf_set_error("cnf_adam_step_dev: bad argument"); return CNF_E_ARG; }
+  if (n == 0) return CNF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_prep_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_dev), coef_dev, lr, beta1, beta2);
+  adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, exp_avg, exp_avg_sq, n, coef_dev, beta1, beta2,
+                                                             eps, weight_decay);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -145,6 +145,12 @@ int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_partials, const
 int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                   void* stream);
+/* Same update with the step count kept on the device (step_dev: int64 [1], incremented by the call;
+ * coef_dev: float32 [2] scratch), so that a whole training step can be captured in a CUDA graph and
+ * replayed: nothing in it depends on host state.                                                    */
+int cnf_adam_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      int64_t* step_dev, float* coef_dev, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, void* stream);
 int cnf_sgd_step(float* params, const float* grad, int64_t n, float lr, float weight_decay,
                  void* stream);
 

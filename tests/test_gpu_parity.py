@@ -437,3 +437,21 @@ def test_planar_radial_inside_a_flow_and_ragged_sizes(cuda_device):
         zo, _ = orc.radial_forward(rl.z0.detach().cpu().numpy().astype(np.float64), rl.a.detach().cpu().numpy(),
                                    rl.b.detach().cpu().numpy(), x.astype(np.float64))
         assert rel_err(z.cpu().numpy(), zo) < TOL
+
+
+def test_calibrator_fit_with_captured_cuda_graph_epochs_matches_eager(cuda_device):
+    """cuda_graph=True (one graph launch per full-batch epoch, Adam step count on the device) reproduces the
+    eager fit: same history and same predictions."""
+    import torch
+    import cnf_b200
+    g = load_golden('calibrator_cal_nvp_k10')
+    hidden = [int(h) for h in g['hidden']]
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(5)
+        cal = cnf_b200.TorchFlowCalibrator(cnf_b200.RealNvpFlow, g['x'], g['y'], layers=int(g['layers']),
+                                           hidden_size=hidden, epochs=12, dev=cuda_device, cuda_graph=graph)
+        out[graph] = (np.array([float(v) for v in cal.history['loss']]), cal.predict(g['x_test']))
+    assert np.isfinite(out[True][0]).all()
+    assert np.allclose(out[True][0], out[False][0], rtol=1e-6, atol=1e-7)
+    assert np.max(np.abs(out[True][1] - out[False][1])) < 1e-6
