@@ -126,9 +126,12 @@ class StackEngine:
         if not ok:
             self._bind(device)
 
-    def pack(self, tc=False):
+    def pack(self, tc=False, fp32=True):
+        """Refresh the kernel-side weight copies from `flat`: the fp32 blob (fp32=True) and/or the bf16
+        tensor-core blob (tc=True)."""
         st = _stream(self.device)
-        _lib.call('cnf_pack_weights', ctypes.byref(self.desc), _ptr(self.flat), _ptr(self.gather), _ptr(self.packed), st)
+        if fp32:
+            _lib.call('cnf_pack_weights', ctypes.byref(self.desc), _ptr(self.flat), _ptr(self.gather), _ptr(self.packed), st)
         if tc and self.packed_tc is not None:
             _lib.call('cnf_pack_weights_tc', ctypes.byref(self.desc_tc), _ptr(self.flat), _ptr(self.gather_tc),
                       _ptr(self.packed_tc), st)

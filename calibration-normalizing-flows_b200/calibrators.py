@@ -88,7 +88,7 @@ class FusedNLLTrainer:
         self.eps, self.gamma = eps, gamma
         self.lr, self.betas, self.adam_eps, self.wd, self.optim = lr, betas, adam_eps, weight_decay, optim
         engine.ensure(x.device)
-        engine.pack(tc=(precision == 'bf16'))
+        engine.pack(tc=(precision == 'bf16'), fp32=(precision != 'bf16'))
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=x.device)
 
     def step(self, xb=None, yb=None, n_batch_total=None):
@@ -107,7 +107,7 @@ class FusedNLLTrainer:
             e.adam(self.lr, self.betas, self.adam_eps, self.wd)
         else:
             e.sgd(self.lr, self.wd)
-        e.pack(tc=(self.precision == 'bf16'))
+        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
 
     # ------------------------------------------------------------------ CUDA-graph epoch
     def _epoch_body(self):
@@ -119,7 +119,7 @@ class FusedNLLTrainer:
             e.adam_dev(self.lr, self.betas, self.adam_eps, self.wd)
         else:
             e.sgd(self.lr, self.wd)
-        e.pack(tc=(self.precision == 'bf16'))
+        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
         self.eval_acc.zero_()
         e.nll_step(self.x, self.y, self.eval_acc, self.eps, self.gamma, self.n_total, with_grad=False,
                    precision=self.precision)
@@ -223,8 +223,15 @@ class TorchFlowCalibrator(Calibrator):
                 trainer.epoch_graph()
                 hist[epoch].copy_(trainer.eval_acc)
             elif full_batch:
+                # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the
+                # full batch and no shuffling effect that number IS the loss the next step's forward computes
+                # on the same weights and samples, so it is taken from there; only the last epoch needs its
+                # own evaluation pass.  Same kernels, same arithmetic: the history is unchanged.
                 trainer.step()
-                trainer.evaluate(out=hist[epoch])
+                if epoch > 0:
+                    hist[epoch - 1].copy_(trainer.loss_acc)
+                if epoch == epochs - 1:
+                    trainer.evaluate(out=hist[epoch])
             else:
                 perm = torch.randperm(n_local, device=self.dev, generator=gen)
                 for s in range(0, n_local, local_bs):

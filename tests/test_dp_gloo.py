@@ -29,7 +29,7 @@ class OracleEngine:
     def ensure(self, device):
         pass
 
-    def pack(self, tc=False):
+    def pack(self, tc=False, fp32=True):
         pass
 
     def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision="fp32"):

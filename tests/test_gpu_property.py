@@ -118,4 +118,9 @@ def test_random_shapes_tensor_core_training_matches_fp32_kernel(cfg, seed, cuda_
     gmax = float(g32.abs().max())
     if gmax > 0:
         assert float((g16 - g32).abs().max()) < 2e-2 * gmax
-    assert bool((g16[g32 == 0] == 0).all())
+    # structurally dead parameters (masked columns / rows) stay exactly zero; a hidden unit that is
+    # dead in fp32 may see a few bf16-flipped samples, so "zero in fp32" alone is not the criterion
+    live = np.zeros(eng.n_flat, dtype=bool)
+    gmap = eng.tc_train[3]
+    live[gmap[gmap >= 0]] = True
+    assert bool((g16.cpu().numpy()[~live] == 0).all())
