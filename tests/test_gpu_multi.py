@@ -19,7 +19,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, precision='fp32'):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, 'oracle'), os.path.join(root, 'tests')):
@@ -40,7 +40,8 @@ def _worker(rank, world, port, out_dir):
     x, y = orc.synth_logits(N, 10, seed=21)
     lo, hi = shard_bounds(N, rank, world)
     flow = build_flow_from_golden(g, dev)
-    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev))
+    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev),
+                         precision=precision)
     assert tr.n_total == N
     losses = []
     for _ in range(4):
@@ -51,7 +52,8 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_dp_matches_single_gpu(tmp_path, cuda_device):
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_two_gpu_dp_matches_single_gpu(precision, tmp_path, cuda_device):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -60,19 +62,22 @@ def test_two_gpu_dp_matches_single_gpu(tmp_path, cuda_device):
     from conftest import load_golden
     from helpers import build_flow_from_golden, rel_err
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), precision), nprocs=world, join=True)
     r = [dict(np.load(os.path.join(str(tmp_path), 'rank%d.npz' % i))) for i in range(world)]
     assert np.array_equal(r[0]['flat'], r[1]['flat'])           # identical update on every rank
     g = load_golden('flow_c2_nvp_k10_init')
     N = 200_003
     x, y = orc.synth_logits(N, 10, seed=21)
     flow = build_flow_from_golden(g, cuda_device)
-    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device))
+    tr = FusedNLLTrainer(flow.engine(), torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device),
+                         precision=precision)
     losses = []
     for _ in range(4):
         tr.step()
         losses.append(-float(tr.loss_acc[0]) / N)
     assert np.allclose(losses, r[0]['losses'], rtol=1e-6, atol=1e-7)
-    assert rel_err(r[0]['grad'], flow.engine().flat_grad.cpu().numpy()) < 1e-4
+    # bf16: the two runs cut the samples into different tiles and accumulate in a different order
+    assert rel_err(r[0]['grad'], flow.engine().flat_grad.cpu().numpy()) < (1e-4 if precision == 'fp32' else 1e-3)
     disp = flow.engine().flat.cpu().numpy() - g['flat']
-    assert rel_err(r[0]['flat'] - g['flat'], disp) < 2e-2      # Adam normalises tiny gradients: compare displacements
+    # Adam normalises tiny gradients (update ~ lr * sign for entries whose gradient is noise): compare displacements
+    assert rel_err(r[0]['flat'] - g['flat'], disp) < (2e-2 if precision == 'fp32' else 1e-1)
