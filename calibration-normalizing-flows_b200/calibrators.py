@@ -175,8 +175,9 @@ class TorchFlowCalibrator(Calibrator):
         # extension: precision='bf16' trains on the tcgen05 kernels (stated bf16 tolerance); default fp32
         self.precision = kwargs.get('precision', 'fp32')
         # extension: cuda_graph=True replays each full-batch epoch as one captured CUDA graph.  Off by default:
-        # at the reference's calibration-set sizes an epoch is already GPU-bound, not launch-bound
-        # (N=10,000, K=3: 135 us per epoch eager vs 147 us replayed, profiles/microbench/c1_fit_speed.py).
+        # at the reference's calibration-set sizes an epoch is already GPU-bound, not launch-bound, and the
+        # eager launches run ahead of the GPU (K=3, N=10,000: 127 us per epoch eager vs 139 us replayed;
+        # K=10, N=5,000, bf16: 102 vs 126 us; profiles/microbench/c1_fit_speed.py, c2_fit_speed.py).
         self.cuda_graph = kwargs.get('cuda_graph', False)
         self.CE = torch.nn.CrossEntropyLoss()
         self.optimizer = torch.optim.Adam(self.flow.parameters())
