@@ -231,12 +231,13 @@ class StackEngine:
         need = chunk * wsb
         if self._train_ws is None or self._train_ws.numel() < need:
             self._train_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        used = ctypes.c_int64(0)
         _lib.call('cnf_nll_train_step_tc', ctypes.byref(self.desc_tc), _ptr(self.packed_tc), _ptr(self.tables),
                   _ptr(x), _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
                   ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials_tc) if with_grad else None,
-                  _ptr(loss_acc), _ptr(self._train_ws), ctypes.c_int64(need), st)
+                  _ptr(loss_acc), _ptr(self._train_ws), ctypes.c_int64(need), ctypes.byref(used), st)
         if with_grad:
-            _lib.call('cnf_grad_reduce_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc),
+            _lib.call('cnf_grad_reduce_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc), used,
                       _ptr(self.gather_tcgrad), _ptr(self.flat_grad), st)
 
     def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision='fp32'):

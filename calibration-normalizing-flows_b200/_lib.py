@@ -54,8 +54,9 @@ SIGNATURES = {
     'cnf_tc_train_info': [_DESC, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                           ctypes.POINTER(ctypes.c_int64)],
     'cnf_plan_build_tcgrad': [_DESC, _P],
-    'cnf_nll_train_step_tc': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P, _I64, _P],
-    'cnf_grad_reduce_tc': [_DESC, _P, _P, _P, _P],
+    'cnf_nll_train_step_tc': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P, _I64,
+                              ctypes.POINTER(ctypes.c_int64), _P],
+    'cnf_grad_reduce_tc': [_DESC, _P, _I64, _P, _P, _P],
     'cnf_adam_step': [_P, _P, _P, _P, _I64, _I64, _F32, _F32, _F32, _F32, _F32, _P],
     'cnf_adam_step_dev': [_P, _P, _P, _P, _I64, _P, _P, _F32, _F32, _F32, _F32, _F32, _P],
     'cnf_sgd_step': [_P, _P, _I64, _F32, _F32, _P],

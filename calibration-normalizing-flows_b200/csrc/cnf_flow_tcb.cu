@@ -659,7 +659,7 @@ extern "C" int cnf_plan_build_tcgrad(const cnf_flow_desc* desc, int32_t* g) {
 extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables,
                                      const float* x, const int64_t* y, int64_t N, float eps, float gamma,
                                      float inv_n_total, float* grad_partials_tc, double* loss_acc, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
+                                     int64_t workspace_bytes, int64_t* rows_used, void* stream) {
   CnfDims d; TbDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
@@ -670,7 +670,12 @@ extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* pack
   const int sms = tb_sms();
   if (sms <= 0) { cnf_set_error("no CUDA device"); return CNF_E_CUDA; }
   if (sms > CNF_TCB_ROWS) { cnf_set_error("device has more SMs than partial rows"); return CNF_E_UNSUPPORTED; }
-  if (grad_partials_tc) CNF_CHECK_CUDA(cudaMemsetAsync(grad_partials_tc, 0, (size_t)CNF_TCB_ROWS * t.n_grad * sizeof(float), st));
+  // rows [0, grid) of the partial buffer are written (one per CTA of the largest launch): only those are
+  // cleared here and summed by cnf_grad_reduce_tc -- at calibration-set sizes that is a few dozen rows, not 160
+  const int64_t nt_all = (N + TILE_M - 1) / TILE_M;
+  const int64_t used = nt_all < sms ? (nt_all > 0 ? nt_all : 1) : sms;
+  if (rows_used) *rows_used = used;
+  if (grad_partials_tc) CNF_CHECK_CUDA(cudaMemsetAsync(grad_partials_tc, 0, (size_t)used * t.n_grad * sizeof(float), st));
   if (N == 0) return CNF_OK;
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
   const int64_t per_sample = (int64_t)(d.K + 1 + 16 * d.L) * 4;
@@ -703,16 +708,16 @@ extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* pack
   return CNF_OK;
 }
 
-extern "C" int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, const int32_t* gather_tcgrad,
-                                  float* flat_grad, void* stream) {
+extern "C" int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, int64_t rows_used,
+                                  const int32_t* gather_tcgrad, float* flat_grad, void* stream) {
   CnfDims d; TbDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!tb_dims(d, &t)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
-  if (!grad_partials_tc || !gather_tcgrad || !flat_grad) { cnf_set_error("cnf_grad_reduce_tc: null pointer"); return CNF_E_ARG; }
+  if (!grad_partials_tc || !gather_tcgrad || !flat_grad || rows_used < 1 || rows_used > CNF_TCB_ROWS) { cnf_set_error("cnf_grad_reduce_tc: null pointer or bad row count"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
-  tcb_reduce_kernel<<<(t.n_grad + 127) / 128, 128, 0, st>>>(grad_partials_tc, gather_tcgrad, flat_grad, t.n_grad, CNF_TCB_ROWS);
+  tcb_reduce_kernel<<<(t.n_grad + 127) / 128, 128, 0, st>>>(grad_partials_tc, gather_tcgrad, flat_grad, t.n_grad, (int)rows_used);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -165,12 +165,14 @@ int cnf_tc_train_info(const cnf_flow_desc* desc, int64_t* n_grad, int64_t* rows,
 int cnf_plan_build_tcgrad(const cnf_flow_desc* desc, int32_t* gather_tcgrad_host);
 /* packed_tc: blob of cnf_pack_weights_tc.  The samples are processed in chunks of
  * workspace_bytes / ws_bytes_per_sample (rounded down to 1024) samples.  grad_partials_tc:
- * float32 [rows, n_grad], overwritten; NULL = evaluation only.  loss_acc as cnf_nll_train_step.  */
+ * float32 [rows, n_grad], its first *rows_used rows overwritten (rows_used: HOST out, may be NULL);
+ * NULL = evaluation only.  loss_acc as cnf_nll_train_step.                                        */
 int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables,
                           const float* x, const int64_t* y, int64_t N, float eps, float gamma,
                           float inv_n_total, float* grad_partials_tc, double* loss_acc,
-                          void* workspace, int64_t workspace_bytes, void* stream);
-int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc,
+                          void* workspace, int64_t workspace_bytes, int64_t* rows_used, void* stream);
+/* rows_used: what cnf_nll_train_step_tc reported (rows [0, rows_used) of the partial buffer were written). */
+int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, int64_t rows_used,
                        const int32_t* gather_tcgrad, float* flat_grad, void* stream);
 
 /* ---- device: metrics ----------------------------------------------------------- */

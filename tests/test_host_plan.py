@@ -210,8 +210,8 @@ def test_new_entry_points_validate_arguments_without_a_device():
     assert lib.cnf_radial_forward(one, one, one, one, one, 0, 3, None) == 0
     desc, _keep = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_FP32)
     acc = ctypes.c_void_p(16)
-    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None)
+    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None, None)
     assert rc == -1 and b'BF16_TC' in lib.cnf_last_error()
     desc, _keep = _lib.make_desc(16, 6, [128], True, True, _lib.PREC_BF16_TC)
-    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None)
+    rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None, None)
     assert rc == -4
