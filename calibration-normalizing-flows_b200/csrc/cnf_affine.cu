@@ -79,8 +79,9 @@ __global__ void affine_backward_kernel(const float* __restrict__ x, const float*
 
 extern "C" int cnf_affine_const(const float* x, const float* s, const float* t, float* z, int64_t N, int32_t K,
                                 int32_t inverse, void* stream) {
-  if (!x || !z || N < 0 || K < 1 || K > 8192) { cnf_set_error("cnf_affine_const: bad argument"); return CNF_E_ARG; }
-  if (N == 0) return CNF_OK;
+  if (N < 0 || K < 1 || K > 8192) { cnf_set_error("cnf_affine_const: bad argument"); return CNF_E_ARG; }
+  if (N == 0) return CNF_OK;      // an empty batch may come with null data pointers
+  if (!x || !z) { cnf_set_error("cnf_affine_const: null pointer"); return CNF_E_ARG; }
   int dev = 0, sms = 0;
   CNF_CHECK_CUDA(cudaGetDevice(&dev));
   CNF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -95,7 +96,7 @@ extern "C" int cnf_affine_const(const float* x, const float* s, const float* t, 
 
 extern "C" int cnf_affine_const_backward(const float* x, const float* g_z, const float* s, float* g_x, float* g_s,
                                          float* g_t, int64_t N, int32_t K, void* stream) {
-  if (!x || !g_z || N < 0 || K < 1 || K > 1024) { cnf_set_error("cnf_affine_const_backward: bad argument"); return CNF_E_ARG; }
+  if ((N > 0 && (!x || !g_z)) || N < 0 || K < 1 || K > 1024) { cnf_set_error("cnf_affine_const_backward: bad argument"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   if (g_s) CNF_CHECK_CUDA(cudaMemsetAsync(g_s, 0, K * sizeof(float), st));
   if (g_t) CNF_CHECK_CUDA(cudaMemsetAsync(g_t, 0, K * sizeof(float), st));

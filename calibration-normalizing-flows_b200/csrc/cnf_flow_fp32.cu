@@ -703,8 +703,9 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!packed || !tables || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
-  if (head == CNF_HEAD_NLL && (!y || !loss_acc)) { cnf_set_error("NLL head needs labels and loss_acc"); return CNF_E_ARG; }
-  if (head == CNF_HEAD_EXTERNAL && (!gz || !gld || !partials)) { cnf_set_error("external head needs g_z, g_logdet, partials"); return CNF_E_ARG; }
+  // an empty batch may come with null data pointers (an empty torch tensor has none)
+  if (head == CNF_HEAD_NLL && ((N > 0 && !y) || !loss_acc)) { cnf_set_error("NLL head needs labels and loss_acc"); return CNF_E_ARG; }
+  if (head == CNF_HEAD_EXTERNAL && ((N > 0 && (!gz || !gld)) || !partials)) { cnf_set_error("external head needs g_z, g_logdet, partials"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
   if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)d.grad_rows * d.n_packed * sizeof(float), st));
   if (N == 0) return CNF_OK;

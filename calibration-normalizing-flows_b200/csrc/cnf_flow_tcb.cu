@@ -665,7 +665,7 @@ extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* pack
   if (rc) return rc;
   if (desc->precision != CNF_PREC_BF16_TC) { cnf_set_error("cnf_nll_train_step_tc needs a CNF_PREC_BF16_TC descriptor"); return CNF_E_ARG; }
   if (!tb_dims(d, &t)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
-  if (!packed_tc || !tables || !y || !loss_acc || !workspace || N < 0) { cnf_set_error("cnf_nll_train_step_tc: null pointer / negative N"); return CNF_E_ARG; }
+  if (!packed_tc || !tables || (N > 0 && !y) || !loss_acc || !workspace || N < 0) { cnf_set_error("cnf_nll_train_step_tc: null pointer / negative N"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = tb_sms();
   if (sms <= 0) { cnf_set_error("no CUDA device"); return CNF_E_CUDA; }

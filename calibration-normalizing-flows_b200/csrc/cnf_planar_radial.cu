@@ -308,8 +308,9 @@ int set_smem(Kern k, size_t bytes) {
 
 extern "C" int cnf_planar_forward(const float* x, const float* w, const float* u_hat, const float* b, float* z,
                                   float* logdet, int64_t N, int32_t K, void* stream) {
-  if (!x || !w || !u_hat || !b || !z || !logdet || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_planar_forward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
-  if (N == 0) return CNF_OK;
+  if (N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_planar_forward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (N == 0) return CNF_OK;      // an empty batch may come with null data pointers
+  if (!x || !w || !u_hat || !b || !z || !logdet) { cnf_set_error("cnf_planar_forward: null pointer"); return CNF_E_ARG; }
   const size_t smem = (size_t)(2 * K + PR_WARPS * 32 * K) * sizeof(float);
   if (smem > 200 * 1024) { cnf_set_error("cnf_planar_forward: K=%d rows do not fit shared memory", K); return CNF_E_SMEM; }
   int grid = 1, rc;
@@ -324,7 +325,8 @@ extern "C" int cnf_planar_forward(const float* x, const float* w, const float* u
 extern "C" int cnf_planar_backward(const float* x, const float* g_z, const float* g_logdet, const float* w,
                                    const float* u_hat, const float* b, float* g_x, float* g_w, float* g_uhat, float* g_b,
                                    int64_t N, int32_t K, void* stream) {
-  if (!x || !g_z || !w || !u_hat || !b || !g_w || !g_uhat || !g_b || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_planar_backward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (!g_w || !g_uhat || !g_b || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_planar_backward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (N > 0 && (!x || !g_z || !w || !u_hat || !b)) { cnf_set_error("cnf_planar_backward: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(g_w, 0, K * sizeof(float), st));
   CNF_CHECK_CUDA(cudaMemsetAsync(g_uhat, 0, K * sizeof(float), st));
@@ -342,8 +344,9 @@ extern "C" int cnf_planar_backward(const float* x, const float* g_z, const float
 
 extern "C" int cnf_radial_forward(const float* x, const float* z0, const float* a, const float* b_hat, float* z,
                                   int64_t N, int32_t K, void* stream) {
-  if (!x || !z0 || !a || !b_hat || !z || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_radial_forward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_radial_forward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
   if (N == 0) return CNF_OK;
+  if (!x || !z0 || !a || !b_hat || !z) { cnf_set_error("cnf_radial_forward: null pointer"); return CNF_E_ARG; }
   const size_t smem = (size_t)(K + PR_WARPS * 32 * K) * sizeof(float);
   if (smem > 200 * 1024) { cnf_set_error("cnf_radial_forward: K=%d rows do not fit shared memory", K); return CNF_E_SMEM; }
   int grid = 1, rc;
@@ -357,7 +360,8 @@ extern "C" int cnf_radial_forward(const float* x, const float* z0, const float* 
 
 extern "C" int cnf_radial_backward(const float* x, const float* g_z, const float* z0, const float* a, const float* b_hat,
                                    float* g_x, float* g_z0, float* g_a, float* g_bhat, int64_t N, int32_t K, void* stream) {
-  if (!x || !g_z || !z0 || !a || !b_hat || !g_z0 || !g_a || !g_bhat || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_radial_backward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (!g_z0 || !g_a || !g_bhat || N < 0 || K < 1 || K > 32 * PR_MAXC) { cnf_set_error("cnf_radial_backward: bad argument (K <= %d)", 32 * PR_MAXC); return CNF_E_ARG; }
+  if (N > 0 && (!x || !g_z || !z0 || !a || !b_hat)) { cnf_set_error("cnf_radial_backward: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(g_z0, 0, K * sizeof(float), st));
   CNF_CHECK_CUDA(cudaMemsetAsync(g_a, 0, sizeof(float), st));

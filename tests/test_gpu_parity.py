@@ -455,3 +455,29 @@ def test_calibrator_fit_with_captured_cuda_graph_epochs_matches_eager(cuda_devic
     assert np.isfinite(out[True][0]).all()
     assert np.allclose(out[True][0], out[False][0], rtol=1e-6, atol=1e-7)
     assert np.max(np.abs(out[True][1] - out[False][1])) < 1e-6
+
+
+def test_empty_batches_on_every_path(cuda_device):
+    """N = 0: every entry point returns empty outputs / zero statistics instead of launching."""
+    import torch
+    import cnf_b200
+    g = load_golden('flow_c2_nvp_k10')
+    x0 = torch.zeros((0, 10), device=cuda_device)
+    y0 = torch.zeros(0, dtype=torch.int64, device=cuda_device)
+    for prec in ('fp32', 'bf16'):
+        flow = build_flow_from_golden(g, cuda_device, precision=prec)
+        with torch.no_grad():
+            zs, ld = flow(x0)
+            xs, ldi = flow.backward(zs[-1])
+        assert zs[-1].shape == (0, 10) and ld.numel() == 0 and xs[-1].shape == (0, 10)
+        eng = flow.engine()
+        eng.pack(tc=True)
+        acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+        eng.nll_step(x0, y0, acc, precision=prec)
+        assert float(acc.abs().sum()) == 0.0
+        assert float(eng.flat_grad.abs().sum()) == 0.0
+    for lay in (cnf_b200.PlanarLayer(10).to(cuda_device), cnf_b200.RadialLayer(10).to(cuda_device),
+                cnf_b200.AffineConstantLayer(10).to(cuda_device)):
+        with torch.no_grad():
+            z, _ = lay(x0)
+        assert z.shape == (0, 10)

@@ -201,6 +201,7 @@ def test_new_entry_points_validate_arguments_without_a_device():
     assert lib.cnf_planar_forward(one, one, one, one, one, one, 4, 0, None) == -1
     assert lib.cnf_planar_forward(one, one, one, one, one, one, 4, 513, None) == -1
     assert b'K <= 512' in lib.cnf_last_error()
+    assert lib.cnf_planar_forward(n, n, n, n, n, n, 0, 3, None) == 0          # empty batch: null pointers are fine
     assert lib.cnf_planar_backward(one, one, None, one, one, one, None, n, one, one, 4, 3, None) == -1
     assert lib.cnf_radial_forward(one, n, one, one, one, 4, 3, None) == -1
     assert lib.cnf_radial_backward(one, one, one, one, one, None, one, one, n, 4, 3, None) == -1
