@@ -481,3 +481,44 @@ def test_empty_batches_on_every_path(cuda_device):
         with torch.no_grad():
             z, _ = lay(x0)
         assert z.shape == (0, 10)
+
+
+def test_misaligned_views_take_the_scalar_paths(cuda_device):
+    """A contiguous row-slice x[1:] starts 4*K bytes into its storage (8-byte aligned for K=10): the 128-bit /
+    TMA fast paths must step aside and the results must not change."""
+    import torch
+    import cnf_b200
+    from cnf_b200.utils import metrics as M
+    g = load_golden('flow_c2_nvp_k10')
+    x, y = orc.synth_logits(3001, 10, seed=4)
+    big = torch.from_numpy(x).to(cuda_device)
+    view = big[1:]
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    copy = view.clone()
+    assert copy.data_ptr() % 16 == 0
+    yv = torch.from_numpy(y).to(cuda_device)[1:]
+    for prec in ('fp32', 'bf16'):
+        flow = build_flow_from_golden(g, cuda_device, precision=prec)
+        with torch.no_grad():
+            za, la = flow(view)
+            zb, lb = flow(copy)
+        assert torch.equal(za[-1], zb[-1]) and torch.equal(la, lb)
+        eng = flow.engine()
+        eng.pack(tc=True)
+        acc_a = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+        eng.nll_step(view, yv.contiguous(), acc_a, precision=prec)
+        ga = eng.flat_grad.clone()
+        acc_b = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+        eng.nll_step(copy, yv.contiguous(), acc_b, precision=prec)
+        assert torch.allclose(acc_a, acc_b, rtol=1e-12) and torch.allclose(ga, eng.flat_grad, rtol=1e-5, atol=1e-9)
+    for lay in (cnf_b200.PlanarLayer(10).to(cuda_device), cnf_b200.RadialLayer(10).to(cuda_device),
+                cnf_b200.AffineConstantLayer(10).to(cuda_device)):
+        with torch.no_grad():
+            za, _ = lay(view)
+            zb, _ = lay(copy)
+        assert torch.equal(za, zb)
+    pv = torch.softmax(view, dim=1)
+    big_p = torch.cat([pv[:1], pv])            # make a misaligned probability view
+    sa = M.statistics(big_p[1:], yv, bins=15)
+    sb = M.statistics(pv.clone(), yv, bins=15)
+    assert torch.allclose(sa, sb, rtol=1e-12, atol=0)
