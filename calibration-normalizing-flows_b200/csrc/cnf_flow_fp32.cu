@@ -617,6 +617,269 @@ __global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, c
 }
 
 // --------------------------------------------------------------------------------------
+// "Lean" training kernel for single-hidden-layer nets whose full tile plan does not fit shared memory
+// (wide K and/or wide hidden layers, e.g. K = 100, H = 512): flow_train_kernel keeps a tape of every
+// layer's pre-layer values (L*d0*TS floats) and a whole net's hidden activations (Hp*TS floats), which
+// at that shape leaves room for 32-sample tiles only -- one warp per SM.  Here
+//   * there is no tape: going backwards, a layer's input is recovered by inverting the layer,
+//     x = (y - t) * exp(-s), with s and t recomputed from the (unchanged) conditioning logits;
+//   * the hidden layer is processed in chunks of 16 units: recompute h -> 16 x TS shared-memory slab ->
+//     cooperative weight-gradient sums -> per-thread pre-activation gradient -> slab -> sums;
+//   * each chunk's weights (first-Linear columns, bias, last-Linear rows: (d1+1+d0) x 16 floats) are
+//     staged cooperatively in shared memory, so the per-thread FMA loops read them with broadcast
+//     LDS.128 instead of going to L2 through a nearly empty L1.
+// Same arithmetic per element as flow_train_kernel; the recovered layer inputs differ from taped ones by
+// fp32 rounding of the inversion (~1e-7 relative).
+// --------------------------------------------------------------------------------------
+struct LeanSmem { int tab, act, gact, outs_s, outs_t, gout_s, hc, wb, b1, total; };
+
+__host__ __device__ inline LeanSmem make_lean(const CnfDims& d, int TSP) {
+  LeanSmem s;
+  int off = 0;
+  s.tab = off; off += (d.n_tables + 3) / 4 * 4;
+  s.act = off; off += d.K * TSP;
+  s.gact = off; off += d.K * TSP;
+  s.outs_s = off; off += d.d0 * TSP;
+  s.outs_t = off; off += d.d0 * TSP;      // doubles as the t-net's output gradient in the backward pass
+  s.gout_s = off; off += d.d0 * TSP;
+  s.hc = off; off += CH * TSP;
+  s.wb = off; off += (d.d1 + 1 + d.d0) * CH;
+  s.b1 = off; off += (d.d0 + 3) / 4 * 4;
+  s.total = off;
+  return s;
+}
+
+// wb <- [W0[c][r0..r0+16) for c < d1 | b0[r0..) | W1[q][r0..) for q < d0] of one net (m == 1)
+__device__ __forceinline__ void stage_chunk(float* wb, const CnfDims& d, const float* __restrict__ Wn, int r0, int tid,
+                                            int NT) {
+  const int Hp = d.Hp[0];
+  const int n4 = (d.d1 + 1 + d.d0) * (CH / 4);
+  for (int i = tid; i < n4; i += NT) {
+    const int row = i / (CH / 4), c4 = i - row * (CH / 4);
+    const float* src = row < d.d1 ? Wn + d.w_off[0] + (size_t)row * Hp + r0
+                       : row == d.d1 ? Wn + d.b_off[0] + r0
+                                     : Wn + d.w_off[1] + (size_t)(row - d.d1 - 1) * Hp + r0;
+    reinterpret_cast<float4*>(wb)[i] = __ldg(reinterpret_cast<const float4*>(src) + c4);
+  }
+}
+
+// out[q][s] = net(act[cond])[q] for this thread's samples; block-cooperative (contains __syncthreads)
+template <int SPT>
+__device__ __forceinline__ void net_forward_lean(const CnfDims& d, const float* Wn, const float* act, const int* cond,
+                                                 float* out, float* wb, float* b1s, int TSP, int tid, int NT) {
+  const int Hp = d.Hp[0];
+  __syncthreads();
+  for (int q = tid; q < d.d0; q += NT) b1s[q] = __ldg(Wn + d.b_off[1] + q);
+  for (int r0 = 0; r0 < Hp; r0 += CH) {
+    if (r0) __syncthreads();            // every thread is done with the previous chunk's weights
+    stage_chunk(wb, d, Wn, r0, tid, NT);
+    __syncthreads();
+    float h[SPT][CH];
+    chunk_from_inputs<SPT, true>(h, wb, CH, wb + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int r = 0; r < CH; ++r) h[k][r] = fmaxf(h[k][r], 0.f);
+    chunk_to_outputs<SPT, true>(h, wb + (d.d1 + 1) * CH, CH, b1s, 0, d.d0, out, nullptr, r0 == 0, false, TSP, tid, NT);
+  }
+}
+
+// Backward of one net for the tile, chunk by chunk.  gout[q][s]: gradient on the net's outputs.
+template <int SPT>
+__device__ __forceinline__ void net_backward_lean(const CnfDims& d, const float* Wn, float* Gn, const float* act,
+                                                  const int* cond, const float* gout, float* hc, float* wb,
+                                                  float* gact, int TS, int TSP, int tid, int NT) {
+  const int Hp = d.Hp[0];
+  __syncthreads();                                    // gout is complete
+  wgrad_rowsum(Gn + d.b_off[1], gout, d.d0, TS, TSP, tid, NT);
+  for (int r0 = 0; r0 < Hp; r0 += CH) {
+    __syncthreads();                                  // previous chunk's slab and weights are free
+    stage_chunk(wb, d, Wn, r0, tid, NT);
+    __syncthreads();
+    float h[SPT][CH], g[SPT][CH];
+    chunk_from_inputs<SPT, true>(h, wb, CH, wb + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int r = 0; r < CH; ++r) {
+        h[k][r] = fmaxf(h[k][r], 0.f);
+        hc[r * TSP + tid + k * NT] = h[k][r];
+      }
+    __syncthreads();
+    // dW1[q][r0+r] += sum_s gout[q][s] h[r][s]
+    wgrad_outer(Gn + d.w_off[1] + r0, Hp, gout, nullptr, d.d0, hc, CH, nullptr, TS, TSP, tid, NT);
+    // g[r] = sum_q W1[q][r0+r] gout[q], masked by the ReLU
+    chunk_from_inputs<SPT, true>(g, wb + (d.d1 + 1) * CH, CH, nullptr, 0, d.d0, gout, nullptr, TSP, tid, NT);
+    __syncthreads();                                  // the weight-gradient pass has read the slab
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int r = 0; r < CH; ++r) {
+        g[k][r] = (h[k][r] > 0.f) ? g[k][r] : 0.f;
+        hc[r * TSP + tid + k * NT] = g[k][r];
+      }
+    // gact[cond[c]] += sum_r W0[c][r0+r] g[r]   (per thread, own samples)
+    chunk_to_outputs<SPT, true>(g, wb, CH, nullptr, 0, d.d1, gact, cond, false, true, TSP, tid, NT);
+    __syncthreads();
+    // dW0[c][r0+r] += sum_s act[cond[c]][s] g[r][s]; db0[r0+r] += sum_s g[r][s]
+    wgrad_outer(Gn + d.w_off[0] + r0, Hp, act, cond, d.d1, hc, CH, Gn + d.b_off[0] + r0, TS, TSP, tid, NT);
+  }
+  __syncthreads();
+}
+
+template <int SPT>
+__global__ void flow_train_lean_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                                       const float* __restrict__ xin, const int64_t* __restrict__ labels,
+                                       const float* __restrict__ gz_ext, const float* __restrict__ gld_ext,
+                                       float* __restrict__ gx_out, float* __restrict__ partials,
+                                       double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n,
+                                       int head) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[32];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TS = NT * SPT, TSP = TS + 4;
+  const bool do_bwd = (partials != nullptr);
+  const LeanSmem sm = make_lean(d, TSP);
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* gact = smem + sm.gact;
+  float* outs_s = smem + sm.outs_s;
+  float* outs_t = smem + sm.outs_t;
+  float* gout_s = smem + sm.gout_s;
+  float* gout_t = outs_t;
+  float* hc = smem + sm.hc;
+  float* wb = smem + sm.wb;
+  float* b1s = smem + sm.b1;
+  float* Grow = do_bwd ? partials + (size_t)(blockIdx.x % d.grad_rows) * d.n_packed : nullptr;
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  __syncthreads();
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    __syncthreads();
+    load_tile(act, xin, base, N, d.K, TS, TSP, nullptr, tid, NT);
+    if (head == CNF_HEAD_EXTERNAL) load_tile(gact, gz_ext, base, N, d.K, TS, TSP, pi_last, tid, NT);
+    __syncthreads();
+    float ld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) ld[k] = 0.f;
+    // ---- forward ----------------------------------------------------------------------
+    for (int l = 0; l < d.L; ++l) {
+      const int* cond = tab + d.tab_cond + l * d.d1;
+      const int* trans = tab + d.tab_trans + l * d.d0;
+      const float* Wl = packed + (size_t)l * d.layer_stride;
+      int slot = 0;
+      if (d.nets & 1) { net_forward_lean<SPT>(d, Wl, act, cond, outs_s, wb, b1s, TSP, tid, NT); ++slot; }
+      if (d.nets & 2) net_forward_lean<SPT>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, wb, b1s, TSP, tid, NT);
+      for (int q = 0; q < d.d0; ++q) {
+        const int p = trans[q];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const float sv = (d.nets & 1) ? outs_s[q * TSP + s] : 0.f;
+          const float tv = (d.nets & 2) ? outs_t[q * TSP + s] : 0.f;
+          act[p * TSP + s] = act[p * TSP + s] * expf(sv) + tv;
+          ld[k] += sv;
+        }
+      }
+    }
+    // ---- loss head (same as flow_train_kernel) ---------------------------------------------
+    float gld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int s = tid + k * NT;
+      const int64_t n = base + s;
+      const bool valid = n < N;
+      gld[k] = 0.f;
+      if (head == CNF_HEAD_NLL) {
+        float mx = -INFINITY;
+        for (int j = 0; j < d.K; ++j) mx = fmaxf(mx, act[pi_last[j] * TSP + s]);
+        float se = 0.f;
+        for (int j = 0; j < d.K; ++j) se += expf(act[pi_last[j] * TSP + s] - mx);
+        int yy = valid ? (int)labels[n] : 0;
+        yy = min(max(yy, 0), d.K - 1);
+        const float zy = act[pi_last[yy] * TSP + s];
+        const float inv_se = 1.f / se;
+        const float py = expf(zy - mx) * inv_se;
+        float ce, coef;
+        if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+        else            { ce = logf(py + eps); coef = py / (py + eps); }
+        if (valid) {
+          const float tot = ce + gamma * ld[k];
+          a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld[k];
+          if (!isfinite(tot)) a_bad += 1.0;
+        }
+        if (do_bwd) {
+          const float sc = valid ? -inv_n * coef : 0.f;
+          for (int j = 0; j < d.K; ++j) {
+            const int p = pi_last[j];
+            const float pj = expf(act[p * TSP + s] - mx) * inv_se;
+            gact[p * TSP + s] = sc * ((j == yy ? 1.f : 0.f) - pj);
+          }
+          gld[k] = valid ? -gamma * inv_n : 0.f;
+        }
+      } else {
+        gld[k] = valid ? gld_ext[n] : 0.f;
+      }
+    }
+    // ---- backward, recovering each layer's input by inverting the layer -------------------------
+    if (do_bwd) {
+      for (int l = d.L - 1; l >= 0; --l) {
+        const int* cond = tab + d.tab_cond + l * d.d1;
+        const int* trans = tab + d.tab_trans + l * d.d0;
+        const float* Wl = packed + (size_t)l * d.layer_stride;
+        float* Gl = Grow + (size_t)l * d.layer_stride;
+        int slot = 0;
+        if (d.nets & 1) { net_forward_lean<SPT>(d, Wl, act, cond, outs_s, wb, b1s, TSP, tid, NT); ++slot; }
+        if (d.nets & 2) net_forward_lean<SPT>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, wb, b1s, TSP, tid, NT);
+        for (int q = 0; q < d.d0; ++q) {
+          const int p = trans[q];
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) {
+            const int s = tid + k * NT;
+            const float sv = (d.nets & 1) ? outs_s[q * TSP + s] : 0.f;
+            const float tv = (d.nets & 2) ? outs_t[q * TSP + s] : 0.f;
+            const float es = expf(sv);
+            const float xv = (act[p * TSP + s] - tv) * expf(-sv);
+            const float gy = gact[p * TSP + s];
+            act[p * TSP + s] = xv;                       // the input of layer l
+            gout_s[q * TSP + s] = gy * xv * es + gld[k];
+            gout_t[q * TSP + s] = gy;                    // overwrites t (already consumed)
+            gact[p * TSP + s] = gy * es;
+          }
+        }
+        slot = 0;
+        if (d.nets & 1) {
+          net_backward_lean<SPT>(d, Wl, Gl, act, cond, gout_s, hc, wb, gact, TS, TSP, tid, NT);
+          ++slot;
+        }
+        if (d.nets & 2)
+          net_backward_lean<SPT>(d, Wl + (size_t)slot * d.net_stride, Gl + (size_t)slot * d.net_stride, act, cond, gout_t,
+                                 hc, wb, gact, TS, TSP, tid, NT);
+      }
+      if (gx_out != nullptr) {
+        __syncthreads();
+        store_tile(gact, gx_out, base, N, d.K, TS, TSP, nullptr, tid, NT);
+      }
+    }
+  }
+  if (loss_acc != nullptr && head == CNF_HEAD_NLL) {
+    double t0 = block_sum(a_loss, red, tid, NT);
+    double t1 = block_sum(a_ce, red, tid, NT);
+    double t2 = block_sum(a_ld, red, tid, NT);
+    double t3 = block_sum(a_bad, red, tid, NT);
+    if (tid == 0) {
+      atomicAdd(loss_acc + 0, t0);
+      atomicAdd(loss_acc + 1, t1);
+      atomicAdd(loss_acc + 2, t2);
+      atomicAdd(loss_acc + 3, t3);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
 // launch plumbing
 // --------------------------------------------------------------------------------------
 struct LaunchCfg { int spt, nt; bool ws; size_t smem; };
@@ -711,7 +974,26 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
   LaunchCfg c;
-  if ((rc = choose_cfg(d, true, &c))) return rc;
+  c.nt = 0; c.spt = 1; c.ws = false; c.smem = 0;
+  rc = choose_cfg(d, true, &c);
+  // single-hidden-layer nets whose full plan only fits narrow tiles (or does not fit at all): lean kernel
+  if (d.m == 1 && (rc != CNF_OK || c.nt * c.spt < 128) && !getenv("CNF_NO_LEAN_TRAIN")) {
+    for (int nt = 256; nt >= 64; nt >>= 1) {
+      const size_t bytes = (size_t)make_lean(d, nt + 4).total * sizeof(float);
+      if ((long long)bytes > g_max_smem - 1024) continue;
+      const int64_t ntl = (N + nt - 1) / nt;
+      int per_sm = (int)(g_max_smem / (bytes + 2048));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+      const int64_t capl = (int64_t)g_num_sms * per_sm;
+      const int gridl = (int)(ntl < capl ? ntl : capl);
+      if ((rc = set_smem(flow_train_lean_kernel<1>, bytes))) return rc;
+      flow_train_lean_kernel<1><<<gridl, nt, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc, N, eps,
+                                                          gamma, inv_n, head);
+      CNF_CHECK_CUDA(cudaGetLastError());
+      return CNF_OK;
+    }
+  }
+  if (rc) return rc;
   const int64_t ntiles = (N + c.nt * c.spt - 1) / (c.nt * c.spt);
   int ctas_per_sm = (int)(g_max_smem / (c.smem + 2048));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
