@@ -879,6 +879,78 @@ __global__ void flow_train_lean_kernel(CnfDims d, const float* __restrict__ pack
   }
 }
 
+// Forward / inverse counterpart of the lean training kernel: same staged 16-unit weight chunks, no
+// hidden-activation storage.  Used for single-hidden-layer nets whose weights do not fit shared memory.
+template <int SPT>
+__global__ void flow_apply_lean_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                                       const float* __restrict__ xin, float* __restrict__ zout,
+                                       float* __restrict__ logdet, float* __restrict__ zs, int64_t N, int inverse) {
+  extern __shared__ __align__(16) float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TS = NT * SPT, TSP = TS + 4;
+  int off = 0;
+  int* tab = reinterpret_cast<int*>(smem + off); off += (d.n_tables + 3) / 4 * 4;
+  float* act = smem + off; off += d.K * TSP;
+  float* outs_s = smem + off; off += d.d0 * TSP;
+  float* outs_t = smem + off; off += d.d0 * TSP;
+  float* wb = smem + off; off += (d.d1 + 1 + d.d0) * CH;
+  float* b1s = smem + off;
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  __syncthreads();
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    __syncthreads();
+    load_tile(act, xin, base, N, d.K, TS, TSP, inverse ? pi_last : nullptr, tid, NT);
+    __syncthreads();
+    float ld[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) ld[k] = 0.f;
+    for (int li = 0; li < d.L; ++li) {
+      const int l = inverse ? d.L - 1 - li : li;
+      const int* cond = tab + d.tab_cond + l * d.d1;
+      const int* trans = tab + d.tab_trans + l * d.d0;
+      const float* Wl = packed + (size_t)l * d.layer_stride;
+      int slot = 0;
+      if (d.nets & 1) { net_forward_lean<SPT>(d, Wl, act, cond, outs_s, wb, b1s, TSP, tid, NT); ++slot; }
+      if (d.nets & 2) net_forward_lean<SPT>(d, Wl + (size_t)slot * d.net_stride, act, cond, outs_t, wb, b1s, TSP, tid, NT);
+      for (int q = 0; q < d.d0; ++q) {
+        const int p = trans[q];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const float xv = act[p * TSP + s];
+          const float sv = (d.nets & 1) ? outs_s[q * TSP + s] : 0.f;
+          const float tv = (d.nets & 2) ? outs_t[q * TSP + s] : 0.f;
+          float yv;
+          if (!inverse) { yv = xv * expf(sv) + tv; ld[k] += sv; }
+          else          { yv = (xv - tv) * expf(-sv); ld[k] -= sv; }
+          act[p * TSP + s] = yv;
+        }
+      }
+      if (zs != nullptr) {
+        const int* pi = tab + d.tab_pi + (inverse ? l : l + 1) * d.K;
+        float* dst = zs + (size_t)li * N * d.K;
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          const int64_t n = base + s;
+          if (n < N)
+            for (int j = 0; j < d.K; ++j) dst[n * d.K + j] = act[pi[j] * TSP + s];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int64_t n = base + tid + k * NT;
+      if (n < N) logdet[n] = ld[k];
+    }
+    __syncthreads();
+    store_tile(act, zout, base, N, d.K, TS, TSP, inverse ? nullptr : pi_last, tid, NT);
+  }
+}
+
 // --------------------------------------------------------------------------------------
 // launch plumbing
 // --------------------------------------------------------------------------------------
@@ -939,7 +1011,28 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
   LaunchCfg c;
-  if ((rc = choose_cfg(d, false, &c))) return rc;
+  c.nt = 0; c.spt = 1; c.ws = false; c.smem = 0;
+  rc = choose_cfg(d, false, &c);
+  // single-hidden-layer nets whose weights do not fit shared memory: staged-chunk kernel instead of L1 reads
+  if (d.m == 1 && (rc != CNF_OK || !c.ws) && !getenv("CNF_NO_LEAN_TRAIN")) {
+    for (int nt = 256; nt >= 64; nt >>= 1) {
+      const int TSP = nt + 4;
+      const size_t bytes = ((size_t)(d.n_tables + 3) / 4 * 4 + (size_t)d.K * TSP + 2 * (size_t)d.d0 * TSP +
+                            (size_t)(d.d1 + 1 + d.d0) * CNF_CH + (size_t)(d.d0 + 3) / 4 * 4) * sizeof(float);
+      if ((long long)bytes > (g_max_smem - 1024) / 2 && nt > 64) continue;      // two CTAs per SM when possible
+      if ((long long)bytes > g_max_smem - 1024) continue;
+      const int64_t ntl = (N + nt - 1) / nt;
+      int per_sm = (int)(g_max_smem / (bytes + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+      const int64_t capl = (int64_t)g_num_sms * per_sm;
+      const int gridl = (int)(ntl < capl ? ntl : capl);
+      if ((rc = set_smem(flow_apply_lean_kernel<1>, bytes))) return rc;
+      flow_apply_lean_kernel<1><<<gridl, nt, bytes, st>>>(d, packed, tables, x, z, logdet, zs, N, inverse);
+      CNF_CHECK_CUDA(cudaGetLastError());
+      return CNF_OK;
+    }
+  }
+  if (rc) return rc;
   const int64_t ntiles = (N + c.nt * c.spt - 1) / (c.nt * c.spt);
   int ctas_per_sm = (int)(g_max_smem / (c.smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
