@@ -436,7 +436,36 @@ def run_ours(args):
                                        'streamed-weight tcgen05 kernel',
                                'tensor_tflops_minimal': c4_flops * n4 / (c4_ms * 1e-3) / 1e12,
                                'frac_of_bf16_peak': c4_flops * n4 / (c4_ms * 1e-3) / 1e12 / peaks()[1]}
-        del x4, z4, l4
+        # the same shape through the fp32 kernels (the 1e-5 parity path and the only training path for wide
+        # shapes): forward on 200,000 samples, full NLL + Adam training step on 100,000
+        n4f = 200_000
+        c4.flow.precision = 'fp32'
+        with torch.no_grad():
+            c4(x4[:n4f])
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                c4(x4[:n4f])
+            f1.record()
+        barrier()
+        c4f_ms = max_over_ranks(f0.elapsed_time(f1)) / 3
+        n4t = 100_000
+        y4 = torch.randint(0, 100, (n4t,), generator=g4, device=dev)
+        tr4 = cnf_b200.FusedNLLTrainer(e4, x4[:n4t].contiguous(), y4, n_total=n4t * world)
+        tr4.step()
+        t40, t41 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t40.record()
+        for _ in range(3):
+            tr4.step()
+        t41.record()
+        barrier()
+        c4t_ms = max_over_ranks(t40.elapsed_time(t41)) / 3
+        extra['c4_fp32'] = {'forward': {'value': world * n4f / (c4f_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4f_ms},
+                            'train_step': {'value': world * n4t / (c4t_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4t_ms},
+                            'dtype': 'f32',
+                            'what': 'C4 shape on the lean fp32 kernels (16-unit hidden chunks, chunk weights staged in '
+                                    'shared memory, no tape): forward on 200,000 samples, NLL + Adam step on 100,000'}
+        del x4, z4, l4, tr4
         # config C1 through the calibrator API (rank 0, N=1 only): NICE, K=3, N=10,000, 4 additive couplings,
         # hidden 32, fit (50 full-batch epochs) + predict, host numpy in and out (calibrators.py:241-353)
         if rank == 0 and world == 1:
@@ -529,6 +558,21 @@ def run_ours(args):
                     'sample': '50 full-batch steps on 10,000 samples: torch autograd + Adam on the reference op '
                               'sequence WITHOUT its DataLoader (calibrators.py:268-283 collates per sample, which '
                               'dominates the reference at this size, SURVEY.md 6)'}
+            if 'c4_fp32' in extra:
+                g4c = torch.Generator().manual_seed(6)
+                n4c = 5_000
+                x4c = 1.5 * torch.randn(n4c, 100, generator=g4c)
+                y4c = torch.randint(0, 100, (n4c,), generator=g4c)
+                n4p = 8 * 2 * (512 * 100 + 512 + 100 * 512 + 100)
+                st4 = rp.TrainState(0.001 * torch.randn(n4p, generator=g4c), 100, 8, [512])
+                st4.step(x4c, y4c)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    st4.step(x4c, y4c)
+                dt4 = (time.perf_counter() - t0) / 2
+                extra['c4_fp32']['train_step']['cpu_baseline'] = {
+                    'value': n4c / dt4, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'sample': '5,000 samples x 2 full-batch steps, torch autograd + Adam on the reference op sequence'}
             n_mc = 2_000_000
             xm, ym_c = synth(n_mc, 17)
             pm_c = torch.softmax(xm, dim=1).numpy()
