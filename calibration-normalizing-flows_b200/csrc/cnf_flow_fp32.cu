@@ -1070,13 +1070,16 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   c.nt = 0; c.spt = 1; c.ws = false; c.smem = 0;
   rc = choose_cfg(d, true, &c);
   // single-hidden-layer nets whose full plan only fits narrow tiles (or does not fit at all): lean kernel
-  if (d.m == 1 && (rc != CNF_OK || c.nt * c.spt < 128) && !getenv("CNF_NO_LEAN_TRAIN")) {
-    for (int nt = 256; nt >= 64; nt >>= 1) {
+  const char* force_lean = getenv("CNF_FORCE_LEAN");      // experiment switch: "<nt>" forces the lean kernel with that tile
+  if (d.m == 1 && (rc != CNF_OK || c.nt * c.spt < 128 || force_lean) && !getenv("CNF_NO_LEAN_TRAIN")) {
+    for (int nt = force_lean ? atoi(force_lean) : 256; nt >= 64; nt >>= 1) {
       const size_t bytes = (size_t)make_lean(d, nt + 4).total * sizeof(float);
       if ((long long)bytes > g_max_smem - 1024) continue;
       const int64_t ntl = (N + nt - 1) / nt;
       int per_sm = (int)(g_max_smem / (bytes + 2048));
-      per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+      const int max_threads = 2048 / nt;
+      per_sm = per_sm < 1 ? 1 : (per_sm > max_threads ? max_threads : per_sm);
+      if (per_sm > 8) per_sm = 8;
       const int64_t capl = (int64_t)g_num_sms * per_sm;
       const int gridl = (int)(ntl < capl ? ntl : capl);
       if ((rc = set_smem(flow_train_lean_kernel<1>, bytes))) return rc;

@@ -522,3 +522,49 @@ def test_misaligned_views_take_the_scalar_paths(cuda_device):
     sa = M.statistics(big_p[1:], yv, bins=15)
     sb = M.statistics(pv.clone(), yv, bins=15)
     assert torch.allclose(sa, sb, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('K,L,H,scale,shift,N', [(100, 2, 512, True, True, 300), (100, 3, 100, False, True, 517),
+                                                 (33, 2, 700, True, False, 129), (4, 3, 888, True, True, 1000)])
+def test_lean_kernels_for_wide_shapes_vs_oracle(K, L, H, scale, shift, N, cuda_device):
+    """Shapes whose weights / tape / hidden activations do not fit the regular fp32 plan run on the lean
+    kernels (staged 16-unit chunks, no tape): forward, inverse, the fused NLL step and autograd through the
+    drop-in Flow, all against the float64 oracle."""
+    import torch
+    import cnf_b200
+    torch.manual_seed(K + H)
+    layers = [cnf_b200.NvpCouplingLayer(K, [H], scale=scale, shift=shift) for _ in range(L)]
+    flow = cnf_b200.Flow(layers)
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(100.0)
+    like = orc.init_params(K, L, [H], scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    x, y = orc.synth_logits(N, K, seed=K)
+    flow.to(cuda_device)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+    with torch.no_grad():
+        zs, ld = flow(xt)
+        xs, _ = flow.backward(zs[-1])
+    assert rel_err(zs[-1].cpu().numpy(), zo[-1]) < TOL
+    assert ld_err(ld.cpu().numpy().reshape(-1), ldo) < TOL
+    assert rel_err(zs[0].cpu().numpy(), zo[0]) < TOL            # intermediates (second launch)
+    assert rel_err(xs[-1].cpu().numpy(), x) < 1e-4
+    eng = flow.engine()
+    eng.pack()
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc)
+    loss, _, _, grads, _ = orc.train_step_grads(params, x.astype(np.float64), y)
+    go = orc.flatten(grads)
+    assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+    assert rel_err(eng.flat_grad.cpu().numpy(), go) < 5e-4
+    # autograd through the drop-in modules (external upstream gradients, g_x returned)
+    xg = xt.clone().requires_grad_(True)
+    zs2, ld2 = flow(xg)
+    (zs2[-1].square().sum() * 1e-3 + ld2.sum()).backward()
+    gz = 2e-3 * zo[-1]
+    _, gx_o = orc.flow_backward(params, x.astype(np.float64), gz, np.ones(N))
+    assert rel_err(xg.grad.cpu().numpy(), gx_o) < 5e-4
