@@ -643,7 +643,7 @@ __host__ __device__ inline LeanSmem make_lean(const CnfDims& d, int TSP) {
   s.outs_t = off; off += d.d0 * TSP;      // doubles as the t-net's output gradient in the backward pass
   s.gout_s = off; off += d.d0 * TSP;
   s.hc = off; off += CH * TSP;
-  s.wb = off; off += (d.d1 + 1 + d.d0) * CH;
+  s.wb = off; off += 2 * (d.d1 + 1 + d.d0) * CH;      // two chunk buffers: the next chunk lands while this one is used
   s.b1 = off; off += (d.d0 + 3) / 4 * 4;
   s.total = off;
   return s;
@@ -693,6 +693,19 @@ __device__ __forceinline__ void store_chunk(float* wb, const float4 (&pf)[LEAN_P
   }
 }
 
+// cp.async variant: no registers held across the chunk's compute (the training kernel has none to spare)
+__device__ __forceinline__ void stage_chunk_async(float* wb, const CnfDims& d, const float* __restrict__ Wn, int r0,
+                                                  int tid, int NT) {
+  const int n4 = (d.d1 + 1 + d.d0) * (CH / 4);
+  for (int i = tid; i < n4; i += NT) {
+    const int row = i / (CH / 4), c4 = i - row * (CH / 4);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float4*>(wb) + i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(chunk_src(d, Wn, r0, row)) + c4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // out[q][s] = net(act[cond])[q] for this thread's samples; block-cooperative (contains __syncthreads)
 template <int SPT, bool PRE>
 __device__ __forceinline__ void net_forward_lean(const CnfDims& d, const float* Wn, const float* act, const int* cond,
@@ -705,22 +718,32 @@ __device__ __forceinline__ void net_forward_lean(const CnfDims& d, const float* 
   const bool pre = PRE && (d.d1 + 1 + d.d0) * (CH / 4) <= LEAN_PF * NT;
   float4 pf[LEAN_PF];
   if (pre) fetch_chunk(pf, d, Wn, 0, tid, NT);
+  const int wbsz = (d.d1 + 1 + d.d0) * CH;
+  float* wcur = wb;
+  if (!PRE) stage_chunk_async(wb, d, Wn, 0, tid, NT);
   for (int r0 = 0; r0 < Hp; r0 += CH) {
-    if (r0) __syncthreads();            // every thread is done with the previous chunk's weights
-    if (pre) {
-      store_chunk(wb, pf, d, tid, NT);
-      if (r0 + CH < Hp) fetch_chunk(pf, d, Wn, r0 + CH, tid, NT);     // in flight during this chunk's FMAs
-    } else {
-      stage_chunk(wb, d, Wn, r0, tid, NT);
+    if (PRE) {
+      if (r0) __syncthreads();          // every thread is done with the previous chunk's weights
+      if (pre) {
+        store_chunk(wb, pf, d, tid, NT);
+        if (r0 + CH < Hp) fetch_chunk(pf, d, Wn, r0 + CH, tid, NT);     // in flight during this chunk's FMAs
+      } else {
+        stage_chunk(wb, d, Wn, r0, tid, NT);
+      }
+      __syncthreads();
+    } else {                            // two buffers: chunk r0 has landed, chunk r0+16 starts flying
+      stage_wait();
+      __syncthreads();
+      if (r0 + CH < Hp) stage_chunk_async(wcur == wb ? wb + wbsz : wb, d, Wn, r0 + CH, tid, NT);
     }
-    __syncthreads();
     float h[SPT][CH];
-    chunk_from_inputs<SPT, true>(h, wb, CH, wb + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
+    chunk_from_inputs<SPT, true>(h, wcur, CH, wcur + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
       for (int r = 0; r < CH; ++r) h[k][r] = fmaxf(h[k][r], 0.f);
-    chunk_to_outputs<SPT, true>(h, wb + (d.d1 + 1) * CH, CH, b1s, 0, d.d0, out, nullptr, r0 == 0, false, TSP, tid, NT);
+    chunk_to_outputs<SPT, true>(h, wcur + (d.d1 + 1) * CH, CH, b1s, 0, d.d0, out, nullptr, r0 == 0, false, TSP, tid, NT);
+    if (!PRE) wcur = (wcur == wb) ? wb + wbsz : wb;
   }
 }
 
@@ -732,12 +755,17 @@ __device__ __forceinline__ void net_backward_lean(const CnfDims& d, const float*
   const int Hp = d.Hp[0];
   __syncthreads();                                    // gout is complete
   wgrad_rowsum(Gn + d.b_off[1], gout, d.d0, TS, TSP, tid, NT);
+  const int wbsz = (d.d1 + 1 + d.d0) * CH;
+  float* wcur = wb;
+  stage_chunk_async(wb, d, Wn, 0, tid, NT);
   for (int r0 = 0; r0 < Hp; r0 += CH) {
-    __syncthreads();                                  // previous chunk's slab and weights are free
-    stage_chunk(wb, d, Wn, r0, tid, NT);
-    __syncthreads();
+    stage_wait();
+    __syncthreads();                                  // chunk r0 has landed; previous chunk's slab and weights are free
+    if (r0 + CH < Hp) stage_chunk_async(wcur == wb ? wb + wbsz : wb, d, Wn, r0 + CH, tid, NT);
+    float* const wbc = wcur;
+    wcur = (wcur == wb) ? wb + wbsz : wb;
     float h[SPT][CH], g[SPT][CH];
-    chunk_from_inputs<SPT, true>(h, wb, CH, wb + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
+    chunk_from_inputs<SPT, true>(h, wbc, CH, wbc + d.d1 * CH, 0, d.d1, act, cond, TSP, tid, NT);
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
@@ -749,7 +777,7 @@ __device__ __forceinline__ void net_backward_lean(const CnfDims& d, const float*
     // dW1[q][r0+r] += sum_s gout[q][s] h[r][s]
     wgrad_outer(Gn + d.w_off[1] + r0, Hp, gout, nullptr, d.d0, hc, CH, nullptr, TS, TSP, tid, NT);
     // g[r] = sum_q W1[q][r0+r] gout[q], masked by the ReLU
-    chunk_from_inputs<SPT, true>(g, wb + (d.d1 + 1) * CH, CH, nullptr, 0, d.d0, gout, nullptr, TSP, tid, NT);
+    chunk_from_inputs<SPT, true>(g, wbc + (d.d1 + 1) * CH, CH, nullptr, 0, d.d0, gout, nullptr, TSP, tid, NT);
     __syncthreads();                                  // the weight-gradient pass has read the slab
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
@@ -759,7 +787,7 @@ __device__ __forceinline__ void net_backward_lean(const CnfDims& d, const float*
         hc[r * TSP + tid + k * NT] = g[k][r];
       }
     // gact[cond[c]] += sum_r W0[c][r0+r] g[r]   (per thread, own samples)
-    chunk_to_outputs<SPT, true>(g, wb, CH, nullptr, 0, d.d1, gact, cond, false, true, TSP, tid, NT);
+    chunk_to_outputs<SPT, true>(g, wbc, CH, nullptr, 0, d.d1, gact, cond, false, true, TSP, tid, NT);
     __syncthreads();
     // dW0[c][r0+r] += sum_s act[cond[c]][s] g[r][s]; db0[r0+r] += sum_s g[r][s]
     wgrad_outer(Gn + d.w_off[0] + r0, Hp, act, cond, d.d1, hc, CH, Gn + d.b_off[0] + r0, TS, TSP, tid, NT);
