@@ -58,10 +58,11 @@ __host__ __device__ inline int hid_rows(const CnfDims& d, bool store_last) {
   return r;
 }
 
-__host__ __device__ inline Smem make_smem(const CnfDims& d, int TSP, bool ws, bool backward) {
+// ws: 0 = weights stay in global memory, 1 = all layers staged once, 2 = one layer staged at a time
+__host__ __device__ inline Smem make_smem(const CnfDims& d, int TSP, int ws, bool backward) {
   Smem s;
   int off = 0;
-  s.w = off; off += ws ? d.n_packed : 0;
+  s.w = off; off += ws == 1 ? d.n_packed : (ws == 2 ? (int)d.layer_stride : 0);
   s.tab = off; off += (d.n_tables + 3) / 4 * 4;
   s.act = off; off += d.K * TSP;
   s.outs = off; off += 2 * d.d0 * TSP;
@@ -311,13 +312,24 @@ __global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, c
 // training: forward + loss head + backward, one pass
 // --------------------------------------------------------------------------------------
 // G[a*ldg + b] += sum_s A[rowA(a)][s] * B[b][s]   (a < na, b < nb), atomics on global.
+// One work item = one b and a block of 8 a's.  With fewer items than threads the sample loop of an item is
+// split over nseg adjacent lanes (interleaved float4s, so a group still reads contiguous shared memory) and
+// the partial sums are folded with shuffles before the atomics.
 __device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, const int* idxA, int na,
                                             const float* B, int nb, float* Gbias_b, int TS, int TSP, int tid,
                                             int NT) {
   constexpr int AB = 8;
   const int nablk = (na + AB - 1) / AB;
   const int items = nb * nablk;
-  for (int it = tid; it < items; it += NT) {
+  const int ts4 = TS >> 2;
+  int nseg = 1;
+  while (nseg < 32 && items * nseg * 2 <= NT && (ts4 % (nseg * 2)) == 0) nseg <<= 1;
+  const int seg = tid & (nseg - 1);
+  const int groups = NT / nseg;
+  for (int it0 = 0; it0 < items; it0 += groups) {      // block-uniform trip count: every lane reaches the shuffles
+    const int it_raw = it0 + tid / nseg;
+    const bool on = it_raw < items;
+    const int it = on ? it_raw : items - 1;
     const int b = it % nb, ablk = it / nb;
     const int a0 = ablk * AB;
     const int an = min(AB, na - a0);
@@ -332,7 +344,8 @@ __device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, c
       rowA[a] = (idxA ? idxA[aa] : aa) * TSP;
     }
     const float* Brow = B + b * TSP;
-    for (int s = 0; s < TS; s += 4) {
+    for (int s4 = seg; s4 < ts4; s4 += nseg) {
+      const int s = s4 << 2;
       const float4 bv = *reinterpret_cast<const float4*>(Brow + s);
       bsum += (bv.x + bv.y) + (bv.z + bv.w);
 #pragma unroll
@@ -344,10 +357,17 @@ __device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, c
         acc[a] = fmaf(av.w, bv.w, acc[a]);
       }
     }
+    for (int o = nseg >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int a = 0; a < AB; ++a)
-      if (a < an) atomicAdd(G + (size_t)(a0 + a) * ldg + b, acc[a]);
-    if (Gbias_b != nullptr && ablk == 0) atomicAdd(Gbias_b + b, bsum);
+      for (int a = 0; a < AB; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    }
+    if (on && seg == 0) {
+#pragma unroll
+      for (int a = 0; a < AB; ++a)
+        if (a < an) atomicAdd(G + (size_t)(a0 + a) * ldg + b, acc[a]);
+      if (Gbias_b != nullptr && ablk == 0) atomicAdd(Gbias_b + b, bsum);
+    }
   }
 }
 
@@ -456,13 +476,15 @@ __global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, c
                                   const float* __restrict__ gz_ext, const float* __restrict__ gld_ext,
                                   float* __restrict__ gx_out, float* __restrict__ partials,
                                   double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n,
-                                  int head) {
+                                  int head, int wl) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[32];
   const int NT = blockDim.x, tid = threadIdx.x;
   const int TS = NT * SPT, TSP = TS + 4;
   const bool do_bwd = (partials != nullptr);
-  const Smem sm = make_smem(d, TSP, WS, true);
+  // wl (with WS): only the current coupling layer's weights are in shared memory, restaged at every layer
+  // boundary; the room this frees goes into a wider tile (twice the resident warps at the C2 shape)
+  const Smem sm = make_smem(d, TSP, WS ? (wl ? 2 : 1) : 0, true);
   int* tab = reinterpret_cast<int*>(smem + sm.tab);
   float* act = smem + sm.act;
   float* outs_s = smem + sm.outs;
@@ -475,11 +497,16 @@ __global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, c
   float* gbuf = smem + sm.gbuf;
   const float* W = WS ? smem + sm.w : packed;
   float* Grow = do_bwd ? partials + (size_t)(blockIdx.x % d.grad_rows) * d.n_packed : nullptr;
-  if (WS) coop_copy(smem + sm.w, packed, d.n_packed, tid, NT);
+  if (WS && !wl) coop_copy(smem + sm.w, packed, d.n_packed, tid, NT);
   for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
   __syncthreads();
   const int* pi_last = tab + d.tab_pi + d.L * d.K;
   const int64_t ntiles = (N + TS - 1) / TS;
+  auto stage_layer = [&](int l) {
+    __syncthreads();   // every thread is done with the layer staged before
+    coop_copy(smem + sm.w, packed + (size_t)l * d.layer_stride, (int)d.layer_stride, tid, NT);
+    __syncthreads();
+  };
   double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t base = tile * TS;
@@ -493,7 +520,8 @@ __global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, c
     for (int l = 0; l < d.L; ++l) {
       const int* cond = tab + d.tab_cond + l * d.d1;
       const int* trans = tab + d.tab_trans + l * d.d0;
-      const float* Wl = W + (size_t)l * d.layer_stride;
+      if (WS && wl) stage_layer(l);
+      const float* Wl = (WS && wl) ? W : W + (size_t)l * d.layer_stride;
       int slot = 0;
       if (d.nets & 1) { net_forward<SPT, WS>(d, Wl, act, cond, outs_s, hid, false, true, TSP, tid, NT); ++slot; }
       if (d.nets & 2)
@@ -556,7 +584,8 @@ __global__ void flow_train_kernel(CnfDims d, const float* __restrict__ packed, c
       for (int l = d.L - 1; l >= 0; --l) {
         const int* cond = tab + d.tab_cond + l * d.d1;
         const int* trans = tab + d.tab_trans + l * d.d0;
-        const float* Wl = W + (size_t)l * d.layer_stride;
+        if (WS && wl && l != d.L - 1) stage_layer(l);   // the forward pass left layer L-1 staged
+        const float* Wl = (WS && wl) ? W : W + (size_t)l * d.layer_stride;
         float* Gl = Grow + (size_t)l * d.layer_stride;
         int slot = 0;
         if (d.nets & 1) {
@@ -1022,7 +1051,7 @@ __global__ void flow_apply_lean_kernel(CnfDims d, const float* __restrict__ pack
 // --------------------------------------------------------------------------------------
 // launch plumbing
 // --------------------------------------------------------------------------------------
-struct LaunchCfg { int spt, nt; bool ws; size_t smem; };
+struct LaunchCfg { int spt, nt; bool ws; int wl; size_t smem; };
 
 int g_max_smem = -1, g_num_sms = -1;
 
@@ -1045,13 +1074,27 @@ int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out) {
   // resident warps per SM at the C2 shape, 1.83 -> 1.34 ms per 2^20 samples on B200
   int nt_max = 256;
   if (const char* v = getenv("CNF_FP32_NT")) { const int n = atoi(v); if (n == 256 || n == 128) nt_max = n; }
-  for (int ws = 1; ws >= 0; --ws)
+  int ws_first = 1;
+  if (const char* v = getenv("CNF_FP32_WS")) ws_first = atoi(v) ? 1 : 0;   // experiment switch: 0 = never stage the weights
+  out->wl = 0;
+  // training: a full-width tile with one layer's weights staged at a time beats a narrower tile with all of them
+  if (backward && ws_first && !getenv("CNF_FP32_NO_WL")) {
+    for (int mode = 1; mode <= 2; ++mode) {
+      const int TSP = nt_max + 4;
+      const size_t bytes = (size_t)make_smem(d, TSP, mode, true).total * 4;
+      if ((long long)bytes <= budget) {
+        out->spt = 1; out->nt = nt_max; out->ws = true; out->wl = mode == 2; out->smem = bytes;
+        return CNF_OK;
+      }
+    }
+  }
+  for (int ws = ws_first; ws >= 0; --ws)
     for (int nt = nt_max; nt >= 32; nt >>= 1)
       for (int si = 0; si < 2; ++si) {
         const int spt = spts[si];
         if (nt < 128 && spt > 1) continue;
         const int TSP = nt * spt + 4;
-        const Smem sm = make_smem(d, TSP, ws != 0, backward);
+        const Smem sm = make_smem(d, TSP, ws, backward);
         const size_t bytes = (size_t)sm.total * 4;
         if ((long long)bytes <= budget) {
           out->spt = spt; out->nt = nt; out->ws = ws != 0; out->smem = bytes;
@@ -1079,7 +1122,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
   LaunchCfg c;
-  c.nt = 0; c.spt = 1; c.ws = false; c.smem = 0;
+  c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, false, &c);
   // single-hidden-layer nets whose weights do not fit shared memory: staged-chunk kernel instead of L1 reads
   if (d.m == 1 && (rc != CNF_OK || !c.ws) && !getenv("CNF_NO_LEAN_TRAIN")) {
@@ -1135,7 +1178,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
   LaunchCfg c;
-  c.nt = 0; c.spt = 1; c.ws = false; c.smem = 0;
+  c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, true, &c);
   // single-hidden-layer nets whose full plan only fits narrow tiles (or does not fit at all): lean kernel
   const char* force_lean = getenv("CNF_FORCE_LEAN");      // experiment switch: "<nt>" forces the lean kernel with that tile
@@ -1168,7 +1211,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   do {                                                                                                 \
     if ((rc = set_smem(flow_train_kernel<SPT, WS>, c.smem))) return rc;                                \
     flow_train_kernel<SPT, WS><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, \
-                                                           loss_acc, N, eps, gamma, inv_n, head);      \
+                                                           loss_acc, N, eps, gamma, inv_n, head, c.wl); \
   } while (0)
   if (c.spt == 2 && c.ws) LAUNCH_TRAIN(2, true);
   else if (c.spt == 2) LAUNCH_TRAIN(2, false);
