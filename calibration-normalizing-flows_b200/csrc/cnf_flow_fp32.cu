@@ -315,15 +315,15 @@ __global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, c
 // One work item = one b and a block of 8 a's.  With fewer items than threads the sample loop of an item is
 // split over nseg adjacent lanes (interleaved float4s, so a group still reads contiguous shared memory) and
 // the partial sums are folded with shuffles before the atomics.
-__device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, const int* idxA, int na,
-                                            const float* B, int nb, float* Gbias_b, int TS, int TSP, int tid,
-                                            int NT) {
+template <int NSEG>   // lanes per item, compile-time for the common cases (0: run-time nseg_rt)
+__device__ __forceinline__ void wgrad_outer_seg(float* G, int ldg, const float* A, const int* idxA, int na,
+                                                const float* B, int nb, float* Gbias_b, int TS, int TSP, int tid,
+                                                int NT, int nseg_rt) {
   constexpr int AB = 8;
   const int nablk = (na + AB - 1) / AB;
   const int items = nb * nablk;
   const int ts4 = TS >> 2;
-  int nseg = 1;
-  while (nseg < 32 && items * nseg * 2 <= NT && (ts4 % (nseg * 2)) == 0) nseg <<= 1;
+  const int nseg = NSEG ? NSEG : nseg_rt;
   const int seg = tid & (nseg - 1);
   const int groups = NT / nseg;
   for (int it0 = 0; it0 < items; it0 += groups) {      // block-uniform trip count: every lane reaches the shuffles
@@ -369,6 +369,18 @@ __device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, c
       if (Gbias_b != nullptr && ablk == 0) atomicAdd(Gbias_b + b, bsum);
     }
   }
+}
+
+__device__ __forceinline__ void wgrad_outer(float* G, int ldg, const float* A, const int* idxA, int na,
+                                            const float* B, int nb, float* Gbias_b, int TS, int TSP, int tid,
+                                            int NT) {
+  const int items = nb * ((na + 7) / 8);
+  const int ts4 = TS >> 2;
+  int nseg = 1;
+  while (nseg < 32 && items * nseg * 2 <= NT && (ts4 % (nseg * 2)) == 0) nseg <<= 1;
+  if (nseg == 1) wgrad_outer_seg<1>(G, ldg, A, idxA, na, B, nb, Gbias_b, TS, TSP, tid, NT, 1);
+  else if (nseg == 2) wgrad_outer_seg<2>(G, ldg, A, idxA, na, B, nb, Gbias_b, TS, TSP, tid, NT, 2);
+  else wgrad_outer_seg<0>(G, ldg, A, idxA, na, B, nb, Gbias_b, TS, TSP, tid, NT, nseg);
 }
 
 // Gb[a] += sum_s A[a][s]
