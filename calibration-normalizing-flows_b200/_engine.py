@@ -206,10 +206,11 @@ class StackEngine:
         g_ld = g_ld.to(torch.float32).contiguous()
         gx = torch.empty_like(x) if need_gx else None
         st = _stream(x.device)
-        _lib.call('cnf_flow_backward', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
-                  _ptr(g_z), _ptr(g_ld), _ptr(gx), _ptr(self.partials), ctypes.c_int64(N), st)
+        used = ctypes.c_int64(0)     # only the partial rows the launch wrote are cleared and reduced
+        _lib.call('cnf_flow_backward_rows', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
+                  _ptr(g_z), _ptr(g_ld), _ptr(gx), _ptr(self.partials), ctypes.c_int64(N), ctypes.byref(used), st)
         flat_grad = torch.empty(self.n_flat, dtype=torch.float32, device=x.device)
-        _lib.call('cnf_grad_reduce', ctypes.byref(self.desc), _ptr(self.partials), _ptr(self.gather),
+        _lib.call('cnf_grad_reduce_rows', ctypes.byref(self.desc), _ptr(self.partials), used, _ptr(self.gather),
                   _ptr(flat_grad), st)
         return gx, flat_grad
 
@@ -252,12 +253,13 @@ class StackEngine:
         st = _stream(x.device)
         if with_grad:
             self._want_partials()
-        _lib.call('cnf_nll_train_step', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
+        used = ctypes.c_int64(0)     # only the partial rows the launch wrote are cleared and reduced
+        _lib.call('cnf_nll_train_step_rows', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x),
                   _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
                   ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials) if with_grad else None,
-                  _ptr(loss_acc), st)
+                  _ptr(loss_acc), ctypes.byref(used), st)
         if with_grad:
-            _lib.call('cnf_grad_reduce', ctypes.byref(self.desc), _ptr(self.partials), _ptr(self.gather),
+            _lib.call('cnf_grad_reduce_rows', ctypes.byref(self.desc), _ptr(self.partials), used, _ptr(self.gather),
                       _ptr(self.flat_grad), st)
 
     def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):

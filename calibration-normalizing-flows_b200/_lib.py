@@ -51,6 +51,9 @@ SIGNATURES = {
     'cnf_nll_train_step': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P],
     'cnf_flow_backward': [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
     'cnf_grad_reduce': [_DESC, _P, _P, _P, _P],
+    'cnf_nll_train_step_rows': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, ctypes.POINTER(ctypes.c_int64), _P],
+    'cnf_flow_backward_rows': [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, ctypes.POINTER(ctypes.c_int64), _P],
+    'cnf_grad_reduce_rows': [_DESC, _P, _I64, _P, _P, _P],
     'cnf_tc_train_info': [_DESC, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                           ctypes.POINTER(ctypes.c_int64)],
     'cnf_plan_build_tcgrad': [_DESC, _P],

@@ -10,7 +10,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st);
 int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x,
                    const int64_t* y, const float* gz, const float* gld, float* gx, float* partials, double* loss_acc,
-                   int64_t N, float eps, float gamma, float inv_n, int head, cudaStream_t st);
+                   int64_t N, float eps, float gamma, float inv_n, int head, int64_t* rows_used, cudaStream_t st);
 int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                  float* logdet, int64_t N, int inverse, cudaStream_t st);
 
@@ -52,7 +52,19 @@ extern "C" int cnf_nll_train_step(const cnf_flow_desc* desc, const void* packed,
   if (rc) return rc;
   if (desc->precision != CNF_PREC_FP32) { cnf_set_error("training runs on the fp32 path"); return CNF_E_UNSUPPORTED; }
   return cnf_fp32_train(desc, (const float*)packed, tables, x, y, nullptr, nullptr, nullptr, grad_partials, loss_acc, N,
-                        eps, gamma, inv_n_total, CNF_HEAD_NLL, (cudaStream_t)stream);
+                        eps, gamma, inv_n_total, CNF_HEAD_NLL, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cnf_nll_train_step_rows(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                                       const float* x, const int64_t* y, int64_t N, float eps, float gamma,
+                                       float inv_n_total, float* grad_partials, double* loss_acc, int64_t* rows_used,
+                                       void* stream) {
+  int rc = check_prec(desc);
+  if (rc) return rc;
+  if (desc->precision != CNF_PREC_FP32) { cnf_set_error("training runs on the fp32 path"); return CNF_E_UNSUPPORTED; }
+  if (!rows_used) { cnf_set_error("cnf_nll_train_step_rows: null rows_used"); return CNF_E_ARG; }
+  return cnf_fp32_train(desc, (const float*)packed, tables, x, y, nullptr, nullptr, nullptr, grad_partials, loss_acc, N,
+                        eps, gamma, inv_n_total, CNF_HEAD_NLL, rows_used, (cudaStream_t)stream);
 }
 
 extern "C" int cnf_flow_backward(const cnf_flow_desc* desc, const void* packed, const int32_t* tables, const float* x,
@@ -62,7 +74,18 @@ extern "C" int cnf_flow_backward(const cnf_flow_desc* desc, const void* packed, 
   if (rc) return rc;
   if (desc->precision != CNF_PREC_FP32) { cnf_set_error("backward runs on the fp32 path"); return CNF_E_UNSUPPORTED; }
   return cnf_fp32_train(desc, (const float*)packed, tables, x, nullptr, g_z, g_logdet, g_x, grad_partials, nullptr, N,
-                        0.f, 0.f, 0.f, CNF_HEAD_EXTERNAL, (cudaStream_t)stream);
+                        0.f, 0.f, 0.f, CNF_HEAD_EXTERNAL, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cnf_flow_backward_rows(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                                      const float* x, const float* g_z, const float* g_logdet, float* g_x,
+                                      float* grad_partials, int64_t N, int64_t* rows_used, void* stream) {
+  int rc = check_prec(desc);
+  if (rc) return rc;
+  if (desc->precision != CNF_PREC_FP32) { cnf_set_error("backward runs on the fp32 path"); return CNF_E_UNSUPPORTED; }
+  if (!rows_used) { cnf_set_error("cnf_flow_backward_rows: null rows_used"); return CNF_E_ARG; }
+  return cnf_fp32_train(desc, (const float*)packed, tables, x, nullptr, g_z, g_logdet, g_x, grad_partials, nullptr, N,
+                        0.f, 0.f, 0.f, CNF_HEAD_EXTERNAL, rows_used, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1061,6 +1061,373 @@ __global__ void flow_apply_lean_kernel(CnfDims d, const float* __restrict__ pack
 }
 
 // --------------------------------------------------------------------------------------
+// Small-batch training kernel (one hidden layer, Hp <= 256).
+// The reference trains full-batch on calibration sets of a few thousand samples
+// (calibrators.py:267-295); with one thread per sample those leave most of the GPU idle and a step
+// costs one thread's serial walk through the whole stack (~300 us).  Here a CTA owns a 32-sample
+// tile (lane = sample) and its warps split the hidden layer: warp w owns hidden units
+// [16w, 16w+16) of both conditioners of every coupling layer.
+//   forward:   h = relu(W0[:, chunk]^T x + b0) in registers, partial outputs W1[:, chunk] h to shared
+//              memory, barrier, the warps sum the partials per output and apply the coupling;
+//   backward:  the same recompute (h stays in registers), then g = relu'(h) * W1[:, chunk]^T gout,
+//              partial input gradients to shared memory, and the chunk's weight gradients with lanes =
+//              matrix entries (h and g pass through a per-warp slab; an entry is one 32-sample dot product);
+//              every (layer, net, chunk) block of the CTA's private partial row has exactly one owner
+//              warp, so the first tile stores and later tiles use reductions without contention.
+// One coupling layer's weights are staged per step with cp.async into a double buffer.
+// Same arithmetic per element as flow_train_kernel; sums over samples and hidden units associate
+// differently (fp32 rounding only).
+// --------------------------------------------------------------------------------------
+constexpr int SPL_TS = 32;
+
+struct SplitSmem { int tab, act, gact, tape, part, gout, gld, ldp, slab, w, total; };
+
+// NW: warps of the CTA, NWn: warps per conditioner (= 16-unit chunks of the hidden layer)
+__host__ __device__ inline SplitSmem make_split(const CnfDims& d, int NW, int NWn) {
+  SplitSmem s;
+  const int dpart = d.d0 > d.d1 ? d.d0 : d.d1;
+  int off = 0;
+  s.tab = off; off += (d.n_tables + 3) / 4 * 4;
+  s.act = off; off += d.K * SPL_TS;
+  s.gact = off; off += d.K * SPL_TS;
+  s.tape = off; off += d.L * d.d0 * SPL_TS;
+  s.part = off; off += 2 * NWn * dpart * SPL_TS;    // forward: [net][chunk][q]; backward: [warp][c]
+  s.gout = off; off += 2 * d.d0 * SPL_TS;
+  s.gld = off; off += SPL_TS;
+  s.ldp = off; off += NW * SPL_TS;
+  s.slab = off; off += NW * 2 * CH * (SPL_TS + 4);   // per warp: h and g of its chunk, [16][36] each
+  s.w = off; off += 2 * d.layer_stride;
+  s.total = off;
+  return s;
+}
+
+__device__ __forceinline__ void stage_layer_async(float* dst, const float* __restrict__ src, int n, int tid, int NT) {
+  const int n4 = n >> 2;     // layer_stride is a multiple of 4 floats
+  for (int i = tid; i < n4; i += NT) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float4*>(dst) + i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(reinterpret_cast<const float4*>(src) + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// h[r] = relu(b0[r0+r] + sum_i W0[i][r0+r] act[cond[i]][lane])
+__device__ __forceinline__ void split_hidden(float (&h)[1][CH], const CnfDims& d, const float* Wn, int r0,
+                                             const float* act, const int* cond, int lane) {
+  chunk_from_inputs<1, true>(h, Wn + d.w_off[0], d.Hp[0], Wn + d.b_off[0], r0, d.d1, act, cond, SPL_TS, lane, 0);
+#pragma unroll
+  for (int r = 0; r < CH; ++r) h[0][r] = fmaxf(h[0][r], 0.f);
+}
+
+// dst[q][lane] = sum_r W1[q][r0+r] h[r]   (this warp's share of the net's d0 outputs)
+__device__ __forceinline__ void split_partial_out(float* dst, const float (&h)[1][CH], const CnfDims& d,
+                                                  const float* Wn, int r0, int lane) {
+  const float* W1 = Wn + d.w_off[1] + r0;
+#pragma unroll 2
+  for (int q = 0; q < d.d0; ++q) {
+    const float* wrow = W1 + (size_t)q * d.Hp[0];
+    float acc = 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * r4);
+      acc = fmaf(wv.x, h[0][4 * r4 + 0], acc);
+      acc = fmaf(wv.y, h[0][4 * r4 + 1], acc);
+      acc = fmaf(wv.z, h[0][4 * r4 + 2], acc);
+      acc = fmaf(wv.w, h[0][4 * r4 + 3], acc);
+    }
+    dst[q * SPL_TS + lane] = acc;
+  }
+}
+
+constexpr int SPL_SLP = SPL_TS + 4;   // row stride of the per-warp slabs: 128-bit row reads by 16 lanes, 2-way at most
+
+// dot product over the tile's 32 samples of two shared-memory rows
+__device__ __forceinline__ float row_dot32(const float* a, const float* b) {
+  float acc = 0.f;
+#pragma unroll
+  for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
+    const float4 av = *reinterpret_cast<const float4*>(a + 4 * s4);
+    const float4 bv = *reinterpret_cast<const float4*>(b + 4 * s4);
+    acc = fmaf(av.x, bv.x, acc);
+    acc = fmaf(av.y, bv.y, acc);
+    acc = fmaf(av.z, bv.z, acc);
+    acc = fmaf(av.w, bv.w, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ float row_sum32(const float* a) {
+  float acc = 0.f;
+#pragma unroll
+  for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
+    const float4 av = *reinterpret_cast<const float4*>(a + 4 * s4);
+    acc += (av.x + av.y) + (av.z + av.w);
+  }
+  return acc;
+}
+__device__ __forceinline__ void grad_put(float* p, float v, bool first) {
+  if (first) *p = v; else atomicAdd(p, v);
+}
+
+// Backward of this warp's chunk of one net.  Per lane (= sample): g = relu'(h) * W1[:, chunk]^T gout and the
+// chunk's share of the input gradient, added into pg[c][lane] (set when init).  Then the chunk's weight
+// gradients with lanes = matrix entries: h and g go through the warp's private slab (slab: [2][16][SPL_SLP]),
+// every entry is one 32-sample dot product of two shared-memory rows.
+__device__ __forceinline__ void split_net_backward(const CnfDims& d, const float* Wn, float* Gn, int r0,
+                                                   const float (&h)[1][CH], const float* gout, const float* act,
+                                                   const int* cond, float* pg, float* slab, bool init,
+                                                   bool bias_owner, int lane, bool first) {
+  const int Hp = d.Hp[0];
+  float* sl_h = slab;
+  float* sl_g = slab + CH * SPL_SLP;
+  float g[CH];
+#pragma unroll
+  for (int r = 0; r < CH; ++r) g[r] = 0.f;
+  for (int q = 0; q < d.d0; ++q) {
+    const float go = gout[q * SPL_TS + lane];
+    const float* wrow = Wn + d.w_off[1] + (size_t)q * Hp + r0;
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * r4);
+      g[4 * r4 + 0] = fmaf(wv.x, go, g[4 * r4 + 0]);
+      g[4 * r4 + 1] = fmaf(wv.y, go, g[4 * r4 + 1]);
+      g[4 * r4 + 2] = fmaf(wv.z, go, g[4 * r4 + 2]);
+      g[4 * r4 + 3] = fmaf(wv.w, go, g[4 * r4 + 3]);
+    }
+  }
+  __syncwarp();                                       // the slab's previous readers are done
+#pragma unroll
+  for (int r = 0; r < CH; ++r) {
+    g[r] = (h[0][r] > 0.f) ? g[r] : 0.f;
+    sl_h[r * SPL_SLP + lane] = h[0][r];
+    sl_g[r * SPL_SLP + lane] = g[r];
+  }
+  for (int i = 0; i < d.d1; ++i) {
+    const float* wrow = Wn + d.w_off[0] + (size_t)i * Hp + r0;
+    float acc = 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < CH / 4; ++r4) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * r4);
+      acc = fmaf(wv.x, g[4 * r4 + 0], acc);
+      acc = fmaf(wv.y, g[4 * r4 + 1], acc);
+      acc = fmaf(wv.z, g[4 * r4 + 2], acc);
+      acc = fmaf(wv.w, g[4 * r4 + 3], acc);
+    }
+    float* pp = pg + i * SPL_TS + lane;
+    *pp = init ? acc : *pp + acc;
+  }
+  __syncwarp();                                       // slab complete
+  // last Linear: dW1[q][r0+r] = sum_s gout[q][s] h[r][s]; db1[q] = sum_s gout[q][s] (owner of chunk 0)
+  for (int e = lane; e < d.d0 * CH; e += 32) {
+    const int q = e / CH, r = e % CH;
+    grad_put(Gn + d.w_off[1] + (size_t)q * Hp + r0 + r, row_dot32(gout + q * SPL_TS, sl_h + r * SPL_SLP), first);
+  }
+  if (bias_owner)
+    for (int q = lane; q < d.d0; q += 32) grad_put(Gn + d.b_off[1] + q, row_sum32(gout + q * SPL_TS), first);
+  // first Linear: dW0[i][r0+r] = sum_s x_i[s] g[r][s]; db0[r0+r] = sum_s g[r][s]
+  for (int e = lane; e < d.d1 * CH; e += 32) {
+    const int i = e / CH, r = e % CH;
+    grad_put(Gn + d.w_off[0] + (size_t)i * Hp + r0 + r, row_dot32(act + cond[i] * SPL_TS, sl_g + r * SPL_SLP), first);
+  }
+  if (lane < CH) grad_put(Gn + d.b_off[0] + r0 + lane, row_sum32(sl_g + lane * SPL_SLP), first);
+}
+
+__global__ void __launch_bounds__(512)
+flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                        const float* __restrict__ xin, const int64_t* __restrict__ labels,
+                        const float* __restrict__ gz_ext, const float* __restrict__ gld_ext,
+                        float* __restrict__ gx_out, float* __restrict__ partials, double* __restrict__ loss_acc,
+                        int64_t N, float eps, float gamma, float inv_n, int head) {
+  extern __shared__ __align__(16) float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+  constexpr int TS = SPL_TS;
+  const bool do_bwd = (partials != nullptr);
+  const bool has_s = d.nets & 1, has_t = d.nets & 2;
+  // with both conditioners and room for twice the warps, one half of the CTA runs the s-net and the other
+  // the t-net concurrently (the host launches 2 x chunks warps); otherwise every warp runs both in turn
+  const int nch = d.Hp[0] / CH;
+  const bool par = has_s && has_t && NW == 2 * nch;
+  const int NWn = par ? NW / 2 : NW;
+  const int cw = par ? warp % NWn : warp;             // this warp's chunk
+  const bool do_s = has_s && (!par || warp < NWn), do_t = has_t && (!par || warp >= NWn);
+  const SplitSmem sm = make_split(d, NW, NWn);
+  const int dpart = d.d0 > d.d1 ? d.d0 : d.d1;
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* gact = smem + sm.gact;
+  float* tape = smem + sm.tape;
+  float* part = smem + sm.part;
+  float* gout_s = smem + sm.gout;
+  float* gout_t = gout_s + d.d0 * TS;
+  float* gld_sm = smem + sm.gld;
+  float* ldp = smem + sm.ldp;
+  float* slab = smem + sm.slab + (size_t)warp * 2 * CH * SPL_SLP;
+  float* wbuf = smem + sm.w;
+  const int r0 = cw * CH;                             // this warp's hidden units
+  const int t_slot = has_s ? 1 : 0;                   // the t-net's block inside a layer
+  float* Grow = do_bwd ? partials + (size_t)blockIdx.x * d.n_packed : nullptr;   // grid <= grad_rows: a private row
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+  bool first = true;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    __syncthreads();                                  // tables visible; the previous tile is fully consumed
+    stage_layer_async(wbuf, packed, d.layer_stride, tid, NT);
+    load_tile(act, xin, base, N, d.K, TS, TS, nullptr, tid, NT);
+    if (head == CNF_HEAD_EXTERNAL) load_tile(gact, gz_ext, base, N, d.K, TS, TS, pi_last, tid, NT);
+    float ld_part = 0.f;
+    // ---- forward ----------------------------------------------------------------------
+    for (int l = 0; l < d.L; ++l) {
+      stage_wait();
+      __syncthreads();                                // layer l's weights and the tile state are visible
+      if (l + 1 < d.L)
+        stage_layer_async(wbuf + ((l + 1) & 1) * d.layer_stride, packed + (size_t)(l + 1) * d.layer_stride,
+                          d.layer_stride, tid, NT);
+      const float* Wl = wbuf + (l & 1) * d.layer_stride;
+      const int* cond = tab + d.tab_cond + l * d.d1;
+      const int* trans = tab + d.tab_trans + l * d.d0;
+      float h[1][CH];
+      if (do_s) {
+        split_hidden(h, d, Wl, r0, act, cond, lane);
+        split_partial_out(part + (size_t)cw * dpart * TS, h, d, Wl, r0, lane);
+      }
+      if (do_t) {
+        const float* Wt = Wl + (size_t)t_slot * d.net_stride;
+        split_hidden(h, d, Wt, r0, act, cond, lane);
+        split_partial_out(part + (size_t)(NWn + cw) * dpart * TS, h, d, Wt, r0, lane);
+      }
+      __syncthreads();
+      for (int q = warp; q < d.d0; q += NW) {
+        float sv = 0.f, tv = 0.f;
+        if (has_s) {
+          sv = Wl[d.b_off[1] + q];
+          for (int w = 0; w < NWn; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
+        }
+        if (has_t) {
+          tv = Wl[(size_t)t_slot * d.net_stride + d.b_off[1] + q];
+          for (int w = 0; w < NWn; ++w) tv += part[((size_t)(NWn + w) * dpart + q) * TS + lane];
+        }
+        const int p = trans[q];
+        const float xv = act[p * TS + lane];
+        tape[(l * d.d0 + q) * TS + lane] = xv;
+        act[p * TS + lane] = xv * expf(sv) + tv;
+        ld_part += sv;
+      }
+    }
+    ldp[warp * TS + lane] = ld_part;
+    __syncthreads();
+    // ---- loss head (warp 0, lane = sample) ---------------------------------------------
+    if (warp == 0) {
+      float ld = 0.f;
+      for (int w = 0; w < NW; ++w) ld += ldp[w * TS + lane];
+      const int64_t n = base + lane;
+      const bool valid = n < N;
+      float gld = 0.f;
+      if (head == CNF_HEAD_NLL) {
+        float mx = -INFINITY;
+        for (int j = 0; j < d.K; ++j) mx = fmaxf(mx, act[pi_last[j] * TS + lane]);
+        float se = 0.f;
+        for (int j = 0; j < d.K; ++j) se += expf(act[pi_last[j] * TS + lane] - mx);
+        int yy = valid ? (int)labels[n] : 0;
+        yy = min(max(yy, 0), d.K - 1);
+        const float zy = act[pi_last[yy] * TS + lane];
+        const float inv_se = 1.f / se;
+        const float py = expf(zy - mx) * inv_se;
+        float ce, coef;
+        if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+        else            { ce = logf(py + eps); coef = py / (py + eps); }
+        if (valid) {
+          const float tot = ce + gamma * ld;
+          a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld;
+          if (!isfinite(tot)) a_bad += 1.0;
+        }
+        if (do_bwd) {
+          const float sc = valid ? -inv_n * coef : 0.f;
+          for (int j = 0; j < d.K; ++j) {
+            const int p = pi_last[j];
+            const float pj = expf(act[p * TS + lane] - mx) * inv_se;
+            gact[p * TS + lane] = sc * ((j == yy ? 1.f : 0.f) - pj);
+          }
+          gld = valid ? -gamma * inv_n : 0.f;
+        }
+      } else {
+        gld = valid ? gld_ext[n] : 0.f;
+      }
+      gld_sm[lane] = gld;
+    }
+    // ---- backward ---------------------------------------------------------------------
+    if (do_bwd) {
+      for (int l = d.L - 1; l >= 0; --l) {
+        if (l != d.L - 1) stage_wait();
+        __syncthreads();                              // gact / gout / act of the step before are visible
+        if (l > 0)
+          stage_layer_async(wbuf + ((l - 1) & 1) * d.layer_stride, packed + (size_t)(l - 1) * d.layer_stride,
+                            d.layer_stride, tid, NT);
+        const float* Wl = wbuf + (l & 1) * d.layer_stride;
+        float* Gl = Grow + (size_t)l * d.layer_stride;
+        const int* cond = tab + d.tab_cond + l * d.d1;
+        const int* trans = tab + d.tab_trans + l * d.d0;
+        const float* Wt = Wl + (size_t)t_slot * d.net_stride;
+        float hs[1][CH], ht[1][CH];
+        if (do_s) {
+          split_hidden(hs, d, Wl, r0, act, cond, lane);
+          split_partial_out(part + (size_t)cw * dpart * TS, hs, d, Wl, r0, lane);
+        }
+        if (do_t) split_hidden(ht, d, Wt, r0, act, cond, lane);
+        __syncthreads();
+        const float gld = gld_sm[lane];
+        for (int q = warp; q < d.d0; q += NW) {
+          const int p = trans[q];
+          const float gy = gact[p * TS + lane];
+          const float xv = tape[(l * d.d0 + q) * TS + lane];
+          if (has_s) {
+            float sv = Wl[d.b_off[1] + q];
+            for (int w = 0; w < NWn; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
+            const float es = expf(sv);
+            gout_s[q * TS + lane] = gy * xv * es + gld;
+            gact[p * TS + lane] = gy * es;
+          }
+          gout_t[q * TS + lane] = gy;
+          act[p * TS + lane] = xv;                     // the tile state steps back to the input of layer l
+        }
+        __syncthreads();
+        float* pg = part + (size_t)warp * dpart * TS;
+        if (do_s) split_net_backward(d, Wl, Gl, r0, hs, gout_s, act, cond, pg, slab, true, cw == 0, lane, first);
+        if (do_t)
+          split_net_backward(d, Wt, Gl + (size_t)t_slot * d.net_stride, r0, ht, gout_t, act, cond, pg, slab,
+                             !do_s, cw == 0, lane, first);
+        __syncthreads();
+        for (int c = warp; c < d.d1; c += NW) {
+          float acc = 0.f;
+          for (int w = 0; w < NW; ++w) acc += part[((size_t)w * dpart + c) * TS + lane];
+          gact[cond[c] * TS + lane] += acc;
+        }
+      }
+      if (gx_out != nullptr) {
+        __syncthreads();
+        store_tile(gact, gx_out, base, N, d.K, TS, TS, nullptr, tid, NT);
+      }
+      first = false;
+    }
+  }
+  if (loss_acc != nullptr && head == CNF_HEAD_NLL && warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a_loss += __shfl_xor_sync(0xffffffffu, a_loss, o);
+      a_ce += __shfl_xor_sync(0xffffffffu, a_ce, o);
+      a_ld += __shfl_xor_sync(0xffffffffu, a_ld, o);
+      a_bad += __shfl_xor_sync(0xffffffffu, a_bad, o);
+    }
+    if (lane == 0) {
+      atomicAdd(loss_acc + 0, a_loss);
+      atomicAdd(loss_acc + 1, a_ce);
+      atomicAdd(loss_acc + 2, a_ld);
+      atomicAdd(loss_acc + 3, a_bad);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
 // launch plumbing
 // --------------------------------------------------------------------------------------
 struct LaunchCfg { int spt, nt; bool ws; int wl; size_t smem; };
@@ -1177,18 +1544,56 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
 
 int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x,
                    const int64_t* y, const float* gz, const float* gld, float* gx, float* partials, double* loss_acc,
-                   int64_t N, float eps, float gamma, float inv_n, int head, cudaStream_t st) {
+                   int64_t N, float eps, float gamma, float inv_n, int head, int64_t* rows_used, cudaStream_t st) {
   CnfDims d;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!packed || !tables || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  // Rows of the partial buffer a launch of `grid` CTAs writes (CTA b -> row b % grad_rows).  With rows_used
+  // (HOST out) only those rows are zeroed and reported, so that small batches do not pay for clearing and
+  // reducing all grad_rows rows; without it every row is cleared (cnf_grad_reduce reads them all).
+  auto clear_rows = [&](int64_t grid) -> int {
+    int64_t rows = d.grad_rows;
+    if (rows_used) { rows = grid < d.grad_rows ? grid : d.grad_rows; *rows_used = rows; }
+    if (partials && rows > 0) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)rows * d.n_packed * sizeof(float), st));
+    return CNF_OK;
+  };
   // an empty batch may come with null data pointers (an empty torch tensor has none)
   if (head == CNF_HEAD_NLL && ((N > 0 && !y) || !loss_acc)) { cnf_set_error("NLL head needs labels and loss_acc"); return CNF_E_ARG; }
   if (head == CNF_HEAD_EXTERNAL && ((N > 0 && (!gz || !gld)) || !partials)) { cnf_set_error("external head needs g_z, g_logdet, partials"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
-  if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)d.grad_rows * d.n_packed * sizeof(float), st));
-  if (N == 0) return CNF_OK;
+  if (N == 0) return clear_rows(0);
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
+  // single-hidden-layer nets up to 256 hidden units: 32-sample tiles with the hidden layer split over the warps
+  // (faster than one thread per sample at every batch size measured, 3x at N <= 10,000)
+  {
+    const char* sw = getenv("CNF_SPLIT_TRAIN");          // "0" disables (experiments)
+    const bool want = sw ? atoi(sw) != 0 : true;
+    if (want && d.m == 1 && d.Hp[0] <= 256) {
+      const int nch = d.Hp[0] / CH;
+      // both nets side by side when the warps fit and every tile gets an SM of its own (the 512-thread CTA is alone on its SM)
+      const bool side_by_side = d.n_nets == 2 && nch <= 8 && (N + SPL_TS - 1) / SPL_TS <= g_num_sms && !getenv("CNF_SPLIT_SEQ");
+      const int nw = side_by_side ? 2 * nch : nch;
+      const size_t bytes = (size_t)make_split(d, nw, nch).total * sizeof(float);
+      if ((long long)bytes <= g_max_smem - 1024) {
+        const int64_t nts = (N + SPL_TS - 1) / SPL_TS;
+        int per_sm = (int)(g_max_smem / (bytes + 2048));
+        const int by_threads = 2048 / (nw * 32), by_regs = 65536 / (128 * nw * 32);
+        per_sm = per_sm < by_threads ? per_sm : by_threads;
+        per_sm = per_sm < by_regs ? per_sm : by_regs;
+        if (per_sm < 1) per_sm = 1;
+        int64_t cap = (int64_t)g_num_sms * per_sm;
+        if (cap > d.grad_rows) cap = d.grad_rows;          // every CTA owns one row of the partial buffer
+        const int grids = (int)(nts < cap ? nts : cap);
+        if ((rc = set_smem(flow_train_split_kernel, bytes))) return rc;
+        if ((rc = clear_rows(grids))) return rc;
+        flow_train_split_kernel<<<grids, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc, N,
+                                                              eps, gamma, inv_n, head);
+        CNF_CHECK_CUDA(cudaGetLastError());
+        return CNF_OK;
+      }
+    }
+  }
   LaunchCfg c;
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, true, &c);
@@ -1206,6 +1611,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
       const int64_t capl = (int64_t)g_num_sms * per_sm;
       const int gridl = (int)(ntl < capl ? ntl : capl);
       if ((rc = set_smem(flow_train_lean_kernel<1>, bytes))) return rc;
+      if ((rc = clear_rows(gridl))) return rc;
       flow_train_lean_kernel<1><<<gridl, nt, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc, N, eps,
                                                           gamma, inv_n, head);
       CNF_CHECK_CUDA(cudaGetLastError());
@@ -1219,6 +1625,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (ctas_per_sm > 2) ctas_per_sm = 2;
   const int64_t cap = (int64_t)g_num_sms * ctas_per_sm;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
+  if ((rc = clear_rows(grid))) return rc;
 #define LAUNCH_TRAIN(SPT, WS)                                                                          \
   do {                                                                                                 \
     if ((rc = set_smem(flow_train_kernel<SPT, WS>, c.smem))) return rc;                                \

@@ -136,6 +136,21 @@ extern "C" int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_part
   return CNF_OK;
 }
 
+extern "C" int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad_partials, int64_t rows_used,
+                                    const int32_t* gather, float* flat_grad, void* stream) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!grad_partials || !gather || !flat_grad) { cnf_set_error("cnf_grad_reduce_rows: null pointer"); return CNF_E_ARG; }
+  if (rows_used < 0 || rows_used > d.grad_rows) { cnf_set_error("cnf_grad_reduce_rows: rows_used %lld out of range", (long long)rows_used); return CNF_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
+  if (rows_used == 0) return CNF_OK;
+  grad_reduce_kernel<<<(d.n_packed + 127) / 128, 128, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, (int)rows_used);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
 extern "C" int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                              void* stream) {

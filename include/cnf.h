@@ -141,6 +141,19 @@ int cnf_flow_backward(const cnf_flow_desc* desc, const void* packed, const int32
 /* flat_grad[gather[i]] = sum over rows of grad_partials[:, i]; dead entries = 0. */
 int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_partials, const int32_t* gather,
                     float* flat_grad, void* stream);
+/* Variants for small batches: only the rows of grad_partials the launch wrote, [0, *rows_used), are cleared
+ * and later reduced (a batch of a few thousand samples uses a fraction of the n_grad_rows rows; clearing and
+ * summing all of them costs more than the training kernel).  rows_used: HOST out, never NULL.
+ * Otherwise identical to cnf_nll_train_step / cnf_flow_backward / cnf_grad_reduce.                       */
+int cnf_nll_train_step_rows(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                            const float* x, const int64_t* y, int64_t N, float eps, float gamma,
+                            float inv_n_total, float* grad_partials, double* loss_acc, int64_t* rows_used,
+                            void* stream);
+int cnf_flow_backward_rows(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                           const float* x, const float* g_z, const float* g_logdet, float* g_x,
+                           float* grad_partials, int64_t N, int64_t* rows_used, void* stream);
+int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad_partials, int64_t rows_used,
+                         const int32_t* gather, float* flat_grad, void* stream);
 /* torch.optim.Adam (L2 weight decay, bias correction as torch); step is 1-based. */
 int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,

@@ -6,7 +6,7 @@ import torch, cnf_b200, bench
 dev = torch.device('cuda:0')
 xt, yt = bench.synth(5000, 77, dev)
 m = bench.make_weights(seed=2).to(dev)
-tr = cnf_b200.FusedNLLTrainer(m.engine(), xt, yt, precision='bf16')
+tr = cnf_b200.FusedNLLTrainer(m.engine(), xt, yt, precision=os.environ.get('CNF_PREC', 'bf16'))
 for _ in range(6):
     tr.step()
 tr.evaluate()

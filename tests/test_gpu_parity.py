@@ -568,3 +568,69 @@ def test_lean_kernels_for_wide_shapes_vs_oracle(K, L, H, scale, shift, N, cuda_d
     gz = 2e-3 * zo[-1]
     _, gx_o = orc.flow_backward(params, x.astype(np.float64), gz, np.ones(N))
     assert rel_err(xg.grad.cpu().numpy(), gx_o) < 5e-4
+
+
+@pytest.mark.parametrize('K,L,H,scale,shift,N', [(10, 6, 128, True, True, 5000),     # both nets side by side (512 threads)
+                                                 (10, 6, 128, True, True, 20001),    # more tiles than SMs: nets in turn
+                                                 (10, 3, 256, True, True, 333),      # 16 chunks
+                                                 (3, 4, 32, False, True, 1000),      # NICE (t-net only), 2 warps
+                                                 (7, 2, 20, True, False, 65),        # scale only, padded hidden layer
+                                                 (40, 2, 100, True, True, 2500)])    # d0, d1 > number of warps
+def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_device, monkeypatch):
+    """The 32-sample-tile training kernel (hidden layer split over the warps of a CTA) against the float64
+    oracle: NLL head with its loss sums, external upstream gradients with g_x, repeated steps on the same
+    partial buffer, and equality with the one-thread-per-sample kernel and with the all-rows C-ABI calls."""
+    import ctypes
+    import torch
+    import cnf_b200
+    from cnf_b200 import _lib
+    from cnf_b200._engine import _ptr, _stream
+    torch.manual_seed(K * 1000 + H)
+    layers = [cnf_b200.NvpCouplingLayer(K, [H], scale=scale, shift=shift) for _ in range(L)]
+    flow = cnf_b200.Flow(layers)
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(100.0)
+    like = orc.init_params(K, L, [H], scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    x, y = orc.synth_logits(N, K, seed=K + 1)
+    flow.to(cuda_device)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    eng = flow.engine()
+    eng.ensure(cuda_device)
+    eng.pack()
+    loss, _, _, grads, _ = orc.train_step_grads(params, x.astype(np.float64), y)
+    go = orc.flatten(grads)
+    for _ in range(2):                       # the second step reuses the partial rows of the first
+        acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+        eng.nll_step(xt, yt, acc)
+        assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+        assert rel_err(eng.flat_grad.cpu().numpy(), go) < 2e-4
+    g_split = eng.flat_grad.clone()
+    # the original entry points (every partial row cleared and reduced) give the same gradient
+    acc2 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    st = _stream(cuda_device)
+    _lib.call('cnf_nll_train_step', ctypes.byref(eng.desc), _ptr(eng.packed), _ptr(eng.tables), _ptr(xt), _ptr(yt),
+              ctypes.c_int64(N), ctypes.c_float(1e-7), ctypes.c_float(1.0), ctypes.c_float(1.0 / N),
+              _ptr(eng.partials), _ptr(acc2), st)
+    g_all = torch.empty_like(eng.flat_grad)
+    _lib.call('cnf_grad_reduce', ctypes.byref(eng.desc), _ptr(eng.partials), _ptr(eng.gather), _ptr(g_all), st)
+    # (same partial rows; the row sums associate differently when the row count differs)
+    assert rel_err(g_all.cpu().numpy(), g_split.cpu().numpy()) < 1e-6
+    assert torch.allclose(acc2, acc, rtol=1e-12, atol=0)
+    # one-thread-per-sample kernel on the same inputs
+    monkeypatch.setenv('CNF_SPLIT_TRAIN', '0')
+    acc3 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc3)
+    monkeypatch.delenv('CNF_SPLIT_TRAIN')
+    assert rel_err(eng.flat_grad.cpu().numpy(), g_split.cpu().numpy()) < 1e-5
+    assert abs(float(acc3[0]) - float(acc[0])) < 1e-6 * abs(float(acc[0]))
+    # external upstream gradients through the drop-in modules
+    zo, _ = orc.flow_forward(params, x.astype(np.float64))
+    xg = xt.clone().requires_grad_(True)
+    zs2, ld2 = flow(xg)
+    (zs2[-1].square().sum() * 1e-3 + ld2.sum()).backward()
+    _, gx_o = orc.flow_backward(params, x.astype(np.float64), 2e-3 * zo[-1], np.ones(N))
+    assert rel_err(xg.grad.cpu().numpy(), gx_o) < 2e-4
