@@ -1140,20 +1140,6 @@ __device__ __forceinline__ void split_partial_out(float* dst, const float (&h)[1
 
 constexpr int SPL_SLP = SPL_TS + 4;   // row stride of the per-warp slabs: 128-bit row reads by 16 lanes, 2-way at most
 
-// dot product over the tile's 32 samples of two shared-memory rows
-__device__ __forceinline__ float row_dot32(const float* a, const float* b) {
-  float acc = 0.f;
-#pragma unroll
-  for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
-    const float4 av = *reinterpret_cast<const float4*>(a + 4 * s4);
-    const float4 bv = *reinterpret_cast<const float4*>(b + 4 * s4);
-    acc = fmaf(av.x, bv.x, acc);
-    acc = fmaf(av.y, bv.y, acc);
-    acc = fmaf(av.z, bv.z, acc);
-    acc = fmaf(av.w, bv.w, acc);
-  }
-  return acc;
-}
 __device__ __forceinline__ float row_sum32(const float* a) {
   float acc = 0.f;
 #pragma unroll
@@ -1169,8 +1155,8 @@ __device__ __forceinline__ void grad_put(float* p, float v, bool first) {
 
 // Backward of this warp's chunk of one net.  Per lane (= sample): g = relu'(h) * W1[:, chunk]^T gout and the
 // chunk's share of the input gradient, added into pg[c][lane] (set when init).  Then the chunk's weight
-// gradients with lanes = matrix entries: h and g go through the warp's private slab (slab: [2][16][SPL_SLP]),
-// every entry is one 32-sample dot product of two shared-memory rows.
+// gradients as 32-sample dot products of shared-memory rows: h and g go through the warp's private slab
+// (slab: [2][16][SPL_SLP]).
 __device__ __forceinline__ void split_net_backward(const CnfDims& d, const float* Wn, float* Gn, int r0,
                                                    const float (&h)[1][CH], const float* gout, const float* act,
                                                    const int* cond, float* pg, float* slab, bool init,
@@ -1215,19 +1201,49 @@ __device__ __forceinline__ void split_net_backward(const CnfDims& d, const float
     *pp = init ? acc : *pp + acc;
   }
   __syncwarp();                                       // slab complete
-  // last Linear: dW1[q][r0+r] = sum_s gout[q][s] h[r][s]; db1[q] = sum_s gout[q][s] (owner of chunk 0)
-  for (int e = lane; e < d.d0 * CH; e += 32) {
-    const int q = e / CH, r = e % CH;
-    grad_put(Gn + d.w_off[1] + (size_t)q * Hp + r0 + r, row_dot32(gout + q * SPL_TS, sl_h + r * SPL_SLP), first);
+  // Weight gradients, one matrix per half-warp at the same time; lane -> hidden unit r, 8 rows per pass:
+  //   lanes  0..15: last Linear   dW1[q][r0+r] = sum_s gout[q][s] h[r][s]
+  //   lanes 16..31: first Linear  dW0[i][r0+r] = sum_s x_i[s] g[r][s],  db0[r0+r] = sum_s g[r][s]
+  // (the row operand is one broadcast per half-warp, the slab row is loaded once per 8 rows)
+  {
+    const int half = lane >> 4, r = lane & 15;
+    const float* brow = (half ? sl_g : sl_h) + r * SPL_SLP;
+    const float* abase = half ? act : gout;
+    const int nrows = half ? d.d1 : d.d0;
+    const int nmax = d.d0 > d.d1 ? d.d0 : d.d1;
+    float* Gm = Gn + (half ? d.w_off[0] : d.w_off[1]) + r0 + r;
+    for (int a0 = 0; a0 < nmax; a0 += 8) {
+      int aoff[8];
+      float acc[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int idx = min(a0 + a, nrows - 1);
+        aoff[a] = (half ? cond[idx] : idx) * SPL_TS;
+        acc[a] = 0.f;
+      }
+      float bs = 0.f;
+#pragma unroll
+      for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
+        const float4 bv = *reinterpret_cast<const float4*>(brow + 4 * s4);
+        bs += (bv.x + bv.y) + (bv.z + bv.w);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const float4 av = *reinterpret_cast<const float4*>(abase + aoff[a] + 4 * s4);
+          acc[a] = fmaf(av.x, bv.x, acc[a]);
+          acc[a] = fmaf(av.y, bv.y, acc[a]);
+          acc[a] = fmaf(av.z, bv.z, acc[a]);
+          acc[a] = fmaf(av.w, bv.w, acc[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a0 + a < nrows) grad_put(Gm + (size_t)(a0 + a) * Hp, acc[a], first);
+      if (half && a0 == 0) grad_put(Gn + d.b_off[0] + r0 + r, bs, first);
+    }
   }
+  // db1[q] = sum_s gout[q][s], by the owner of chunk 0
   if (bias_owner)
     for (int q = lane; q < d.d0; q += 32) grad_put(Gn + d.b_off[1] + q, row_sum32(gout + q * SPL_TS), first);
-  // first Linear: dW0[i][r0+r] = sum_s x_i[s] g[r][s]; db0[r0+r] = sum_s g[r][s]
-  for (int e = lane; e < d.d1 * CH; e += 32) {
-    const int i = e / CH, r = e % CH;
-    grad_put(Gn + d.w_off[0] + (size_t)i * Hp + r0 + r, row_dot32(act + cond[i] * SPL_TS, sl_g + r * SPL_SLP), first);
-  }
-  if (lane < CH) grad_put(Gn + d.b_off[0] + r0 + lane, row_sum32(sl_g + lane * SPL_SLP), first);
 }
 
 __global__ void __launch_bounds__(512)
@@ -1373,7 +1389,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
           split_hidden(hs, d, Wl, r0, act, cond, lane);
           split_partial_out(part + (size_t)cw * dpart * TS, hs, d, Wl, r0, lane);
         }
-        if (do_t) split_hidden(ht, d, Wt, r0, act, cond, lane);
+        if (do_t && par) split_hidden(ht, d, Wt, r0, act, cond, lane);   // its own warps: ahead of the barrier
         __syncthreads();
         const float gld = gld_sm[lane];
         for (int q = warp; q < d.d0; q += NW) {
@@ -1393,6 +1409,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         __syncthreads();
         float* pg = part + (size_t)warp * dpart * TS;
         if (do_s) split_net_backward(d, Wl, Gl, r0, hs, gout_s, act, cond, pg, slab, true, cw == 0, lane, first);
+        if (do_t && !par) split_hidden(ht, d, Wt, r0, act, cond, lane);  // after the s-net: the two never live together
         if (do_t)
           split_net_backward(d, Wt, Gl + (size_t)t_slot * d.net_stride, r0, ht, gout_t, act, cond, pg, slab,
                              !do_s, cw == 0, lane, first);
