@@ -33,24 +33,40 @@ __global__ void gather_bf16_kernel(const float* __restrict__ flat, const int* __
   }
 }
 
-// flat_grad[gather[i]] = sum_rows partials[row][i]; rows summed in fixed order (deterministic
-// given the partials).  flat_grad must be zeroed first (dead entries keep exactly 0).
-__global__ void grad_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ gather,
-                                   float* __restrict__ flat_grad, int n_packed, int rows) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_packed) return;
-  const int g = gather[i];
-  if (g < 0) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = 0;
-  for (; r + 4 <= rows; r += 4) {
-    a0 += partials[(size_t)(r + 0) * n_packed + i];
-    a1 += partials[(size_t)(r + 1) * n_packed + i];
-    a2 += partials[(size_t)(r + 2) * n_packed + i];
-    a3 += partials[(size_t)(r + 3) * n_packed + i];
+// flat_grad[gather[i]] = sum_rows partials[row][i]; fixed summation order (deterministic given the
+// partials).  flat_grad must be zeroed first (dead entries keep exactly 0).
+// Block = 32 columns x 8 row groups: thread (c, rg) sums rows rg, rg+8, ... of column c with 8 loads in
+// flight (the row walk is latency-bound), the 8 group sums are folded through shared memory in a fixed order.
+constexpr int RED_RG = 8;
+__global__ void __launch_bounds__(32 * RED_RG)
+grad_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ gather,
+                   float* __restrict__ flat_grad, int n_packed, int rows) {
+  __shared__ float part[RED_RG][32];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (i < n_packed) {
+    for (int r = rg; r < rows; r += 8 * RED_RG) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = r + k * RED_RG;
+        if (rr < rows) a[k] += partials[(size_t)rr * n_packed + i];
+      }
+    }
   }
-  for (; r < rows; ++r) a0 += partials[(size_t)r * n_packed + i];
-  flat_grad[g] = (a0 + a1) + (a2 + a3);
+  part[rg][c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (rg == 0 && i < n_packed) {
+    const int g = gather[i];
+    if (g >= 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < RED_RG; ++k) t += part[k][c];
+      flat_grad[g] = t;
+    }
+  }
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -131,7 +147,7 @@ extern "C" int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_part
   if (!grad_partials || !gather || !flat_grad) { cnf_set_error("cnf_grad_reduce: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
-  grad_reduce_kernel<<<(d.n_packed + 127) / 128, 128, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, d.grad_rows);
+  grad_reduce_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, d.grad_rows);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -146,7 +162,7 @@ extern "C" int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
   if (rows_used == 0) return CNF_OK;
-  grad_reduce_kernel<<<(d.n_packed + 127) / 128, 128, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, (int)rows_used);
+  grad_reduce_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, (int)rows_used);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

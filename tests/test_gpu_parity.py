@@ -609,6 +609,11 @@ def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_de
         assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
         assert rel_err(eng.flat_grad.cpu().numpy(), go) < 2e-4
     g_split = eng.flat_grad.clone()
+    # every entry of a partial row has one writer and the rows are summed in a fixed order: the gradient is
+    # bitwise reproducible run to run (a shared-memory race would show up here)
+    for _ in range(8):
+        eng.nll_step(xt, yt, torch.zeros(4, dtype=torch.float64, device=cuda_device))
+        assert torch.equal(eng.flat_grad, g_split)
     # the original entry points (every partial row cleared and reduced) give the same gradient
     acc2 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
     st = _stream(cuda_device)
