@@ -1111,19 +1111,19 @@ __device__ __forceinline__ void stage_layer_async(float* dst, const float* __res
 }
 
 // h[r] = relu(b0[r0+r] + sum_i W0[i][r0+r] act[cond[i]][lane])
-__device__ __forceinline__ void split_hidden(float (&h)[1][CH], const CnfDims& d, const float* Wn, int r0,
+__device__ __forceinline__ void split_hidden(float (&h)[1][CH], const CnfDims& d, int d1, const float* Wn, int r0,
                                              const float* act, const int* cond, int lane) {
-  chunk_from_inputs<1, true>(h, Wn + d.w_off[0], d.Hp[0], Wn + d.b_off[0], r0, d.d1, act, cond, SPL_TS, lane, 0);
+  chunk_from_inputs<1, true>(h, Wn + d.w_off[0], d.Hp[0], Wn + d.b_off[0], r0, d1, act, cond, SPL_TS, lane, 0);
 #pragma unroll
   for (int r = 0; r < CH; ++r) h[0][r] = fmaxf(h[0][r], 0.f);
 }
 
 // dst[q][lane] = sum_r W1[q][r0+r] h[r]   (this warp's share of the net's d0 outputs)
-__device__ __forceinline__ void split_partial_out(float* dst, const float (&h)[1][CH], const CnfDims& d,
+__device__ __forceinline__ void split_partial_out(float* dst, const float (&h)[1][CH], const CnfDims& d, int d0,
                                                   const float* Wn, int r0, int lane) {
   const float* W1 = Wn + d.w_off[1] + r0;
-#pragma unroll 2
-  for (int q = 0; q < d.d0; ++q) {
+#pragma unroll 5
+  for (int q = 0; q < d0; ++q) {
     const float* wrow = W1 + (size_t)q * d.Hp[0];
     float acc = 0.f;
 #pragma unroll
@@ -1153,11 +1153,56 @@ __device__ __forceinline__ void grad_put(float* p, float v, bool first) {
   if (first) *p = v; else atomicAdd(p, v);
 }
 
+// Weight gradients of one chunk, one matrix per half-warp at the same time; lane -> hidden unit r, AB rows per pass:
+//   lanes  0..15: last Linear   dW1[q][r0+r] = sum_s gout[q][s] h[r][s]
+//   lanes 16..31: first Linear  dW0[i][r0+r] = sum_s x_i[s] g[r][s],  db0[r0+r] = sum_s g[r][s]
+// (the row operand is one broadcast per half-warp, the slab row is loaded once per AB rows)
+template <int AB>
+__device__ __forceinline__ void split_wgrad(const CnfDims& d, int d0, int d1, float* Gn, int r0, const float* gout, const float* act,
+                                            const int* cond, const float* sl_h, const float* sl_g, int lane,
+                                            bool first) {
+  const int Hp = d.Hp[0];
+  const int half = lane >> 4, r = lane & 15;
+  const float* brow = (half ? sl_g : sl_h) + r * SPL_SLP;
+  const float* abase = half ? act : gout;
+  const int nrows = half ? d1 : d0;
+  const int nmax = d0 > d1 ? d0 : d1;
+  float* Gm = Gn + (half ? d.w_off[0] : d.w_off[1]) + r0 + r;
+  for (int a0 = 0; a0 < nmax; a0 += AB) {
+    int aoff[AB];
+    float acc[AB];
+#pragma unroll
+    for (int a = 0; a < AB; ++a) {
+      const int idx = min(a0 + a, nrows - 1);
+      aoff[a] = (half ? cond[idx] : idx) * SPL_TS;
+      acc[a] = 0.f;
+    }
+    float bs = 0.f;
+#pragma unroll
+    for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
+      const float4 bv = *reinterpret_cast<const float4*>(brow + 4 * s4);
+      bs += (bv.x + bv.y) + (bv.z + bv.w);
+#pragma unroll
+      for (int a = 0; a < AB; ++a) {
+        const float4 av = *reinterpret_cast<const float4*>(abase + aoff[a] + 4 * s4);
+        acc[a] = fmaf(av.x, bv.x, acc[a]);
+        acc[a] = fmaf(av.y, bv.y, acc[a]);
+        acc[a] = fmaf(av.z, bv.z, acc[a]);
+        acc[a] = fmaf(av.w, bv.w, acc[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < AB; ++a)
+      if (a0 + a < nrows) grad_put(Gm + (size_t)(a0 + a) * Hp, acc[a], first);
+    if (half && a0 == 0) grad_put(Gn + d.b_off[0] + r0 + r, bs, first);
+  }
+}
+
 // Backward of this warp's chunk of one net.  Per lane (= sample): g = relu'(h) * W1[:, chunk]^T gout and the
 // chunk's share of the input gradient, added into pg[c][lane] (set when init).  Then the chunk's weight
 // gradients as 32-sample dot products of shared-memory rows: h and g go through the warp's private slab
 // (slab: [2][16][SPL_SLP]).
-__device__ __forceinline__ void split_net_backward(const CnfDims& d, const float* Wn, float* Gn, int r0,
+__device__ __forceinline__ void split_net_backward(const CnfDims& d, int d0, int d1, const float* Wn, float* Gn, int r0,
                                                    const float (&h)[1][CH], const float* gout, const float* act,
                                                    const int* cond, float* pg, float* slab, bool init,
                                                    bool bias_owner, int lane, bool first) {
@@ -1167,7 +1212,8 @@ __device__ __forceinline__ void split_net_backward(const CnfDims& d, const float
   float g[CH];
 #pragma unroll
   for (int r = 0; r < CH; ++r) g[r] = 0.f;
-  for (int q = 0; q < d.d0; ++q) {
+#pragma unroll 5
+  for (int q = 0; q < d0; ++q) {
     const float go = gout[q * SPL_TS + lane];
     const float* wrow = Wn + d.w_off[1] + (size_t)q * Hp + r0;
 #pragma unroll
@@ -1186,7 +1232,8 @@ __device__ __forceinline__ void split_net_backward(const CnfDims& d, const float
     sl_h[r * SPL_SLP + lane] = h[0][r];
     sl_g[r * SPL_SLP + lane] = g[r];
   }
-  for (int i = 0; i < d.d1; ++i) {
+#pragma unroll 5
+  for (int i = 0; i < d1; ++i) {
     const float* wrow = Wn + d.w_off[0] + (size_t)i * Hp + r0;
     float acc = 0.f;
 #pragma unroll
@@ -1201,51 +1248,16 @@ __device__ __forceinline__ void split_net_backward(const CnfDims& d, const float
     *pp = init ? acc : *pp + acc;
   }
   __syncwarp();                                       // slab complete
-  // Weight gradients, one matrix per half-warp at the same time; lane -> hidden unit r, 8 rows per pass:
-  //   lanes  0..15: last Linear   dW1[q][r0+r] = sum_s gout[q][s] h[r][s]
-  //   lanes 16..31: first Linear  dW0[i][r0+r] = sum_s x_i[s] g[r][s],  db0[r0+r] = sum_s g[r][s]
-  // (the row operand is one broadcast per half-warp, the slab row is loaded once per 8 rows)
-  {
-    const int half = lane >> 4, r = lane & 15;
-    const float* brow = (half ? sl_g : sl_h) + r * SPL_SLP;
-    const float* abase = half ? act : gout;
-    const int nrows = half ? d.d1 : d.d0;
-    const int nmax = d.d0 > d.d1 ? d.d0 : d.d1;
-    float* Gm = Gn + (half ? d.w_off[0] : d.w_off[1]) + r0 + r;
-    for (int a0 = 0; a0 < nmax; a0 += 8) {
-      int aoff[8];
-      float acc[8];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int idx = min(a0 + a, nrows - 1);
-        aoff[a] = (half ? cond[idx] : idx) * SPL_TS;
-        acc[a] = 0.f;
-      }
-      float bs = 0.f;
-#pragma unroll
-      for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
-        const float4 bv = *reinterpret_cast<const float4*>(brow + 4 * s4);
-        bs += (bv.x + bv.y) + (bv.z + bv.w);
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const float4 av = *reinterpret_cast<const float4*>(abase + aoff[a] + 4 * s4);
-          acc[a] = fmaf(av.x, bv.x, acc[a]);
-          acc[a] = fmaf(av.y, bv.y, acc[a]);
-          acc[a] = fmaf(av.z, bv.z, acc[a]);
-          acc[a] = fmaf(av.w, bv.w, acc[a]);
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        if (a0 + a < nrows) grad_put(Gm + (size_t)(a0 + a) * Hp, acc[a], first);
-      if (half && a0 == 0) grad_put(Gn + d.b_off[0] + r0 + r, bs, first);
-    }
-  }
+  // weight gradients of the chunk; K = 10 (d0 = d1 = 5) gets an exact 5-row pass
+  if (d0 <= 5 && d1 <= 5) split_wgrad<5>(d, d0, d1, Gn, r0, gout, act, cond, sl_h, sl_g, lane, first);
+  else split_wgrad<8>(d, d0, d1, Gn, r0, gout, act, cond, sl_h, sl_g, lane, first);
   // db1[q] = sum_s gout[q][s], by the owner of chunk 0
   if (bias_owner)
-    for (int q = lane; q < d.d0; q += 32) grad_put(Gn + d.b_off[1] + q, row_sum32(gout + q * SPL_TS), first);
+    for (int q = lane; q < d0; q += 32) grad_put(Gn + d.b_off[1] + q, row_sum32(gout + q * SPL_TS), first);
 }
 
+// DC: 5 = the coupling split of K = 10 (d0 = d1 = 5; BASELINE configs C2/C3/C5) known at compile time, 0 = any
+template <int DC>
 __global__ void __launch_bounds__(512)
 flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                         const float* __restrict__ xin, const int64_t* __restrict__ labels,
@@ -1256,6 +1268,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
   const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
   constexpr int TS = SPL_TS;
   const bool do_bwd = (partials != nullptr);
+  const int d0 = DC ? DC : d.d0, d1 = DC ? DC : d.d1;
   const bool has_s = d.nets & 1, has_t = d.nets & 2;
   // with both conditioners and room for twice the warps, one half of the CTA runs the s-net and the other
   // the t-net concurrently (the host launches 2 x chunks warps); otherwise every warp runs both in turn
@@ -1265,14 +1278,14 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
   const int cw = par ? warp % NWn : warp;             // this warp's chunk
   const bool do_s = has_s && (!par || warp < NWn), do_t = has_t && (!par || warp >= NWn);
   const SplitSmem sm = make_split(d, NW, NWn);
-  const int dpart = d.d0 > d.d1 ? d.d0 : d.d1;
+  const int dpart = d0 > d1 ? d0 : d1;
   int* tab = reinterpret_cast<int*>(smem + sm.tab);
   float* act = smem + sm.act;
   float* gact = smem + sm.gact;
   float* tape = smem + sm.tape;
   float* part = smem + sm.part;
   float* gout_s = smem + sm.gout;
-  float* gout_t = gout_s + d.d0 * TS;
+  float* gout_t = gout_s + d0 * TS;
   float* gld_sm = smem + sm.gld;
   float* ldp = smem + sm.ldp;
   float* slab = smem + sm.slab + (size_t)warp * 2 * CH * SPL_SLP;
@@ -1300,20 +1313,20 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         stage_layer_async(wbuf + ((l + 1) & 1) * d.layer_stride, packed + (size_t)(l + 1) * d.layer_stride,
                           d.layer_stride, tid, NT);
       const float* Wl = wbuf + (l & 1) * d.layer_stride;
-      const int* cond = tab + d.tab_cond + l * d.d1;
-      const int* trans = tab + d.tab_trans + l * d.d0;
+      const int* cond = tab + d.tab_cond + l * d1;
+      const int* trans = tab + d.tab_trans + l * d0;
       float h[1][CH];
       if (do_s) {
-        split_hidden(h, d, Wl, r0, act, cond, lane);
-        split_partial_out(part + (size_t)cw * dpart * TS, h, d, Wl, r0, lane);
+        split_hidden(h, d, d1, Wl, r0, act, cond, lane);
+        split_partial_out(part + (size_t)cw * dpart * TS, h, d, d0, Wl, r0, lane);
       }
       if (do_t) {
         const float* Wt = Wl + (size_t)t_slot * d.net_stride;
-        split_hidden(h, d, Wt, r0, act, cond, lane);
-        split_partial_out(part + (size_t)(NWn + cw) * dpart * TS, h, d, Wt, r0, lane);
+        split_hidden(h, d, d1, Wt, r0, act, cond, lane);
+        split_partial_out(part + (size_t)(NWn + cw) * dpart * TS, h, d, d0, Wt, r0, lane);
       }
       __syncthreads();
-      for (int q = warp; q < d.d0; q += NW) {
+      for (int q = warp; q < d0; q += NW) {
         float sv = 0.f, tv = 0.f;
         if (has_s) {
           sv = Wl[d.b_off[1] + q];
@@ -1325,7 +1338,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         }
         const int p = trans[q];
         const float xv = act[p * TS + lane];
-        tape[(l * d.d0 + q) * TS + lane] = xv;
+        tape[(l * d0 + q) * TS + lane] = xv;
         act[p * TS + lane] = xv * expf(sv) + tv;
         ld_part += sv;
       }
@@ -1381,21 +1394,21 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
                             d.layer_stride, tid, NT);
         const float* Wl = wbuf + (l & 1) * d.layer_stride;
         float* Gl = Grow + (size_t)l * d.layer_stride;
-        const int* cond = tab + d.tab_cond + l * d.d1;
-        const int* trans = tab + d.tab_trans + l * d.d0;
+        const int* cond = tab + d.tab_cond + l * d1;
+        const int* trans = tab + d.tab_trans + l * d0;
         const float* Wt = Wl + (size_t)t_slot * d.net_stride;
         float hs[1][CH], ht[1][CH];
         if (do_s) {
-          split_hidden(hs, d, Wl, r0, act, cond, lane);
-          split_partial_out(part + (size_t)cw * dpart * TS, hs, d, Wl, r0, lane);
+          split_hidden(hs, d, d1, Wl, r0, act, cond, lane);
+          split_partial_out(part + (size_t)cw * dpart * TS, hs, d, d0, Wl, r0, lane);
         }
-        if (do_t && par) split_hidden(ht, d, Wt, r0, act, cond, lane);   // its own warps: ahead of the barrier
+        if (do_t && par) split_hidden(ht, d, d1, Wt, r0, act, cond, lane);   // its own warps: ahead of the barrier
         __syncthreads();
         const float gld = gld_sm[lane];
-        for (int q = warp; q < d.d0; q += NW) {
+        for (int q = warp; q < d0; q += NW) {
           const int p = trans[q];
           const float gy = gact[p * TS + lane];
-          const float xv = tape[(l * d.d0 + q) * TS + lane];
+          const float xv = tape[(l * d0 + q) * TS + lane];
           if (has_s) {
             float sv = Wl[d.b_off[1] + q];
             for (int w = 0; w < NWn; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
@@ -1408,13 +1421,13 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         }
         __syncthreads();
         float* pg = part + (size_t)warp * dpart * TS;
-        if (do_s) split_net_backward(d, Wl, Gl, r0, hs, gout_s, act, cond, pg, slab, true, cw == 0, lane, first);
-        if (do_t && !par) split_hidden(ht, d, Wt, r0, act, cond, lane);  // after the s-net: the two never live together
+        if (do_s) split_net_backward(d, d0, d1, Wl, Gl, r0, hs, gout_s, act, cond, pg, slab, true, cw == 0, lane, first);
+        if (do_t && !par) split_hidden(ht, d, d1, Wt, r0, act, cond, lane);  // after the s-net: the two never live together
         if (do_t)
-          split_net_backward(d, Wt, Gl + (size_t)t_slot * d.net_stride, r0, ht, gout_t, act, cond, pg, slab,
+          split_net_backward(d, d0, d1, Wt, Gl + (size_t)t_slot * d.net_stride, r0, ht, gout_t, act, cond, pg, slab,
                              !do_s, cw == 0, lane, first);
         __syncthreads();
-        for (int c = warp; c < d.d1; c += NW) {
+        for (int c = warp; c < d1; c += NW) {
           float acc = 0.f;
           for (int w = 0; w < NW; ++w) acc += part[((size_t)w * dpart + c) * TS + lane];
           gact[cond[c] * TS + lane] += acc;
@@ -1602,10 +1615,15 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
         int64_t cap = (int64_t)g_num_sms * per_sm;
         if (cap > d.grad_rows) cap = d.grad_rows;          // every CTA owns one row of the partial buffer
         const int grids = (int)(nts < cap ? nts : cap);
-        if ((rc = set_smem(flow_train_split_kernel, bytes))) return rc;
+        const bool dc5 = d.d0 == 5 && d.d1 == 5 && !getenv("CNF_SPLIT_GENERIC");
+        if ((rc = dc5 ? set_smem(flow_train_split_kernel<5>, bytes) : set_smem(flow_train_split_kernel<0>, bytes))) return rc;
         if ((rc = clear_rows(grids))) return rc;
-        flow_train_split_kernel<<<grids, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc, N,
-                                                              eps, gamma, inv_n, head);
+        if (dc5)
+          flow_train_split_kernel<5><<<grids, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc,
+                                                                   N, eps, gamma, inv_n, head);
+        else
+          flow_train_split_kernel<0><<<grids, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc,
+                                                                   N, eps, gamma, inv_n, head);
         CNF_CHECK_CUDA(cudaGetLastError());
         return CNF_OK;
       }
