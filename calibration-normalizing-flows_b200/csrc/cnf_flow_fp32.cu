@@ -1256,6 +1256,50 @@ __device__ __forceinline__ void split_net_backward(const CnfDims& d, int d0, int
     for (int q = lane; q < d0; q += 32) grad_put(Gn + d.b_off[1] + q, row_sum32(gout + q * SPL_TS), first);
 }
 
+// Loss head of a 32-sample tile, lane = sample (act / gact rows of SPL_TS floats): accumulates the NLL sums,
+// writes d loss / d z into gact (NLL head) and returns d loss / d logdet of the lane's sample.
+__device__ __forceinline__ float tile_head32(const CnfDims& d, const float* act, float* gact, const int* pi_last,
+                                             const int64_t* __restrict__ labels, const float* __restrict__ gld_ext,
+                                             int64_t base, int64_t N, int lane, float ld, float eps, float gamma,
+                                             float inv_n, int head, bool do_bwd, double& a_loss, double& a_ce,
+                                             double& a_ld, double& a_bad) {
+  constexpr int TS = SPL_TS;
+  const int64_t n = base + lane;
+  const bool valid = n < N;
+  float gld = 0.f;
+  if (head == CNF_HEAD_NLL) {
+    float mx = -INFINITY;
+    for (int j = 0; j < d.K; ++j) mx = fmaxf(mx, act[pi_last[j] * TS + lane]);
+    float se = 0.f;
+    for (int j = 0; j < d.K; ++j) se += expf(act[pi_last[j] * TS + lane] - mx);
+    int yy = valid ? (int)labels[n] : 0;
+    yy = min(max(yy, 0), d.K - 1);  // out-of-range labels are clamped, never read out of bounds
+    const float zy = act[pi_last[yy] * TS + lane];
+    const float inv_se = 1.f / se;
+    const float py = expf(zy - mx) * inv_se;
+    float ce, coef;
+    if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+    else            { ce = logf(py + eps); coef = py / (py + eps); }
+    if (valid) {
+      const float tot = ce + gamma * ld;
+      a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld;
+      if (!isfinite(tot)) a_bad += 1.0;
+    }
+    if (do_bwd) {
+      const float sc = valid ? -inv_n * coef : 0.f;
+      for (int j = 0; j < d.K; ++j) {
+        const int p = pi_last[j];
+        const float pj = expf(act[p * TS + lane] - mx) * inv_se;
+        gact[p * TS + lane] = sc * ((j == yy ? 1.f : 0.f) - pj);
+      }
+      gld = valid ? -gamma * inv_n : 0.f;
+    }
+  } else {
+    gld = valid ? gld_ext[n] : 0.f;
+  }
+  return gld;
+}
+
 // DC: 5 = the coupling split of K = 10 (d0 = d1 = 5; BASELINE configs C2/C3/C5) known at compile time, 0 = any
 template <int DC>
 __global__ void __launch_bounds__(512)
@@ -1349,40 +1393,8 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
     if (warp == 0) {
       float ld = 0.f;
       for (int w = 0; w < NW; ++w) ld += ldp[w * TS + lane];
-      const int64_t n = base + lane;
-      const bool valid = n < N;
-      float gld = 0.f;
-      if (head == CNF_HEAD_NLL) {
-        float mx = -INFINITY;
-        for (int j = 0; j < d.K; ++j) mx = fmaxf(mx, act[pi_last[j] * TS + lane]);
-        float se = 0.f;
-        for (int j = 0; j < d.K; ++j) se += expf(act[pi_last[j] * TS + lane] - mx);
-        int yy = valid ? (int)labels[n] : 0;
-        yy = min(max(yy, 0), d.K - 1);
-        const float zy = act[pi_last[yy] * TS + lane];
-        const float inv_se = 1.f / se;
-        const float py = expf(zy - mx) * inv_se;
-        float ce, coef;
-        if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
-        else            { ce = logf(py + eps); coef = py / (py + eps); }
-        if (valid) {
-          const float tot = ce + gamma * ld;
-          a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld;
-          if (!isfinite(tot)) a_bad += 1.0;
-        }
-        if (do_bwd) {
-          const float sc = valid ? -inv_n * coef : 0.f;
-          for (int j = 0; j < d.K; ++j) {
-            const int p = pi_last[j];
-            const float pj = expf(act[p * TS + lane] - mx) * inv_se;
-            gact[p * TS + lane] = sc * ((j == yy ? 1.f : 0.f) - pj);
-          }
-          gld = valid ? -gamma * inv_n : 0.f;
-        }
-      } else {
-        gld = valid ? gld_ext[n] : 0.f;
-      }
-      gld_sm[lane] = gld;
+      gld_sm[lane] = tile_head32(d, act, gact, pi_last, labels, gld_ext, base, N, lane, ld, eps, gamma, inv_n, head,
+                                 do_bwd, a_loss, a_ce, a_ld, a_bad);
     }
     // ---- backward ---------------------------------------------------------------------
     if (do_bwd) {
@@ -1430,6 +1442,348 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         for (int c = warp; c < d1; c += NW) {
           float acc = 0.f;
           for (int w = 0; w < NW; ++w) acc += part[((size_t)w * dpart + c) * TS + lane];
+          gact[cond[c] * TS + lane] += acc;
+        }
+      }
+      if (gx_out != nullptr) {
+        __syncthreads();
+        store_tile(gact, gx_out, base, N, d.K, TS, TS, nullptr, tid, NT);
+      }
+      first = false;
+    }
+  }
+  if (loss_acc != nullptr && head == CNF_HEAD_NLL && warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a_loss += __shfl_xor_sync(0xffffffffu, a_loss, o);
+      a_ce += __shfl_xor_sync(0xffffffffu, a_ce, o);
+      a_ld += __shfl_xor_sync(0xffffffffu, a_ld, o);
+      a_bad += __shfl_xor_sync(0xffffffffu, a_bad, o);
+    }
+    if (lane == 0) {
+      atomicAdd(loss_acc + 0, a_loss);
+      atomicAdd(loss_acc + 1, a_ce);
+      atomicAdd(loss_acc + 2, a_ld);
+      atomicAdd(loss_acc + 3, a_bad);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// The same 32-sample-tile scheme for conditioners with two or more hidden layers (each <= 256 units):
+// warp w owns hidden units [16w, 16w+16) of EVERY hidden layer.  A layer's activations go to shared memory
+// (hbuf) so that the next layer's chunks can read all of them, with a barrier per layer; going backwards
+// the pre-activation gradient of layer j is exchanged the same way (gx, two buffers in turn) and warp w
+// forms its chunk of layer j-1's gradient from it.  Weight gradients: rows of the layer's input (shared
+// memory) against the warp's 16 x 32 slab of gradients, 8 rows per pass, the two half-warps on alternate
+// row blocks.  Weights are read from global memory (uniform 128-bit loads, L1/L2 resident: a middle
+// Linear alone is 64 KB at 128 x 128).  The one-thread-per-sample kernel stores every hidden activation of
+// a tile plus two gradient buffers per sample and only fits 32-64 samples per SM for such nets.
+// --------------------------------------------------------------------------------------
+struct DeepSmem { int tab, act, gact, tape, part, gout, gld, ldp, slab, hbuf, gx, total; };
+
+__host__ __device__ inline DeepSmem make_deep(const CnfDims& d, int NW) {
+  DeepSmem s;
+  const int dpart = d.d0 > d.d1 ? d.d0 : d.d1;
+  int hsum = 0;
+  for (int j = 0; j < d.m; ++j) hsum += d.Hp[j];
+  int off = 0;
+  s.tab = off; off += (d.n_tables + 3) / 4 * 4;
+  s.act = off; off += d.K * SPL_TS;
+  s.gact = off; off += d.K * SPL_TS;
+  s.tape = off; off += d.L * d.d0 * SPL_TS;
+  s.part = off; off += 2 * NW * dpart * SPL_TS;
+  s.gout = off; off += 2 * d.d0 * SPL_TS;
+  s.gld = off; off += SPL_TS;
+  s.ldp = off; off += NW * SPL_TS;
+  s.slab = off; off += NW * 2 * CH * (SPL_TS + 4);
+  s.hbuf = off; off += hsum * SPL_TS;
+  s.gx = off; off += 2 * d.Hmax * SPL_TS;
+  s.total = off;
+  return s;
+}
+
+// G[i*ldg + r] (+)= sum_s rows[row(i)][s] * slab[r][s], i < nrows, r < 16; Gb[r] (+)= sum_s slab[r][s].
+// Lanes 0..15 take the even 8-row blocks, lanes 16..31 the odd ones.
+__device__ __forceinline__ void deep_wgrad(float* G, int ldg, const float* rows, const int* idx, int nrows,
+                                           const float* slab, float* Gb, int lane, bool first) {
+  const int half = lane >> 4, r = lane & 15;
+  const float* brow = slab + r * SPL_SLP;
+  for (int a0 = half * 8; a0 < nrows; a0 += 16) {
+    int aoff[8];
+    float acc[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int i = min(a0 + a, nrows - 1);
+      aoff[a] = (idx ? idx[i] : i) * SPL_TS;
+      acc[a] = 0.f;
+    }
+    float bs = 0.f;
+#pragma unroll
+    for (int s4 = 0; s4 < SPL_TS / 4; ++s4) {
+      const float4 bv = *reinterpret_cast<const float4*>(brow + 4 * s4);
+      bs += (bv.x + bv.y) + (bv.z + bv.w);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const float4 av = *reinterpret_cast<const float4*>(rows + aoff[a] + 4 * s4);
+        acc[a] = fmaf(av.x, bv.x, acc[a]);
+        acc[a] = fmaf(av.y, bv.y, acc[a]);
+        acc[a] = fmaf(av.z, bv.z, acc[a]);
+        acc[a] = fmaf(av.w, bv.w, acc[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      if (a0 + a < nrows) grad_put(G + (size_t)(a0 + a) * ldg + r, acc[a], first);
+    if (Gb != nullptr && a0 == 0) grad_put(Gb + r, bs, first);
+  }
+}
+
+__global__ void __launch_bounds__(512)
+flow_train_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                       const float* __restrict__ xin, const int64_t* __restrict__ labels,
+                       const float* __restrict__ gz_ext, const float* __restrict__ gld_ext,
+                       float* __restrict__ gx_out, float* __restrict__ partials, double* __restrict__ loss_acc,
+                       int64_t N, float eps, float gamma, float inv_n, int head) {
+  extern __shared__ __align__(16) float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+  constexpr int TS = SPL_TS;
+  const bool do_bwd = (partials != nullptr);
+  const int m = d.m, d0 = d.d0, d1 = d.d1;
+  const bool has_s = d.nets & 1, has_t = d.nets & 2;
+  const DeepSmem sm = make_deep(d, NW);
+  const int dpart = d0 > d1 ? d0 : d1;
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* gact = smem + sm.gact;
+  float* tape = smem + sm.tape;
+  float* part = smem + sm.part;
+  float* gout_s = smem + sm.gout;
+  float* gout_t = gout_s + d0 * TS;
+  float* gld_sm = smem + sm.gld;
+  float* ldp = smem + sm.ldp;
+  float* sl_h = smem + sm.slab + (size_t)warp * 2 * CH * SPL_SLP;
+  float* sl_g = sl_h + CH * SPL_SLP;
+  float* hbuf = smem + sm.hbuf;
+  float* gxb = smem + sm.gx;
+  int hoff[CNF_MAX_HIDDEN], nch[CNF_MAX_HIDDEN];
+  {
+    int o = 0;
+    for (int j = 0; j < m; ++j) { hoff[j] = o; o += d.Hp[j]; nch[j] = d.Hp[j] / CH; }
+  }
+  const int r0 = warp * CH;
+  const int HL = d.Hp[m - 1];                          // width of the last hidden layer
+  const int t_slot = has_s ? 1 : 0;
+  float* Grow = do_bwd ? partials + (size_t)blockIdx.x * d.n_packed : nullptr;   // grid <= grad_rows: a private row
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+  bool first = true;
+
+  // Forward of one conditioner: every hidden layer into hbuf (a barrier after each); h = this warp's chunk of
+  // the last hidden layer; with pdst, this warp's share of the d0 outputs goes to pdst[warp][q][lane].
+  auto net_fwd = [&](const float* Wn, const int* cond, float* pdst, float (&h)[1][CH]) {
+    for (int j = 0; j < m; ++j) {
+      if (warp < nch[j]) {
+        chunk_from_inputs<1, false>(h, Wn + d.w_off[j], d.Hp[j], Wn + d.b_off[j], r0, j ? d.Hp[j - 1] : d1,
+                                    j ? hbuf + hoff[j - 1] * TS : act, j ? nullptr : cond, TS, lane, 0);
+#pragma unroll
+        for (int r = 0; r < CH; ++r) {
+          h[0][r] = fmaxf(h[0][r], 0.f);
+          hbuf[(hoff[j] + r0 + r) * TS + lane] = h[0][r];
+        }
+      }
+      __syncthreads();
+    }
+    if (pdst != nullptr && warp < nch[m - 1]) {
+      for (int q = 0; q < d0; ++q) {
+        const float* wrow = Wn + d.w_off[m] + (size_t)q * HL + r0;
+        float acc = 0.f;
+#pragma unroll
+        for (int r4 = 0; r4 < CH / 4; ++r4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + r4);
+          acc = fmaf(wv.x, h[0][4 * r4 + 0], acc);
+          acc = fmaf(wv.y, h[0][4 * r4 + 1], acc);
+          acc = fmaf(wv.z, h[0][4 * r4 + 2], acc);
+          acc = fmaf(wv.w, h[0][4 * r4 + 3], acc);
+        }
+        pdst[((size_t)warp * dpart + q) * TS + lane] = acc;
+      }
+    }
+  };
+
+  // Backward of one conditioner whose activations are in hbuf: weight gradients into Gn, this warp's share of
+  // the input gradient into part[warp][c][lane] (set when init, else added).
+  auto net_bwd = [&](const float* Wn, float* Gn, const float* gout, const int* cond, bool init) {
+    float g[CH];
+    int cur = 0;
+    if (warp < nch[m - 1]) {
+#pragma unroll
+      for (int r = 0; r < CH; ++r) g[r] = 0.f;
+      for (int q = 0; q < d0; ++q) {
+        const float go = gout[q * TS + lane];
+        const float* wrow = Wn + d.w_off[m] + (size_t)q * HL + r0;
+#pragma unroll
+        for (int r4 = 0; r4 < CH / 4; ++r4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + r4);
+          g[4 * r4 + 0] = fmaf(wv.x, go, g[4 * r4 + 0]);
+          g[4 * r4 + 1] = fmaf(wv.y, go, g[4 * r4 + 1]);
+          g[4 * r4 + 2] = fmaf(wv.z, go, g[4 * r4 + 2]);
+          g[4 * r4 + 3] = fmaf(wv.w, go, g[4 * r4 + 3]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < CH; ++r) {
+        const float hv = hbuf[(hoff[m - 1] + r0 + r) * TS + lane];
+        g[r] = (hv > 0.f) ? g[r] : 0.f;
+        sl_h[r * SPL_SLP + lane] = hv;
+        sl_g[r * SPL_SLP + lane] = g[r];
+      }
+      __syncwarp();
+      // last Linear: dW[q][r0+r] = sum_s gout[q][s] h[r][s]
+      deep_wgrad(Gn + d.w_off[m] + r0, HL, gout, nullptr, d0, sl_h, nullptr, lane, first);
+    }
+    if (warp == 0)
+      for (int q = lane; q < d0; q += 32) grad_put(Gn + d.b_off[m] + q, row_sum32(gout + q * TS), first);
+    for (int j = m - 1; j >= 0; --j) {
+      // warps below nch[j] hold the masked gradient of layer j's pre-activations in g and in sl_g
+      if (warp < nch[j]) {
+        deep_wgrad(Gn + d.w_off[j] + r0, d.Hp[j], j ? hbuf + hoff[j - 1] * TS : act, j ? nullptr : cond,
+                   j ? d.Hp[j - 1] : d1, sl_g, Gn + d.b_off[j] + r0, lane, first);
+        if (j == 0) {
+          for (int c = 0; c < d1; ++c) {
+            const float* wrow = Wn + d.w_off[0] + (size_t)c * d.Hp[0] + r0;
+            float acc = 0.f;
+#pragma unroll
+            for (int r4 = 0; r4 < CH / 4; ++r4) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + r4);
+              acc = fmaf(wv.x, g[4 * r4 + 0], acc);
+              acc = fmaf(wv.y, g[4 * r4 + 1], acc);
+              acc = fmaf(wv.z, g[4 * r4 + 2], acc);
+              acc = fmaf(wv.w, g[4 * r4 + 3], acc);
+            }
+            float* pp = part + ((size_t)warp * dpart + c) * TS + lane;
+            *pp = init ? acc : *pp + acc;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < CH; ++r) gxb[(cur * d.Hmax + r0 + r) * TS + lane] = g[r];
+        }
+      }
+      if (j == 0) break;
+      __syncthreads();                                 // layer j's gradient is complete in gx[cur]
+      if (warp < nch[j - 1]) {
+        // g_{j-1}[r0+rp] = relu'(h_{j-1}) * sum_r W_j[r0+rp][r] g_j[r]
+#pragma unroll
+        for (int r = 0; r < CH; ++r) g[r] = 0.f;
+        const float* Wj = Wn + d.w_off[j] + (size_t)r0 * d.Hp[j];
+        const float* gsrc = gxb + (size_t)cur * d.Hmax * TS + lane;
+        for (int r4 = 0; r4 < d.Hp[j] / 4; ++r4) {
+          const float g0 = gsrc[(4 * r4 + 0) * TS], g1 = gsrc[(4 * r4 + 1) * TS];
+          const float g2 = gsrc[(4 * r4 + 2) * TS], g3 = gsrc[(4 * r4 + 3) * TS];
+#pragma unroll
+          for (int rp = 0; rp < CH; ++rp) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(Wj + (size_t)rp * d.Hp[j]) + r4);
+            g[rp] = fmaf(wv.x, g0, g[rp]);
+            g[rp] = fmaf(wv.y, g1, g[rp]);
+            g[rp] = fmaf(wv.z, g2, g[rp]);
+            g[rp] = fmaf(wv.w, g3, g[rp]);
+          }
+        }
+        __syncwarp();                                  // the slab's readers of the layer above are done
+#pragma unroll
+        for (int r = 0; r < CH; ++r) {
+          const float hv = hbuf[(hoff[j - 1] + r0 + r) * TS + lane];
+          g[r] = (hv > 0.f) ? g[r] : 0.f;
+          sl_g[r * SPL_SLP + lane] = g[r];
+        }
+        __syncwarp();
+      }
+      cur ^= 1;
+    }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    __syncthreads();
+    load_tile(act, xin, base, N, d.K, TS, TS, nullptr, tid, NT);
+    if (head == CNF_HEAD_EXTERNAL) load_tile(gact, gz_ext, base, N, d.K, TS, TS, pi_last, tid, NT);
+    __syncthreads();
+    float ld_part = 0.f;
+    float h[1][CH];
+    // ---- forward ----------------------------------------------------------------------
+    for (int l = 0; l < d.L; ++l) {
+      const float* Wl = packed + (size_t)l * d.layer_stride;
+      const int* cond = tab + d.tab_cond + l * d1;
+      const int* trans = tab + d.tab_trans + l * d0;
+      if (has_s) net_fwd(Wl, cond, part, h);
+      if (has_t) net_fwd(Wl + (size_t)t_slot * d.net_stride, cond, part + (size_t)NW * dpart * TS, h);
+      __syncthreads();
+      for (int q = warp; q < d0; q += NW) {
+        float sv = 0.f, tv = 0.f;
+        if (has_s) {
+          sv = __ldg(Wl + d.b_off[m] + q);
+          for (int w = 0; w < nch[m - 1]; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
+        }
+        if (has_t) {
+          tv = __ldg(Wl + (size_t)t_slot * d.net_stride + d.b_off[m] + q);
+          for (int w = 0; w < nch[m - 1]; ++w) tv += part[((size_t)(NW + w) * dpart + q) * TS + lane];
+        }
+        const int p = trans[q];
+        const float xv = act[p * TS + lane];
+        tape[(l * d0 + q) * TS + lane] = xv;
+        act[p * TS + lane] = xv * expf(sv) + tv;
+        ld_part += sv;
+      }
+      __syncthreads();
+    }
+    ldp[warp * TS + lane] = ld_part;
+    __syncthreads();
+    if (warp == 0) {
+      float ld = 0.f;
+      for (int w = 0; w < NW; ++w) ld += ldp[w * TS + lane];
+      gld_sm[lane] = tile_head32(d, act, gact, pi_last, labels, gld_ext, base, N, lane, ld, eps, gamma, inv_n, head,
+                                 do_bwd, a_loss, a_ce, a_ld, a_bad);
+    }
+    // ---- backward ---------------------------------------------------------------------
+    if (do_bwd) {
+      for (int l = d.L - 1; l >= 0; --l) {
+        __syncthreads();
+        const float* Wl = packed + (size_t)l * d.layer_stride;
+        float* Gl = Grow + (size_t)l * d.layer_stride;
+        const int* cond = tab + d.tab_cond + l * d1;
+        const int* trans = tab + d.tab_trans + l * d0;
+        const float* Wt = Wl + (size_t)t_slot * d.net_stride;
+        if (has_s) net_fwd(Wl, cond, part, h);
+        __syncthreads();
+        const float gld = gld_sm[lane];
+        for (int q = warp; q < d0; q += NW) {
+          const int p = trans[q];
+          const float gy = gact[p * TS + lane];
+          const float xv = tape[(l * d0 + q) * TS + lane];
+          if (has_s) {
+            float sv = __ldg(Wl + d.b_off[m] + q);
+            for (int w = 0; w < nch[m - 1]; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
+            const float es = expf(sv);
+            gout_s[q * TS + lane] = gy * xv * es + gld;
+            gact[p * TS + lane] = gy * es;
+          }
+          gout_t[q * TS + lane] = gy;
+          act[p * TS + lane] = xv;                     // the tile state steps back to the input of layer l
+        }
+        __syncthreads();
+        if (has_s) net_bwd(Wl, Gl, gout_s, cond, true);
+        if (has_t) {
+          __syncthreads();                             // the s-net's activations in hbuf are no longer needed
+          net_fwd(Wt, cond, nullptr, h);
+          net_bwd(Wt, Gl + (size_t)t_slot * d.net_stride, gout_t, cond, !has_s);
+        }
+        __syncthreads();
+        for (int c = warp; c < d1; c += NW) {
+          float acc = 0.f;
+          for (int w = 0; w < nch[0]; ++w) acc += part[((size_t)w * dpart + c) * TS + lane];
           gact[cond[c] * TS + lane] += acc;
         }
       }
@@ -1624,6 +1978,35 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
         else
           flow_train_split_kernel<0><<<grids, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc,
                                                                    N, eps, gamma, inv_n, head);
+        CNF_CHECK_CUDA(cudaGetLastError());
+        return CNF_OK;
+      }
+    }
+  }
+  // two or more hidden layers, the widest of 64..256 units: the same tiles with the activations exchanged through
+  // shared memory (narrower nets are quicker with one thread per sample; "1" forces, "0" disables: experiments)
+  {
+    const char* sw = getenv("CNF_DEEP_TRAIN");
+    bool fits = d.m >= 2;
+    for (int j = 0; j < d.m; ++j) fits = fits && d.Hp[j] <= 256;
+    const bool want = sw ? atoi(sw) != 0 : d.Hmax >= 64;
+    if (fits && want) {
+      const int nw = d.Hmax / CH;
+      const size_t bytes = (size_t)make_deep(d, nw).total * sizeof(float);
+      if ((long long)bytes <= g_max_smem - 1024) {
+        const int64_t nts = (N + SPL_TS - 1) / SPL_TS;
+        int per_sm = (int)(g_max_smem / (bytes + 2048));
+        const int by_threads = 2048 / (nw * 32), by_regs = 65536 / (128 * nw * 32);
+        per_sm = per_sm < by_threads ? per_sm : by_threads;
+        per_sm = per_sm < by_regs ? per_sm : by_regs;
+        if (per_sm < 1) per_sm = 1;
+        int64_t cap = (int64_t)g_num_sms * per_sm;
+        if (cap > d.grad_rows) cap = d.grad_rows;
+        const int gridd = (int)(nts < cap ? nts : cap);
+        if ((rc = set_smem(flow_train_deep_kernel, bytes))) return rc;
+        if ((rc = clear_rows(gridd))) return rc;
+        flow_train_deep_kernel<<<gridd, nw * 32, bytes, st>>>(d, packed, tables, x, y, gz, gld, gx, partials, loss_acc, N,
+                                                             eps, gamma, inv_n, head);
         CNF_CHECK_CUDA(cudaGetLastError());
         return CNF_OK;
       }

@@ -575,7 +575,12 @@ def test_lean_kernels_for_wide_shapes_vs_oracle(K, L, H, scale, shift, N, cuda_d
                                                  (10, 3, 256, True, True, 333),      # 16 chunks
                                                  (3, 4, 32, False, True, 1000),      # NICE (t-net only), 2 warps
                                                  (7, 2, 20, True, False, 65),        # scale only, padded hidden layer
-                                                 (40, 2, 100, True, True, 2500)])    # d0, d1 > number of warps
+                                                 (40, 2, 100, True, True, 2500),     # d0, d1 > number of warps
+                                                 (10, 3, [128, 128], True, True, 1500),   # deeper nets: activations
+                                                 (10, 2, [128, 64], True, True, 333),     #   exchanged through shared
+                                                 (10, 2, [48, 128], False, True, 97),     #   memory (flow_train_deep_kernel)
+                                                 (100, 2, [64, 64, 64], True, True, 200),
+                                                 (6, 2, [256, 256], True, False, 64)])
 def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_device, monkeypatch):
     """The 32-sample-tile training kernel (hidden layer split over the warps of a CTA) against the float64
     oracle: NLL head with its loss sums, external upstream gradients with g_x, repeated steps on the same
@@ -585,14 +590,15 @@ def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_de
     import cnf_b200
     from cnf_b200 import _lib
     from cnf_b200._engine import _ptr, _stream
-    torch.manual_seed(K * 1000 + H)
-    layers = [cnf_b200.NvpCouplingLayer(K, [H], scale=scale, shift=shift) for _ in range(L)]
+    hidden = H if isinstance(H, list) else [H]
+    torch.manual_seed(K * 1000 + sum(hidden))
+    layers = [cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)]
     flow = cnf_b200.Flow(layers)
     with torch.no_grad():
         for p in flow.parameters():
             if p.requires_grad:
-                p.mul_(100.0)
-    like = orc.init_params(K, L, [H], scale, shift)
+                p.mul_(100.0 if len(hidden) == 1 else 30.0)
+    like = orc.init_params(K, L, hidden, scale, shift)
     flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in layers for p in lay.canonical_parameters()])
     params = orc.unflatten(flat.astype(np.float64), like)
     x, y = orc.synth_logits(N, K, seed=K + 1)
@@ -627,9 +633,11 @@ def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_de
     assert torch.allclose(acc2, acc, rtol=1e-12, atol=0)
     # one-thread-per-sample kernel on the same inputs
     monkeypatch.setenv('CNF_SPLIT_TRAIN', '0')
+    monkeypatch.setenv('CNF_DEEP_TRAIN', '0')
     acc3 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
     eng.nll_step(xt, yt, acc3)
     monkeypatch.delenv('CNF_SPLIT_TRAIN')
+    monkeypatch.delenv('CNF_DEEP_TRAIN')
     assert rel_err(eng.flat_grad.cpu().numpy(), g_split.cpu().numpy()) < 1e-5
     assert abs(float(acc3[0]) - float(acc[0])) < 1e-6 * abs(float(acc[0]))
     # external upstream gradients through the drop-in modules
