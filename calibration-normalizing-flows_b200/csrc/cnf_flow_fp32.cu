@@ -1492,7 +1492,7 @@ __host__ __device__ inline DeepSmem make_deep(const CnfDims& d, int NW) {
   s.act = off; off += d.K * SPL_TS;
   s.gact = off; off += d.K * SPL_TS;
   s.tape = off; off += d.L * d.d0 * SPL_TS;
-  s.part = off; off += 2 * NW * dpart * SPL_TS;
+  s.part = off; off += NW * dpart * SPL_TS;         // one net's partial sums at a time
   s.gout = off; off += 2 * d.d0 * SPL_TS;
   s.gld = off; off += SPL_TS;
   s.ldp = off; off += NW * SPL_TS;
@@ -1718,18 +1718,25 @@ flow_train_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* _
       const float* Wl = packed + (size_t)l * d.layer_stride;
       const int* cond = tab + d.tab_cond + l * d1;
       const int* trans = tab + d.tab_trans + l * d0;
-      if (has_s) net_fwd(Wl, cond, part, h);
-      if (has_t) net_fwd(Wl + (size_t)t_slot * d.net_stride, cond, part + (size_t)NW * dpart * TS, h);
+      if (has_s) {
+        net_fwd(Wl, cond, part, h);
+        __syncthreads();
+        // s outputs summed right away (kept in gout_s, free in the forward pass) so that the t-net can reuse
+        // the partial buffer; its first writes come after the barriers inside net_fwd
+        for (int q = warp; q < d0; q += NW) {
+          float sv = __ldg(Wl + d.b_off[m] + q);
+          for (int w = 0; w < nch[m - 1]; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
+          gout_s[q * TS + lane] = sv;
+        }
+      }
+      if (has_t) net_fwd(Wl + (size_t)t_slot * d.net_stride, cond, part, h);
       __syncthreads();
       for (int q = warp; q < d0; q += NW) {
         float sv = 0.f, tv = 0.f;
-        if (has_s) {
-          sv = __ldg(Wl + d.b_off[m] + q);
-          for (int w = 0; w < nch[m - 1]; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
-        }
+        if (has_s) sv = gout_s[q * TS + lane];         // written by this very thread
         if (has_t) {
           tv = __ldg(Wl + (size_t)t_slot * d.net_stride + d.b_off[m] + q);
-          for (int w = 0; w < nch[m - 1]; ++w) tv += part[((size_t)(NW + w) * dpart + q) * TS + lane];
+          for (int w = 0; w < nch[m - 1]; ++w) tv += part[((size_t)w * dpart + q) * TS + lane];
         }
         const int p = trans[q];
         const float xv = act[p * TS + lane];
@@ -1983,11 +1990,13 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
       }
     }
   }
-  // two or more hidden layers, the widest of 64..256 units: the same tiles with the activations exchanged through
+  // hidden layers of up to 256 units, the widest of at least 64: the same tiles with the activations exchanged through
   // shared memory (narrower nets are quicker with one thread per sample; "1" forces, "0" disables: experiments)
   {
     const char* sw = getenv("CNF_DEEP_TRAIN");
-    bool fits = d.m >= 2;
+    // (also single-hidden-layer nets that did not fit the plan above with its staged weights, on small batches:
+    //  K=30 / hidden 256 at N=10,000: 2.3 -> 0.8 ms per step)
+    bool fits = d.m >= 2 || (d.m == 1 && N <= 65536);
     for (int j = 0; j < d.m; ++j) fits = fits && d.Hp[j] <= 256;
     const bool want = sw ? atoi(sw) != 0 : d.Hmax >= 64;
     if (fits && want) {

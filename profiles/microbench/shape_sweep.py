@@ -8,7 +8,7 @@ import ref_port_torch as rp
 dev = torch.device('cuda:0')
 torch.set_num_threads(os.cpu_count())
 N = 10000
-for (K, L, hidden) in ((10, 4, [5, 5]), (10, 6, [64, 64]), (10, 6, [128, 128]), (100, 4, [100, 100]), (100, 4, [64, 64, 64]), (30, 6, [256]), (100, 8, [512])):
+for (K, L, hidden) in ((10, 4, [5, 5]), (10, 6, [64, 64]), (10, 6, [128, 128]), (100, 4, [100, 100]), (100, 4, [64, 64, 64]), (30, 6, [256]), (100, 4, [100]), (100, 8, [512])):
     g = torch.Generator().manual_seed(1)
     x = 1.5 * torch.randn(N, K, generator=g); y = torch.randint(0, K, (N,), generator=g)
     torch.manual_seed(2)

@@ -580,6 +580,9 @@ def test_lean_kernels_for_wide_shapes_vs_oracle(K, L, H, scale, shift, N, cuda_d
                                                  (10, 2, [128, 64], True, True, 333),     #   exchanged through shared
                                                  (10, 2, [48, 128], False, True, 97),     #   memory (flow_train_deep_kernel)
                                                  (100, 2, [64, 64, 64], True, True, 200),
+                                                 (100, 2, [100, 100], True, True, 150),
+                                                 (30, 2, 256, True, True, 200),           # one hidden layer, too big for the split plan
+                                                 (100, 2, 100, True, True, 150),
                                                  (6, 2, [256, 256], True, False, 64)])
 def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_device, monkeypatch):
     """The 32-sample-tile training kernel (hidden layer split over the warps of a CTA) against the float64
