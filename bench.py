@@ -492,6 +492,27 @@ def run_ours(args):
                                               'training samples per second of wall time',
                                       'finite': bool(np.isfinite(p1).all())}
 
+        # C2 shape at a real calibration-set size: one full-batch epoch (optimiser step + evaluation pass) at
+        # N = 5,000, the regime the reference's calibrators run in (calibrators.py:267-328)
+        if rank == 0 and world == 1:
+            xe, ye = synth(5000, 77, dev)
+            ep = {}
+            for prec in (('fp32', 'bf16') if precision == 'bf16' else ('fp32',)):
+                me = make_weights(seed=2).to(dev)
+                tre = cnf_b200.FusedNLLTrainer(me.engine(), xe, ye, precision=prec)
+                for _ in range(5):
+                    tre.step(); tre.evaluate()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(200):
+                    tre.step(); tre.evaluate()
+                torch.cuda.synchronize()
+                ep[prec] = (time.perf_counter() - t0) / 200
+            extra['calibration_set_epoch'] = {
+                'value': 5000 / ep['fp32'], 'unit': UNIT, 'us_per_epoch': {k: v * 1e6 for k, v in ep.items()},
+                'dtype': 'f32', 'what': 'C2 shape, N=5,000: full-batch Adam step + evaluation pass per epoch, wall time '
+                                        'over 200 epochs; value = samples per second on the fp32 (1e-5 parity) kernels'}
+
     hbm, tf, src = peaks()
     ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
     kname = 'flow_tc_kernel' if precision == 'bf16' else 'flow_apply_kernel'
@@ -558,6 +579,21 @@ def run_ours(args):
                     'sample': '50 full-batch steps on 10,000 samples: torch autograd + Adam on the reference op '
                               'sequence WITHOUT its DataLoader (calibrators.py:268-283 collates per sample, which '
                               'dominates the reference at this size, SURVEY.md 6)'}
+            if 'calibration_set_epoch' in extra:
+                ge = torch.Generator().manual_seed(7)
+                xse = 1.5 * torch.randn(5000, 10, generator=ge)
+                yse = torch.randint(0, 10, (5000,), generator=ge)
+                npe = 6 * 2 * (128 * 10 + 128 + 10 * 128 + 10)
+                ste = rp.TrainState(0.001 * torch.randn(npe, generator=ge), 10, 6, [128])
+                ste.step(xse, yse)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    ste.step(xse, yse)
+                dte = (time.perf_counter() - t0) / 20
+                extra['calibration_set_epoch']['cpu_baseline'] = {
+                    'value': 5000 / dte, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'us_per_epoch': dte * 1e6,
+                    'sample': '20 full-batch steps on 5,000 samples (no evaluation pass): torch autograd + Adam on the '
+                              'reference op sequence'}
             if 'c4_fp32' in extra:
                 g4c = torch.Generator().manual_seed(6)
                 n4c = 5_000
