@@ -1539,6 +1539,141 @@ __device__ __forceinline__ void deep_wgrad(float* G, int ldg, const float* rows,
   }
 }
 
+// Forward of one conditioner on a 32-sample tile, warp w owning units [16w, 16w+16) of every hidden layer:
+// each layer's activations go to hbuf (a block barrier after each layer); h = this warp's chunk of the last
+// hidden layer; with pdst, this warp's share of the d0 outputs goes to pdst[warp][q][lane].  Block-cooperative.
+__device__ __forceinline__ void deep_net_forward(const CnfDims& d, const int* hoff, const int* nch, float* hbuf,
+                                                 const float* act, const float* Wn, const int* cond, float* pdst,
+                                                 int dpart, int warp, int lane, float (&h)[1][CH]) {
+  constexpr int TS = SPL_TS;
+  const int m = d.m, r0 = warp * CH, HL = d.Hp[m - 1];
+  for (int j = 0; j < m; ++j) {
+    if (warp < nch[j]) {
+      chunk_from_inputs<1, false>(h, Wn + d.w_off[j], d.Hp[j], Wn + d.b_off[j], r0, j ? d.Hp[j - 1] : d.d1,
+                                  j ? hbuf + hoff[j - 1] * TS : act, j ? nullptr : cond, TS, lane, 0);
+#pragma unroll
+      for (int r = 0; r < CH; ++r) {
+        h[0][r] = fmaxf(h[0][r], 0.f);
+        hbuf[(hoff[j] + r0 + r) * TS + lane] = h[0][r];
+      }
+    }
+    __syncthreads();
+  }
+  if (pdst != nullptr && warp < nch[m - 1]) {
+    for (int q = 0; q < d.d0; ++q) {
+      const float* wrow = Wn + d.w_off[m] + (size_t)q * HL + r0;
+      float acc = 0.f;
+#pragma unroll
+      for (int r4 = 0; r4 < CH / 4; ++r4) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + r4);
+        acc = fmaf(wv.x, h[0][4 * r4 + 0], acc);
+        acc = fmaf(wv.y, h[0][4 * r4 + 1], acc);
+        acc = fmaf(wv.z, h[0][4 * r4 + 2], acc);
+        acc = fmaf(wv.w, h[0][4 * r4 + 3], acc);
+      }
+      pdst[((size_t)warp * dpart + q) * TS + lane] = acc;
+    }
+  }
+}
+
+// Forward / inverse (+ log-det, optional per-layer outputs) on the same tiles: for nets with two or more hidden
+// layers at any batch size and for single-hidden-layer nets on small batches, where one thread per sample
+// leaves the GPU idle.  Same arithmetic per element as flow_apply_kernel.
+struct DeepFwdSmem { int tab, act, part, outs, ldp, hbuf, total; };
+__host__ __device__ inline DeepFwdSmem make_deep_fwd(const CnfDims& d, int NW) {
+  DeepFwdSmem s;
+  int hsum = 0;
+  for (int j = 0; j < d.m; ++j) hsum += d.Hp[j];
+  int off = 0;
+  s.tab = off; off += (d.n_tables + 3) / 4 * 4;
+  s.act = off; off += d.K * SPL_TS;
+  s.part = off; off += NW * d.d0 * SPL_TS;
+  s.outs = off; off += d.d0 * SPL_TS;
+  s.ldp = off; off += NW * SPL_TS;
+  s.hbuf = off; off += hsum * SPL_TS;
+  s.total = off;
+  return s;
+}
+
+__global__ void __launch_bounds__(512)
+flow_apply_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                       const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet,
+                       float* __restrict__ zs, int64_t N, int inverse) {
+  extern __shared__ __align__(16) float smem[];
+  const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+  constexpr int TS = SPL_TS;
+  const int m = d.m, d0 = d.d0, d1 = d.d1;
+  const bool has_s = d.nets & 1, has_t = d.nets & 2;
+  const DeepFwdSmem sm = make_deep_fwd(d, NW);
+  int* tab = reinterpret_cast<int*>(smem + sm.tab);
+  float* act = smem + sm.act;
+  float* part = smem + sm.part;
+  float* outs_s = smem + sm.outs;
+  float* ldp = smem + sm.ldp;
+  float* hbuf = smem + sm.hbuf;
+  int hoff[CNF_MAX_HIDDEN], nch[CNF_MAX_HIDDEN];
+  {
+    int o = 0;
+    for (int j = 0; j < m; ++j) { hoff[j] = o; o += d.Hp[j]; nch[j] = d.Hp[j] / CH; }
+  }
+  const int t_slot = has_s ? 1 : 0;
+  for (int i = tid; i < d.n_tables; i += NT) tab[i] = tables[i];
+  const int* pi_last = tab + d.tab_pi + d.L * d.K;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    __syncthreads();                                   // tables visible; the previous tile is stored
+    load_tile(act, xin, base, N, d.K, TS, TS, inverse ? pi_last : nullptr, tid, NT);
+    __syncthreads();
+    float ld_part = 0.f;
+    float h[1][CH];
+    for (int li = 0; li < d.L; ++li) {
+      const int l = inverse ? d.L - 1 - li : li;
+      const float* Wl = packed + (size_t)l * d.layer_stride;
+      const int* cond = tab + d.tab_cond + l * d1;
+      const int* trans = tab + d.tab_trans + l * d0;
+      if (has_s) {
+        deep_net_forward(d, hoff, nch, hbuf, act, Wl, cond, part, d0, warp, lane, h);
+        __syncthreads();
+        for (int q = warp; q < d0; q += NW) {
+          float sv = __ldg(Wl + d.b_off[m] + q);
+          for (int w = 0; w < nch[m - 1]; ++w) sv += part[((size_t)w * d0 + q) * TS + lane];
+          outs_s[q * TS + lane] = sv;
+        }
+      }
+      if (has_t) deep_net_forward(d, hoff, nch, hbuf, act, Wl + (size_t)t_slot * d.net_stride, cond, part, d0, warp, lane, h);
+      __syncthreads();
+      for (int q = warp; q < d0; q += NW) {
+        float sv = 0.f, tv = 0.f;
+        if (has_s) sv = outs_s[q * TS + lane];         // written by this very thread
+        if (has_t) {
+          tv = __ldg(Wl + (size_t)t_slot * d.net_stride + d.b_off[m] + q);
+          for (int w = 0; w < nch[m - 1]; ++w) tv += part[((size_t)w * d0 + q) * TS + lane];
+        }
+        const int p = trans[q];
+        const float xv = act[p * TS + lane];
+        if (!inverse) { act[p * TS + lane] = xv * expf(sv) + tv; ld_part += sv; }
+        else          { act[p * TS + lane] = (xv - tv) * expf(-sv); ld_part -= sv; }
+      }
+      __syncthreads();
+      if (zs != nullptr) {
+        // forward: zs[l] is the output of layer l in its logical order pi_{l+1};
+        // inverse: xs[li] is the input of layer l in logical order pi_l.
+        store_tile(act, zs + (size_t)li * N * d.K, base, N, d.K, TS, TS, tab + d.tab_pi + (inverse ? l : l + 1) * d.K,
+                   tid, NT);
+      }
+    }
+    ldp[warp * TS + lane] = ld_part;
+    __syncthreads();
+    if (warp == 0) {
+      float ld = 0.f;
+      for (int w = 0; w < NW; ++w) ld += ldp[w * TS + lane];
+      if (base + lane < N) logdet[base + lane] = ld;
+    }
+    store_tile(act, zout, base, N, d.K, TS, TS, inverse ? nullptr : pi_last, tid, NT);
+  }
+}
+
 __global__ void __launch_bounds__(512)
 flow_train_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                        const float* __restrict__ xin, const int64_t* __restrict__ labels,
@@ -1581,36 +1716,8 @@ flow_train_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* _
   double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
   bool first = true;
 
-  // Forward of one conditioner: every hidden layer into hbuf (a barrier after each); h = this warp's chunk of
-  // the last hidden layer; with pdst, this warp's share of the d0 outputs goes to pdst[warp][q][lane].
   auto net_fwd = [&](const float* Wn, const int* cond, float* pdst, float (&h)[1][CH]) {
-    for (int j = 0; j < m; ++j) {
-      if (warp < nch[j]) {
-        chunk_from_inputs<1, false>(h, Wn + d.w_off[j], d.Hp[j], Wn + d.b_off[j], r0, j ? d.Hp[j - 1] : d1,
-                                    j ? hbuf + hoff[j - 1] * TS : act, j ? nullptr : cond, TS, lane, 0);
-#pragma unroll
-        for (int r = 0; r < CH; ++r) {
-          h[0][r] = fmaxf(h[0][r], 0.f);
-          hbuf[(hoff[j] + r0 + r) * TS + lane] = h[0][r];
-        }
-      }
-      __syncthreads();
-    }
-    if (pdst != nullptr && warp < nch[m - 1]) {
-      for (int q = 0; q < d0; ++q) {
-        const float* wrow = Wn + d.w_off[m] + (size_t)q * HL + r0;
-        float acc = 0.f;
-#pragma unroll
-        for (int r4 = 0; r4 < CH / 4; ++r4) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow) + r4);
-          acc = fmaf(wv.x, h[0][4 * r4 + 0], acc);
-          acc = fmaf(wv.y, h[0][4 * r4 + 1], acc);
-          acc = fmaf(wv.z, h[0][4 * r4 + 2], acc);
-          acc = fmaf(wv.w, h[0][4 * r4 + 3], acc);
-        }
-        pdst[((size_t)warp * dpart + q) * TS + lane] = acc;
-      }
-    }
+    deep_net_forward(d, hoff, nch, hbuf, act, Wn, cond, pdst, dpart, warp, lane, h);
   };
 
   // Backward of one conditioner whose activations are in hbuf: weight gradients into Gn, this warp's share of
@@ -1891,6 +1998,32 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
+  // 32-sample tiles with the hidden layers split over the warps: nets with two or more hidden layers (the widest
+  // of at least 64 units), and single-hidden-layer nets on small batches ("0" disables, "1" forces: experiments)
+  {
+    const char* sw = getenv("CNF_DEEP_APPLY");
+    bool fits = d.m >= 1;
+    for (int j = 0; j < d.m; ++j) fits = fits && d.Hp[j] <= 256;
+    const bool want = sw ? atoi(sw) != 0 : (d.Hmax >= 64 && (d.m >= 2 || N <= 32768));
+    if (fits && want) {
+      const int nw = d.Hmax / CH;
+      const size_t bytes = (size_t)make_deep_fwd(d, nw).total * sizeof(float);
+      if ((long long)bytes <= g_max_smem - 1024) {
+        const int64_t nts = (N + SPL_TS - 1) / SPL_TS;
+        int per_sm = (int)(g_max_smem / (bytes + 2048));
+        const int by_threads = 2048 / (nw * 32), by_regs = 65536 / (128 * nw * 32);
+        per_sm = per_sm < by_threads ? per_sm : by_threads;
+        per_sm = per_sm < by_regs ? per_sm : by_regs;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)g_num_sms * per_sm;
+        const int gridd = (int)(nts < cap ? nts : cap);
+        if ((rc = set_smem(flow_apply_deep_kernel, bytes))) return rc;
+        flow_apply_deep_kernel<<<gridd, nw * 32, bytes, st>>>(d, packed, tables, x, z, logdet, zs, N, inverse);
+        CNF_CHECK_CUDA(cudaGetLastError());
+        return CNF_OK;
+      }
+    }
+  }
   LaunchCfg c;
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, false, &c);
