@@ -1069,7 +1069,8 @@ __global__ void flow_apply_lean_kernel(CnfDims d, const float* __restrict__ pack
 // [16w, 16w+16) of both conditioners of every coupling layer.
 //   forward:   h = relu(W0[:, chunk]^T x + b0) in registers, partial outputs W1[:, chunk] h to shared
 //              memory, barrier, the warps sum the partials per output and apply the coupling;
-//   backward:  the same recompute (h stays in registers), then g = relu'(h) * W1[:, chunk]^T gout,
+//   backward:  output gradients from the taped x and s, the hidden units recomputed (h stays in registers),
+//              then g = relu'(h) * W1[:, chunk]^T gout,
 //              partial input gradients to shared memory, and the chunk's weight gradients with lanes =
 //              matrix entries (h and g pass through a per-warp slab; an entry is one 32-sample dot product);
 //              every (layer, net, chunk) block of the CTA's private partial row has exactly one owner
@@ -1080,7 +1081,7 @@ __global__ void flow_apply_lean_kernel(CnfDims d, const float* __restrict__ pack
 // --------------------------------------------------------------------------------------
 constexpr int SPL_TS = 32;
 
-struct SplitSmem { int tab, act, gact, tape, part, gout, gld, ldp, slab, w, total; };
+struct SplitSmem { int tab, act, gact, tape, stape, part, gout, gld, ldp, slab, w, total; };
 
 // NW: warps of the CTA, NWn: warps per conditioner (= 16-unit chunks of the hidden layer)
 __host__ __device__ inline SplitSmem make_split(const CnfDims& d, int NW, int NWn) {
@@ -1090,7 +1091,8 @@ __host__ __device__ inline SplitSmem make_split(const CnfDims& d, int NW, int NW
   s.tab = off; off += (d.n_tables + 3) / 4 * 4;
   s.act = off; off += d.K * SPL_TS;
   s.gact = off; off += d.K * SPL_TS;
-  s.tape = off; off += d.L * d.d0 * SPL_TS;
+  s.tape = off; off += d.L * d.d0 * SPL_TS;         // pre-layer values of the transformed logits
+  s.stape = off; off += d.L * d.d0 * SPL_TS;        // scale-net outputs of the forward pass
   s.part = off; off += 2 * NWn * dpart * SPL_TS;    // forward: [net][chunk][q]; backward: [warp][c]
   s.gout = off; off += 2 * d.d0 * SPL_TS;
   s.gld = off; off += SPL_TS;
@@ -1327,6 +1329,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
   float* act = smem + sm.act;
   float* gact = smem + sm.gact;
   float* tape = smem + sm.tape;
+  float* stape = smem + sm.stape;
   float* part = smem + sm.part;
   float* gout_s = smem + sm.gout;
   float* gout_t = gout_s + d0 * TS;
@@ -1383,6 +1386,7 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         const int p = trans[q];
         const float xv = act[p * TS + lane];
         tape[(l * d0 + q) * TS + lane] = xv;
+        stape[(l * d0 + q) * TS + lane] = sv;
         act[p * TS + lane] = xv * expf(sv) + tv;
         ld_part += sv;
       }
@@ -1410,27 +1414,23 @@ flow_train_split_kernel(CnfDims d, const float* __restrict__ packed, const int* 
         const int* trans = tab + d.tab_trans + l * d0;
         const float* Wt = Wl + (size_t)t_slot * d.net_stride;
         float hs[1][CH], ht[1][CH];
-        if (do_s) {
-          split_hidden(hs, d, d1, Wl, r0, act, cond, lane);
-          split_partial_out(part + (size_t)cw * dpart * TS, hs, d, d0, Wl, r0, lane);
-        }
-        if (do_t && par) split_hidden(ht, d, d1, Wt, r0, act, cond, lane);   // its own warps: ahead of the barrier
-        __syncthreads();
+        // output gradients of both nets from the taped x and s (the transformed logits are not inputs of this
+        // layer's nets, so stepping them back here does not disturb the recompute below)
         const float gld = gld_sm[lane];
         for (int q = warp; q < d0; q += NW) {
           const int p = trans[q];
           const float gy = gact[p * TS + lane];
           const float xv = tape[(l * d0 + q) * TS + lane];
           if (has_s) {
-            float sv = Wl[d.b_off[1] + q];
-            for (int w = 0; w < NWn; ++w) sv += part[((size_t)w * dpart + q) * TS + lane];
-            const float es = expf(sv);
+            const float es = expf(stape[(l * d0 + q) * TS + lane]);
             gout_s[q * TS + lane] = gy * xv * es + gld;
             gact[p * TS + lane] = gy * es;
           }
           gout_t[q * TS + lane] = gy;
           act[p * TS + lane] = xv;                     // the tile state steps back to the input of layer l
         }
+        if (do_s) split_hidden(hs, d, d1, Wl, r0, act, cond, lane);
+        if (do_t && par) split_hidden(ht, d, d1, Wt, r0, act, cond, lane);   // its own warps: ahead of the barrier
         __syncthreads();
         float* pg = part + (size_t)warp * dpart * TS;
         if (do_s) split_net_backward(d, d0, d1, Wl, Gl, r0, hs, gout_s, act, cond, pg, slab, true, cw == 0, lane, first);
