@@ -2011,7 +2011,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
       if ((long long)bytes <= g_max_smem - 1024) {
         const int64_t nts = (N + SPL_TS - 1) / SPL_TS;
         int per_sm = (int)(g_max_smem / (bytes + 2048));
-        const int by_threads = 2048 / (nw * 32), by_regs = 65536 / (128 * nw * 32);
+        const int by_threads = 2048 / (nw * 32), by_regs = 65536 / (64 * nw * 32);   // the kernel needs 64 registers (grid cap only)
         per_sm = per_sm < by_threads ? per_sm : by_threads;
         per_sm = per_sm < by_regs ? per_sm : by_regs;
         if (per_sm < 1) per_sm = 1;
