@@ -216,3 +216,30 @@ def test_new_entry_points_validate_arguments_without_a_device():
     desc, _keep = _lib.make_desc(16, 6, [128], True, True, _lib.PREC_BF16_TC)
     rc = lib.cnf_nll_train_step_tc(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, None, acc, one, 1 << 20, None, None)
     assert rc == -4
+
+
+def test_rows_aware_training_entry_points_validate_arguments_without_a_device():
+    """cnf_nll_train_step_rows / cnf_flow_backward_rows / cnf_grad_reduce_rows reject bad arguments before any
+    CUDA call: missing rows_used, a row count outside the partial buffer, null pointers, bf16 descriptors."""
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)          # never dereferenced: validation fails first
+    used = ctypes.c_int64(-7)
+    desc, _keep = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_FP32)
+    info, _, _ = plan_host(10, 6, [128], True, True)
+    rc = lib.cnf_nll_train_step_rows(ctypes.byref(desc), one, one, one, one, 8, 1e-7, 1.0, 0.125, one, one, None, None)
+    assert rc == -1 and b'rows_used' in lib.cnf_last_error()
+    rc = lib.cnf_flow_backward_rows(ctypes.byref(desc), one, one, one, one, one, one, one, 8, None, None)
+    assert rc == -1 and b'rows_used' in lib.cnf_last_error()
+    rc = lib.cnf_nll_train_step_rows(ctypes.byref(desc), None, one, one, one, 8, 1e-7, 1.0, 0.125, one, one,
+                                     ctypes.byref(used), None)
+    assert rc == -1
+    assert lib.cnf_grad_reduce_rows(ctypes.byref(desc), one, info.n_grad_rows + 1, one, one, None) == -1
+    assert b'out of range' in lib.cnf_last_error()
+    assert lib.cnf_grad_reduce_rows(ctypes.byref(desc), one, -1, one, one, None) == -1
+    assert lib.cnf_grad_reduce_rows(ctypes.byref(desc), None, 4, one, one, None) == -1
+    desc16, _keep16 = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_BF16_TC)
+    rc = lib.cnf_nll_train_step_rows(ctypes.byref(desc16), one, one, one, one, 8, 1e-7, 1.0, 0.125, one, one,
+                                     ctypes.byref(used), None)
+    assert rc == -4 and b'fp32' in lib.cnf_last_error()
