@@ -654,3 +654,16 @@ def test_small_batch_training_kernel_vs_oracle(K, L, H, scale, shift, N, cuda_de
     (zs2[-1].square().sum() * 1e-3 + ld2.sum()).backward()
     _, gx_o = orc.flow_backward(params, x.astype(np.float64), 2e-3 * zo[-1], np.ones(N))
     assert rel_err(xg.grad.cpu().numpy(), gx_o) < 2e-4
+
+
+@pytest.mark.parametrize('name', ['nvp_k5_oddL', 'scaleonly_k4_h888', 'c2_nvp_k10', 'c1_nice_k3', 'nvp_k7_randflip'])
+def test_tile_kernels_forced_on_the_reference_goldens(name, cuda_device, monkeypatch):
+    """The 32-sample-tile kernels for deeper conditioners (flow_apply_deep_kernel, flow_train_deep_kernel) are
+    picked by default only for wide nets; forced here onto the reference's golden cases (hidden [5,5], [8,8,8],
+    random flips, NICE), they must reproduce the reference's outputs, inverse and autograd gradients."""
+    monkeypatch.setenv('CNF_DEEP_APPLY', '1')
+    monkeypatch.setenv('CNF_DEEP_TRAIN', '1')
+    monkeypatch.setenv('CNF_SPLIT_TRAIN', '0')
+    test_forward_inverse_vs_reference_golden(name, cuda_device)
+    for tag, eps, gamma in (('cal', 1e-7, 1.0), ('script', 0.0, 1.0), ('script_nodet', 0.0, 0.0)):
+        test_fused_train_step_gradients_vs_reference_autograd(name, tag, eps, gamma, cuda_device)
