@@ -141,6 +141,33 @@ class FusedNLLTrainer:
             return
         self._graph.replay()
 
+    def _step_body(self):
+        e = self.engine
+        self.loss_acc.zero_()
+        e.nll_step(self.x, self.y, self.loss_acc, self.eps, self.gamma, self.n_total, with_grad=True,
+                   precision=self.precision)
+        if self.optim == 'adam':
+            e.adam_dev(self.lr, self.betas, self.adam_eps, self.wd)
+        else:
+            e.sgd(self.lr, self.wd)
+        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
+
+    def step_graph(self):
+        """``step()`` on all local samples as ONE CUDA-graph launch (no evaluation pass: ``fit`` takes an epoch's
+        evaluation from the next step's forward, see there).  First call: eager + capture; later calls replay.
+        Single-process only."""
+        if self.dist is not None:
+            raise RuntimeError('step_graph is single-process; use step() under torch.distributed')
+        if getattr(self, '_sgraph', None) is None:
+            self._step_body()                                    # step 0: eager, for real
+            torch.cuda.current_stream(self.x.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()                                # recorded, not executed
+            self._sgraph = g
+            return
+        self._sgraph.replay()
+
     def evaluate(self, xb=None, yb=None, out=None):
         """Loss statistics (sum(ce+gamma*ld), sum ce, sum ld, #non-finite) of a batch, summed
         over ranks, as a float64 device tensor."""
@@ -174,10 +201,10 @@ class TorchFlowCalibrator(Calibrator):
 
         # extension: precision='bf16' trains on the tcgen05 kernels (stated bf16 tolerance); default fp32
         self.precision = kwargs.get('precision', 'fp32')
-        # extension: cuda_graph=True replays each full-batch epoch as one captured CUDA graph.  Off by default:
-        # at the reference's calibration-set sizes an epoch is already GPU-bound, not launch-bound, and the
-        # eager launches run ahead of the GPU (K=3, N=10,000: 127 us per epoch eager vs 139 us replayed;
-        # K=10, N=5,000, bf16: 102 vs 126 us; profiles/microbench/c1_fit_speed.py, c2_fit_speed.py).
+        # extension: cuda_graph=True replays each full-batch optimiser step as one captured CUDA graph.  Off by
+        # default: the steady state is only ~5-10 % faster than the eager launches (K=10, N=5,000, bf16: 93 vs
+        # 104 us per epoch including the capture; K=3, N=10,000: 59 vs 61 us), and the first capture in a
+        # process costs seconds (profiles/microbench/c1_fit_speed.py, c2_fit_speed.py).
         self.cuda_graph = kwargs.get('cuda_graph', False)
         self.CE = torch.nn.CrossEntropyLoss()
         self.optimizer = torch.optim.Adam(self.flow.parameters())
@@ -221,8 +248,12 @@ class TorchFlowCalibrator(Calibrator):
         use_graph = full_batch and dist is None and bool(getattr(self, 'cuda_graph', False))
         for epoch in range(epochs):
             if use_graph:
-                trainer.epoch_graph()
-                hist[epoch].copy_(trainer.eval_acc)
+                # the same scheme as the eager branch below, with the step replayed as one graph launch
+                trainer.step_graph()
+                if epoch > 0:
+                    hist[epoch - 1].copy_(trainer.loss_acc)
+                if epoch == epochs - 1:
+                    trainer.evaluate(out=hist[epoch])
             elif full_batch:
                 # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the
                 # full batch and no shuffling effect that number IS the loss the next step's forward computes
