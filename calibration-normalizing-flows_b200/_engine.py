@@ -34,6 +34,54 @@ def require_cuda(t, what='input'):
                            'sm_100a CUDA only; there is no CPU fallback.' % (what, t.device))
 
 
+def on_device(device):
+    """Context manager: make `device` the current CUDA device for the ctypes calls inside.  libcnf
+    launches on the caller's stream, but cudaFuncSetAttribute / cudaGetDevice and the launch itself act
+    on the *current* device, so every call into the library runs under this guard (a flow may live on
+    cuda:1 while the process's current device is cuda:0, as the reference's ``dev=`` argument allows)."""
+    return torch.cuda.device(device)
+
+
+def _guarded(fn):
+    """Run an engine method with the engine's device current (no-op when it already is)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+def check_logits(x, K, what='x', cast=True):
+    """[N, K] float32 contiguous view of `x` for the C ABI (which reads N*K floats blindly).  Wrong rank or
+    column count raises ValueError like the reference's matmul would; other float dtypes are cast when
+    `cast`, else rejected."""
+    if x.dim() != 2 or x.shape[1] != K:
+        raise ValueError('cnf_b200: %s must have shape [N, %d], got %s' % (what, K, tuple(x.shape)))
+    if x.dtype != torch.float32:
+        if not cast or not x.dtype.is_floating_point:
+            raise ValueError('cnf_b200: %s must be float32, got %s' % (what, x.dtype))
+        x = x.to(torch.float32)
+    return x.contiguous()
+
+
+def check_labels(y, N, device, what='y'):
+    """int64 [N] contiguous labels on `device` (the kernels read 8 bytes per sample)."""
+    if y.dim() != 1 or y.shape[0] != N:
+        raise ValueError('cnf_b200: %s must have shape [%d], got %s' % (what, N, tuple(y.shape)))
+    if y.dtype != torch.int64:
+        if y.dtype.is_floating_point or y.dtype == torch.bool:
+            raise ValueError('cnf_b200: %s must be an integer tensor, got %s' % (what, y.dtype))
+        y = y.to(torch.int64)
+    if y.device != device:
+        raise ValueError('cnf_b200: %s lives on %s, the samples on %s' % (what, y.device, device))
+    return y.contiguous()
+
+
 class StackEngine:
     """One homogeneous stack of coupling layers (same K, hidden sizes, scale/shift flags)."""
 
@@ -129,12 +177,13 @@ class StackEngine:
     def pack(self, tc=False, fp32=True):
         """Refresh the kernel-side weight copies from `flat`: the fp32 blob (fp32=True) and/or the bf16
         tensor-core blob (tc=True)."""
-        st = _stream(self.device)
-        if fp32:
-            _lib.call('cnf_pack_weights', ctypes.byref(self.desc), _ptr(self.flat), _ptr(self.gather), _ptr(self.packed), st)
-        if tc and self.packed_tc is not None:
-            _lib.call('cnf_pack_weights_tc', ctypes.byref(self.desc_tc), _ptr(self.flat), _ptr(self.gather_tc),
-                      _ptr(self.packed_tc), st)
+        with on_device(self.device):
+            st = _stream(self.device)
+            if fp32:
+                _lib.call('cnf_pack_weights', ctypes.byref(self.desc), _ptr(self.flat), _ptr(self.gather), _ptr(self.packed), st)
+            if tc and self.packed_tc is not None:
+                _lib.call('cnf_pack_weights_tc', ctypes.byref(self.desc_tc), _ptr(self.flat), _ptr(self.gather_tc),
+                          _ptr(self.packed_tc), st)
 
     def _want_partials(self):
         if self.partials is None:
@@ -145,7 +194,7 @@ class StackEngine:
     def apply(self, x, inverse=False, want_all=False, precision='fp32', repack=True):
         """Returns (out [N,K], logdet [N], all_or_None [L,N,K])."""
         require_cuda(x)
-        x = x.detach().to(torch.float32).contiguous()
+        x = check_logits(x.detach(), self.K)
         self.ensure(x.device)
         N = x.shape[0]
         use_tc = precision == 'bf16'
@@ -160,9 +209,67 @@ class StackEngine:
         fn = 'cnf_flow_inverse' if inverse else 'cnf_flow_forward'
         desc = self.desc_tc if use_tc else self.desc
         packed = self.packed_tc if use_tc else self.packed
-        _lib.call(fn, ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x), _ptr(out), _ptr(ld),
-                  _ptr(allz), ctypes.c_int64(N), _stream(x.device))
+        with on_device(x.device):
+            _lib.call(fn, ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x), _ptr(out), _ptr(ld),
+                      _ptr(allz), ctypes.c_int64(N), _stream(x.device))
         return out, ld, allz
+
+    def predict(self, x, center=False, log_priors=None, y=None, bins=15, want_z=False, want_probs=False,
+                precision='fp32', repack=True):
+        """One fused launch (cnf_flow_predict): [row-mean centring] -> flow forward -> calibrated probabilities
+        ``softmax(log(softmax(z)+1e-7) - log_priors)`` (or the statistics of plain ``softmax(z)`` when
+        `log_priors` is None) and / or the ECE-NLL-accuracy statistics against labels `y`, without z making a
+        round trip through HBM.  Returns a dict with the requested entries: 'z', 'logdet' (want_z), 'probs'
+        float64 (want_probs, needs log_priors), 'stats' float64 [3*bins+3] (when y is given).  Shapes outside
+        the fused kernels raise NotImplementedError (callers then compose apply() + the metrics kernel)."""
+        require_cuda(x)
+        x = check_logits(x.detach(), self.K)
+        dev = x.device
+        self.ensure(dev)
+        N = x.shape[0]
+        use_tc = precision == 'bf16'
+        if use_tc and self.packed_tc is None:
+            raise NotImplementedError('cnf_b200: the bf16 tensor-core path does not cover this flow shape')
+        if want_probs and log_priors is None:
+            raise ValueError('cnf_b200: calibrated probabilities need log_priors')
+        if repack:
+            self.pack(tc=use_tc)
+        mode = _lib.METRICS_CALIBRATED if log_priors is not None else _lib.METRICS_LOGITS
+        lp = None
+        if log_priors is not None:
+            lp = torch.as_tensor(np.asarray(log_priors, dtype=np.float64)).to(dev).contiguous()
+            if lp.numel() != self.K:
+                raise ValueError('cnf_b200: log_priors must have %d entries' % self.K)
+        z = ld = probs = acc = edges = None
+        if want_z:
+            z = torch.empty_like(x)
+            ld = torch.empty(N, dtype=torch.float32, device=dev)
+        if want_probs:
+            probs = torch.empty((N, self.K), dtype=torch.float64, device=dev)
+        if y is not None:
+            y = check_labels(y, N, dev)
+            acc = torch.zeros(3 * bins + 3, dtype=torch.float64, device=dev)
+            edges = torch.tensor([i * (1. / bins) for i in range(bins + 1)], dtype=torch.float64, device=dev)
+        desc = self.desc_tc if use_tc else self.desc
+        packed = self.packed_tc if use_tc else self.packed
+        with on_device(dev):
+            try:
+                _lib.call('cnf_flow_predict', ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x),
+                          ctypes.c_int64(N), ctypes.c_int32(1 if center else 0), ctypes.c_int32(mode), _ptr(lp),
+                          _ptr(z), _ptr(ld), _ptr(probs), _ptr(y), ctypes.c_int32(bins), _ptr(edges), _ptr(acc),
+                          _stream(dev))
+            except _lib.CnfError as e:
+                if e.code in (-3, -4):       # CNF_E_SMEM / CNF_E_UNSUPPORTED: shape outside the fused kernels
+                    raise NotImplementedError(str(e))
+                raise
+        out = {}
+        if want_z:
+            out['z'], out['logdet'] = z, ld
+        if want_probs:
+            out['probs'] = probs
+        if acc is not None:
+            out['stats'] = acc
+        return out
 
     def apply_host(self, x_host, out_host=None, ld_host=None, inverse=False, precision='fp32',
                    chunk=1 << 17, slots=4, repack=True, device=None):
@@ -174,12 +281,16 @@ class StackEngine:
         x_host = torch.as_tensor(x_host, dtype=torch.float32)
         if x_host.is_cuda:
             raise RuntimeError('apply_host expects host memory')
-        x_host = x_host.contiguous()
+        x_host = check_logits(x_host, self.K, 'x_host')
         N, K = x_host.shape
         if out_host is None:
             out_host = torch.empty((N, K), dtype=torch.float32, pin_memory=True)
         if ld_host is None:
             ld_host = torch.empty(N, dtype=torch.float32, pin_memory=True)
+        for t, shape, what in ((out_host, (N, K), 'out_host'), (ld_host, (N,), 'ld_host')):
+            if (not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shape
+                    or not t.is_contiguous()):
+                raise ValueError('cnf_b200: %s must be a contiguous float32 CPU tensor of shape %s' % (what, shape))
         self.ensure(device)
         use_tc = precision == 'bf16'
         if use_tc and self.packed_tc is None:
@@ -192,18 +303,27 @@ class StackEngine:
             ws = self._host_ws = torch.empty(need, dtype=torch.uint8, device=device)
         desc = self.desc_tc if use_tc else self.desc
         packed = self.packed_tc if use_tc else self.packed
-        _lib.call('cnf_flow_apply_host', ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x_host),
-                  _ptr(out_host), _ptr(ld_host), ctypes.c_int64(N), ctypes.c_int32(1 if inverse else 0), _ptr(ws),
-                  ctypes.c_int64(need), ctypes.c_int64(chunk), _stream(device))
+        with on_device(device):
+            _lib.call('cnf_flow_apply_host', ctypes.byref(desc), _ptr(packed), _ptr(self.tables), _ptr(x_host),
+                      _ptr(out_host), _ptr(ld_host), ctypes.c_int64(N), ctypes.c_int32(1 if inverse else 0), _ptr(ws),
+                      ctypes.c_int64(need), ctypes.c_int64(chunk), _stream(device))
         return out_host, ld_host
 
     def backward(self, x, g_z, g_ld, need_gx=True):
         """Generic autograd backward: returns (g_x or None, flat_grad)."""
         self.ensure(x.device)
+        with on_device(x.device):
+            return self._backward(x, g_z, g_ld, need_gx)
+
+    def _backward(self, x, g_z, g_ld, need_gx):
         self._want_partials()
+        x = check_logits(x, self.K, cast=False)
         N = x.shape[0]
         g_z = g_z.to(torch.float32).contiguous()
         g_ld = g_ld.to(torch.float32).contiguous()
+        if g_z.shape != x.shape or g_ld.numel() != N:
+            raise ValueError('cnf_b200: upstream gradients of shape %s / %s do not match the output [%d, %d] / [%d]'
+                             % (tuple(g_z.shape), tuple(g_ld.shape), N, self.K, N))
         gx = torch.empty_like(x) if need_gx else None
         st = _stream(x.device)
         used = ctypes.c_int64(0)     # only the partial rows the launch wrote are cleared and reduced
@@ -215,6 +335,19 @@ class StackEngine:
         return gx, flat_grad
 
     TRAIN_CHUNK = 1 << 20   # samples per forward/backward kernel pair on the tensor-core training path
+
+    def _check_batch(self, x, y, loss_acc):
+        """The training kernels read N*K floats and N int64 labels blindly."""
+        if x.dim() != 2 or x.shape[1] != self.K or x.dtype != torch.float32 or not x.is_contiguous():
+            raise ValueError('cnf_b200: x must be a contiguous float32 [N, %d] tensor, got %s %s'
+                             % (self.K, x.dtype, tuple(x.shape)))
+        if y.dim() != 1 or y.shape[0] != x.shape[0] or y.dtype != torch.int64 or not y.is_contiguous():
+            raise ValueError('cnf_b200: y must be a contiguous int64 [%d] tensor, got %s %s'
+                             % (x.shape[0], y.dtype, tuple(y.shape)))
+        if not x.is_cuda or y.device != x.device or loss_acc.device != x.device:
+            raise ValueError('cnf_b200: x, y and loss_acc must live on the same CUDA device')
+        if loss_acc.dtype != torch.float64 or loss_acc.numel() < 4:
+            raise ValueError('cnf_b200: loss_acc must be float64 [4]')
 
     def _nll_step_tc(self, x, y, loss_acc, eps, gamma, n_total, with_grad):
         if self.tc_train is None:
@@ -241,6 +374,7 @@ class StackEngine:
             _lib.call('cnf_grad_reduce_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc), used,
                       _ptr(self.gather_tcgrad), _ptr(self.flat_grad), st)
 
+    @_guarded
     def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision='fp32'):
         """One fused forward+loss(+backward) pass over the local samples.  Accumulates the
         loss sums into loss_acc (float64 [4], device) and, with_grad, leaves
@@ -248,6 +382,7 @@ class StackEngine:
         backward kernels (weights must have been packed with pack(tc=True))."""
         N = x.shape[0]
         n_total = N if n_total is None else n_total
+        self._check_batch(x, y, loss_acc)
         if precision == 'bf16':
             return self._nll_step_tc(x, y, loss_acc, eps, gamma, n_total, with_grad)
         st = _stream(x.device)
@@ -262,6 +397,7 @@ class StackEngine:
             _lib.call('cnf_grad_reduce_rows', ctypes.byref(self.desc), _ptr(self.partials), used, _ptr(self.gather),
                       _ptr(self.flat_grad), st)
 
+    @_guarded
     def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if getattr(self, 'adam_step_dev', None) is not None:      # steps were taken on the device-counted path
             return self.adam_dev(lr, betas, eps, weight_decay)
@@ -275,6 +411,7 @@ class StackEngine:
                   ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
                   ctypes.c_float(weight_decay), _stream(self.device))
 
+    @_guarded
     def adam_dev(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """Adam with the step count kept on the device (cnf_adam_step_dev): no host state, so the call can
         sit inside a captured CUDA graph.  Continues from the host-counted steps taken so far."""
@@ -290,6 +427,7 @@ class StackEngine:
                   ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
                   ctypes.c_float(weight_decay), _stream(self.device))
 
+    @_guarded
     def sgd(self, lr, weight_decay=0.0):
         _lib.call('cnf_sgd_step', _ptr(self.flat), _ptr(self.flat_grad), ctypes.c_int64(self.n_flat),
                   ctypes.c_float(lr), ctypes.c_float(weight_decay), _stream(self.device))

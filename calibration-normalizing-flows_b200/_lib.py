@@ -30,7 +30,11 @@ class PlanInfo(ctypes.Structure):
 
 
 class CnfError(RuntimeError):
-    pass
+    """A libcnf_b200 call returned a negative CNF_E_* code (``.code``)."""
+
+    def __init__(self, msg, code=0):
+        super().__init__(msg)
+        self.code = code
 
 
 _P = ctypes.c_void_p
@@ -47,6 +51,7 @@ SIGNATURES = {
     'cnf_pack_weights_tc': [_DESC, _P, _P, _P, _P],
     'cnf_flow_forward': [_DESC, _P, _P, _P, _P, _P, _P, _I64, _P],
     'cnf_flow_inverse': [_DESC, _P, _P, _P, _P, _P, _P, _I64, _P],
+    'cnf_flow_predict': [_DESC, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P],
     'cnf_flow_apply_host': [_DESC, _P, _P, _P, _P, _P, _I64, _I32, _P, _I64, _I64, _P],
     'cnf_nll_train_step': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P],
     'cnf_flow_backward': [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
@@ -100,7 +105,7 @@ def load():
 
 def check(rc):
     if rc != 0:
-        raise CnfError('libcnf_b200 error %d: %s' % (rc, load().cnf_last_error().decode()))
+        raise CnfError('libcnf_b200 error %d: %s' % (rc, load().cnf_last_error().decode()), rc)
 
 
 def call(name, *args):

@@ -23,7 +23,7 @@ import torch
 from scipy.special import softmax
 
 from . import _lib
-from ._engine import _ptr, _stream
+from ._engine import _ptr, _stream, on_device, check_logits, check_labels
 from .utils.ops import onehot_encode
 
 
@@ -66,14 +66,43 @@ def shard_bounds(n, rank, world):
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
+def plan_fit(n_all, world, batch_size):
+    """Rank-invariant schedule of one ``fit`` epoch over `n_all` samples sharded over `world` ranks:
+    (full_batch, local_bs, steps_per_epoch, batch_totals).  Depends on (n_all, world, batch_size) only --
+    never on a rank's own shard size -- so every rank issues the same sequence of collectives even when
+    n_all % world != 0 (shards then differ by one row; the shorter ones contribute an empty slice to the
+    last step).  batch_totals[s] = true number of samples all ranks together feed into step s (the
+    gradient of step s is the mean over exactly those)."""
+    world = max(1, int(world))
+    shards = [shard_bounds(n_all, r, world) for r in range(world)]
+    max_shard = max(hi - lo for lo, hi in shards)
+    bs = max(1, int(batch_size))
+    full_batch = bs >= n_all
+    local_bs = max(1, bs // world)
+    steps = 1 if full_batch else max(1, -(-max_shard // local_bs))
+    if full_batch:
+        totals = [n_all]
+    else:
+        totals = [sum(min(max((hi - lo) - s * local_bs, 0), local_bs) for lo, hi in shards) for s in range(steps)]
+    return full_batch, local_bs, steps, totals
+
+
 class FusedNLLTrainer:
     """The calibrator's optimisation loop on device buffers.  Data-parallel when
-    torch.distributed is initialised: every rank holds a contiguous shard of the samples, the
-    flat gradient (and the loss sums) are all-reduced once per step, and every rank applies the
-    same optimiser update, so parameters stay bit-identical across ranks without a broadcast."""
+    torch.distributed is initialised: every rank holds a contiguous shard of the samples; per step the
+    flat gradient and the four loss sums travel in ONE all-reduce (a float64 buffer [n_flat + 4]: the
+    loss sums keep their precision and the gradient sum is rounded once), and every rank applies the
+    same optimiser update.  The initial parameters, optimiser state and random_flip permutations are
+    taken from rank 0 at construction (each rank builds its flow from its own RNG state), so
+    parameters are bit-identical across ranks from the first step on."""
 
     def __init__(self, engine, x, y, n_total=None, eps=1e-7, gamma=1.0, lr=1e-3, betas=(0.9, 0.999),
                  adam_eps=1e-8, weight_decay=0.0, optim='adam', precision='fp32'):
+        if x.is_cuda:                # (host-logic tests inject a CPU engine; the product engine is CUDA-only)
+            x = check_logits(x, engine.K, cast=False)
+            y = check_labels(y, x.shape[0], x.device)
+        elif x.dim() != 2 or x.shape[1] != engine.K or y.shape[0] != x.shape[0]:
+            raise ValueError('cnf_b200: x must be [N, %d] and y [N], got %s / %s' % (engine.K, tuple(x.shape), tuple(y.shape)))
         self.engine, self.x, self.y = engine, x, y
         self.precision = precision
         self.n_local = x.shape[0]
@@ -88,26 +117,78 @@ class FusedNLLTrainer:
         self.eps, self.gamma = eps, gamma
         self.lr, self.betas, self.adam_eps, self.wd, self.optim = lr, betas, adam_eps, weight_decay, optim
         engine.ensure(x.device)
+        if self.dist is not None:
+            self._sync_from_rank0()
         engine.pack(tc=(precision == 'bf16'), fp32=(precision != 'bf16'))
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=x.device)
+        self._comm = None
+
+    def _sync_from_rank0(self):
+        """Every rank must start from the same model: compare the index tables (random_flip permutations are
+        structure, they cannot be patched in) and broadcast the parameters and Adam state from rank 0."""
+        e, d = self.engine, self.dist
+        tab = e.tables.to(torch.int64).clone()
+        ref = tab.clone()
+        d.broadcast(ref, src=0)
+        same = torch.tensor([1 if (ref.numel() == tab.numel() and bool((ref == tab).all())) else 0],
+                            dtype=torch.int64, device=tab.device)
+        d.all_reduce(same, op=d.ReduceOp.MIN)
+        if int(same.item()) != 1:
+            raise RuntimeError('cnf_b200: the flow\'s random_flip permutations differ between ranks; seed numpy '
+                               'identically on every rank before building the flow (np.random.seed)')
+        d.broadcast(e.flat, src=0)
+        has_state = torch.tensor([0 if e.adam_m is None else 1], dtype=torch.int64, device=e.flat.device)
+        d.broadcast(has_state, src=0)
+        if int(has_state.item()):
+            if e.adam_m is None:
+                e.adam_m, e.adam_v = torch.zeros_like(e.flat), torch.zeros_like(e.flat)
+            t = torch.tensor([e.adam_t], dtype=torch.int64, device=e.flat.device)
+            d.broadcast(e.adam_m, src=0)
+            d.broadcast(e.adam_v, src=0)
+            d.broadcast(t, src=0)
+            e.adam_t = int(t.item())
+
+    def _all_reduce_step(self, loss_acc):
+        """Gradient + loss sums in one collective."""
+        e = self.engine
+        n = e.n_flat
+        if self._comm is None or self._comm.numel() != n + 4 or self._comm.device != e.flat_grad.device:
+            self._comm = torch.empty(n + 4, dtype=torch.float64, device=e.flat_grad.device)
+        c = self._comm
+        c[:n].copy_(e.flat_grad)
+        c[n:].copy_(loss_acc)
+        self.dist.all_reduce(c)
+        e.flat_grad.copy_(c[:n])
+        loss_acc.copy_(c[n:])
+
+    def _optim_and_pack(self, dev_counter=False):
+        e = self.engine
+        if self.optim == 'adam':
+            (e.adam_dev if dev_counter else e.adam)(self.lr, self.betas, self.adam_eps, self.wd)
+        else:
+            e.sgd(self.lr, self.wd)
+        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
 
     def step(self, xb=None, yb=None, n_batch_total=None):
-        """One optimiser step on (xb, yb) (default: all local samples).  Returns nothing;
-        the summed loss statistics of the batch are left in self.loss_acc (device)."""
+        """One optimiser step on (xb, yb) (default: all local samples; an empty batch is a valid
+        contribution of zero under torch.distributed).  Returns nothing; the summed loss statistics of the
+        batch are left in self.loss_acc (device)."""
         e = self.engine
         xb = self.x if xb is None else xb
         yb = self.y if yb is None else yb
         n_tot = self.n_total if n_batch_total is None else n_batch_total
+        nvtx = torch.cuda.nvtx
         self.loss_acc.zero_()
+        nvtx.range_push('cnf.fwd_bwd')
         e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision)
+        nvtx.range_pop()
         if self.dist is not None:
-            self.dist.all_reduce(e.flat_grad)
-            self.dist.all_reduce(self.loss_acc)
-        if self.optim == 'adam':
-            e.adam(self.lr, self.betas, self.adam_eps, self.wd)
-        else:
-            e.sgd(self.lr, self.wd)
-        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
+            nvtx.range_push('cnf.all_reduce')
+            self._all_reduce_step(self.loss_acc)
+            nvtx.range_pop()
+        nvtx.range_push('cnf.optim')
+        self._optim_and_pack()
+        nvtx.range_pop()
 
     # ------------------------------------------------------------------ CUDA-graph epoch
     def _epoch_body(self):
@@ -115,21 +196,20 @@ class FusedNLLTrainer:
         self.loss_acc.zero_()
         e.nll_step(self.x, self.y, self.loss_acc, self.eps, self.gamma, self.n_total, with_grad=True,
                    precision=self.precision)
-        if self.optim == 'adam':
-            e.adam_dev(self.lr, self.betas, self.adam_eps, self.wd)
-        else:
-            e.sgd(self.lr, self.wd)
-        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
+        if self.dist is not None:
+            self._all_reduce_step(self.loss_acc)
+        self._optim_and_pack(dev_counter=True)
         self.eval_acc.zero_()
         e.nll_step(self.x, self.y, self.eval_acc, self.eps, self.gamma, self.n_total, with_grad=False,
                    precision=self.precision)
+        if self.dist is not None:
+            self.dist.all_reduce(self.eval_acc)
 
     def epoch_graph(self):
         """One full-batch epoch of ``fit`` -- optimiser step, then the evaluation pass into ``self.eval_acc``
         -- as ONE CUDA-graph launch.  The first call runs the body eagerly (allocating every buffer) and
-        captures it; later calls replay (~10 launches per epoch become one).  Single-process only; with torch.distributed the eager ``step`` / ``evaluate`` pair is used."""
-        if self.dist is not None:
-            raise RuntimeError('epoch_graph is single-process; use step() / evaluate() under torch.distributed')
+        captures it; later calls replay (~10 launches per epoch become one).  Under torch.distributed (NCCL)
+        the all-reduce is part of the captured graph; every rank must then call this the same number of times."""
         if getattr(self, '_graph', None) is None:
             self.eval_acc = torch.zeros(4, dtype=torch.float64, device=self.x.device)
             self._epoch_body()                                   # epoch 0: eager, for real
@@ -146,18 +226,14 @@ class FusedNLLTrainer:
         self.loss_acc.zero_()
         e.nll_step(self.x, self.y, self.loss_acc, self.eps, self.gamma, self.n_total, with_grad=True,
                    precision=self.precision)
-        if self.optim == 'adam':
-            e.adam_dev(self.lr, self.betas, self.adam_eps, self.wd)
-        else:
-            e.sgd(self.lr, self.wd)
-        e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
+        if self.dist is not None:
+            self._all_reduce_step(self.loss_acc)
+        self._optim_and_pack(dev_counter=True)
 
     def step_graph(self):
         """``step()`` on all local samples as ONE CUDA-graph launch (no evaluation pass: ``fit`` takes an epoch's
         evaluation from the next step's forward, see there).  First call: eager + capture; later calls replay.
-        Single-process only."""
-        if self.dist is not None:
-            raise RuntimeError('step_graph is single-process; use step() under torch.distributed')
+        Under torch.distributed (NCCL) the one all-reduce of the step is captured with it."""
         if getattr(self, '_sgraph', None) is None:
             self._step_body()                                    # step 0: eager, for real
             torch.cuda.current_stream(self.x.device).synchronize()
@@ -167,6 +243,43 @@ class FusedNLLTrainer:
             self._sgraph = g
             return
         self._sgraph.replay()
+
+    def fit_loop(self, epochs, batch_size, perm_fn, cuda_graph=False):
+        """The epoch loop of ``TorchFlowCalibrator.fit`` (calibrators.py:283-317) on the resident local
+        samples.  Returns the per-epoch loss sums [epochs, 4] (float64, summed over ranks; divide by n_total).
+        `perm_fn(n_local)` yields the shuffled order of the local samples for one pass."""
+        x, y = self.x, self.y
+        n_local, n_all = self.n_local, self.n_total
+        world = self.dist.get_world_size() if self.dist is not None else 1
+        # Every decision that shapes the sequence of collectives comes from (n_all, world, batch_size) only
+        # (plan_fit), never from the rank-local shard size.
+        full_batch, local_bs, steps_per_epoch, batch_totals = plan_fit(n_all, world, batch_size)
+        hist = torch.zeros((max(epochs, 0), 4), dtype=torch.float64, device=x.device)
+        use_graph = full_batch and cuda_graph
+        for epoch in range(epochs):
+            if full_batch:
+                # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the
+                # full batch and no shuffling effect that number IS the loss the next step's forward computes
+                # on the same weights and samples, so it is taken from there; only the last epoch needs its
+                # own evaluation pass.  Same kernels, same arithmetic: the history is unchanged.
+                if use_graph:
+                    self.step_graph()       # the same step replayed as one captured graph launch
+                else:
+                    self.step()
+                if epoch > 0:
+                    hist[epoch - 1].copy_(self.loss_acc)
+                if epoch == epochs - 1:
+                    self.evaluate(out=hist[epoch])
+            else:
+                perm = perm_fn(n_local)
+                for s in range(steps_per_epoch):
+                    idx = perm[s * local_bs:(s + 1) * local_bs]        # may be empty on the shorter shards
+                    self.step(x.index_select(0, idx), y.index_select(0, idx), n_batch_total=batch_totals[s])
+                # reference quirk: only the last evaluation batch survives (calibrators.py:309-317)
+                perm = perm_fn(n_local)
+                last = perm[(steps_per_epoch - 1) * local_bs:steps_per_epoch * local_bs]
+                self.evaluate(x.index_select(0, last), y.index_select(0, last), out=hist[epoch])
+        return hist
 
     def evaluate(self, xb=None, yb=None, out=None):
         """Loss statistics (sum(ce+gamma*ld), sum ce, sum ld, #non-finite) of a batch, summed
@@ -238,42 +351,11 @@ class TorchFlowCalibrator(Calibrator):
                                   betas=group['betas'], adam_eps=group['eps'], weight_decay=group['weight_decay'],
                                   precision=getattr(self, 'precision', 'fp32'))
         self.trainer = trainer
-        n_local = x.shape[0]
-        world = dist.get_world_size() if dist is not None else 1
-        local_bs = max(1, min(n_local, int(batch_size) // world if dist is not None else int(batch_size)))
-        full_batch = local_bs >= n_local
-        hist = torch.zeros((max(epochs, 0), 4), dtype=torch.float64, device=self.dev)
         gen = torch.Generator(device=self.dev)
         gen.manual_seed(int(torch.initial_seed()) & 0x7fffffff)
-        use_graph = full_batch and dist is None and bool(getattr(self, 'cuda_graph', False))
-        for epoch in range(epochs):
-            if use_graph:
-                # the same scheme as the eager branch below, with the step replayed as one graph launch
-                trainer.step_graph()
-                if epoch > 0:
-                    hist[epoch - 1].copy_(trainer.loss_acc)
-                if epoch == epochs - 1:
-                    trainer.evaluate(out=hist[epoch])
-            elif full_batch:
-                # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the
-                # full batch and no shuffling effect that number IS the loss the next step's forward computes
-                # on the same weights and samples, so it is taken from there; only the last epoch needs its
-                # own evaluation pass.  Same kernels, same arithmetic: the history is unchanged.
-                trainer.step()
-                if epoch > 0:
-                    hist[epoch - 1].copy_(trainer.loss_acc)
-                if epoch == epochs - 1:
-                    trainer.evaluate(out=hist[epoch])
-            else:
-                perm = torch.randperm(n_local, device=self.dev, generator=gen)
-                for s in range(0, n_local, local_bs):
-                    idx = perm[s:s + local_bs]
-                    nb = idx.numel() * world
-                    trainer.step(x.index_select(0, idx), y.index_select(0, idx), n_batch_total=nb)
-                # reference quirk: only the last evaluation batch survives (calibrators.py:309-317)
-                perm = torch.randperm(n_local, device=self.dev, generator=gen)
-                last = perm[(n_local - 1) // local_bs * local_bs:]
-                trainer.evaluate(x.index_select(0, last), y.index_select(0, last), out=hist[epoch])
+        gen_holder = [gen]
+        hist = trainer.fit_loop(epochs, batch_size, lambda n: self._epoch_permutation(n, gen_holder[0]),
+                                cuda_graph=bool(getattr(self, 'cuda_graph', False)))
         hist = hist / float(n_all)
         history = {
             'loss': [v for v in (-hist[:, 0]).to(torch.float32).unbind(0)],
@@ -284,6 +366,11 @@ class TorchFlowCalibrator(Calibrator):
         self.flow.cpu()
         torch.cuda.empty_cache()
         return history
+
+    def _epoch_permutation(self, n_local, gen):
+        """Shuffled order of the local samples for one pass (the reference's DataLoader(shuffle=True),
+        calibrators.py:274).  A hook: tests pin it to compare the mini-batch branch with the oracle."""
+        return torch.randperm(n_local, device=self.dev, generator=gen)
 
     # ------------------------------------------------------------------ inference
     def _forward_device(self, logits):
@@ -304,16 +391,66 @@ class TorchFlowCalibrator(Calibrator):
     def predict_post(self, logits):
         return softmax(self.predict_logits(logits), axis=1)
 
+    def _fused(self, logits, target=None, bins=15, want_probs=True):
+        """The fused pass (cnf_flow_predict): raw logits -> row-mean centring (calibrators.py:42) -> flow ->
+        ``softmax(log(softmax(z)+1e-7) - log_priors)`` (:44) [-> ECE / NLL / accuracy statistics] in ONE
+        kernel launch.  Returns the engine's result dict, or None when the flow / shape is outside the fused
+        kernels (float64 input, K > 128, heterogeneous flows): the caller then composes the separate kernels."""
+        eng = self.flow.engine() if hasattr(self.flow, 'engine') else None
+        logits = np.asarray(logits) if not isinstance(logits, torch.Tensor) else logits
+        if eng is None or eng.K > 128 or logits.dtype not in (np.float32, torch.float32):
+            return None          # numpy centres float64 logits in float64: keep that arithmetic on the host
+        x = torch.as_tensor(np.ascontiguousarray(logits) if not isinstance(logits, torch.Tensor) else logits)
+        self.flow.to(self.dev)
+        x = x.to(self.dev)
+        y = None
+        if target is not None:
+            t = np.asarray(target) if not isinstance(target, torch.Tensor) else target
+            if t.ndim == 2:
+                t = t.argmax(1)
+            y = torch.as_tensor(t).to(torch.int64).to(self.dev)
+        try:
+            return eng.predict(x, center=True, log_priors=self.log_priors, y=y, bins=bins, want_probs=want_probs,
+                               precision=getattr(self, 'precision', 'fp32'))
+        except NotImplementedError:
+            return None
+
     def predict(self, logits):
-        """Same result as the base-class ``predict`` (calibrators.py:40-44) with the whole tail
-        fused on the device; returns float64 probabilities."""
+        """Same result as the base-class ``predict`` (calibrators.py:40-44): float64 calibrated probabilities.
+        Centring, flow and the predict tail run as one kernel launch (see ``_fused``)."""
+        res = self._fused(logits)
+        if res is not None:
+            out = res['probs'].cpu().numpy()
+            self.flow.cpu()
+            return out
         logits = np.asarray(logits)
         z = self._forward_device(logits - logits.mean(axis=1, keepdims=True)).contiguous()
         n, k = z.shape
         lp = torch.as_tensor(np.asarray(self.log_priors, dtype=np.float64)).to(self.dev)
         out = torch.empty((n, k), dtype=torch.float64, device=self.dev)
-        _lib.call('cnf_calibrated_probs', _ptr(z), ctypes.c_int64(n), ctypes.c_int32(k), _ptr(lp), _ptr(out),
-                  _stream(self.dev))
+        with on_device(self.dev):
+            _lib.call('cnf_calibrated_probs', _ptr(z), ctypes.c_int64(n), ctypes.c_int32(k), _ptr(lp), _ptr(out),
+                      _stream(self.dev))
         res = out.cpu().numpy()
         self.flow.cpu()
         return res
+
+    def evaluate(self, logits, target, bins=15, reduce=True):
+        """ECE / NLL / accuracy of the calibrated probabilities ``self.predict(logits)`` against `target`
+        (what the notebooks compute with utils/metrics.py:35-73, 6-15, 76-80 on the calibrator's output) in
+        one fused pass: the probabilities are never materialised.  Under torch.distributed every rank passes
+        its own shard of (logits, target) and, with `reduce`, the 3*bins+3 sufficient statistics are
+        all-reduced before the metrics are formed, so every rank returns the metrics of the whole set."""
+        from .utils import metrics as M
+        res = self._fused(logits, target=target, bins=bins, want_probs=False)
+        if res is not None:
+            stats = res['stats']
+        else:
+            logits = np.asarray(logits)
+            z = self._forward_device(logits - logits.mean(axis=1, keepdims=True)).contiguous()
+            stats = M.statistics(z, target, bins=bins, mode=_lib.METRICS_CALIBRATED, log_priors=self.log_priors,
+                                 device=self.dev)
+        if reduce:
+            stats = M.reduce_statistics(stats)
+        self.flow.cpu()
+        return M.metrics_from_statistics(stats, bins)

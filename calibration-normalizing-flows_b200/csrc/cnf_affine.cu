@@ -79,7 +79,7 @@ __global__ void affine_backward_kernel(const float* __restrict__ x, const float*
 
 extern "C" int cnf_affine_const(const float* x, const float* s, const float* t, float* z, int64_t N, int32_t K,
                                 int32_t inverse, void* stream) {
-  if (N < 0 || K < 1 || K > 8192) { cnf_set_error("cnf_affine_const: bad argument"); return CNF_E_ARG; }
+  if (N < 0 || K < 1 || K > 1024) { cnf_set_error("cnf_affine_const: bad argument (1 <= K <= 1024, as the backward pass)"); return CNF_E_ARG; }
   if (N == 0) return CNF_OK;      // an empty batch may come with null data pointers
   if (!x || !z) { cnf_set_error("cnf_affine_const: null pointer"); return CNF_E_ARG; }
   int dev = 0, sms = 0;

@@ -14,6 +14,13 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
 int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                  float* logdet, int64_t N, int inverse, cudaStream_t st);
 
+
+
+int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
+                     float* logdet, int64_t N, const CnfTail& ta, cudaStream_t st);
+int cnf_tc_predict(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                   float* logdet, int64_t N, const CnfTail& ta, cudaStream_t st);
+
 static int check_prec(const cnf_flow_desc* desc) {
   if (!desc) { cnf_set_error("null descriptor"); return CNF_E_ARG; }
   if (desc->precision != CNF_PREC_FP32 && desc->precision != CNF_PREC_BF16_TC) {
@@ -43,6 +50,27 @@ extern "C" int cnf_flow_inverse(const cnf_flow_desc* desc, const void* packed, c
     return cnf_tc_apply(desc, packed, tables, z, x, logdet, N, 1, (cudaStream_t)stream);
   }
   return cnf_fp32_apply(desc, (const float*)packed, tables, z, x, logdet, xs, N, 1, (cudaStream_t)stream);
+}
+
+extern "C" int cnf_flow_predict(const cnf_flow_desc* desc, const void* packed, const int32_t* tables, const float* x,
+                                int64_t N, int32_t center, int32_t mode, const double* log_priors, float* z,
+                                float* logdet, double* probs_out, const int64_t* y, int32_t bins, const double* edges,
+                                double* acc, void* stream) {
+  int rc = check_prec(desc);
+  if (rc) return rc;
+  if (N == 0) return CNF_OK;
+  if (!packed || !tables || !x || N < 0) { cnf_set_error("cnf_flow_predict: null pointer / negative N"); return CNF_E_ARG; }
+  if (mode != CNF_METRICS_LOGITS && mode != CNF_METRICS_CALIBRATED) { cnf_set_error("cnf_flow_predict: bad mode %d", mode); return CNF_E_ARG; }
+  if (mode == CNF_METRICS_CALIBRATED && !log_priors) { cnf_set_error("cnf_flow_predict: calibrated mode needs log_priors"); return CNF_E_ARG; }
+  if (probs_out && mode != CNF_METRICS_CALIBRATED) { cnf_set_error("cnf_flow_predict: probs_out needs the calibrated mode"); return CNF_E_ARG; }
+  if (acc && (!y || !edges || bins < 1 || bins > 1024)) { cnf_set_error("cnf_flow_predict: statistics need labels, edges and 1 <= bins <= 1024"); return CNF_E_ARG; }
+  if (!z && !probs_out && !acc) { cnf_set_error("cnf_flow_predict: no output requested"); return CNF_E_ARG; }
+  if (center && desc->K > 128) { cnf_set_error("cnf_flow_predict: fused centring covers K <= 128"); return CNF_E_UNSUPPORTED; }
+  CnfTail ta;
+  ta.mode = mode; ta.center = center ? 1 : 0; ta.bins = acc ? bins : 1;
+  ta.y = acc ? y : nullptr; ta.log_priors = log_priors; ta.edges = acc ? edges : nullptr; ta.acc = acc; ta.probs_out = probs_out;
+  if (desc->precision == CNF_PREC_BF16_TC) return cnf_tc_predict(desc, packed, tables, x, z, logdet, N, ta, (cudaStream_t)stream);
+  return cnf_fp32_predict(desc, (const float*)packed, tables, x, z, logdet, N, ta, (cudaStream_t)stream);
 }
 
 extern "C" int cnf_nll_train_step(const cnf_flow_desc* desc, const void* packed, const int32_t* tables, const float* x,

@@ -27,6 +27,27 @@ struct CnfDims {
   int grad_rows;
 };
 
+#ifndef __CUDACC__
+#define CNF_HD
+#else
+#define CNF_HD __host__ __device__
+#endif
+// What the fused tail of a flow kernel needs (kernel parameter, by value).  mode: CNF_METRICS_LOGITS
+// (statistics of softmax(z)) or CNF_METRICS_CALIBRATED (softmax(log(softmax(z)+1e-7) - log_priors)).
+struct CnfTail {
+  int mode, center, bins;
+  const int64_t* y;           // labels or NULL
+  const double* log_priors;   // [K] (calibrated mode)
+  const double* edges;        // [bins+1] or NULL (no ECE bins)
+  double* acc;                // [3*bins+3] or NULL (no statistics)
+  double* probs_out;          // [N,K] calibrated probabilities or NULL
+};
+
+// shared-memory bytes of the tail's per-CTA state: conf sums, log priors, float edges, counts, correct
+CNF_HD inline int cnf_tail_smem_bytes(int bins, int K) {
+  return ((bins * 8 + K * 8 + (bins + 2) * 4 + bins * 8) + 15) / 16 * 16;
+}
+
 void cnf_set_error(const char* fmt, ...);
 int cnf_make_dims(const cnf_flow_desc* desc, CnfDims* out);
 long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d);

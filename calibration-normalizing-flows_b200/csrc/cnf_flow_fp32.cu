@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "cnf_common.h"
+#include "cnf_metrics_dev.cuh"
 
 namespace {
 
@@ -48,6 +49,7 @@ struct Smem {
   int tape;    // [L][d0][TSP]
   int gout;    // [2][d0][TSP]
   int gbuf;    // [2][Hmax][TSP] (m >= 2)
+  int tail;    // fused statistics tail (forward kernel only): cnf_tail_smem_bytes / 4 floats
   int total;   // floats
 };
 
@@ -59,9 +61,10 @@ __host__ __device__ inline int hid_rows(const CnfDims& d, bool store_last) {
 }
 
 // ws: 0 = weights stay in global memory, 1 = all layers staged once, 2 = one layer staged at a time
-__host__ __device__ inline Smem make_smem(const CnfDims& d, int TSP, int ws, bool backward) {
+__host__ __device__ inline Smem make_smem(const CnfDims& d, int TSP, int ws, bool backward, int tail_bins = 0) {
   Smem s;
   int off = 0;
+  s.tail = off; off += tail_bins > 0 ? cnf_tail_smem_bytes(tail_bins, d.K) / 4 : 0;   // first: 16-byte aligned doubles
   s.w = off; off += ws == 1 ? d.n_packed : (ws == 2 ? (int)d.layer_stride : 0);
   s.tab = off; off += (d.n_tables + 3) / 4 * 4;
   s.act = off; off += d.K * TSP;
@@ -234,14 +237,29 @@ __device__ __forceinline__ void store_tile(const float* act, float* g, int64_t b
 // --------------------------------------------------------------------------------------
 // forward / inverse
 // --------------------------------------------------------------------------------------
-template <int SPT, bool WS>
-__global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+// TAIL (0 / CNF_METRICS_LOGITS / CNF_METRICS_CALIBRATED): the fused Calibrator.predict tail and ECE / NLL /
+// accuracy statistics taken from the finished tile while it is still in shared memory (calibrators.py:40-44,
+// 350-353; utils/metrics.py:35-73, 6-15, 76-80), and the row-mean centring of the raw logits as a prologue
+// (calibrators.py:17, 42).  zout / logdet may then be NULL: the pass reads 4K (+8) bytes per sample and writes
+// only what was asked for.
+template <int SPT, bool WS, int TAIL>
+__global__ void __launch_bounds__(256, 2) flow_apply_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                                   const float* __restrict__ xin, float* __restrict__ zout,
-                                  float* __restrict__ logdet, float* __restrict__ zs, int64_t N, int inverse) {
+                                  float* __restrict__ logdet, float* __restrict__ zs, int64_t N, int inverse,
+                                  CnfTail ta) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ double tail_red[32];
   const int NT = blockDim.x, tid = threadIdx.x;
   const int TS = NT * SPT, TSP = TS + 4;
-  const Smem sm = make_smem(d, TSP, WS, false);
+  const Smem sm = make_smem(d, TSP, WS, false, TAIL ? ta.bins : 0);
+  TailSmem tsm;
+  BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
+  double a_nll = 0.0;
+  unsigned a_correct = 0u, a_n = 0u;
+  if (TAIL) {
+    tsm = tail_carve(reinterpret_cast<unsigned char*>(smem + sm.tail), ta.bins, d.K);
+    tail_init(tsm, ta, d.K, tid, NT);
+  }
   int* tab = reinterpret_cast<int*>(smem + sm.tab);
   float* act = smem + sm.act;
   float* outs_s = smem + sm.outs;
@@ -257,6 +275,14 @@ __global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, c
     const int64_t base = tile * TS;
     load_tile(act, xin, base, N, d.K, TS, TSP, inverse ? pi_last : nullptr, tid, NT);
     __syncthreads();
+    if (TAIL && ta.center) {   // forward only (host-checked): act row f holds logical column f
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        float* col = act + tid + k * NT;
+        const float mean = numpy_row_mean([&](int j) -> float { return col[j * TSP]; }, d.K);
+        for (int j = 0; j < d.K; ++j) col[j * TSP] = __fsub_rn(col[j * TSP], mean);
+      }
+    }
     float ld[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k) ld[k] = 0.f;
@@ -300,12 +326,18 @@ __global__ void flow_apply_kernel(CnfDims d, const float* __restrict__ packed, c
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int64_t n = base + tid + k * NT;
-      if (n < N) logdet[n] = ld[k];
+      if (n < N && (!TAIL || logdet != nullptr)) logdet[n] = ld[k];
+      if (TAIL && n < N) {   // the finished sample, logical class order (forward: z[j] = act[pi_L(j)])
+        const float* col = act + tid + k * NT;
+        auto get = [&](int jj) -> float { return col[(inverse ? jj : pi_last[jj]) * TSP]; };
+        tail_row<TAIL == 0 ? CNF_METRICS_LOGITS : TAIL>(get, n, d.K, ta, tsm, cache, a_nll, a_correct, a_n);
+      }
     }
     __syncthreads();
-    store_tile(act, zout, base, N, d.K, TS, TSP, inverse ? nullptr : pi_last, tid, NT);
+    if (!TAIL || zout != nullptr) store_tile(act, zout, base, N, d.K, TS, TSP, inverse ? nullptr : pi_last, tid, NT);
     __syncthreads();
   }
+  if (TAIL) stats_finish_block(a_nll, a_correct, a_n, cache, tsm.s_cnt, tsm.s_cor, tsm.s_conf, ta.bins, ta.acc, tail_red, tid, NT);
 }
 
 // --------------------------------------------------------------------------------------
@@ -1944,7 +1976,7 @@ int device_limits() {
 }
 
 // Pick the widest tile whose shared-memory plan fits, preferring weights in shared memory.
-int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out) {
+int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out, int tail_bins = 0) {
   const int budget = g_max_smem - (backward ? 1024 : 256);
   const int spts[2] = {2, 1};
   // 256-thread CTAs share one staged copy of the weights between twice as many warps: 16 instead of 8
@@ -1971,7 +2003,7 @@ int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out) {
         const int spt = spts[si];
         if (nt < 128 && spt > 1) continue;
         const int TSP = nt * spt + 4;
-        const Smem sm = make_smem(d, TSP, ws, backward);
+        const Smem sm = make_smem(d, TSP, ws, backward, tail_bins);
         const size_t bytes = (size_t)sm.total * 4;
         if ((long long)bytes <= budget) {
           out->spt = spt; out->nt = nt; out->ws = ws != 0; out->smem = bytes;
@@ -2054,14 +2086,51 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   const int grid = (int)(ntiles < (int64_t)g_num_sms * ctas_per_sm ? ntiles : (int64_t)g_num_sms * ctas_per_sm);
 #define LAUNCH_APPLY(SPT, WS)                                                                         \
   do {                                                                                                \
-    if ((rc = set_smem(flow_apply_kernel<SPT, WS>, c.smem))) return rc;                               \
-    flow_apply_kernel<SPT, WS><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, z, logdet, zs, N, inverse); \
+    if ((rc = set_smem(flow_apply_kernel<SPT, WS, 0>, c.smem))) return rc;                            \
+    flow_apply_kernel<SPT, WS, 0><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, z, logdet, zs, N, inverse, CnfTail()); \
   } while (0)
   if (c.spt == 2 && c.ws) LAUNCH_APPLY(2, true);
   else if (c.spt == 2) LAUNCH_APPLY(2, false);
   else if (c.ws) LAUNCH_APPLY(1, true);
   else LAUNCH_APPLY(1, false);
 #undef LAUNCH_APPLY
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+// Fused pass of cnf_flow_predict on the fp32 path: [centring] -> flow -> [calibrated probabilities | statistics]
+// in one launch of flow_apply_kernel<.., TAIL> (every shape whose tile plan fits shared memory).
+int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
+                     float* logdet, int64_t N, const CnfTail& ta, cudaStream_t st) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (N == 0) return CNF_OK;
+  if ((rc = device_limits())) return rc;
+  LaunchCfg c;
+  c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
+  if ((rc = choose_cfg(d, false, &c, ta.bins))) return rc;
+  const int64_t ntiles = (N + c.nt * c.spt - 1) / (c.nt * c.spt);
+  int ctas_per_sm = (int)(g_max_smem / (c.smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  const int grid = (int)(ntiles < (int64_t)g_num_sms * ctas_per_sm ? ntiles : (int64_t)g_num_sms * ctas_per_sm);
+#define LAUNCH_TAIL(SPT, WS, M)                                                                        \
+  do {                                                                                                 \
+    if ((rc = set_smem(flow_apply_kernel<SPT, WS, M>, c.smem))) return rc;                             \
+    flow_apply_kernel<SPT, WS, M><<<grid, c.nt, c.smem, st>>>(d, packed, tables, x, z, logdet, nullptr, N, 0, ta); \
+  } while (0)
+#define LAUNCH_TAIL_M(SPT, WS)                                                                         \
+  do {                                                                                                 \
+    if (ta.mode == CNF_METRICS_LOGITS) LAUNCH_TAIL(SPT, WS, CNF_METRICS_LOGITS);                       \
+    else LAUNCH_TAIL(SPT, WS, CNF_METRICS_CALIBRATED);                                                 \
+  } while (0)
+  if (c.spt == 2 && c.ws) LAUNCH_TAIL_M(2, true);
+  else if (c.spt == 2) LAUNCH_TAIL_M(2, false);
+  else if (c.ws) LAUNCH_TAIL_M(1, true);
+  else LAUNCH_TAIL_M(1, false);
+#undef LAUNCH_TAIL_M
+#undef LAUNCH_TAIL
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -29,6 +29,7 @@
 #include "cnf_common.h"
 #include "cnf_tc_dims.h"
 #include "cnf_tc_ptx.cuh"
+#include "cnf_metrics_dev.cuh"
 
 int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
 // wide variant (cnf_flow_tcw.cu): used when the resident-weight kernel does not cover the shape
@@ -80,6 +81,7 @@ bool cnf_tc_dims(const CnfDims& d, TcDims* t) {
   }
   off += TC_SLOTS * t->sm_slot_stride;
   t->sm_bar = off; off += 128;
+  t->sm_tail = off;          // fused statistics tail (cnf_flow_predict): the launcher adds its bytes to sm_total
   t->sm_total = off;
   return t->sm_total <= 227 * 1024;
 }
@@ -106,13 +108,24 @@ __device__ __forceinline__ uint32_t pack_hidden(uint32_t lo, uint32_t hi) {
 // SH: 1 = the shape constants of BASELINE configs C2/C3/C5 (K = 10: d0 = d1 = 5, 128 hidden units, both nets)
 // are compile-time, which removes the guards and index arithmetic of the generic loops (about a quarter
 // of the epilogue's instructions); 0 = every shape the kernel covers, read from TcDims.
-template <int EPI, bool TAPE, int SH>
+// TAIL (0 / CNF_METRICS_LOGITS / CNF_METRICS_CALIBRATED): fused Calibrator.predict tail / ECE-NLL-accuracy
+// statistics on the finished tile and row-mean centring of the raw logits as a prologue (cnf_flow_predict).
+template <int EPI, bool TAPE, int SH, int TAIL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict__ tables,
                const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
-               int inverse, int io16, float* __restrict__ tape) {
+               int inverse, int io16, float* __restrict__ tape, CnfTail ta) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ double tail_red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TailSmem tsm;
+  BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
+  double a_nll = 0.0;
+  unsigned a_correct = 0u, a_n = 0u;
+  if (TAIL) {
+    tsm = tail_carve(smem + p.sm_tail, ta.bins, p.K);
+    tail_init(tsm, ta, p.K, tid, TC_THREADS);     // visible to the epilogue warps after the set-up barrier below
+  }
   int* tab = reinterpret_cast<int*>(smem + p.sm_tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
   // per slot s: a1_ready[s] (128 arrivals, once per layer)      epilogue -> MMA: A1 row block in smem
@@ -263,6 +276,11 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         }
       }
       wg_sync(slot);
+      if (TAIL && ta.center) {   // forward only (host-checked): act row f holds logical column f of sample t
+        float* col = act + t;
+        const float mean = numpy_row_mean([&](int j) -> float { return col[j * TILE_M]; }, K);
+        for (int j = 0; j < K; ++j) col[j * TILE_M] = __fsub_rn(col[j * TILE_M], mean);
+      }
       {
         const int64_t nxt = tile + tstep;
         prefetched = false;
@@ -366,9 +384,14 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
           }
         }
       }
-      if (base + t < N) logdet[base + t] = ld;
+      if (base + t < N && (!TAIL || logdet != nullptr)) logdet[base + t] = ld;
+      if (TAIL && base + t < N) {   // the finished sample in logical class order, still in shared memory
+        const float* col = act + t;
+        auto get = [&](int jj) -> float { return col[(inverse ? jj : pi_last[jj]) * TILE_M]; };
+        tail_row<TAIL == 0 ? CNF_METRICS_LOGITS : TAIL>(get, base + t, K, ta, tsm, cache, a_nll, a_correct, a_n);
+      }
       // ---- act -> row-major staging -> coalesced global store ---------------------------------
-      {
+      if (!TAIL || zout != nullptr) {
         int s = s0, f = f0;
         const bool full = io16 && (base + TILE_M <= N);
         float* gp = zout + base * K;
@@ -392,6 +415,8 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
           }
           wg_sync(slot);
         }
+      } else {
+        wg_sync(slot);                         // the tail has read act: the next tile may overwrite it
       }
     }
   }
@@ -401,6 +426,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
   if (warp == 3) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+  if (TAIL) stats_finish_block(a_nll, a_correct, a_n, cache, tsm.s_cnt, tsm.s_cor, tsm.s_conf, ta.bins, ta.acc, tail_red, tid, TC_THREADS);
 }
 
 int g_tc_sms = -1;
@@ -488,26 +514,43 @@ extern "C" int cnf_pack_weights_tc(const cnf_flow_desc* desc, const float* flat,
   return CNF_OK;
 }
 
-int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
-                      float* logdet, float* tape, int64_t N, int inverse, cudaStream_t st);
+int cnf_tc_apply_ex(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                    float* logdet, float* tape, int64_t N, int inverse, const CnfTail* tail, cudaStream_t st);
 
 int cnf_tc_apply(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                  float* logdet, int64_t N, int inverse, cudaStream_t st) {
-  return cnf_tc_apply_tape(desc, packed_tc, tables, x, z, logdet, nullptr, N, inverse, st);
+  return cnf_tc_apply_ex(desc, packed_tc, tables, x, z, logdet, nullptr, N, inverse, nullptr, st);
 }
 
 // tape (optional, resident-weight kernel only): float32 [L, N, 16]; per layer and sample the pre-layer
 // values of the transformed slots (0..7) and the scale-net outputs s (8..15).
 int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                       float* logdet, float* tape, int64_t N, int inverse, cudaStream_t st) {
+  return cnf_tc_apply_ex(desc, packed_tc, tables, x, z, logdet, tape, N, inverse, nullptr, st);
+}
+
+// Fused pass of cnf_flow_predict on the tensor-core path; CNF_E_UNSUPPORTED for shapes only the
+// streamed-weight kernel covers (the caller then composes the two-pass form).
+int cnf_tc_predict(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                   float* logdet, int64_t N, const CnfTail& ta, cudaStream_t st) {
+  return cnf_tc_apply_ex(desc, packed_tc, tables, x, z, logdet, nullptr, N, 0, &ta, st);
+}
+
+int cnf_tc_apply_ex(const cnf_flow_desc* desc, const void* packed_tc, const int32_t* tables, const float* x, float* z,
+                    float* logdet, float* tape, int64_t N, int inverse, const CnfTail* tail, cudaStream_t st) {
   CnfDims d; TcDims t;
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (N == 0) return CNF_OK;
-  if (!packed_tc || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
+  if (!packed_tc || !tables || !x || N < 0 || (!tail && (!z || !logdet))) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if (!cnf_tc_dims(d, &t)) {
     if (tape) { cnf_set_error("the training tape is only produced by the resident-weight tensor-core kernel"); return CNF_E_UNSUPPORTED; }
+    if (tail) { cnf_set_error("the fused predict tail is not available on the streamed-weight tensor-core kernel"); return CNF_E_UNSUPPORTED; }
     return cnf_tcw_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
+  }
+  if (tail) {
+    t.sm_total += cnf_tail_smem_bytes(tail->bins, d.K);
+    if (t.sm_total > 227 * 1024) { cnf_set_error("fused tail: %d bins do not fit shared memory", tail->bins); return CNF_E_SMEM; }
   }
   if (g_tc_sms < 0) {
     int dev = 0, s = 0;
@@ -522,17 +565,21 @@ int cnf_tc_apply_tape(const cnf_flow_desc* desc, const void* packed_tc, const in
   int epi = 0;
   if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
   const int sh = (d.K == 10 && t.Hp == 128 && d.nets == 3 && !getenv("CNF_TC_GENERIC")) ? 1 : 0;
-#define LAUNCH_TC_S(E, T, S)                                                                                    \
+  const CnfTail ta = tail ? *tail : CnfTail();
+#define LAUNCH_TC_S(E, T, S, M)                                                                                 \
   do {                                                                                                          \
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
-    flow_tc_kernel<E, T, S><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, \
-                                                                  inverse, io16, tape);                         \
+    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
+    flow_tc_kernel<E, T, S, M><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, \
+                                                                     inverse, io16, tape, ta);                  \
   } while (0)
 #define LAUNCH_TC(E, T)                                                                                         \
   do {                                                                                                          \
-    if (sh) LAUNCH_TC_S(E, T, 1); else LAUNCH_TC_S(E, T, 0);                                                    \
+    if (sh) LAUNCH_TC_S(E, T, 1, 0); else LAUNCH_TC_S(E, T, 0, 0);                                              \
   } while (0)
-  if (tape) { if (epi == 0) LAUNCH_TC(0, true); else LAUNCH_TC(1, true); }
+  if (tail) {
+    if (tail->mode == CNF_METRICS_LOGITS) { if (sh) LAUNCH_TC_S(0, false, 1, CNF_METRICS_LOGITS); else LAUNCH_TC_S(0, false, 0, CNF_METRICS_LOGITS); }
+    else { if (sh) LAUNCH_TC_S(0, false, 1, CNF_METRICS_CALIBRATED); else LAUNCH_TC_S(0, false, 0, CNF_METRICS_CALIBRATED); }
+  } else if (tape) { if (epi == 0) LAUNCH_TC(0, true); else LAUNCH_TC(1, true); }
   else      { if (epi == 0) LAUNCH_TC(0, false); else LAUNCH_TC(1, false); }
 #undef LAUNCH_TC_S
 #undef LAUNCH_TC

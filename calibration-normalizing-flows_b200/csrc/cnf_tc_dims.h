@@ -11,7 +11,7 @@ struct TcDims {
   int n_bf16, n_f32, blob_bytes;
   int tab_pi, tab_cond, tab_trans, n_tables;
   // shared-memory carve-up (bytes)
-  int sm_tab, sm_slot, sm_slot_stride, sm_act, sm_raw_in, sm_raw_out, sm_bar, sm_total;
+  int sm_tab, sm_slot, sm_slot_stride, sm_act, sm_raw_in, sm_raw_out, sm_bar, sm_tail, sm_total;
 };
 
 // false when the shape is outside the resident-weight kernel's coverage (see cnf_flow_tc.cu)

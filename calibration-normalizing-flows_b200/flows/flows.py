@@ -24,11 +24,21 @@ from .utils import MLP
 import ctypes
 
 from .. import _lib
-from .._engine import StackEngine, stack_forward, require_cuda, _ptr, _stream
+from .._engine import StackEngine, stack_forward, require_cuda, on_device, check_logits, _ptr, _stream
 
 
 def _zero_net(x):
     return x.new_zeros(x.size())
+
+
+def _vec(p, K, what):
+    """float32 contiguous [K] device vector for the C ABI; a length mismatch raises instead of reading out of bounds."""
+    if p is None:
+        return None
+    v = p.detach().to(torch.float32).contiguous().view(-1)
+    if v.numel() != K:
+        raise ValueError('cnf_b200: %s has %d entries, the input has %d columns' % (what, v.numel(), K))
+    return v
 
 
 class _AffineConstFn(torch.autograd.Function):
@@ -36,13 +46,15 @@ class _AffineConstFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, s, t):
+        if x.dim() != 2:
+            raise ValueError('cnf_b200: expected [N, K] input, got %s' % (tuple(x.shape),))
         x = x.to(torch.float32).contiguous()
         N, K = x.shape
         z = torch.empty_like(x)
-        sv = None if s is None else s.detach().to(torch.float32).contiguous()
-        tv = None if t is None else t.detach().to(torch.float32).contiguous()
-        _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(N), ctypes.c_int32(K),
-                  ctypes.c_int32(0), _stream(x.device))
+        sv, tv = _vec(s, K, 's'), _vec(t, K, 't')
+        with on_device(x.device):
+            _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(N), ctypes.c_int32(K),
+                      ctypes.c_int32(0), _stream(x.device))
         ctx.save_for_backward(x, sv)
         ctx.has = (s is not None, t is not None)
         return z
@@ -55,20 +67,23 @@ class _AffineConstFn(torch.autograd.Function):
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gs = torch.empty(K, dtype=torch.float32, device=x.device) if ctx.has[0] else None
         gt = torch.empty(K, dtype=torch.float32, device=x.device) if ctx.has[1] else None
-        _lib.call('cnf_affine_const_backward', _ptr(x), _ptr(g_z), _ptr(sv), _ptr(gx), _ptr(gs), _ptr(gt),
-                  ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        with on_device(x.device):
+            _lib.call('cnf_affine_const_backward', _ptr(x), _ptr(g_z), _ptr(sv), _ptr(gx), _ptr(gs), _ptr(gt),
+                      ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
         return gx, gs, gt
 
 
 def affine_const_apply(x, s=None, t=None, inverse=False):
     """Non-differentiable helper: forward or inverse of the per-dimension affine map."""
     require_cuda(x)
+    if x.dim() != 2:
+        raise ValueError('cnf_b200: expected [N, K] input, got %s' % (tuple(x.shape),))
     x = x.detach().to(torch.float32).contiguous()
     z = torch.empty_like(x)
-    sv = None if s is None else s.detach().to(torch.float32).contiguous().view(-1)
-    tv = None if t is None else t.detach().to(torch.float32).contiguous().view(-1)
-    _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(x.shape[0]),
-              ctypes.c_int32(x.shape[1]), ctypes.c_int32(1 if inverse else 0), _stream(x.device))
+    sv, tv = _vec(s, x.shape[1], 's'), _vec(t, x.shape[1], 't')
+    with on_device(x.device):
+        _lib.call('cnf_affine_const', _ptr(x), _ptr(sv), _ptr(tv), _ptr(z), ctypes.c_int64(x.shape[0]),
+                  ctypes.c_int32(x.shape[1]), ctypes.c_int32(1 if inverse else 0), _stream(x.device))
     return z
 
 
@@ -106,13 +121,16 @@ class _PlanarFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, u_hat, b):
+        if x.dim() != 2:
+            raise ValueError('cnf_b200: expected [N, K] input, got %s' % (tuple(x.shape),))
         x = x.to(torch.float32).contiguous()
         N, K = x.shape
-        wv, uv, bv = (t.detach().to(torch.float32).contiguous().view(-1) for t in (w, u_hat, b))
+        wv, uv, bv = _vec(w, K, 'w'), _vec(u_hat, K, 'u'), _vec(b, 1, 'b')
         z = torch.empty_like(x)
         ld = torch.empty(N, dtype=torch.float32, device=x.device)
-        _lib.call('cnf_planar_forward', _ptr(x), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(z), _ptr(ld), ctypes.c_int64(N),
-                  ctypes.c_int32(K), _stream(x.device))
+        with on_device(x.device):
+            _lib.call('cnf_planar_forward', _ptr(x), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(z), _ptr(ld), ctypes.c_int64(N),
+                      ctypes.c_int32(K), _stream(x.device))
         ctx.save_for_backward(x, wv, uv, bv)
         ctx.shapes = (w.shape, u_hat.shape, b.shape)
         return z, ld
@@ -127,8 +145,9 @@ class _PlanarFn(torch.autograd.Function):
         gw = torch.empty(K, dtype=torch.float32, device=x.device)
         gu = torch.empty(K, dtype=torch.float32, device=x.device)
         gb = torch.empty(1, dtype=torch.float32, device=x.device)
-        _lib.call('cnf_planar_backward', _ptr(x), _ptr(g_z), _ptr(g_ld), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(gx),
-                  _ptr(gw), _ptr(gu), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        with on_device(x.device):
+            _lib.call('cnf_planar_backward', _ptr(x), _ptr(g_z), _ptr(g_ld), _ptr(wv), _ptr(uv), _ptr(bv), _ptr(gx),
+                      _ptr(gw), _ptr(gu), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
         ws, us, bs = ctx.shapes
         return gx, gw.view(ws), gu.view(us), gb.view(bs)
 
@@ -167,12 +186,15 @@ class _RadialFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, z0, a, b_hat):
+        if x.dim() != 2:
+            raise ValueError('cnf_b200: expected [N, K] input, got %s' % (tuple(x.shape),))
         x = x.to(torch.float32).contiguous()
         N, K = x.shape
-        zv, av, bv = (t.detach().to(torch.float32).contiguous().view(-1) for t in (z0, a, b_hat))
+        zv, av, bv = _vec(z0, K, 'z0'), _vec(a, 1, 'a'), _vec(b_hat, 1, 'b')
         z = torch.empty_like(x)
-        _lib.call('cnf_radial_forward', _ptr(x), _ptr(zv), _ptr(av), _ptr(bv), _ptr(z), ctypes.c_int64(N),
-                  ctypes.c_int32(K), _stream(x.device))
+        with on_device(x.device):
+            _lib.call('cnf_radial_forward', _ptr(x), _ptr(zv), _ptr(av), _ptr(bv), _ptr(z), ctypes.c_int64(N),
+                      ctypes.c_int32(K), _stream(x.device))
         ctx.save_for_backward(x, zv, av, bv)
         ctx.shapes = (z0.shape, a.shape, b_hat.shape)
         return z
@@ -186,8 +208,9 @@ class _RadialFn(torch.autograd.Function):
         gz0 = torch.empty(K, dtype=torch.float32, device=x.device)
         ga = torch.empty(1, dtype=torch.float32, device=x.device)
         gb = torch.empty(1, dtype=torch.float32, device=x.device)
-        _lib.call('cnf_radial_backward', _ptr(x), _ptr(g_z), _ptr(zv), _ptr(av), _ptr(bv), _ptr(gx), _ptr(gz0),
-                  _ptr(ga), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
+        with on_device(x.device):
+            _lib.call('cnf_radial_backward', _ptr(x), _ptr(g_z), _ptr(zv), _ptr(av), _ptr(bv), _ptr(gx), _ptr(gz0),
+                      _ptr(ga), _ptr(gb), ctypes.c_int64(N), ctypes.c_int32(K), _stream(x.device))
         zs, as_, bs = ctx.shapes
         return gx, gz0.view(zs), ga.view(as_), gb.view(bs)
 

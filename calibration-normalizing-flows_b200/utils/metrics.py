@@ -3,6 +3,11 @@
 numpy (or torch) in, Python floats out, like the reference; the arithmetic is one pass of the
 ``cnf_metrics`` CUDA kernel (histogram reduction over right-closed bins).  float32 and
 float64 probability arrays are both accepted and binned in their own dtype, as NumPy does.
+
+Sharded evaluation: the kernel produces additive sufficient statistics
+(``3*bins+3`` float64 values); with ``sharded=True`` every rank of an initialised torch.distributed
+group passes its own shard and the statistics are all-reduced before the metric is formed, so each
+rank returns the metric of the whole set.  ``sharded`` is a collective: call it on every rank.
 """
 import ctypes
 
@@ -10,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._engine import _ptr, _stream
+from .._engine import _ptr, _stream, on_device
 
 
 def _device():
@@ -60,10 +65,37 @@ def statistics(values, target, bins=15, mode=_lib.METRICS_PROBS, log_priors=None
     lp = None
     if log_priors is not None:
         lp = _as_device(np.asarray(log_priors, dtype=np.float64), dev)
-    _lib.call('cnf_metrics', _ptr(v), ctypes.c_int32(1 if v.dtype == torch.float64 else 0), _ptr(y),
-              ctypes.c_int64(N), ctypes.c_int32(K), ctypes.c_int32(bins), ctypes.c_int32(mode), _ptr(lp),
-              _ptr(edges), _ptr(acc), _stream(dev))
+    if v.dim() != 2:
+        raise ValueError('cnf_b200.metrics: expected a [N, K] array, got shape %s' % (tuple(v.shape),))
+    if y.dim() != 1 or y.shape[0] != N:
+        raise ValueError('cnf_b200.metrics: %d rows but labels of shape %s' % (N, tuple(y.shape)))
+    if lp is not None and lp.numel() != K:
+        raise ValueError('cnf_b200.metrics: log_priors must have %d entries' % K)
+    with on_device(dev):
+        _lib.call('cnf_metrics', _ptr(v), ctypes.c_int32(1 if v.dtype == torch.float64 else 0), _ptr(y),
+                  ctypes.c_int64(N), ctypes.c_int32(K), ctypes.c_int32(bins), ctypes.c_int32(mode), _ptr(lp),
+                  _ptr(edges), _ptr(acc), _stream(dev))
     return acc
+
+
+def reduce_statistics(stats):
+    """Sum the sufficient statistics over the ranks of the default torch.distributed group (no-op when it
+    is not initialised or has one rank).  Works on CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return stats
+    t = stats if isinstance(stats, torch.Tensor) else torch.as_tensor(np.asarray(stats, dtype=np.float64))
+    t = t.clone()
+    dist.all_reduce(t)
+    return t
+
+
+def metrics_from_statistics(stats, bins):
+    """{'ece', 'nll', 'accuracy', 'n'} from a statistics vector (utils/metrics.py:66-73, :15, :80)."""
+    st = np.asarray(stats.cpu() if isinstance(stats, torch.Tensor) else stats, dtype=np.float64)
+    n = st[3 * bins + 2]
+    return {'ece': float(ece_from_statistics(st, bins)), 'nll': float(st[3 * bins] / n) if n > 0 else 0.0,
+            'accuracy': float(st[3 * bins + 1] / n) if n > 0 else 0.0, 'n': int(n)}
 
 
 def ece_from_statistics(stats, bins):
@@ -86,20 +118,28 @@ def _two_columns(probs):
     return probs
 
 
-def expected_calibration_error(probs, target, bins=15):
+def expected_calibration_error(probs, target, bins=15, sharded=False):
     if not isinstance(probs, torch.Tensor):
         probs = _two_columns(probs)
     stats = statistics(probs, target, bins=bins)
+    if sharded:
+        stats = reduce_statistics(stats)
     return float(ece_from_statistics(stats, bins))
 
 
-def neg_log_likelihood(probs, target):
+def neg_log_likelihood(probs, target, sharded=False):
     if not isinstance(probs, torch.Tensor):
         probs = _two_columns(probs)
-    stats = statistics(probs, target, bins=1).cpu().numpy()
+    stats = statistics(probs, target, bins=1)
+    if sharded:
+        stats = reduce_statistics(stats)
+    stats = stats.cpu().numpy()
     return float(stats[3] / stats[5])
 
 
-def accuracy(probs, target):
-    stats = statistics(probs, target, bins=1).cpu().numpy()
+def accuracy(probs, target, sharded=False):
+    stats = statistics(probs, target, bins=1)
+    if sharded:
+        stats = reduce_statistics(stats)
+    stats = stats.cpu().numpy()
     return float(stats[4] / stats[5])

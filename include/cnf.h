@@ -20,6 +20,8 @@
  *   cnf_flow_backward    autograd of Flow.forward (torch, third party)
  *   cnf_adam_step        torch.optim.Adam.step    calibrators.py:259,295
  *   cnf_sgd_step         torch.optim.SGD.step     run_experiment3D.py:59-61,135
+ *   cnf_flow_predict     Calibrator.predict / predict_post + metrics, one pass
+ *                                                 calibrators.py:17, 40-44, 350-353
  *   cnf_metrics          expected_calibration_error / neg_log_likelihood / accuracy
  *                                                 utils/metrics.py:35-73, 6-15, 76-80
  *                        (+ Calibrator.predict tail calibrators.py:40-44, 350-353)
@@ -111,6 +113,26 @@ int cnf_flow_forward(const cnf_flow_desc* desc, const void* packed, const int32_
 /* xs (optional): float32 [L, N, K]; xs[L-1] == x.                                */
 int cnf_flow_inverse(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
                      const float* z, float* x, float* logdet, float* xs, int64_t N, void* stream);
+
+/* One fused pass replacing Calibrator.predict (calibrators.py:40-44) on top of
+ * TorchFlowCalibrator.predict_post (:350-353) and, with labels, the metrics of utils/metrics.py
+ * (:35-73 ECE, :6-15 NLL, :76-80 accuracy) without a second pass over z:
+ *   center != 0: x <- x - mean(x, axis=1) per row, in numpy's float32 summation order
+ *                (calibrators.py:17, 42); K <= 128
+ *   flow forward (+ log-det)
+ *   mode CNF_METRICS_LOGITS:     p = softmax(z)                       (predict_post)
+ *        CNF_METRICS_CALIBRATED: p = softmax(log(softmax(z)+1e-7) - log_priors)   (predict)
+ * Outputs, each optional (NULL = not produced, nothing written): z [N,K] and logdet [N] float32;
+ * probs_out [N,K] float64 (calibrated mode only); acc [3*bins+3] float64 ACCUMULATED statistics of p
+ * against labels y, laid out as in cnf_metrics (needs y, edges [bins+1], 1 <= bins <= 1024).
+ * With only acc requested the pass reads 4K+8 bytes per sample and writes nothing.
+ * Shapes: the fp32 path covers every shape whose tile plan fits shared memory; the bf16 path the
+ * resident-weight tensor-core kernel (CNF_E_UNSUPPORTED otherwise: compose cnf_flow_forward +
+ * cnf_metrics / cnf_calibrated_probs).                                                          */
+int cnf_flow_predict(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
+                     const float* x, int64_t N, int32_t center, int32_t mode,
+                     const double* log_priors, float* z, float* logdet, double* probs_out,
+                     const int64_t* y, int32_t bins, const double* edges, double* acc, void* stream);
 
 /* Host-buffer variant of the two calls above: x_host / z_host / logdet_host are HOST pointers
  * (pinned memory gives full PCIe speed).  The samples stream through the GPU in chunks of `chunk`
