@@ -3,19 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Own arm.  Workload at every N: BASELINE config C2 -- RealNVP affine flow, K=10 classes, 6 coupling
-layers, hidden 128, fused forward + log-det over a batch of 1,000,000 synthetic logits per GPU per
-step (weak scaling: samples shard with no collective).  `value` = samples/s with inputs resident in
-HBM; `e2e` = the same pass through the public host-buffer API (pinned host logits -> H2D -> kernel ->
-D2H of z and log-det inside the timed region).  Extra keys: `roofline` (dominant kernel, CUDA
-events), `cpu_baseline` (the reference's arithmetic on the box's host cores), `train_step`
-(config C3 shape: fused NLL forward+backward+Adam, NCCL all-reduce of the flat gradient at N>1).
+Own arm.  A step = one fused forward + log-det pass of the RealNVP calibrator of BASELINE config C2
+(K=10 classes, 6 affine couplings, hidden 128) over 10^8 synthetic logits per GPU -- the size
+BASELINE.json's north_star quotes the headline on (configs[1] is the same shape at N=10^6; it is timed
+too, as `legs.c2_1m`).  Samples shard over GPUs with no collective (weak scaling).
+  value  samples/s with the logits resident in HBM, bf16 tcgen05 kernel (stated tolerance 1e-2); the fp32
+         kernel (the API default, 1e-5 of the reference) is timed on the same workload: `summary.fwd_fp32`.
+  e2e    the same step through the public host-buffer API (`transform_host` -> cnf_flow_apply_host):
+         pinned host logits -> H2D -> kernel -> D2H of z and log-det, all inside the timed region.
+Other legs (all in `legs`, headline numbers repeated in `summary`, the LAST key of the line):
+C3 training step (bf16 and fp32), C5 as one job (inverse sampling + fused flow->ECE/NLL/accuracy pass +
+all-reduce of the 48 statistics), the HBM-bound metrics / affine kernels, C4 (K=100, hidden 512), C1
+calibrator fit, a calibration-set-sized epoch, and at N>1 a data-parallel consistency check.
 
-Reference arm (--impl reference): the reference's own CPU implementation of the same pass
-(oracle/ref_port_torch.py: the reference's torch op sequence; /root/reference does not exist on
-the GPU box) on all host threads, rank 0 only.
+Reference arm (--impl reference): the UNMODIFIED reference (`Flow.forward`, flows/flows.py:17-25) from
+oracle/_ref/reference (copied there by __graft_entry__.build(); the GPU box has no /root/reference) on
+all host threads, rank 0 only, on a bounded sample of the same workload.  It imports nothing of the
+product.  Falls back to the torch-CPU port (oracle/ref_port_torch.py, kind "port") when the copy is absent.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,19 +36,22 @@ sys.path.insert(0, ROOT)
 METRIC = 'calibrated samples/sec (flow fwd+logdet)'
 UNIT = 'samples/s'
 K, L, HIDDEN = 10, 6, [128]
-N_STEP = 1_000_000
-N_ROT = 8                       # rotating input batches: 8 x 84 MB in+out > 126 MB L2
+N_HEAD = 100_000_000            # north-star size: 10^8 K=10 logits on one GPU (4 GB in, 4.4 GB out)
+N_C2 = 1_000_000                # BASELINE configs[1]
+N_ROT = 8                       # rotating input batches of the 10^6 leg: 8 x 84 MB in+out > 126 MB L2
+N_E2E_CHUNK = 10_000_000        # pinned host buffers of the end-to-end leg (one step = N_HEAD / this many calls)
 BYTES_PER_SAMPLE = 8 * K + 4    # read x, write z, write log-det
-FLOPS_PER_SAMPLE = L * 2 * 2 * (5 * 128 + 128 * 5)   # minimal, mask-exploiting
-WORKLOAD = 'C2: RealNVP K=10 L=6 hidden=[128], fused fwd+logdet, N=1,000,000 synthetic logits per GPU per step'
+FLOPS_PER_SAMPLE = L * 2 * 2 * (5 * 128 + 128 * 5)   # minimal, mask-exploiting: 30 720
+WORKLOAD = ('C2 shape at the north-star size: RealNVP K=10 L=6 hidden=[128], fused fwd+logdet, '
+            'N=100,000,000 synthetic logits per GPU per step')
 
 
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         p = json.load(open(path))
-        return p['hbm_gbs'], p['bf16_tflops'], 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+        return p['hbm_gbs'], p['bf16_tflops'], p.get('bf16_tflops_sustained'), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, None, 'fallback (B200_PROFILING.md)'
 
 
 class ClockSampler:
@@ -107,25 +117,14 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def make_weights(seed=1):
-    """Reference init (nn.Linear default x 0.001, flows/flows.py:76-79) x 300 = 'trained-like' scale."""
-    import torch
-    import cnf_b200
-    torch.manual_seed(seed)
-    model = cnf_b200.RealNvpFlow(K, layers=L, hidden_size=HIDDEN)
-    with torch.no_grad():
-        for p in model.parameters():
-            if p.requires_grad:
-                p.mul_(300.0)
-    return model
-
-
-def synth(n, seed, device=None):
-    """Over-confident 80%-accurate synthetic classifier logits, row-centred."""
+# ------------------------------------------------------------------------------------------------
+# synthetic data: over-confident 80%-accurate classifier logits, row-centred
+# ------------------------------------------------------------------------------------------------
+def synth(n, seed, device=None, k=K):
     import torch
     g = torch.Generator(device='cpu').manual_seed(seed)
-    y = torch.randint(0, K, (n,), generator=g)
-    x = 1.5 * torch.randn((n, K), generator=g)
+    y = torch.randint(0, k, (n,), generator=g)
+    x = 1.5 * torch.randn((n, k), generator=g)
     hit = (torch.rand(n, generator=g) < 0.8).float()
     x[torch.arange(n), y] += 3.0 * hit
     x -= x.mean(dim=1, keepdim=True)
@@ -134,22 +133,158 @@ def synth(n, seed, device=None):
     return x, y
 
 
-def cpu_reference_pass(flat, x, reps, warm=1):
-    """Seconds per forward+log-det pass of the reference's torch-CPU arithmetic on x."""
+def synth_dev(n, seed, dev, k=K, block=12_500_000):
+    """The same distribution generated on the device in blocks of 12.5 M rows with per-block seeds, so that
+    block b of a sharded run equals block b of the single-GPU run (config C5 splits 10^8 rows 8 ways)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import ref_port_torch as rp
-    layers = rp.unflatten(flat, K, L, HIDDEN)
-    times = []
+    x = torch.empty((n, k), dtype=torch.float32, device=dev)
+    y = torch.empty(n, dtype=torch.int64, device=dev)
+    for b, lo in enumerate(range(0, n, block)):
+        hi = min(n, lo + block)
+        synth_block(x[lo:hi], y[lo:hi], seed + b)
+    return x, y
+
+
+def synth_block(xb, yb, seed):
+    import torch
+    m, k = xb.shape
+    g = torch.Generator(device=xb.device).manual_seed(seed)
+    yb.copy_(torch.randint(0, k, (m,), generator=g, device=xb.device))
+    torch.randn((m, k), generator=g, device=xb.device, out=xb)
+    xb.mul_(1.5)
+    hit = (torch.rand(m, generator=g, device=xb.device) < 0.8).float() * 3.0
+    xb.scatter_add_(1, yb.view(-1, 1), hit.view(-1, 1))
+    xb.sub_(xb.mean(dim=1, keepdim=True))
+
+
+def init_flat(seed=1, wmult=300.0, k=K, layers=L, hidden=HIDDEN):
+    """Reference init (nn.Linear default x 0.001, flows/flows.py:76-79; same RNG consumption as the reference's
+    constructors) x wmult ('trained-like' scale for throughput runs), as the canonical flat vector.  Plain
+    torch: shared by both arms, imports nothing of the product."""
+    import torch
+    torch.manual_seed(seed)
+    chunks = []
+    widths = [k] + list(hidden) + [k]
+    for _ in range(layers):
+        for _net in range(2):
+            for fan_in, fan_out in zip(widths, widths[1:]):
+                lin = torch.nn.Linear(fan_in, fan_out)
+                chunks += [lin.weight.detach().reshape(-1) * 0.001 * wmult, lin.bias.detach().reshape(-1) * 0.001 * wmult]
+    return torch.cat(chunks)
+
+
+def make_model(seed=1, wmult=300.0, k=K, layers=L, hidden=HIDDEN):
+    import torch
+    import cnf_b200
+    model = cnf_b200.RealNvpFlow(k, layers=layers, hidden_size=hidden)
+    flat = init_flat(seed, wmult, k, layers, hidden)
+    off = 0
     with torch.no_grad():
-        for i in range(warm + reps):
-            t0 = time.perf_counter()
-            zs, ld = rp.forward(layers, x)
-            dt = time.perf_counter() - t0
-            if i >= warm:
-                times.append(dt)
-    times.sort()
-    return times[len(times) // 2], times
+        for lay in model.layers:
+            for p in lay.canonical_parameters():
+                p.copy_(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+    assert off == flat.numel()
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+class HostReference:
+    """The reference's CPU implementation of the path: the unmodified modules when oracle/_ref/reference (or
+    /root/reference) exists -> kind 'reference'; else the torch-CPU port -> kind 'port'."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import ref_loader
+        self.ref = ref_loader.load()
+        self.kind = 'reference' if self.ref is not None else 'port'
+        if self.ref is None:
+            import ref_port_torch
+            self.port = ref_port_torch
+
+    def flow(self, flat, k=K, layers=L, hidden=HIDDEN, scale=True):
+        """A callable bundle (forward, inverse, module-or-None) with the weights of `flat`."""
+        import torch
+        if self.ref is not None:
+            f = self.ref.Flow([self.ref.NvpCouplingLayer(k, hidden_size=list(hidden), scale=scale) for _ in range(layers)])
+            off = 0
+            with torch.no_grad():
+                for lay in f.layers:
+                    for net in (lay.s, lay.t):
+                        if isinstance(net, torch.nn.Module):
+                            for lin in net.layers:
+                                for p in (lin.weight, lin.bias):
+                                    p.copy_(flat[off:off + p.numel()].view(p.shape))
+                                    off += p.numel()
+            assert off == flat.numel()
+            return f
+        return self.port.unflatten(flat, k, layers, hidden, scale=scale)
+
+    def forward(self, f, x):
+        import torch
+        with torch.no_grad():
+            if self.ref is not None:
+                zs, ld = f(x)              # Flow.forward, flows/flows.py:17-25
+                return zs[-1], ld
+            zs, ld = self.port.forward(f, x)
+            return zs[-1], ld
+
+    def inverse(self, f, z):
+        import torch
+        with torch.no_grad():
+            if self.ref is not None:
+                xs, ld = f.backward(z)     # Flow.backward, flows/flows.py:27-37
+                return xs[-1], ld
+            return self.port.inverse(f, z)
+
+    def train_stepper(self, flat, k=K, layers=L, hidden=HIDDEN, scale=True):
+        """step(x, y) = one optimiser step of calibrators.py:287-295 (loss, zero_grad, backward, Adam.step)."""
+        import torch
+        if self.ref is None:
+            st = self.port.TrainState(flat, k, layers, hidden, scale=scale, shift=True)
+            return st.step
+        f = self.flow(flat, k, layers, hidden, scale)
+        opt = torch.optim.Adam(f.parameters())
+        softmx = torch.nn.Softmax(dim=1)
+
+        def step(xb, yb):
+            zs, log_det = f(xb)
+            probs = softmx(zs[-1])
+            ce = torch.log(probs.gather(1, yb.view(-1, 1)) + 1e-7)
+            loss = -torch.mean(ce.squeeze() + log_det)
+            f.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        return step
+
+    def metrics(self, probs, y):
+        """ECE(15) + NLL + accuracy: utils/metrics.py:35-73, 6-15, 76-80 (NumPy-2 shim, see ref_loader)."""
+        import numpy as np
+        if self.ref is not None:
+            m = self.ref.metrics
+            oh = np.eye(probs.shape[1], dtype=np.int32)[y]
+            return m.expected_calibration_error(probs, y, bins=15), m.neg_log_likelihood(probs, oh), m.accuracy(probs, oh)
+        import flow_oracle as orc
+        return orc.expected_calibration_error(probs, y, 15), orc.neg_log_likelihood(probs, y), orc.accuracy(probs, y)
+
+    def what(self):
+        return ('unmodified reference modules (%s)' % os.path.relpath(self.ref.root, ROOT) if self.ref is not None
+                else 'torch CPU ops restating flows/flows.py:101-126 (oracle/ref_port_torch.py)')
+
+
+def median_time(fn, reps, warm=1):
+    ts = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            ts.append(dt)
+    ts.sort()
+    return ts[len(ts) // 2], ts
 
 
 def run_reference(args):
@@ -158,25 +293,27 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    model = make_weights()
-    flat = torch.cat([p.detach().reshape(-1) for lay in model.layers for p in lay.canonical_parameters()])
-    # size the per-step sample so the whole run stays within ~2 minutes
+    host = HostReference()
+    flat = init_flat()
+    f = host.flow(flat)
+    # size the per-step sample so that the whole run stays within ~2 minutes
     probe, _ = synth(100_000, 7)
-    t_probe, _ = cpu_reference_pass(flat, probe, reps=1, warm=1)
+    t_probe, _ = median_time(lambda: host.forward(f, probe), reps=1, warm=1)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    n = int(min(N_STEP, max(50_000, 100_000 * budget / max(t_probe, 1e-6))))
+    n = int(min(N_C2, max(50_000, 100_000 * budget / max(t_probe, 1e-6))))
     x, _ = synth(n, 11)
-    med, times = cpu_reference_pass(flat, x, reps=args.steps, warm=args.warmup)
+    _, times = median_time(lambda: host.forward(f, x), reps=args.steps, warm=args.warmup)
     total = sum(times)
     value = n * len(times) / total
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample_per_step': n, 'device': 'cpu'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': '%d samples per step, %d steps, torch CPU ops restating flows/flows.py:101-112 '
-                                   '(oracle/ref_port_torch.py)' % (n, len(times))},
+        'config': {'workload': WORKLOAD, 'sample_per_step': n, 'device': 'cpu',
+                   'weights': 'reference init x300 (trained-like), seed 1'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': host.kind,
+                         'sample': '%d samples per step, %d steps: Flow.forward under no_grad, %s'
+                                   % (n, len(times), host.what())},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -204,9 +341,13 @@ def bind_to_gpu_cpus(local):
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import cnf_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
+    from cnf_b200 import _lib
+    from cnf_b200._engine import _ptr, _stream
+    from cnf_b200.utils import metrics as M
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -218,6 +359,8 @@ def run_ours(args):
     numa = bind_to_gpu_cpus(local) if world > 1 and not os.environ.get('CNF_NO_AFFINITY') else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    hbm_peak, tf_peak, tf_sustained, peak_src = peaks()
+    G = 1e9
 
     def barrier():
         if world > 1:
@@ -231,409 +374,504 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    model = make_weights().to(dev)
-    eng = model.engine()
-    precision = args.precision
-    if precision == 'auto':
-        precision = 'bf16' if eng.tc_bytes > 0 else 'fp32'
-    eng.ensure(dev)
-    eng.pack(tc=(precision == 'bf16'))
-
-    # ---- kernel-resident measurement: inputs already in HBM ---------------------------------
-    xs = [synth(N_STEP, 100 + rank * N_ROT + i, dev)[0] for i in range(N_ROT)]
-    import ctypes
-    from cnf_b200 import _lib
-    from cnf_b200._engine import _ptr, _stream
-    z = torch.empty_like(xs[0])
-    ld = torch.empty(N_STEP, dtype=torch.float32, device=dev)
-    desc = eng.desc_tc if precision == 'bf16' else eng.desc
-    packed = eng.packed_tc if precision == 'bf16' else eng.packed
-
-    def step(i):
-        _lib.call('cnf_flow_forward', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
-                  _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
-
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    def timed(fn, steps, warm=3, sampler=None):
+        """ms per step of fn(i): `warm` untimed calls, then exactly `steps` calls between CUDA events on the
+        launching stream, a barrier + synchronize on both sides, max over ranks."""
+        for i in range(max(3, warm)):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.__enter__()
         e0.record()
-        for i in range(args.steps):
-            step(i)
+        for i in range(steps):
+            fn(i)
         e1.record()
         barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    value = world * N_STEP * args.steps / (ms * 1e-3)
-    kern_ms = e0.elapsed_time(e1) / args.steps        # one kernel per step on this stream
+        if sampler is not None:
+            sampler.__exit__()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def wall_timed(fn, steps, warm=3):
+        for i in range(max(3, warm)):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0) * 1e3 / steps
+
+    model = make_model().to(dev)
+    eng = model.engine()
+    eng.ensure(dev)
+    has_tc = eng.tc_bytes > 0
+    eng.pack(tc=has_tc)
+    precisions = (['bf16'] if has_tc else []) + ['fp32']
+    if args.precision != 'auto':
+        precisions = [args.precision]
+    head_prec = precisions[0]
+    n_head = args.head_n or N_HEAD
+    few = max(3, min(args.steps, 5))             # step count of the slower side legs
+    legs = {}
+
+    def fwd_call(prec, x, z, ld, n, inverse=False):
+        desc = eng.desc_tc if prec == 'bf16' else eng.desc
+        packed = eng.packed_tc if prec == 'bf16' else eng.packed
+        _lib.call('cnf_flow_inverse' if inverse else 'cnf_flow_forward', ctypes.byref(desc), _ptr(packed),
+                  _ptr(eng.tables), _ptr(x), _ptr(z), _ptr(ld), None, ctypes.c_int64(n), _stream(dev))
+
+    # ---- headline: 10^8 resident logits per step, one launch per step -----------------------------
+    xh_dev, yh_dev = synth_dev(n_head, 1000 * (rank + 1), dev)
+    zh_dev = torch.empty_like(xh_dev)
+    ldh_dev = torch.empty(n_head, dtype=torch.float32, device=dev)
+    clocks = ClockSampler(local)
+    fwd_ms = {}
+    for prec in precisions:
+        steps = args.steps if prec == head_prec else few
+        fwd_ms[prec] = timed(lambda i, p=prec: fwd_call(p, xh_dev, zh_dev, ldh_dev, n_head), steps, args.warmup,
+                             sampler=clocks if prec == head_prec else None)
+    ms = fwd_ms[head_prec]
+    value = world * n_head / (ms * 1e-3)
     launches = args.steps
 
-    # ---- end to end through the public host-buffer API ---------------------------------------
-    xh = torch.empty((N_STEP, K), dtype=torch.float32, pin_memory=True)
-    xh.copy_(synth(N_STEP, 999 + rank)[0])
-    zh = torch.empty((N_STEP, K), dtype=torch.float32, pin_memory=True)
-    lh = torch.empty(N_STEP, dtype=torch.float32, pin_memory=True)
-    model.flow.precision = precision
-    for _ in range(max(3, args.warmup)):
-        model.transform_host(xh, zh, lh, device=dev)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        model.transform_host(xh, zh, lh, device=dev)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {'value': world * N_STEP * args.steps / e2e_s, 'unit': UNIT,
-           'h2d_bytes_per_step': xh.numel() * 4, 'd2h_bytes_per_step': zh.numel() * 4 + lh.numel() * 4,
-           'api': 'RealNvpFlow.transform_host (pinned host logits in, host z + log-det out)'}
+    # ---- configs[1] as written: N = 10^6 per launch, rotating inputs (same kernels) ------------------
+    xs = [xh_dev[i * N_C2:(i + 1) * N_C2] for i in range(N_ROT)] if n_head >= N_ROT * N_C2 else [synth(N_C2, 100 + i, dev)[0] for i in range(N_ROT)]
+    z1 = torch.empty((N_C2, K), dtype=torch.float32, device=dev)
+    l1 = torch.empty(N_C2, dtype=torch.float32, device=dev)
+    c2 = {}
+    for prec in precisions:
+        t = timed(lambda i, p=prec: fwd_call(p, xs[i % N_ROT], z1, l1, N_C2), max(args.steps, 20), args.warmup)
+        c2[prec] = {'value': world * N_C2 / (t * 1e-3), 'ms_per_step': t}
+    legs['c2_1m'] = {'what': 'BASELINE configs[1]: the same pass at N=1,000,000 per GPU per launch, 8 rotating inputs',
+                     'unit': UNIT, **{p: c2[p] for p in c2}}
 
-    # ---- training step, config C3 shape: tensor-core path (headline) and fp32 path -------------
-    train = train_fp32 = None
+    # ---- end to end through the public host-buffer API ---------------------------------------------
+    n_chunk = min(N_E2E_CHUNK, n_head)
+    calls_per_step = max(1, n_head // n_chunk)
+    xh = torch.empty((n_chunk, K), dtype=torch.float32, pin_memory=True)
+    xh.copy_(xh_dev[:n_chunk])
+    zh = torch.empty((n_chunk, K), dtype=torch.float32, pin_memory=True)
+    lh = torch.empty(n_chunk, dtype=torch.float32, pin_memory=True)
+    e2e_by = {}
+    for prec in precisions:
+        model.flow.precision = prec
+
+        def e2e_step(i):
+            for _ in range(calls_per_step):
+                model.transform_host(xh, zh, lh, device=dev)      # synchronises: the result is on the host
+        steps = args.steps if prec == head_prec else few
+        t = wall_timed(e2e_step, steps, 3)
+        e2e_by[prec] = world * calls_per_step * n_chunk / (t * 1e-3)
+    model.flow.precision = 'fp32'
+    e2e = {'value': e2e_by[head_prec], 'unit': UNIT,
+           'h2d_bytes_per_step': calls_per_step * xh.numel() * 4,
+           'd2h_bytes_per_step': calls_per_step * (zh.numel() * 4 + lh.numel() * 4),
+           'api': 'RealNvpFlow.transform_host -> cnf_flow_apply_host: pinned host logits in, host z + log-det out; '
+                  'one step = %d calls of %d samples through the same pinned buffers' % (calls_per_step, n_chunk),
+           'by_precision': e2e_by}
+    del xh, zh, lh
+
+    # ---- config C5 as ONE job: inverse sampling + fused flow -> ECE/NLL/accuracy + all-reduce ---------
+    # 10^8 samples in total at every N (strong scaling): rank r owns blocks r, r+world, ... of 12.5 M rows.
+    c5 = None
+    if not args.no_extra:
+        n5 = (args.c5_n or 100_000_000) // world
+        if n5 > n_head:
+            n5 = n_head
+        # logits of this rank's blocks (block seeds are global, so the union over ranks is the same set at every N)
+        blocks = list(range(rank, 8, world)) if (n5 * world == 100_000_000 and world in (1, 2, 4, 8)) else None
+        x5, y5 = xh_dev[:n5], yh_dev[:n5]
+        if blocks is not None:
+            for j, b in enumerate(blocks):
+                synth_block(x5[j * 12_500_000:(j + 1) * 12_500_000], y5[j * 12_500_000:(j + 1) * 12_500_000], 5000 + b)
+        lp = torch.log(torch.bincount(y5, minlength=K).double() / n5)
+        if world > 1:
+            cnt = torch.bincount(y5, minlength=K).double()
+            dist.all_reduce(cnt)
+            lp = torch.log(cnt / cnt.sum())
+        lp_np = lp.cpu().numpy()
+        zbase = zh_dev[:n5]                    # "sampling": base-space points to invert (here the forward images)
+        fwd_call(head_prec, x5, zbase, ldh_dev[:n5], n5)
+        xrec = torch.empty_like(zbase)
+        ldi = torch.empty(n5, dtype=torch.float32, device=dev)
+        stats_box = [None]
+
+        def c5_job(i, prec=head_prec):
+            fwd_call(prec, zbase, xrec, ldi, n5, inverse=True)                       # inverse-pass sampling
+            res = eng.predict(x5, center=False, log_priors=lp_np, y=y5, bins=15, precision=prec, repack=False)
+            stats_box[0] = M.reduce_statistics(res['stats'])                        # 48 doubles over NCCL
+        c5 = {}
+        for prec in precisions:
+            t = timed(lambda i, p=prec: c5_job(i, p), few, 3)
+            st = stats_box[0]
+            mt = M.metrics_from_statistics(st, 15)
+            c5[prec] = {'value': world * n5 / (t * 1e-3), 'ms_per_step': t, 'ece': mt['ece'], 'nll': mt['nll'],
+                        'accuracy': mt['accuracy'], 'n': mt['n']}
+        # the fused statistics pass alone: reads 4K+8 B/sample, writes nothing
+        fused = {}
+        for prec in precisions:
+            t = timed(lambda i, p=prec: eng.predict(x5, center=False, log_priors=lp_np, y=y5, bins=15, precision=p,
+                                                    repack=False), few, 3)
+            fused[prec] = {'value': world * n5 / (t * 1e-3), 'ms_per_step': t,
+                           'hbm_gbs': (4 * K + 8) * n5 / (t * 1e-3) / 1e9}
+        rt = float((xrec - x5).abs().max())
+        legs['c5_job'] = {'what': 'C5 as one job: Flow.backward (inverse + log-det) on this rank\'s share of 10^8 base points, '
+                                  'then ONE fused pass flow -> softmax(log(softmax(z)+1e-7)-log_priors) -> ECE(15)/NLL/accuracy '
+                                  '(4K+8 B/sample read, nothing written), then all-reduce of the 48 statistics; value = '
+                                  'samples/s of the whole job', 'unit': UNIT, 'samples_total': n5 * world,
+                          'scaling': 'strong (10^8 samples over all GPUs)', 'roundtrip_max_abs': rt, **c5}
+        legs['c5_fused_stats'] = {'what': 'the fused flow -> calibrated ECE/NLL/accuracy pass alone (cnf_flow_predict, statistics only)',
+                                  'unit': UNIT, 'algorithmic_bytes_per_sample': 4 * K + 8, **fused,
+                                  'note': 'bound by the flow arithmetic, not by HBM: 48 B/sample at this rate is a few % of the HBM roof'}
+        del xrec, ldi
+
+    # ---- training step, config C3 shape ---------------------------------------------------------------
+    train = {}
     if not args.no_train:
         n_loc = args.train_n or (64 * (1 << 20)) // world
-        xt, yt = synth(n_loc, 5000 + rank, dev)
-
-        def time_training(prec):
-            tmodel = make_weights(seed=2)
-            with torch.no_grad():
-                for p in tmodel.parameters():
-                    if p.requires_grad:
-                        p.mul_(1.0 / 300.0)          # reference init for training
-            tmodel.to(dev)
+        xt, yt = xh_dev[:n_loc], yh_dev[:n_loc]
+        if n_loc > n_head:
+            xt, yt = synth_dev(n_loc, 7000 + rank, dev)
+        for prec in precisions:
+            if prec == 'bf16' and eng.tc_train is None:
+                continue
+            tmodel = make_model(seed=2, wmult=1.0).to(dev)          # reference init for training
             tr = cnf_b200.FusedNLLTrainer(tmodel.engine(), xt, yt, n_total=n_loc * world, precision=prec)
-            for _ in range(3):
-                tr.step()
-            barrier()
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            tsteps = max(3, min(args.steps, 5))
-            for _ in range(tsteps):
-                tr.step()
-            t1e.record()
-            barrier()
-            tms = max_over_ranks(t0e.elapsed_time(t1e))
-            kern = ('tcgen05 forward (+tape) and backward kernels per 2^20-sample chunk' if prec == 'bf16'
-                    else 'fused NLL fwd+bwd kernel')
-            return {'value': world * n_loc * tsteps / (tms * 1e-3), 'unit': UNIT, 'ms_per_step': tms / tsteps,
-                    'samples_per_gpu': n_loc, 'samples_total': n_loc * world,
-                    'scaling': 'strong (C3: 64 Mi samples over all GPUs)' if not args.train_n else 'weak',
-                    'steps': tsteps, 'dtype': 'bf16' if prec == 'bf16' else 'f32',
-                    'what': kern + ' + grad reduce' + (' + NCCL all-reduce' if world > 1 else '') +
-                            ' + Adam + repack per step', 'loss': -float(tr.loss_acc[0]) / (n_loc * world)}
+            t = timed(lambda i: tr.step(), few, 3)
+            train[prec] = {'value': world * n_loc / (t * 1e-3), 'unit': UNIT, 'ms_per_step': t,
+                           'samples_per_gpu': n_loc, 'samples_total': n_loc * world, 'steps': few,
+                           'scaling': 'strong (C3: 64 Mi samples over all GPUs)' if not args.train_n else 'weak',
+                           'loss': -float(tr.loss_acc[0]) / (n_loc * world),
+                           'what': ('tcgen05 forward (+tape) and backward kernels per 2^20-sample chunk' if prec == 'bf16'
+                                    else 'fused NLL fwd+bwd kernel') + ' + grad reduce' +
+                                   (' + ONE NCCL all-reduce (grad + loss sums)' if world > 1 else '') + ' + Adam + repack per step'}
+            if prec == 'bf16':
+                train[prec]['tensor_tflops_minimal'] = train[prec]['value'] * 4 * FLOPS_PER_SAMPLE / 1e12
+            del tr, tmodel
+        legs['train_step'] = train
 
-        if precision == 'bf16':
-            train = time_training('bf16')
-            train['tensor_tflops_minimal'] = train['value'] * 4 * FLOPS_PER_SAMPLE / 1e12   # fwd + recompute + dgrad + wgrad
-        train_fp32 = time_training('fp32')
-        if train is None:
-            train = train_fp32
-        del xt, yt
+    # ---- data-parallel consistency (N > 1): identical parameters on every rank, same loss as one rank -----
+    dp_check = None
+    if world > 1 and not args.no_train:
+        n_dp = 1 << 20
+        xg, yg = synth_dev(n_dp, 4242, dev)                       # the same global set on every rank
+        lo, hi = cnf_b200.calibrators.shard_bounds(n_dp, rank, world)
+        torch.manual_seed(100 + rank)                             # ranks start from DIFFERENT weights on purpose
+        m_dp = cnf_b200.RealNvpFlow(K, layers=L, hidden_size=HIDDEN).to(dev)
+        tr = cnf_b200.FusedNLLTrainer(m_dp.engine(), xg[lo:hi].contiguous(), yg[lo:hi].contiguous(), n_total=n_dp)
+        start = m_dp.engine().flat.clone()                        # rank 0's weights after the broadcast
+        for _ in range(4):
+            tr.step()
+        flat = m_dp.engine().flat
+        sig = torch.stack([flat.view(torch.int32).to(torch.int64).sum(), (flat.view(torch.int32).to(torch.int64) *
+                           torch.arange(1, flat.numel() + 1, device=dev)).sum()])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        identical = all(bool((s == sigs[0]).all()) for s in sigs)
+        loss_dp = -float(tr.loss_acc[0]) / n_dp
+        # the same four steps on ONE rank over the whole set, from the same start
+        m_1 = cnf_b200.RealNvpFlow(K, layers=L, hidden_size=HIDDEN).to(dev)
+        e1 = m_1.engine()
+        e1.ensure(dev)
+        e1.flat.copy_(start)
+        saved = cnf_b200.calibrators._dist
+        cnf_b200.calibrators._dist = lambda: None
+        try:
+            tr1 = cnf_b200.FusedNLLTrainer(e1, xg, yg, n_total=n_dp)
+            for _ in range(4):
+                tr1.step()
+        finally:
+            cnf_b200.calibrators._dist = saved
+        loss_1 = -float(tr1.loss_acc[0]) / n_dp
+        dflat = float((e1.flat - flat).abs().max())
+        dp_check = {'ok': bool(identical and abs(loss_dp - loss_1) <= 1e-6 * max(1.0, abs(loss_1))),
+                    'params_bit_identical_across_ranks': identical, 'loss_dp': loss_dp, 'loss_single_rank': loss_1,
+                    'max_abs_param_diff_vs_single_rank': dflat,
+                    'what': '4 fp32 Adam steps on 2^20 samples sharded over the ranks (ranks built from different '
+                            'seeds, start state broadcast from rank 0) vs the same steps on one rank'}
+        del xg, yg, tr, tr1
 
-    # ---- config C5 pieces: inverse pass and the metrics kernel (HBM-bound) -------------------
-    extra = None
+    # ---- HBM-bound kernels of the path: metrics and the constant affine layer ----------------------------
     if not args.no_extra:
-        from cnf_b200.utils import metrics as M
-        for i in range(3):
-            _lib.call('cnf_flow_inverse', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
-                      _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
-        barrier()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record()
-        for i in range(20):
-            _lib.call('cnf_flow_inverse', ctypes.byref(desc), _ptr(packed), _ptr(eng.tables), _ptr(xs[i % N_ROT]),
-                      _ptr(z), _ptr(ld), None, ctypes.c_int64(N_STEP), _stream(dev))
-        i1.record()
-        barrier()
-        inv_ms = max_over_ranks(i0.elapsed_time(i1)) / 20
-        n_m = 12_500_000                      # 10^8 samples over 8 GPUs (config C5)
-        pm = torch.softmax(synth(n_m, 31 + rank, dev)[0], dim=1).contiguous()
-        ym = synth(n_m, 31 + rank)[1].to(dev)
+        n_m = 12_500_000
+        pm = torch.softmax(xh_dev[:n_m], dim=1).contiguous()
+        ym = yh_dev[:n_m]
         edges = torch.from_numpy(M.bin_edges(15)).to(dev)
         macc = torch.zeros(48, dtype=torch.float64, device=dev)
 
-        def mstep():
+        def mstep(i):
             _lib.call('cnf_metrics', _ptr(pm), ctypes.c_int32(0), _ptr(ym), ctypes.c_int64(n_m), ctypes.c_int32(K),
                       ctypes.c_int32(15), ctypes.c_int32(0), None, _ptr(edges), _ptr(macc), _stream(dev))
-        for _ in range(3):
-            mstep()
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        for _ in range(20):
-            mstep()
-        m1.record()
-        barrier()
-        met_ms = max_over_ranks(m0.elapsed_time(m1)) / 20
-        # AffineConstantLayer / TempScaler streaming kernel: pure 8K B/sample
+        met_ms = timed(mstep, 20, 3)
         n_a = 10_000_000
-        xa = synth(n_a, 41 + rank, dev)[0]
-        za = torch.empty_like(xa)
+        xa = xh_dev[:n_a]
+        za = zh_dev[:n_a]
         sa = torch.full((K,), 0.1, device=dev)
         ta = torch.full((K,), -0.2, device=dev)
 
-        def astep():
+        def astep(i):
             _lib.call('cnf_affine_const', _ptr(xa), _ptr(sa), _ptr(ta), _ptr(za), ctypes.c_int64(n_a), ctypes.c_int32(K),
                       ctypes.c_int32(0), _stream(dev))
-        for _ in range(3):
-            astep()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(20):
-            astep()
-        a1.record()
-        barrier()
-        aff_ms = max_over_ranks(a0.elapsed_time(a1)) / 20
-        del xa, za
-        hbm_peak = peaks()[0]
+        aff_ms = timed(astep, 20, 3)
         ab = 8 * K * n_a / (aff_ms * 1e-3) / 1e9
         mb = (4 * K + 8) * n_m / (met_ms * 1e-3) / 1e9
-        extra = {'affine_const': {'value': world * n_a / (aff_ms * 1e-3), 'unit': UNIT, 'ms_per_step': aff_ms,
-                                  'samples_per_gpu': n_a,
-                                  'what': 'AffineConstantLayer.forward z = x*exp(s)+t (flows/flows.py:53-58), fp32',
-                                  'roofline': {'bound': 'hbm', 'achieved': ab, 'peak': hbm_peak, 'unit': 'GB/s',
-                                               'frac': ab / hbm_peak, 'note': 'algorithmic bytes 8K = 80 B/sample'}},
-                 'inverse': {'value': world * N_STEP / (inv_ms * 1e-3), 'unit': UNIT, 'ms_per_step': inv_ms,
-                             'what': 'Flow.backward (inverse + log-det) on 1,000,000 samples per GPU, same path as value'},
-                 'metrics': {'value': world * n_m / (met_ms * 1e-3), 'unit': UNIT, 'ms_per_step': met_ms,
-                             'samples_per_gpu': n_m, 'what': 'ECE(15 bins)+NLL+accuracy in one pass over fp32 probabilities',
-                             'roofline': {'bound': 'hbm', 'achieved': mb, 'peak': hbm_peak, 'unit': 'GB/s',
-                                          'frac': mb / hbm_peak, 'note': 'algorithmic bytes 4K+8 = 48 B/sample'}}}
-        del pm, ym
-        # config C4: K=100, 8 couplings, hidden 512 on the streamed-weight tensor-core kernel
-        torch.manual_seed(4)
-        c4 = cnf_b200.RealNvpFlow(100, layers=8, hidden_size=[512])
-        with torch.no_grad():
-            for prm in c4.parameters():
-                if prm.requires_grad:
-                    prm.mul_(60.0)
-        c4.to(dev)
+        legs['affine_const'] = {'value': world * n_a / (aff_ms * 1e-3), 'unit': UNIT, 'ms_per_step': aff_ms, 'samples_per_gpu': n_a,
+                                'what': 'AffineConstantLayer.forward z = x*exp(s)+t (flows/flows.py:53-58), fp32',
+                                'roofline': {'bound': 'hbm', 'achieved': ab, 'peak': hbm_peak, 'unit': 'GB/s',
+                                             'frac': ab / hbm_peak, 'note': 'algorithmic bytes 8K = 80 B/sample'}}
+        legs['metrics'] = {'value': world * n_m / (met_ms * 1e-3), 'unit': UNIT, 'ms_per_step': met_ms, 'samples_per_gpu': n_m,
+                           'what': 'ECE(15 bins)+NLL+accuracy in one pass over fp32 probabilities',
+                           'roofline': {'bound': 'hbm', 'achieved': mb, 'peak': hbm_peak, 'unit': 'GB/s',
+                                        'frac': mb / hbm_peak, 'note': 'algorithmic bytes 4K+8 = 48 B/sample'}}
+        del pm
+
+    # the 8.8 GB of headline buffers are no longer needed
+    inv_keep = None
+    if not args.no_extra:
+        t = timed(lambda i: fwd_call(head_prec, zh_dev, xh_dev, ldh_dev, min(n_head, 12_500_000), inverse=True), few, 3)
+        inv_keep = {'value': world * min(n_head, 12_500_000) / (t * 1e-3), 'unit': UNIT, 'ms_per_step': t, 'dtype': head_prec,
+                    'what': 'Flow.backward (inverse + log-det) on 12,500,000 samples per GPU (config C5 share at 8 GPUs)'}
+        legs['inverse'] = inv_keep
+    flat_c2 = eng.flat.detach().cpu().clone()
+    del xh_dev, zh_dev, ldh_dev, yh_dev, xs, z1, l1
+    torch.cuda.empty_cache()
+
+    # ---- config C4: K=100, 8 couplings, hidden 512 --------------------------------------------------------
+    if not args.no_extra:
+        c4 = make_model(seed=4, wmult=60.0, k=100, layers=8, hidden=[512]).to(dev)
         e4 = c4.engine()
         e4.ensure(dev)
         e4.pack(tc=True)
-        n4 = 1_000_000
+        n4 = args.c4_n or 10_000_000
         g4 = torch.Generator(device=dev).manual_seed(40 + rank)
-        x4 = 1.5 * torch.randn((n4, 100), generator=g4, device=dev)
-        x4 -= x4.mean(dim=1, keepdim=True)
+        x4 = torch.empty((n4, 100), dtype=torch.float32, device=dev)
+        for lo in range(0, n4, 1_000_000):
+            blk = x4[lo:lo + 1_000_000]
+            torch.randn(blk.shape, generator=g4, device=dev, out=blk)
+            blk.mul_(1.5)
+            blk.sub_(blk.mean(dim=1, keepdim=True))
         z4 = torch.empty_like(x4)
         l4 = torch.empty(n4, dtype=torch.float32, device=dev)
 
-        def c4step():
+        def c4step(i):
             _lib.call('cnf_flow_forward', ctypes.byref(e4.desc_tc), _ptr(e4.packed_tc), _ptr(e4.tables), _ptr(x4),
                       _ptr(z4), _ptr(l4), None, ctypes.c_int64(n4), _stream(dev))
-        for _ in range(2):
-            c4step()
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(5):
-            c4step()
-        c1.record()
-        barrier()
-        c4_ms = max_over_ranks(c0.elapsed_time(c1)) / 5
+        c4_ms = timed(c4step, few, 3)
         c4_flops = 8 * 2 * 2 * (50 * 512 + 512 * 50)
-        extra['c4_forward'] = {'value': world * n4 / (c4_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4_ms, 'dtype': 'bf16',
-                               'what': 'C4: RealNVP K=100 L=8 hidden=[512] fwd+logdet, 1,000,000 samples per GPU, '
-                                       'streamed-weight tcgen05 kernel',
-                               'tensor_tflops_minimal': c4_flops * n4 / (c4_ms * 1e-3) / 1e12,
-                               'frac_of_bf16_peak': c4_flops * n4 / (c4_ms * 1e-3) / 1e12 / peaks()[1]}
-        # the same shape through the fp32 kernels (the 1e-5 parity path and the only training path for wide
-        # shapes): forward on 200,000 samples, full NLL + Adam training step on 100,000
-        n4f = 200_000
+        c4_tf = c4_flops * n4 / (c4_ms * 1e-3) / 1e12
+        legs['c4_forward'] = {'value': world * n4 / (c4_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4_ms, 'dtype': 'bf16',
+                              'what': 'C4: RealNVP K=100 L=8 hidden=[512] fwd+logdet, %d samples per GPU, '
+                                      'streamed-weight tcgen05 kernel' % n4,
+                              'roofline': {'bound': 'tensor', 'achieved': c4_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                           'frac': c4_tf / tf_peak, 'note': 'minimal 1,638,400 flop/sample'}}
+        # the same shape through the fp32 kernels (the 1e-5 parity path and the training path of wide shapes)
+        n4f = 1_000_000
         c4.flow.precision = 'fp32'
         with torch.no_grad():
-            c4(x4[:n4f])
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(3):
-                c4(x4[:n4f])
-            f1.record()
-        barrier()
-        c4f_ms = max_over_ranks(f0.elapsed_time(f1)) / 3
+            c4f_ms = timed(lambda i: c4(x4[:n4f]), 3, 3)
         n4t = 100_000
         y4 = torch.randint(0, 100, (n4t,), generator=g4, device=dev)
         tr4 = cnf_b200.FusedNLLTrainer(e4, x4[:n4t].contiguous(), y4, n_total=n4t * world)
-        tr4.step()
-        t40, t41 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t40.record()
-        for _ in range(3):
-            tr4.step()
-        t41.record()
-        barrier()
-        c4t_ms = max_over_ranks(t40.elapsed_time(t41)) / 3
-        extra['c4_fp32'] = {'forward': {'value': world * n4f / (c4f_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4f_ms},
-                            'train_step': {'value': world * n4t / (c4t_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4t_ms},
-                            'dtype': 'f32',
-                            'what': 'C4 shape on the lean fp32 kernels (16-unit hidden chunks, chunk weights staged in '
-                                    'shared memory, no tape): forward on 200,000 samples, NLL + Adam step on 100,000'}
-        del x4, z4, l4, tr4
-        # config C1 through the calibrator API (rank 0, N=1 only): NICE, K=3, N=10,000, 4 additive couplings,
-        # hidden 32, fit (50 full-batch epochs) + predict, host numpy in and out (calibrators.py:241-353)
-        if rank == 0 and world == 1:
-            import numpy as np
-            rs = np.random.RandomState(3)
-            y1 = rs.randint(0, 3, size=10_000)
-            x1 = (1.5 * rs.randn(10_000, 3)).astype(np.float32)
-            x1[np.arange(10_000), y1] += 3.0 * (rs.rand(10_000) < 0.8)
-            t1 = np.eye(3, dtype=np.float32)[y1]
+        c4t_ms = timed(lambda i: tr4.step(), 3, 3)
+        legs['c4_fp32'] = {'forward': {'value': world * n4f / (c4f_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4f_ms},
+                           'train_step': {'value': world * n4t / (c4t_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c4t_ms},
+                           'dtype': 'f32',
+                           'what': 'C4 shape on the lean fp32 kernels: forward on 1,000,000 samples, NLL + Adam step on 100,000'}
+        del x4, z4, l4, tr4, c4, e4
+        torch.cuda.empty_cache()
 
-            def c1_run():
-                cal = cnf_b200.TorchFlowCalibrator(cnf_b200.NiceFlow, x1, t1, layers=4, hidden_size=[32], epochs=50,
-                                                   dev=dev)
-                return cal.predict(x1)
-            c1_run()
-            torch.cuda.synchronize()
+    # ---- calibrator API at calibration-set sizes (rank 0, N=1 only) -----------------------------------------
+    if not args.no_extra and rank == 0 and world == 1:
+        rs = np.random.RandomState(3)
+        y1 = rs.randint(0, 3, size=10_000)
+        x1 = (1.5 * rs.randn(10_000, 3)).astype(np.float32)
+        x1[np.arange(10_000), y1] += 3.0 * (rs.rand(10_000) < 0.8)
+        t1 = np.eye(3, dtype=np.float32)[y1]
+
+        def c1_run():
+            cal = cnf_b200.TorchFlowCalibrator(cnf_b200.NiceFlow, x1, t1, layers=4, hidden_size=[32], epochs=50, dev=dev)
+            return cal.predict(x1)
+        c1_run()
+        torch.cuda.synchronize()
+        c1_times = []
+        for _ in range(5):
             t0 = time.perf_counter()
             p1 = c1_run()
             torch.cuda.synchronize()
-            c1_s = time.perf_counter() - t0
-            extra['c1_calibrator'] = {'value': 10_000 * 50 / c1_s, 'unit': UNIT, 'wall_s': c1_s, 'dtype': 'f32',
-                                      'what': 'C1: TorchFlowCalibrator(NiceFlow, K=3, N=10,000, 4 couplings, hidden 32): '
-                                              'fit 50 full-batch epochs + predict, host numpy in/out; value = '
-                                              'training samples per second of wall time',
-                                      'finite': bool(np.isfinite(p1).all())}
+            c1_times.append(time.perf_counter() - t0)
+        c1_s = sorted(c1_times)[2]
+        legs['c1_calibrator'] = {'value': 10_000 * 50 / c1_s, 'unit': UNIT, 'wall_s': c1_s, 'dtype': 'f32', 'repeats': 5,
+                                 'what': 'C1: TorchFlowCalibrator(NiceFlow, K=3, N=10,000, 4 couplings, hidden 32): fit 50 '
+                                         'full-batch epochs + fused predict, host numpy in/out; median wall time of 5 runs',
+                                 'finite': bool(np.isfinite(p1).all())}
+        xe, ye = synth(5000, 77, dev)
+        ep = {}
+        for prec in precisions:
+            me = make_model(seed=2, wmult=1.0).to(dev)
+            if prec == 'bf16' and me.engine().tc_train is None:
+                continue
+            tre = cnf_b200.FusedNLLTrainer(me.engine(), xe, ye, precision=prec)
 
-        # C2 shape at a real calibration-set size: one full-batch epoch (optimiser step + evaluation pass) at
-        # N = 5,000, the regime the reference's calibrators run in (calibrators.py:267-328)
-        if rank == 0 and world == 1:
-            xe, ye = synth(5000, 77, dev)
-            ep = {}
-            for prec in (('fp32', 'bf16') if precision == 'bf16' else ('fp32',)):
-                me = make_weights(seed=2).to(dev)
-                tre = cnf_b200.FusedNLLTrainer(me.engine(), xe, ye, precision=prec)
-                for _ in range(5):
-                    tre.step(); tre.evaluate()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(200):
-                    tre.step(); tre.evaluate()
-                torch.cuda.synchronize()
-                ep[prec] = (time.perf_counter() - t0) / 200
-            extra['calibration_set_epoch'] = {
-                'value': 5000 / ep['fp32'], 'unit': UNIT, 'us_per_epoch': {k: v * 1e6 for k, v in ep.items()},
-                'dtype': 'f32', 'what': 'C2 shape, N=5,000: full-batch Adam step + evaluation pass per epoch, wall time '
-                                        'over 200 epochs; value = samples per second on the fp32 (1e-5 parity) kernels'}
+            def epoch(i):
+                tre.step()
+                tre.evaluate()
+            ep[prec] = wall_timed(epoch, 200, 5) * 1e3
+        legs['calibration_set_epoch'] = {
+            'value': 5000 / (ep['fp32'] * 1e-6), 'unit': UNIT, 'us_per_epoch': ep, 'dtype': 'f32',
+            'what': 'C2 shape, N=5,000: full-batch Adam step + evaluation pass per epoch, wall time over 200 epochs; '
+                    'value = samples per second on the fp32 (1e-5 parity) kernels'}
 
-    hbm, tf, src = peaks()
-    ach = BYTES_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e9
-    kname = 'flow_tc_kernel' if precision == 'bf16' else 'flow_apply_kernel'
+    # ---- rooflines of the dominant kernel (measured above with CUDA events on the launching stream) ----------
+    kname = 'flow_tc_kernel' if head_prec == 'bf16' else 'flow_apply_kernel'
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from ncu --set full
-        traffic = json.load(open(tpath)).get(kname)
-    roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': traffic,
-            'kernel': kname, 'peak_source': src,
-            'note': 'algorithmic bytes 84 B/sample x 1e6 samples per launch'}
-    ach_tf = FLOPS_PER_SAMPLE * N_STEP / (kern_ms * 1e-3) / 1e12
-    roof_tensor = {'bound': 'tensor', 'achieved': ach_tf, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach_tf / tf,
-                   'note': 'minimal (mask-exploiting) 30720 flop/sample; peak = measured bf16 burst'}
+        traffic = json.load(open(tpath)).get(kname + '_1e8' if n_head == N_HEAD else kname)
+    ach_tf = FLOPS_PER_SAMPLE * n_head / (ms * 1e-3) / 1e12
+    ach_gb = BYTES_PER_SAMPLE * n_head / (ms * 1e-3) / 1e9
+    if head_prec == 'bf16':
+        roof = {'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / tf_peak,
+                'traffic': traffic, 'kernel': kname, 'peak_source': peak_src + ', bf16 burst',
+                'frac_of_sustained_peak': (ach_tf / tf_sustained) if tf_sustained else None,
+                'hbm_note': {'achieved_gbs': ach_gb, 'frac_of_hbm_peak': ach_gb / hbm_peak},
+                'note': 'minimal (mask-exploiting) 30,720 flop/sample x %d samples per launch; the tensor pipe binds '
+                        '(SURVEY.md 8d / F13), algorithmic HBM bytes 84 B/sample' % n_head}
+    else:
+        fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof = {'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gb / hbm_peak,
+                'traffic': traffic, 'kernel': kname, 'peak_source': peak_src,
+                'fma_note': {'achieved_tflops': ach_tf, 'fp32_fma_peak_tflops': fma_peak, 'frac': ach_tf / fma_peak},
+                'note': 'fp32 path is FMA-issue bound; HBM figure from 84 B/sample'}
+    if 'fp32' in fwd_ms:
+        tf32 = FLOPS_PER_SAMPLE * n_head / (fwd_ms['fp32'] * 1e-3) / 1e12
+        legs['fwd_fp32'] = {'value': world * n_head / (fwd_ms['fp32'] * 1e-3), 'unit': UNIT, 'ms_per_step': fwd_ms['fp32'],
+                            'what': 'the headline workload on the fp32 CUDA-core kernel (API default, 1e-5 of the reference)',
+                            'roofline': {'bound': 'fp32 FMA issue', 'achieved': tf32, 'peak': 148 * 128 * 2 * 1.965e9 / 1e12,
+                                         'unit': 'TFLOP/s', 'frac': tf32 / (148 * 128 * 2 * 1.965e9 / 1e12)}}
 
+    # ---- the reference on this box's host cores (rank 0, N=1) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        flat = eng.flat.detach().cpu()
-        xc, _ = synth(N_STEP, 11)
-        med, times = cpu_reference_pass(flat, xc, reps=3, warm=1)
-        cpu = {'value': N_STEP / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': '1,000,000 samples x 3 passes (median), torch CPU ops restating flows/flows.py:101-112'}
-        # the other legs of SURVEY.md 8(d) on the same host cores, bounded samples
-        import ref_port_torch as rp
-        import flow_oracle as orc
+        host = HostReference()
         cores = torch.get_num_threads()
-        if train is not None:
+        f = host.flow(flat_c2)
+        xc, yc = synth(N_C2, 11)
+        med, _ = median_time(lambda: host.forward(f, xc), reps=3, warm=1)
+        cpu = {'value': N_C2 / med, 'unit': UNIT, 'cores': cores, 'kind': host.kind,
+               'sample': '1,000,000 samples x 3 passes (median): Flow.forward under no_grad, ' + host.what()}
+        if train:
             n_t = 200_000
             xt_c, yt_c = synth(n_t, 13)
-            st = rp.TrainState(flat / 300.0, K, L, HIDDEN)
-            st.step(xt_c, yt_c)
+            step = host.train_stepper(flat_c2 / 300.0)
+            step(xt_c, yt_c)
             t0 = time.perf_counter()
             for _ in range(2):
-                st.step(xt_c, yt_c)
+                step(xt_c, yt_c)
             dt = (time.perf_counter() - t0) / 2
-            cb = {'value': n_t / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                  'sample': '200,000 samples x 2 full-batch steps: torch autograd + torch.optim.Adam on the '
-                            'reference op sequence (calibrators.py:287-295)'}
-            train['cpu_baseline'] = cb
-            if train_fp32 is not None:
-                train_fp32['cpu_baseline'] = cb
-        if extra is not None:
-            layers = rp.unflatten(flat, K, L, HIDDEN)
-            with torch.no_grad():
-                rp.inverse(layers, xc[:200_000])
-                t0 = time.perf_counter()
-                rp.inverse(layers, xc)
-                dt = time.perf_counter() - t0
-            extra['inverse']['cpu_baseline'] = {'value': N_STEP / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                                'sample': '1,000,000 samples, one pass, flows/flows.py:114-126 in torch CPU ops'}
-            if 'c1_calibrator' in extra:
-                g1 = torch.Generator().manual_seed(5)
-                xs1 = 1.5 * torch.randn(10_000, 3, generator=g1)
-                ys1 = torch.randint(0, 3, (10_000,), generator=g1)
-                n1 = 4 * (32 * 3 + 32 + 3 * 32 + 3)
-                st1 = rp.TrainState(0.001 * torch.randn(n1, generator=g1), 3, 4, [32], scale=False, shift=True)
-                st1.step(xs1, ys1)
-                t0 = time.perf_counter()
-                for _ in range(50):
-                    st1.step(xs1, ys1)
-                dt1 = time.perf_counter() - t0
-                extra['c1_calibrator']['cpu_baseline'] = {
-                    'value': 10_000 * 50 / dt1, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                    'sample': '50 full-batch steps on 10,000 samples: torch autograd + Adam on the reference op '
-                              'sequence WITHOUT its DataLoader (calibrators.py:268-283 collates per sample, which '
-                              'dominates the reference at this size, SURVEY.md 6)'}
-            if 'calibration_set_epoch' in extra:
-                ge = torch.Generator().manual_seed(7)
-                xse = 1.5 * torch.randn(5000, 10, generator=ge)
-                yse = torch.randint(0, 10, (5000,), generator=ge)
-                npe = 6 * 2 * (128 * 10 + 128 + 10 * 128 + 10)
-                ste = rp.TrainState(0.001 * torch.randn(npe, generator=ge), 10, 6, [128])
-                ste.step(xse, yse)
-                t0 = time.perf_counter()
-                for _ in range(20):
-                    ste.step(xse, yse)
-                dte = (time.perf_counter() - t0) / 20
-                extra['calibration_set_epoch']['cpu_baseline'] = {
-                    'value': 5000 / dte, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'us_per_epoch': dte * 1e6,
-                    'sample': '20 full-batch steps on 5,000 samples (no evaluation pass): torch autograd + Adam on the '
-                              'reference op sequence'}
-            if 'c4_fp32' in extra:
-                g4c = torch.Generator().manual_seed(6)
-                n4c = 5_000
-                x4c = 1.5 * torch.randn(n4c, 100, generator=g4c)
-                y4c = torch.randint(0, 100, (n4c,), generator=g4c)
-                n4p = 8 * 2 * (512 * 100 + 512 + 100 * 512 + 100)
-                st4 = rp.TrainState(0.001 * torch.randn(n4p, generator=g4c), 100, 8, [512])
-                st4.step(x4c, y4c)
-                t0 = time.perf_counter()
-                for _ in range(2):
-                    st4.step(x4c, y4c)
-                dt4 = (time.perf_counter() - t0) / 2
-                extra['c4_fp32']['train_step']['cpu_baseline'] = {
-                    'value': n4c / dt4, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                    'sample': '5,000 samples x 2 full-batch steps, torch autograd + Adam on the reference op sequence'}
+            legs['train_step']['cpu_baseline'] = {
+                'value': n_t / dt, 'unit': UNIT, 'cores': cores, 'kind': host.kind,
+                'sample': '200,000 samples x 2 full-batch steps of calibrators.py:287-295 (loss, backward, Adam.step), ' + host.what()}
+        if not args.no_extra:
+            zc, _ = host.forward(f, xc)
+            med_i, _ = median_time(lambda: host.inverse(f, zc), reps=1, warm=1)
+            legs['inverse']['cpu_baseline'] = {'value': N_C2 / med_i, 'unit': UNIT, 'cores': cores, 'kind': host.kind,
+                                               'sample': '1,000,000 samples, one pass of Flow.backward, ' + host.what()}
+            # C5 job on the host: inverse + forward + predict tail + metrics on 1,000,000 samples
+            from scipy.special import softmax as sp_softmax
+            lp_c = np.log(np.bincount(yc.numpy(), minlength=K) / float(N_C2))
+
+            def c5_host():
+                host.inverse(f, zc)
+                zz, _ = host.forward(f, xc)
+                pr = sp_softmax(np.log(sp_softmax(zz.numpy(), axis=1) + 1e-7) - lp_c, axis=1)     # calibrators.py:44, 352
+                return host.metrics(pr, yc.numpy())
+            t0 = time.perf_counter()
+            mt_c = c5_host()
+            dt5 = time.perf_counter() - t0
+            legs['c5_job']['cpu_baseline'] = {'value': N_C2 / dt5, 'unit': UNIT, 'cores': cores, 'kind': host.kind,
+                                              'ece': float(mt_c[0]), 'sample': '1,000,000 samples, one run of the same job, ' + host.what()}
             n_mc = 2_000_000
             xm, ym_c = synth(n_mc, 17)
             pm_c = torch.softmax(xm, dim=1).numpy()
-            ym_n = ym_c.numpy()
             t0 = time.perf_counter()
-            orc.expected_calibration_error(pm_c, ym_n, 15)
-            orc.neg_log_likelihood(pm_c, ym_n)
-            orc.accuracy(pm_c, ym_n)
+            host.metrics(pm_c, ym_c.numpy())
             dt = time.perf_counter() - t0
-            extra['metrics']['cpu_baseline'] = {'value': n_mc / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                                                'sample': '2,000,000 samples: numpy restatement of utils/metrics.py:35-73, 6-15, 76-80 '
-                                                          '(15 masked passes + one-hot NLL + argmax accuracy)'}
+            legs['metrics']['cpu_baseline'] = {'value': n_mc / dt, 'unit': UNIT, 'cores': 1, 'kind': host.kind,
+                                               'sample': '2,000,000 samples: utils/metrics.py:35-73, 6-15, 76-80 (numpy), ' + host.what()}
+            if 'c1_calibrator' in legs:
+                st1 = host.train_stepper(_nice_flat(), 3, 4, [32], scale=False)
+                g1 = torch.Generator().manual_seed(5)
+                xs1 = 1.5 * torch.randn(10_000, 3, generator=g1)
+                ys1 = torch.randint(0, 3, (10_000,), generator=g1)
+                st1(xs1, ys1)
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    st1(xs1, ys1)
+                dt1 = time.perf_counter() - t0
+                legs['c1_calibrator']['cpu_baseline'] = {
+                    'value': 10_000 * 50 / dt1, 'unit': UNIT, 'cores': cores, 'kind': host.kind,
+                    'sample': '50 full-batch steps on 10,000 samples WITHOUT the reference\'s DataLoader (calibrators.py:'
+                              '268-283 collates per sample, which dominates the reference at this size, SURVEY.md 6), ' + host.what()}
+            if 'calibration_set_epoch' in legs:
+                ge = torch.Generator().manual_seed(7)
+                xse = 1.5 * torch.randn(5000, 10, generator=ge)
+                yse = torch.randint(0, 10, (5000,), generator=ge)
+                ste = host.train_stepper(flat_c2 / 300.0)
+                ste(xse, yse)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    ste(xse, yse)
+                dte = (time.perf_counter() - t0) / 20
+                legs['calibration_set_epoch']['cpu_baseline'] = {
+                    'value': 5000 / dte, 'unit': UNIT, 'cores': cores, 'kind': host.kind, 'us_per_epoch': dte * 1e6,
+                    'sample': '20 full-batch steps on 5,000 samples (no evaluation pass), ' + host.what()}
 
     if rank == 0:
+        def g(v):
+            return None if v is None else round(v / G, 4)
+        tr_ = legs.get('train_step', {})
+        summary = {
+            'unit': 'G samples/s', 'n_gpus': world,
+            'fwd_bf16': g(world * n_head / (fwd_ms['bf16'] * 1e-3)) if 'bf16' in fwd_ms else None,
+            'fwd_fp32': g(world * n_head / (fwd_ms['fp32'] * 1e-3)) if 'fp32' in fwd_ms else None,
+            'e2e_bf16': g(e2e_by.get('bf16')), 'e2e_fp32': g(e2e_by.get('fp32')),
+            'train_bf16': g(tr_.get('bf16', {}).get('value')), 'train_fp32': g(tr_.get('fp32', {}).get('value')),
+            'c5_job': g(legs.get('c5_job', {}).get(head_prec, {}).get('value')),
+            'c5_ece': legs.get('c5_job', {}).get(head_prec, {}).get('ece'),
+            'c4_fwd_bf16': g(legs.get('c4_forward', {}).get('value')),
+            'tensor_frac': round(ach_tf / tf_peak, 4) if head_prec == 'bf16' else None,
+            'dp_check_ok': None if dp_check is None else dp_check['ok'],
+        }
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'l2': 'inputs larger than L2: %d rotating batches' % N_ROT,
-                           'precision_path': precision, 'weights': 'reference init x300 (trained-like), seed 1',
+                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16' if head_prec == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD if n_head == N_HEAD else WORKLOAD.replace('100,000,000', str(n_head)),
+                           'l2': 'inputs larger than L2: %.1f GB of logits per launch' % (n_head * K * 4 / 1e9),
+                           'precision_path': ('bf16 tcgen05 kernel (stated tolerance 1e-2 on z / log-det / probabilities, '
+                                              'measured 4e-4 / 2e-3 / 7e-4); the fp32 kernel (API default, 1e-5) on the '
+                                              'same workload is summary.fwd_fp32 / e2e_fp32') if head_prec == 'bf16'
+                           else 'fp32 CUDA-core kernel (1e-5 of the reference)',
+                           'weights': 'reference init x300 (trained-like), seed 1',
                            'cpu_affinity': ('%d GPU-local CPUs per rank' % numa) if numa else 'default'},
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
-                'roofline_tensor': roof_tensor, 'cpu_baseline': cpu, 'train_step': train, 'train_step_fp32': train_fp32, 'c5': extra}
+                'cpu_baseline': cpu, 'legs': legs, 'dp_check': dp_check, 'summary': summary}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _nice_flat():
+    """Reference init of the C1 NICE flow (K=3, 4 additive couplings, hidden 32): t-nets only."""
+    import torch
+    torch.manual_seed(5)
+    chunks = []
+    for _ in range(4):
+        for fan_in, fan_out in ((3, 32), (32, 3)):
+            lin = torch.nn.Linear(fan_in, fan_out)
+            chunks += [lin.weight.detach().reshape(-1) * 0.001, lin.bias.detach().reshape(-1) * 0.001]
+    return torch.cat(chunks)
 
 
 _JSON_OUT = None
@@ -654,11 +892,14 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='auto', choices=['auto', 'fp32', 'bf16'])
+    ap.add_argument('--head-n', type=int, default=0, help='samples per GPU per headline step (default 10^8)')
     ap.add_argument('--train-n', type=int, default=0, help='training samples per GPU (default: 64 Mi / n_gpus, config C3)')
+    ap.add_argument('--c5-n', type=int, default=0, help='total samples of the C5 job (default 10^8)')
+    ap.add_argument('--c4-n', type=int, default=0, help='samples per GPU of the C4 forward leg (default 10^7)')
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extra', action='store_true')
