@@ -2022,6 +2022,12 @@ int set_smem(Kern k, size_t bytes) {
 
 }  // namespace
 
+// register-resident kernel for K = 10 (cnf_flow_fp32r.cu)
+bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const float* x, const float* z, int tail_bins,
+                         int max_smem, size_t* smem_out);
+int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
+                    int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
+
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
   CnfDims d;
@@ -2030,6 +2036,14 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
+  // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel once the batch fills the GPU
+  // (CNF_FP32R: "off" disables, "0".."5" picks the (threads, samples per thread) variant -- experiments)
+  {
+    const char* sw = getenv("CNF_FP32R");
+    size_t smem_r = 0;
+    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r))
+      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, sw ? atoi(sw) : 0, st);
+  }
   // 32-sample tiles with the hidden layers split over the warps: nets with two or more hidden layers (the widest
   // of at least 64 units), and single-hidden-layer nets on small batches ("0" disables, "1" forces: experiments)
   {
@@ -2107,6 +2121,12 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   if (rc) return rc;
   if (N == 0) return CNF_OK;
   if ((rc = device_limits())) return rc;
+  {
+    size_t smem_r = 0;
+    const char* sw = getenv("CNF_FP32R");
+    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
+      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms, 0, st);
+  }
   LaunchCfg c;
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   if ((rc = choose_cfg(d, false, &c, ta.bins))) return rc;

@@ -98,7 +98,7 @@ metrics_stream_kernel(const T* __restrict__ in, const int64_t* __restrict__ y, i
   if (edges != nullptr)
     for (int i = tid; i <= bins; i += NT) s_edges[i] = (T)edges[i];
   if (log_priors != nullptr)
-    for (int i = tid; i < K; i += NT) m.s_lp[i] = log_priors[i];
+    for (int i = tid; i < K; i += NT) m.s_lp[i] = exp(-log_priors[i]);     // 1 / prior (see row_stats)
   __syncthreads();
 
   const int tile_elems = 32 * K;
@@ -229,7 +229,7 @@ __global__ void metrics_direct_kernel(const T* __restrict__ in, const int64_t* _
   if (edges != nullptr)
     for (int i = tid; i <= bins; i += NT) s_edges[i] = (T)edges[i];
   if (log_priors != nullptr)
-    for (int i = tid; i < K; i += NT) m.s_lp[i] = log_priors[i];
+    for (int i = tid; i < K; i += NT) m.s_lp[i] = exp(-log_priors[i]);     // 1 / prior (see row_stats)
   __syncthreads();
   BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
   double a_nll = 0.0;

@@ -93,30 +93,31 @@ __device__ __forceinline__ void row_stats(Get get, Col col, int yy, int64_t n, i
       conf = (T)best; py = (T)pyf;
       a_nll -= (double)logf(pyf + 1e-7f);
     } else {
-      // u_j = (double)log(p_j + 1e-7f) - log_prior_j ; float64 softmax of u
-      double umax = -INFINITY;
-#pragma unroll
-      for (int jj = 0; jj < K; ++jj) {
-        const float pj = expf((float)get(jj) - mx) / se;
-        const double u = (double)logf(pj + 1e-7f) - s_lp[col(jj)];
-        if (u > umax) umax = u;
-      }
-      double sd = 0.0;
-#pragma unroll
-      for (int jj = 0; jj < K; ++jj) {
-        const float pj = expf((float)get(jj) - mx) / se;
-        sd += exp((double)logf(pj + 1e-7f) - s_lp[col(jj)] - umax);
-      }
-      double best = -1.0, pyd = 0.0;
+      // Calibrator.predict tail (calibrators.py:44): q = softmax(log(p + 1e-7) - log_priors) in float64 on float32 p.
+      // exp(log(p_j + 1e-7) - lp_j) = (p_j + 1e-7) / prior_j, so q_j = w_j / sum_k w_k with
+      // w_j = (double)(p_j + 1e-7f) * (1 / prior_j): the same quantity without the log / exp round trip (the
+      // reference's float32 log contributes <= 1e-6 relative rounding noise to q, which this form does not carry).
+      // s_lp[] holds 1 / prior_j = exp(-log_prior_j), formed once per CTA.
+      double wsum = 0.0, best = -1.0, wy = 0.0;
 #pragma unroll
       for (int jj = 0; jj < K; ++jj) {
         const float pj = expf((float)get(jj) - mx) / se;
         const int c = col(jj);
-        const double q = exp((double)logf(pj + 1e-7f) - s_lp[c] - umax) / sd;
-        if (probs_out != nullptr) probs_out[n * K + c] = q;
-        if (q > best || (q == best && c < pred)) { best = q; pred = c; }
-        if (c == yy) pyd = q;
+        const double w = (double)(pj + 1e-7f) * s_lp[c];
+        wsum += w;
+        if (w > best || (w == best && c < pred)) { best = w; pred = c; }
+        if (c == yy) wy = w;
       }
+      if (probs_out != nullptr) {
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          const float pj = expf((float)get(jj) - mx) / se;
+          const int c = col(jj);
+          probs_out[n * K + c] = (double)(pj + 1e-7f) * s_lp[c] / wsum;
+        }
+      }
+      best /= wsum;
+      const double pyd = wy / wsum;
       a_nll -= log(pyd + 1e-7);
       const unsigned ok = (pred == yy) ? 1u : 0u;
       a_correct += ok; a_n += 1u;
@@ -237,7 +238,7 @@ __device__ __forceinline__ void tail_init(const TailSmem& m, const CnfTail& ta, 
   if (ta.edges != nullptr)
     for (int i = tid; i <= ta.bins; i += NT) m.s_edges[i] = (float)ta.edges[i];
   if (ta.log_priors != nullptr)
-    for (int i = tid; i < K; i += NT) m.s_lp[i] = ta.log_priors[i];
+    for (int i = tid; i < K; i += NT) m.s_lp[i] = exp(-ta.log_priors[i]);     // 1 / prior (see row_stats)
 }
 
 // Tail of one finished sample: get(j) = calibrated logit j (logical class order).
