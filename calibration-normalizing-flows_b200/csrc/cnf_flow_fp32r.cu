@@ -24,14 +24,14 @@ namespace {
 constexpr int RK = 10, RD = 5;          // classes, half split
 
 // one conditioner net for this thread's SPT samples: out[k][q] = b2[q] + sum_h W2[q][h] * relu(b1[h] + sum_j W1[h][j] c[k][j])
-template <int SPT>
+template <int SPT, int U>
 __device__ __forceinline__ void net_eval(const float4* __restrict__ w, const float* __restrict__ b2, int Hp,
                                          const float (&c)[SPT][RD], float (&out)[SPT][RD]) {
 #pragma unroll
   for (int k = 0; k < SPT; ++k)
 #pragma unroll
     for (int q = 0; q < RD; ++q) out[k][q] = b2[q];
-#pragma unroll 2
+#pragma unroll U
   for (int h = 0; h < Hp; ++h) {
     const float4 v0 = w[3 * h], v1 = w[3 * h + 1], v2 = w[3 * h + 2];
 #pragma unroll
@@ -51,24 +51,40 @@ __device__ __forceinline__ void net_eval(const float4* __restrict__ w, const flo
   }
 }
 
-// one coupling layer: c conditions, t is transformed in place (flows/flows.py:105-109 / :119-125)
-template <int SPT>
+// one coupling layer: c conditions, t is transformed in place (flows/flows.py:105-109 / :119-125).  One net's outputs
+// are consumed before the other net runs (forward: scale first, t*e^s then + shift; inverse: shift first, (t - shift)
+// then * e^-s), so only one [SPT][5] output block is live at a time.
+template <int SPT, int U>
 __device__ __forceinline__ void layer_eval(const float4* __restrict__ w, const float* __restrict__ b2, int Hp, int inverse,
                                            const float (&c)[SPT][RD], float (&t)[SPT][RD], float (&ld)[SPT]) {
-  float s[SPT][RD], sh[SPT][RD];
-  net_eval<SPT>(w, b2, Hp, c, s);
-  net_eval<SPT>(w + 3 * Hp, b2 + 8, Hp, c, sh);
+  float o[SPT][RD];
+  if (!inverse) {
+    net_eval<SPT, U>(w, b2, Hp, c, o);                       // s
 #pragma unroll
-  for (int k = 0; k < SPT; ++k)
+    for (int k = 0; k < SPT; ++k)
 #pragma unroll
-    for (int q = 0; q < RD; ++q) {
-      if (!inverse) { t[k][q] = t[k][q] * expf(s[k][q]) + sh[k][q]; ld[k] += s[k][q]; }
-      else          { t[k][q] = (t[k][q] - sh[k][q]) * expf(-s[k][q]); ld[k] -= s[k][q]; }
-    }
+      for (int q = 0; q < RD; ++q) { t[k][q] *= expf(o[k][q]); ld[k] += o[k][q]; }
+    net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);          // shift
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int q = 0; q < RD; ++q) t[k][q] += o[k][q];
+  } else {
+    net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);          // shift
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int q = 0; q < RD; ++q) t[k][q] -= o[k][q];
+    net_eval<SPT, U>(w, b2, Hp, c, o);                       // s
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+#pragma unroll
+      for (int q = 0; q < RD; ++q) { t[k][q] *= expf(-o[k][q]); ld[k] -= o[k][q]; }
+  }
 }
 
-template <int R_NT, int SPT, int TAIL>
-__global__ void __launch_bounds__(R_NT, (R_NT * SPT >= 1024 || R_NT >= 512) ? 1 : 2)
+template <int R_NT, int SPT, int U, int MINB, int TAIL>
+__global__ void __launch_bounds__(R_NT, MINB)
 flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                   const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
                   int inverse, CnfTail ta) {
@@ -167,8 +183,8 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
       const int l = inverse ? L - 1 - li : li;
       const float4* w = ws + (size_t)l * 2 * Hp * 3;
       const float* b2 = b2s + l * 16;
-      if (l & 1) layer_eval<SPT>(w, b2, Hp, inverse, lo, hi, ld);
-      else       layer_eval<SPT>(w, b2, Hp, inverse, hi, lo, ld);
+      if (l & 1) layer_eval<SPT, U>(w, b2, Hp, inverse, lo, hi, ld);
+      else       layer_eval<SPT, U>(w, b2, Hp, inverse, hi, lo, ld);
     }
     // ---- registers -> rows (+ fused tail) -----------------------------------------------------------------------
 #pragma unroll
@@ -205,17 +221,17 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
   if (TAIL) stats_finish_block(a_nll, a_correct, a_n, cache, tsm.s_cnt, tsm.s_cor, tsm.s_conf, ta.bins, ta.acc, tail_red, tid, R_NT);
 }
 
-template <int R_NT, int SPT, int TAIL>
+template <int R_NT, int SPT, int U, int MINB, int TAIL>
 int launch_reg10(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                  int64_t N, int inverse, const CnfTail& ta, size_t smem, int sms, cudaStream_t st) {
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_reg10_kernel<R_NT, SPT, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_reg10_kernel<R_NT, SPT, TAIL>, R_NT, smem));
+  CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, R_NT, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t ntiles = (N + R_NT * SPT - 1) / (R_NT * SPT);
   const int64_t cap = (int64_t)sms * per_sm;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
-  flow_reg10_kernel<R_NT, SPT, TAIL><<<grid, R_NT, smem, st>>>(d, packed, tables, x, z, logdet, N, inverse, ta);
+  flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL><<<grid, R_NT, smem, st>>>(d, packed, tables, x, z, logdet, N, inverse, ta);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -238,15 +254,18 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st) {
   const CnfTail ta = tail ? *tail : CnfTail();
   if (!tail) {
-    switch (variant) {      // (threads per CTA, samples per thread): experiment switch, see cnf_fp32_apply
-      case 1: return launch_reg10<256, 3, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-      case 2: return launch_reg10<256, 4, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-      case 3: return launch_reg10<512, 2, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-      case 4: return launch_reg10<384, 2, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-      case 5: return launch_reg10<128, 4, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-      default: return launch_reg10<256, 2, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
+#define RV(NT, SPT, U, MB) return launch_reg10<NT, SPT, U, MB, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st)
+    // Measured on B200 at the C2 shape, 10^7 samples (profiles/microbench/fp32r_speed.py): 128 threads x 8 samples
+    // 1.59 G samples/s; x 6 (3 CTAs/SM) 1.52; x 4 1.44; 256 x 8 (1 CTA/SM) 1.57; 128 x 12 (1 CTA/SM, 4 warps) 1.59;
+    // 64 x 8 1.19; generic flow_apply_kernel 0.79.  Samples per thread (weight loads per FMA) matter, occupancy does not.
+    switch (variant) {      // (threads per CTA, samples per thread, unroll, min CTAs per SM): experiment switch
+      case 1: RV(128, 4, 2, 3);
+      case 2: RV(128, 6, 2, 3);
+      case 3: RV(256, 8, 2, 1);
+      default: RV(128, 8, 2, 2);
     }
+#undef RV
   }
-  if (ta.mode == CNF_METRICS_LOGITS) return launch_reg10<256, 2, CNF_METRICS_LOGITS>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-  return launch_reg10<256, 2, CNF_METRICS_CALIBRATED>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
+  if (ta.mode == CNF_METRICS_LOGITS) return launch_reg10<128, 8, 2, 2, CNF_METRICS_LOGITS>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
+  return launch_reg10<128, 8, 2, 2, CNF_METRICS_CALIBRATED>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
 }
