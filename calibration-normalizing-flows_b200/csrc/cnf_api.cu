@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "cnf_common.h"
 
@@ -125,29 +126,38 @@ extern "C" int cnf_flow_backward_rows(const cnf_flow_desc* desc, const void* pac
 // ------------------------------------------------------------------------------------------
 namespace {
 constexpr int kHostSlots = 4;
+constexpr int kMaxDev = 64;
 struct HostPool {
   bool ready = false;
-  int device = -1;
   cudaStream_t s[kHostSlots];
   cudaEvent_t done[kHostSlots];
   cudaEvent_t start;
 };
-HostPool g_pool;   // one-time, per process (single device per process in this framework)
+HostPool g_pool[kMaxDev];   // one per device, created on first use and kept for the life of the process
+std::mutex g_pool_mu;
 
-int pool_init() {
+int pool_get(HostPool** out) {
   int dev = 0;
   CNF_CHECK_CUDA(cudaGetDevice(&dev));
-  if (g_pool.ready && g_pool.device == dev) return CNF_OK;
-  for (int i = 0; i < kHostSlots; ++i) {
-    CNF_CHECK_CUDA(cudaStreamCreateWithFlags(&g_pool.s[i], cudaStreamNonBlocking));
-    CNF_CHECK_CUDA(cudaEventCreateWithFlags(&g_pool.done[i], cudaEventDisableTiming));
+  if (dev < 0 || dev >= kMaxDev) { cnf_set_error("device id %d out of range", dev); return CNF_E_CUDA; }
+  HostPool& p = g_pool[dev];
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  if (!p.ready) {
+    for (int i = 0; i < kHostSlots; ++i) {
+      CNF_CHECK_CUDA(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));
+      CNF_CHECK_CUDA(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+    }
+    CNF_CHECK_CUDA(cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming));
+    p.ready = true;
   }
-  CNF_CHECK_CUDA(cudaEventCreateWithFlags(&g_pool.start, cudaEventDisableTiming));
-  g_pool.ready = true;
-  g_pool.device = dev;
+  *out = &p;
   return CNF_OK;
 }
 }  // namespace
+
+// true when the fp32 path would run a kernel that reads its rows with plain loads straight from `x` (no shared-memory
+// staging of whole tiles), i.e. one that can run on device-mapped host memory without a slow-down of the other SMs
+bool cnf_fp32_streams_rows(const cnf_flow_desc* desc, const float* x, const float* z, int64_t N);
 
 extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
                                    const float* x_host, float* z_host, float* logdet_host, int64_t N, int32_t inverse,
@@ -170,24 +180,31 @@ extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed
   // (cp.async, one tile ahead per slot, ~2 MB in flight) hides the PCIe latency and both
   // directions stream concurrently, without per-chunk DMA set-up costs: 1.18 ms vs 1.58 ms per
   // 10^6 K=10 samples on B200 (46 GB/s per direction when both are busy).
-  if (desc->precision == CNF_PREC_BF16_TC && !getenv("CNF_NO_ZEROCOPY")) {
+  // The fp32 register-resident kernel (K = 10) reads and writes its rows straight from / to global memory as well
+  // and takes the same route.
+  if (!cnf_switch(CNF_SW_NO_ZEROCOPY)) {
     cudaPointerAttributes ax, az, al;
     const bool ok = cudaPointerGetAttributes(&ax, x_host) == cudaSuccess && ax.type == cudaMemoryTypeHost &&
                     cudaPointerGetAttributes(&az, z_host) == cudaSuccess && az.type == cudaMemoryTypeHost &&
                     cudaPointerGetAttributes(&al, logdet_host) == cudaSuccess && al.type == cudaMemoryTypeHost;
     cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers
-    if (ok)
+    if (ok && desc->precision == CNF_PREC_BF16_TC)
       return cnf_tc_apply(desc, packed, tables, (const float*)ax.devicePointer, (float*)az.devicePointer,
                           (float*)al.devicePointer, N, inverse, user);
+    if (ok && cnf_fp32_streams_rows(desc, (const float*)ax.devicePointer, (const float*)az.devicePointer, N))
+      return cnf_fp32_apply(desc, (const float*)packed, tables, (const float*)ax.devicePointer, (float*)az.devicePointer,
+                            (float*)al.devicePointer, nullptr, N, inverse, user);
   }
-  if ((rc = pool_init())) return rc;
-  CNF_CHECK_CUDA(cudaEventRecord(g_pool.start, user));          // weights were packed on the caller's stream
-  for (int i = 0; i < slots; ++i) CNF_CHECK_CUDA(cudaStreamWaitEvent(g_pool.s[i], g_pool.start, 0));
+  HostPool* poolp = nullptr;
+  if ((rc = pool_get(&poolp))) return rc;
+  HostPool& pool = *poolp;
+  CNF_CHECK_CUDA(cudaEventRecord(pool.start, user));          // weights were packed on the caller's stream
+  for (int i = 0; i < slots; ++i) CNF_CHECK_CUDA(cudaStreamWaitEvent(pool.s[i], pool.start, 0));
   int64_t lo = 0;
   for (int64_t c = 0; lo < N; ++c, lo += chunk) {
     const int64_t n = (N - lo < chunk) ? N - lo : chunk;
     const int i = (int)(c % slots);
-    cudaStream_t st = g_pool.s[i];
+    cudaStream_t st = pool.s[i];
     float* xin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + (size_t)i * per_slot);
     float* zout = xin + chunk * K;
     float* ld = zout + chunk * K;
@@ -199,8 +216,8 @@ extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed
     CNF_CHECK_CUDA(cudaMemcpyAsync(logdet_host + lo, ld, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   for (int i = 0; i < slots; ++i) {
-    CNF_CHECK_CUDA(cudaEventRecord(g_pool.done[i], g_pool.s[i]));
-    CNF_CHECK_CUDA(cudaStreamWaitEvent(user, g_pool.done[i], 0));
+    CNF_CHECK_CUDA(cudaEventRecord(pool.done[i], pool.s[i]));
+    CNF_CHECK_CUDA(cudaStreamWaitEvent(user, pool.done[i], 0));
   }
   return CNF_OK;
 }

@@ -49,6 +49,27 @@ CNF_HD inline int cnf_tail_smem_bytes(int bins, int K) {
 }
 
 void cnf_set_error(const char* fmt, ...);
+
+// ---- per-device state (cnf_device.cu) -------------------------------------------------------------------
+// The library keeps no mutable state besides these caches, all keyed by CUDA device id and filled once under a
+// mutex: device limits, the dynamic-shared-memory attribute already granted to each kernel, and the internal
+// stream pool of cnf_flow_apply_host.  Any number of devices per process; calls act on the CURRENT device.
+struct CnfDevInfo { int id, sms, max_smem; };
+int cnf_dev_info(CnfDevInfo* out);
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes) once per (device, kernel): repeated launches with
+// a size already granted cost one table lookup.
+int cnf_func_smem(const void* func, int bytes);
+template <typename Kern>
+static inline int cnf_kernel_smem(Kern k, size_t bytes) { return cnf_func_smem(reinterpret_cast<const void*>(k), (int)bytes); }
+
+// Experiment switches (environment variables, see NOTES.md): looked up ONCE per process and cached -- the launch
+// path never calls getenv -- unless CNF_LIVE_ENV is set (tests and micro-benchmarks flip switches between calls).
+enum CnfSwitch {
+  CNF_SW_NO_ZEROCOPY, CNF_SW_DEEP_APPLY, CNF_SW_DEEP_TRAIN, CNF_SW_FORCE_LEAN, CNF_SW_FP32R, CNF_SW_FP32_NO_WL,
+  CNF_SW_FP32_NT, CNF_SW_FP32_WS, CNF_SW_NO_LEAN_TRAIN, CNF_SW_SPLIT_GENERIC, CNF_SW_SPLIT_SEQ, CNF_SW_SPLIT_TRAIN,
+  CNF_SW_TC_EPI, CNF_SW_TC_GENERIC, CNF_SW_METRICS_STAGES, CNF_SW_COUNT
+};
+const char* cnf_switch(CnfSwitch s);   // value of the switch or nullptr
 int cnf_make_dims(const cnf_flow_desc* desc, CnfDims* out);
 long long cnf_tc_blob_bytes(const cnf_flow_desc* desc, const CnfDims& d);
 

@@ -1962,16 +1962,15 @@ flow_train_deep_kernel(CnfDims d, const float* __restrict__ packed, const int* _
 // --------------------------------------------------------------------------------------
 struct LaunchCfg { int spt, nt; bool ws; int wl; size_t smem; };
 
-int g_max_smem = -1, g_num_sms = -1;
+// limits of the current device (cached per device in cnf_device.cu); thread-local so that concurrent host threads
+// driving different devices do not see each other's values
+thread_local int g_max_smem = -1, g_num_sms = -1;
 
 int device_limits() {
-  if (g_max_smem >= 0) return CNF_OK;
-  int dev = 0;
-  CNF_CHECK_CUDA(cudaGetDevice(&dev));
-  int v = 0, s = 0;
-  CNF_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
-  g_max_smem = v; g_num_sms = s;
+  CnfDevInfo di;
+  int rc = cnf_dev_info(&di);
+  if (rc) return rc;
+  g_max_smem = di.max_smem; g_num_sms = di.sms;
   return CNF_OK;
 }
 
@@ -1982,12 +1981,12 @@ int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out, int tail_bins = 
   // 256-thread CTAs share one staged copy of the weights between twice as many warps: 16 instead of 8
   // resident warps per SM at the C2 shape, 1.83 -> 1.34 ms per 2^20 samples on B200
   int nt_max = 256;
-  if (const char* v = getenv("CNF_FP32_NT")) { const int n = atoi(v); if (n == 256 || n == 128) nt_max = n; }
+  if (const char* v = cnf_switch(CNF_SW_FP32_NT)) { const int n = atoi(v); if (n == 256 || n == 128) nt_max = n; }
   int ws_first = 1;
-  if (const char* v = getenv("CNF_FP32_WS")) ws_first = atoi(v) ? 1 : 0;   // experiment switch: 0 = never stage the weights
+  if (const char* v = cnf_switch(CNF_SW_FP32_WS)) ws_first = atoi(v) ? 1 : 0;   // experiment switch: 0 = never stage the weights
   out->wl = 0;
   // training: a full-width tile with one layer's weights staged at a time beats a narrower tile with all of them
-  if (backward && ws_first && !getenv("CNF_FP32_NO_WL")) {
+  if (backward && ws_first && !cnf_switch(CNF_SW_FP32_NO_WL)) {
     for (int mode = 1; mode <= 2; ++mode) {
       const int TSP = nt_max + 4;
       const size_t bytes = (size_t)make_smem(d, TSP, mode, true).total * 4;
@@ -2015,10 +2014,7 @@ int choose_cfg(const CnfDims& d, bool backward, LaunchCfg* out, int tail_bins = 
 }
 
 template <typename Kern>
-int set_smem(Kern k, size_t bytes) {
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return CNF_OK;
-}
+int set_smem(Kern k, size_t bytes) { return cnf_kernel_smem(k, bytes); }
 
 }  // namespace
 
@@ -2027,6 +2023,14 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
                          int max_smem, size_t* smem_out);
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
+
+bool cnf_fp32_streams_rows(const cnf_flow_desc* desc, const float* x, const float* z, int64_t N) {
+  CnfDims d;
+  size_t smem_r = 0;
+  const char* sw = cnf_switch(CNF_SW_FP32R);
+  if (cnf_make_dims(desc, &d) != CNF_OK || device_limits() != CNF_OK) return false;
+  return N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r);
+}
 
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
@@ -2039,7 +2043,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel once the batch fills the GPU
   // (CNF_FP32R: "off" disables, "0".."5" picks the (threads, samples per thread) variant -- experiments)
   {
-    const char* sw = getenv("CNF_FP32R");
+    const char* sw = cnf_switch(CNF_SW_FP32R);
     size_t smem_r = 0;
     if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, sw ? atoi(sw) : 0, st);
@@ -2047,7 +2051,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   // 32-sample tiles with the hidden layers split over the warps: nets with two or more hidden layers (the widest
   // of at least 64 units), and single-hidden-layer nets on small batches ("0" disables, "1" forces: experiments)
   {
-    const char* sw = getenv("CNF_DEEP_APPLY");
+    const char* sw = cnf_switch(CNF_SW_DEEP_APPLY);
     bool fits = d.m >= 1;
     for (int j = 0; j < d.m; ++j) fits = fits && d.Hp[j] <= 256;
     const bool want = sw ? atoi(sw) != 0 : (d.Hmax >= 64 && (d.m >= 2 || N <= 32768));
@@ -2074,7 +2078,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, false, &c);
   // single-hidden-layer nets whose weights do not fit shared memory: staged-chunk kernel instead of L1 reads
-  if (d.m == 1 && (rc != CNF_OK || !c.ws) && !getenv("CNF_NO_LEAN_TRAIN")) {
+  if (d.m == 1 && (rc != CNF_OK || !c.ws) && !cnf_switch(CNF_SW_NO_LEAN_TRAIN)) {
     for (int nt = 256; nt >= 64; nt >>= 1) {
       const int TSP = nt + 4;
       const size_t bytes = ((size_t)(d.n_tables + 3) / 4 * 4 + (size_t)d.K * TSP + 2 * (size_t)d.d0 * TSP +
@@ -2123,7 +2127,7 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   if ((rc = device_limits())) return rc;
   {
     size_t smem_r = 0;
-    const char* sw = getenv("CNF_FP32R");
+    const char* sw = cnf_switch(CNF_SW_FP32R);
     if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms, 0, st);
   }
@@ -2180,12 +2184,12 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // single-hidden-layer nets up to 256 hidden units: 32-sample tiles with the hidden layer split over the warps
   // (faster than one thread per sample at every batch size measured, 3x at N <= 10,000)
   {
-    const char* sw = getenv("CNF_SPLIT_TRAIN");          // "0" disables (experiments)
+    const char* sw = cnf_switch(CNF_SW_SPLIT_TRAIN);          // "0" disables (experiments)
     const bool want = sw ? atoi(sw) != 0 : true;
     if (want && d.m == 1 && d.Hp[0] <= 256) {
       const int nch = d.Hp[0] / CH;
       // both nets side by side when the warps fit and every tile gets an SM of its own (the 512-thread CTA is alone on its SM)
-      const bool side_by_side = d.n_nets == 2 && nch <= 8 && (N + SPL_TS - 1) / SPL_TS <= g_num_sms && !getenv("CNF_SPLIT_SEQ");
+      const bool side_by_side = d.n_nets == 2 && nch <= 8 && (N + SPL_TS - 1) / SPL_TS <= g_num_sms && !cnf_switch(CNF_SW_SPLIT_SEQ);
       const int nw = side_by_side ? 2 * nch : nch;
       const size_t bytes = (size_t)make_split(d, nw, nch).total * sizeof(float);
       if ((long long)bytes <= g_max_smem - 1024) {
@@ -2198,7 +2202,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
         int64_t cap = (int64_t)g_num_sms * per_sm;
         if (cap > d.grad_rows) cap = d.grad_rows;          // every CTA owns one row of the partial buffer
         const int grids = (int)(nts < cap ? nts : cap);
-        const bool dc5 = d.d0 == 5 && d.d1 == 5 && !getenv("CNF_SPLIT_GENERIC");
+        const bool dc5 = d.d0 == 5 && d.d1 == 5 && !cnf_switch(CNF_SW_SPLIT_GENERIC);
         if ((rc = dc5 ? set_smem(flow_train_split_kernel<5>, bytes) : set_smem(flow_train_split_kernel<0>, bytes))) return rc;
         if ((rc = clear_rows(grids))) return rc;
         if (dc5)
@@ -2215,7 +2219,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // hidden layers of up to 256 units, the widest of at least 64: the same tiles with the activations exchanged through
   // shared memory (narrower nets are quicker with one thread per sample; "1" forces, "0" disables: experiments)
   {
-    const char* sw = getenv("CNF_DEEP_TRAIN");
+    const char* sw = cnf_switch(CNF_SW_DEEP_TRAIN);
     // (also single-hidden-layer nets that did not fit the plan above with its staged weights, on small batches:
     //  K=30 / hidden 256 at N=10,000: 2.3 -> 0.8 ms per step)
     bool fits = d.m >= 2 || (d.m == 1 && N <= 65536);
@@ -2247,8 +2251,8 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
   rc = choose_cfg(d, true, &c);
   // single-hidden-layer nets whose full plan only fits narrow tiles (or does not fit at all): lean kernel
-  const char* force_lean = getenv("CNF_FORCE_LEAN");      // experiment switch: "<nt>" forces the lean kernel with that tile
-  if (d.m == 1 && (rc != CNF_OK || c.nt * c.spt < 128 || force_lean) && !getenv("CNF_NO_LEAN_TRAIN")) {
+  const char* force_lean = cnf_switch(CNF_SW_FORCE_LEAN);      // experiment switch: "<nt>" forces the lean kernel with that tile
+  if (d.m == 1 && (rc != CNF_OK || c.nt * c.spt < 128 || force_lean) && !cnf_switch(CNF_SW_NO_LEAN_TRAIN)) {
     for (int nt = force_lean ? atoi(force_lean) : 256; nt >= 64; nt >>= 1) {
       const size_t bytes = (size_t)make_lean(d, nt + 4).total * sizeof(float);
       if ((long long)bytes > g_max_smem - 1024) continue;

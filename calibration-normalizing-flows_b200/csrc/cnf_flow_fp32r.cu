@@ -224,7 +224,7 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
 template <int R_NT, int SPT, int U, int MINB, int TAIL>
 int launch_reg10(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                  int64_t N, int inverse, const CnfTail& ta, size_t smem, int sms, cudaStream_t st) {
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc = cnf_kernel_smem(flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, smem); if (rc) return rc; }
   int per_sm = 0;
   CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, R_NT, smem));
   if (per_sm < 1) per_sm = 1;

@@ -429,7 +429,6 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
   if (TAIL) stats_finish_block(a_nll, a_correct, a_n, cache, tsm.s_cnt, tsm.s_cor, tsm.s_conf, ta.bins, ta.acc, tail_red, tid, TC_THREADS);
 }
 
-int g_tc_sms = -1;
 
 }  // namespace
 
@@ -552,23 +551,20 @@ int cnf_tc_apply_ex(const cnf_flow_desc* desc, const void* packed_tc, const int3
     t.sm_total += cnf_tail_smem_bytes(tail->bins, d.K);
     if (t.sm_total > 227 * 1024) { cnf_set_error("fused tail: %d bins do not fit shared memory", tail->bins); return CNF_E_SMEM; }
   }
-  if (g_tc_sms < 0) {
-    int dev = 0, s = 0;
-    CNF_CHECK_CUDA(cudaGetDevice(&dev));
-    CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
-    g_tc_sms = s;
-  }
+  CnfDevInfo di;
+  if ((rc = cnf_dev_info(&di))) return rc;
+  const int g_tc_sms = di.sms;
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int grid = (int)(ntiles < g_tc_sms ? ntiles : g_tc_sms);
   // 16-byte tile I/O needs 16 B-aligned pointers and whole tiles that are a multiple of 16 B
   const int io16 = (((uintptr_t)x | (uintptr_t)z) % 16 == 0 && (TILE_M * d.K) % 4 == 0) ? 1 : 0;
   int epi = 0;
-  if (const char* v = getenv("CNF_TC_EPI")) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
-  const int sh = (d.K == 10 && t.Hp == 128 && d.nets == 3 && !getenv("CNF_TC_GENERIC")) ? 1 : 0;
+  if (const char* v = cnf_switch(CNF_SW_TC_EPI)) epi = atoi(v);   // 0: round-to-nearest F2FP, 1: truncate+compensate
+  const int sh = (d.K == 10 && t.Hp == 128 && d.nets == 3 && !cnf_switch(CNF_SW_TC_GENERIC)) ? 1 : 0;
   const CnfTail ta = tail ? *tail : CnfTail();
 #define LAUNCH_TC_S(E, T, S, M)                                                                                 \
   do {                                                                                                          \
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tc_kernel<E, T, S, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total)); \
+    if ((rc = cnf_kernel_smem(flow_tc_kernel<E, T, S, M>, t.sm_total))) return rc;                                          \
     flow_tc_kernel<E, T, S, M><<<grid, TC_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, \
                                                                      inverse, io16, tape, ta);                  \
   } while (0)

@@ -590,16 +590,10 @@ __global__ void tcb_reduce_kernel(const float* __restrict__ partials, const int*
   flat_grad[g] = (a0 + a1) + (a2 + a3);
 }
 
-int g_tb_sms = -1;
 
 int tb_sms() {
-  if (g_tb_sms < 0) {
-    int dev = 0, s = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    g_tb_sms = s;
-  }
-  return g_tb_sms;
+  CnfDevInfo di;
+  return cnf_dev_info(&di) == CNF_OK ? di.sms : -1;
 }
 
 }  // namespace
@@ -686,9 +680,8 @@ extern "C" int cnf_nll_train_step_tc(const cnf_flow_desc* desc, const void* pack
   float* zbuf = reinterpret_cast<float*>(workspace);
   float* ldbuf = zbuf + chunk * d.K;
   float* tapebuf = ldbuf + chunk;
-  const bool sh = d.K == 10 && t.Hp == 128 && d.nets == 3 && !getenv("CNF_TC_GENERIC");
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+  const bool sh = d.K == 10 && t.Hp == 128 && d.nets == 3 && !cnf_switch(CNF_SW_TC_GENERIC);
+  if ((rc = sh ? cnf_kernel_smem(flow_tcb_kernel<1>, t.sm_total) : cnf_kernel_smem(flow_tcb_kernel<0>, t.sm_total))) return rc;
   for (int64_t lo = 0; lo < N; lo += chunk) {
     const int64_t n = (N - lo < chunk) ? N - lo : chunk;
     rc = cnf_tc_apply_tape(desc, packed_tc, tables, x + lo * d.K, zbuf, ldbuf, grad_partials_tc ? tapebuf : nullptr, n, 0, st);

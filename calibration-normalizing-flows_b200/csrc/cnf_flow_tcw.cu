@@ -341,7 +341,6 @@ __global__ void tcw_gather_f32(const float* __restrict__ flat, const int* __rest
   if (i < n) { const int gi = gather[i]; out[i] = gi >= 0 ? flat[gi] : 0.f; }
 }
 
-int g_tcw_sms = -1;
 
 }  // namespace
 
@@ -407,21 +406,18 @@ int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables
                   float* logdet, int64_t N, int inverse, cudaStream_t st) {
   TcwDims t;
   if (!tcw_dims(d, &t)) { cnf_set_error("wide tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
-  if (g_tcw_sms < 0) {
-    int dev = 0, s = 0;
-    CNF_CHECK_CUDA(cudaGetDevice(&dev));
-    CNF_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev));
-    g_tcw_sms = s;
-  }
+  CnfDevInfo di;
+  { const int rc2 = cnf_dev_info(&di); if (rc2) return rc2; }
+  const int g_tcw_sms = di.sms;
   if ((uintptr_t)packed_tc % 16 != 0) { cnf_set_error("packed_tc must be 16-byte aligned"); return CNF_E_ARG; }
   const int64_t ntiles = (N + TILE_M - 1) / TILE_M;
   const int grid = (int)(ntiles < g_tcw_sms ? ntiles : g_tcw_sms);
-  const bool sh = d.K == 100 && d.H[0] == 512 && d.nets == 3 && !getenv("CNF_TC_GENERIC");
+  const bool sh = d.K == 100 && d.H[0] == 512 && d.nets == 3 && !cnf_switch(CNF_SW_TC_GENERIC);
   if (sh) {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    { const int rc2 = cnf_kernel_smem(flow_tcw_kernel<1>, t.sm_total); if (rc2) return rc2; }
     flow_tcw_kernel<1><<<grid, W_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse);
   } else {
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(flow_tcw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.sm_total));
+    { const int rc2 = cnf_kernel_smem(flow_tcw_kernel<0>, t.sm_total); if (rc2) return rc2; }
     flow_tcw_kernel<0><<<grid, W_THREADS, t.sm_total, st>>>(t, (const uint8_t*)packed_tc, tables, x, z, logdet, N, inverse);
   }
   CNF_CHECK_CUDA(cudaGetLastError());

@@ -272,7 +272,7 @@ int launch_metrics(const T* in, const int64_t* y, int64_t N, int K, int bins, in
   for (int wi = 0; wi < 3 && !nwarps && aligned; ++wi)
     for (int si = 0; si < 3; ++si)
       if (fixed + 16 + (tile * sopts[si] + hist_per_warp) * wopts[wi] <= budget) { nwarps = wopts[wi]; stages = sopts[si]; break; }
-  if (const char* v = getenv("CNF_METRICS_STAGES")) { const int sv = atoi(v); if (sv >= 2 && sv <= 4 && nwarps) stages = sv; }
+  if (const char* v = cnf_switch(CNF_SW_METRICS_STAGES)) { const int sv = atoi(v); if (sv >= 2 && sv <= 4 && nwarps) stages = sv; }
   if (nwarps) {
     const size_t smem = fixed + tile * nwarps * stages + (hist_per_warp ? 16 + hist_per_warp * nwarps : 0);
     const int64_t nt = (N + 31) / 32;
@@ -286,8 +286,7 @@ int launch_metrics(const T* in, const int64_t* y, int64_t N, int K, int bins, in
     const bool priv = hist_per_warp > 0 && tiles_per_warp < 65536;     // 16-bit private counts
 #define LAUNCH_STREAM_KP(M, KT, P)                                                                           \
   do {                                                                                                       \
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_stream_kernel<T, M, KT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                         \
+    { const int rc2 = cnf_kernel_smem(metrics_stream_kernel<T, M, KT, P>, smem); if (rc2) return rc2; }     \
     metrics_stream_kernel<T, M, KT, P><<<(int)grid, nwarps * 32, smem, st>>>(in, y, N, K, bins, lp, edges, acc, \
                                                                                probs_out, stages, rot);      \
   } while (0)
@@ -311,8 +310,7 @@ int launch_metrics(const T* in, const int64_t* y, int64_t N, int K, int bins, in
     const int grid = (int)(want < cap ? want : cap);
 #define LAUNCH_DIRECT(M)                                                                                     \
   do {                                                                                                       \
-    CNF_CHECK_CUDA(cudaFuncSetAttribute(metrics_direct_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)fixed));                                                        \
+    { const int rc2 = cnf_kernel_smem(metrics_direct_kernel<T, M>, fixed); if (rc2) return rc2; }           \
     metrics_direct_kernel<T, M><<<grid, nt, fixed, st>>>(in, y, N, K, bins, lp, edges, acc, probs_out);        \
   } while (0)
     if (mode == CNF_METRICS_PROBS) LAUNCH_DIRECT(CNF_METRICS_PROBS);

@@ -300,8 +300,7 @@ int launch_cfg(int64_t N, int K, size_t smem, int* grid) {
 
 template <typename Kern>
 int set_smem(Kern k, size_t bytes) {
-  CNF_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return CNF_OK;
+  return cnf_kernel_smem(k, bytes);
 }
 
 }  // namespace

@@ -3,6 +3,8 @@ flow_apply_kernel (CNF_FP32R=off), CUDA events, 10^7 samples; parity of every va
 import os
 import sys
 
+os.environ['CNF_LIVE_ENV'] = '1'     # switches are flipped between calls below
+
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))

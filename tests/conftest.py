@@ -11,6 +11,9 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
+# the library caches its experiment switches at first use; tests flip them between calls (monkeypatch.setenv)
+os.environ.setdefault('CNF_LIVE_ENV', '1')
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
