@@ -208,8 +208,11 @@ class FusedNLLTrainer:
     def epoch_graph(self):
         """One full-batch epoch of ``fit`` -- optimiser step, then the evaluation pass into ``self.eval_acc``
         -- as ONE CUDA-graph launch.  The first call runs the body eagerly (allocating every buffer) and
-        captures it; later calls replay (~10 launches per epoch become one).  Under torch.distributed (NCCL)
-        the all-reduce is part of the captured graph; every rank must then call this the same number of times."""
+        captures it; later calls replay (~10 launches per epoch become one).  Single-process only: capturing the
+        NCCL all-reduce inside the graph hung on this stack (torch 2.11 / NCCL 2.28.9, 2 x B200; NOTES.md), so
+        under torch.distributed the eager ``step`` / ``evaluate`` pair is used."""
+        if self.dist is not None:
+            raise RuntimeError('epoch_graph is single-process; use step() / evaluate() under torch.distributed')
         if getattr(self, '_graph', None) is None:
             self.eval_acc = torch.zeros(4, dtype=torch.float64, device=self.x.device)
             self._epoch_body()                                   # epoch 0: eager, for real
@@ -233,7 +236,9 @@ class FusedNLLTrainer:
     def step_graph(self):
         """``step()`` on all local samples as ONE CUDA-graph launch (no evaluation pass: ``fit`` takes an epoch's
         evaluation from the next step's forward, see there).  First call: eager + capture; later calls replay.
-        Under torch.distributed (NCCL) the one all-reduce of the step is captured with it."""
+        Single-process only (see epoch_graph)."""
+        if self.dist is not None:
+            raise RuntimeError('step_graph is single-process; use step() under torch.distributed')
         if getattr(self, '_sgraph', None) is None:
             self._step_body()                                    # step 0: eager, for real
             torch.cuda.current_stream(self.x.device).synchronize()
@@ -255,7 +260,7 @@ class FusedNLLTrainer:
         # (plan_fit), never from the rank-local shard size.
         full_batch, local_bs, steps_per_epoch, batch_totals = plan_fit(n_all, world, batch_size)
         hist = torch.zeros((max(epochs, 0), 4), dtype=torch.float64, device=x.device)
-        use_graph = full_batch and cuda_graph
+        use_graph = full_batch and cuda_graph and self.dist is None
         for epoch in range(epochs):
             if full_batch:
                 # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the
