@@ -464,12 +464,32 @@ def run_ours(args):
         t = wall_timed(e2e_step, steps, 3)
         e2e_by[prec] = world * calls_per_step * n_chunk / (t * 1e-3)
     model.flow.precision = 'fp32'
+    # platform ceiling of this leg: pinned cudaMemcpyAsync of the same buffers, both directions at once, on every rank
+    # at the same time (what the box's host-memory / PCIe path carries, whatever kernel sits in between)
+    d_in = torch.empty_like(xh, device=dev)
+    d_out = torch.empty((n_chunk, K + 1), dtype=torch.float32, device=dev)
+    h_out = torch.empty((n_chunk, K + 1), dtype=torch.float32, pin_memory=True)
+    cs1, cs2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copy_round(i):
+        with torch.cuda.stream(cs1):
+            d_in.copy_(xh, non_blocking=True)
+        with torch.cuda.stream(cs2):
+            h_out.copy_(d_out, non_blocking=True)
+        cs1.synchronize()
+        cs2.synchronize()
+    t_copy = wall_timed(copy_round, 5, 3)
+    ceiling = world * n_chunk / (t_copy * 1e-3)
+    del d_in, d_out, h_out
     e2e = {'value': e2e_by[head_prec], 'unit': UNIT,
            'h2d_bytes_per_step': calls_per_step * xh.numel() * 4,
            'd2h_bytes_per_step': calls_per_step * (zh.numel() * 4 + lh.numel() * 4),
            'api': 'RealNvpFlow.transform_host -> cnf_flow_apply_host: pinned host logits in, host z + log-det out; '
                   'one step = %d calls of %d samples through the same pinned buffers' % (calls_per_step, n_chunk),
-           'by_precision': e2e_by}
+           'by_precision': e2e_by,
+           'platform_ceiling': {'value': ceiling, 'unit': UNIT, 'frac': e2e_by[head_prec] / ceiling,
+                                'what': 'pinned cudaMemcpyAsync H2D + D2H of the same 84 B/sample at the same time on all '
+                                        '%d rank(s): the host-memory / PCIe path of the box' % world}}
     del xh, zh, lh
 
     # ---- config C5 as ONE job: inverse sampling + fused flow -> ECE/NLL/accuracy + all-reduce ---------
@@ -836,7 +856,7 @@ def run_ours(args):
             'unit': 'G samples/s', 'n_gpus': world,
             'fwd_bf16': g(world * n_head / (fwd_ms['bf16'] * 1e-3)) if 'bf16' in fwd_ms else None,
             'fwd_fp32': g(world * n_head / (fwd_ms['fp32'] * 1e-3)) if 'fp32' in fwd_ms else None,
-            'e2e_bf16': g(e2e_by.get('bf16')), 'e2e_fp32': g(e2e_by.get('fp32')),
+            'e2e_bf16': g(e2e_by.get('bf16')), 'e2e_fp32': g(e2e_by.get('fp32')), 'e2e_frac_of_pcie_ceiling': round(e2e_by[head_prec] / ceiling, 3),
             'train_bf16': g(tr_.get('bf16', {}).get('value')), 'train_fp32': g(tr_.get('fp32', {}).get('value')),
             'c5_job': g(legs.get('c5_job', {}).get(head_prec, {}).get('value')),
             'c5_ece': legs.get('c5_job', {}).get(head_prec, {}).get('ece'),
