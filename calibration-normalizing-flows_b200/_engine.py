@@ -272,7 +272,7 @@ class StackEngine:
         return out
 
     def apply_host(self, x_host, out_host=None, ld_host=None, inverse=False, precision='fp32',
-                   chunk=1 << 17, slots=4, repack=True, device=None):
+                   chunk=None, slots=4, repack=True, device=None):
         """Host buffers in, host buffers out: the samples stream through the GPU in chunks on
         `slots` CUDA streams so that the H2D copy, the flow kernel and the D2H copy of
         neighbouring chunks overlap.  x_host: CPU float32 [N,K] (pinned memory gives full PCIe
@@ -283,6 +283,10 @@ class StackEngine:
             raise RuntimeError('apply_host expects host memory')
         x_host = check_logits(x_host, self.K, 'x_host')
         N, K = x_host.shape
+        if chunk is None:
+            # rows per H2D -> kernel -> D2H stage: 2^17 keeps a 10^6-row call pipelined over 4 streams, 2^19 is the
+            # measured optimum once a call has >= 2^23 rows (1.00 vs 0.81 G samples/s at 10^7 rows on one B200)
+            chunk = min(1 << 19, max(1 << 17, N // 16))
         if out_host is None:
             out_host = torch.empty((N, K), dtype=torch.float32, pin_memory=True)
         if ld_host is None:

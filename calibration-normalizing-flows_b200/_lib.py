@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcnf_b200.so')
+LIB_PATH = os.environ.get('CNF_B200_LIB') or os.path.join(_HERE, 'libcnf_b200.so')     # (override: experiments only)
 
 CNF_MAX_HIDDEN = 4
 PREC_FP32, PREC_BF16_TC = 0, 1

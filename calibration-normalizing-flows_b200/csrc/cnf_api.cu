@@ -155,10 +155,6 @@ int pool_get(HostPool** out) {
 }
 }  // namespace
 
-// true when the fp32 path would run a kernel that reads its rows with plain loads straight from `x` (no shared-memory
-// staging of whole tiles), i.e. one that can run on device-mapped host memory without a slow-down of the other SMs
-bool cnf_fp32_streams_rows(const cnf_flow_desc* desc, const float* x, const float* z, int64_t N);
-
 extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed, const int32_t* tables,
                                    const float* x_host, float* z_host, float* logdet_host, int64_t N, int32_t inverse,
                                    void* workspace, int64_t workspace_bytes, int64_t chunk, void* stream) {
@@ -180,20 +176,19 @@ extern "C" int cnf_flow_apply_host(const cnf_flow_desc* desc, const void* packed
   // (cp.async, one tile ahead per slot, ~2 MB in flight) hides the PCIe latency and both
   // directions stream concurrently, without per-chunk DMA set-up costs: 1.18 ms vs 1.58 ms per
   // 10^6 K=10 samples on B200 (46 GB/s per direction when both are busy).
-  // The fp32 register-resident kernel (K = 10) reads and writes its rows straight from / to global memory as well
-  // and takes the same route.
   if (!cnf_switch(CNF_SW_NO_ZEROCOPY)) {
     cudaPointerAttributes ax, az, al;
     const bool ok = cudaPointerGetAttributes(&ax, x_host) == cudaSuccess && ax.type == cudaMemoryTypeHost &&
                     cudaPointerGetAttributes(&az, z_host) == cudaSuccess && az.type == cudaMemoryTypeHost &&
                     cudaPointerGetAttributes(&al, logdet_host) == cudaSuccess && al.type == cudaMemoryTypeHost;
     cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers
-    if (ok && desc->precision == CNF_PREC_BF16_TC)
+    // Measured on one B200 (round 2, 10^7 samples per call): the copy-engine pipeline below with 2^19-row chunks carries
+    // 1.00 G samples/s, the zero-copy launch 0.90; the fp32 register kernel on host pointers only 0.58 (its 8-byte row
+    // reads make small PCIe requests).  Zero-copy stays for the tensor-core kernel on calls of up to 2^21 rows, where
+    // the pipeline cannot fill (1.18 vs 1.58 ms per 10^6 rows).
+    if (ok && desc->precision == CNF_PREC_BF16_TC && N <= (1 << 21))
       return cnf_tc_apply(desc, packed, tables, (const float*)ax.devicePointer, (float*)az.devicePointer,
                           (float*)al.devicePointer, N, inverse, user);
-    if (ok && cnf_fp32_streams_rows(desc, (const float*)ax.devicePointer, (const float*)az.devicePointer, N))
-      return cnf_fp32_apply(desc, (const float*)packed, tables, (const float*)ax.devicePointer, (float*)az.devicePointer,
-                            (float*)al.devicePointer, nullptr, N, inverse, user);
   }
   HostPool* poolp = nullptr;
   if ((rc = pool_get(&poolp))) return rc;

@@ -2024,14 +2024,6 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
 
-bool cnf_fp32_streams_rows(const cnf_flow_desc* desc, const float* x, const float* z, int64_t N) {
-  CnfDims d;
-  size_t smem_r = 0;
-  const char* sw = cnf_switch(CNF_SW_FP32R);
-  if (cnf_make_dims(desc, &d) != CNF_OK || device_limits() != CNF_OK) return false;
-  return N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r);
-}
-
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
   CnfDims d;

@@ -43,7 +43,10 @@ int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables
 
 namespace {
 
-constexpr int TC_SLOTS = 3;                       // tiles in flight per CTA
+#ifndef CNF_TC_SLOTS
+#define CNF_TC_SLOTS 3
+#endif
+constexpr int TC_SLOTS = CNF_TC_SLOTS;             // tiles in flight per CTA
 constexpr int TC_THREADS = 128 + 128 * TC_SLOTS;  // warps 0..2 MMA issuers, warp 3 TMEM allocator, then one epilogue warpgroup per slot
 constexpr int SLOT_COLS = 160;                    // TMEM columns per slot: D1 (<=128) + D2 (16), padded
 

@@ -14,6 +14,7 @@ import cnf_b200  # noqa: E402,F401
 dev = torch.device('cuda:0')
 model = bench.make_model().to(dev)
 eng = model.engine()
+eng.ensure(dev)
 N = int(os.environ.get('N', 10_000_000))
 x, _ = bench.synth_dev(N, 1, dev)
 names = {'off': 'generic flow_apply_kernel', '0': '128 thr x 8 u2 (2/SM)', '1': '128 x 8 u1', '2': '128 x 8 u4', '3': '64 x 8 (3/SM)',
