@@ -13,10 +13,10 @@ from .flows.flows import (Flow, NvpCouplingLayer, CouplingStack, AffineConstantL
 from .flows.utils import MLP, TempScaler  # noqa: E402
 from .flows.nice_torch import NiceFlow  # noqa: E402
 from .flows.realNVP_torch import RealNvpFlow  # noqa: E402
-from .calibrators import Calibrator, TorchFlowCalibrator, FusedNLLTrainer  # noqa: E402
+from .calibrators import Calibrator, TorchFlowCalibrator, FusedNLLTrainer, HostStreamNLLTrainer  # noqa: E402
 from .utils.metrics import expected_calibration_error, neg_log_likelihood, accuracy  # noqa: E402
 from .utils.ops import onehot_encode  # noqa: E402
 
 __all__ = ['Flow', 'NvpCouplingLayer', 'CouplingStack', 'AffineConstantLayer', 'PlanarLayer', 'RadialLayer', 'TempScaler', 'MLP', 'NiceFlow', 'RealNvpFlow', 'Calibrator',
-           'TorchFlowCalibrator', 'FusedNLLTrainer', 'expected_calibration_error', 'neg_log_likelihood',
+           'TorchFlowCalibrator', 'FusedNLLTrainer', 'HostStreamNLLTrainer', 'expected_calibration_error', 'neg_log_likelihood',
            'accuracy', 'onehot_encode']

@@ -299,6 +299,142 @@ class FusedNLLTrainer:
         return acc
 
 
+class HostStreamNLLTrainer(FusedNLLTrainer):
+    """The same optimisation loop for samples that live in (pinned) HOST memory -- the on-disk logit sets of
+    utils/data.py (reference utils/data.py:170-210) loaded by ``cnf_b200.utils.data`` -- instead of HBM.
+
+    * ``resident=False`` (data larger than the HBM budget): every full-batch step streams the samples through two
+      device staging buffers of ``chunk_rows`` rows; the H2D copy of chunk c+1 (copy stream) overlaps the fused
+      forward+backward kernel of chunk c, per-chunk gradients are summed on the device (``inv_n_total`` makes the
+      sum the full-batch gradient), then one all-reduce / optimiser update as usual.
+    * ``resident=True`` (default when the shard fits): the FIRST step streams the chunks straight into their final
+      place in HBM and computes on each chunk as it lands, so the load is hidden behind the first epoch; later steps
+      run on the resident copy in one launch, exactly as ``FusedNLLTrainer``.
+    Full-batch only (the reference's default ``batch_size = N``, calibrators.py:263-265)."""
+
+    def __init__(self, engine, x_host, y_host, device, n_total=None, chunk_rows=1 << 22, resident=None, **kw):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        x_host = torch.as_tensor(x_host)
+        y_host = torch.as_tensor(y_host)
+        if x_host.is_cuda or y_host.is_cuda:
+            raise ValueError('cnf_b200: HostStreamNLLTrainer expects host tensors')
+        x_host = check_logits(x_host, engine.K, 'x_host', cast=True)
+        if y_host.dim() != 1 or y_host.shape[0] != x_host.shape[0] or y_host.dtype.is_floating_point:
+            raise ValueError('cnf_b200: y_host must be an integer tensor of shape [%d]' % x_host.shape[0])
+        y_host = y_host.to(torch.int64).contiguous()
+        if not x_host.is_pinned():
+            x_host = x_host.pin_memory()
+        if not y_host.is_pinned():
+            y_host = y_host.pin_memory()
+        self.x_host, self.y_host = x_host, y_host
+        n, K = x_host.shape
+        self.chunk_rows = max(1024, int(chunk_rows))
+        if resident is None:
+            free, _ = torch.cuda.mem_get_info(device)
+            resident = n * (4 * K + 8) < 0.6 * free
+        self.resident = bool(resident)
+        self._loaded = False
+        rows = n if self.resident else min(n, 2 * self.chunk_rows)
+        xbuf = torch.empty((rows, K), dtype=torch.float32, device=device)
+        ybuf = torch.empty(rows, dtype=torch.int64, device=device)
+        super().__init__(engine, xbuf, ybuf, n_total=n_total if n_total is not None else None, **kw)
+        self.n_local = n
+        if n_total is None:          # the base class counted the staging rows: count the real shard
+            t = torch.tensor([n], dtype=torch.int64, device=device)
+            if self.dist is not None:
+                self.dist.all_reduce(t)
+            self.n_total = int(t.item())
+        self._copy_stream = torch.cuda.Stream(device=device)
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self._freed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._grad_acc = None
+
+    def _chunks(self):
+        n = self.n_local
+        return [(lo, min(n, lo + self.chunk_rows)) for lo in range(0, n, self.chunk_rows)] or [(0, 0)]
+
+    def _streamed_pass(self, with_grad, acc):
+        """One pass over the host samples: H2D of the next chunk overlaps the kernel of the current one."""
+        e = self.engine
+        dev = self.x.device
+        cur = torch.cuda.current_stream(dev)
+        chunks = self._chunks()
+        if with_grad:
+            if self._grad_acc is None:
+                self._grad_acc = torch.zeros(e.n_flat, dtype=torch.float32, device=dev)
+            self._grad_acc.zero_()
+
+        def place(c):      # device rows that receive chunk c
+            lo, hi = chunks[c]
+            if self.resident:
+                return self.x[lo:hi], self.y[lo:hi]
+            base = (c % 2) * self.chunk_rows
+            return self.x[base:base + (hi - lo)], self.y[base:base + (hi - lo)]
+
+        def issue_copy(c):
+            lo, hi = chunks[c]
+            xd, yd = place(c)
+            with torch.cuda.stream(self._copy_stream):
+                if not self.resident and c >= 2:
+                    self._copy_stream.wait_event(self._freed[c % 2])     # the kernel that last read this staging half
+                xd.copy_(self.x_host[lo:hi], non_blocking=True)
+                yd.copy_(self.y_host[lo:hi], non_blocking=True)
+                self._copied[c % 2].record(self._copy_stream)
+
+        self._copy_stream.wait_stream(cur)
+        issue_copy(0)
+        for c in range(len(chunks)):
+            cur.wait_event(self._copied[c % 2])
+            if c + 1 < len(chunks):
+                issue_copy(c + 1)
+            xd, yd = place(c)
+            e.nll_step(xd, yd, acc, self.eps, self.gamma, self.n_total, with_grad=with_grad, precision=self.precision)
+            if with_grad:
+                self._grad_acc.add_(e.flat_grad)
+            self._freed[c % 2].record(cur)
+        if with_grad:
+            e.flat_grad.copy_(self._grad_acc)
+        if self.resident:
+            self._loaded = True
+
+    def step(self, xb=None, yb=None, n_batch_total=None):
+        if xb is not None or yb is not None:
+            raise NotImplementedError('HostStreamNLLTrainer is full-batch (mini-batches need the samples resident)')
+        if self.resident and self._loaded:
+            return super().step()
+        nvtx = torch.cuda.nvtx
+        self.loss_acc.zero_()
+        nvtx.range_push('cnf.fwd_bwd(streamed)')
+        self._streamed_pass(True, self.loss_acc)
+        nvtx.range_pop()
+        if self.dist is not None:
+            self._all_reduce_step(self.loss_acc)
+        self._optim_and_pack()
+
+    def step_graph(self):
+        raise RuntimeError('CUDA-graph steps need resident samples; use FusedNLLTrainer')
+
+    epoch_graph = step_graph
+
+    def evaluate(self, xb=None, yb=None, out=None):
+        if xb is not None or yb is not None:
+            raise NotImplementedError('HostStreamNLLTrainer evaluates the whole local shard')
+        if self.resident and self._loaded:
+            return super().evaluate(out=out)
+        acc = torch.zeros(4, dtype=torch.float64, device=self.x.device) if out is None else out.zero_()
+        self._streamed_pass(False, acc)
+        if self.dist is not None:
+            self.dist.all_reduce(acc)
+        return acc
+
+    def fit_loop(self, epochs, batch_size, perm_fn, cuda_graph=False):
+        if int(batch_size) < self.n_total:
+            raise NotImplementedError('HostStreamNLLTrainer trains full-batch (batch_size >= N)')
+        return super().fit_loop(epochs, batch_size, perm_fn, cuda_graph=False)
+
+
 class TorchFlowCalibrator(Calibrator):
 
     def __init__(self, Flow, logits, target, **kwargs):
@@ -324,6 +460,7 @@ class TorchFlowCalibrator(Calibrator):
         # 104 us per epoch including the capture; K=3, N=10,000: 59 vs 61 us), and the first capture in a
         # process costs seconds (profiles/microbench/c1_fit_speed.py, c2_fit_speed.py).
         self.cuda_graph = kwargs.get('cuda_graph', False)
+        self.host_stream = kwargs.get('host_stream', 'auto')
         self.CE = torch.nn.CrossEntropyLoss()
         self.optimizer = torch.optim.Adam(self.flow.parameters())
         self.history = self.fit(self.logits, self.target,
@@ -347,14 +484,25 @@ class TorchFlowCalibrator(Calibrator):
             rank, world = dist.get_rank(), dist.get_world_size()
             lo, hi = shard_bounds(n_all, rank, world)
             logits, target = logits[lo:hi], target[lo:hi]
-        x = logits.to(self.dev).contiguous()
-        y = target.to(self.dev).contiguous()
         self.flow.to(self.dev)
         eng = self._engine()
         group = self.optimizer.param_groups[0]
-        trainer = FusedNLLTrainer(eng, x, y, n_total=n_all, eps=1e-7, gamma=1.0, lr=group['lr'],
-                                  betas=group['betas'], adam_eps=group['eps'], weight_decay=group['weight_decay'],
-                                  precision=getattr(self, 'precision', 'fp32'))
+        opt = dict(n_total=n_all, eps=1e-7, gamma=1.0, lr=group['lr'], betas=group['betas'], adam_eps=group['eps'],
+                   weight_decay=group['weight_decay'], precision=getattr(self, 'precision', 'fp32'))
+        # extension: host_stream=True keeps the samples in pinned host memory and streams them through the GPU
+        # (first epoch overlapped with the load when they fit HBM, every epoch when they do not); 'auto' switches to
+        # it when the local shard would not fit comfortably.  Full-batch only.
+        hs = getattr(self, 'host_stream', 'auto')
+        n_loc = logits.shape[0]
+        if hs == 'auto':
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            hs = int(batch_size) >= n_all and n_loc * (4 * self.n_classes + 8) > 0.5 * free
+        if hs:
+            trainer = HostStreamNLLTrainer(eng, logits, target, self.dev, **opt)
+        else:
+            x = logits.to(self.dev).contiguous()
+            y = target.to(self.dev).contiguous()
+            trainer = FusedNLLTrainer(eng, x, y, **opt)
         self.trainer = trainer
         gen = torch.Generator(device=self.dev)
         gen.manual_seed(int(torch.initial_seed()) & 0x7fffffff)

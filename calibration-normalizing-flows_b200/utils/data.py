@@ -21,7 +21,7 @@ def _pinned(arr, dtype):
     """numpy array (possibly memory-mapped) -> pinned torch tensor of `dtype`, one copy."""
     arr = np.asarray(arr)
     out = torch.empty(arr.shape, dtype=dtype, pin_memory=torch.cuda.is_available())
-    out.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+    out.copy_(torch.from_numpy(np.array(arr, copy=True)))      # (a memory-mapped array is read-only: copy, then wrap)
     return out
 
 

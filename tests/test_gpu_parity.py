@@ -175,7 +175,13 @@ def test_fused_adam_and_sgd_vs_torch_optim(name, cuda_device):
     assert np.allclose(losses, g['adam3_losses'], rtol=1e-4, atol=1e-5)
     flat = flow.engine().flat.cpu().numpy()
     disp, disp_ref = flat - g['flat'], g['adam3_flat'] - g['flat']
-    assert np.max(np.abs(disp - disp_ref)) < 0.05 * np.max(np.abs(disp_ref))
+    # Adam normalises every entry to ~lr per step, so an entry whose gradient is rounding noise can land +-lr either
+    # way: all entries within 5 % of the largest displacement, and the entries with a gradient well above the noise
+    # (> 1e-3 of the largest) -- where the update is a smooth function of the gradient -- within 5e-3 of it
+    scale = np.max(np.abs(disp_ref))
+    assert np.max(np.abs(disp - disp_ref)) < 0.05 * scale
+    solid = np.abs(g['grad_cal']) > 1e-3 * np.max(np.abs(g['grad_cal']))
+    assert solid.any() and np.max(np.abs(disp - disp_ref)[solid]) < 5e-3 * scale, np.max(np.abs(disp - disp_ref)[solid]) / scale
     assert np.all(disp[g['grad_cal'] == 0] == 0)
     # the nn.Parameters alias the flat buffer: state_dict sees the update
     p0 = flow.layers[0].canonical_parameters()[0]
@@ -268,6 +274,70 @@ def test_calibrator_drop_in_vs_reference(name, cuda_device):
     # mini-batch mode runs and keeps finite history
     cal2 = cnf_b200.TorchFlowCalibrator(Factory, g['x'], g['y'], epochs=2, batch_size=64, dev=cuda_device)
     assert np.isfinite([float(v) for v in cal2.history['loss']]).all()
+
+
+def test_calibrator_minibatch_fit_vs_oracle_with_pinned_permutation(cuda_device):
+    """The mini-batch branch of TorchFlowCalibrator.fit (calibrators.py:274-317: shuffled batches, one Adam step per
+    batch, history from the LAST evaluation batch only) against the float64 oracle driven with the same batch
+    order (the shuffle is pinned through the _epoch_permutation hook)."""
+    import torch
+    import cnf_b200
+    g = load_golden('calibrator_cal_nvp_k10')
+    K, hidden, layers = int(g['K']), [int(h) for h in g['hidden']], int(g['layers'])
+    N, bs, epochs = g['x'].shape[0], 64, 3
+    perms = [np.random.default_rng(40 + i).permutation(N) for i in range(2 * epochs)]
+
+    class Factory(cnf_b200.CouplingStack):
+        def __init__(self, dim, **kw):
+            super().__init__(dim, layers=layers, hidden_size=hidden, scale=bool(g['scale']), **{
+                k: v for k, v in kw.items() if k not in ('layers', 'hidden_size', 'scale')})
+            flat = torch.from_numpy(g['flat0'].astype(np.float32))
+            off = 0
+            with torch.no_grad():
+                for lay in self.layers:
+                    for p in lay.canonical_parameters():
+                        p.copy_(flat[off:off + p.numel()].view(p.shape))
+                        off += p.numel()
+
+    class Pinned(cnf_b200.TorchFlowCalibrator):
+        calls = 0
+
+        def _epoch_permutation(self, n_local, gen):
+            p = perms[Pinned.calls]
+            Pinned.calls += 1
+            return torch.from_numpy(p).to(self.dev)
+
+    cal = Pinned(Factory, g['x'], g['y'], epochs=epochs, batch_size=bs, dev=cuda_device)
+    assert Pinned.calls == 2 * epochs
+    hist = {k: np.array([float(v) for v in cal.history[k]]) for k in ('loss', 'ce', 'log_det')}
+    # oracle: same centring, same batches, Adam with torch defaults
+    x = orc.center(g['x']).astype(np.float64)
+    y = np.argmax(orc.onehot_encode(g['y']), axis=1) if g['y'].ndim == 1 else np.argmax(g['y'], axis=1)
+    like = orc.init_params(K, layers, hidden, bool(g['scale']), True)
+    flat = g['flat0'].astype(np.float64)
+    m, v, t = np.zeros_like(flat), np.zeros_like(flat), 0
+    ref = {'loss': [], 'ce': [], 'log_det': []}
+    for e in range(epochs):
+        p = perms[2 * e]
+        for s in range(0, N, bs):
+            idx = p[s:s + bs]
+            _, _, _, grads, _ = orc.train_step_grads(orc.unflatten(flat, like), x[idx], y[idx])
+            t += 1
+            flat, m, v = orc.adam_step(flat, orc.flatten(grads), m, v, t)
+        p = perms[2 * e + 1]
+        idx = p[(N - 1) // bs * bs:]
+        zs, ld = orc.flow_forward(orc.unflatten(flat, like), x[idx])
+        loss, ce, ldm, _, _ = orc.nll_head(zs[-1], ld, y[idx])
+        # reference quirk: the last batch's mean times its length over N (calibrators.py:309-317)
+        ref['loss'].append(loss * len(idx) / N)
+        ref['ce'].append(ce * len(idx) / N)
+        ref['log_det'].append(ldm * len(idx) / N)
+    for k in ref:
+        assert np.allclose(hist[k], np.array(ref[k]), rtol=2e-4, atol=1e-6), (k, hist[k], ref[k])
+    got = np.concatenate([p.detach().cpu().numpy().reshape(-1) for lay in cal.flow.layers for p in lay.canonical_parameters()])
+    disp = flat - g['flat0']
+    big = np.abs(disp) > 0.1 * np.max(np.abs(disp))
+    assert rel_err((got - g['flat0'])[big], disp[big]) < 2e-2
 
 
 def test_full_size_properties_c2(cuda_device):
