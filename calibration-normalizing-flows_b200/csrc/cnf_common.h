@@ -7,7 +7,8 @@
 #include "../../include/cnf.h"
 
 #define CNF_CH 16          // hidden-unit chunk held in registers by the fp32 kernels
-#define CNF_GRAD_ROWS 296  // 2 x 148 SMs: rows of the gradient partial buffer
+#define CNF_GRAD_ROWS 296      // 2 x 148 SMs: rows of the gradient partial buffer the per-CTA kernels use
+#define CNF_GRAD_ROWS_MAX 1184 // rows allocated: the register-resident training kernel owns one row per WARP (4 x 296)
 #define CNF_GRAD_BUDGET_FLOATS (64ll << 20)
 
 // Everything the kernels need to know about the model, derived from cnf_flow_desc.
@@ -24,7 +25,8 @@ struct CnfDims {
   int net_stride, layer_stride, n_packed;
   int tab_pi, tab_cond, tab_trans, n_tables;  // offsets inside the int32 tables
   int n_flat;
-  int grad_rows;
+  int grad_rows;       // rows used by kernels whose CTAs own a row each (<= CNF_GRAD_ROWS)
+  int grad_rows_max;   // rows of the partial buffer (plan info n_grad_rows; <= CNF_GRAD_ROWS_MAX, budget-limited)
 };
 
 #ifndef __CUDACC__
@@ -67,7 +69,7 @@ static inline int cnf_kernel_smem(Kern k, size_t bytes) { return cnf_func_smem(r
 enum CnfSwitch {
   CNF_SW_NO_ZEROCOPY, CNF_SW_DEEP_APPLY, CNF_SW_DEEP_TRAIN, CNF_SW_FORCE_LEAN, CNF_SW_FP32R, CNF_SW_FP32_NO_WL,
   CNF_SW_FP32_NT, CNF_SW_FP32_WS, CNF_SW_NO_LEAN_TRAIN, CNF_SW_SPLIT_GENERIC, CNF_SW_SPLIT_SEQ, CNF_SW_SPLIT_TRAIN,
-  CNF_SW_TC_EPI, CNF_SW_TC_GENERIC, CNF_SW_METRICS_STAGES, CNF_SW_COUNT
+  CNF_SW_TC_EPI, CNF_SW_TC_GENERIC, CNF_SW_METRICS_STAGES, CNF_SW_FP32R_TRAIN, CNF_SW_COUNT
 };
 const char* cnf_switch(CnfSwitch s);   // value of the switch or nullptr
 int cnf_make_dims(const cnf_flow_desc* desc, CnfDims* out);

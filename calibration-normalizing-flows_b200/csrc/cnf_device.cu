@@ -22,7 +22,7 @@ std::mutex g_mu;
 const char* const kSwitchNames[CNF_SW_COUNT] = {
     "CNF_NO_ZEROCOPY", "CNF_DEEP_APPLY", "CNF_DEEP_TRAIN", "CNF_FORCE_LEAN", "CNF_FP32R", "CNF_FP32_NO_WL",
     "CNF_FP32_NT", "CNF_FP32_WS", "CNF_NO_LEAN_TRAIN", "CNF_SPLIT_GENERIC", "CNF_SPLIT_SEQ", "CNF_SPLIT_TRAIN",
-    "CNF_TC_EPI", "CNF_TC_GENERIC", "CNF_METRICS_STAGES"};
+    "CNF_TC_EPI", "CNF_TC_GENERIC", "CNF_METRICS_STAGES", "CNF_FP32R_TRAIN"};
 struct Switches {
   bool live;
   const char* v[CNF_SW_COUNT];

@@ -2023,6 +2023,9 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
                          int max_smem, size_t* smem_out);
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
+int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
+                    float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
+                    int sms, int variant, int64_t* rows_out, cudaStream_t st);
 
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
@@ -2162,8 +2165,8 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // (HOST out) only those rows are zeroed and reported, so that small batches do not pay for clearing and
   // reducing all grad_rows rows; without it every row is cleared (cnf_grad_reduce reads them all).
   auto clear_rows = [&](int64_t grid) -> int {
-    int64_t rows = d.grad_rows;
-    if (rows_used) { rows = grid < d.grad_rows ? grid : d.grad_rows; *rows_used = rows; }
+    int64_t rows = d.grad_rows_max;
+    if (rows_used) { rows = grid < d.grad_rows_max ? grid : d.grad_rows_max; *rows_used = rows; }
     if (partials && rows > 0) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)rows * d.n_packed * sizeof(float), st));
     return CNF_OK;
   };
@@ -2173,6 +2176,15 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if ((rc = device_limits())) return rc;
   if (N == 0) return clear_rows(0);
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
+  // K = 10, one hidden layer, both nets, NLL head, a batch that fills the GPU: the register-resident kernel
+  // (CNF_FP32R_TRAIN: "off" disables, a digit picks the variant -- experiments)
+  if (head == CNF_HEAD_NLL && N >= 65536) {
+    const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
+    size_t smem_r = 0;
+    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r))
+      return cnf_fp32r_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_r, g_num_sms,
+                             sw ? atoi(sw) : 0, rows_used, st);
+  }
   // single-hidden-layer nets up to 256 hidden units: 32-sample tiles with the hidden layer split over the warps
   // (faster than one thread per sample at every batch size measured, 3x at N <= 10,000)
   {

@@ -221,6 +221,292 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
   if (TAIL) stats_finish_block(a_nll, a_correct, a_n, cache, tsm.s_cnt, tsm.s_cor, tsm.s_conf, ta.bins, ta.acc, tail_red, tid, R_NT);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Training: the fused NLL step (forward, loss head, backward, weight gradients) of calibrators.py:287-293 with the
+// same register-resident scheme, for batches that fill the GPU.  No tape and no barrier: after the forward pass
+// and the loss head a thread walks the layers backwards; a layer's input is recovered from its output by the
+// inverse (x = (y - t) e^-s with s, t recomputed from the unchanged conditioning half -- the recompute the
+// backward pass needs anyway), then a second walk over the hidden units forms, per unit,
+//   a = b1 + W1.c, r = relu(a), gh = [a > 0] W2^T g_out,  g_c += W1^T gh            (15 FMAs per sample)
+//   dW2[:, h] += r g_out,  dW1[h, :] += gh c,  db1[h] += gh                          (11 FMAs per sample)
+// summed first over the thread's SPT samples in registers, then over the warp's 32 lanes by a transposing
+// butterfly (16 values -> 16 shuffles), and added by red.global into the WARP's own row of the partial buffer
+// (rows are private to a warp and tiles follow each other on it: the sums are order-deterministic).
+// ---------------------------------------------------------------------------------------------------------
+
+// v[0..16) hold one value per index on every lane; on return v[0] of lane L is the warp-wide sum of value
+// reduce16_index(L).  8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5.
+__device__ __forceinline__ int reduce16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < w) {
+        const float send = up ? v[i] : v[i + w];
+        const float keep = up ? v[i + w] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Backward of one conditioner net for this thread's SPT samples (c: conditioning values, go: gradient on the net's
+// five outputs).  Adds W1^T gh into gc and the weight gradients into the warp's partial row Gn (packed layout of one
+// net; goff = this lane's entry offset for reduce16_index(lane), -1 for none, see train kernel).
+template <int SPT, int U>
+__device__ __forceinline__ void net_backward(const float4* __restrict__ w, int Hp, const float (&c)[SPT][RD],
+                                             const float (&go)[SPT][RD], float (&gc)[SPT][RD], float* __restrict__ Gn,
+                                             int goff, int lane) {
+#pragma unroll U
+  for (int h = 0; h < Hp; ++h) {
+    const float4 v0 = w[3 * h], v1 = w[3 * h + 1], v2 = w[3 * h + 2];
+    float wg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wg[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      float a = fmaf(v0.x, c[k][0], v1.y);
+      a = fmaf(v0.y, c[k][1], a);
+      a = fmaf(v0.z, c[k][2], a);
+      a = fmaf(v0.w, c[k][3], a);
+      a = fmaf(v1.x, c[k][4], a);
+      const float r = fmaxf(a, 0.f);
+      float gh = v1.z * go[k][0];
+      gh = fmaf(v1.w, go[k][1], gh);
+      gh = fmaf(v2.x, go[k][2], gh);
+      gh = fmaf(v2.y, go[k][3], gh);
+      gh = fmaf(v2.z, go[k][4], gh);
+      gh = a > 0.f ? gh : 0.f;
+      gc[k][0] = fmaf(v0.x, gh, gc[k][0]);
+      gc[k][1] = fmaf(v0.y, gh, gc[k][1]);
+      gc[k][2] = fmaf(v0.z, gh, gc[k][2]);
+      gc[k][3] = fmaf(v0.w, gh, gc[k][3]);
+      gc[k][4] = fmaf(v1.x, gh, gc[k][4]);
+#pragma unroll
+      for (int e = 0; e < RD; ++e) {
+        wg[e] = fmaf(r, go[k][e], wg[e]);           // dW2[slot e][h]
+        wg[RD + e] = fmaf(gh, c[k][e], wg[RD + e]); // dW1[h][slot e]
+      }
+      wg[10] += gh;                                 // db1[h]
+    }
+    const float tot = warp_reduce16(wg, lane);
+    if (goff >= 0) atomicAdd(Gn + goff + h, tot);
+  }
+}
+
+template <int R_NT, int SPT, int U, int MINB>
+__global__ void __launch_bounds__(R_NT, MINB)
+train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
+                   const float* __restrict__ xin, const int64_t* __restrict__ labels, float* __restrict__ partials,
+                   double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double red[4][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Hp = d.Hp[0], L = d.L;
+  float4* ws = reinterpret_cast<float4*>(smem);
+  float* b2s = reinterpret_cast<float*>(ws + (size_t)L * 2 * Hp * 3);
+  int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: [5] packed input index of slot e, [5] packed output index
+  const bool do_bwd = partials != nullptr;
+  // ---- stage the weights exactly as flow_reg10_kernel does; plus the slot -> packed-index maps ------------------
+  {
+    float* wf = reinterpret_cast<float*>(ws);
+    const int per_layer = 2 * Hp * 12;
+    for (int i = tid; i < L * per_layer; i += R_NT) {
+      const int l = i / per_layer, r = i - l * per_layer;
+      const int net = r / (Hp * 12), rr = r - net * (Hp * 12);
+      const int h = rr / 12, e = rr - h * 12;
+      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
+      const int* cond = tables + d.tab_cond + l * RD;
+      const int* trans = tables + d.tab_trans + l * RD;
+      const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;
+      float v = 0.f;
+      if (e < 5) {
+        for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = Wn[d.w_off[0] + j * Hp + h];
+      } else if (e == 5) {
+        v = Wn[d.b_off[0] + h];
+      } else if (e < 11) {
+        for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 6) v = Wn[d.w_off[1] + q * Hp + h];
+      }
+      wf[i] = v;
+    }
+    for (int i = tid; i < L * 16; i += R_NT) {
+      const int l = i >> 4, net = (i >> 3) & 1, e = i & 7;
+      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
+      const int* trans = tables + d.tab_trans + l * RD;
+      const int tbase = (l & 1) ? RD : 0;
+      float v = 0.f;
+      for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e) v = Wn[d.b_off[1] + q];
+      b2s[i] = v;
+    }
+    for (int i = tid; i < L * 10; i += R_NT) {
+      const int l = i / 10, e = i - l * 10;
+      const int* cond = tables + d.tab_cond + l * RD;
+      const int* trans = tables + d.tab_trans + l * RD;
+      const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;
+      int v = 0;
+      if (e < 5) { for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = j; }
+      else       { for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 5) v = q; }
+      maps[i] = v;
+    }
+  }
+  __syncthreads();
+
+  const int TS = R_NT * SPT;
+  const int64_t ntiles = (N + TS - 1) / TS;
+  const bool rev_io = (L & 1) != 0;
+  const int vidx = reduce16_index(lane);                  // which of the 16 reduced values this lane ends up holding
+  const bool writer = (lane & 1) == 0;
+  float* Grow = do_bwd ? partials + ((size_t)blockIdx.x * (R_NT / 32) + warp) * d.n_packed : nullptr;
+  double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TS;
+    float lo[SPT][RD], hi[SPT][RD], ld[SPT];
+    bool valid[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int64_t n = base + tid + k * R_NT;
+      valid[k] = n < N;
+      float v[RK];
+      if (valid[k]) {
+        const float2* p = reinterpret_cast<const float2*>(xin + n * RK);
+#pragma unroll
+        for (int j = 0; j < RD; ++j) { const float2 t2 = __ldg(p + j); v[2 * j] = t2.x; v[2 * j + 1] = t2.y; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < RK; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < RD; ++j) { lo[k][j] = v[j]; hi[k][j] = v[RD + j]; }
+      ld[k] = 0.f;
+    }
+    // ---- forward ------------------------------------------------------------------------------------------------
+    for (int l = 0; l < L; ++l) {
+      const float4* w = ws + (size_t)l * 2 * Hp * 3;
+      const float* b2 = b2s + l * 16;
+      if (l & 1) layer_eval<SPT, U>(w, b2, Hp, 0, lo, hi, ld);
+      else       layer_eval<SPT, U>(w, b2, Hp, 0, hi, lo, ld);
+    }
+    // ---- loss head (calibrators.py:288-291; eps == 0: CrossEntropyLoss, run_experiment3D.py:107) ------------------
+    float glo[SPT][RD], ghi[SPT][RD];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int64_t n = base + tid + k * R_NT;
+      float zv[RK];     // logical order: z[j] = a[pi_L(j)]
+#pragma unroll
+      for (int j = 0; j < RD; ++j) {
+        zv[j] = rev_io ? hi[k][RD - 1 - j] : lo[k][j];
+        zv[RD + j] = rev_io ? lo[k][RD - 1 - j] : hi[k][j];
+      }
+      int yy = valid[k] ? (int)labels[n] : 0;
+      yy = min(max(yy, 0), RK - 1);
+      float mx = zv[0];
+#pragma unroll
+      for (int j = 1; j < RK; ++j) mx = fmaxf(mx, zv[j]);
+      float se = 0.f, zy = 0.f;
+      float pj[RK];
+#pragma unroll
+      for (int j = 0; j < RK; ++j) { pj[j] = expf(zv[j] - mx); se += pj[j]; zy = (j == yy) ? zv[j] : zy; }
+      const float inv_se = 1.f / se;
+      const float py = expf(zy - mx) * inv_se;
+      float ce, coef;
+      if (eps == 0.f) { ce = (zy - mx) - logf(se); coef = 1.f; }
+      else            { ce = logf(py + eps); coef = py / (py + eps); }
+      if (valid[k]) {
+        const float tot = ce + gamma * ld[k];
+        a_loss += (double)tot; a_ce += (double)ce; a_ld += (double)ld[k];
+        if (!isfinite(tot)) a_bad += 1.0;
+      }
+      const float sc = valid[k] ? -inv_n * coef : 0.f;
+      float gz[RK];
+#pragma unroll
+      for (int j = 0; j < RK; ++j) gz[j] = sc * ((j == yy ? 1.f : 0.f) - pj[j] * inv_se);
+#pragma unroll
+      for (int j = 0; j < RD; ++j) {          // back to physical slots
+        glo[k][j] = rev_io ? gz[RK - 1 - j] : gz[j];
+        ghi[k][j] = rev_io ? gz[RD - 1 - j] : gz[RD + j];
+      }
+    }
+    if (!do_bwd) continue;
+    // ---- backward -------------------------------------------------------------------------------------------------
+    for (int l = L - 1; l >= 0; --l) {
+      const float4* w = ws + (size_t)l * 2 * Hp * 3;
+      const float* b2 = b2s + l * 16;
+      const int* mp = maps + l * 10;
+      float* Gl = Grow + (size_t)l * d.layer_stride;
+      // this lane's entry in a net's packed gradient block for the value it holds after the butterfly:
+      // values 0..4 = dW2 of output slot e, 5..9 = dW1 of input slot e, 10 = db1
+      int goff = -1;
+      if (writer) {
+        if (vidx < 5) goff = d.w_off[1] + mp[5 + vidx] * Hp;
+        else if (vidx < 10) goff = d.w_off[0] + mp[vidx - 5] * Hp;
+        else if (vidx == 10) goff = d.b_off[0];
+      }
+      const int boff = (writer && vidx < 5) ? d.b_off[1] + mp[5 + vidx] : -1;      // db2 of output slot vidx
+      auto run = [&](float (&c)[SPT][RD], float (&t)[SPT][RD], float (&gcnd)[SPT][RD], float (&gt)[SPT][RD]) {
+        // recompute s and shift from the conditioning half; step the transformed half back to the layer input
+        float o[SPT][RD], gs[SPT][RD];
+        net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);                  // shift
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+          for (int q = 0; q < RD; ++q) t[k][q] -= o[k][q];              // y - shift  (= x e^s)
+        net_eval<SPT, U>(w, b2, Hp, c, o);                               // s
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+          for (int q = 0; q < RD; ++q) {
+            const float gy = gt[k][q];
+            gs[k][q] = fmaf(gy, t[k][q], valid[k] ? -gamma * inv_n : 0.f);   // g_s = g_y x e^s + g_ld
+            t[k][q] *= expf(-o[k][q]);                                   // x
+            o[k][q] = gy * expf(o[k][q]);                                // g_x of the transformed half
+          }
+        // shift net first (its output gradient is g_y itself), then the scale net
+        {
+          float wb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wb[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < SPT; ++k)
+#pragma unroll
+            for (int q = 0; q < RD; ++q) { wb[q] += gt[k][q]; wb[8 + q] += gs[k][q]; }
+          // values 0..4: db2 of the shift net, 8..12: db2 of the scale net
+          const float tot = warp_reduce16(wb, lane);
+          if (writer && vidx < 5) atomicAdd(Gl + d.net_stride + d.b_off[1] + mp[5 + vidx], tot);
+          if (writer && vidx >= 8 && vidx < 13) atomicAdd(Gl + d.b_off[1] + mp[5 + vidx - 8], tot);
+        }
+        net_backward<SPT, U>(w + 3 * Hp, Hp, c, gt, gcnd, Gl + d.net_stride, goff, lane);
+        net_backward<SPT, U>(w, Hp, c, gs, gcnd, Gl, goff, lane);
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+          for (int q = 0; q < RD; ++q) gt[k][q] = o[k][q];
+      };
+      (void)boff;
+      if (l & 1) run(lo, hi, glo, ghi);
+      else       run(hi, lo, ghi, glo);
+    }
+  }
+  // ---- loss sums: lanes -> warp -> CTA -> global (float64) ---------------------------------------------------------
+  if (loss_acc != nullptr) {
+    double v4[4] = {a_loss, a_ce, a_ld, a_bad};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v4[q] += __shfl_xor_sync(0xffffffffu, v4[q], o);
+      if (lane == 0) red[q][warp] = v4[q];
+    }
+    __syncthreads();
+    if (tid < 4) {
+      double s = 0.0;
+      for (int w = 0; w < R_NT / 32; ++w) s += red[tid][w];
+      atomicAdd(loss_acc + tid, s);
+    }
+  }
+}
+
 template <int R_NT, int SPT, int U, int MINB, int TAIL>
 int launch_reg10(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                  int64_t N, int inverse, const CnfTail& ta, size_t smem, int sms, cudaStream_t st) {
@@ -268,4 +554,38 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
   }
   if (ta.mode == CNF_METRICS_LOGITS) return launch_reg10<128, 8, 2, 2, CNF_METRICS_LOGITS>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
   return launch_reg10<128, 8, 2, 2, CNF_METRICS_CALIBRATED>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
+}
+
+// Fused NLL training step on the register-resident kernel; rows_used = partial rows written (one per warp).
+int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
+                    float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
+                    int sms, int variant, int64_t* rows_out, cudaStream_t st) {
+  const size_t smem = smem_fwd + (size_t)d.L * 10 * sizeof(int);
+#define TV(NT, SPT, U, MB)                                                                                           \
+  do {                                                                                                               \
+    int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, U, MB>, smem);                                              \
+    if (rc) return rc;                                                                                               \
+    int per_sm = 0;                                                                                                  \
+    CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_reg10_kernel<NT, SPT, U, MB>, NT, smem)); \
+    if (per_sm < 1) per_sm = 1;                                                                                      \
+    const int64_t ntiles = (N + NT * SPT - 1) / (NT * SPT);                                                          \
+    int64_t cap = (int64_t)sms * per_sm;                                                                             \
+    if (partials && cap > d.grad_rows_max / (NT / 32)) cap = d.grad_rows_max / (NT / 32);                            \
+    if (cap < 1) { cnf_set_error("partial buffer too small for the register-resident training kernel"); return CNF_E_SMEM; } \
+    const int grid = (int)(ntiles < cap ? ntiles : cap);                                                             \
+    const int64_t rows = (int64_t)grid * (NT / 32);                                                                  \
+    if (rows_out) *rows_out = rows;                                                                                  \
+    if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)(rows_out ? rows : d.grad_rows_max) * d.n_packed * sizeof(float), st)); \
+    train_reg10_kernel<NT, SPT, U, MB><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n); \
+    CNF_CHECK_CUDA(cudaGetLastError());                                                                              \
+    return CNF_OK;                                                                                                   \
+  } while (0)
+  switch (variant) {
+    case 1: TV(128, 2, 2, 2);
+    case 2: TV(128, 3, 2, 2);
+    case 3: TV(128, 4, 1, 2);
+    case 4: TV(256, 4, 2, 1);
+    default: TV(128, 4, 2, 2);
+  }
+#undef TV
 }

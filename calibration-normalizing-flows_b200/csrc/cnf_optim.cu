@@ -147,7 +147,7 @@ extern "C" int cnf_grad_reduce(const cnf_flow_desc* desc, const float* grad_part
   if (!grad_partials || !gather || !flat_grad) { cnf_set_error("cnf_grad_reduce: null pointer"); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
-  grad_reduce_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, d.grad_rows);
+  grad_reduce_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, d.grad_rows_max);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -158,7 +158,7 @@ extern "C" int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad
   int rc = cnf_make_dims(desc, &d);
   if (rc) return rc;
   if (!grad_partials || !gather || !flat_grad) { cnf_set_error("cnf_grad_reduce_rows: null pointer"); return CNF_E_ARG; }
-  if (rows_used < 0 || rows_used > d.grad_rows) { cnf_set_error("cnf_grad_reduce_rows: rows_used %lld out of range", (long long)rows_used); return CNF_E_ARG; }
+  if (rows_used < 0 || rows_used > d.grad_rows_max) { cnf_set_error("cnf_grad_reduce_rows: rows_used %lld out of range", (long long)rows_used); return CNF_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
   if (rows_used == 0) return CNF_OK;

@@ -83,12 +83,13 @@ int cnf_make_dims(const cnf_flow_desc* desc, CnfDims* d) {
     per_net += (long long)d->K * prev + d->K;
   }
   d->n_flat = (int)(per_net * d->n_nets * d->L);
-  long long rows = CNF_GRAD_ROWS;
+  long long rows = CNF_GRAD_ROWS_MAX;
   if (d->n_packed > 0 && rows * d->n_packed > CNF_GRAD_BUDGET_FLOATS) {
     rows = CNF_GRAD_BUDGET_FLOATS / d->n_packed;
     if (rows < 1) rows = 1;
   }
-  d->grad_rows = (int)rows;
+  d->grad_rows_max = (int)rows;
+  d->grad_rows = (int)(rows < CNF_GRAD_ROWS ? rows : CNF_GRAD_ROWS);
   return CNF_OK;
 }
 
@@ -101,7 +102,7 @@ extern "C" int cnf_plan_info_get(const cnf_flow_desc* desc, cnf_plan_info* out) 
   out->n_flat = d.n_flat;
   out->n_packed = d.n_packed;
   out->n_tables = d.n_tables;
-  out->n_grad_rows = d.grad_rows;
+  out->n_grad_rows = d.grad_rows_max;
   out->tc_bytes = 0;
   out->d0 = d.d0; out->d1 = d.d1;
   for (int j = 0; j < d.m; ++j) out->hidden_padded[j] = d.Hp[j];
