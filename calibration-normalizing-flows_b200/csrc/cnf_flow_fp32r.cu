@@ -309,6 +309,7 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   float4* ws = reinterpret_cast<float4*>(smem);
   float* b2s = reinterpret_cast<float*>(ws + (size_t)L * 2 * Hp * 3);
   int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: [5] packed input index of slot e, [5] packed output index
+  float* park = reinterpret_cast<float*>(maps + ((L * 10 + 3) / 4) * 4);   // [3][SPT][5][R_NT] per-thread parking slots
   const bool do_bwd = partials != nullptr;
   // ---- stage the weights exactly as flow_reg10_kernel does; plus the slot -> packed-index maps ------------------
   {
@@ -445,15 +446,36 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
         else if (vidx == 10) goff = d.b_off[0];
       }
       const int boff = (writer && vidx < 5) ? d.b_off[1] + mp[5 + vidx] : -1;      // db2 of output slot vidx
+      // Register pressure: of the four [SPT][5] blocks of a layer (conditioning values c, transformed values t and the
+      // gradients on both) only two or three are used inside each hidden-unit loop; the others wait in a per-thread
+      // shared-memory slot (park[slot][value][tid]: conflict-free), which is what lets SPT reach 8.
+      auto park_put = [&](int slot, const float (&a)[SPT][RD]) {
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+          for (int q = 0; q < RD; ++q) park[((slot * SPT + k) * RD + q) * R_NT + tid] = a[k][q];
+      };
+      auto park_get = [&](int slot, float (&a)[SPT][RD]) {
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+          for (int q = 0; q < RD; ++q) a[k][q] = park[((slot * SPT + k) * RD + q) * R_NT + tid];
+      };
       auto run = [&](float (&c)[SPT][RD], float (&t)[SPT][RD], float (&gcnd)[SPT][RD], float (&gt)[SPT][RD]) {
         // recompute s and shift from the conditioning half; step the transformed half back to the layer input
-        float o[SPT][RD], gs[SPT][RD];
+        float o[SPT][RD];
+        park_put(0, gcnd);
+        park_put(1, gt);
         net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);                  // shift
 #pragma unroll
         for (int k = 0; k < SPT; ++k)
 #pragma unroll
           for (int q = 0; q < RD; ++q) t[k][q] -= o[k][q];              // y - shift  (= x e^s)
+        park_put(2, t);
         net_eval<SPT, U>(w, b2, Hp, c, o);                               // s
+        park_get(2, t);
+        park_get(1, gt);
+        float gs[SPT][RD];
 #pragma unroll
         for (int k = 0; k < SPT; ++k)
 #pragma unroll
@@ -463,7 +485,6 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
             t[k][q] *= expf(-o[k][q]);                                   // x
             o[k][q] = gy * expf(o[k][q]);                                // g_x of the transformed half
           }
-        // shift net first (its output gradient is g_y itself), then the scale net
         {
           float wb[16];
 #pragma unroll
@@ -477,12 +498,16 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
           if (writer && vidx < 5) atomicAdd(Gl + d.net_stride + d.b_off[1] + mp[5 + vidx], tot);
           if (writer && vidx >= 8 && vidx < 13) atomicAdd(Gl + d.b_off[1] + mp[5 + vidx - 8], tot);
         }
+        park_put(1, t);          // x: final for this layer
+        park_put(2, o);          // g_x of the transformed half: becomes gt below
+        park_get(0, gcnd);
+        park_put(0, gs);
+        // shift net first (its output gradient is g_y itself), then the scale net
         net_backward<SPT, U>(w + 3 * Hp, Hp, c, gt, gcnd, Gl + d.net_stride, goff, lane);
-        net_backward<SPT, U>(w, Hp, c, gs, gcnd, Gl, goff, lane);
-#pragma unroll
-        for (int k = 0; k < SPT; ++k)
-#pragma unroll
-          for (int q = 0; q < RD; ++q) gt[k][q] = o[k][q];
+        park_get(0, gt);         // gs
+        net_backward<SPT, U>(w, Hp, c, gt, gcnd, Gl, goff, lane);
+        park_get(1, t);
+        park_get(2, gt);
       };
       (void)boff;
       if (l & 1) run(lo, hi, glo, ghi);
@@ -559,10 +584,11 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
 // Fused NLL training step on the register-resident kernel; rows_used = partial rows written (one per warp).
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                     float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                    int sms, int variant, int64_t* rows_out, cudaStream_t st) {
-  const size_t smem = smem_fwd + (size_t)d.L * 10 * sizeof(int);
+                    int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st) {
 #define TV(NT, SPT, U, MB)                                                                                           \
   do {                                                                                                               \
+    const size_t smem = smem_fwd + (size_t)((d.L * 10 + 3) / 4) * 4 * sizeof(int) + (size_t)3 * SPT * RD * NT * sizeof(float); \
+    if ((long long)smem > max_smem - 1024) break;      /* this variant's plan does not fit: try the next smaller one */ \
     int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, U, MB>, smem);                                              \
     if (rc) return rc;                                                                                               \
     int per_sm = 0;                                                                                                  \
@@ -580,12 +606,20 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
     CNF_CHECK_CUDA(cudaGetLastError());                                                                              \
     return CNF_OK;                                                                                                   \
   } while (0)
-  switch (variant) {
-    case 1: TV(128, 2, 2, 2);
-    case 2: TV(128, 3, 2, 2);
-    case 3: TV(128, 4, 1, 2);
-    case 4: TV(256, 4, 2, 1);
-    default: TV(128, 4, 2, 2);
+  // Measured on B200 at the C2 shape, 4 Mi samples (profiles/microbench/fp32r_train_speed.py): 256 threads x 8 samples
+  // (one CTA per SM, the whole register file) 266.8 M samples/s; 256 x 6 241; 128 x 8 214; 128 x 4 (2 CTAs/SM) 206;
+  // the 32-sample-tile split kernel 164.6.  Samples per thread amortise the weight loads and the butterfly.
+  switch (variant) {      // experiment switch (CNF_FP32R_TRAIN); a plan that does not fit shared memory falls through
+    case 1: TV(128, 6, 2, 1);
+    case 2: TV(128, 8, 2, 1);
+    case 4: TV(256, 6, 2, 1);
+    case 5: TV(128, 4, 2, 2);
+    default: break;
   }
+  TV(256, 8, 2, 1);
+  TV(128, 8, 2, 1);
+  TV(128, 4, 2, 2);
+  cnf_set_error("register-resident training kernel: the weights of %d layers do not fit shared memory", d.L);
+  return CNF_E_SMEM;
 #undef TV
 }

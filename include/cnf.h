@@ -80,7 +80,8 @@ typedef struct cnf_plan_info {
   int64_t n_flat;          /* floats in the canonical flat parameter vector         */
   int64_t n_packed;        /* floats in the fp32 packed blob                        */
   int64_t n_tables;        /* int32 entries of the index tables                     */
-  int64_t n_grad_rows;     /* rows of the per-CTA gradient partial buffer           */
+  int64_t n_grad_rows;     /* rows of the gradient partial buffer (one per CTA or   */
+                           /* per warp of the training kernels; <= 1184)            */
   int64_t tc_bytes;        /* bytes of the bf16 tensor-core blob, 0 if shape not    */
                            /* supported by the tensor-core path                     */
   int32_t d0, d1;          /* transformed / conditioning dims per layer             */

@@ -17,9 +17,9 @@ model = bench.make_model(seed=2, wmult=float(os.environ.get('WMULT', 1.0))).to(d
 eng = model.engine()
 eng.ensure(dev)
 eng.pack()
-names = {'off': 'split kernel (32-sample tiles)', '0': 'reg 128 thr x 4 u2', '1': 'reg 128 x 2', '2': 'reg 128 x 3', '3': 'reg 128 x 4 u1', '4': 'reg 256 x 4 (1/SM)'}
+names = {'off': 'split kernel (32-sample tiles)', '0': 'reg 128 thr x 4 u2 (2/SM)', '1': 'reg 128 x 6 u2 (1/SM)', '2': 'reg 128 x 8 u2', '3': 'reg 256 x 8 u2', '4': 'reg 256 x 6 u2', '5': 'reg 128 x 8 u1', '6': 'reg 256 x 8 u1'}
 ref = None
-for v in ['off', '0', '1', '2', '3', '4']:
+for v in ['off', '0', '1', '2', '3', '4', '5', '6']:
     os.environ['CNF_FP32R_TRAIN'] = v
     acc = torch.zeros(4, dtype=torch.float64, device=dev)
     eng.nll_step(x, y, acc)

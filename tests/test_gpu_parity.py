@@ -340,6 +340,46 @@ def test_calibrator_minibatch_fit_vs_oracle_with_pinned_permutation(cuda_device)
     assert rel_err((got - g['flat0'])[big], disp[big]) < 2e-2
 
 
+@pytest.mark.parametrize('golden,N', [('flow_c2_nvp_k10', 65_536), ('flow_c2_nvp_k10', 70_003), ('flow_c2_nvp_k10_init', 131_075)])
+@pytest.mark.parametrize('eps,gamma', [(1e-7, 1.0), (0.0, 1.0), (0.0, 0.0)])
+def test_register_resident_training_kernel_vs_oracle(golden, N, eps, gamma, cuda_device, monkeypatch):
+    """Batches of >= 65,536 samples at K = 10 train on train_reg10_kernel (tapeless backward, butterfly-reduced
+    weight gradients): loss and gradient against the float64 oracle (fp32 tolerances: loss 1e-5, gradient 2e-4 of its
+    maximum), against the 32-sample-tile kernel on the same data, bitwise repeatable, and evaluation-only calls."""
+    import torch
+    g = load_golden(golden)
+    flow = build_flow_from_golden(g, cuda_device)
+    eng = flow.engine()
+    eng.ensure(cuda_device)
+    eng.pack()
+    p = oracle_params_from_golden(g, np.float64)
+    x, y = orc.synth_logits(N, 10, seed=N % 1000)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc, eps=eps, gamma=gamma)
+    grad = eng.flat_grad.cpu().numpy().copy()
+    loss, ce, ldm, grads, _ = orc.train_step_grads(p, x.astype(np.float64), y, eps=eps, gamma=gamma)
+    ref = orc.flatten(grads)
+    assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+    assert abs(-float(acc[1]) / N - ce) < 1e-5 * max(1.0, abs(ce)) and float(acc[3]) == 0.0
+    assert rel_err(grad, ref) < 2e-4, rel_err(grad, ref)
+    assert np.all(grad[ref == 0] == 0)
+    # one row of the partial buffer per warp, tiles in a fixed order on each: the sums do not depend on scheduling
+    acc2 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc2, eps=eps, gamma=gamma)
+    assert np.array_equal(eng.flat_grad.cpu().numpy(), grad)
+    # evaluation only: same sums, no gradient buffer touched
+    acc3 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc3, eps=eps, gamma=gamma, with_grad=False)
+    assert np.allclose(acc3.cpu().numpy(), acc.cpu().numpy(), rtol=1e-12)
+    # the tile kernel on the same batch
+    monkeypatch.setenv('CNF_FP32R_TRAIN', 'off')
+    acc4 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
+    assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 1e-5
+    assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
+
+
 def test_full_size_properties_c2(cuda_device):
     """BASELINE config C2 size (K=10, N=1M, L=6, H=128): size-independent properties."""
     import torch
