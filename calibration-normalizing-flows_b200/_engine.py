@@ -129,6 +129,11 @@ class StackEngine:
         self.flat_grad = None
         self.adam_m = self.adam_v = None
         self.adam_t = 0
+        self.version = 0        # bumped whenever the library changes the weights (torch's own counter does not see that)
+
+    def weights_version(self):
+        """Identity of the current weights: changes on every update through this engine or through torch."""
+        return None if self.flat is None else (self.version, self.flat._version, self.flat.data_ptr())
 
     # ------------------------------------------------------------------ buffers
     def _bind(self, device):
@@ -142,6 +147,7 @@ class StackEngine:
                 p.data = self.flat[off:off + n].view(p.shape)
                 off += n
         self.device = device
+        self.version += 1
         self.gather = torch.from_numpy(self._gather_host).to(device)
         self.tables = torch.from_numpy(self._tables_host).to(device)
         self.packed = torch.empty(self.n_packed, dtype=torch.float32, device=device)
@@ -410,6 +416,7 @@ class StackEngine:
             self.adam_v = torch.zeros_like(self.flat)
             self.adam_t = 0
         self.adam_t += 1
+        self.version += 1
         _lib.call('cnf_adam_step', _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
                   ctypes.c_int64(self.n_flat), ctypes.c_int64(self.adam_t), ctypes.c_float(lr),
                   ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
@@ -426,6 +433,7 @@ class StackEngine:
         if getattr(self, 'adam_step_dev', None) is None or self.adam_step_dev.device != self.flat.device:
             self.adam_step_dev = torch.full((1,), int(self.adam_t), dtype=torch.int64, device=self.flat.device)
             self.adam_coef = torch.zeros(2, dtype=torch.float32, device=self.flat.device)
+        self.version += 1
         _lib.call('cnf_adam_step_dev', _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
                   ctypes.c_int64(self.n_flat), _ptr(self.adam_step_dev), _ptr(self.adam_coef), ctypes.c_float(lr),
                   ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
@@ -433,6 +441,7 @@ class StackEngine:
 
     @_guarded
     def sgd(self, lr, weight_decay=0.0):
+        self.version += 1
         _lib.call('cnf_sgd_step', _ptr(self.flat), _ptr(self.flat_grad), ctypes.c_int64(self.n_flat),
                   ctypes.c_float(lr), ctypes.c_float(weight_decay), _stream(self.device))
 

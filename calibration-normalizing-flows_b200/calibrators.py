@@ -223,6 +223,7 @@ class FusedNLLTrainer:
             self._graph = g
             return
         self._graph.replay()
+        self.engine.version += 1         # the replayed graph updated the weights
 
     def _step_body(self):
         e = self.engine
@@ -248,6 +249,7 @@ class FusedNLLTrainer:
             self._sgraph = g
             return
         self._sgraph.replay()
+        self.engine.version += 1         # the replayed graph updated the weights
 
     def fit_loop(self, epochs, batch_size, perm_fn, cuda_graph=False):
         """The epoch loop of ``TorchFlowCalibrator.fit`` (calibrators.py:283-317) on the resident local

@@ -325,7 +325,14 @@ def build_engine(layers):
 
 class _LazyOutputs:
     """List-like view of the per-layer outputs of a Flow pass.  ``[-1]`` is available at once;
-    any other index triggers (once per fused segment) a launch that writes all intermediates."""
+    any other index triggers (once per fused segment) a launch that writes all intermediates.
+
+    Differences from the reference's plain list (flows/flows.py:17-25), by design: the intermediates are
+    recomputed from the segment's input when first indexed, by the fp32 kernel (also when ``zs[-1]`` came from
+    the bf16 kernel), and they carry no autograd graph -- only ``zs[-1]`` is differentiable.  They must be read
+    before the weights change: the pass remembers the version of every stack's parameter buffer and indexing an
+    intermediate after an optimiser step / ``load_state_dict`` raises instead of silently returning the
+    outputs of the NEW weights."""
 
     def __init__(self, flow, segments, seg_inputs, seg_outputs, inverse):
         self._flow, self._segments = flow, segments
@@ -333,6 +340,7 @@ class _LazyOutputs:
         self._inverse = inverse
         self._cache = {}
         self._n = sum(seg[2] - seg[1] for seg in segments)
+        self._versions = [seg[3].weights_version() if seg[0] == 'stack' else None for seg in segments]
 
     def __len__(self):
         return self._n
@@ -354,6 +362,11 @@ class _LazyOutputs:
                 if i == pos + n - 1:
                     return self._outputs[si]
                 if si not in self._cache:
+                    v = self._versions[si]
+                    if v is not None and eng.weights_version() != v:
+                        raise RuntimeError('cnf_b200: the flow\'s weights changed since this pass; intermediate outputs '
+                                           '(zs[i], i < L-1) are materialised lazily and must be read before the next '
+                                           'optimiser step / load_state_dict (zs[-1] is always available)')
                     with torch.no_grad():
                         _, _, allz = eng.apply(self._inputs[si], inverse=self._inverse, want_all=True)
                     self._cache[si] = allz
@@ -412,10 +425,12 @@ class Flow(nn.Module):
         for kind, a, b, obj in segs:
             ins.append(x)
             if kind == 'stack':
+                torch.cuda.nvtx.range_push('cnf.flow_forward')
                 if self.precision == 'bf16' and not torch.is_grad_enabled():
                     x, ld, _ = obj.apply(x, precision='bf16')
                 else:
                     x, ld = stack_forward(obj, x)
+                torch.cuda.nvtx.range_pop()
                 ld = ld.squeeze()
             else:
                 x, ld = obj(x)
@@ -432,7 +447,9 @@ class Flow(nn.Module):
         for kind, a, b, obj in segs:
             ins.append(z)
             if kind == 'stack':
+                torch.cuda.nvtx.range_push('cnf.flow_inverse')
                 z, ld, _ = obj.apply(z, inverse=True, precision=self.precision)
+                torch.cuda.nvtx.range_pop()
                 ld = ld.squeeze()
             else:
                 z, ld = obj.backward(z)

@@ -204,3 +204,33 @@ def test_flow_on_a_non_current_device(cuda_device):
     p = torch.softmax(z1[-1], dim=1)
     assert abs(cnf_b200.expected_calibration_error(p, torch.from_numpy(y).to(dev1)) -
                cnf_b200.expected_calibration_error(p.cpu().numpy(), y)) < 1e-6
+
+
+def test_lazy_intermediates_refuse_stale_weights(cuda_device):
+    """zs[i < L-1] are materialised lazily: reading them after the weights changed must raise, not return
+    the outputs of the new weights; zs[-1] stays valid; a fresh pass works again."""
+    import torch
+    import cnf_b200
+    g = load_golden('flow_c2_nvp_k10')
+    flow = build_flow_from_golden(g, cuda_device)
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(x)
+        z0 = zs[0].clone()                         # read before any update: fine
+        assert np.max(np.abs(z0.cpu().numpy() - g['zs'][0])) <= 1e-5 * np.max(np.abs(g['zs'][0]))
+        zs2, _ = flow(x)
+    tr = cnf_b200.FusedNLLTrainer(flow.engine(), x, y)
+    tr.step()                                      # fused Adam through the C ABI: torch's version counter does not move
+    with pytest.raises(RuntimeError):
+        zs2[1]
+    assert torch.equal(zs2[-1], zs[-1])
+    with torch.no_grad():
+        zs3, _ = flow(x)
+        zs3[1]
+        with torch.no_grad():
+            for p in flow.parameters():
+                if p.requires_grad:
+                    p.mul_(1.01)                   # a torch-side in-place update is seen too
+        with pytest.raises(RuntimeError):
+            zs3[2]
