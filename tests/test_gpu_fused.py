@@ -227,10 +227,11 @@ def test_lazy_intermediates_refuse_stale_weights(cuda_device):
     assert torch.equal(zs2[-1], zs[-1])
     with torch.no_grad():
         zs3, _ = flow(x)
-        zs3[1]
-        with torch.no_grad():
-            for p in flow.parameters():
-                if p.requires_grad:
-                    p.mul_(1.01)                   # a torch-side in-place update is seen too
+        zs4, _ = flow(x)
+        first = zs3[1].clone()                     # materialises (and caches) the whole segment with the weights of the pass
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(1.01)                       # a torch-side in-place update is seen too
+        assert torch.equal(zs3[2], zs3[2]) and torch.equal(zs3[1], first)    # cached: still the old weights' outputs
         with pytest.raises(RuntimeError):
-            zs3[2]
+            zs4[2]                                 # never materialised before the update
