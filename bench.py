@@ -576,6 +576,29 @@ def run_ours(args):
                 train[prec]['what'] = train[prec]['what'].replace('fused NLL fwd+bwd kernel', 'register-resident fused NLL fwd+bwd kernel (train_reg10_kernel)')
             del tr, tmodel
         legs['train_step'] = train
+        # the same step with the samples in pinned HOST memory, streamed through the GPU every step (SURVEY.md 8f rank 4:
+        # sets larger than HBM): H2D of chunk c+1 overlaps the kernel of chunk c
+        if not args.no_extra:
+            n_st = min(n_loc, 16 * (1 << 20))
+            xs_h = torch.empty((n_st, K), dtype=torch.float32, pin_memory=True)
+            ys_h = torch.empty(n_st, dtype=torch.int64, pin_memory=True)
+            xs_h.copy_(xt[:n_st])
+            ys_h.copy_(yt[:n_st])
+            streamed = {}
+            for prec in precisions:
+                if prec == 'bf16' and eng.tc_train is None:
+                    continue
+                tmodel = make_model(seed=2, wmult=1.0).to(dev)
+                trs = cnf_b200.HostStreamNLLTrainer(tmodel.engine(), xs_h, ys_h, dev, n_total=n_st * world, resident=False,
+                                                    chunk_rows=1 << 21, precision=prec)
+                t = wall_timed(lambda i: (trs.step(), torch.cuda.current_stream(dev).synchronize()), few, 3)
+                streamed[prec] = {'value': world * n_st / (t * 1e-3), 'ms_per_step': t}
+                del trs, tmodel
+            legs['train_step_host_streamed'] = {
+                'what': 'the same Adam step with the %d samples per GPU resident in pinned host memory and streamed over PCIe '
+                        'every step (HostStreamNLLTrainer, 2^21-row chunks double-buffered; 48 B/sample H2D)' % n_st,
+                'unit': UNIT, 'h2d_bytes_per_step': n_st * (4 * K + 8), **streamed}
+            del xs_h, ys_h
 
     # ---- data-parallel consistency (N > 1): identical parameters on every rank, same loss as one rank -----
     dp_check = None
@@ -864,6 +887,7 @@ def run_ours(args):
             'fwd_fp32': g(world * n_head / (fwd_ms['fp32'] * 1e-3)) if 'fp32' in fwd_ms else None,
             'e2e_bf16': g(e2e_by.get('bf16')), 'e2e_fp32': g(e2e_by.get('fp32')), 'e2e_frac_of_pcie_ceiling': round(e2e_by[head_prec] / ceiling, 3),
             'train_bf16': g(tr_.get('bf16', {}).get('value')), 'train_fp32': g(tr_.get('fp32', {}).get('value')),
+            'train_streamed_bf16': g(legs.get('train_step_host_streamed', {}).get('bf16', {}).get('value')),
             'c5_job': g(legs.get('c5_job', {}).get(head_prec, {}).get('value')),
             'c5_ece': legs.get('c5_job', {}).get(head_prec, {}).get('ece'),
             'c4_fwd_bf16': g(legs.get('c4_forward', {}).get('value')),
