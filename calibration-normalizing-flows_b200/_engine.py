@@ -133,7 +133,11 @@ class StackEngine:
 
     def weights_version(self):
         """Identity of the current weights: changes on every update through this engine or through torch."""
-        return None if self.flat is None else (self.version, self.flat._version, self.flat.data_ptr())
+        if self.flat is None:
+            return None
+        # the nn.Parameters are views into `flat` with version counters of their own: torch optimisers and in-place
+        # edits bump those, the fused optimiser kernels bump self.version
+        return (self.version, self.flat.data_ptr(), sum(p._version for p in self.params))
 
     # ------------------------------------------------------------------ buffers
     def _bind(self, device):
