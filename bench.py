@@ -17,7 +17,7 @@ all-reduce of the 48 statistics), the HBM-bound metrics / affine kernels, C4 (K=
 calibrator fit, a calibration-set-sized epoch, and at N>1 a data-parallel consistency check.
 
 Reference arm (--impl reference): the UNMODIFIED reference (`Flow.forward`, flows/flows.py:17-25) from
-oracle/_ref/reference (copied there by __graft_entry__.build(); the GPU box has no /root/reference) on
+oracle/_ref/reference.zip (packed there by __graft_entry__.build(); the GPU box has no /root/reference) on
 all host threads, rank 0 only, on a bounded sample of the same workload.  It imports nothing of the
 product.  Falls back to the torch-CPU port (oracle/ref_port_torch.py, kind "port") when the copy is absent.
 """
@@ -192,7 +192,7 @@ def make_model(seed=1, wmult=300.0, k=K, layers=L, hidden=HIDDEN):
 # the reference on the host cores
 # ------------------------------------------------------------------------------------------------
 class HostReference:
-    """The reference's CPU implementation of the path: the unmodified modules when oracle/_ref/reference (or
+    """The reference's CPU implementation of the path: the unmodified modules when oracle/_ref/reference.zip (or
     /root/reference) exists -> kind 'reference'; else the torch-CPU port -> kind 'port'."""
 
     def __init__(self):

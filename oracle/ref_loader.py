@@ -2,8 +2,8 @@
 (bench.py's reference arm and cpu_baseline legs, oracle/make_golden.py-style checks); never imported by
 the product package.
 
-Search order: oracle/_ref/reference (copied by oracle/fetch_reference.py, travels to the GPU box), then
-/root/reference (authoring container).  Returns None when neither exists (callers fall back to the
+Search order: oracle/_ref/reference.zip (packed by oracle/fetch_reference.py, travels to the GPU box; imported
+straight from the archive), then /root/reference (authoring container).  Returns None when neither exists (callers fall back to the
 port in oracle/ref_port_torch.py and say kind == "port").
 
 Shims applied in memory only (the files stay byte-identical):
@@ -16,9 +16,10 @@ import importlib
 import os
 import sys
 import types
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CANDIDATES = [os.path.join(HERE, '_ref', 'reference'), '/root/reference']
+CANDIDATES = [os.path.join(HERE, '_ref', 'reference.zip'), '/root/reference']
 
 
 class Reference:
@@ -34,7 +35,10 @@ class Reference:
         finally:
             sys.path.remove(root)
         self.Flow, self.NvpCouplingLayer = self.flows.Flow, self.flows.NvpCouplingLayer
-        src = open(os.path.join(root, 'utils', 'metrics.py')).read()
+        if zipfile.is_zipfile(root):
+            src = zipfile.ZipFile(root).read('utils/metrics.py').decode()
+        else:
+            src = open(os.path.join(root, 'utils', 'metrics.py')).read()
         src = src.replace('np.equal(preds, target, dtype=np.float32)', 'np.equal(preds, target).astype(np.float32)')
         src = src.replace('from .ops import onehot_encode', 'from utils.ops import onehot_encode')
         self.metrics = types.ModuleType('ref_metrics')
@@ -68,6 +72,6 @@ class Reference:
 
 def load():
     for root in CANDIDATES:
-        if os.path.isfile(os.path.join(root, 'flows', 'flows.py')):
+        if (os.path.isfile(root) and zipfile.is_zipfile(root)) or os.path.isfile(os.path.join(root, 'flows', 'flows.py')):
             return Reference(root)
     return None
