@@ -259,7 +259,10 @@ class StackEngine:
         if y is not None:
             y = check_labels(y, N, dev)
             acc = torch.zeros(3 * bins + 3, dtype=torch.float64, device=dev)
-            edges = torch.tensor([i * (1. / bins) for i in range(bins + 1)], dtype=torch.float64, device=dev)
+            cache = self.__dict__.setdefault('_edges', {})
+            edges = cache.get((bins, dev))
+            if edges is None:        # bin edges i * (1 / bins) as the reference forms them (utils/metrics.py:57, 61)
+                edges = cache[(bins, dev)] = torch.tensor([i * (1. / bins) for i in range(bins + 1)], dtype=torch.float64, device=dev)
         desc = self.desc_tc if use_tc else self.desc
         packed = self.packed_tc if use_tc else self.packed
         with on_device(dev):

@@ -341,13 +341,15 @@ class HostStreamNLLTrainer(FusedNLLTrainer):
         rows = n if self.resident else min(n, 2 * self.chunk_rows)
         xbuf = torch.empty((rows, K), dtype=torch.float32, device=device)
         ybuf = torch.empty(rows, dtype=torch.int64, device=device)
-        super().__init__(engine, xbuf, ybuf, n_total=n_total if n_total is not None else None, **kw)
+        if n_total is None:          # the size of the whole set: the sum of the ranks' host shards
+            n_total = n
+            d = _dist()
+            if d is not None:
+                t = torch.tensor([n], dtype=torch.int64, device=device)
+                d.all_reduce(t)
+                n_total = int(t.item())
+        super().__init__(engine, xbuf, ybuf, n_total=n_total, **kw)
         self.n_local = n
-        if n_total is None:          # the base class counted the staging rows: count the real shard
-            t = torch.tensor([n], dtype=torch.int64, device=device)
-            if self.dist is not None:
-                self.dist.all_reduce(t)
-            self.n_total = int(t.item())
         self._copy_stream = torch.cuda.Stream(device=device)
         self._copied = [torch.cuda.Event(), torch.cuda.Event()]
         self._freed = [torch.cuda.Event(), torch.cuda.Event()]
