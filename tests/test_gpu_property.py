@@ -68,6 +68,31 @@ def test_random_shapes_match_oracle(cfg, seed, cuda_device):
         zb, lb, _ = eng.apply(xt, precision='bf16')
         assert rel_err(zb.cpu().numpy(), zo[-1]) < 1e-2
         assert np.max(np.abs(lb.cpu().numpy() - ldo)) < 1e-2 * scale_ld
+    # the fused pass on RAW logits (cnf_flow_predict): centring prologue + flow + Calibrator.predict tail + statistics,
+    # against numpy centring (calibrators.py:42) -> oracle flow -> oracle tail / metrics
+    xraw = (x + np.float32(0.5 + 0.01 * seed % 3)).astype(np.float32)
+    lp = orc.log_priors(orc.onehot_encode(np.concatenate([y, np.arange(K)])))
+    yt = torch.from_numpy(y).to(cuda_device)
+    precs = ['fp32'] + (['bf16'] if eng.tc_bytes > 0 else [])
+    zc, _ = orc.flow_forward(params, orc.center(xraw).astype(np.float64))
+    pc = orc.calibrated_probs(zc[-1], lp)
+    for prec in precs:
+        try:
+            res = eng.predict(torch.from_numpy(xraw).to(cuda_device), center=True, log_priors=lp, y=yt, bins=15,
+                              want_z=True, want_probs=True, precision=prec)
+        except NotImplementedError:
+            continue                 # shape outside the fused kernels (the streamed-weight tensor-core kernel)
+        tol = 1e-5 if prec == 'fp32' else 1e-2
+        assert rel_err(res['z'].cpu().numpy(), zc[-1]) < tol
+        probs = res['probs'].cpu().numpy()
+        assert np.max(np.abs(probs - pc)) < (2e-5 if prec == 'fp32' else 1e-2)
+        st_ = res['stats'].cpu().numpy()
+        assert st_[47] == N and st_[:15].sum() == N
+        if prec == 'fp32':
+            oh = np.eye(K, dtype=np.int32)[y]            # (onehot_encode sizes by max(label)+1, utils/ops.py:46)
+            nll = orc.neg_log_likelihood(pc, oh)
+            assert abs(st_[45] / N - nll) < 1e-4 * max(1.0, abs(nll))
+            assert abs(st_[46] / N - orc.accuracy(pc, oh)) <= 2.0 / N      # an argmax tie may fall either way
 
 
 @st.composite
