@@ -557,6 +557,10 @@ class TorchFlowCalibrator(Calibrator):
         logits = np.asarray(logits) if not isinstance(logits, torch.Tensor) else logits
         if eng is None or eng.K > 128 or logits.dtype not in (np.float32, torch.float32):
             return None          # numpy centres float64 logits in float64: keep that arithmetic on the host
+        if getattr(self, 'precision', 'fp32') != 'bf16' and logits.shape[0] <= 32768 and not getattr(self, 'force_fused', False):
+            # fp32 at calibration-set sizes: the 32-sample-tile forward kernel plus the tail kernel is quicker than the
+            # one-thread-per-sample fused kernel (0.08 vs ~0.2 ms at N = 10,000); the fused pass pays from ~10^5 rows
+            return None
         x = torch.as_tensor(np.ascontiguousarray(logits) if not isinstance(logits, torch.Tensor) else logits)
         self.flow.to(self.dev)
         x = x.to(self.dev)

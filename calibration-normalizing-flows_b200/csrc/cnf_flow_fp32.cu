@@ -2035,12 +2035,14 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
-  // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel once the batch fills the GPU
-  // (CNF_FP32R: "off" disables, "0".."5" picks the (threads, samples per thread) variant -- experiments)
+  // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel once the batch fills the GPU with
+  // its 1024-sample tiles.  Measured crossover on B200 (profiles/microbench/fp32r_crossover.py, us per call, generic /
+  // register kernel): N = 131,072: 197 / 278; 262,144: 385 / 356; 524,288: 755 / 538; 4 Mi: 5308 / 2800.
+  // (CNF_FP32R: "off" disables, a digit forces a (threads, samples per thread) variant at any N >= 65,536 -- experiments)
   {
     const char* sw = cnf_switch(CNF_SW_FP32R);
     size_t smem_r = 0;
-    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r))
+    if (!zs && N >= (sw ? 65536 : 262144) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, sw ? atoi(sw) : 0, st);
   }
   // 32-sample tiles with the hidden layers split over the warps: nets with two or more hidden layers (the widest
@@ -2123,7 +2125,7 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   {
     size_t smem_r = 0;
     const char* sw = cnf_switch(CNF_SW_FP32R);
-    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
+    if (N >= (sw ? 1 : 262144) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms, 0, st);
   }
   LaunchCfg c;
@@ -2176,9 +2178,11 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if ((rc = device_limits())) return rc;
   if (N == 0) return clear_rows(0);
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
-  // K = 10, one hidden layer, both nets, NLL head, a batch that fills the GPU: the register-resident kernel
-  // (CNF_FP32R_TRAIN: "off" disables, a digit picks the variant -- experiments)
-  if (head == CNF_HEAD_NLL && N >= 65536) {
+  // K = 10, one hidden layer, both nets, NLL head, a batch that fills the GPU: the register-resident kernel.  Measured
+  // crossover (fp32r_crossover.py, us per fused pass, 32-sample-tile kernel / register kernel): N = 131,072: 819 / 877;
+  // 262,144: 1613 / 1334; 1 Mi: 6330 / 4681; 4 Mi: 25457 / 15714.
+  // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 65,536 -- experiments)
+  if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 262144)) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
     if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r)) {

@@ -573,6 +573,10 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
       case 1: RV(128, 4, 2, 3);
       case 2: RV(128, 6, 2, 3);
       case 3: RV(256, 8, 2, 1);
+      case 4: RV(128, 2, 2, 3);
+      case 5: RV(128, 1, 2, 3);
+      case 6: RV(64, 2, 2, 3);
+      case 7: RV(64, 1, 2, 3);
       default: RV(128, 8, 2, 2);
     }
 #undef RV
@@ -615,6 +619,12 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
     case 4: TV(256, 6, 2, 1);
     case 5: TV(128, 4, 2, 2);
     default: break;
+  }
+  {
+    // 2048-sample tiles (256 x 8) unless 1536-sample tiles (256 x 6) need fewer or cheaper waves over the SMs
+    // (one wave of either takes ~1.23 / ~1.04 ms at the C2 shape: 400,000 samples are 2 waves of either)
+    const long long w8 = (N + 2048LL * sms - 1) / (2048LL * sms), w6 = (N + 1536LL * sms - 1) / (1536LL * sms);
+    if (variant == 0 && w6 * 104 < w8 * 123) TV(256, 6, 2, 1);
   }
   TV(256, 8, 2, 1);
   TV(128, 8, 2, 1);

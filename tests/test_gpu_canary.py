@@ -32,7 +32,7 @@ def check(buf, view, n, misalign=0, written=True):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-@pytest.mark.parametrize('N', [1, 33, 1000, 40_001, 70_003])
+@pytest.mark.parametrize('N', [1, 33, 1000, 40_001, 70_003, 262_147])
 @pytest.mark.parametrize('misalign', [0, 1])
 def test_flow_outputs_stay_inside_their_buffers(precision, N, misalign, cuda_device):
     import torch

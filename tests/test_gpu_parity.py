@@ -343,10 +343,11 @@ def test_calibrator_minibatch_fit_vs_oracle_with_pinned_permutation(cuda_device)
 @pytest.mark.parametrize('golden,N', [('flow_c2_nvp_k10', 65_536), ('flow_c2_nvp_k10', 70_003), ('flow_c2_nvp_k10_init', 131_075)])
 @pytest.mark.parametrize('eps,gamma', [(1e-7, 1.0), (0.0, 1.0), (0.0, 0.0)])
 def test_register_resident_training_kernel_vs_oracle(golden, N, eps, gamma, cuda_device, monkeypatch):
-    """Batches of >= 65,536 samples at K = 10 train on train_reg10_kernel (tapeless backward, butterfly-reduced
+    """Large batches (>= 262,144 samples) at K = 10 train on train_reg10_kernel (tapeless backward, butterfly-reduced
     weight gradients): loss and gradient against the float64 oracle (fp32 tolerances: loss 1e-5, gradient 2e-4 of its
     maximum), against the 32-sample-tile kernel on the same data, bitwise repeatable, and evaluation-only calls."""
     import torch
+    monkeypatch.setenv('CNF_FP32R_TRAIN', '0')      # by default the kernel takes over from 262,144 samples; forced here
     g = load_golden(golden)
     flow = build_flow_from_golden(g, cuda_device)
     eng = flow.engine()
@@ -396,12 +397,12 @@ def test_full_size_properties_c2(cuda_device):
         assert float((ld + ldr).abs().max()) < 5e-4
         assert torch.isfinite(zs[-1]).all()
         # a slice equals the same rows computed alone (tiles are independent): bitwise on the same kernel ...
-        z_mid, ld_mid = flow(xt[123456:123456 + 70_001])
-        assert torch.equal(z_mid[-1], zs[-1][123456:123456 + 70_001])
-        assert torch.equal(ld_mid, ld[123456:123456 + 70_001])
+        z_mid, ld_mid = flow(xt[123456:123456 + 300_001])
+        assert torch.equal(z_mid[-1], zs[-1][123456:123456 + 300_001])
+        assert torch.equal(ld_mid, ld[123456:123456 + 300_001])
         # ... and to fp32 rounding on the kernels that serve smaller batches (generic thread-per-sample below
-        # 65,536 rows, 32-sample tiles below 32,768: other summation orders)
-        for n_small in (40_001, 777):
+        # 262,144 rows, 32-sample tiles up to 32,768: other summation orders)
+        for n_small in (70_001, 40_001, 777):
             z_small, ld_small = flow(xt[123456:123456 + n_small])
             assert float((z_small[-1] - zs[-1][123456:123456 + n_small]).abs().max()) < 2e-6 * float(zs[-1].abs().max())
             assert float((ld_small - ld[123456:123456 + n_small]).abs().max()) < 2e-6 * max(1.0, float(ld.abs().max()))
@@ -435,10 +436,8 @@ def test_host_buffer_api_matches_device_api(precision, cuda_device):
     if precision == 'bf16':
         assert torch.equal(zh, z.cpu()) and torch.equal(lh, ld.cpu())
     else:
-        # fp32: full 65,536-row chunks run on the same kernel as the device-resident call (bitwise); the ragged last
-        # chunk is below that kernel's batch threshold and takes the generic one (another summation order)
-        full = 4 * 65536
-        assert torch.equal(zh[:full], z.cpu()[:full]) and torch.equal(lh[:full], ld.cpu()[:full])
+        # fp32: the 65,536-row chunks take the generic kernel, the 300,007-row device-resident call the
+        # register-resident one (another summation order)
         assert float((zh - z.cpu()).abs().max()) < 2e-6 * float(z.abs().max())
         assert float((lh - ld.cpu()).abs().max()) < 2e-6 * max(1.0, float(ld.abs().max()))
     # pageable numpy input and inverse direction
