@@ -2035,15 +2035,18 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return CNF_OK;
   if (!packed || !tables || !x || !z || !logdet || N < 0) { cnf_set_error("null pointer / negative N"); return CNF_E_ARG; }
   if ((rc = device_limits())) return rc;
-  // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel once the batch fills the GPU with
-  // its 1024-sample tiles.  Measured crossover on B200 (profiles/microbench/fp32r_crossover.py, us per call, generic /
-  // register kernel): N = 131,072: 197 / 278; 262,144: 385 / 356; 524,288: 755 / 538; 4 Mi: 5308 / 2800.
-  // (CNF_FP32R: "off" disables, a digit forces a (threads, samples per thread) variant at any N >= 65,536 -- experiments)
+  // K = 10, one hidden layer, both nets, standard flips: the register-resident kernel from 65,536 samples, with 2, 4 or
+  // 8 samples per thread (256- / 512- / 1024-sample tiles) so that the tiles fill the SMs.  Measured on B200
+  // (profiles/microbench/fp32r_crossover.py, us per call, generic kernel / best register variant): N = 65,536: 141 / 108
+  // (x2); 131,072: 197 / 153 (x4); 262,144: 386 / 232 (x8); 1 Mi: 1331 / 789; 4 Mi: 5303 / 2669.
+  // (CNF_FP32R: "off" disables, a digit forces a (threads, samples per thread) variant -- experiments)
   {
     const char* sw = cnf_switch(CNF_SW_FP32R);
     size_t smem_r = 0;
-    if (!zs && N >= (sw ? 65536 : 262144) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r))
-      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, sw ? atoi(sw) : 0, st);
+    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r)) {
+      const int variant = sw ? atoi(sw) : (N >= 240000 ? 0 : (N >= 113000 ? 1 : 4));
+      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, variant, st);
+    }
   }
   // 32-sample tiles with the hidden layers split over the warps: nets with two or more hidden layers (the widest
   // of at least 64 units), and single-hidden-layer nets on small batches ("0" disables, "1" forces: experiments)
@@ -2125,8 +2128,9 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   {
     size_t smem_r = 0;
     const char* sw = cnf_switch(CNF_SW_FP32R);
-    if (N >= (sw ? 1 : 262144) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
-      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms, 0, st);
+    if (N >= (sw ? 1 : 65536) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
+      return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms,
+                             N >= 240000 ? 0 : (N >= 113000 ? 1 : 4), st);
   }
   LaunchCfg c;
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
@@ -2179,10 +2183,11 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (N == 0) return clear_rows(0);
   if (!x) { cnf_set_error("null x"); return CNF_E_ARG; }
   // K = 10, one hidden layer, both nets, NLL head, a batch that fills the GPU: the register-resident kernel.  Measured
-  // crossover (fp32r_crossover.py, us per fused pass, 32-sample-tile kernel / register kernel): N = 131,072: 819 / 877;
-  // 262,144: 1613 / 1334; 1 Mi: 6330 / 4681; 4 Mi: 25457 / 15714.
+  // crossover (fp32r_crossover.py, us per fused pass, 32-sample-tile kernel / register kernel): N = 131,072: 819 / 953;
+  // 200,000: 1232 / 994; 262,144: 1612 / 1216; 1 Mi: 6326 / 4594; 4 Mi: 25462 / 15689 (one wave of its 2048-sample
+  // tiles takes ~0.95 ms whatever it holds, the tile kernel's time grows with N: they cross at ~155,000 samples).
   // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 65,536 -- experiments)
-  if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 262144)) {
+  if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000)) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
     if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r)) {

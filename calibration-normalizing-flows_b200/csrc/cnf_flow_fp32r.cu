@@ -83,6 +83,47 @@ __device__ __forceinline__ void layer_eval(const float4* __restrict__ w, const f
   }
 }
 
+// Stage the weights of all layers: packed [d1][Hp] / [Hp] / [d0][Hp] / [d0p] per net -> per hidden unit 12 floats
+// [W1 of slot 0..4 | b1 | W2 of slot 0..4 | 0], inputs and outputs placed by their PHYSICAL slot inside the conditioning /
+// transformed half (even layers condition on slots 5..9, odd ones on 0..4).  maps[l][0..4] = packed input index of
+// conditioning slot e, maps[l][5..9] = packed output index of transformed slot e (from the index tables; formed first
+// so that the copy below reads the packed blob with h fastest, i.e. coalesced, and never searches).
+template <int R_NT>
+__device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const float* __restrict__ packed,
+                                                    const int* __restrict__ tables, float* wf, float* b2s, int* maps, int tid) {
+  const int Hp = d.Hp[0], L = d.L;
+  for (int i = tid; i < L * 10; i += R_NT) {
+    const int l = i / 10, e = i - l * 10;
+    const int* cond = tables + d.tab_cond + l * RD;
+    const int* trans = tables + d.tab_trans + l * RD;
+    const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;
+    int v = 0;
+    if (e < 5) { for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = j; }
+    else       { for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 5) v = q; }
+    maps[i] = v;
+  }
+  __syncthreads();
+  const int per_net = 12 * Hp;
+  for (int i = tid; i < L * 2 * per_net; i += R_NT) {
+    const int ln = i / per_net, r = i - ln * per_net;      // ln = l * 2 + net
+    const int e = r / Hp, h = r - e * Hp;                  // h fastest: coalesced reads of the packed rows
+    const int l = ln >> 1, net = ln & 1;
+    const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
+    const int* mp = maps + l * 10;
+    float v = 0.f;
+    if (e < 5) v = __ldg(Wn + d.w_off[0] + mp[e] * Hp + h);
+    else if (e == 5) v = __ldg(Wn + d.b_off[0] + h);
+    else if (e < 11) v = __ldg(Wn + d.w_off[1] + mp[e - 1] * Hp + h);
+    wf[((size_t)ln * Hp + h) * 12 + e] = v;
+  }
+  for (int i = tid; i < L * 16; i += R_NT) {
+    const int l = i >> 4, net = (i >> 3) & 1, e = i & 7;
+    const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
+    b2s[i] = e < RD ? __ldg(Wn + d.b_off[1] + maps[l * 10 + 5 + e]) : 0.f;
+  }
+  __syncthreads();
+}
+
 template <int R_NT, int SPT, int U, int MINB, int TAIL>
 __global__ void __launch_bounds__(R_NT, MINB)
 flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
@@ -92,10 +133,11 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
   __shared__ double tail_red[32];
   const int tid = threadIdx.x;
   const int Hp = d.Hp[0], L = d.L;
-  // shared memory: [tail state][per layer: 2 nets x Hp x 3 float4][per layer: 2 x 8 floats of b2]
+  // shared memory: [tail state][per layer: 2 nets x Hp x 3 float4][per layer: 2 x 8 floats of b2][per layer: 10 ints]
   const int tail_floats = TAIL ? cnf_tail_smem_bytes(ta.bins, RK) / 4 : 0;
   float4* ws = reinterpret_cast<float4*>(smem + tail_floats);
   float* b2s = reinterpret_cast<float*>(ws + (size_t)L * 2 * Hp * 3);
+  int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: packed input index of conditioning slot e, packed output index of transformed slot e
   TailSmem tsm;
   BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
   double a_nll = 0.0;
@@ -104,40 +146,7 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
     tsm = tail_carve(reinterpret_cast<unsigned char*>(smem), ta.bins, RK);
     tail_init(tsm, ta, RK, tid, R_NT);
   }
-  // ---- stage the weights: packed [d1][Hp] / [Hp] / [d0][Hp] / [d0p] per net -> per hidden unit 12 floats, inputs and
-  //      outputs placed by their physical slot inside the conditioning / transformed half (tables) ------------------
-  {
-    float* wf = reinterpret_cast<float*>(ws);
-    const int per_layer = 2 * Hp * 12;
-    for (int i = tid; i < L * per_layer; i += R_NT) {
-      const int l = i / per_layer, r = i - l * per_layer;
-      const int net = r / (Hp * 12), rr = r - net * (Hp * 12);
-      const int h = rr / 12, e = rr - h * 12;
-      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
-      const int* cond = tables + d.tab_cond + l * RD;
-      const int* trans = tables + d.tab_trans + l * RD;
-      const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;   // even layers condition on slots 5..9
-      float v = 0.f;
-      if (e < 5) {                      // W1 column of the conditioning input that lives in slot cbase + e
-        for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = Wn[d.w_off[0] + j * Hp + h];
-      } else if (e == 5) {
-        v = Wn[d.b_off[0] + h];
-      } else if (e < 11) {              // W2 row of the output that lands in slot tbase + (e - 6)
-        for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 6) v = Wn[d.w_off[1] + q * Hp + h];
-      }
-      wf[i] = v;
-    }
-    for (int i = tid; i < L * 16; i += R_NT) {
-      const int l = i >> 4, net = (i >> 3) & 1, e = i & 7;
-      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
-      const int* trans = tables + d.tab_trans + l * RD;
-      const int tbase = (l & 1) ? RD : 0;
-      float v = 0.f;
-      for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e) v = Wn[d.b_off[1] + q];
-      b2s[i] = v;
-    }
-  }
-  __syncthreads();
+  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -311,49 +320,7 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: [5] packed input index of slot e, [5] packed output index
   float* park = reinterpret_cast<float*>(maps + ((L * 10 + 3) / 4) * 4);   // [3][SPT][5][R_NT] per-thread parking slots
   const bool do_bwd = partials != nullptr;
-  // ---- stage the weights exactly as flow_reg10_kernel does; plus the slot -> packed-index maps ------------------
-  {
-    float* wf = reinterpret_cast<float*>(ws);
-    const int per_layer = 2 * Hp * 12;
-    for (int i = tid; i < L * per_layer; i += R_NT) {
-      const int l = i / per_layer, r = i - l * per_layer;
-      const int net = r / (Hp * 12), rr = r - net * (Hp * 12);
-      const int h = rr / 12, e = rr - h * 12;
-      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
-      const int* cond = tables + d.tab_cond + l * RD;
-      const int* trans = tables + d.tab_trans + l * RD;
-      const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;
-      float v = 0.f;
-      if (e < 5) {
-        for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = Wn[d.w_off[0] + j * Hp + h];
-      } else if (e == 5) {
-        v = Wn[d.b_off[0] + h];
-      } else if (e < 11) {
-        for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 6) v = Wn[d.w_off[1] + q * Hp + h];
-      }
-      wf[i] = v;
-    }
-    for (int i = tid; i < L * 16; i += R_NT) {
-      const int l = i >> 4, net = (i >> 3) & 1, e = i & 7;
-      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
-      const int* trans = tables + d.tab_trans + l * RD;
-      const int tbase = (l & 1) ? RD : 0;
-      float v = 0.f;
-      for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e) v = Wn[d.b_off[1] + q];
-      b2s[i] = v;
-    }
-    for (int i = tid; i < L * 10; i += R_NT) {
-      const int l = i / 10, e = i - l * 10;
-      const int* cond = tables + d.tab_cond + l * RD;
-      const int* trans = tables + d.tab_trans + l * RD;
-      const int cbase = (l & 1) ? 0 : RD, tbase = (l & 1) ? RD : 0;
-      int v = 0;
-      if (e < 5) { for (int j = 0; j < RD; ++j) if (cond[j] - cbase == e) v = j; }
-      else       { for (int q = 0; q < RD; ++q) if (trans[q] - tbase == e - 5) v = q; }
-      maps[i] = v;
-    }
-  }
-  __syncthreads();
+  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -555,7 +522,8 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
                          int max_smem, size_t* smem_out) {
   if (d.K != RK || d.m != 1 || d.nets != 3 || desc->perm != nullptr) return false;
   if (((uintptr_t)x | (uintptr_t)z) % 8 != 0) return false;
-  const size_t smem = (size_t)d.L * (2 * d.Hp[0] * 12 + 16) * sizeof(float) + (tail_bins > 0 ? cnf_tail_smem_bytes(tail_bins, RK) : 0);
+  const size_t smem = (size_t)d.L * (2 * d.Hp[0] * 12 + 16) * sizeof(float) + (size_t)((d.L * 10 + 3) / 4) * 4 * sizeof(int) +
+                      (tail_bins > 0 ? cnf_tail_smem_bytes(tail_bins, RK) : 0);
   if ((long long)smem > max_smem - 1024) return false;
   *smem_out = smem;
   return true;
@@ -581,8 +549,15 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
     }
 #undef RV
   }
-  if (ta.mode == CNF_METRICS_LOGITS) return launch_reg10<128, 8, 2, 2, CNF_METRICS_LOGITS>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
-  return launch_reg10<128, 8, 2, 2, CNF_METRICS_CALIBRATED>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st);
+#define RT(SPT, MB)                                                                                                       \
+  do {                                                                                                                    \
+    if (ta.mode == CNF_METRICS_LOGITS) return launch_reg10<128, SPT, 2, MB, CNF_METRICS_LOGITS>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st); \
+    return launch_reg10<128, SPT, 2, MB, CNF_METRICS_CALIBRATED>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st); \
+  } while (0)
+  if (variant == 4) RT(2, 3);       // the same tile sizes as the plain forward: 256 / 512 / 1024 samples
+  if (variant == 1) RT(4, 3);
+  RT(8, 2);
+#undef RT
 }
 
 // Fused NLL training step on the register-resident kernel; rows_used = partial rows written (one per warp).
@@ -591,7 +566,7 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
                     int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st) {
 #define TV(NT, SPT, U, MB)                                                                                           \
   do {                                                                                                               \
-    const size_t smem = smem_fwd + (size_t)((d.L * 10 + 3) / 4) * 4 * sizeof(int) + (size_t)3 * SPT * RD * NT * sizeof(float); \
+    const size_t smem = smem_fwd + (size_t)3 * SPT * RD * NT * sizeof(float);                                       \
     if ((long long)smem > max_smem - 1024) break;      /* this variant's plan does not fit: try the next smaller one */ \
     int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, U, MB>, smem);                                              \
     if (rc) return rc;                                                                                               \
