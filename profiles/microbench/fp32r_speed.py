@@ -17,10 +17,10 @@ eng = model.engine()
 eng.ensure(dev)
 N = int(os.environ.get('N', 10_000_000))
 x, _ = bench.synth_dev(N, 1, dev)
-names = {'off': 'generic flow_apply_kernel', '0': '128 thr x 8 u2 (2/SM)', '1': '128 x 8 u1', '2': '128 x 8 u4', '3': '64 x 8 (3/SM)',
-         '4': '128 x 10 u1', '5': '128 x 10 u2', '6': '256 x 8 (1/SM)', '7': '128 x 12 u1 (1/SM)', '8': '192 x 8 (1/SM)', '9': '128 x 6 (3/SM)'}
+names = {'off': 'generic flow_apply_kernel', '0': '128 thr x 8 (2 CTAs/SM)', '1': '128 x 4 (3/SM)', '2': '128 x 6 (3/SM)', '3': '256 x 8 (1/SM)',
+         '4': '128 x 2 (3/SM)', '5': '128 x 1', '6': '64 x 2', '7': '64 x 1'}
 ref = None
-for v in ['off'] + [str(i) for i in range(10)]:
+for v in ['off'] + [str(i) for i in range(8)]:
     os.environ['CNF_FP32R'] = v
     for inverse in (False, True):
         z, ld, _ = eng.apply(x, inverse=inverse)
