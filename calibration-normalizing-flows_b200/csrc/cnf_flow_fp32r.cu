@@ -593,7 +593,7 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
     case 2: TV(128, 8, 2, 1);
     case 4: TV(256, 6, 2, 1);
     case 5: TV(128, 4, 2, 2);
-    default: break;
+    default: break;        // (tried: 128 x 2, 256 x 4, 256 x 2 for 65k..160k samples -- never ahead of the tile kernel there)
   }
   {
     // 2048-sample tiles (256 x 8) unless 1536-sample tiles (256 x 6) need fewer or cheaper waves over the SMs

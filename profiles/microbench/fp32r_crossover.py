@@ -45,7 +45,7 @@ def t_train(n, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-sizes = [65536, 100_000, 131072, 200_000, 262144, 400_000, 524288, 1 << 20, 2 << 20, 4 << 20]
+sizes = [40_000, 65536, 100_000, 131072, 200_000, 262144, 400_000, 524288, 1 << 20, 4 << 20]
 fv = {'off': 'generic', '0': '128x8', '1': '128x4', '4': '128x2', '5': '128x1', '6': '64x2', '7': '64x1'}
 print('forward, us per call:  N ' + ' '.join('%9s' % v for v in fv.values()))
 for n in sizes:
@@ -54,7 +54,7 @@ for n in sizes:
         os.environ['CNF_FP32R'] = k
         row.append(t_fwd(n))
     print('%22d ' % n + ' '.join('%9.1f' % v for v in row), flush=True)
-tv = {'off': 'split', '0': '256x8', '2': '128x8', '4': '256x6', '5': '128x4'}
+tv = {'off': 'split', '0': 'auto', '2': '128x8', '4': '256x6', '5': '128x4'}
 print('training, us per fused fwd+bwd pass:  N ' + ' '.join('%9s' % v for v in tv.values()))
 for n in sizes:
     row = []
