@@ -23,6 +23,13 @@
 
 int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
 
+// Timing-only experiment switches (wrong results; profiles/microbench/build_variant.sh): bit 0 = weights are not
+// streamed after the first two phases, bit 1 = EPI1 does no work, bit 2 = no tile load / store,
+// bit 3 = no EPI2 math, bit 4 = no A1 build.
+#ifndef CNF_TCW_EXP
+#define CNF_TCW_EXP 0
+#endif
+
 namespace {
 
 constexpr int W_THREADS = 384;   // warps 0 / 3 MMA issuers (slot 0 / 1), 1 weight producer, 2 TMEM allocator, 4-7 / 8-11 epilogue
@@ -133,6 +140,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
           const int l = inverse ? p.L - 1 - li : li;
           for (int ph = 0; ph < n_ph; ++ph, ++g) {
             const int st = g & 1;
+            if ((CNF_TCW_EXP & 1) && g >= 2) continue;
             if (g >= 2) mbar_wait(w_empty + st, ((g >> 1) - 1) & 1);
             mbar_expect_tx(w_full + st, (uint32_t)p.phase_bytes);
             bulk_copy_g2s(smem + p.sm_ring + st * p.phase_bytes, blob + ((size_t)l * n_ph + ph) * p.phase_bytes,
@@ -166,6 +174,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         for (int li = 0; li < p.L; ++li) {
           if (!has_tile) {           // keep the ring's arrival count
             for (int ph = 0; ph < n_ph; ++ph, ++g) {
+              if ((CNF_TCW_EXP & 1) && g >= 2) continue;
               mbar_wait_backoff(w_full + (g & 1), (g >> 1) & 1);
               mbar_arrive(w_empty + (g & 1));
             }
@@ -173,7 +182,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
           }
           mbar_wait_backoff(a1_ready + s, lay_cnt & 1);
           ++lay_cnt;
-          mbar_wait_backoff(w_full + (g & 1), (g >> 1) & 1);
+          if (!(CNF_TCW_EXP & 1) || g < 2) mbar_wait_backoff(w_full + (g & 1), (g >> 1) & 1);
           tc_fence_after();
           gemm1(g);
           for (int ph = 0; ph < n_ph; ++ph, ++g) {
@@ -193,7 +202,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
             // this slot's GEMM1 of the next phase goes in right behind its GEMM2 (D1 is free once the GEMM2
             // ahead of it in the pipe has read it): the next EPI1 overlaps the other slot's tensor work
             if (ph + 1 < n_ph) {
-              mbar_wait_backoff(w_full + ((g + 1) & 1), ((g + 1) >> 1) & 1);
+              if (!(CNF_TCW_EXP & 1) || g + 1 < 2) mbar_wait_backoff(w_full + ((g + 1) & 1), ((g + 1) >> 1) & 1);
               tc_fence_after();
               gemm1(g + 1);
             }
@@ -217,29 +226,65 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
     const bool both = (NETS == 3);
     uint32_t lay_cnt = 0, ph_cnt = 0;
+    auto epi2_chunk = [&](const int qc, const int l, float& ld) {
+      const float* bl = bias + l * 2 * N2;
+      const int* trans = tab + p.tab_trans + l * D0;
+      uint32_t r1[16], r2[16];
+      tmem_ld16(tm + d2_col0 + qc, r1);
+      if (both) tmem_ld16(tm + d2_col0 + N2 + qc, r2);
+      tmem_wait_ld16(r1);
+      if (both) tmem_wait_ld16(r2);
+      // eight outputs at a time: every shared-memory load of the group is issued before its first store (bias and
+      // act share an element type, so the compiler cannot move a later output's loads above an earlier output's
+      // store itself, and one output at a time is a chain of dependent shared-memory round trips)
+#pragma unroll
+      for (int h = 0; h < 16; h += 8) {
+        int ps[8];
+        float xv[8], bs[8], bt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ps[i] = (qc + h + i < D0) ? trans[qc + h + i] * ACT_LD + t : t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = qc + h + i;
+          xv[i] = act[ps[i]];
+          bs[i] = (q < D0) ? bl[q] : 0.f;
+          bt[i] = (both && q < D0) ? bl[N2 + q] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float first = __uint_as_float(r1[h + i]) + bs[i];
+          const float second = both ? __uint_as_float(r2[h + i]) + bt[i] : 0.f;
+          const float sv = (NETS & 1) ? first : 0.f;
+          const float tv = both ? second : ((NETS & 2) ? first : 0.f);
+          if (qc + h + i < D0) {
+            if (!inverse) { xv[i] = xv[i] * expf(sv) + tv; ld += sv; }
+            else          { xv[i] = (xv[i] - tv) * expf(-sv); ld -= sv; }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (qc + h + i < D0) act[ps[i]] = xv[i];
+      }
+    };
     for (int64_t r = 0; r < nt[slot]; ++r) {
       const int64_t tile = blockIdx.x + (2 * r + slot) * (int64_t)G;
       const int64_t base = tile * TILE_M;
-      {
-        // coalesced loads, 10 in flight per thread, then the transposing stores
+      if (!(CNF_TCW_EXP & 4)) {
+        // the tile goes straight into the transposed layout with 4-byte cp.async copies (all of a thread's
+        // tile_elems / 128 copies in flight at once; rows past N are zero-filled): staging it through registers
+        // ten loads at a time cost 14 % of the kernel
         const float* gp = xin + base * K;
         const int64_t avail = (N - base) * (int64_t)K;
+        const uint32_t act_s = smem_u32(act);
         int s = s0, f = f0;
-        constexpr int U = 10;
-        for (int e0 = t; e0 < tile_elems; e0 += 128 * U) {
-          float v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int e = e0 + 128 * u;
-            v[u] = (e < tile_elems && e < avail) ? __ldg(gp + e) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (e0 + 128 * u < tile_elems) act[(inverse ? pi_last[f] : f) * ACT_LD + s] = v[u];
-            s += ds; f += df;
-            while (f >= K) { f -= K; ++s; }
-          }
+        for (int e = t; e < tile_elems; e += 128) {
+          const bool ok = e < avail;
+          cp_async4_zfill(act_s + (uint32_t)((inverse ? pi_last[f] : f) * ACT_LD + s) * 4u, ok ? gp + e : gp, ok ? 4u : 0u);
+          s += ds; f += df;
+          while (f >= K) { f -= K; ++s; }
         }
+        cp_async_commit();
+        cp_async_wait_all();
       }
       wg_sync(slot);
       float ld = 0.f;
@@ -267,6 +312,12 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         for (int ph = 0; ph < n_ph; ++ph, ++ph_cnt) {
           mbar_wait(d1_ready + slot, ph_cnt & 1);
           tc_fence_after();
+          if (CNF_TCW_EXP & 2) {
+            tc_fence_before();
+            mbar_arrive(a2_ready + 2 * slot);
+            mbar_arrive(a2_ready + 2 * slot + 1);
+            continue;
+          }
           uint32_t ra[32], rb[32], pk[16];
           tmem_ld32(tm, ra);
 #pragma unroll 1
@@ -287,36 +338,17 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
           }
         }
         // ---- EPI2: coupling update in fp32, 16 outputs at a time --------------------------------
+        // (unrolled so that the q < D0 guards of the compile-time shape are resolved at compile time: as
+        // per-output branches they serialised the sixteen outputs of a chunk)
         mbar_wait(d2_ready + slot, lay_cnt & 1);
         tc_fence_after();
-        const float* bl = bias + l * 2 * N2;
-        for (int qc = 0; qc < N2; qc += 16) {
-          uint32_t r1[16], r2[16];
-          tmem_ld16(tm + d2_col0 + qc, r1);
-          if (both) tmem_ld16(tm + d2_col0 + N2 + qc, r2);
-          tmem_wait_ld16(r1);
-          if (both) tmem_wait_ld16(r2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int q = qc + i;
-            if (q < D0) {
-              const float first = __uint_as_float(r1[i]) + bl[q];
-              const float second = both ? __uint_as_float(r2[i]) + bl[N2 + q] : 0.f;
-              const float sv = (NETS & 1) ? first : 0.f;
-              const float tv = both ? second : ((NETS & 2) ? first : 0.f);
-              const int ps = trans[q] * ACT_LD + t;
-              const float xv = act[ps];
-              float yv;
-              if (!inverse) { yv = xv * expf(sv) + tv; ld += sv; }
-              else          { yv = (xv - tv) * expf(-sv); ld -= sv; }
-              act[ps] = yv;
-            }
-          }
-        }
+        for (int qc = 0; qc < (SH ? 64 : 1); qc += 16) epi2_chunk(qc, l, ld);
+        if (!SH) for (int qc = 16; qc < N2; qc += 16) epi2_chunk(qc, l, ld);
       }
       if (base + t < N) logdet[base + t] = ld;
       wg_sync(slot);
-      {
+      if (!(CNF_TCW_EXP & 4)) {
         float* gp = zout + base * K;
         const int64_t avail = (N - base) * (int64_t)K;
         int s = s0, f = f0;

@@ -47,8 +47,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // for single-thread issuer / producer warps: back off between polls so the spinning warp does not
 // take issue slots from the epilogue warps that share its scheduler
+#ifndef CNF_BACKOFF_NS
+#define CNF_BACKOFF_NS 20
+#endif
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) __nanosleep(20);
+#if CNF_BACKOFF_NS > 0
+  while (!mbar_try(bar, parity)) __nanosleep(CNF_BACKOFF_NS);
+#else
+  while (!mbar_try(bar, parity)) {}
+#endif
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -165,6 +172,10 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+// 4-byte copy to a shared-memory address; src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst_saddr, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_saddr), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

@@ -23,7 +23,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
-__host__ __device__ inline uint32_t make_idesc(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
+__host__ __device__ inline uint32_t make_idesc(int N, int M = 128) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -38,6 +38,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // mode: 0 = 1x SS N=256 ; 1 = nk x TS N=16 one accumulator ; 2 = nk x TS N=16, 4 accumulators ;
 //       3 = nk x SS N=16 one accumulator ; 4 = nk x TS N=32 ; 5 = 1x SS N=256 followed by nk x TS N=16 (back to back)
 //       6 = nk x SS N=256 K=16 accumulate (plain GEMM pacing)
+//       7.. = nk x SS accumulate with the B image rotating over four 8 KB blocks (round 2: is the B port as
+//       narrow as the A port?): 7 = M64 N256, 8 = M128 N256, 9 = M64 N128, 10 = M64 N64, 11 = M64 N16
 __global__ void __launch_bounds__(128, 1) micro(int mode, int nk, int reps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -75,6 +77,29 @@ __global__ void __launch_bounds__(128, 1) micro(int mode, int nk, int reps, long
         for (int j = 0; j < nk; ++j) mma_ts(tm + 128, tm + j * 8, make_desc(sb + j * 512, 256, 128), make_idesc(16), j > 0);
       } else if (mode == 6) {
         for (int j = 0; j < nk; ++j) mma_ss(tm, make_desc(sb, 128, 256), make_desc(sb + 8192, 128, 256), make_idesc(256), j > 0);
+      } else if (mode >= 7 && mode <= 11) {
+        const int M = mode == 8 ? 128 : 64;
+        const int N = mode == 7 || mode == 8 ? 256 : mode == 9 ? 128 : mode == 10 ? 64 : 16;
+        const uint32_t id = make_idesc(N, M);
+        for (int j = 0; j < nk; ++j) mma_ss(tm, make_desc(sb + (j & 1) * 4096, 128, 256), make_desc(sb + 8192 + (j & 3) * 8192, 128, 256), id, j > 0);
+      }
+      else if (mode == 12) {          // C4 GEMM1: nk x (4 k-steps SS M128 N128)
+        for (int j = 0; j < nk; ++j)
+          for (int k = 0; k < 4; ++k) mma_ss(tm, make_desc(sb + k * 4096, 2048, 128), make_desc(sb + 16384 + (j & 1) * 32768 + k * 4096, 2048, 128), make_idesc(128), k > 0);
+      } else if (mode == 13) {        // C4 GEMM2: nk x (8 k-steps TS M128 N64)
+        for (int j = 0; j < nk; ++j)
+          for (int k = 0; k < 8; ++k) mma_ts(tm + 128, tm + k * 8, make_desc(sb + 32768 + (j & 1) * 32768 + k * 2048, 1024, 128), make_idesc(64), k > 0);
+      } else if (mode == 14) {        // C4 phase: GEMM1 then GEMM2, nk phases back to back
+        for (int j = 0; j < nk; ++j) {
+          for (int k = 0; k < 4; ++k) mma_ss(tm + (j & 1) * 256, make_desc(sb + k * 4096, 2048, 128), make_desc(sb + 16384 + (j & 1) * 32768 + k * 4096, 2048, 128), make_idesc(128), k > 0);
+          for (int k = 0; k < 8; ++k) mma_ts(tm + 128 + (j & 1) * 256, tm + (j & 1) * 256 + k * 8, make_desc(sb + 32768 + (j & 1) * 32768 + k * 2048, 1024, 128), make_idesc(64), k > 0);
+        }
+      } else if (mode == 15) {        // N sweep, TS M128 K16: nk MMAs of N = 32 * reps_n (passed through nk high bits)
+        const int N = (nk >> 8) * 8, cnt = nk & 255;
+        for (int j = 0; j < cnt; ++j) mma_ts(tm + 256, tm + (j & 7) * 8, make_desc(sb + 32768 + (j & 3) * 8192, 128, 256), make_idesc(N), j > 0);
+      } else if (mode == 16) {        // N sweep, SS M128 K16
+        const int N = (nk >> 8) * 8, cnt = nk & 255;
+        for (int j = 0; j < cnt; ++j) mma_ss(tm + 256, make_desc(sb + (j & 3) * 4096, 128, 256), make_desc(sb + 32768 + (j & 3) * 8192, 128, 256), make_idesc(N), j > 0);
       }
       tc_commit(&bar);
       const long long t1 = clock64();
@@ -122,7 +147,14 @@ int main() {
       {0, 1, "1x SS M128 N256 K16"},          {1, 16, "16x TS N16, one accumulator"}, {1, 2, "2x TS N16, one accumulator"},
       {1, 1, "1x TS N16"},                    {2, 16, "16x TS N16, 4 accumulators"},  {3, 16, "16x SS N16, one accumulator"},
       {4, 8, "8x TS N32"},                    {5, 16, "SS N256 then 16x TS N16"},     {6, 16, "16x SS N256 accumulate"},
-      {6, 64, "64x SS N256 accumulate"},      {1, 64, "64x TS N16 one accumulator"}};
+      {6, 64, "64x SS N256 accumulate"},      {1, 64, "64x TS N16 one accumulator"},
+      {7, 64, "64x SS M64 N256 (rotating B)"}, {8, 64, "64x SS M128 N256 (rotating B)"}, {9, 64, "64x SS M64 N128"},
+      {10, 64, "64x SS M64 N64"},             {11, 64, "64x SS M64 N16"},             {7, 16, "16x SS M64 N256"},
+      {12, 16, "16x C4 GEMM1 (4x SS N128)"},  {13, 16, "16x C4 GEMM2 (8x TS N64)"},   {14, 16, "16x C4 phase (GEMM1+GEMM2)"},
+      {15, (2 << 8) | 64, "64x TS N16"},      {15, (4 << 8) | 64, "64x TS N32"},      {15, (8 << 8) | 64, "64x TS N64"},
+      {15, (12 << 8) | 64, "64x TS N96"},     {15, (16 << 8) | 64, "64x TS N128"},    {15, (32 << 8) | 64, "64x TS N256"},
+      {16, (2 << 8) | 64, "64x SS N16"},      {16, (8 << 8) | 64, "64x SS N64"},      {16, (16 << 8) | 64, "64x SS N128"},
+      {16, (24 << 8) | 64, "64x SS N192"},    {16, (32 << 8) | 64, "64x SS N256"}};
   for (auto& c : cases) {
     for (int i = 0; i < 8; ++i) out[i] = 0;
     micro<<<1, 128, 131072>>>(c.mode, c.nk, 50, out);
