@@ -372,8 +372,8 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
               const float sv = (SH || (p.nets & 1)) ? first : 0.f;
               const float tv = both ? second : ((p.nets & 2) ? first : 0.f);
               float yv;
-              if (!inverse) { yv = xv[q] * expf(sv) + tv; ld += sv; }
-              else          { yv = (xv[q] - tv) * expf(-sv); ld -= sv; }
+              if (!inverse) { yv = xv[q] * tc_exp(sv) + tv; ld += sv; }
+              else          { yv = (xv[q] - tv) * tc_exp(-sv); ld -= sv; }
               act[ps[q]] = yv;
               if (TAPE) svs[q] = sv;
             }

@@ -19,13 +19,18 @@
 #include <cstdlib>
 
 #include "cnf_common.h"
+// e^s as ex2.approx(s * log2 e) in this kernel: 50 outputs per sample and layer make the coupling epilogue its
+// largest serial section (+2.6 % at C4); relative error ~1e-6, far inside the bf16 path's stated 1e-2
+#ifndef CNF_TC_FASTEXP
+#define CNF_TC_FASTEXP 1
+#endif
 #include "cnf_tc_ptx.cuh"
 
 int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n, cudaStream_t st);
 
 // Timing-only experiment switches (wrong results; profiles/microbench/build_variant.sh): bit 0 = weights are not
 // streamed after the first two phases, bit 1 = EPI1 does no work, bit 2 = no tile load / store,
-// bit 3 = no EPI2 math, bit 4 = no A1 build.
+// bit 3 = no EPI2 math, bit 4 = no A1 build; bit 5 (results stay right) = the scale half of EPI2 stays at the layer boundary.
 #ifndef CNF_TCW_EXP
 #define CNF_TCW_EXP 0
 #endif
@@ -43,12 +48,13 @@ struct TcwDims {
   int phase_bytes, b1_bytes;        // one phase of weights: B1 block then B2 block
   int bias_off, n_bf16, n_f32, blob_bytes;
   int tab_pi, tab_cond, tab_trans, n_tables;
-  int sm_ring, sm_bias, sm_tab, sm_slot, sm_slot_stride, sm_act, sm_bar, sm_total;
+  int sm_ring, sm_bias, sm_tab, sm_tp, sm_slot, sm_slot_stride, sm_act, sm_bar, sm_total;
 };
 
 bool tcw_dims(const CnfDims& d, TcwDims* t) {
   if (d.m != 1 || d.n_nets < 1) return false;
   if (d.d1 + 1 > 64 || d.d0 > 64) return false;
+  if (d.K * ACT_LD > 65535) return false;            // act offsets are kept as uint16
   t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->H = d.H[0]; t->nets = d.nets; t->n_nets = d.n_nets;
   t->K1 = cnf_round_up(d.d1 + 1, 16);
   t->N2 = cnf_round_up(d.d0, 16);
@@ -67,6 +73,7 @@ bool tcw_dims(const CnfDims& d, TcwDims* t) {
   t->sm_ring = off; off += 2 * t->phase_bytes;
   t->sm_bias = off; off += (t->n_f32 * 4 + 127) / 128 * 128;
   t->sm_tab = off; off += (d.n_tables * 4 + 127) / 128 * 128;
+  t->sm_tp = off; off += (d.L * t->N2 * 2 + 127) / 128 * 128;   // act offsets (uint16) of the transformed slots, padded to N2
   t->sm_slot = off;
   t->sm_act = HB * t->K1 * 2;                       // A1 tile first, then the fp32 tile
   t->sm_slot_stride = t->sm_act + (d.K * ACT_LD * 4 + 127) / 128 * 128;
@@ -97,6 +104,13 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   for (int i = tid; i < p.n_tables; i += W_THREADS) tab[i] = tables[i];
+  // EPI2 needs no guards: a padded output (q >= d0: zero weights and biases, so s = t = 0 exactly) "updates" the
+  // layer's first conditioning slot, which no real output touches, with x * e^0 + 0 = x
+  unsigned short* tp = reinterpret_cast<unsigned short*>(smem + p.sm_tp);
+  for (int i = tid; i < p.L * p.N2; i += W_THREADS) {
+    const int l = i / p.N2, q = i - l * p.N2;
+    tp[i] = (unsigned short)((q < p.d0 ? tables[p.tab_trans + l * p.d0 + q] : tables[p.tab_cond + l * p.d1]) * ACT_LD);
+  }
   {
     const float* gb = reinterpret_cast<const float*>(blob + p.bias_off);
     for (int i = tid; i < p.n_f32; i += W_THREADS) bias[i] = __ldg(gb + i);
@@ -126,7 +140,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
   const int64_t nt[2] = {(mine + 1) / 2, mine / 2};
   const int64_t rounds = nt[0];
   const int n_ph = SH ? 8 : p.n_ph, n_blk = SH ? 4 : p.n_blk;
-  const int K1 = SH ? 64 : p.K1, N2 = SH ? 64 : p.N2, D0 = SH ? 50 : p.d0, D1 = SH ? 50 : p.d1, KK = SH ? 100 : p.K;
+  const int K1 = SH ? 64 : p.K1, N2 = SH ? 64 : p.N2, D1 = SH ? 50 : p.d1, KK = SH ? 100 : p.K;
   const int NETS = SH ? 3 : p.nets;
   const int k1_steps = K1 / 16;
   const int d2_col0 = 128;
@@ -226,44 +240,49 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
     const int s0 = t / K, f0 = t - s0 * K, ds = TILE_M / K, df = TILE_M - ds * K;
     const bool both = (NETS == 3);
     uint32_t lay_cnt = 0, ph_cnt = 0;
-    auto epi2_chunk = [&](const int qc, const int l, float& ld) {
-      const float* bl = bias + l * 2 * N2;
-      const int* trans = tab + p.tab_trans + l * D0;
+    // EPI2 on outputs qc .. qc+15.  mode 0: the whole coupling update; 1: its scale half (x *= e^s, log-det);
+    // 2: its shift half (x += t).  Eight outputs at a time, every shared-memory load of the group issued before
+    // its first store: bias and act share an element type, so the compiler cannot move a later output's loads
+    // above an earlier output's store itself, and one output at a time is a chain of dependent shared-memory
+    // round trips (27 % of the kernel when it was written that way).  No guards: see tp.
+    auto epi2_chunk = [&](const int qc, const int l, float& ld, const int mode) {
+      const float* bl = bias + l * 2 * N2 + qc;
+      const unsigned short* tpl = tp + l * N2 + qc;
       uint32_t r1[16], r2[16];
-      tmem_ld16(tm + d2_col0 + qc, r1);
-      if (both) tmem_ld16(tm + d2_col0 + N2 + qc, r2);
-      tmem_wait_ld16(r1);
-      if (both) tmem_wait_ld16(r2);
-      // eight outputs at a time: every shared-memory load of the group is issued before its first store (bias and
-      // act share an element type, so the compiler cannot move a later output's loads above an earlier output's
-      // store itself, and one output at a time is a chain of dependent shared-memory round trips)
+      if (mode != 2) tmem_ld16(tm + d2_col0 + qc, r1);
+      if (mode == 2 || (mode == 0 && both)) tmem_ld16(tm + d2_col0 + N2 + qc, r2);
+      if (mode != 2) tmem_wait_ld16(r1);
+      if (mode == 2 || (mode == 0 && both)) tmem_wait_ld16(r2);
 #pragma unroll
       for (int h = 0; h < 16; h += 8) {
         int ps[8];
         float xv[8], bs[8], bt[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ps[i] = (qc + h + i < D0) ? trans[qc + h + i] * ACT_LD + t : t;
+        for (int i = 0; i < 8; ++i) ps[i] = (int)tpl[h + i] + t;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int q = qc + h + i;
           xv[i] = act[ps[i]];
-          bs[i] = (q < D0) ? bl[q] : 0.f;
-          bt[i] = (both && q < D0) ? bl[N2 + q] : 0.f;
+          bs[i] = (mode != 2) ? bl[h + i] : 0.f;
+          bt[i] = (mode == 2 || (mode == 0 && both)) ? bl[N2 + h + i] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float first = __uint_as_float(r1[h + i]) + bs[i];
-          const float second = both ? __uint_as_float(r2[h + i]) + bt[i] : 0.f;
-          const float sv = (NETS & 1) ? first : 0.f;
-          const float tv = both ? second : ((NETS & 2) ? first : 0.f);
-          if (qc + h + i < D0) {
-            if (!inverse) { xv[i] = xv[i] * expf(sv) + tv; ld += sv; }
-            else          { xv[i] = (xv[i] - tv) * expf(-sv); ld -= sv; }
+          if (mode == 1) {
+            const float sv = __uint_as_float(r1[h + i]) + bs[i];
+            xv[i] *= tc_exp(sv); ld += sv;
+          } else if (mode == 2) {
+            xv[i] += __uint_as_float(r2[h + i]) + bt[i];
+          } else {
+            const float first = __uint_as_float(r1[h + i]) + bs[i];
+            const float second = both ? __uint_as_float(r2[h + i]) + bt[i] : 0.f;
+            const float sv = (NETS & 1) ? first : 0.f;
+            const float tv = both ? second : ((NETS & 2) ? first : 0.f);
+            if (!inverse) { xv[i] = xv[i] * tc_exp(sv) + tv; ld += sv; }
+            else          { xv[i] = (xv[i] - tv) * tc_exp(-sv); ld -= sv; }
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (qc + h + i < D0) act[ps[i]] = xv[i];
+        for (int i = 0; i < 8; ++i) act[ps[i]] = xv[i];
       }
     };
     for (int64_t r = 0; r < nt[slot]; ++r) {
@@ -291,24 +310,39 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
       for (int li = 0; li < p.L; ++li, ++lay_cnt) {
         const int l = inverse ? p.L - 1 - li : li;
         const int* cond = tab + p.tab_cond + l * D1;
-        const int* trans = tab + p.tab_trans + l * D0;
         // ---- A1 row: K1 bf16 = conditioning logits, the constant one, zero padding ------------
-        for (int kb = 0; kb < K1 / 8; ++kb) {
-          float u[8];
+        // (sixteen gathers per pass, all issued before the pass's two stores; for the compile-time shape the
+        // k < D1 selects are resolved at compile time)
+        auto a1_pass = [&](const int kb) {
+          float u[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const int k = kb * 8 + i;
             u[i] = (k < D1) ? act[cond[k] * ACT_LD + t] : (k == D1 ? 1.f : 0.f);
           }
-          uint4 v;
+          uint4 v, w;
           v.x = pack_bf16(u[0], u[1]); v.y = pack_bf16(u[2], u[3]);
           v.z = pack_bf16(u[4], u[5]); v.w = pack_bf16(u[6], u[7]);
+          w.x = pack_bf16(u[8], u[9]); w.y = pack_bf16(u[10], u[11]);
+          w.z = pack_bf16(u[12], u[13]); w.w = pack_bf16(u[14], u[15]);
           *reinterpret_cast<uint4*>(a1_row + kb * W_LBO1) = v;
+          *reinterpret_cast<uint4*>(a1_row + (kb + 1) * W_LBO1) = w;
+        };
+        if (!(CNF_TCW_EXP & 16)) {
+#pragma unroll
+          for (int kb = 0; kb < (SH ? 8 : 2); kb += 2) a1_pass(kb);
+          if (!SH) for (int kb = 2; kb < K1 / 8; kb += 2) a1_pass(kb);
         }
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(a1_ready + slot);
         // ---- phases: EPI1 on the 128 hidden units of (net, block) ------------------------------
+        // Forward with both nets: the scale half of the coupling update does not wait for the layer's last MMA.
+        // D2_s is complete when the first t-net phase's D1 arrives (the commit behind that GEMM1 covers every
+        // earlier MMA of the issuer), so it runs in 16-output chunks behind the EPI1s of the t-net phases, where
+        // this warpgroup otherwise waits for the tensor pipe; only "+ t" is left for the layer boundary.
+        const bool early = !inverse && both && !(CNF_TCW_EXP & 32);
+        const int e_chunks = N2 / 16, cpp = (e_chunks + n_blk - 1) / n_blk;
         for (int ph = 0; ph < n_ph; ++ph, ++ph_cnt) {
           mbar_wait(d1_ready + slot, ph_cnt & 1);
           tc_fence_after();
@@ -336,15 +370,16 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
             tc_fence_before();
             mbar_arrive(a2_ready + 2 * slot + (c >> 6));
           }
+          if (early && ph >= n_blk)
+            for (int ch = (ph - n_blk) * cpp; ch < min((ph - n_blk + 1) * cpp, e_chunks); ++ch) epi2_chunk(ch * 16, l, ld, 1);
         }
-        // ---- EPI2: coupling update in fp32, 16 outputs at a time --------------------------------
-        // (unrolled so that the q < D0 guards of the compile-time shape are resolved at compile time: as
-        // per-output branches they serialised the sixteen outputs of a chunk)
+        // ---- EPI2: coupling update in fp32, 16 outputs at a time (what is left of it) -----------
         mbar_wait(d2_ready + slot, lay_cnt & 1);
         tc_fence_after();
-#pragma unroll
-        for (int qc = 0; qc < (SH ? 64 : 1); qc += 16) epi2_chunk(qc, l, ld);
-        if (!SH) for (int qc = 16; qc < N2; qc += 16) epi2_chunk(qc, l, ld);
+        if (!(CNF_TCW_EXP & 8)) {
+          if (early) for (int qc = 0; qc < N2; qc += 16) epi2_chunk(qc, l, ld, 2);
+          else       for (int qc = 0; qc < N2; qc += 16) epi2_chunk(qc, l, ld, 0);
+        }
       }
       if (base + t < N) logdet[base + t] = ld;
       wg_sync(slot);

@@ -165,6 +165,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// e^x of the coupling update in the bf16 kernels: expf (8 instructions), or with CNF_TC_FASTEXP ex2.approx(x*log2e)
+#ifndef CNF_TC_FASTEXP
+#define CNF_TC_FASTEXP 0
+#endif
+__device__ __forceinline__ float tc_exp(float x) {
+#if CNF_TC_FASTEXP
+  return __expf(x);
+#else
+  return expf(x);
+#endif
+}
 __device__ __forceinline__ void wg_sync(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
