@@ -46,6 +46,18 @@
 #include "cnf_tc_dims.h"
 #include "cnf_tc_ptx.cuh"
 
+// Timing-only experiment switches (wrong results; profiles/microbench/build_variant.sh): bit 0 = E1 does no work,
+// bit 1 = no E0 math, bit 2 = no loss head, bit 3 = no E5, bit 4 = no T4 MMAs, bit 5 = no T2 MMAs.
+#ifndef CNF_TCB_EXP
+#define CNF_TCB_EXP 0
+#endif
+#ifndef CNF_TCB_STAGGER
+#define CNF_TCB_STAGGER 0
+#endif
+#ifndef CNF_TCB_BATON
+#define CNF_TCB_BATON 1
+#endif
+
 namespace {
 
 constexpr int TB_SLOTS = 2;                       // tiles in flight per CTA, one epilogue warpgroup each
@@ -140,6 +152,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   uint64_t* w_full = bars + 4 * TB_SLOTS;
   uint64_t* w_empty = w_full + MAX_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + MAX_STAGES);
+  volatile uint32_t* mid = tmem_ptr + 4;          // [slot] net phases whose first half this slot has passed
   constexpr int MMA_WARP0 = 4 * TB_SLOTS, PROD_WARP = 4 * TB_SLOTS + TB_SLOTS;
 
   // ---- one-time setup ---------------------------------------------------------------------
@@ -150,6 +163,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
   }
   for (int i = tid; i < 4 * TB_SLOTS * p.L * 16; i += TB_THREADS) gb2[i] = 0.f;
   if (tid == 0) {
+    mid[0] = 0u; mid[1] = 0u;
     for (int sl = 0; sl < TB_SLOTS; ++sl) {
       mbar_init(ag_ready + sl, 128);
       mbar_init(t1_done + sl, 1);
@@ -228,6 +242,14 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       const uint32_t id_t2 = make_idesc_ex(16, 0, 1);
       const uint32_t id_t4 = make_idesc_ex(16, 1, 1);
       uint32_t lc = 0, hc = 0;
+      // Anti-phase baton (TB_SLOTS == 2).  Started together the two slots stay in phase: both run their E1s at
+      // the same time and then queue their T4 blocks behind each other, and the step costs the sum of epilogue
+      // and tensor time instead of their maximum.  So slot 1 starts net phase k only once slot 0 is past the first
+      // half of its net phase k, and slot 0 starts k once slot 1 is past the first half of k-1 (counters in shared
+      // memory, capped by the partner's total so that a slot without tiles never blocks the other).
+      const int64_t cnt_other = (my_tiles + sl) / 2;                    // tiles of the other slot
+      const uint32_t np_other = (uint32_t)(cnt_other * p.L * n_ph);
+      uint32_t kk = 0;
       for (int64_t i = 0; i < npairs; ++i) {
         const bool has_tile = TB_SLOTS * i + sl < my_tiles;
         for (int li = 0; li < p.L; ++li) {
@@ -252,6 +274,10 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             const uint64_t w2_mn = make_desc(b2p, 128, 256);
             // B1 image (hid, feat) read MN-major over feat: S_mn = 128, S_k = 256; k-step (16 hidden) = 512 B
             const uint64_t w1_mn = make_desc(b1p, 256, 128);
+            if (CNF_TCB_BATON) {
+              const uint32_t need = min(sl == 0 ? kk : kk + 1, np_other);
+              while (mid[sl ^ 1] < need) {}
+            }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               if (hf >= n_half) break;
@@ -264,8 +290,9 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
               // ---- T2 (half): GU += ghm . W1p
               mbar_wait_backoff(hg_ready + sl, (hc - 1) & 1);
               tc_fence_after();
+              if (CNF_TCB_BATON && hf == (CNF_TCB_BATON == 2 ? n_half - 1 : 0)) mid[sl] = ++kk;
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
+              for (int jj = 0; jj < ((CNF_TCB_EXP & 32) ? 0 : 4); ++jj) {
                 const int j = h0 / 16 + jj;
                 if (j < (h0 + w) / 16)
                   mma_ss(tm + COL_GU, ghm_k + (uint64_t)(j * 16), w1_mn + (uint64_t)(j * 32), id_t2, (ph > 0 || j > 0) ? 1u : 0u);
@@ -274,9 +301,9 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             // ---- T4: weight gradients, contraction over the tile's 128 samples (8 k-steps of 16)
             const uint32_t acc = tmem_base + COL_ACC + (l * n_ph + ph) * 16;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mma_ss(acc, h_mn + j * img_kstep, g2p_mn[ph] + j * rec_kstep, id_t4, 1u);
+            for (int j = 0; j < ((CNF_TCB_EXP & 16) ? 0 : 8); ++j) mma_ss(acc, h_mn + j * img_kstep, g2p_mn[ph] + j * rec_kstep, id_t4, 1u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mma_ss(acc, ghm_mn + j * img_kstep, a1_mn + j * rec_kstep, id_t4, 1u);
+            for (int j = 0; j < ((CNF_TCB_EXP & 16) ? 0 : 8); ++j) mma_ss(acc, ghm_mn + j * img_kstep, a1_mn + j * rec_kstep, id_t4, 1u);
             tc_commit(t4_done + sl);
           }
           tc_commit(w_empty + st);           // this slot no longer reads the stage once everything above completed
@@ -330,6 +357,14 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
     };
     const int64_t tile0 = blockIdx.x + (int64_t)sl * G, tstep = (int64_t)TB_SLOTS * G;
     if (tile0 < ntiles) fetch_tile(tile0);
+    // Slot 1 starts half a net phase behind slot 0.  Started together, the two slots stay in phase: both run their
+    // E1s at the same time (sharing the TMEM read port) and then queue their T4 blocks behind each other, so the
+    // step costs the sum of epilogue and tensor time instead of their maximum.  The offset persists (equal
+    // periods): +13 % on the backward kernel (profiles/microbench/tcb_speed.py; 1500 clk: nothing, 3000-6500: the same).
+    if (sl == 1 && CNF_TCB_STAGGER > 0 && my_tiles >= 2 * TB_SLOTS) {
+      const long long c0 = clock64();
+      while (clock64() - c0 < CNF_TCB_STAGGER) {}
+    }
     for (int64_t tile = tile0; tile < ntiles; tile += tstep) {
       const int64_t base = tile * TILE_M;
       const int64_t n = base + t;
@@ -353,7 +388,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
       if (tile + tstep < ntiles) fetch_tile(tile + tstep);
       // ---- loss head (calibrators.py:288-291), one thread per sample ----------------------------
       float gld = 0.f;
-      {
+      if (!(CNF_TCB_EXP & 4)) {
         float mx = -INFINITY;
         for (int j = 0; j < K; ++j) mx = fmaxf(mx, act[j * TILE_M + t]);
         float se = 0.f;
@@ -387,23 +422,40 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           const int* trans = tab + p.tab_trans + l * D0;
           // ---- E0 -------------------------------------------------------------------------------
           {
-            const float xt[8] = {tq[0].x, tq[0].y, tq[0].z, tq[0].w, tq[1].x, tq[1].y, tq[1].z, tq[1].w};
-            const float sv[8] = {tq[2].x, tq[2].y, tq[2].z, tq[2].w, tq[3].x, tq[3].y, tq[3].z, tq[3].w};
             float gv[16];                      // 0..7: gradient on the first present net's outputs, 8..15: second
 #pragma unroll
+            for (int q = 0; q < 16; ++q) gv[q] = 0.f;
+            if (!(CNF_TCB_EXP & 2)) {
+            const float xt[8] = {tq[0].x, tq[0].y, tq[0].z, tq[0].w, tq[1].x, tq[1].y, tq[1].z, tq[1].w};
+            const float sv[8] = {tq[2].x, tq[2].y, tq[2].z, tq[2].w, tq[3].x, tq[3].y, tq[3].z, tq[3].w};
+            // the gathers of all transformed slots first, then the math, then the stores: interleaved, every load
+            // waited for the store in front of it (act, gact and the loads share an element type)
+            int psq[8];
+            float gyq[8];
+#pragma unroll
             for (int q = 0; q < 8; ++q) {
-              gv[q] = 0.f; gv[8 + q] = 0.f;
+              psq[q] = (q < D0) ? trans[q] * TILE_M + t : t;
+              gyq[q] = (q < D0) ? gact[psq[q]] : 0.f;
+            }
+            float esq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              gv[q] = 0.f; gv[8 + q] = 0.f; esq[q] = 1.f;
               if (q < D0) {
-                const int ps = trans[q] * TILE_M + t;
-                const float gy = gact[ps];
+                const float gy = gyq[q];
                 const float es = has_s ? expf(sv[q]) : 1.f;
                 const float gs = gy * xt[q] * es + gld;
-                act[ps] = xt[q];               // step the tile state back to the input of layer l
-                gact[ps] = gy * es;
+                esq[q] = es;
                 if (has_s) { gv[q] = gs; gv[8 + q] = has_t ? gy : 0.f; }
                 else       { gv[q] = gy; }
               }
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < D0) {
+                act[psq[q]] = xt[q];           // step the tile state back to the input of layer l
+                gact[psq[q]] = gyq[q] * esq[q];
+              }
             if (l > 0) fetch_tape(l - 1, n);   // in flight while this layer's MMAs and epilogues run
             uint4 v;
             v.x = pack_bf16(gv[0], gv[1]); v.y = pack_bf16(gv[2], gv[3]);
@@ -424,6 +476,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
               v.z |= (wi == 2) ? ob : 0u; v.w |= (wi == 3) ? ob : 0u;
             }
             *reinterpret_cast<uint4*>(rec_row + OFF_A1) = v;
+            } else if (l > 0) fetch_tape(l - 1, n);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(ag_ready + sl);
@@ -490,9 +543,11 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
                   sts128(ghm_row + off, vg[0], vg[1], vg[2], vg[3]);
                 }
               };
+              if (!(CNF_TCB_EXP & 1)) {
               tmem_ld16(tm + COL_D1, rdA);
               tmem_ld16(tm + COL_GH, rgA);
-              for (int c = 0; c < w; c += 32) {
+              }
+              for (int c = 0; c < ((CNF_TCB_EXP & 1) ? 0 : w); c += 32) {
                 tmem_wait_ld16(rdA);
                 tmem_wait_ld16(rgA);
                 if (c + 16 < w) { tmem_ld16(tm + COL_D1 + c + 16, rdB); tmem_ld16(tm + COL_GH + c + 16, rgB); }
@@ -512,13 +567,20 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
           // ---- E5: gradient on the conditioning logits ---------------------------------------------
           mbar_wait(t4_done + sl, (pc - 1) & 1);
           tc_fence_after();
-          {
+          if (!(CNF_TCB_EXP & 8)) {
             uint32_t r[16];
             tmem_ld16(tm + COL_GU, r);
             tmem_wait_ld16(r);
+            int pk[8];
+            float gk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              pk[k] = (k < D1) ? cond[k] * TILE_M + t : t;
+              gk[k] = (k < D1) ? gact[pk[k]] : 0.f;
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (k < D1) gact[cond[k] * TILE_M + t] += __uint_as_float(r[k]);
+              if (k < D1) gact[pk[k]] = gk[k] + __uint_as_float(r[k]);
           }
           tc_fence_before();
         }
