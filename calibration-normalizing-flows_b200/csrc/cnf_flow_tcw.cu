@@ -31,6 +31,9 @@ int cnf_pack_bf16(const float* flat, const int32_t* gather, void* packed, int n,
 // Timing-only experiment switches (wrong results; profiles/microbench/build_variant.sh): bit 0 = weights are not
 // streamed after the first two phases, bit 1 = EPI1 does no work, bit 2 = no tile load / store,
 // bit 3 = no EPI2 math, bit 4 = no A1 build; bit 5 (results stay right) = the scale half of EPI2 stays at the layer boundary.
+#ifndef CNF_TCW_STAGGER
+#define CNF_TCW_STAGGER 0
+#endif
 #ifndef CNF_TCW_EXP
 #define CNF_TCW_EXP 0
 #endif
@@ -285,6 +288,9 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
         for (int i = 0; i < 8; ++i) act[ps[i]] = xv[i];
       }
     };
+#if CNF_TCW_STAGGER > 0
+    if (slot > 0) { const long long c0 = clock64(); while (clock64() - c0 < CNF_TCW_STAGGER) {} }
+#endif
     for (int64_t r = 0; r < nt[slot]; ++r) {
       const int64_t tile = blockIdx.x + (2 * r + slot) * (int64_t)G;
       const int64_t base = tile * TILE_M;

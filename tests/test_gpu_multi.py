@@ -79,10 +79,21 @@ def test_two_gpu_dp_matches_single_gpu(precision, tmp_path, cuda_device):
     # bf16: the two runs cut the samples into different tiles and accumulate in a different order
     assert rel_err(r[0]['grad'], flow.engine().flat_grad.cpu().numpy()) < (1e-4 if precision == 'fp32' else 1e-3)
     disp = flow.engine().flat.cpu().numpy() - g['flat']
-    # Adam normalises tiny gradients (update ~ lr * sign for entries whose gradient is noise): compare displacements
-    # (the gradients above agree to 1e-4; entries at rounding-noise level get +-lr whichever way the noise falls, and
-    #  the two runs sum the samples in different tiles)
-    assert rel_err(r[0]['flat'] - g['flat'], disp) < (5e-2 if precision == 'fp32' else 1e-1)
+    disp_dp = r[0]['flat'] - g['flat']
+    # Adam normalises every entry to ~lr per step, so an entry whose gradient is rounding noise can land +-lr either
+    # way, and the two runs sum the samples in different orders (different shards, and at this size the single-rank
+    # run takes the register-resident kernel while the half-size shards take the tile kernel): the entries whose
+    # gradient is well above the noise (> 1e-3 of the largest) -- where the update is a smooth function of the
+    # gradient -- must agree closely; of all entries at most 1 % may differ by more than 5 % of the largest
+    # displacement
+    scale = np.max(np.abs(disp))
+    diff = np.abs(disp_dp - disp)
+    gref = flow.engine().flat_grad.cpu().numpy()
+    solid = np.abs(gref) > 1e-3 * np.max(np.abs(gref))
+    tol = 5e-3 if precision == 'fp32' else 5e-2
+    assert solid.any() and np.max(diff[solid]) < tol * scale, np.max(diff[solid]) / scale
+    assert np.mean(diff > 0.05 * scale) < 0.01, np.mean(diff > 0.05 * scale)
+    assert np.all(disp_dp[gref == 0] == 0)
     # ... and the entries whose gradient is well above the noise agree tightly
     gref = flow.engine().flat_grad.cpu().numpy()
     solid = np.abs(gref) > 1e-3 * np.max(np.abs(gref))
