@@ -5,8 +5,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import torch, cnf_b200, bench
 dev = torch.device('cuda:0')
 n = 1 << 21
-xt, yt = bench.synth(n, 5000, dev)
-m = bench.make_weights(seed=2).to(dev)
+xt, yt = bench.synth_dev(n, 5000, dev)
+m = bench.make_model(seed=2, wmult=1.0).to(dev)
 tr = cnf_b200.FusedNLLTrainer(m.engine(), xt, yt, precision='bf16')
 for _ in range(3): tr.step()
 torch.cuda.synchronize()
