@@ -153,6 +153,9 @@ class StackEngine:
         self.device = device
         self.version += 1
         self.gather = torch.from_numpy(self._gather_host).to(device)
+        live = self._gather_host[self._gather_host >= 0]
+        # the one-launch optimiser tail (reduce_adam_pack) needs every live flat entry at exactly one packed position
+        self.gather_one_to_one = bool(live.size == np.unique(live).size)
         self.tables = torch.from_numpy(self._tables_host).to(device)
         self.packed = torch.empty(self.n_packed, dtype=torch.float32, device=device)
         self.packed_tc = None
@@ -366,7 +369,7 @@ class StackEngine:
         if loss_acc.dtype != torch.float64 or loss_acc.numel() < 4:
             raise ValueError('cnf_b200: loss_acc must be float64 [4]')
 
-    def _nll_step_tc(self, x, y, loss_acc, eps, gamma, n_total, with_grad):
+    def _nll_step_tc(self, x, y, loss_acc, eps, gamma, n_total, with_grad, reduce=True):
         if self.tc_train is None:
             raise NotImplementedError('cnf_b200: the bf16 tensor-core training path does not cover this flow shape '
                                       '(K=%d, hidden=%s, L=%d); use precision="fp32"' % (self.K, self.hidden, self.L))
@@ -387,12 +390,52 @@ class StackEngine:
                   _ptr(x), _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
                   ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials_tc) if with_grad else None,
                   _ptr(loss_acc), _ptr(self._train_ws), ctypes.c_int64(need), ctypes.byref(used), st)
-        if with_grad:
+        self.rows_used_tc = int(used.value)
+        if with_grad and reduce:
             _lib.call('cnf_grad_reduce_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc), used,
                       _ptr(self.gather_tcgrad), _ptr(self.flat_grad), st)
 
+    def tc_tail_maps(self):
+        """scatter_tc (flat entry -> its position in the tensor-core blob's gather map) on the device, or None when
+        the one-launch tail does not apply (no tensor-core training path, or a map that is not one-to-one)."""
+        if getattr(self, '_scatter_tc_dev', None) is not None and self._scatter_tc_dev.device == self.flat.device:
+            return self._scatter_tc_dev
+        if self.tc_train is None or self._gather_tc_host is None:
+            return None
+        if getattr(self, '_scatter_tc_host', None) is None:
+            gt, gg = np.asarray(self._gather_tc_host), np.asarray(self.tc_train[3])
+            pos = np.nonzero(gt >= 0)[0]
+            live_g = gg[gg >= 0]
+            ok = (np.unique(gt[pos]).size == pos.size) and (np.unique(live_g).size == live_g.size)
+            inv = np.full(self.n_flat, -1, dtype=np.int32)
+            inv[gt[pos]] = pos.astype(np.int32)
+            # every packed entry must receive its gradient through the tail (else its blob copy would go stale)
+            ok = ok and bool(np.all(np.isin(gt[pos], live_g)))
+            self._scatter_tc_host = inv if ok else False
+        if self._scatter_tc_host is False:
+            return None
+        self._scatter_tc_dev = torch.from_numpy(self._scatter_tc_host).to(self.flat.device)
+        return self._scatter_tc_dev
+
     @_guarded
-    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision='fp32'):
+    def reduce_adam_pack_tc(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """One-launch tail of a single-process bf16 Adam step (cnf_reduce_adam_pack_tc) behind
+        nll_step(precision='bf16', reduce=False)."""
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+            self.adam_t = 0
+        self.adam_t += 1
+        self.version += 1
+        _lib.call('cnf_reduce_adam_pack_tc', ctypes.byref(self.desc_tc), _ptr(self.partials_tc),
+                  ctypes.c_int64(self.rows_used_tc), _ptr(self.gather_tcgrad), _ptr(self.tc_tail_maps()),
+                  _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.packed_tc),
+                  ctypes.c_int64(self.adam_t), ctypes.c_float(lr), ctypes.c_float(betas[0]), ctypes.c_float(betas[1]),
+                  ctypes.c_float(eps), _stream(self.device))
+
+    @_guarded
+    def nll_step(self, x, y, loss_acc, eps=1e-7, gamma=1.0, n_total=None, with_grad=True, precision='fp32',
+                 reduce=True):
         """One fused forward+loss(+backward) pass over the local samples.  Accumulates the
         loss sums into loss_acc (float64 [4], device) and, with_grad, leaves
         d(sum loss)/n_total in self.flat_grad.  precision='bf16' runs the tcgen05 forward and
@@ -401,7 +444,7 @@ class StackEngine:
         n_total = N if n_total is None else n_total
         self._check_batch(x, y, loss_acc)
         if precision == 'bf16':
-            return self._nll_step_tc(x, y, loss_acc, eps, gamma, n_total, with_grad)
+            return self._nll_step_tc(x, y, loss_acc, eps, gamma, n_total, with_grad, reduce)
         st = _stream(x.device)
         if with_grad:
             self._want_partials()
@@ -410,9 +453,27 @@ class StackEngine:
                   _ptr(y), ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma),
                   ctypes.c_float(1.0 / max(n_total, 1)), _ptr(self.partials) if with_grad else None,
                   _ptr(loss_acc), ctypes.byref(used), st)
-        if with_grad:
+        self.rows_used = int(used.value)
+        if with_grad and reduce:          # (reduce=False: the caller follows with reduce_adam_pack)
             _lib.call('cnf_grad_reduce_rows', ctypes.byref(self.desc), _ptr(self.partials), used, _ptr(self.gather),
                       _ptr(self.flat_grad), st)
+
+    @_guarded
+    def reduce_adam_pack(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """The tail of a single-process fp32 Adam step in ONE launch (cnf_reduce_adam_pack_rows): the partial rows of
+        the nll_step(reduce=False) before it are summed, Adam (no weight decay) updates the parameters and the packed
+        fp32 blob is refreshed; bitwise what cnf_grad_reduce_rows + adam + pack produce."""
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+            self.adam_t = 0
+        self.adam_t += 1
+        self.version += 1
+        _lib.call('cnf_reduce_adam_pack_rows', ctypes.byref(self.desc), _ptr(self.partials),
+                  ctypes.c_int64(self.rows_used), _ptr(self.gather), _ptr(self.flat), _ptr(self.flat_grad),
+                  _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.packed), ctypes.c_int64(self.adam_t),
+                  ctypes.c_float(lr), ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps),
+                  _stream(self.device))
 
     @_guarded
     def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):

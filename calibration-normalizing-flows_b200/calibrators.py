@@ -179,7 +179,24 @@ class FusedNLLTrainer:
         n_tot = self.n_total if n_batch_total is None else n_batch_total
         nvtx = torch.cuda.nvtx
         self.loss_acc.zero_()
+        # single process, Adam without weight decay (the reference's defaults, calibrators.py:259): the partial
+        # reduction, the update and the repack are ONE launch behind the training kernel
+        fused_tail = (self.dist is None and self.optim == 'adam' and self.wd == 0.0 and xb.shape[0] > 0
+                      and getattr(e, 'adam_step_dev', None) is None and hasattr(e, 'reduce_adam_pack'))
+        if fused_tail:
+            fused_tail = (e.tc_tail_maps() is not None) if self.precision == 'bf16' else getattr(e, 'gather_one_to_one', False)
         nvtx.range_push('cnf.fwd_bwd')
+        if fused_tail:
+            e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision,
+                       reduce=False)
+            nvtx.range_pop()
+            nvtx.range_push('cnf.optim')
+            if self.precision == 'bf16':
+                e.reduce_adam_pack_tc(self.lr, self.betas, self.adam_eps)
+            else:
+                e.reduce_adam_pack(self.lr, self.betas, self.adam_eps)
+            nvtx.range_pop()
+            return
         e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision)
         nvtx.range_pop()
         if self.dist is not None:

@@ -85,3 +85,17 @@ static inline int cnf_round_up(int x, int m) { return (x + m - 1) / m * m; }
       return CNF_E_CUDA;                                                            \
     }                                                                               \
   } while (0)
+
+#ifdef __CUDACC__
+// torch.optim.Adam's update of one entry (no weight decay), every rounding spelled out so that each kernel that
+// applies it -- cnf_adam_step, cnf_adam_step_dev and the one-launch tails -- produces the same bits
+// (calibrators.py:259, 295: exp_avg.lerp_(grad, 1-b1); exp_avg_sq.mul_(b2).addcmul_(grad, grad, 1-b2);
+//  p -= (lr/bc1) * exp_avg / (sqrt(exp_avg_sq)/sqrt(bc2) + eps)).
+__device__ __forceinline__ float cnf_adam_entry(float p, float g, float& m, float& v, float lr_over_bc1,
+                                                float inv_sqrt_bc2, float b1, float b2, float eps) {
+  m = __fmaf_rn(__fsub_rn(g, m), 1.f - b1, m);
+  v = __fmaf_rn(__fmul_rn(1.f - b2, g), g, __fmul_rn(v, b2));
+  const float denom = __fmaf_rn(sqrtf(v), inv_sqrt_bc2, eps);
+  return __fmaf_rn(-lr_over_bc1, __fdiv_rn(m, denom), p);
+}
+#endif

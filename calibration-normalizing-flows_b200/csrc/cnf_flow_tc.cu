@@ -43,6 +43,11 @@ int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables
 
 namespace {
 
+// Timing-only experiment switches (wrong results): bit 0 = EPI1 does no work, bit 1 = no EPI2 math, bit 2 = no tile
+// load / store, bit 3 = no GEMM2 MMAs.
+#ifndef CNF_TC_EXP
+#define CNF_TC_EXP 0
+#endif
 #ifndef CNF_TC_SLOTS
 #define CNF_TC_SLOTS 3
 #endif
@@ -212,7 +217,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {     // GEMM2 k-steps of this net accumulate into the shared 16-column D2
               const int j = 4 * g + jj;
-              if (j < Hp / 16)
+              if (j < Hp / 16 && !(CNF_TC_EXP & 8))
                 mma_ts(tm + d2_col, tm + j * 8, db2 + (uint64_t)((ph * (Hp / 16) + j) * 32), idesc2,
                        (ph > 0 || j > 0) ? 1u : 0u);
             }
@@ -262,7 +267,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         cp_async_wait_all();
         wg_sync(slot);
         int s = s0, f = f0;
-        for (int e = t; e < tile_elems; e += 128) {
+        for (int e = t; e < ((CNF_TC_EXP & 4) ? 0 : tile_elems); e += 128) {
           act[(inverse ? pi_last[f] : f) * TILE_M + s] = raw_in[e];
           s += ds; f += df;
           if (f >= K) { f -= K; ++s; }
@@ -335,6 +340,11 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         for (int ph = 0; ph < n_ph; ++ph, ++cnt) {
           mbar_wait(d1_ready + slot, cnt & 1);
           tc_fence_after();
+          if (CNF_TC_EXP & 1) {
+            tc_fence_before();
+            for (int c = 0; c < Hp; c += 64) mbar_arrive(a2_ready + 2 * slot + (c >> 6));
+            continue;
+          }
           uint32_t ra[32], rb[32], pk[16];
           tmem_ld32(tm, ra);
           for (int c = 0; c < Hp; c += 64) {
@@ -358,7 +368,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         // ---- EPI2: coupling update in fp32 --------------------------------------------------
         mbar_wait(d2_ready + slot, it & 1);
         tc_fence_after();
-        {
+        if (!(CNF_TC_EXP & 2)) {
           uint32_t r[16];
           float svs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           tmem_ld16(tm + d2_col, r);
@@ -394,7 +404,7 @@ flow_tc_kernel(TcDims p, const uint8_t* __restrict__ blob, const int* __restrict
         tail_row<TAIL == 0 ? CNF_METRICS_LOGITS : TAIL>(get, base + t, K, ta, tsm, cache, a_nll, a_correct, a_n);
       }
       // ---- act -> row-major staging -> coalesced global store ---------------------------------
-      if (!TAIL || zout != nullptr) {
+      if ((!TAIL || zout != nullptr) && !(CNF_TC_EXP & 4)) {
         int s = s0, f = f0;
         const bool full = io16 && (base + TILE_M <= N);
         float* gp = zout + base * K;

@@ -40,6 +40,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdlib>
 
 #include "cnf_common.h"
@@ -653,6 +654,40 @@ __global__ void tcb_reduce_kernel(const float* __restrict__ partials, const int*
 }
 
 
+// The tail of a single-GPU bf16 training step in one launch: tcb_reduce_kernel's sum (same order), Adam on the flat
+// entry the gradient entry maps to (no weight decay: entries without a gradient stay as they are), and the entry's
+// place in the tensor-core blob refreshed (bf16 image element or fp32 last-layer bias).
+__global__ void tcb_reduce_adam_pack_kernel(const float* __restrict__ partials, const int* __restrict__ gather,
+                                            const int* __restrict__ scatter, float* __restrict__ flat,
+                                            float* __restrict__ flat_grad, float* __restrict__ m, float* __restrict__ v,
+                                            uint8_t* __restrict__ blob, int n_bf16, int bias_off, int n_grad, int rows,
+                                            float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_grad) return;
+  const int g = gather[i];
+  if (g < 0) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4) {
+    a0 += partials[(size_t)(r + 0) * n_grad + i];
+    a1 += partials[(size_t)(r + 1) * n_grad + i];
+    a2 += partials[(size_t)(r + 2) * n_grad + i];
+    a3 += partials[(size_t)(r + 3) * n_grad + i];
+  }
+  for (; r < rows; ++r) a0 += partials[(size_t)r * n_grad + i];
+  const float gi = (a0 + a1) + (a2 + a3);
+  flat_grad[g] = gi;
+  float mi = m[g], vi = v[g];
+  const float pn = cnf_adam_entry(flat[g], gi, mi, vi, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+  m[g] = mi; v[g] = vi;
+  flat[g] = pn;
+  const int j = scatter[g];
+  if (j >= 0) {
+    if (j < n_bf16) reinterpret_cast<__nv_bfloat16*>(blob)[j] = __float2bfloat16_rn(pn);
+    else            reinterpret_cast<float*>(blob + bias_off)[j - n_bf16] = pn;
+  }
+}
+
 int tb_sms() {
   CnfDevInfo di;
   return cnf_dev_info(&di) == CNF_OK ? di.sms : -1;
@@ -773,6 +808,25 @@ extern "C" int cnf_grad_reduce_tc(const cnf_flow_desc* desc, const float* grad_p
   cudaStream_t st = (cudaStream_t)stream;
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
   tcb_reduce_kernel<<<(t.n_grad + 127) / 128, 128, 0, st>>>(grad_partials_tc, gather_tcgrad, flat_grad, t.n_grad, (int)rows_used);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_reduce_adam_pack_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, int64_t rows_used,
+                                       const int32_t* gather_tcgrad, const int32_t* scatter_tc, float* flat,
+                                       float* flat_grad, float* exp_avg, float* exp_avg_sq, void* packed_tc, int64_t step,
+                                       float lr, float beta1, float beta2, float eps, void* stream) {
+  CnfDims d; TbDims t; TcDims f;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!tb_dims(d, &t) || !cnf_tc_dims(d, &f)) { cnf_set_error("shape not covered by the tensor-core training kernel"); return CNF_E_UNSUPPORTED; }
+  if (!grad_partials_tc || !gather_tcgrad || !scatter_tc || !flat || !flat_grad || !exp_avg || !exp_avg_sq || !packed_tc ||
+      rows_used < 1 || rows_used > CNF_TCB_ROWS || step < 1) { cnf_set_error("cnf_reduce_adam_pack_tc: null pointer, bad row count or step < 1"); return CNF_E_ARG; }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  tcb_reduce_adam_pack_kernel<<<(t.n_grad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      grad_partials_tc, gather_tcgrad, scatter_tc, flat, flat_grad, exp_avg, exp_avg_sq, (uint8_t*)packed_tc, f.n_bf16,
+      f.bias_off, t.n_grad, (int)rows_used, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -69,6 +69,49 @@ grad_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ g
   }
 }
 
+// The whole tail of a single-GPU fp32 training step in one launch: the partial-row reduction above, Adam on the
+// entry the column maps to, and the refreshed packed weight (the gather map is one-to-one on live entries, checked
+// by the caller).  Same summation order and the same update expression as grad_reduce_kernel + adam_kernel +
+// gather_kernel, so the results are bitwise those of the three launches.  Entries of flat the kernels never read
+// (masked weight columns) have zero gradient and, without weight decay, Adam leaves them untouched: they are skipped.
+__global__ void __launch_bounds__(32 * RED_RG)
+reduce_adam_pack_kernel(const float* __restrict__ partials, const int* __restrict__ gather, float* __restrict__ flat,
+                        float* __restrict__ flat_grad, float* __restrict__ m, float* __restrict__ v,
+                        float* __restrict__ packed, int n_packed, int rows, float lr_over_bc1, float inv_sqrt_bc2,
+                        float b1, float b2, float eps) {
+  __shared__ float part[RED_RG][32];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (i < n_packed) {
+    for (int r = rg; r < rows; r += 8 * RED_RG) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = r + k * RED_RG;
+        if (rr < rows) a[k] += partials[(size_t)rr * n_packed + i];
+      }
+    }
+  }
+  part[rg][c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (rg == 0 && i < n_packed) {
+    const int g = gather[i];
+    if (g >= 0) {
+      float gi = 0.f;
+#pragma unroll
+      for (int k = 0; k < RED_RG; ++k) gi += part[k][c];
+      flat_grad[g] = gi;
+      float mi = m[g], vi = v[g];
+      const float pn = cnf_adam_entry(flat[g], gi, mi, vi, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+      m[g] = mi; v[g] = vi;
+      flat[g] = pn;
+      packed[i] = pn;
+    }
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2,
                             float eps, float wd) {
@@ -77,12 +120,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   float gi = g[i];
   const float pi = p[i];
   if (wd != 0.f) gi = fmaf(wd, pi, gi);
-  // torch: exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  float mi = m[i], vi = v[i];
+  p[i] = cnf_adam_entry(pi, gi, mi, vi, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
   m[i] = mi; v[i] = vi;
-  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-  p[i] = pi - lr_over_bc1 * (mi / denom);
 }
 
 // CUDA-graph friendly Adam: the step count lives in device memory, so a captured training step can be
@@ -105,11 +145,9 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   float gi = g[i];
   const float pi = p[i];
   if (wd != 0.f) gi = fmaf(wd, pi, gi);
-  const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  float mi = m[i], vi = v[i];
+  p[i] = cnf_adam_entry(pi, gi, mi, vi, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
   m[i] = mi; v[i] = vi;
-  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-  p[i] = pi - lr_over_bc1 * (mi / denom);
 }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd) {
@@ -163,6 +201,24 @@ extern "C" int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad
   CNF_CHECK_CUDA(cudaMemsetAsync(flat_grad, 0, (size_t)d.n_flat * sizeof(float), st));
   if (rows_used == 0) return CNF_OK;
   grad_reduce_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, st>>>(grad_partials, gather, flat_grad, d.n_packed, (int)rows_used);
+  CNF_CHECK_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+extern "C" int cnf_reduce_adam_pack_rows(const cnf_flow_desc* desc, const float* grad_partials, int64_t rows_used,
+                                        const int32_t* gather, float* flat, float* flat_grad, float* exp_avg,
+                                        float* exp_avg_sq, float* packed, int64_t step, float lr, float beta1,
+                                        float beta2, float eps, void* stream) {
+  CnfDims d;
+  int rc = cnf_make_dims(desc, &d);
+  if (rc) return rc;
+  if (!grad_partials || !gather || !flat || !flat_grad || !exp_avg || !exp_avg_sq || !packed || step < 1) { cnf_set_error("cnf_reduce_adam_pack_rows: null pointer or step < 1"); return CNF_E_ARG; }
+  if (rows_used < 1 || rows_used > d.grad_rows_max) { cnf_set_error("cnf_reduce_adam_pack_rows: rows_used %lld out of range", (long long)rows_used); return CNF_E_ARG; }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  reduce_adam_pack_kernel<<<(d.n_packed + 31) / 32, 32 * RED_RG, 0, (cudaStream_t)stream>>>(
+      grad_partials, gather, flat, flat_grad, exp_avg, exp_avg_sq, packed, d.n_packed, (int)rows_used,
+      (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }

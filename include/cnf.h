@@ -177,6 +177,23 @@ int cnf_flow_backward_rows(const cnf_flow_desc* desc, const void* packed, const 
                            float* grad_partials, int64_t N, int64_t* rows_used, void* stream);
 int cnf_grad_reduce_rows(const cnf_flow_desc* desc, const float* grad_partials, int64_t rows_used,
                          const int32_t* gather, float* flat_grad, void* stream);
+/* The tail of a single-GPU fp32 Adam step in ONE launch: cnf_grad_reduce_rows, then torch.optim.Adam (no weight decay:
+ * calibrators.py:259 defaults) on every entry a partial column maps to, then the refreshed entry of `packed`
+ * (= cnf_grad_reduce_rows + cnf_adam_step + cnf_pack_weights, bitwise).  Replaces loss.backward()'s gradient
+ * accumulation + optimizer.step() (calibrators.py:293-295).  `gather` must be one-to-one on its entries >= 0 and
+ * `packed` must have been fully packed once; flat_grad entries the kernels never touch are left as they are (zero
+ * them once); step is 1-based. */
+int cnf_reduce_adam_pack_rows(const cnf_flow_desc* desc, const float* grad_partials, int64_t rows_used,
+                              const int32_t* gather, float* flat, float* flat_grad, float* exp_avg,
+                              float* exp_avg_sq, float* packed, int64_t step, float lr, float beta1, float beta2,
+                              float eps, void* stream);
+/* The same one-launch tail for the tensor-core training path: cnf_grad_reduce_tc + cnf_adam_step + cnf_pack_weights_tc.
+ * scatter_tc: int32 [n_flat], the position of each flat entry in the gather map of cnf_plan_build_tc (-1: not packed);
+ * both maps must be one-to-one on their live entries. */
+int cnf_reduce_adam_pack_tc(const cnf_flow_desc* desc, const float* grad_partials_tc, int64_t rows_used,
+                            const int32_t* gather_tcgrad, const int32_t* scatter_tc, float* flat, float* flat_grad,
+                            float* exp_avg, float* exp_avg_sq, void* packed_tc, int64_t step, float lr, float beta1,
+                            float beta2, float eps, void* stream);
 /* torch.optim.Adam (L2 weight decay, bias correction as torch); step is 1-based. */
 int cnf_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,

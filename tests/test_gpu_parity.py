@@ -195,6 +195,38 @@ def test_fused_adam_and_sgd_vs_torch_optim(name, cuda_device):
     assert rel_err(flat - g['flat'], g['sgd2_flat'] - g['flat']) < 2e-3
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name', ['c2_nvp_k10', 'c1_nice_k3', 'nvp_k7_randflip'])
+def test_one_launch_optimiser_tail_is_bitwise_the_three_launch_tail(name, precision, cuda_device):
+    """cnf_reduce_adam_pack_rows / cnf_reduce_adam_pack_tc (reduce + Adam + repack in one launch) against
+    cnf_grad_reduce_* + cnf_adam_step + cnf_pack_weights* on the same partial rows."""
+    import torch
+    from cnf_b200 import FusedNLLTrainer
+    g = load_golden('flow_' + name)
+    x = torch.from_numpy(g['x']).to(cuda_device)
+    y = torch.from_numpy(g['y']).to(cuda_device)
+    state = []
+    for fused in (True, False):
+        flow = build_flow_from_golden(g, cuda_device)
+        e = flow.engine()
+        tr = FusedNLLTrainer(e, x, y, precision=precision)
+        if precision == 'bf16':
+            assert e.tc_tail_maps() is not None
+            if not fused:
+                e._scatter_tc_host, e._scatter_tc_dev = False, None      # step() falls back to the separate launches
+        else:
+            assert e.gather_one_to_one
+            if not fused:
+                e.gather_one_to_one = False
+        for _ in range(3):
+            tr.step()
+        blob = e.packed_tc if precision == 'bf16' else e.packed
+        state.append([t.detach().cpu().numpy().copy() for t in (e.flat, e.flat_grad, e.adam_m, e.adam_v, blob)])
+        assert e.adam_t == 3
+    for what, a, b in zip(('flat', 'flat_grad', 'adam_m', 'adam_v', 'packed'), *state):
+        assert np.array_equal(a, b), (what, int(np.sum(a != b)), float(np.max(np.abs(a.astype(np.float64) - b))))
+
+
 def test_metrics_vs_reference_golden(cuda_device):
     import cnf_b200
     from cnf_b200.utils import metrics as M
