@@ -243,3 +243,30 @@ def test_rows_aware_training_entry_points_validate_arguments_without_a_device():
     rc = lib.cnf_nll_train_step_rows(ctypes.byref(desc16), one, one, one, one, 8, 1e-7, 1.0, 0.125, one, one,
                                      ctypes.byref(used), None)
     assert rc == -4 and b'fp32' in lib.cnf_last_error()
+
+
+def test_one_launch_optimiser_tails_validate_arguments_without_a_device():
+    """cnf_reduce_adam_pack_rows / cnf_reduce_adam_pack_tc reject null pointers, row counts outside the partial
+    buffer, step < 1 and shapes outside the tensor-core training coverage before any CUDA call."""
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)          # never dereferenced: validation fails first
+    f = ctypes.c_float
+    desc, _keep = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_FP32)
+    info, _, _ = plan_host(10, 6, [128], True, True)
+    ok_tail = (f(1e-3), f(0.9), f(0.999), f(1e-8), None)
+    assert lib.cnf_reduce_adam_pack_rows(ctypes.byref(desc), None, 4, one, one, one, one, one, one, 1, *ok_tail) == -1
+    assert lib.cnf_reduce_adam_pack_rows(ctypes.byref(desc), one, 4, one, one, one, one, one, None, 1, *ok_tail) == -1
+    assert lib.cnf_reduce_adam_pack_rows(ctypes.byref(desc), one, 4, one, one, one, one, one, one, 0, *ok_tail) == -1
+    assert b'step' in lib.cnf_last_error()
+    assert lib.cnf_reduce_adam_pack_rows(ctypes.byref(desc), one, 0, one, one, one, one, one, one, 1, *ok_tail) == -1
+    assert lib.cnf_reduce_adam_pack_rows(ctypes.byref(desc), one, info.n_grad_rows + 1, one, one, one, one, one, one, 1,
+                                         *ok_tail) == -1
+    assert b'out of range' in lib.cnf_last_error()
+    desc16, _k16 = _lib.make_desc(10, 6, [128], True, True, _lib.PREC_BF16_TC)
+    assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(desc16), one, 4, one, None, one, one, one, one, one, 1, *ok_tail) == -1
+    assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(desc16), one, 161, one, one, one, one, one, one, one, 1, *ok_tail) == -1
+    assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(desc16), one, 4, one, one, one, one, one, one, one, 0, *ok_tail) == -1
+    wide, _kw = _lib.make_desc(100, 8, [512], True, True, _lib.PREC_BF16_TC)
+    assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(wide), one, 4, one, one, one, one, one, one, one, 1, *ok_tail) == -4
