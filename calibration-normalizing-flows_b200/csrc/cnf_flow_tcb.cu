@@ -277,7 +277,7 @@ flow_tcb_kernel(TbDims p, const uint8_t* __restrict__ blob, const int* __restric
             const uint64_t w1_mn = make_desc(b1p, 256, 128);
             if (CNF_TCB_BATON) {
               const uint32_t need = min(sl == 0 ? kk : kk + 1, np_other);
-              while (mid[sl ^ 1] < need) {}
+              while (mid[sl ^ 1] < need) __nanosleep(20);
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
