@@ -291,6 +291,7 @@ flow_tcw_kernel(TcwDims p, const uint8_t* __restrict__ blob, const int* __restri
 #if CNF_TCW_STAGGER > 0
     if (slot > 0) { const long long c0 = clock64(); while (clock64() - c0 < CNF_TCW_STAGGER) {} }
 #endif
+
     for (int64_t r = 0; r < nt[slot]; ++r) {
       const int64_t tile = blockIdx.x + (2 * r + slot) * (int64_t)G;
       const int64_t base = tile * TILE_M;
