@@ -316,8 +316,26 @@ class NvpCouplingLayer(nn.Module):
         return x, ld.squeeze()
 
 
+def _check_conditioner(net):
+    """The fused kernels evaluate Linear-ReLU-...-Linear conditioners (what the reference's coupling layer builds,
+    flows/flows.py:76-79 with flows/utils.py:10).  Anything else must fail loudly, not silently run as ReLU."""
+    import torch.nn.functional as F
+    if not isinstance(net, nn.Module):
+        return                                    # absent net (scale=False / shift=False)
+    act = getattr(net, 'activation', None)
+    if not (act is F.relu or act is torch.relu or isinstance(act, nn.ReLU)):
+        raise NotImplementedError('cnf_b200: the fused coupling kernels evaluate ReLU conditioners only (the '
+                                  'reference\'s NvpCouplingLayer never builds another one); got activation=%r' % (act,))
+    if not hasattr(net, 'canonical_parameters') or not all(isinstance(l, nn.Linear) for l in net.layers):
+        raise NotImplementedError('cnf_b200: a coupling layer\'s s / t must be cnf_b200.flows.utils.MLP instances '
+                                  '(stacks of nn.Linear), got %s' % type(net).__name__)
+
+
 def build_engine(layers):
     first = layers[0]
+    for lay in layers:
+        _check_conditioner(lay.s)
+        _check_conditioner(lay.t)
     perms = [lay.perm_list() for lay in layers] if any(lay.random_flip for lay in layers) else None
     return StackEngine(first.dim, first.hidden_size, first.has_scale, first.has_shift, perms,
                        [lay.canonical_parameters() for lay in layers])

@@ -270,3 +270,19 @@ def test_one_launch_optimiser_tails_validate_arguments_without_a_device():
     assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(desc16), one, 4, one, one, one, one, one, one, one, 0, *ok_tail) == -1
     wide, _kw = _lib.make_desc(100, 8, [512], True, True, _lib.PREC_BF16_TC)
     assert lib.cnf_reduce_adam_pack_tc(ctypes.byref(wide), one, 4, one, one, one, one, one, one, one, 1, *ok_tail) == -4
+
+
+def test_non_relu_conditioners_fail_loudly():
+    """A conditioner with another activation (or a foreign module as s / t) must not silently run as ReLU."""
+    import torch
+    import cnf_b200
+    from cnf_b200.flows.flows import build_engine
+    from cnf_b200.flows.utils import MLP
+    lay = cnf_b200.NvpCouplingLayer(6, [8])
+    lay.s = MLP(6, [8], activation=torch.tanh, wscale=0.001)
+    with pytest.raises(NotImplementedError, match='ReLU'):
+        build_engine([lay])
+    lay = cnf_b200.NvpCouplingLayer(6, [8])
+    lay.t = torch.nn.Sequential(torch.nn.Linear(6, 6))
+    with pytest.raises(NotImplementedError):
+        build_engine([lay])
