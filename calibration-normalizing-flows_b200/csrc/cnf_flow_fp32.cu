@@ -2020,7 +2020,7 @@ int set_smem(Kern k, size_t bytes) { return cnf_kernel_smem(k, bytes); }
 
 // register-resident kernel for K = 10 (cnf_flow_fp32r.cu)
 bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const float* x, const float* z, int tail_bins,
-                         int max_smem, size_t* smem_out);
+                         int max_smem, size_t* smem_out, bool two_ok);
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
@@ -2043,7 +2043,7 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   {
     const char* sw = cnf_switch(CNF_SW_FP32R);
     size_t smem_r = 0;
-    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r)) {
+    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r, true)) {
       const int variant = sw ? atoi(sw) : (N >= 240000 ? 0 : (N >= 113000 ? 1 : 4));
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, variant, st);
     }
@@ -2128,7 +2128,7 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   {
     size_t smem_r = 0;
     const char* sw = cnf_switch(CNF_SW_FP32R);
-    if (N >= (sw ? 1 : 65536) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r))
+    if (N >= (sw ? 1 : 65536) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r, true))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms,
                              N >= 240000 ? 0 : (N >= 113000 ? 1 : 4), st);
   }
@@ -2190,7 +2190,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000)) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
-    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r)) {
+    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r, false)) {
       rc = cnf_fp32r_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_r, g_num_sms,
                            g_max_smem, sw ? atoi(sw) : 0, rows_used, st);
       if (rc != CNF_E_SMEM) return rc;      // (too many layers for its shared-memory plan: the tile kernels below)

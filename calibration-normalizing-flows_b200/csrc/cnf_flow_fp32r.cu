@@ -23,30 +23,57 @@ namespace {
 
 constexpr int RK = 10, RD = 5;          // classes, half split
 
+// one hidden unit for one sample: out += W2[:, h] * relu(b1[h] + W1[h, :] . in)
+__device__ __forceinline__ void unit_fma(const float4& v0, const float4& v1, const float4& v2, const float (&in)[RD],
+                                         float (&out)[RD]) {
+  float a = fmaf(v0.x, in[0], v1.y);
+  a = fmaf(v0.y, in[1], a);
+  a = fmaf(v0.z, in[2], a);
+  a = fmaf(v0.w, in[3], a);
+  a = fmaf(v1.x, in[4], a);
+  const float r = fmaxf(a, 0.f);
+  out[0] = fmaf(v1.z, r, out[0]);
+  out[1] = fmaf(v1.w, r, out[1]);
+  out[2] = fmaf(v2.x, r, out[2]);
+  out[3] = fmaf(v2.y, r, out[3]);
+  out[4] = fmaf(v2.z, r, out[4]);
+}
+
 // one conditioner net for this thread's SPT samples: out[k][q] = b2[q] + sum_h W2[q][h] * relu(b1[h] + sum_j W1[h][j] c[k][j])
-template <int SPT, int U>
-__device__ __forceinline__ void net_eval(const float4* __restrict__ w, const float* __restrict__ b2, int Hp,
+// M2 (two hidden layers, the first of at most five units -- the reference's default conditioner hidden_size=[5, 5],
+// flows/flows.py:69): the first hidden layer is materialised in registers (five units per sample, records
+// [W1(5) | b1 | 0 0] in front of the net's unit records) and takes the place of c in the stream over the second one.
+template <int SPT, int U, bool M2 = false>
+__device__ __forceinline__ void net_eval(const float4* __restrict__ w, const float* __restrict__ b2, int Hn,
                                          const float (&c)[SPT][RD], float (&out)[SPT][RD]) {
 #pragma unroll
   for (int k = 0; k < SPT; ++k)
 #pragma unroll
     for (int q = 0; q < RD; ++q) out[k][q] = b2[q];
+  float h1[M2 ? SPT : 1][RD];
+  if (M2) {
+#pragma unroll
+    for (int i = 0; i < RD; ++i) {
+      const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        float a = fmaf(v0.x, c[k][0], v1.y);
+        a = fmaf(v0.y, c[k][1], a);
+        a = fmaf(v0.z, c[k][2], a);
+        a = fmaf(v0.w, c[k][3], a);
+        a = fmaf(v1.x, c[k][4], a);
+        h1[M2 ? k : 0][i] = fmaxf(a, 0.f);
+      }
+    }
+    w += 2 * RD;
+  }
 #pragma unroll U
-  for (int h = 0; h < Hp; ++h) {
+  for (int h = 0; h < Hn; ++h) {
     const float4 v0 = w[3 * h], v1 = w[3 * h + 1], v2 = w[3 * h + 2];
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
-      float a = fmaf(v0.x, c[k][0], v1.y);
-      a = fmaf(v0.y, c[k][1], a);
-      a = fmaf(v0.z, c[k][2], a);
-      a = fmaf(v0.w, c[k][3], a);
-      a = fmaf(v1.x, c[k][4], a);
-      const float r = fmaxf(a, 0.f);
-      out[k][0] = fmaf(v1.z, r, out[k][0]);
-      out[k][1] = fmaf(v1.w, r, out[k][1]);
-      out[k][2] = fmaf(v2.x, r, out[k][2]);
-      out[k][3] = fmaf(v2.y, r, out[k][3]);
-      out[k][4] = fmaf(v2.z, r, out[k][4]);
+      if constexpr (M2) unit_fma(v0, v1, v2, h1[k], out[k]);
+      else              unit_fma(v0, v1, v2, c[k], out[k]);
     }
   }
 }
@@ -54,28 +81,29 @@ __device__ __forceinline__ void net_eval(const float4* __restrict__ w, const flo
 // one coupling layer: c conditions, t is transformed in place (flows/flows.py:105-109 / :119-125).  One net's outputs
 // are consumed before the other net runs (forward: scale first, t*e^s then + shift; inverse: shift first, (t - shift)
 // then * e^-s), so only one [SPT][5] output block is live at a time.
-template <int SPT, int U>
+template <int SPT, int U, bool M2 = false>
 __device__ __forceinline__ void layer_eval(const float4* __restrict__ w, const float* __restrict__ b2, int Hp, int inverse,
                                            const float (&c)[SPT][RD], float (&t)[SPT][RD], float (&ld)[SPT]) {
   float o[SPT][RD];
+  const int ns4 = 3 * Hp + (M2 ? 2 * RD : 0);               // float4 per net: [first-layer records] unit records
   if (!inverse) {
-    net_eval<SPT, U>(w, b2, Hp, c, o);                       // s
+    net_eval<SPT, U, M2>(w, b2, Hp, c, o);                   // s
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
       for (int q = 0; q < RD; ++q) { t[k][q] *= expf(o[k][q]); ld[k] += o[k][q]; }
-    net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);          // shift
+    net_eval<SPT, U, M2>(w + ns4, b2 + 8, Hp, c, o);         // shift
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
       for (int q = 0; q < RD; ++q) t[k][q] += o[k][q];
   } else {
-    net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);          // shift
+    net_eval<SPT, U, M2>(w + ns4, b2 + 8, Hp, c, o);         // shift
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
       for (int q = 0; q < RD; ++q) t[k][q] -= o[k][q];
-    net_eval<SPT, U>(w, b2, Hp, c, o);                       // s
+    net_eval<SPT, U, M2>(w, b2, Hp, c, o);                   // s
 #pragma unroll
     for (int k = 0; k < SPT; ++k)
 #pragma unroll
@@ -88,10 +116,14 @@ __device__ __forceinline__ void layer_eval(const float4* __restrict__ w, const f
 // transformed half (even layers condition on slots 5..9, odd ones on 0..4).  maps[l][0..4] = packed input index of
 // conditioning slot e, maps[l][5..9] = packed output index of transformed slot e (from the index tables; formed first
 // so that the copy below reads the packed blob with h fastest, i.e. coalesced, and never searches).
-template <int R_NT>
+template <int R_NT, bool M2 = false>
 __device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const float* __restrict__ packed,
                                                     const int* __restrict__ tables, float* wf, float* b2s, int* maps, int tid) {
-  const int Hp = d.Hp[0], L = d.L;
+  // M2: per net 5 first-layer records of 8 floats [W1 of slot 0..4 | b1 | 0 0], then one 12-float record per unit of
+  // the SECOND hidden layer (true width, not padded) [Wm from first-layer unit 0..4 | bm | W3 of slot 0..4 | 0]
+  const int Hp = M2 ? d.H[1] : d.Hp[0], L = d.L;
+  const int pre = M2 ? 8 * RD : 0;                         // floats in front of a net's unit records
+  const int last = M2 ? 2 : 1;                             // index of the last Linear
   for (int i = tid; i < L * 10; i += R_NT) {
     const int l = i / 10, e = i - l * 10;
     const int* cond = tables + d.tab_cond + l * RD;
@@ -104,6 +136,7 @@ __device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const floa
   }
   __syncthreads();
   const int per_net = 12 * Hp;
+  const int Hrow = M2 ? d.Hp[1] : d.Hp[0];                 // row length of the packed matrices the unit records read
   for (int i = tid; i < L * 2 * per_net; i += R_NT) {
     const int ln = i / per_net, r = i - ln * per_net;      // ln = l * 2 + net
     const int e = r / Hp, h = r - e * Hp;                  // h fastest: coalesced reads of the packed rows
@@ -111,20 +144,41 @@ __device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const floa
     const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
     const int* mp = maps + l * 10;
     float v = 0.f;
-    if (e < 5) v = __ldg(Wn + d.w_off[0] + mp[e] * Hp + h);
-    else if (e == 5) v = __ldg(Wn + d.b_off[0] + h);
-    else if (e < 11) v = __ldg(Wn + d.w_off[1] + mp[e - 1] * Hp + h);
-    wf[((size_t)ln * Hp + h) * 12 + e] = v;
+    if (M2) {
+      if (e < 5) v = e < d.H[0] ? __ldg(Wn + d.w_off[1] + e * Hrow + h) : 0.f;      // middle Linear [in][out]
+      else if (e == 5) v = __ldg(Wn + d.b_off[1] + h);
+      else if (e < 11) v = __ldg(Wn + d.w_off[2] + mp[e - 1] * Hrow + h);
+    } else {
+      if (e < 5) v = __ldg(Wn + d.w_off[0] + mp[e] * Hrow + h);
+      else if (e == 5) v = __ldg(Wn + d.b_off[0] + h);
+      else if (e < 11) v = __ldg(Wn + d.w_off[1] + mp[e - 1] * Hrow + h);
+    }
+    wf[(size_t)ln * (pre + per_net) + pre + (size_t)h * 12 + e] = v;
+  }
+  if constexpr (M2) {
+    for (int i = tid; i < L * 2 * pre; i += R_NT) {
+      const int ln = i / pre, r = i - ln * pre;
+      const int e = r / RD, u = r - e * RD;                // u = first-layer unit
+      const int l = ln >> 1, net = ln & 1;
+      const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
+      const int* mp = maps + l * 10;
+      float v = 0.f;
+      if (u < d.H[0]) {
+        if (e < 5) v = __ldg(Wn + d.w_off[0] + mp[e] * d.Hp[0] + u);
+        else if (e == 5) v = __ldg(Wn + d.b_off[0] + u);
+      }
+      wf[(size_t)ln * (pre + per_net) + (size_t)u * 8 + e] = v;
+    }
   }
   for (int i = tid; i < L * 16; i += R_NT) {
     const int l = i >> 4, net = (i >> 3) & 1, e = i & 7;
     const float* Wn = packed + (size_t)l * d.layer_stride + (size_t)net * d.net_stride;
-    b2s[i] = e < RD ? __ldg(Wn + d.b_off[1] + maps[l * 10 + 5 + e]) : 0.f;
+    b2s[i] = e < RD ? __ldg(Wn + d.b_off[last] + maps[l * 10 + 5 + e]) : 0.f;
   }
   __syncthreads();
 }
 
-template <int R_NT, int SPT, int U, int MINB, int TAIL>
+template <int R_NT, int SPT, int U, int MINB, int TAIL, bool M2 = false>
 __global__ void __launch_bounds__(R_NT, MINB)
 flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                   const float* __restrict__ xin, float* __restrict__ zout, float* __restrict__ logdet, int64_t N,
@@ -132,11 +186,12 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
   extern __shared__ __align__(16) float smem[];
   __shared__ double tail_red[32];
   const int tid = threadIdx.x;
-  const int Hp = d.Hp[0], L = d.L;
-  // shared memory: [tail state][per layer: 2 nets x Hp x 3 float4][per layer: 2 x 8 floats of b2][per layer: 10 ints]
+  const int Hp = M2 ? d.H[1] : d.Hp[0], L = d.L;            // units streamed per net
+  const int lay4 = 2 * (3 * Hp + (M2 ? 2 * RD : 0));        // float4 per layer
+  // shared memory: [tail state][per layer: 2 nets x ([5 x 2 float4]) Hp x 3 float4][per layer: 2 x 8 floats of b2][per layer: 10 ints]
   const int tail_floats = TAIL ? cnf_tail_smem_bytes(ta.bins, RK) / 4 : 0;
   float4* ws = reinterpret_cast<float4*>(smem + tail_floats);
-  float* b2s = reinterpret_cast<float*>(ws + (size_t)L * 2 * Hp * 3);
+  float* b2s = reinterpret_cast<float*>(ws + (size_t)L * lay4);
   int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: packed input index of conditioning slot e, packed output index of transformed slot e
   TailSmem tsm;
   BinCache cache; cache.bin = -1; cache.cnt = 0; cache.correct = 0; cache.sconf = 0.0;
@@ -146,7 +201,7 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
     tsm = tail_carve(reinterpret_cast<unsigned char*>(smem), ta.bins, RK);
     tail_init(tsm, ta, RK, tid, R_NT);
   }
-  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
+  stage_weights_reg10<R_NT, M2>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -190,10 +245,10 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
     // ---- the stack -------------------------------------------------------------------------------------------
     for (int li = 0; li < L; ++li) {
       const int l = inverse ? L - 1 - li : li;
-      const float4* w = ws + (size_t)l * 2 * Hp * 3;
+      const float4* w = ws + (size_t)l * lay4;
       const float* b2 = b2s + l * 16;
-      if (l & 1) layer_eval<SPT, U>(w, b2, Hp, inverse, lo, hi, ld);
-      else       layer_eval<SPT, U>(w, b2, Hp, inverse, hi, lo, ld);
+      if (l & 1) layer_eval<SPT, U, M2>(w, b2, Hp, inverse, lo, hi, ld);
+      else       layer_eval<SPT, U, M2>(w, b2, Hp, inverse, hi, lo, ld);
     }
     // ---- registers -> rows (+ fused tail) -----------------------------------------------------------------------
 #pragma unroll
@@ -499,17 +554,17 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   }
 }
 
-template <int R_NT, int SPT, int U, int MINB, int TAIL>
+template <int R_NT, int SPT, int U, int MINB, int TAIL, bool M2 = false>
 int launch_reg10(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                  int64_t N, int inverse, const CnfTail& ta, size_t smem, int sms, cudaStream_t st) {
-  { const int rc = cnf_kernel_smem(flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, smem); if (rc) return rc; }
+  { const int rc = cnf_kernel_smem(flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL, M2>, smem); if (rc) return rc; }
   int per_sm = 0;
-  CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL>, R_NT, smem));
+  CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL, M2>, R_NT, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t ntiles = (N + R_NT * SPT - 1) / (R_NT * SPT);
   const int64_t cap = (int64_t)sms * per_sm;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
-  flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL><<<grid, R_NT, smem, st>>>(d, packed, tables, x, z, logdet, N, inverse, ta);
+  flow_reg10_kernel<R_NT, SPT, U, MINB, TAIL, M2><<<grid, R_NT, smem, st>>>(d, packed, tables, x, z, logdet, N, inverse, ta);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -517,12 +572,15 @@ int launch_reg10(const CnfDims& d, const float* packed, const int32_t* tables, c
 }  // namespace
 
 // Shapes this kernel serves: K = 10, one hidden layer, both nets, standard flips (no random_flip), 8-byte aligned rows,
-// weights of all layers within the shared-memory budget.
+// weights of all layers within the shared-memory budget; forward / inverse / fused predict (two_ok) also two hidden
+// layers with at most five units in the first -- the reference's default conditioner, hidden_size=[5, 5].
 bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const float* x, const float* z, int tail_bins,
-                         int max_smem, size_t* smem_out) {
-  if (d.K != RK || d.m != 1 || d.nets != 3 || desc->perm != nullptr) return false;
+                         int max_smem, size_t* smem_out, bool two_ok) {
+  if (d.K != RK || d.nets != 3 || desc->perm != nullptr) return false;
+  if (!(d.m == 1 || (two_ok && d.m == 2 && d.H[0] <= RD))) return false;
   if (((uintptr_t)x | (uintptr_t)z) % 8 != 0) return false;
-  const size_t smem = (size_t)d.L * (2 * d.Hp[0] * 12 + 16) * sizeof(float) + (size_t)((d.L * 10 + 3) / 4) * 4 * sizeof(int) +
+  const int unit_floats = d.m == 2 ? 2 * (d.H[1] * 12 + 8 * RD) : 2 * d.Hp[0] * 12;
+  const size_t smem = (size_t)d.L * (unit_floats + 16) * sizeof(float) + (size_t)((d.L * 10 + 3) / 4) * 4 * sizeof(int) +
                       (tail_bins > 0 ? cnf_tail_smem_bytes(tail_bins, RK) : 0);
   if ((long long)smem > max_smem - 1024) return false;
   *smem_out = smem;
@@ -532,6 +590,16 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st) {
   const CnfTail ta = tail ? *tail : CnfTail();
+  if (d.m == 2) {          // first hidden layer materialised (the reference's default [5, 5] conditioner)
+    const int spt = variant == 4 ? 2 : (variant == 1 ? 4 : 8);
+#define R2(SPT, MB, TL) return launch_reg10<128, SPT, 2, MB, TL, true>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st)
+    if (!tail) { if (spt == 2) R2(2, 3, 0); if (spt == 4) R2(4, 3, 0); R2(8, 2, 0); }
+    if (ta.mode == CNF_METRICS_LOGITS) { if (spt == 2) R2(2, 3, CNF_METRICS_LOGITS); if (spt == 4) R2(4, 3, CNF_METRICS_LOGITS); R2(8, 2, CNF_METRICS_LOGITS); }
+    if (spt == 2) R2(2, 3, CNF_METRICS_CALIBRATED);
+    if (spt == 4) R2(4, 3, CNF_METRICS_CALIBRATED);
+    R2(8, 2, CNF_METRICS_CALIBRATED);
+#undef R2
+  }
   if (!tail) {
 #define RV(NT, SPT, U, MB) return launch_reg10<NT, SPT, U, MB, 0>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st)
     // Measured on B200 at the C2 shape, 10^7 samples (profiles/microbench/fp32r_speed.py): 128 threads x 8 samples

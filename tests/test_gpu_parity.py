@@ -818,3 +818,52 @@ def test_tile_kernels_forced_on_the_reference_goldens(name, cuda_device, monkeyp
     test_forward_inverse_vs_reference_golden(name, cuda_device)
     for tag, eps, gamma in (('cal', 1e-7, 1.0), ('script', 0.0, 1.0), ('script_nodet', 0.0, 0.0)):
         test_fused_train_step_gradients_vs_reference_autograd(name, tag, eps, gamma, cuda_device)
+
+
+@pytest.mark.parametrize('L,hidden,wmul', [(6, [5, 5], 300.0), (5, [5, 5], 300.0), (4, [3, 20], 200.0), (6, [5, 64], 100.0)])
+@pytest.mark.parametrize('N', [70_001, 130_003, 300_001])
+def test_register_kernel_with_a_small_first_hidden_layer_vs_oracle(L, hidden, wmul, N, cuda_device, monkeypatch):
+    """K = 10 flows whose conditioners have two hidden layers with at most five units in the first -- the reference's
+    DEFAULT NvpCouplingLayer(dim, hidden_size=[5, 5]) (flows/flows.py:69) -- run forward / inverse / fused predict on
+    flow_reg10_kernel<..., M2> from 65,536 samples (2 / 4 / 8 samples per thread by batch size): against the float64
+    oracle, against the generic kernel, and through the fused statistics pass."""
+    import torch
+    import cnf_b200
+    monkeypatch.setenv('CNF_LIVE_ENV', '1')
+    torch.manual_seed(L + hidden[1])
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(10, hidden) for _ in range(L)])
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(wmul)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), orc.init_params(10, L, hidden, True, True))
+    flow.to(cuda_device)
+    x, y = orc.synth_logits(N, 10, seed=N % 1000)
+    xt = torch.from_numpy(x).to(cuda_device)
+    with torch.no_grad():
+        zs, ld = flow(xt)
+        xr, ldr = flow.backward(zs[-1])
+        monkeypatch.setenv('CNF_FP32R', 'off')               # the same call on the generic kernel
+        zs_g, ld_g = flow(xt)
+        z_g, ldg = zs_g[-1].clone(), ld_g.clone()
+        monkeypatch.delenv('CNF_FP32R')
+    z = zs[-1]
+    assert float((z - z_g).abs().max()) < 2e-6 * float(z_g.abs().max())
+    assert float((ld - ldg).abs().max()) < 2e-6 * max(1.0, float(ldg.abs().max()))
+    idx = np.concatenate([np.arange(0, N, 499), np.arange(N - 300, N)])        # strided subset + the ragged tail
+    zo, ldo = orc.flow_forward(params, x[idx].astype(np.float64))
+    tidx = torch.from_numpy(idx).to(cuda_device)
+    assert rel_err(z[tidx].cpu().numpy(), zo[-1]) < TOL
+    assert ld_err(ld[tidx].cpu().numpy(), ldo) < TOL
+    assert rel_err(xr[-1][tidx].cpu().numpy(), x[idx]) < 5e-5
+    assert ld_err(ldr[tidx].cpu().numpy(), -ldo) < 5e-5
+    # fused statistics pass (register kernel with the tail) == statistics of the plain forward's logits
+    from cnf_b200 import _lib
+    from cnf_b200.utils import metrics as M
+    yt = torch.from_numpy(y).to(cuda_device)
+    st_fused = flow.engine().predict(xt, y=yt, bins=15)['stats'].cpu().numpy()
+    st_plain = M.statistics(z, yt, bins=15, mode=_lib.METRICS_LOGITS).cpu().numpy()
+    assert np.array_equal(st_fused[[-2, -1]], st_plain[[-2, -1]])            # correct count, N
+    assert np.array_equal(st_fused[:15], st_plain[:15])                      # bin counts
+    assert np.allclose(st_fused, st_plain, rtol=1e-9, atol=1e-6)
