@@ -118,10 +118,11 @@ __device__ __forceinline__ void layer_eval(const float4* __restrict__ w, const f
 // so that the copy below reads the packed blob with h fastest, i.e. coalesced, and never searches).
 template <int R_NT, bool M2 = false>
 __device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const float* __restrict__ packed,
-                                                    const int* __restrict__ tables, float* wf, float* b2s, int* maps, int tid) {
+                                                    const int* __restrict__ tables, float* wf, float* b2s, int* maps, int tid, int Hn) {
   // M2: per net 5 first-layer records of 8 floats [W1 of slot 0..4 | b1 | 0 0], then one 12-float record per unit of
   // the SECOND hidden layer (true width, not padded) [Wm from first-layer unit 0..4 | bm | W3 of slot 0..4 | 0]
-  const int Hp = M2 ? d.H[1] : d.Hp[0], L = d.L;
+  // Hn = hidden units streamed per net: the true width for the forward kernel, the padded one for the training kernel
+  const int Hp = Hn, L = d.L;
   const int pre = M2 ? 8 * RD : 0;                         // floats in front of a net's unit records
   const int last = M2 ? 2 : 1;                             // index of the last Linear
   for (int i = tid; i < L * 10; i += R_NT) {
@@ -186,7 +187,7 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
   extern __shared__ __align__(16) float smem[];
   __shared__ double tail_red[32];
   const int tid = threadIdx.x;
-  const int Hp = M2 ? d.H[1] : d.Hp[0], L = d.L;            // units streamed per net
+  const int Hp = M2 ? d.H[1] : d.H[0], L = d.L;             // units streamed per net (true width: padding units are zeros)
   const int lay4 = 2 * (3 * Hp + (M2 ? 2 * RD : 0));        // float4 per layer
   // shared memory: [tail state][per layer: 2 nets x ([5 x 2 float4]) Hp x 3 float4][per layer: 2 x 8 floats of b2][per layer: 10 ints]
   const int tail_floats = TAIL ? cnf_tail_smem_bytes(ta.bins, RK) / 4 : 0;
@@ -201,7 +202,7 @@ flow_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __rest
     tsm = tail_carve(reinterpret_cast<unsigned char*>(smem), ta.bins, RK);
     tail_init(tsm, ta, RK, tid, R_NT);
   }
-  stage_weights_reg10<R_NT, M2>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
+  stage_weights_reg10<R_NT, M2>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid, Hp);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -375,7 +376,7 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: [5] packed input index of slot e, [5] packed output index
   float* park = reinterpret_cast<float*>(maps + ((L * 10 + 3) / 4) * 4);   // [3][SPT][5][R_NT] per-thread parking slots
   const bool do_bwd = partials != nullptr;
-  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid);
+  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid, Hp);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -591,13 +592,15 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st) {
   const CnfTail ta = tail ? *tail : CnfTail();
   if (d.m == 2) {          // first hidden layer materialised (the reference's default [5, 5] conditioner)
-    const int spt = variant == 4 ? 2 : (variant == 1 ? 4 : 8);
+    // These nets are tiny (150 FMAs per sample and layer at [5, 5]): resident warps matter more than weight-load reuse.
+    // Measured at K = 10, L = 6, [5, 5], 10^7 samples (default_shape_speed.py): 8 samples per thread 11.4 G samples/s,
+    // 4 per thread 15.5 G, 2 per thread 15.7 G (the generic tile kernel: 2.3 G).
+    const int spt = variant == 4 ? 2 : 4;
 #define R2(SPT, MB, TL) return launch_reg10<128, SPT, 2, MB, TL, true>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st)
-    if (!tail) { if (spt == 2) R2(2, 3, 0); if (spt == 4) R2(4, 3, 0); R2(8, 2, 0); }
-    if (ta.mode == CNF_METRICS_LOGITS) { if (spt == 2) R2(2, 3, CNF_METRICS_LOGITS); if (spt == 4) R2(4, 3, CNF_METRICS_LOGITS); R2(8, 2, CNF_METRICS_LOGITS); }
-    if (spt == 2) R2(2, 3, CNF_METRICS_CALIBRATED);
-    if (spt == 4) R2(4, 3, CNF_METRICS_CALIBRATED);
-    R2(8, 2, CNF_METRICS_CALIBRATED);
+    if (!tail) { if (spt == 2) R2(2, 6, 0); R2(4, 4, 0); }
+    if (ta.mode == CNF_METRICS_LOGITS) { if (spt == 2) R2(2, 6, CNF_METRICS_LOGITS); R2(4, 4, CNF_METRICS_LOGITS); }
+    if (spt == 2) R2(2, 6, CNF_METRICS_CALIBRATED);
+    R2(4, 4, CNF_METRICS_CALIBRATED);
 #undef R2
   }
   if (!tail) {
