@@ -2190,7 +2190,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000)) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
-    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r, false)) {
+    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r, true)) {
       rc = cnf_fp32r_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_r, g_num_sms,
                            g_max_smem, sw ? atoi(sw) : 0, rows_used, st);
       if (rc != CNF_E_SMEM) return rc;      // (too many layers for its shared-memory plan: the tile kernels below)

@@ -362,7 +362,90 @@ __device__ __forceinline__ void net_backward(const float4* __restrict__ w, int H
   }
 }
 
-template <int R_NT, int SPT, int U, int MINB>
+// The same for a net with two hidden layers, the first of at most five units (hidden_size=[5, 5]): the first layer is
+// recomputed into registers, the stream over the second layer's units also accumulates the gradient on the first
+// layer's activations, and a last pass over the five first-layer units forms W1^T ga, dW1 and db1.
+// goff: entry offset of this lane for the second-layer / last-Linear values (0..4 dW3 of output slot e, 5..9 dWm from
+// first-layer unit e, 10 dbm); goff1: for the first-layer values (0..4 dW1 of input slot e, 5 db1); -1 for none.
+template <int SPT, int U>
+__device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, int Hn, int H1, const float (&c)[SPT][RD],
+                                                const float (&go)[SPT][RD], float (&gc)[SPT][RD], float* __restrict__ Gn,
+                                                int goff, int goff1, int lane) {
+  float h1[SPT][RD], gh1[SPT][RD];
+#pragma unroll
+  for (int i = 0; i < RD; ++i) {
+    const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      float a = fmaf(v0.x, c[k][0], v1.y);
+      a = fmaf(v0.y, c[k][1], a);
+      a = fmaf(v0.z, c[k][2], a);
+      a = fmaf(v0.w, c[k][3], a);
+      a = fmaf(v1.x, c[k][4], a);
+      h1[k][i] = fmaxf(a, 0.f);
+      gh1[k][i] = 0.f;
+    }
+  }
+  const float4* wu = w + 2 * RD;
+#pragma unroll U
+  for (int h = 0; h < Hn; ++h) {
+    const float4 v0 = wu[3 * h], v1 = wu[3 * h + 1], v2 = wu[3 * h + 2];
+    float wg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wg[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      float a = fmaf(v0.x, h1[k][0], v1.y);
+      a = fmaf(v0.y, h1[k][1], a);
+      a = fmaf(v0.z, h1[k][2], a);
+      a = fmaf(v0.w, h1[k][3], a);
+      a = fmaf(v1.x, h1[k][4], a);
+      const float r = fmaxf(a, 0.f);
+      float gh = v1.z * go[k][0];
+      gh = fmaf(v1.w, go[k][1], gh);
+      gh = fmaf(v2.x, go[k][2], gh);
+      gh = fmaf(v2.y, go[k][3], gh);
+      gh = fmaf(v2.z, go[k][4], gh);
+      gh = a > 0.f ? gh : 0.f;
+      gh1[k][0] = fmaf(v0.x, gh, gh1[k][0]);
+      gh1[k][1] = fmaf(v0.y, gh, gh1[k][1]);
+      gh1[k][2] = fmaf(v0.z, gh, gh1[k][2]);
+      gh1[k][3] = fmaf(v0.w, gh, gh1[k][3]);
+      gh1[k][4] = fmaf(v1.x, gh, gh1[k][4]);
+#pragma unroll
+      for (int e = 0; e < RD; ++e) {
+        wg[e] = fmaf(r, go[k][e], wg[e]);              // dW3[slot e][h]
+        wg[RD + e] = fmaf(gh, h1[k][e], wg[RD + e]);   // dWm[first-layer unit e][h]
+      }
+      wg[10] += gh;                                    // dbm[h]
+    }
+    const float tot = warp_reduce16(wg, lane);
+    if (goff >= 0) atomicAdd(Gn + goff + h, tot);
+  }
+#pragma unroll
+  for (int i = 0; i < RD; ++i) {
+    const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
+    float wg[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) wg[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const float ga = h1[k][i] > 0.f ? gh1[k][i] : 0.f;
+      gc[k][0] = fmaf(v0.x, ga, gc[k][0]);
+      gc[k][1] = fmaf(v0.y, ga, gc[k][1]);
+      gc[k][2] = fmaf(v0.z, ga, gc[k][2]);
+      gc[k][3] = fmaf(v0.w, ga, gc[k][3]);
+      gc[k][4] = fmaf(v1.x, ga, gc[k][4]);
+#pragma unroll
+      for (int e = 0; e < RD; ++e) wg[e] = fmaf(ga, c[k][e], wg[e]);   // dW1[unit i][slot e]
+      wg[RD] += ga;                                                      // db1[unit i]
+    }
+    const float tot = warp_reduce16(wg, lane);
+    if (goff1 >= 0 && i < H1) atomicAdd(Gn + goff1 + i, tot);
+  }
+}
+
+template <int R_NT, int SPT, int U, int MINB, bool M2 = false>
 __global__ void __launch_bounds__(R_NT, MINB)
 train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                    const float* __restrict__ xin, const int64_t* __restrict__ labels, float* __restrict__ partials,
@@ -370,13 +453,16 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[4][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Hp = d.Hp[0], L = d.L;
+  const int Hp = M2 ? d.H[1] : d.Hp[0], L = d.L;            // units streamed per net
+  const int ns4 = 3 * Hp + (M2 ? 2 * RD : 0), lay4 = 2 * ns4;   // float4 per net / per layer
+  const int Hrow = M2 ? d.Hp[1] : d.Hp[0];                  // row length of the packed matrices the unit gradients land in
+  const int last = M2 ? 2 : 1;                              // index of the last Linear
   float4* ws = reinterpret_cast<float4*>(smem);
-  float* b2s = reinterpret_cast<float*>(ws + (size_t)L * 2 * Hp * 3);
+  float* b2s = reinterpret_cast<float*>(ws + (size_t)L * lay4);
   int* maps = reinterpret_cast<int*>(b2s + L * 16);       // per layer: [5] packed input index of slot e, [5] packed output index
   float* park = reinterpret_cast<float*>(maps + ((L * 10 + 3) / 4) * 4);   // [3][SPT][5][R_NT] per-thread parking slots
   const bool do_bwd = partials != nullptr;
-  stage_weights_reg10<R_NT>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid, Hp);
+  stage_weights_reg10<R_NT, M2>(d, packed, tables, reinterpret_cast<float*>(ws), b2s, maps, tid, Hp);
 
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
@@ -408,10 +494,10 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
     }
     // ---- forward ------------------------------------------------------------------------------------------------
     for (int l = 0; l < L; ++l) {
-      const float4* w = ws + (size_t)l * 2 * Hp * 3;
+      const float4* w = ws + (size_t)l * lay4;
       const float* b2 = b2s + l * 16;
-      if (l & 1) layer_eval<SPT, U>(w, b2, Hp, 0, lo, hi, ld);
-      else       layer_eval<SPT, U>(w, b2, Hp, 0, hi, lo, ld);
+      if (l & 1) layer_eval<SPT, U, M2>(w, b2, Hp, 0, lo, hi, ld);
+      else       layer_eval<SPT, U, M2>(w, b2, Hp, 0, hi, lo, ld);
     }
     // ---- loss head (calibrators.py:288-291; eps == 0: CrossEntropyLoss, run_experiment3D.py:107) ------------------
     float glo[SPT][RD], ghi[SPT][RD];
@@ -456,19 +542,24 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
     if (!do_bwd) continue;
     // ---- backward -------------------------------------------------------------------------------------------------
     for (int l = L - 1; l >= 0; --l) {
-      const float4* w = ws + (size_t)l * 2 * Hp * 3;
+      const float4* w = ws + (size_t)l * lay4;
       const float* b2 = b2s + l * 16;
       const int* mp = maps + l * 10;
       float* Gl = Grow + (size_t)l * d.layer_stride;
       // this lane's entry in a net's packed gradient block for the value it holds after the butterfly:
-      // values 0..4 = dW2 of output slot e, 5..9 = dW1 of input slot e, 10 = db1
-      int goff = -1;
+      // values 0..4 = dW(last Linear) of output slot e, 5..9 = dW(the Linear in front of the streamed units) of its
+      // input e (a conditioning slot, or with M2 a first-layer unit), 10 = that Linear's bias
+      int goff = -1, goff1 = -1;
       if (writer) {
-        if (vidx < 5) goff = d.w_off[1] + mp[5 + vidx] * Hp;
-        else if (vidx < 10) goff = d.w_off[0] + mp[vidx - 5] * Hp;
-        else if (vidx == 10) goff = d.b_off[0];
+        if (vidx < 5) goff = d.w_off[last] + mp[5 + vidx] * Hrow;
+        else if (vidx < 10) goff = M2 ? (vidx - 5 < d.H[0] ? d.w_off[1] + (vidx - 5) * Hrow : -1) : d.w_off[0] + mp[vidx - 5] * Hrow;
+        else if (vidx == 10) goff = d.b_off[last - 1];
+        if (M2) {                                   // first-layer values: 0..4 dW1 of input slot e, 5 db1
+          if (vidx < 5) goff1 = d.w_off[0] + mp[vidx] * d.Hp[0];
+          else if (vidx == 5) goff1 = d.b_off[0];
+        }
       }
-      const int boff = (writer && vidx < 5) ? d.b_off[1] + mp[5 + vidx] : -1;      // db2 of output slot vidx
+      const int boff = (writer && vidx < 5) ? d.b_off[last] + mp[5 + vidx] : -1;      // db(last) of output slot vidx
       // Register pressure: of the four [SPT][5] blocks of a layer (conditioning values c, transformed values t and the
       // gradients on both) only two or three are used inside each hidden-unit loop; the others wait in a per-thread
       // shared-memory slot (park[slot][value][tid]: conflict-free), which is what lets SPT reach 8.
@@ -489,13 +580,13 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
         float o[SPT][RD];
         park_put(0, gcnd);
         park_put(1, gt);
-        net_eval<SPT, U>(w + 3 * Hp, b2 + 8, Hp, c, o);                  // shift
+        net_eval<SPT, U, M2>(w + ns4, b2 + 8, Hp, c, o);                 // shift
 #pragma unroll
         for (int k = 0; k < SPT; ++k)
 #pragma unroll
           for (int q = 0; q < RD; ++q) t[k][q] -= o[k][q];              // y - shift  (= x e^s)
         park_put(2, t);
-        net_eval<SPT, U>(w, b2, Hp, c, o);                               // s
+        net_eval<SPT, U, M2>(w, b2, Hp, c, o);                           // s
         park_get(2, t);
         park_get(1, gt);
         float gs[SPT][RD];
@@ -518,21 +609,23 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
             for (int q = 0; q < RD; ++q) { wb[q] += gt[k][q]; wb[8 + q] += gs[k][q]; }
           // values 0..4: db2 of the shift net, 8..12: db2 of the scale net
           const float tot = warp_reduce16(wb, lane);
-          if (writer && vidx < 5) atomicAdd(Gl + d.net_stride + d.b_off[1] + mp[5 + vidx], tot);
-          if (writer && vidx >= 8 && vidx < 13) atomicAdd(Gl + d.b_off[1] + mp[5 + vidx - 8], tot);
+          if (writer && vidx < 5) atomicAdd(Gl + d.net_stride + d.b_off[last] + mp[5 + vidx], tot);
+          if (writer && vidx >= 8 && vidx < 13) atomicAdd(Gl + d.b_off[last] + mp[5 + vidx - 8], tot);
         }
         park_put(1, t);          // x: final for this layer
         park_put(2, o);          // g_x of the transformed half: becomes gt below
         park_get(0, gcnd);
         park_put(0, gs);
         // shift net first (its output gradient is g_y itself), then the scale net
-        net_backward<SPT, U>(w + 3 * Hp, Hp, c, gt, gcnd, Gl + d.net_stride, goff, lane);
+        if constexpr (M2) net_backward_m2<SPT, U>(w + ns4, Hp, d.H[0], c, gt, gcnd, Gl + d.net_stride, goff, goff1, lane);
+        else              net_backward<SPT, U>(w + ns4, Hp, c, gt, gcnd, Gl + d.net_stride, goff, lane);
         park_get(0, gt);         // gs
-        net_backward<SPT, U>(w, Hp, c, gt, gcnd, Gl, goff, lane);
+        if constexpr (M2) net_backward_m2<SPT, U>(w, Hp, d.H[0], c, gt, gcnd, Gl, goff, goff1, lane);
+        else              net_backward<SPT, U>(w, Hp, c, gt, gcnd, Gl, goff, lane);
         park_get(1, t);
         park_get(2, gt);
       };
-      (void)boff;
+      (void)boff; (void)goff1;
       if (l & 1) run(lo, hi, glo, ghi);
       else       run(hi, lo, ghi, glo);
     }
@@ -635,14 +728,14 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                     float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
                     int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st) {
-#define TV(NT, SPT, U, MB)                                                                                           \
+#define TVX(NT, SPT, U, MB, M2)                                                                                     \
   do {                                                                                                               \
     const size_t smem = smem_fwd + (size_t)3 * SPT * RD * NT * sizeof(float);                                       \
     if ((long long)smem > max_smem - 1024) break;      /* this variant's plan does not fit: try the next smaller one */ \
-    int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, U, MB>, smem);                                              \
+    int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, U, MB, M2>, smem);                                              \
     if (rc) return rc;                                                                                               \
     int per_sm = 0;                                                                                                  \
-    CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_reg10_kernel<NT, SPT, U, MB>, NT, smem)); \
+    CNF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, train_reg10_kernel<NT, SPT, U, MB, M2>, NT, smem)); \
     if (per_sm < 1) per_sm = 1;                                                                                      \
     const int64_t ntiles = (N + NT * SPT - 1) / (NT * SPT);                                                          \
     int64_t cap = (int64_t)sms * per_sm;                                                                             \
@@ -652,10 +745,19 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
     const int64_t rows = (int64_t)grid * (NT / 32);                                                                  \
     if (rows_out) *rows_out = rows;                                                                                  \
     if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)(rows_out ? rows : d.grad_rows_max) * d.n_packed * sizeof(float), st)); \
-    train_reg10_kernel<NT, SPT, U, MB><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n); \
+    train_reg10_kernel<NT, SPT, U, MB, M2><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n); \
     CNF_CHECK_CUDA(cudaGetLastError());                                                                              \
     return CNF_OK;                                                                                                   \
   } while (0)
+#define TV(NT, SPT, U, MB) TVX(NT, SPT, U, MB, false)
+  if (d.m == 2) {          // two hidden layers, the first of at most five units (the reference's default [5, 5])
+    if (variant == 5) TVX(128, 4, 2, 2, true);
+    if (variant == 2) TVX(128, 8, 2, 1, true);
+    TVX(256, 4, 2, 1, true);
+    TVX(128, 4, 2, 2, true);
+    cnf_set_error("register-resident training kernel: the weights of %d layers do not fit shared memory", d.L);
+    return CNF_E_SMEM;
+  }
   // Measured on B200 at the C2 shape, 4 Mi samples (profiles/microbench/fp32r_train_speed.py): 256 threads x 8 samples
   // (one CTA per SM, the whole register file) 266.8 M samples/s; 256 x 6 241; 128 x 8 214; 128 x 4 (2 CTAs/SM) 206;
   // the 32-sample-tile split kernel 164.6.  Samples per thread amortise the weight loads and the butterfly.
@@ -678,4 +780,5 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
   cnf_set_error("register-resident training kernel: the weights of %d layers do not fit shared memory", d.L);
   return CNF_E_SMEM;
 #undef TV
+#undef TVX
 }

@@ -867,3 +867,47 @@ def test_register_kernel_with_a_small_first_hidden_layer_vs_oracle(L, hidden, wm
     assert np.array_equal(st_fused[[-2, -1]], st_plain[[-2, -1]])            # correct count, N
     assert np.array_equal(st_fused[:15], st_plain[:15])                      # bin counts
     assert np.allclose(st_fused, st_plain, rtol=1e-9, atol=1e-6)
+
+
+@pytest.mark.parametrize('L,hidden,wmul', [(6, [5, 5], 300.0), (5, [5, 5], 1.0), (4, [3, 20], 200.0)])
+@pytest.mark.parametrize('N,eps,gamma', [(65_536, 1e-7, 1.0), (70_003, 0.0, 1.0), (131_075, 0.0, 0.0)])
+def test_register_training_kernel_with_a_small_first_hidden_layer_vs_oracle(L, hidden, wmul, N, eps, gamma, cuda_device,
+                                                                             monkeypatch):
+    """train_reg10_kernel<..., M2>: the NLL step of K = 10 flows whose conditioners have two hidden layers with at most
+    five units in the first (the reference's default hidden_size=[5, 5]): loss and gradient against the float64
+    oracle, bitwise repeatable, and against the generic one-thread-per-sample kernel on the same batch."""
+    import torch
+    import cnf_b200
+    monkeypatch.setenv('CNF_LIVE_ENV', '1')
+    monkeypatch.setenv('CNF_FP32R_TRAIN', '0')      # by default the kernel takes over from 160,000 samples; forced here
+    torch.manual_seed(L + hidden[1])
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(10, hidden) for _ in range(L)])
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(wmul)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), orc.init_params(10, L, hidden, True, True))
+    flow.to(cuda_device)
+    eng = flow.engine()
+    eng.ensure(cuda_device)
+    eng.pack()
+    x, y = orc.synth_logits(N, 10, seed=N % 1000)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc, eps=eps, gamma=gamma)
+    grad = eng.flat_grad.cpu().numpy().copy()
+    loss, ce, ldm, grads, _ = orc.train_step_grads(params, x.astype(np.float64), y, eps=eps, gamma=gamma)
+    ref = orc.flatten(grads)
+    assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+    assert abs(-float(acc[1]) / N - ce) < 1e-5 * max(1.0, abs(ce)) and float(acc[3]) == 0.0
+    assert rel_err(grad, ref) < 2e-4, rel_err(grad, ref)
+    assert np.all(grad[ref == 0] == 0)
+    acc2 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc2, eps=eps, gamma=gamma)
+    assert np.array_equal(eng.flat_grad.cpu().numpy(), grad)
+    monkeypatch.setenv('CNF_FP32R_TRAIN', 'off')
+    acc4 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
+    assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 2e-4
+    assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
