@@ -501,7 +501,7 @@ def run_ours(args):
             n5 = n_head
         # logits of this rank's blocks (block seeds are global, so the union over ranks is the same set at every N)
         blocks = list(range(rank, 8, world)) if (n5 * world == 100_000_000 and world in (1, 2, 4, 8)) else None
-        x5, y5 = xh_dev[:n5], yh_dev[:n5]
+        x5, y5 = synth_dev(n5, 5000 + rank, dev)
         if blocks is not None:
             for j, b in enumerate(blocks):
                 synth_block(x5[j * 12_500_000:(j + 1) * 12_500_000], y5[j * 12_500_000:(j + 1) * 12_500_000], 5000 + b)
@@ -730,6 +730,37 @@ def run_ours(args):
         del x4, z4, l4, tr4, c4, e4
         torch.cuda.empty_cache()
 
+    # ---- the reference's DEFAULT conditioner (NvpCouplingLayer(dim, hidden_size=[5, 5]), flows/flows.py:69) ----------
+    if not args.no_extra:
+        n5 = 10_000_000
+        m5 = make_model(seed=5, wmult=300.0, hidden=[5, 5]).to(dev)
+        e5 = m5.engine()
+        e5.ensure(dev)
+        e5.pack()
+        x5, y5 = synth_dev(n5, 5000 + rank, dev)
+        z5 = torch.empty_like(x5)
+        l5 = torch.empty(n5, dtype=torch.float32, device=dev)
+
+        def d5step(i):
+            _lib.call('cnf_flow_forward', ctypes.byref(e5.desc), _ptr(e5.packed), _ptr(e5.tables), _ptr(x5), _ptr(z5),
+                      _ptr(l5), None, ctypes.c_int64(n5), _stream(dev))
+        d5_ms = timed(d5step, few, 3)
+        n5t = min(n5, 4_000_000)
+        m5t = make_model(seed=6, wmult=1.0, hidden=[5, 5]).to(dev)
+        tr5 = cnf_b200.FusedNLLTrainer(m5t.engine(), x5[:n5t], y5[:n5t], n_total=n5t * world)
+        d5t_ms = timed(lambda i: tr5.step(), few, 3)
+        f5 = 6 * 2 * 2 * (5 * 5 + 5 * 5 + 5 * 5)                  # minimal flops per sample
+        legs['default_conditioner'] = {
+            'what': 'K=10, 6 couplings, hidden_size=[5, 5] (the reference default), fp32 register-resident kernels: '
+                    'forward + log-det on %d samples per GPU, NLL + Adam step on %d' % (n5, n5t),
+            'unit': UNIT, 'dtype': 'f32',
+            'forward': {'value': world * n5 / (d5_ms * 1e-3), 'ms_per_step': d5_ms,
+                        'hbm_gbs': 84 * n5 / (d5_ms * 1e-3) / 1e9, 'frac_of_hbm_peak': 84 * n5 / (d5_ms * 1e-3) / 1e9 / hbm_peak,
+                        'fma_tflops_minimal': f5 * n5 / (d5_ms * 1e-3) / 1e12},
+            'train_step': {'value': world * n5t / (d5t_ms * 1e-3), 'ms_per_step': d5t_ms}}
+        del x5, y5, z5, l5, tr5, m5, m5t, e5
+        torch.cuda.empty_cache()
+
     # ---- calibrator API at calibration-set sizes (rank 0, N=1 only) -----------------------------------------
     if not args.no_extra and rank == 0 and world == 1:
         rs = np.random.RandomState(3)
@@ -891,6 +922,8 @@ def run_ours(args):
             'c5_job': g(legs.get('c5_job', {}).get(head_prec, {}).get('value')),
             'c5_ece': legs.get('c5_job', {}).get(head_prec, {}).get('ece'),
             'c4_fwd_bf16': g(legs.get('c4_forward', {}).get('value')),
+            'fwd_fp32_hidden_5_5': g(legs.get('default_conditioner', {}).get('forward', {}).get('value')),
+            'train_fp32_hidden_5_5': g(legs.get('default_conditioner', {}).get('train_step', {}).get('value')),
             'tensor_frac': round(ach_tf / tf_peak, 4) if head_prec == 'bf16' else None,
             'dp_check_ok': None if dp_check is None else dp_check['ok'],
         }
