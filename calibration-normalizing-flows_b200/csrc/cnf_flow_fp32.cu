@@ -2043,8 +2043,12 @@ int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t
   {
     const char* sw = cnf_switch(CNF_SW_FP32R);
     size_t smem_r = 0;
-    if (!zs && N >= 65536 && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r, true)) {
-      const int variant = sw ? atoi(sw) : (N >= 240000 ? 0 : (N >= 113000 ? 1 : 4));
+    // (two tiny hidden layers -- the reference's default [5, 5] -- from 1,024 samples: their alternative is the generic
+    //  tile kernel, 5x slower at every size measured)
+    const bool tiny2 = d.m == 2;
+    if (!zs && N >= (tiny2 ? 1024 : 65536) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, 0, g_max_smem, &smem_r, true)) {
+      const int variant = sw ? atoi(sw) : (tiny2 ? (N >= 113000 ? 1 : (N >= 256LL * g_num_sms ? 4 : 5))
+                                                 : (N >= 240000 ? 0 : (N >= 113000 ? 1 : 4)));
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, inverse, nullptr, smem_r, g_num_sms, variant, st);
     }
   }
@@ -2128,9 +2132,10 @@ int cnf_fp32_predict(const cnf_flow_desc* desc, const float* packed, const int32
   {
     size_t smem_r = 0;
     const char* sw = cnf_switch(CNF_SW_FP32R);
-    if (N >= (sw ? 1 : 65536) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r, true))
+    const bool tiny2 = d.m == 2;
+    if (N >= (sw ? 1 : (tiny2 ? 1024 : 65536)) && !(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, z, ta.bins, g_max_smem, &smem_r, true))
       return cnf_fp32r_apply(d, packed, tables, x, z, logdet, N, 0, &ta, smem_r, g_num_sms,
-                             N >= 240000 ? 0 : (N >= 113000 ? 1 : 4), st);
+                             tiny2 ? (N >= 113000 ? 1 : (N >= 256LL * g_num_sms ? 4 : 5)) : (N >= 240000 ? 0 : (N >= 113000 ? 1 : 4)), st);
   }
   LaunchCfg c;
   c.nt = 0; c.spt = 1; c.ws = false; c.wl = 0; c.smem = 0;
@@ -2187,7 +2192,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // 200,000: 1232 / 994; 262,144: 1612 / 1216; 1 Mi: 6326 / 4594; 4 Mi: 25462 / 15689 (one wave of its 2048-sample
   // tiles takes ~0.95 ms whatever it holds, the tile kernel's time grows with N: they cross at ~155,000 samples).
   // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 65,536 -- experiments)
-  if (head == CNF_HEAD_NLL && N >= (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000)) {
+  if (head == CNF_HEAD_NLL && N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000))) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
     if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r, true)) {

@@ -688,10 +688,13 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
     // These nets are tiny (150 FMAs per sample and layer at [5, 5]): resident warps matter more than weight-load reuse.
     // Measured at K = 10, L = 6, [5, 5], 10^7 samples (default_shape_speed.py): 8 samples per thread 11.4 G samples/s,
     // 4 per thread 15.5 G, 2 per thread 15.7 G (the generic tile kernel: 2.3 G).
-    const int spt = variant == 4 ? 2 : 4;
+    // Small batches (these shapes leave the generic tile kernels from 1,024 samples on): 128-sample tiles (one sample
+    // per thread) while they do not fill the SMs, then 256- and 512-sample tiles.
+    const int spt = variant == 5 ? 1 : (variant == 4 ? 2 : 4);
 #define R2(SPT, MB, TL) return launch_reg10<128, SPT, 2, MB, TL, true>(d, packed, tables, x, z, logdet, N, inverse, ta, smem, sms, st)
-    if (!tail) { if (spt == 2) R2(2, 6, 0); R2(4, 4, 0); }
-    if (ta.mode == CNF_METRICS_LOGITS) { if (spt == 2) R2(2, 6, CNF_METRICS_LOGITS); R2(4, 4, CNF_METRICS_LOGITS); }
+    if (!tail) { if (spt == 1) R2(1, 8, 0); if (spt == 2) R2(2, 6, 0); R2(4, 4, 0); }
+    if (ta.mode == CNF_METRICS_LOGITS) { if (spt == 1) R2(1, 8, CNF_METRICS_LOGITS); if (spt == 2) R2(2, 6, CNF_METRICS_LOGITS); R2(4, 4, CNF_METRICS_LOGITS); }
+    if (spt == 1) R2(1, 8, CNF_METRICS_CALIBRATED);
     if (spt == 2) R2(2, 6, CNF_METRICS_CALIBRATED);
     R2(4, 4, CNF_METRICS_CALIBRATED);
 #undef R2
@@ -751,8 +754,15 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
   } while (0)
 #define TV(NT, SPT, U, MB) TVX(NT, SPT, U, MB, false)
   if (d.m == 2) {          // two hidden layers, the first of at most five units (the reference's default [5, 5])
+    // these shapes come here from 1,024 samples on (their alternative is the generic one-thread-per-sample tile kernel):
+    // the largest tile that still gives every SM one, 128 x 1 at calibration-set sizes
     if (variant == 5) TVX(128, 4, 2, 2, true);
     if (variant == 2) TVX(128, 8, 2, 1, true);
+    if (variant == 0) {
+      if (N < 128LL * 2 * sms) TVX(128, 1, 2, 4, true);
+      if (N < 128LL * 4 * sms) TVX(128, 2, 2, 4, true);
+      if (N < 256LL * 4 * sms) TVX(128, 4, 2, 2, true);
+    }
     TVX(256, 4, 2, 1, true);
     TVX(128, 4, 2, 2, true);
     cnf_set_error("register-resident training kernel: the weights of %d layers do not fit shared memory", d.L);
