@@ -109,6 +109,45 @@ def test_tc_wide_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda
         assert rel_err(xr[-1].cpu().numpy(), x) < RTOL
 
 
+@pytest.mark.parametrize('K,L,hidden,scale,shift,wmul', [(10, 6, [128, 128], True, True, 30.0), (3, 4, [32, 20], False, True, 60.0),
+                                                         (65, 2, [128, 17], True, False, 30.0), (20, 3, [100, 64], True, True, 40.0),
+                                                         (10, 5, [16, 128], True, True, 40.0), (33, 2, [48, 112], True, True, 40.0)])
+def test_tc_two_hidden_layer_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda_device):
+    """Conditioners with two hidden layers of up to 128 units run on cnf_flow_tcm.cu (the H1 x H2 middle Linear as
+    full-width tcgen05 MMAs; flows/utils.py:6-31): forward, log-det and the inverse round trip against the float64
+    oracle within the stated bf16 tolerance, ragged sizes included, and against the fp32 kernel."""
+    import torch
+    import cnf_b200
+    torch.manual_seed(K + L)
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)],
+                         precision='bf16')
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(wmul)
+    like = orc.init_params(K, L, hidden, scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    flow.to(cuda_device)
+    assert flow.engine().tc_bytes > 0
+    for N in (1, 300, 128 * 148 * 2 + 77, 128 * 148 * 5):
+        x, _ = orc.synth_logits(N, K, seed=3 + N)
+        xt = torch.from_numpy(x).to(cuda_device)
+        with torch.no_grad():
+            zs, ld = flow(xt)
+            xr, ldr = flow.backward(zs[-1])
+            z32, ld32, _ = flow.engine().apply(xt)
+        zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+        zz = zs[-1].cpu().numpy()
+        assert np.isfinite(zz).all()
+        assert float(np.max(np.abs(zo[-1] - x))) > 1e-3 * float(np.max(np.abs(x)))      # the flow does something
+        assert rel_err(zz, zo[-1]) < RTOL
+        assert np.max(np.abs(ld.cpu().numpy().reshape(-1) - ldo)) < RTOL * max(1.0, np.max(np.abs(ldo)))
+        assert rel_err(xr[-1].cpu().numpy(), x) < RTOL
+        assert np.max(np.abs((ld + ldr).cpu().numpy())) < RTOL * max(1.0, np.max(np.abs(ldo)))
+        assert rel_err(zz, z32.cpu().numpy()) < RTOL
+
+
 # ---------------------------------------------------------------------------------------------
 # tensor-core TRAINING path (cnf_flow_tcb.cu): stated bf16 tolerance on the gradient:
 #   max|g - g_ref| <= 2e-2 * max|g_ref| over the whole flat gradient for batches of >= 4096 samples,
