@@ -730,6 +730,37 @@ def run_ours(args):
         del x4, z4, l4, tr4, c4, e4
         torch.cuda.empty_cache()
 
+    # ---- conditioners with two wide hidden layers (flows/utils.py:6-31): the H x H middle Linear on tcgen05 -----------
+    if not args.no_extra:
+        n6 = 4_000_000
+        m6 = make_model(seed=7, wmult=30.0, hidden=[128, 128]).to(dev)
+        e6 = m6.engine()
+        e6.ensure(dev)
+        e6.pack(tc=True)
+        e6.pack()
+        x6, _ = synth_dev(n6, 6000 + rank, dev)
+        z6 = torch.empty_like(x6)
+        l6 = torch.empty(n6, dtype=torch.float32, device=dev)
+
+        def d6step(i):
+            _lib.call('cnf_flow_forward', ctypes.byref(e6.desc_tc), _ptr(e6.packed_tc), _ptr(e6.tables), _ptr(x6),
+                      _ptr(z6), _ptr(l6), None, ctypes.c_int64(n6), _stream(dev))
+        d6_ms = timed(d6step, few, 3)
+        n6f = 400_000
+        with torch.no_grad():
+            d6f_ms = timed(lambda i: e6.apply(x6[:n6f], repack=False), 3, 3)
+        f6 = 6 * 2 * 2 * (5 * 128 + 128 * 128 + 128 * 5)          # minimal flops per sample
+        d6_tf = f6 * n6 / (d6_ms * 1e-3) / 1e12
+        legs['two_hidden_layers'] = {
+            'what': 'K=10, 6 couplings, hidden_size=[128, 128], fwd+logdet: bf16 tcgen05 kernel (cnf_flow_tcm.cu) on %d '
+                    'samples per GPU; the fp32 kernel (flow_apply_deep_kernel) on %d' % (n6, n6f),
+            'value': world * n6 / (d6_ms * 1e-3), 'unit': UNIT, 'ms_per_step': d6_ms, 'dtype': 'bf16',
+            'fp32': {'value': world * n6f / (d6f_ms * 1e-3), 'unit': UNIT, 'ms_per_step': d6f_ms},
+            'roofline': {'bound': 'tensor', 'achieved': d6_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': d6_tf / tf_peak,
+                         'note': 'minimal %d flop/sample' % f6}}
+        del x6, z6, l6, m6, e6
+        torch.cuda.empty_cache()
+
     # ---- the reference's DEFAULT conditioner (NvpCouplingLayer(dim, hidden_size=[5, 5]), flows/flows.py:69) ----------
     if not args.no_extra:
         n5 = 10_000_000
@@ -952,6 +983,7 @@ def run_ours(args):
             'c5_job': g(legs.get('c5_job', {}).get(head_prec, {}).get('value')),
             'c5_ece': legs.get('c5_job', {}).get(head_prec, {}).get('ece'),
             'c4_fwd_bf16': g(legs.get('c4_forward', {}).get('value')),
+            'fwd_bf16_hidden_128_128': g(legs.get('two_hidden_layers', {}).get('value')),
             'fwd_fp32_hidden_5_5': g(legs.get('default_conditioner', {}).get('forward', {}).get('value')),
             'train_fp32_hidden_5_5': g(legs.get('default_conditioner', {}).get('train_step', {}).get('value')),
             'tensor_frac': round(ach_tf / tf_peak, 4) if head_prec == 'bf16' else None,
