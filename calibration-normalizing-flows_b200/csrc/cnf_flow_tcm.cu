@@ -1,5 +1,5 @@
 // bf16 tensor-core kernel of the coupling-flow stack for conditioners with TWO hidden layers of up to 128 units
-// each (flows/utils.py:6-31 allows any depth; flows/flows.py:69 defaults to two hidden layers), K up to 65 classes,
+// each, at least 16 (flows/utils.py:6-31 allows any depth; flows/flows.py:69 defaults to two hidden layers), K up to 65 classes,
 // sm_100a.  The H1 x H2 middle Linear is the one dense contraction of the path: [128 x 128] x [128 x 128] per tile
 // and net, eight full-width tcgen05.mma k-steps.
 //
@@ -49,7 +49,9 @@ struct TcmDims {
 
 bool tcm_dims(const CnfDims& d, TcmDims* t) {
   if (d.m != 2 || d.n_nets < 1) return false;
-  if (d.H[0] < 1 || d.H[0] > 128 || d.H[1] < 1 || d.H[1] > 128) return false;
+  // at least one 16-unit k-step per hidden layer: narrower nets (the reference's default [5, 5]) are no dense
+  // contraction and belong on the fp32 register kernels (15 G samples/s there)
+  if (d.H[0] < 16 || d.H[0] > 128 || d.H[1] < 16 || d.H[1] > 128) return false;
   if (d.d1 + 1 > 64 || d.d0 > 32) return false;
   t->K = d.K; t->L = d.L; t->d0 = d.d0; t->d1 = d.d1; t->nets = d.nets; t->n_nets = d.n_nets;
   t->H1p = cnf_round_up(d.H[0], 16);

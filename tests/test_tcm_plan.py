@@ -90,7 +90,7 @@ def test_tcm_plan_images_against_oracle(K, L, hidden, scale, shift, rflip):
 def test_tcm_shapes_outside_coverage_have_no_tc_blob():
     import cnf_b200  # noqa: F401
     from cnf_b200 import _lib
-    for K, hidden in ((10, [129, 64]), (10, [64, 200]), (80, [64, 64]), (10, [32, 32, 32])):
+    for K, hidden in ((10, [129, 64]), (10, [64, 200]), (80, [64, 64]), (10, [32, 32, 32]), (10, [5, 5]), (10, [64, 15])):
         desc, _keep = _lib.make_desc(K, 2, hidden, True, True, _lib.PREC_FP32)
         info = _lib.PlanInfo()
         _lib.call('cnf_plan_info_get', ctypes.byref(desc), ctypes.byref(info))
