@@ -96,8 +96,10 @@ int cnf_plan_info_get(const cnf_flow_desc* desc, cnf_plan_info* out);
 /* gather[i] = index into flat for packed float i, or -1 for structural zero.
  * tables = [pi (L+1)*K | cond L*d1 | trans L*d0] physical-slot index maps.     */
 int cnf_plan_build(const cnf_flow_desc* desc, int32_t* gather_host, int32_t* tables_host);
-/* Gather map of the tensor-core blob (bf16 UMMA images of both Linears, then the fp32
- * last-layer biases); *n = number of int32 entries, 0 if the shape is not covered.  */
+/* Gather map of the tensor-core blob (bf16 UMMA images of the Linears, then the fp32
+ * biases added in the epilogues); *n = number of int32 entries, 0 if the shape is not
+ * covered.  Covered (forward / inverse): one hidden layer with K <= 126 (any width), or two
+ * hidden layers of 16..128 units each with K <= 65 (flows/utils.py:6-31).               */
 int cnf_tc_gather_len(const cnf_flow_desc* desc, int64_t* n);
 int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* gather_tc_host);
 
