@@ -427,23 +427,23 @@ int cnf_tcm_pack(const CnfDims& d, const float* flat, const int32_t* gather_tc, 
 int cnf_tcm_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                   float* logdet, int64_t N, int inverse, cudaStream_t st);
 
-bool cnf_tcw_supported(const CnfDims& d) { TcwDims t; return d.m == 2 ? cnf_tcm_supported(d) : tcw_dims(d, &t); }
+bool cnf_tcw_supported(const CnfDims& d) { TcwDims t; return d.m >= 2 ? cnf_tcm_supported(d) : tcw_dims(d, &t); }
 
 long long cnf_tcw_blob_bytes(const CnfDims& d) {
   TcwDims t;
-  if (d.m == 2) return cnf_tcm_blob_bytes(d);
+  if (d.m >= 2) return cnf_tcm_blob_bytes(d);
   return tcw_dims(d, &t) ? (long long)t.blob_bytes : 0;
 }
 
 long long cnf_tcw_gather_len(const CnfDims& d) {
   TcwDims t;
-  if (d.m == 2) return cnf_tcm_gather_len(d);
+  if (d.m >= 2) return cnf_tcm_gather_len(d);
   return tcw_dims(d, &t) ? (long long)t.n_bf16 + t.n_f32 : 0;
 }
 
 int cnf_tcw_plan_build(const CnfDims& d, int32_t* g) {
   TcwDims t;
-  if (d.m == 2) return cnf_tcm_plan_build(d, g);
+  if (d.m >= 2) return cnf_tcm_plan_build(d, g);
   if (!tcw_dims(d, &t)) { cnf_set_error("wide tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   const int K = d.K, half = K / 2, H = d.H[0];
   const long long total = (long long)t.n_bf16 + t.n_f32;
@@ -485,7 +485,7 @@ int cnf_tcw_plan_build(const CnfDims& d, int32_t* g) {
 
 int cnf_tcw_pack(const CnfDims& d, const float* flat, const int32_t* gather_tc, void* packed_tc, cudaStream_t st) {
   TcwDims t;
-  if (d.m == 2) return cnf_tcm_pack(d, flat, gather_tc, packed_tc, st);
+  if (d.m >= 2) return cnf_tcm_pack(d, flat, gather_tc, packed_tc, st);
   if (!tcw_dims(d, &t)) { cnf_set_error("wide tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   int rc = cnf_pack_bf16(flat, gather_tc, packed_tc, t.n_bf16, st);
   if (rc) return rc;
@@ -498,7 +498,7 @@ int cnf_tcw_pack(const CnfDims& d, const float* flat, const int32_t* gather_tc, 
 int cnf_tcw_apply(const CnfDims& d, const void* packed_tc, const int32_t* tables, const float* x, float* z,
                   float* logdet, int64_t N, int inverse, cudaStream_t st) {
   TcwDims t;
-  if (d.m == 2) return cnf_tcm_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
+  if (d.m >= 2) return cnf_tcm_apply(d, packed_tc, tables, x, z, logdet, N, inverse, st);
   if (!tcw_dims(d, &t)) { cnf_set_error("wide tensor-core path not available for this shape"); return CNF_E_UNSUPPORTED; }
   CnfDevInfo di;
   { const int rc2 = cnf_dev_info(&di); if (rc2) return rc2; }

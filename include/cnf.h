@@ -98,8 +98,8 @@ int cnf_plan_info_get(const cnf_flow_desc* desc, cnf_plan_info* out);
 int cnf_plan_build(const cnf_flow_desc* desc, int32_t* gather_host, int32_t* tables_host);
 /* Gather map of the tensor-core blob (bf16 UMMA images of the Linears, then the fp32
  * biases added in the epilogues); *n = number of int32 entries, 0 if the shape is not
- * covered.  Covered (forward / inverse): one hidden layer with K <= 126 (any width), or two
- * hidden layers of 16..128 units each with K <= 65 (flows/utils.py:6-31).               */
+ * covered.  Covered (forward / inverse): one hidden layer with K <= 126 (any width), or two to
+ * four hidden layers of 16..128 units each with K <= 65 (flows/utils.py:6-31).          */
 int cnf_tc_gather_len(const cnf_flow_desc* desc, int64_t* n);
 int cnf_plan_build_tc(const cnf_flow_desc* desc, int32_t* gather_tc_host);
 

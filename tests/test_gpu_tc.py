@@ -109,22 +109,59 @@ def test_tc_wide_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda
         assert rel_err(xr[-1].cpu().numpy(), x) < RTOL
 
 
-@pytest.mark.parametrize('K,L,hidden,scale,shift,wmul', [(10, 6, [128, 128], True, True, 30.0), (3, 4, [32, 20], False, True, 60.0),
-                                                         (65, 2, [128, 17], True, False, 30.0), (20, 3, [100, 64], True, True, 40.0),
-                                                         (10, 5, [16, 128], True, True, 40.0), (33, 2, [48, 112], True, True, 40.0)])
-def test_tc_two_hidden_layer_kernel_vs_float64_oracle(K, L, hidden, scale, shift, wmul, cuda_device):
-    """Conditioners with two hidden layers of up to 128 units run on cnf_flow_tcm.cu (the H1 x H2 middle Linear as
-    full-width tcgen05 MMAs; flows/utils.py:6-31): forward, log-det and the inverse round trip against the float64
-    oracle within the stated bf16 tolerance, ragged sizes included, and against the fp32 kernel."""
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(100, 8, [512], True, True), (33, 3, [200], False, True), (40, 2, [24], True, True),
+                                                    (126, 2, [130], True, True), (20, 4, [300], True, False),
+                                                    (10, 6, [128], True, True), (14, 5, [100], True, True), (3, 4, [32], False, True)])
+def test_tc_single_hidden_layer_kernels_dense_weights_vs_float64_oracle(K, L, hidden, scale, shift, cuda_device):
+    """The resident-weight and the streamed-weight kernels (cnf_flow_tc.cu / cnf_flow_tcw.cu) with dense O(1) conditioner
+    weights, where the hidden layer -- not the last bias, as with the reference's wscale=0.001 init times a constant --
+    carries the output: forward, log-det, inverse round trip against the float64 oracle and the fp32 kernel."""
     import torch
     import cnf_b200
+    from helpers import set_dense_weights
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)],
+                         precision='bf16')
+    set_dense_weights(flow, seed=K + L)
+    like = orc.init_params(K, L, hidden, scale, shift)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), like)
+    flow.to(cuda_device)
+    assert flow.engine().tc_bytes > 0
+    for N in (300, 128 * 148 * 3 + 5):
+        x, _ = orc.synth_logits(N, K, seed=3 + N)
+        xt = torch.from_numpy(x).to(cuda_device)
+        with torch.no_grad():
+            zs, ld = flow(xt)
+            xr, ldr = flow.backward(zs[-1])
+            z32, ld32, _ = flow.engine().apply(xt)
+        zo, ldo = orc.flow_forward(params, x.astype(np.float64))
+        zz = zs[-1].cpu().numpy()
+        z0 = x[:, ::-1] if L % 2 else x
+        assert float(np.max(np.abs(zo[-1] - z0))) > 3e-2 * float(np.max(np.abs(zo[-1])))
+        assert rel_err(zz, zo[-1]) < RTOL
+        assert np.max(np.abs(ld.cpu().numpy().reshape(-1) - ldo)) < RTOL * max(1.0, np.max(np.abs(ldo)))
+        assert rel_err(xr[-1].cpu().numpy(), x) < RTOL
+        assert rel_err(z32.cpu().numpy(), zo[-1]) < 1e-5
+        assert np.max(np.abs(ld32.cpu().numpy().reshape(-1) - ldo)) < 1e-5 * max(1.0, np.max(np.abs(ldo)))
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(10, 6, [128, 128], True, True), (3, 4, [32, 20], False, True),
+                                                    (65, 2, [128, 17], True, False), (20, 3, [100, 64], True, True),
+                                                    (10, 5, [16, 128], True, True), (33, 2, [48, 112], True, True),
+                                                    (10, 4, [128, 128, 128], True, True), (7, 3, [32, 64, 16, 96], True, True),
+                                                    (40, 2, [64, 128, 80], False, True)])
+def test_tc_deep_kernel_vs_float64_oracle(K, L, hidden, scale, shift, cuda_device):
+    """Conditioners with two to four hidden layers of 16 .. 128 units run on cnf_flow_tcm.cu (the H x H middle Linears
+    as full-width tcgen05 MMAs; flows/utils.py:6-31): forward, log-det and the inverse round trip against the float64
+    oracle within the stated bf16 tolerance, ragged sizes included, and against the fp32 kernel.  Dense O(1) weights:
+    the hidden layers carry the output (measured: the flow moves z by 5 .. 45 % of its range, |log-det| up to 2)."""
+    import torch
+    import cnf_b200
+    from helpers import set_dense_weights
     torch.manual_seed(K + L)
     flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)],
                          precision='bf16')
-    with torch.no_grad():
-        for p in flow.parameters():
-            if p.requires_grad:
-                p.mul_(wmul)
+    set_dense_weights(flow, seed=K + L)
     like = orc.init_params(K, L, hidden, scale, shift)
     flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
     params = orc.unflatten(flat.astype(np.float64), like)
@@ -140,7 +177,9 @@ def test_tc_two_hidden_layer_kernel_vs_float64_oracle(K, L, hidden, scale, shift
         zo, ldo = orc.flow_forward(params, x.astype(np.float64))
         zz = zs[-1].cpu().numpy()
         assert np.isfinite(zz).all()
-        assert float(np.max(np.abs(zo[-1] - x))) > 1e-3 * float(np.max(np.abs(x)))      # the flow does something
+        if N >= 300:        # the conditioners do something: compare with the same stack at zero weights (flips only)
+            z0 = x[:, ::-1] if L % 2 else x
+            assert float(np.max(np.abs(zo[-1] - z0))) > 3e-2 * float(np.max(np.abs(zo[-1])))
         assert rel_err(zz, zo[-1]) < RTOL
         assert np.max(np.abs(ld.cpu().numpy().reshape(-1) - ldo)) < RTOL * max(1.0, np.max(np.abs(ldo)))
         assert rel_err(xr[-1].cpu().numpy(), x) < RTOL

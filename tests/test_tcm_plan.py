@@ -1,4 +1,4 @@
-"""CPU test of the two-hidden-layer tensor-core plan (cnf_flow_tcm.cu): the gather map of the bf16 phase images
+"""CPU test of the deep (two to four hidden layers) tensor-core plan (cnf_flow_tcm.cu): the gather map of the bf16 phase images
 (B1 | Bm | B2 in the no-swizzle K-major UMMA layout) and of the fp32 bias section, decoded in numpy with the layout
 formulas of the kernel's descriptors and evaluated against the float64 oracle (flows/flows.py:101-112,
 flows/utils.py:26-31).  No GPU needed: the planner is pure index logic."""
@@ -18,7 +18,9 @@ def _rup(x, m):
 @pytest.mark.parametrize('K,L,hidden,scale,shift,rflip', [(10, 6, [128, 128], True, True, False),
                                                           (3, 4, [32, 20], False, True, False),
                                                           (7, 3, [100, 64], True, True, True),
-                                                          (65, 2, [128, 17], True, False, False)])
+                                                          (65, 2, [128, 17], True, False, False),
+                                                          (10, 3, [64, 128, 32], True, True, False),
+                                                          (5, 2, [16, 48, 100, 128], True, True, True)])
 def test_tcm_plan_images_against_oracle(K, L, hidden, scale, shift, rflip):
     import cnf_b200  # noqa: F401
     from cnf_b200 import _lib
@@ -34,13 +36,22 @@ def test_tcm_plan_images_against_oracle(K, L, hidden, scale, shift, rflip):
     g = np.empty(n_g.value, dtype=np.int32)
     _lib.call('cnf_plan_build_tc', ctypes.byref(desc), g.ctypes.data_as(ctypes.c_void_p))
     d0, d1 = K // 2, K - K // 2
-    H1, H2 = hidden
-    H1p, H2p, K1, N2 = _rup(H1, 16), _rup(H2, 16), _rup(d1 + 1, 16), _rup(d0, 16)
+    m = len(hidden)
+    Hp = [_rup(h, 16) for h in hidden]
+    K1, N2 = _rup(d1 + 1, 16), _rup(d0, 16)
     n_nets = int(scale) + int(shift)
-    b1_el, bm_el, b2_el = 128 * K1, H1p * H2p, H2p * N2
-    ph_el = b1_el + bm_el + b2_el
+    b1_el = 128 * K1
+    # blocks of one phase: block b = [B1 if b == 0] | Bm_(b+1) | [B2 if b == m - 2]
+    mid_off, off = [], 0
+    for b in range(m - 1):
+        if b == 0:
+            off += b1_el
+        mid_off.append(off)
+        off += Hp[b] * Hp[b + 1]
+    b2_off = off
+    ph_el = off + Hp[-1] * N2
     n_bf16 = L * n_nets * ph_el
-    bm_floats = L * n_nets * 128
+    bm_floats = L * n_nets * (m - 1) * 128
     assert g.size == n_bf16 + bm_floats + L * 2 * N2
     assert info.tc_bytes == 2 * n_bf16 + 4 * (g.size - n_bf16)
     used = g[g >= 0]
@@ -67,14 +78,15 @@ def test_tcm_plan_images_against_oracle(K, L, hidden, scale, shift, rflip):
         for slot in range(n_nets):
             ph = img[(l * n_nets + slot) * ph_el:(l * n_nets + slot + 1) * ph_el]
             # A1 / B1: [k-block][row-block] core matrices, 128 rows: k-halves 1024 elements apart, k-step = 2 of them
-            B1 = kmajor(ph[:b1_el], 128, K1, 1024, 2048)[:H1p]
-            Bm = kmajor(ph[b1_el:b1_el + bm_el], H2p, H1p, H2p * 8, H2p * 16)
-            B2 = kmajor(ph[b1_el + bm_el:], N2, H2p, N2 * 8, N2 * 16)
-            bm = img[n_bf16 + (l * n_nets + slot) * 128: n_bf16 + (l * n_nets + slot) * 128 + H2p]
+            B1 = kmajor(ph[:b1_el], 128, K1, 1024, 2048)[:Hp[0]]
+            h = np.maximum(a1 @ B1.T, 0)
+            for b in range(m - 1):
+                Bm = kmajor(ph[mid_off[b]:mid_off[b] + Hp[b] * Hp[b + 1]], Hp[b + 1], Hp[b], Hp[b + 1] * 8, Hp[b + 1] * 16)
+                o0 = n_bf16 + ((l * n_nets + slot) * (m - 1) + b) * 128
+                h = np.maximum(h @ Bm.T + img[o0:o0 + Hp[b + 1]], 0)
+            B2 = kmajor(ph[b2_off:], N2, Hp[-1], N2 * 8, N2 * 16)
             b2 = img[n_bf16 + bm_floats + (l * 2 + slot) * N2: n_bf16 + bm_floats + (l * 2 + slot + 1) * N2]
-            h1 = np.maximum(a1 @ B1.T, 0)
-            h2 = np.maximum(h1 @ Bm.T + bm, 0)
-            o = h2 @ B2.T + b2
+            o = h @ B2.T + b2
             assert np.all(o[:, d0:] == 0)            # padded outputs are exact zeros (the kernel's EPI2 relies on it)
             outs.append(o[:, :d0])
         s = outs[0] if scale else np.zeros_like(outs[0])
@@ -90,7 +102,7 @@ def test_tcm_plan_images_against_oracle(K, L, hidden, scale, shift, rflip):
 def test_tcm_shapes_outside_coverage_have_no_tc_blob():
     import cnf_b200  # noqa: F401
     from cnf_b200 import _lib
-    for K, hidden in ((10, [129, 64]), (10, [64, 200]), (80, [64, 64]), (10, [32, 32, 32]), (10, [5, 5]), (10, [64, 15])):
+    for K, hidden in ((10, [129, 64]), (10, [64, 200]), (80, [64, 64]), (10, [32, 32, 8]), (10, [5, 5]), (10, [64, 15])):
         desc, _keep = _lib.make_desc(K, 2, hidden, True, True, _lib.PREC_FP32)
         info = _lib.PlanInfo()
         _lib.call('cnf_plan_info_get', ctypes.byref(desc), ctypes.byref(info))
