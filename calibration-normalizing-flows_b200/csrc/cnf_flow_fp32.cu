@@ -2023,6 +2023,7 @@ bool cnf_fp32r_supported(const cnf_flow_desc* desc, const CnfDims& d, const floa
                          int max_smem, size_t* smem_out, bool two_ok);
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st);
+bool cnf_fp32r_train_supported(const cnf_flow_desc* desc, const CnfDims& d, const float* x, int max_smem, size_t* smem_out);
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                     float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
                     int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st);
@@ -2195,7 +2196,7 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   if (head == CNF_HEAD_NLL && N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000))) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
-    if (!(sw && sw[0] == 'o') && cnf_fp32r_supported(desc, d, x, x, 0, g_max_smem - 1024, &smem_r, true)) {
+    if (!(sw && sw[0] == 'o') && cnf_fp32r_train_supported(desc, d, x, g_max_smem - 1024, &smem_r)) {
       rc = cnf_fp32r_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_r, g_num_sms,
                            g_max_smem, sw ? atoi(sw) : 0, rows_used, st);
       if (rc != CNF_E_SMEM) return rc;      // (too many layers for its shared-memory plan: the tile kernels below)

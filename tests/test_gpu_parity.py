@@ -911,3 +911,57 @@ def test_register_training_kernel_with_a_small_first_hidden_layer_vs_oracle(L, h
     eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
     assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 2e-4
     assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(3, 5, [3, 3], True, True), (3, 5, [3, 3], False, True), (3, 10, [5, 5], True, True),
+                                                    (2, 4, [4, 7], True, True), (4, 3, [5, 5], True, False), (5, 6, [2, 20], True, True),
+                                                    (7, 4, [5, 5], True, True), (8, 3, [3, 3], False, True), (9, 5, [5, 9], True, True),
+                                                    (10, 4, [5, 5], False, True), (3, 4, [32], False, True), (6, 3, [40], True, True)])
+@pytest.mark.parametrize('N,eps,gamma', [(1_500, 1e-7, 1.0), (5_003, 0.0, 1.0), (70_001, 0.0, 0.0)])
+def test_register_training_kernel_other_class_counts_vs_oracle(K, L, hidden, scale, shift, N, eps, gamma, cuda_device, monkeypatch):
+    """train_reg10_kernel<..., KK> for K = 2 .. 9 (cnf_flow_fp32rk.cu) and for flows without a scale or shift net: the
+    reference's notebook / script shapes (K = 3, hidden_size [3, 3] / [5, 5], NiceFlow and RealNvpFlow,
+    notebooks/simulated-predictions-flows.ipynb:214, 224; run_experiment3D.py:33-38).  Loss and gradient against the
+    float64 oracle (odd K: the middle logit is a conditioning dim of every layer), bitwise repeatable, dead
+    weight entries exactly zero, and against the generic tile kernels on the same batch."""
+    import torch
+    import cnf_b200
+    monkeypatch.setenv('CNF_LIVE_ENV', '1')
+    monkeypatch.setenv('CNF_FP32R_TRAIN', '0')      # single-hidden-layer shapes: forced on below 160,000 samples
+    torch.manual_seed(K + L + hidden[-1])
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)])
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(250.0)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), orc.init_params(K, L, hidden, scale, shift))
+    flow.to(cuda_device)
+    eng = flow.engine()
+    eng.ensure(cuda_device)
+    eng.pack()
+    x, y = orc.synth_logits(N, K, seed=N % 1000)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc, eps=eps, gamma=gamma)
+    grad = eng.flat_grad.cpu().numpy().copy()
+    loss, ce, ldm, grads, _ = orc.train_step_grads(params, x.astype(np.float64), y, eps=eps, gamma=gamma)
+    ref = orc.flatten(grads)
+    assert abs(-float(acc[0]) / N - loss) < 1e-5 * max(1.0, abs(loss))
+    assert abs(-float(acc[1]) / N - ce) < 1e-5 * max(1.0, abs(ce)) and float(acc[3]) == 0.0
+    assert abs(float(acc[2]) / N - ldm) < 1e-5 * max(1.0, abs(ldm))
+    assert np.max(np.abs(ref)) > 0
+    assert rel_err(grad, ref) < 2e-4, rel_err(grad, ref)
+    assert np.all(grad[ref == 0] == 0)
+    acc2 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc2, eps=eps, gamma=gamma)
+    assert np.array_equal(eng.flat_grad.cpu().numpy(), grad)
+    # forward-only (evaluation) pass of the same kernel
+    acc3 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc3, eps=eps, gamma=gamma, with_grad=False)
+    assert np.allclose(acc3.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-9)
+    monkeypatch.setenv('CNF_FP32R_TRAIN', 'off')
+    acc4 = torch.zeros(4, dtype=torch.float64, device=cuda_device)
+    eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
+    assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 2e-4
+    assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
