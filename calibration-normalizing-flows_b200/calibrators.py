@@ -169,16 +169,20 @@ class FusedNLLTrainer:
             e.sgd(self.lr, self.wd)
         e.pack(tc=(self.precision == 'bf16'), fp32=(self.precision != 'bf16'))
 
-    def step(self, xb=None, yb=None, n_batch_total=None):
+    def step(self, xb=None, yb=None, n_batch_total=None, acc=None):
         """One optimiser step on (xb, yb) (default: all local samples; an empty batch is a valid
         contribution of zero under torch.distributed).  Returns nothing; the summed loss statistics of the
-        batch are left in self.loss_acc (device)."""
+        batch are left in self.loss_acc (device) -- or ADDED to `acc` (float64 [4], device, zeroed by the caller)
+        when one is given: ``fit`` passes the history row the sums belong to, which saves a clear and a copy
+        launch per epoch."""
         e = self.engine
         xb = self.x if xb is None else xb
         yb = self.y if yb is None else yb
         n_tot = self.n_total if n_batch_total is None else n_batch_total
         nvtx = torch.cuda.nvtx
-        self.loss_acc.zero_()
+        loss_acc = self.loss_acc if acc is None else acc
+        if acc is None:
+            loss_acc.zero_()
         # single process, Adam without weight decay (the reference's defaults, calibrators.py:259): the partial
         # reduction, the update and the repack are ONE launch behind the training kernel
         fused_tail = (self.dist is None and self.optim == 'adam' and self.wd == 0.0 and xb.shape[0] > 0
@@ -187,7 +191,7 @@ class FusedNLLTrainer:
             fused_tail = (e.tc_tail_maps() is not None) if self.precision == 'bf16' else getattr(e, 'gather_one_to_one', False)
         nvtx.range_push('cnf.fwd_bwd')
         if fused_tail:
-            e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision,
+            e.nll_step(xb, yb, loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision,
                        reduce=False)
             nvtx.range_pop()
             nvtx.range_push('cnf.optim')
@@ -197,11 +201,11 @@ class FusedNLLTrainer:
                 e.reduce_adam_pack(self.lr, self.betas, self.adam_eps)
             nvtx.range_pop()
             return
-        e.nll_step(xb, yb, self.loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision)
+        e.nll_step(xb, yb, loss_acc, self.eps, self.gamma, n_tot, with_grad=True, precision=self.precision)
         nvtx.range_pop()
         if self.dist is not None:
             nvtx.range_push('cnf.all_reduce')
-            self._all_reduce_step(self.loss_acc)
+            self._all_reduce_step(loss_acc)
             nvtx.range_pop()
         nvtx.range_push('cnf.optim')
         self._optim_and_pack()
@@ -288,10 +292,10 @@ class FusedNLLTrainer:
                 # own evaluation pass.  Same kernels, same arithmetic: the history is unchanged.
                 if use_graph:
                     self.step_graph()       # the same step replayed as one captured graph launch
-                else:
-                    self.step()
-                if epoch > 0:
-                    hist[epoch - 1].copy_(self.loss_acc)
+                    if epoch > 0:
+                        hist[epoch - 1].copy_(self.loss_acc)
+                else:                       # the step's forward adds its loss sums straight into the history row
+                    self.step(acc=hist[epoch - 1] if epoch > 0 else None)
                 if epoch == epochs - 1:
                     self.evaluate(out=hist[epoch])
             else:
@@ -420,18 +424,20 @@ class HostStreamNLLTrainer(FusedNLLTrainer):
         if self.resident:
             self._loaded = True
 
-    def step(self, xb=None, yb=None, n_batch_total=None):
+    def step(self, xb=None, yb=None, n_batch_total=None, acc=None):
         if xb is not None or yb is not None:
             raise NotImplementedError('HostStreamNLLTrainer is full-batch (mini-batches need the samples resident)')
         if self.resident and self._loaded:
-            return super().step()
+            return super().step(acc=acc)
         nvtx = torch.cuda.nvtx
-        self.loss_acc.zero_()
+        loss_acc = self.loss_acc if acc is None else acc
+        if acc is None:
+            loss_acc.zero_()
         nvtx.range_push('cnf.fwd_bwd(streamed)')
-        self._streamed_pass(True, self.loss_acc)
+        self._streamed_pass(True, loss_acc)
         nvtx.range_pop()
         if self.dist is not None:
-            self._all_reduce_step(self.loss_acc)
+            self._all_reduce_step(loss_acc)
         self._optim_and_pack()
 
     def step_graph(self):
