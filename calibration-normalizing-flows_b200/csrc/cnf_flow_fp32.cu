@@ -2192,8 +2192,8 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // crossover (fp32r_crossover.py, us per fused pass, 32-sample-tile kernel / register kernel): N = 131,072: 819 / 953;
   // 200,000: 1232 / 994; 262,144: 1612 / 1216; 1 Mi: 6326 / 4594; 4 Mi: 25462 / 15689 (one wave of its 2048-sample
   // tiles takes ~0.95 ms whatever it holds, the tile kernel's time grows with N: they cross at ~155,000 samples).
-  // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 65,536 -- experiments)
-  if (head == CNF_HEAD_NLL && N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 65536 : 160000))) {
+  // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 1,024 -- experiments)
+  if (head == CNF_HEAD_NLL && N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 1024 : 160000))) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
     if (!(sw && sw[0] == 'o') && cnf_fp32r_train_supported(desc, d, x, g_max_smem - 1024, &smem_r)) {

@@ -17,8 +17,11 @@ def timeit(f, reps=300):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(reps): f()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps * 1e6
-for K, L, hidden, scale, N in ((3, 5, [3, 3], True, 1500), (3, 5, [3, 3], False, 1500), (3, 10, [5, 5], True, 1500), (3, 4, [32], False, 10000),
-                               (5, 6, [5, 5], True, 5000)):
+CASES = ((3, 5, [3, 3], True, 1500), (3, 5, [3, 3], False, 1500), (3, 10, [5, 5], True, 1500), (3, 4, [32], False, 10000),
+         (5, 6, [5, 5], True, 5000))
+if os.environ.get('SINGLE'):      # single-hidden-layer shapes at calibration-set sizes: where does the register kernel win?
+    CASES = tuple((K, L, [H], sc, N) for (K, L, sc) in ((3, 4, False), (10, 6, True)) for H in (16, 32, 64, 128) for N in (5000, 20000))
+for K, L, hidden, scale, N in CASES:
     x, y = data(N, K)
     out = []
     for sw in ('0' if len(hidden) == 1 else None, 'off'):
