@@ -476,6 +476,35 @@ class StackEngine:
                   _stream(self.device))
 
     @_guarded
+    def fit_full_batch(self, x, y, epochs, eps=1e-7, gamma=1.0, n_total=None, lr=1e-3, betas=(0.9, 0.999), adam_eps=1e-8):
+        """`epochs` full-batch fp32 Adam steps on (x, y) enqueued by ONE library call (cnf_fit_full_batch: per epoch the
+        fused NLL pass and the one-launch optimiser tail, no Python between the launches).  Returns the per-epoch loss
+        sums [epochs, 4] (float64, device) as ``FusedNLLTrainer.fit_loop`` defines them.  Needs a one-to-one gather map
+        (``gather_one_to_one``) and host-counted Adam steps; bitwise the same as nll_step(reduce=False) +
+        reduce_adam_pack repeated."""
+        N = x.shape[0]
+        n_total = N if n_total is None else n_total
+        hist = torch.empty((epochs, 4), dtype=torch.float64, device=x.device)
+        scratch = torch.empty(4, dtype=torch.float64, device=x.device)
+        self._check_batch(x, y, scratch)
+        if epochs <= 0:
+            return hist
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat)
+            self.adam_v = torch.zeros_like(self.flat)
+            self.adam_t = 0
+        self._want_partials()
+        _lib.call('cnf_fit_full_batch', ctypes.byref(self.desc), _ptr(self.packed), _ptr(self.tables), _ptr(x), _ptr(y),
+                  ctypes.c_int64(N), ctypes.c_float(eps), ctypes.c_float(gamma), ctypes.c_float(1.0 / max(n_total, 1)),
+                  _ptr(self.partials), _ptr(self.gather), _ptr(self.flat), _ptr(self.flat_grad), _ptr(self.adam_m),
+                  _ptr(self.adam_v), ctypes.c_int64(self.adam_t), ctypes.c_float(lr), ctypes.c_float(betas[0]),
+                  ctypes.c_float(betas[1]), ctypes.c_float(adam_eps), ctypes.c_int64(epochs), _ptr(hist), _ptr(scratch),
+                  _stream(x.device))
+        self.adam_t += epochs
+        self.version += epochs
+        return hist
+
+    @_guarded
     def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if getattr(self, 'adam_step_dev', None) is not None:      # steps were taken on the device-counted path
             return self.adam_dev(lr, betas, eps, weight_decay)

@@ -66,6 +66,8 @@ SIGNATURES = {
                               ctypes.POINTER(ctypes.c_int64), _P],
     'cnf_grad_reduce_tc': [_DESC, _P, _I64, _P, _P, _P],
     'cnf_reduce_adam_pack_rows': [_DESC, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P],
+    'cnf_fit_full_batch': [_DESC, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _P, _P, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32,
+                           _I64, _P, _P, _P],
     'cnf_reduce_adam_pack_tc': [_DESC, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _P],
     'cnf_adam_step': [_P, _P, _P, _P, _I64, _I64, _F32, _F32, _F32, _F32, _F32, _P],
     'cnf_adam_step_dev': [_P, _P, _P, _P, _I64, _P, _P, _F32, _F32, _F32, _F32, _F32, _P],

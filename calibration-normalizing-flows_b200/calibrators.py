@@ -282,8 +282,17 @@ class FusedNLLTrainer:
         # Every decision that shapes the sequence of collectives comes from (n_all, world, batch_size) only
         # (plan_fit), never from the rank-local shard size.
         full_batch, local_bs, steps_per_epoch, batch_totals = plan_fit(n_all, world, batch_size)
-        hist = torch.zeros((max(epochs, 0), 4), dtype=torch.float64, device=x.device)
         use_graph = full_batch and cuda_graph and self.dist is None
+        e = self.engine
+        # single process, full batch, fp32, Adam without weight decay (the reference's defaults, calibrators.py:259,
+        # 263-265): the whole epoch loop is enqueued by one library call -- the same two launches per epoch as step(),
+        # without the interpreter between them (K = 3, N = 1,500 notebook fits: 39 -> ~25 us per epoch)
+        if (full_batch and not use_graph and self.dist is None and epochs > 0 and n_local > 0 and self.precision != 'bf16'
+                and self.optim == 'adam' and self.wd == 0.0 and type(self).step is FusedNLLTrainer.step
+                and getattr(e, 'adam_step_dev', None) is None and getattr(e, 'gather_one_to_one', False)
+                and hasattr(e, 'fit_full_batch')):
+            return e.fit_full_batch(x, y, epochs, self.eps, self.gamma, self.n_total, self.lr, self.betas, self.adam_eps)
+        hist = torch.zeros((max(epochs, 0), 4), dtype=torch.float64, device=x.device)
         for epoch in range(epochs):
             if full_batch:
                 # The reference evaluates the whole set after every update (calibrators.py:297-317).  With the

@@ -260,3 +260,35 @@ extern "C" int cnf_sgd_step(float* params, const float* grad, int64_t n, float l
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
+
+
+// TorchFlowCalibrator.fit's full-batch epoch loop (calibrators.py:283-317) enqueued from C -- no host-language work
+// between the launches: `epochs` times the fused NLL training pass (cnf_nll_train_step_rows) and the one-launch
+// optimiser tail (cnf_reduce_adam_pack_rows).  The reference evaluates the whole set after every update (:297-317);
+// with the full batch that number IS the loss the next epoch's forward computes on the same weights and samples, so
+// epoch e's sums are taken from the training pass of epoch e + 1 and only the last epoch gets its own evaluation pass.
+// Same kernels in the same order as the step-by-step calls: the history and the parameters are bitwise the same.
+extern "C" int cnf_fit_full_batch(const cnf_flow_desc* desc, void* packed, const int32_t* tables, const float* x,
+                                  const int64_t* y, int64_t N, float eps, float gamma, float inv_n_total,
+                                  float* grad_partials, const int32_t* gather, float* flat, float* flat_grad,
+                                  float* exp_avg, float* exp_avg_sq, int64_t steps_before, float lr, float beta1,
+                                  float beta2, float adam_eps, int64_t epochs, double* hist, double* scratch4,
+                                  void* stream) {
+  if (epochs < 0 || steps_before < 0 || N < 1) { cnf_set_error("cnf_fit_full_batch: epochs, steps_before >= 0 and N >= 1"); return CNF_E_ARG; }
+  if (!hist || !scratch4 || !grad_partials) { cnf_set_error("cnf_fit_full_batch: null pointer"); return CNF_E_ARG; }
+  if (epochs == 0) return CNF_OK;
+  CNF_CHECK_CUDA(cudaMemsetAsync(scratch4, 0, 4 * sizeof(double), (cudaStream_t)stream));
+  CNF_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)epochs * 4 * sizeof(double), (cudaStream_t)stream));
+  for (int64_t e = 0; e < epochs; ++e) {
+    int64_t used = 0;
+    int rc = cnf_nll_train_step_rows(desc, packed, tables, x, y, N, eps, gamma, inv_n_total, grad_partials,
+                                     e == 0 ? scratch4 : hist + 4 * (e - 1), &used, stream);
+    if (rc) return rc;
+    rc = cnf_reduce_adam_pack_rows(desc, grad_partials, used, gather, flat, flat_grad, exp_avg, exp_avg_sq,
+                                   reinterpret_cast<float*>(packed), steps_before + e + 1, lr, beta1, beta2, adam_eps, stream);
+    if (rc) return rc;
+  }
+  int64_t used = 0;
+  return cnf_nll_train_step_rows(desc, packed, tables, x, y, N, eps, gamma, inv_n_total, nullptr, hist + 4 * (epochs - 1),
+                                 &used, stream);
+}

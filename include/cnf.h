@@ -189,6 +189,17 @@ int cnf_reduce_adam_pack_rows(const cnf_flow_desc* desc, const float* grad_parti
                               const int32_t* gather, float* flat, float* flat_grad, float* exp_avg,
                               float* exp_avg_sq, float* packed, int64_t step, float lr, float beta1, float beta2,
                               float eps, void* stream);
+/* The full-batch epoch loop of TorchFlowCalibrator.fit (calibrators.py:283-317, default batch_size = N) enqueued
+ * from C: per epoch cnf_nll_train_step_rows + cnf_reduce_adam_pack_rows, nothing else; hist: float64 [epochs, 4]
+ * device, row e = (sum(ce + gamma*ld), sum ce, sum ld, #non-finite) of the evaluation after update e (taken from the
+ * next epoch's forward; the last row from one evaluation pass at the end).  steps_before: optimiser steps already
+ * taken (Adam's bias correction continues from there); scratch4: float64 [4] device.  Bitwise what the same calls
+ * issued one by one produce. */
+int cnf_fit_full_batch(const cnf_flow_desc* desc, void* packed, const int32_t* tables, const float* x,
+                       const int64_t* y, int64_t N, float eps, float gamma, float inv_n_total,
+                       float* grad_partials, const int32_t* gather, float* flat, float* flat_grad, float* exp_avg,
+                       float* exp_avg_sq, int64_t steps_before, float lr, float beta1, float beta2, float adam_eps,
+                       int64_t epochs, double* hist, double* scratch4, void* stream);
 /* The same one-launch tail for the tensor-core training path: cnf_grad_reduce_tc + cnf_adam_step + cnf_pack_weights_tc.
  * scatter_tc: int32 [n_flat], the position of each flat entry in the gather map of cnf_plan_build_tc (-1: not packed);
  * both maps must be one-to-one on their live entries. */

@@ -965,3 +965,35 @@ def test_register_training_kernel_other_class_counts_vs_oracle(K, L, hidden, sca
     eng.nll_step(xt, yt, acc4, eps=eps, gamma=gamma)
     assert rel_err(eng.flat_grad.cpu().numpy(), grad) < 2e-4
     assert np.allclose(acc4.cpu().numpy()[:3], acc.cpu().numpy()[:3], rtol=1e-6)
+
+
+@pytest.mark.parametrize('K,L,hidden,scale', [(3, 5, [3, 3], True), (3, 4, [32], False), (10, 6, [128], True), (10, 6, [5, 5], True)])
+def test_fit_loop_enqueued_from_c_is_bitwise_the_stepwise_loop(K, L, hidden, scale, cuda_device):
+    """cnf_fit_full_batch (the epoch loop of TorchFlowCalibrator.fit, calibrators.py:283-317, enqueued by one library
+    call) against the same loop driven step by step from Python: identical history, parameters and Adam state."""
+    import torch
+    import cnf_b200
+    N, epochs = 1500, 25
+    x, y = orc.synth_logits(N, K, seed=K)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    out = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale) for _ in range(L)]).to(cuda_device)
+        tr = cnf_b200.FusedNLLTrainer(flow.engine(), xt, yt, lr=1e-3)
+        if fused:
+            hist = tr.fit_loop(epochs, N, None)
+        else:
+            hist = torch.zeros((epochs, 4), dtype=torch.float64, device=cuda_device)
+            for e in range(epochs):
+                tr.step(acc=hist[e - 1] if e > 0 else None)
+            tr.evaluate(out=hist[epochs - 1])
+        eng = flow.engine()
+        out.append((hist.cpu().numpy(), eng.flat.cpu().numpy().copy(), eng.adam_m.cpu().numpy().copy(), eng.adam_t))
+    assert np.isfinite(out[0][0]).all() and out[0][0][-1, 0] != out[0][0][0, 0]
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert out[0][3] == out[1][3] == epochs
+    # a second call continues the same optimiser (bias correction from step 26 on)
+    h2 = tr.fit_loop(3, N, None)
+    assert np.isfinite(h2.cpu().numpy()).all() and flow.engine().adam_t == epochs + 3

@@ -286,3 +286,18 @@ def test_non_relu_conditioners_fail_loudly():
     lay.t = torch.nn.Sequential(torch.nn.Linear(6, 6))
     with pytest.raises(NotImplementedError):
         build_engine([lay])
+
+
+def test_fit_full_batch_validates_arguments_without_a_device():
+    import cnf_b200  # noqa: F401
+    from cnf_b200 import _lib
+    lib = _lib.load()
+    desc, _keep = _lib.make_desc(3, 5, [3, 3], True, True)
+    one = ctypes.c_void_p(16)
+    args = lambda N, steps, epochs, hist: (ctypes.byref(desc), one, one, one, one, N, 1e-7, 1.0, 0.5, one, one, one, one, one, one,
+                                           steps, 1e-3, 0.9, 0.999, 1e-8, epochs, hist, one, None)
+    assert lib.cnf_fit_full_batch(*args(8, 0, -1, one)) == -1
+    assert lib.cnf_fit_full_batch(*args(0, 0, 2, one)) == -1
+    assert lib.cnf_fit_full_batch(*args(8, -3, 2, one)) == -1
+    assert lib.cnf_fit_full_batch(*args(8, 0, 2, None)) == -1
+    assert lib.cnf_fit_full_batch(*args(8, 0, 0, one)) == 0           # no epochs: nothing is touched
