@@ -916,7 +916,8 @@ def test_register_training_kernel_with_a_small_first_hidden_layer_vs_oracle(L, h
 @pytest.mark.parametrize('K,L,hidden,scale,shift', [(3, 5, [3, 3], True, True), (3, 5, [3, 3], False, True), (3, 10, [5, 5], True, True),
                                                     (2, 4, [4, 7], True, True), (4, 3, [5, 5], True, False), (5, 6, [2, 20], True, True),
                                                     (7, 4, [5, 5], True, True), (8, 3, [3, 3], False, True), (9, 5, [5, 9], True, True),
-                                                    (10, 4, [5, 5], False, True), (3, 4, [32], False, True), (6, 3, [40], True, True)])
+                                                    (10, 4, [5, 5], False, True), (3, 4, [32], False, True), (6, 3, [40], True, True),
+                                                    (10, 3, [40], False, True), (10, 2, [24], True, False)])
 @pytest.mark.parametrize('N,eps,gamma', [(1_500, 1e-7, 1.0), (5_003, 0.0, 1.0), (70_001, 0.0, 0.0)])
 def test_register_training_kernel_other_class_counts_vs_oracle(K, L, hidden, scale, shift, N, eps, gamma, cuda_device, monkeypatch):
     """train_reg10_kernel<..., KK> for K = 2 .. 9 (cnf_flow_fp32rk.cu) and for flows without a scale or shift net: the
