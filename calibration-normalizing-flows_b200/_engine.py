@@ -480,7 +480,7 @@ class StackEngine:
         """`epochs` full-batch fp32 Adam steps on (x, y) enqueued by ONE library call (cnf_fit_full_batch: per epoch the
         fused NLL pass and the one-launch optimiser tail, no Python between the launches).  Returns the per-epoch loss
         sums [epochs, 4] (float64, device) as ``FusedNLLTrainer.fit_loop`` defines them.  Needs a one-to-one gather map
-        (``gather_one_to_one``) and host-counted Adam steps; bitwise the same as nll_step(reduce=False) +
+        (``gather_one_to_one``) and host-counted Adam steps; the parameters come out bitwise as from nll_step(reduce=False) +
         reduce_adam_pack repeated."""
         N = x.shape[0]
         n_total = N if n_total is None else n_total

@@ -331,6 +331,7 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
   }
 #pragma unroll
   for (int i = 0; i < RD; ++i) {
+    if (i >= H1) break;       // units the first hidden layer does not have (zero records: they would add exact zeros)
     const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
     float wg[16];
 #pragma unroll
@@ -348,7 +349,7 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
       wg[RD] += ga;                                                      // db1[unit i]
     }
     const float tot = warp_reduce16(wg, lane);
-    if (goff1 >= 0 && i < H1) atomicAdd(Gn + goff1 + i, tot);
+    if (goff1 >= 0) atomicAdd(Gn + goff1 + i, tot);
   }
 }
 

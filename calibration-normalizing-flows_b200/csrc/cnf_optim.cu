@@ -267,7 +267,8 @@ extern "C" int cnf_sgd_step(float* params, const float* grad, int64_t n, float l
 // optimiser tail (cnf_reduce_adam_pack_rows).  The reference evaluates the whole set after every update (:297-317);
 // with the full batch that number IS the loss the next epoch's forward computes on the same weights and samples, so
 // epoch e's sums are taken from the training pass of epoch e + 1 and only the last epoch gets its own evaluation pass.
-// Same kernels in the same order as the step-by-step calls: the history and the parameters are bitwise the same.
+// Same kernels in the same order as the step-by-step calls: the parameters and the optimiser state are bitwise the same
+// (the loss sums are float64 atomic adds of per-CTA sums: equal up to their order).
 extern "C" int cnf_fit_full_batch(const cnf_flow_desc* desc, void* packed, const int32_t* tables, const float* x,
                                   const int64_t* y, int64_t N, float eps, float gamma, float inv_n_total,
                                   float* grad_partials, const int32_t* gather, float* flat, float* flat_grad,

@@ -193,8 +193,8 @@ int cnf_reduce_adam_pack_rows(const cnf_flow_desc* desc, const float* grad_parti
  * from C: per epoch cnf_nll_train_step_rows + cnf_reduce_adam_pack_rows, nothing else; hist: float64 [epochs, 4]
  * device, row e = (sum(ce + gamma*ld), sum ce, sum ld, #non-finite) of the evaluation after update e (taken from the
  * next epoch's forward; the last row from one evaluation pass at the end).  steps_before: optimiser steps already
- * taken (Adam's bias correction continues from there); scratch4: float64 [4] device.  Bitwise what the same calls
- * issued one by one produce. */
+ * taken (Adam's bias correction continues from there); scratch4: float64 [4] device.  The same kernels in the same order as
+ * the calls issued one by one: parameters and optimiser state come out bitwise equal. */
 int cnf_fit_full_batch(const cnf_flow_desc* desc, void* packed, const int32_t* tables, const float* x,
                        const int64_t* y, int64_t N, float eps, float gamma, float inv_n_total,
                        float* grad_partials, const int32_t* gather, float* flat, float* flat_grad, float* exp_avg,

@@ -971,7 +971,8 @@ def test_register_training_kernel_other_class_counts_vs_oracle(K, L, hidden, sca
 @pytest.mark.parametrize('K,L,hidden,scale', [(3, 5, [3, 3], True), (3, 4, [32], False), (10, 6, [128], True), (10, 6, [5, 5], True)])
 def test_fit_loop_enqueued_from_c_is_bitwise_the_stepwise_loop(K, L, hidden, scale, cuda_device):
     """cnf_fit_full_batch (the epoch loop of TorchFlowCalibrator.fit, calibrators.py:283-317, enqueued by one library
-    call) against the same loop driven step by step from Python: identical history, parameters and Adam state."""
+    call) against the same loop driven step by step from Python: the same history, bitwise the same parameters and Adam
+    state."""
     import torch
     import cnf_b200
     N, epochs = 1500, 25
@@ -992,7 +993,8 @@ def test_fit_loop_enqueued_from_c_is_bitwise_the_stepwise_loop(K, L, hidden, sca
         eng = flow.engine()
         out.append((hist.cpu().numpy(), eng.flat.cpu().numpy().copy(), eng.adam_m.cpu().numpy().copy(), eng.adam_t))
     assert np.isfinite(out[0][0]).all() and out[0][0][-1, 0] != out[0][0][0, 0]
-    assert np.array_equal(out[0][0], out[1][0])
+    # parameters and Adam state bitwise; the history rows are float64 atomic adds of per-CTA sums, whose order is free
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-12, atol=1e-9)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
     assert out[0][3] == out[1][3] == epochs
     # a second call continues the same optimiser (bias correction from step 26 on)
