@@ -478,6 +478,31 @@ def test_host_buffer_api_matches_device_api(precision, cuda_device):
     assert rel_err(zi.numpy(), x) < (1e-2 if precision == 'bf16' else 5e-5)
 
 
+@pytest.mark.parametrize('K,hidden', [(10, [128, 128]), (20, [64, 96, 32]), (100, [512])])
+def test_host_buffer_api_on_the_streamed_weight_tensor_core_kernels(K, hidden, cuda_device):
+    """cnf_flow_apply_host with the bf16 kernels that stream their weights (cnf_flow_tcw.cu, cnf_flow_tcm.cu): the
+    zero-copy launch on pinned host pointers (calls of <= 2^21 rows) and the chunked copy-engine pipeline give
+    exactly what the device-resident call gives, ragged sizes included."""
+    import torch
+    import cnf_b200
+    from helpers import set_dense_weights
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden) for _ in range(3)], precision='bf16')
+    set_dense_weights(flow, seed=K)
+    flow.to(cuda_device)
+    eng = flow.engine()
+    assert eng.tc_bytes > 0
+    for N, chunk in ((70_003, None), (70_003, 16_384)):
+        x, _ = orc.synth_logits(N, K, seed=9)
+        xh = torch.from_numpy(x).pin_memory()
+        zh, lh = eng.apply_host(xh, precision='bf16', device=cuda_device, chunk=chunk)
+        z, ld, _ = eng.apply(torch.from_numpy(x).to(cuda_device), precision='bf16')
+        torch.cuda.synchronize()
+        assert torch.equal(zh, z.cpu()) and torch.equal(lh, ld.cpu())
+        xi, li = eng.apply_host(zh, inverse=True, precision='bf16', device=cuda_device, chunk=chunk)
+        torch.cuda.synchronize()
+        assert rel_err(xi.numpy(), x) < 1e-2
+
+
 def test_affine_constant_layer_and_tempscaler_vs_reference(cuda_device):
     """AffineConstantLayer between coupling layers (loaded through the reference's
     own state_dict keys), forward / inverse / autograd; TempScaler forward and dT."""
