@@ -209,6 +209,38 @@ __device__ __forceinline__ void stage_weights_reg10(const CnfDims& d, const floa
 // v[0..16) hold one value per index on every lane; on return v[0] of lane L is the warp-wide sum of value
 // reduce16_index(L).  8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5.
 __device__ __forceinline__ int reduce16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+// The same over 8 values (K <= 5: a hidden unit's weight gradients are at most 2 + 5 + 1 values): 4 + 2 + 1 + 1 + 1 = 9
+// shuffles; on return v[0] of lane L is the warp-wide sum of value reduce8_index(L), the same on the 4 lanes of a group.
+__device__ __forceinline__ int reduce8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int w = 4, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < w) {
+        const float send = up ? v[i] : v[i + w];
+        const float keep = up ? v[i + w] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+  const float t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+  return t + __shfl_xor_sync(0xffffffffu, t, 1);
+}
+// Where a hidden unit's weight-gradient values sit in the reduced vector.  K >= 6: 16 values, [0,5) last-Linear row
+// entries of output position e, [5,10) the Linear in front of the streamed units (input e), 10 its bias.  K <= 5 (at
+// most two transformed and three conditioning dims): 8 values, [0,2) outputs, [2,7) inputs, 7 the bias.
+template <int KK> struct GradLayout {
+  static constexpr bool SMALL = KK <= 5;
+  static constexpr int NV = SMALL ? 8 : 16, NO = SMALL ? 2 : RD, P_O = 0, P_I = SMALL ? 2 : RD, P_B = SMALL ? 7 : 10;
+  static constexpr int PB_S = SMALL ? 4 : 8;     // bias butterfly: shift-net sums at [0, NO), scale-net sums at [PB_S, PB_S + NO)
+  static __device__ __forceinline__ int index(int lane) { return SMALL ? reduce8_index(lane) : reduce16_index(lane); }
+  static __device__ __forceinline__ bool writer(int lane) { return SMALL ? (lane & 3) == 0 : (lane & 1) == 0; }
+};
+template <int NV> struct WarpReduce;
+template <> struct WarpReduce<16> { static __device__ __forceinline__ float run(float (&v)[16], int lane); };
+template <> struct WarpReduce<8> { static __device__ __forceinline__ float run(float (&v)[8], int lane) { return warp_reduce8(v, lane); } };
 __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 #pragma unroll
   for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
@@ -224,20 +256,22 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
+__device__ __forceinline__ float WarpReduce<16>::run(float (&v)[16], int lane) { return warp_reduce16(v, lane); }
 
 // Backward of one conditioner net for this thread's SPT samples (c: conditioning values, go: gradient on the net's
 // five outputs).  Adds W1^T gh into gc and the weight gradients into the warp's partial row Gn (packed layout of one
 // net; goff = this lane's entry offset for reduce16_index(lane), -1 for none, see train kernel).
-template <int SPT, int U>
+template <int SPT, int U, int KK = RK>
 __device__ __forceinline__ void net_backward(const float4* __restrict__ w, int Hp, const float (&c)[SPT][RD],
                                              const float (&go)[SPT][RD], float (&gc)[SPT][RD], float* __restrict__ Gn,
                                              int goff, int lane) {
 #pragma unroll U
   for (int h = 0; h < Hp; ++h) {
     const float4 v0 = w[3 * h], v1 = w[3 * h + 1], v2 = w[3 * h + 2];
-    float wg[16];
+    using GL = GradLayout<KK>;
+    float wg[GL::NV];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) wg[i] = 0.f;
+    for (int i = 0; i < GL::NV; ++i) wg[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       float a = fmaf(v0.x, c[k][0], v1.y);
@@ -258,13 +292,12 @@ __device__ __forceinline__ void net_backward(const float4* __restrict__ w, int H
       gc[k][3] = fmaf(v0.w, gh, gc[k][3]);
       gc[k][4] = fmaf(v1.x, gh, gc[k][4]);
 #pragma unroll
-      for (int e = 0; e < RD; ++e) {
-        wg[e] = fmaf(r, go[k][e], wg[e]);           // dW2[slot e][h]
-        wg[RD + e] = fmaf(gh, c[k][e], wg[RD + e]); // dW1[h][slot e]
-      }
-      wg[10] += gh;                                 // db1[h]
+      for (int e = 0; e < GL::NO; ++e) wg[GL::P_O + e] = fmaf(r, go[k][e], wg[GL::P_O + e]);      // dW2[slot e][h]
+#pragma unroll
+      for (int e = 0; e < RD; ++e) wg[GL::P_I + e] = fmaf(gh, c[k][e], wg[GL::P_I + e]);          // dW1[h][slot e]
+      wg[GL::P_B] += gh;                                                                          // db1[h]
     }
-    const float tot = warp_reduce16(wg, lane);
+    const float tot = WarpReduce<GL::NV>::run(wg, lane);
     if (goff >= 0) atomicAdd(Gn + goff + h, tot);
   }
 }
@@ -274,7 +307,7 @@ __device__ __forceinline__ void net_backward(const float4* __restrict__ w, int H
 // layer's activations, and a last pass over the five first-layer units forms W1^T ga, dW1 and db1.
 // goff: entry offset of this lane for the second-layer / last-Linear values (0..4 dW3 of output slot e, 5..9 dWm from
 // first-layer unit e, 10 dbm); goff1: for the first-layer values (0..4 dW1 of input slot e, 5 db1); -1 for none.
-template <int SPT, int U>
+template <int SPT, int U, int KK = RK>
 __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, int Hn, int H1, const float (&c)[SPT][RD],
                                                 const float (&go)[SPT][RD], float (&gc)[SPT][RD], float* __restrict__ Gn,
                                                 int goff, int goff1, int lane) {
@@ -297,9 +330,10 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
 #pragma unroll U
   for (int h = 0; h < Hn; ++h) {
     const float4 v0 = wu[3 * h], v1 = wu[3 * h + 1], v2 = wu[3 * h + 2];
-    float wg[16];
+    using GL = GradLayout<KK>;
+    float wg[GL::NV];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) wg[i] = 0.f;
+    for (int i = 0; i < GL::NV; ++i) wg[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       float a = fmaf(v0.x, h1[k][0], v1.y);
@@ -320,22 +354,21 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
       gh1[k][3] = fmaf(v0.w, gh, gh1[k][3]);
       gh1[k][4] = fmaf(v1.x, gh, gh1[k][4]);
 #pragma unroll
-      for (int e = 0; e < RD; ++e) {
-        wg[e] = fmaf(r, go[k][e], wg[e]);              // dW3[slot e][h]
-        wg[RD + e] = fmaf(gh, h1[k][e], wg[RD + e]);   // dWm[first-layer unit e][h]
-      }
-      wg[10] += gh;                                    // dbm[h]
+      for (int e = 0; e < GL::NO; ++e) wg[GL::P_O + e] = fmaf(r, go[k][e], wg[GL::P_O + e]);      // dW3[slot e][h]
+#pragma unroll
+      for (int e = 0; e < RD; ++e) wg[GL::P_I + e] = fmaf(gh, h1[k][e], wg[GL::P_I + e]);         // dWm[first-layer unit e][h]
+      wg[GL::P_B] += gh;                                                                          // dbm[h]
     }
-    const float tot = warp_reduce16(wg, lane);
+    const float tot = WarpReduce<GL::NV>::run(wg, lane);
     if (goff >= 0) atomicAdd(Gn + goff + h, tot);
   }
 #pragma unroll
   for (int i = 0; i < RD; ++i) {
     if (i >= H1) break;       // units the first hidden layer does not have (zero records: they would add exact zeros)
     const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
-    float wg[16];
+    float wg[GradLayout<KK>::NV];      // (the first-layer values sit at [0, 5) and 5 in either layout)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) wg[j] = 0.f;
+    for (int j = 0; j < GradLayout<KK>::NV; ++j) wg[j] = 0.f;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const float ga = h1[k][i] > 0.f ? gh1[k][i] : 0.f;
@@ -348,7 +381,7 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
       for (int e = 0; e < RD; ++e) wg[e] = fmaf(ga, c[k][e], wg[e]);   // dW1[unit i][slot e]
       wg[RD] += ga;                                                      // db1[unit i]
     }
-    const float tot = warp_reduce16(wg, lane);
+    const float tot = WarpReduce<GradLayout<KK>::NV>::run(wg, lane);
     if (goff1 >= 0) atomicAdd(Gn + goff1 + i, tot);
   }
 }
@@ -378,8 +411,9 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
   const int TS = R_NT * SPT;
   const int64_t ntiles = (N + TS - 1) / TS;
   const bool rev_io = (L & 1) != 0;
-  const int vidx = reduce16_index(lane);                  // which of the 16 reduced values this lane ends up holding
-  const bool writer = (lane & 1) == 0;
+  using GL = GradLayout<KK>;
+  const int vidx = GL::index(lane);                       // which of the reduced values this lane ends up holding
+  const bool writer = GL::writer(lane);
   float* Grow = do_bwd ? partials + ((size_t)blockIdx.x * (R_NT / 32) + warp) * d.n_packed : nullptr;
   double a_loss = 0.0, a_ce = 0.0, a_ld = 0.0, a_bad = 0.0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -469,20 +503,21 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
       const int* mp = maps + l * 10;
       float* Gl = Grow + (size_t)l * d.layer_stride;
       // this lane's entry in a net's packed gradient block for the value it holds after the butterfly:
-      // values 0..4 = dW(last Linear) of output slot e, 5..9 = dW(the Linear in front of the streamed units) of its
+      // (GradLayout; K >= 6:) values 0..4 = dW(last Linear) of output slot e, 5..9 = dW(the Linear in front of the streamed units) of its
       // input e (a conditioning slot, or with M2 a first-layer unit), 10 = that Linear's bias
       int goff = -1, goff1 = -1;
       if (writer) {         // (positions K does not use have no packed entry: -1)
-        if (vidx < 5) goff = mp[5 + vidx] >= 0 ? d.w_off[last] + mp[5 + vidx] * Hrow : -1;
-        else if (vidx < 10) goff = M2 ? (vidx - 5 < d.H[0] ? d.w_off[1] + (vidx - 5) * Hrow : -1)
-                                      : (mp[vidx - 5] >= 0 ? d.w_off[0] + mp[vidx - 5] * Hrow : -1);
-        else if (vidx == 10) goff = d.b_off[last - 1];
+        if (vidx < GL::P_O + GL::NO) goff = mp[5 + vidx - GL::P_O] >= 0 ? d.w_off[last] + mp[5 + vidx - GL::P_O] * Hrow : -1;
+        else if (vidx >= GL::P_I && vidx < GL::P_I + RD)
+          goff = M2 ? (vidx - GL::P_I < d.H[0] ? d.w_off[1] + (vidx - GL::P_I) * Hrow : -1)
+                    : (mp[vidx - GL::P_I] >= 0 ? d.w_off[0] + mp[vidx - GL::P_I] * Hrow : -1);
+        else if (vidx == GL::P_B) goff = d.b_off[last - 1];
         if (M2) {                                   // first-layer values: 0..4 dW1 of input slot e, 5 db1
           if (vidx < 5) goff1 = mp[vidx] >= 0 ? d.w_off[0] + mp[vidx] * d.Hp[0] : -1;
           else if (vidx == 5) goff1 = d.b_off[0];
         }
       }
-      const int boff = (writer && vidx < 5 && mp[5 + vidx] >= 0) ? d.b_off[last] + mp[5 + vidx] : -1;      // db(last) of output slot vidx
+      const int boff = (writer && vidx < GL::NO && mp[5 + vidx] >= 0) ? d.b_off[last] + mp[5 + vidx] : -1;      // db(last) of output slot vidx
       // Register pressure: of the four [SPT][5] blocks of a layer (conditioning values c, transformed values t and the
       // gradients on both) only two or three are used inside each hidden-unit loop; the others wait in a per-thread
       // shared-memory slot (park[slot][value][tid]: conflict-free), which is what lets SPT reach 8.
@@ -532,17 +567,18 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
             o[k][q] = gy * expf(o[k][q]);                                // g_x of the transformed half
           }
         {
-          float wb[16];
+          float wb[GL::NV];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) wb[i] = 0.f;
+          for (int i = 0; i < GL::NV; ++i) wb[i] = 0.f;
 #pragma unroll
           for (int k = 0; k < SPT; ++k)
 #pragma unroll
-            for (int q = 0; q < RD; ++q) { wb[q] += gt[k][q]; wb[8 + q] += gs[k][q]; }
-          // values 0..4: db2 of the shift net, 8..12: db2 of the scale net
-          const float tot = warp_reduce16(wb, lane);
+            for (int q = 0; q < GL::NO; ++q) { wb[q] += gt[k][q]; wb[GL::PB_S + q] += gs[k][q]; }
+          // values [0, NO): db2 of the shift net, [PB_S, PB_S + NO): db2 of the scale net
+          const float tot = WarpReduce<GL::NV>::run(wb, lane);
           if (boff >= 0 && (nets & 2)) atomicAdd(Gl + off_t + boff, tot);
-          if (writer && vidx >= 8 && vidx < 13 && (nets & 1) && mp[5 + vidx - 8] >= 0) atomicAdd(Gl + d.b_off[last] + mp[5 + vidx - 8], tot);
+          if (writer && vidx >= GL::PB_S && vidx < GL::PB_S + GL::NO && (nets & 1) && mp[5 + vidx - GL::PB_S] >= 0)
+            atomicAdd(Gl + d.b_off[last] + mp[5 + vidx - GL::PB_S], tot);
         }
         park_put(1, t);          // x: final for this layer
         park_put(2, o);          // g_x of the transformed half: becomes gt below
@@ -550,13 +586,13 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
         park_put(0, gs);
         // shift net first (its output gradient is g_y itself), then the scale net
         if (nets & 2) {
-          if constexpr (M2) net_backward_m2<SPT, U>(w + ns4, Hp, d.H[0], c, gt, gcnd, Gl + off_t, goff, goff1, lane);
-          else              net_backward<SPT, U>(w + ns4, Hp, c, gt, gcnd, Gl + off_t, goff, lane);
+          if constexpr (M2) net_backward_m2<SPT, U, KK>(w + ns4, Hp, d.H[0], c, gt, gcnd, Gl + off_t, goff, goff1, lane);
+          else              net_backward<SPT, U, KK>(w + ns4, Hp, c, gt, gcnd, Gl + off_t, goff, lane);
         }
         park_get(0, gt);         // gs
         if (nets & 1) {
-          if constexpr (M2) net_backward_m2<SPT, U>(w, Hp, d.H[0], c, gt, gcnd, Gl, goff, goff1, lane);
-          else              net_backward<SPT, U>(w, Hp, c, gt, gcnd, Gl, goff, lane);
+          if constexpr (M2) net_backward_m2<SPT, U, KK>(w, Hp, d.H[0], c, gt, gcnd, Gl, goff, goff1, lane);
+          else              net_backward<SPT, U, KK>(w, Hp, c, gt, gcnd, Gl, goff, lane);
         }
         park_get(1, t);
         park_get(2, gt);
