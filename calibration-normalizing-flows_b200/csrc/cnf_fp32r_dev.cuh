@@ -366,9 +366,9 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
   for (int i = 0; i < RD; ++i) {
     if (i >= H1) break;       // units the first hidden layer does not have (zero records: they would add exact zeros)
     const float4 v0 = w[2 * i], v1 = w[2 * i + 1];
-    float wg[GradLayout<KK>::NV];      // (the first-layer values sit at [0, 5) and 5 in either layout)
+    float wg[8];      // six values per first-layer unit: the 8-value butterfly whatever K is (goff1 follows reduce8_index)
 #pragma unroll
-    for (int j = 0; j < GradLayout<KK>::NV; ++j) wg[j] = 0.f;
+    for (int j = 0; j < 8; ++j) wg[j] = 0.f;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const float ga = h1[k][i] > 0.f ? gh1[k][i] : 0.f;
@@ -381,7 +381,7 @@ __device__ __forceinline__ void net_backward_m2(const float4* __restrict__ w, in
       for (int e = 0; e < RD; ++e) wg[e] = fmaf(ga, c[k][e], wg[e]);   // dW1[unit i][slot e]
       wg[RD] += ga;                                                      // db1[unit i]
     }
-    const float tot = WarpReduce<GradLayout<KK>::NV>::run(wg, lane);
+    const float tot = warp_reduce8(wg, lane);
     if (goff1 >= 0) atomicAdd(Gn + goff1 + i, tot);
   }
 }
@@ -512,10 +512,11 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
           goff = M2 ? (vidx - GL::P_I < d.H[0] ? d.w_off[1] + (vidx - GL::P_I) * Hrow : -1)
                     : (mp[vidx - GL::P_I] >= 0 ? d.w_off[0] + mp[vidx - GL::P_I] * Hrow : -1);
         else if (vidx == GL::P_B) goff = d.b_off[last - 1];
-        if (M2) {                                   // first-layer values: 0..4 dW1 of input slot e, 5 db1
-          if (vidx < 5) goff1 = mp[vidx] >= 0 ? d.w_off[0] + mp[vidx] * d.Hp[0] : -1;
-          else if (vidx == 5) goff1 = d.b_off[0];
-        }
+      }
+      if (M2 && (lane & 3) == 0) {                  // first-layer values (8-value butterfly): 0..4 dW1 of input slot e, 5 db1
+        const int v8 = reduce8_index(lane);
+        if (v8 < 5) goff1 = mp[v8] >= 0 ? d.w_off[0] + mp[v8] * d.Hp[0] : -1;
+        else if (v8 == 5) goff1 = d.b_off[0];
       }
       const int boff = (writer && vidx < GL::NO && mp[5 + vidx] >= 0) ? d.b_off[last] + mp[5 + vidx] : -1;      // db(last) of output slot vidx
       // Register pressure: of the four [SPT][5] blocks of a layer (conditioning values c, transformed values t and the
