@@ -2026,7 +2026,8 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
 bool cnf_fp32r_train_supported(const cnf_flow_desc* desc, const CnfDims& d, const float* x, int max_smem, size_t* smem_out);
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                     float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                    int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st);
+                    int sms, int max_smem, int variant, int64_t* rows_out, const float* gz_ext, const float* gld_ext,
+                    cudaStream_t st);
 
 int cnf_fp32_apply(const cnf_flow_desc* desc, const float* packed, const int32_t* tables, const float* x, float* z,
                    float* logdet, float* zs, int64_t N, int inverse, cudaStream_t st) {
@@ -2193,12 +2194,16 @@ int cnf_fp32_train(const cnf_flow_desc* desc, const float* packed, const int32_t
   // 200,000: 1232 / 994; 262,144: 1612 / 1216; 1 Mi: 6326 / 4594; 4 Mi: 25462 / 15689 (one wave of its 2048-sample
   // tiles takes ~0.95 ms whatever it holds, the tile kernel's time grows with N: they cross at ~155,000 samples).
   // (CNF_FP32R_TRAIN: "off" disables, a digit forces a variant at any N >= 1,024 -- experiments)
-  if (head == CNF_HEAD_NLL && N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 1024 : 160000))) {
+  // (also the external head -- the autograd backward of the drop-in Flow, run_experiment3D.py:133-134 -- when the
+  //  caller wants no input gradient: K = 3, 10 x [5, 5], N = 1,500: 275 -> ~70 us)
+  if ((head == CNF_HEAD_NLL || (head == CNF_HEAD_EXTERNAL && gx == nullptr)) &&
+      N >= (d.m == 2 ? 1024 : (cnf_switch(CNF_SW_FP32R_TRAIN) ? 1024 : 160000))) {
     const char* sw = cnf_switch(CNF_SW_FP32R_TRAIN);
     size_t smem_r = 0;
     if (!(sw && sw[0] == 'o') && cnf_fp32r_train_supported(desc, d, x, g_max_smem - 1024, &smem_r)) {
       rc = cnf_fp32r_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_r, g_num_sms,
-                           g_max_smem, sw ? atoi(sw) : 0, rows_used, st);
+                           g_max_smem, sw ? atoi(sw) : 0, rows_used, head == CNF_HEAD_EXTERNAL ? gz : nullptr,
+                           head == CNF_HEAD_EXTERNAL ? gld : nullptr, st);
       if (rc != CNF_E_SMEM) return rc;      // (too many layers for its shared-memory plan: the tile kernels below)
     }
   }

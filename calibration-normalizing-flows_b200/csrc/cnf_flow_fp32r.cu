@@ -177,7 +177,7 @@ bool cnf_fp32r_train_supported(const cnf_flow_desc* desc, const CnfDims& d, cons
 
 int cnf_fp32rk_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                      float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                     int sms, int max_smem, int64_t* rows_out, cudaStream_t st);
+                     int sms, int max_smem, int64_t* rows_out, const float* gz_ext, const float* gld_ext, cudaStream_t st);
 
 int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, float* z, float* logdet,
                     int64_t N, int inverse, const CnfTail* tail, size_t smem, int sms, int variant, cudaStream_t st) {
@@ -228,8 +228,9 @@ int cnf_fp32r_apply(const CnfDims& d, const float* packed, const int32_t* tables
 // Fused NLL training step on the register-resident kernel; rows_used = partial rows written (one per warp).
 int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                     float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                    int sms, int max_smem, int variant, int64_t* rows_out, cudaStream_t st) {
-  if (d.K != RK) return cnf_fp32rk_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_fwd, sms, max_smem, rows_out, st);
+                    int sms, int max_smem, int variant, int64_t* rows_out, const float* gz_ext, const float* gld_ext,
+                    cudaStream_t st) {
+  if (d.K != RK) return cnf_fp32rk_train(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_fwd, sms, max_smem, rows_out, gz_ext, gld_ext, st);
 #define TVX(NT, SPT, U, MB, M2)                                                                                     \
   do {                                                                                                               \
     const size_t smem = smem_fwd + (size_t)3 * SPT * RD * NT * sizeof(float);                                       \
@@ -247,7 +248,7 @@ int cnf_fp32r_train(const CnfDims& d, const float* packed, const int32_t* tables
     const int64_t rows = (int64_t)grid * (NT / 32);                                                                  \
     if (rows_out) *rows_out = rows;                                                                                  \
     if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)(rows_out ? rows : d.grad_rows_max) * d.n_packed * sizeof(float), st)); \
-    train_reg10_kernel<NT, SPT, U, MB, M2><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n); \
+    train_reg10_kernel<NT, SPT, U, MB, M2><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, gz_ext, gld_ext); \
     CNF_CHECK_CUDA(cudaGetLastError());                                                                              \
     return CNF_OK;                                                                                                   \
   } while (0)

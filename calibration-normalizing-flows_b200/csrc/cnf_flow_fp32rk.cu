@@ -14,7 +14,7 @@ namespace {
 template <int KK, int NT, int SPT, int MB, bool M2>
 int launch_train_k(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                    float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                   int sms, int max_smem, int64_t* rows_out, cudaStream_t st) {
+                   int sms, int max_smem, int64_t* rows_out, const float* gz_ext, const float* gld_ext, cudaStream_t st) {
   const size_t smem = smem_fwd + (size_t)3 * SPT * RD * NT * sizeof(float);
   if ((long long)smem > max_smem - 1024) return CNF_E_SMEM;
   int rc = cnf_kernel_smem(train_reg10_kernel<NT, SPT, 2, MB, M2, KK>, smem);
@@ -30,7 +30,7 @@ int launch_train_k(const CnfDims& d, const float* packed, const int32_t* tables,
   const int64_t rows = (int64_t)grid * (NT / 32);
   if (rows_out) *rows_out = rows;
   if (partials) CNF_CHECK_CUDA(cudaMemsetAsync(partials, 0, (size_t)(rows_out ? rows : d.grad_rows_max) * d.n_packed * sizeof(float), st));
-  train_reg10_kernel<NT, SPT, 2, MB, M2, KK><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n);
+  train_reg10_kernel<NT, SPT, 2, MB, M2, KK><<<grid, NT, smem, st>>>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, gz_ext, gld_ext);
   CNF_CHECK_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -38,12 +38,12 @@ int launch_train_k(const CnfDims& d, const float* packed, const int32_t* tables,
 template <int KK>
 int train_k(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
             float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd, int sms,
-            int max_smem, int64_t* rows_out, cudaStream_t st) {
+            int max_smem, int64_t* rows_out, const float* gz_ext, const float* gld_ext, cudaStream_t st) {
   // the largest tile that still gives every SM one: 128 x 1 at calibration-set sizes (as for K = 10, [5, 5])
 #define TRY(SPT, MB, M2)                                                                                              \
   do {                                                                                                                \
     const int rc = launch_train_k<KK, 128, SPT, MB, M2>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, \
-                                                        smem_fwd, sms, max_smem, rows_out, st);                      \
+                                                        smem_fwd, sms, max_smem, rows_out, gz_ext, gld_ext, st);     \
     if (rc != CNF_E_SMEM) return rc;                                                                                  \
   } while (0)
   if (d.m == 2) {
@@ -66,8 +66,8 @@ int train_k(const CnfDims& d, const float* packed, const int32_t* tables, const 
 
 int cnf_fp32rk_train(const CnfDims& d, const float* packed, const int32_t* tables, const float* x, const int64_t* y,
                      float* partials, double* loss_acc, int64_t N, float eps, float gamma, float inv_n, size_t smem_fwd,
-                     int sms, int max_smem, int64_t* rows_out, cudaStream_t st) {
-#define K_CASE(KK) case KK: return train_k<KK>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_fwd, sms, max_smem, rows_out, st)
+                     int sms, int max_smem, int64_t* rows_out, const float* gz_ext, const float* gld_ext, cudaStream_t st) {
+#define K_CASE(KK) case KK: return train_k<KK>(d, packed, tables, x, y, partials, loss_acc, N, eps, gamma, inv_n, smem_fwd, sms, max_smem, rows_out, gz_ext, gld_ext, st)
   switch (d.K) {
     K_CASE(2); K_CASE(3); K_CASE(4); K_CASE(5); K_CASE(6); K_CASE(7); K_CASE(8); K_CASE(9);
     default: break;

@@ -390,7 +390,8 @@ template <int R_NT, int SPT, int U, int MINB, bool M2 = false, int KK = RK>
 __global__ void __launch_bounds__(R_NT, MINB)
 train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __restrict__ tables,
                    const float* __restrict__ xin, const int64_t* __restrict__ labels, float* __restrict__ partials,
-                   double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n) {
+                   double* __restrict__ loss_acc, int64_t N, float eps, float gamma, float inv_n,
+                   const float* __restrict__ gz_ext = nullptr, const float* __restrict__ gld_ext = nullptr) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[4][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -453,10 +454,26 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
       else       layer_eval<SPT, U, M2>(w, b2, Hp, 0, hi, lo, ld, nets);
     }
     // ---- loss head (calibrators.py:288-291; eps == 0: CrossEntropyLoss, run_experiment3D.py:107) ------------------
-    float glo[SPT][RD], ghi[SPT][RD];
+    // (gz_ext != nullptr: external head -- the upstream gradients dL/dz [N, K] and dL/dlog_det [N] come from the
+    //  caller, the autograd backward of the drop-in Flow, run_experiment3D.py:133-134; no loss is formed)
+    float glo[SPT][RD], ghi[SPT][RD], gld[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int64_t n = base + tid + k * R_NT;
+      if (gz_ext != nullptr) {
+        float gz[KK];
+#pragma unroll
+        for (int j = 0; j < KK; ++j) gz[j] = valid[k] ? __ldg(gz_ext + n * KK + j) : 0.f;
+        gld[k] = valid[k] ? __ldg(gld_ext + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < RD; ++j) {          // logical -> physical slot -> register position, as below
+          glo[k][j] = j < MP::D0 ? (rev_io ? gz[KK - 1 - j] : gz[j])
+                                 : ((MP::ODD && j == MP::D0) ? (rev_io ? gz[KK - 1 - MP::D0] : gz[MP::D0]) : 0.f);
+          ghi[k][j] = j < MP::D0 ? (rev_io ? gz[KK - 1 - (MP::D1 + j)] : gz[MP::D1 + j]) : 0.f;
+        }
+        continue;
+      }
+      gld[k] = valid[k] ? -gamma * inv_n : 0.f;
       float av[KK];     // by physical slot
 #pragma unroll
       for (int p = 0; p < KK; ++p) av[p] = p < MP::D1 ? lo[k][p < MP::D0 ? p : MP::D0] : hi[k][p - MP::D1];
@@ -563,7 +580,7 @@ train_reg10_kernel(CnfDims d, const float* __restrict__ packed, const int* __res
 #pragma unroll
           for (int q = 0; q < RD; ++q) {
             const float gy = gt[k][q];
-            gs[k][q] = fmaf(gy, t[k][q], valid[k] ? -gamma * inv_n : 0.f);   // g_s = g_y x e^s + g_ld
+            gs[k][q] = fmaf(gy, t[k][q], gld[k]);                            // g_s = g_y x e^s + g_ld
             t[k][q] *= expf(-o[k][q]);                                   // x
             o[k][q] = gy * expf(o[k][q]);                                // g_x of the transformed half
           }

@@ -1025,3 +1025,50 @@ def test_fit_loop_enqueued_from_c_is_bitwise_the_stepwise_loop(K, L, hidden, sca
     # a second call continues the same optimiser (bias correction from step 26 on)
     h2 = tr.fit_loop(3, N, None)
     assert np.isfinite(h2.cpu().numpy()).all() and flow.engine().adam_t == epochs + 3
+
+
+@pytest.mark.parametrize('K,L,hidden,scale,shift', [(3, 10, [5, 5], True, True), (3, 5, [3, 3], False, True), (10, 6, [5, 5], True, True),
+                                                    (7, 4, [4, 9], True, True)])
+def test_autograd_backward_on_the_register_kernel_vs_oracle(K, L, hidden, scale, shift, cuda_device):
+    """The script loop (run_experiment3D.py:98-135: loss = CE(zs[-1], y) - det * mean(log_det); loss.backward()) through
+    the drop-in Flow at the script's own shapes: the autograd backward (external head: upstream dL/dz, dL/dlog_det) runs
+    on the register-resident kernel when the input needs no gradient.  Parameter gradients against the float64 oracle
+    and against the tile kernel (CNF_FP32R_TRAIN=off)."""
+    import os
+    import torch
+    import cnf_b200
+    N = 1500
+    torch.manual_seed(K + L)
+    flow = cnf_b200.Flow([cnf_b200.NvpCouplingLayer(K, hidden, scale=scale, shift=shift) for _ in range(L)])
+    with torch.no_grad():
+        for p in flow.parameters():
+            if p.requires_grad:
+                p.mul_(250.0)
+    flat = np.concatenate([p.detach().numpy().reshape(-1) for lay in flow.layers for p in lay.canonical_parameters()])
+    params = orc.unflatten(flat.astype(np.float64), orc.init_params(K, L, hidden, scale, shift))
+    flow.to(cuda_device)
+    x, y = orc.synth_logits(N, K, seed=11)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+
+    def grads_now():
+        for p in flow.parameters():
+            p.grad = None
+        zs, ld = flow(xt)
+        loss = torch.nn.functional.cross_entropy(zs[-1], yt) - ld.mean()
+        loss.backward()
+        return float(loss), np.concatenate([p.grad.detach().cpu().numpy().reshape(-1) for lay in flow.layers
+                                            for p in lay.canonical_parameters()])
+    loss, g = grads_now()
+    lo, _, _, gro, _ = orc.train_step_grads(params, x.astype(np.float64), y, eps=0.0, gamma=1.0)
+    ref = orc.flatten(gro)
+    assert abs(loss - lo) < 1e-5 * max(1.0, abs(lo))
+    assert rel_err(g, ref) < 2e-4, rel_err(g, ref)
+    assert np.all(g[ref == 0] == 0)
+    os.environ['CNF_LIVE_ENV'] = '1'
+    os.environ['CNF_FP32R_TRAIN'] = 'off'
+    try:
+        _, g_tile = grads_now()
+    finally:
+        os.environ.pop('CNF_FP32R_TRAIN', None)
+        os.environ.pop('CNF_LIVE_ENV', None)
+    assert rel_err(g_tile, g) < 2e-4
